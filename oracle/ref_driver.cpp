@@ -1,0 +1,462 @@
+// TEST INFRASTRUCTURE ONLY (never linked into the product): a headless driver around the UNMODIFIED
+// reference sources in /root/reference/include, built into oracle/_ref/gi_ref by oracle/Makefile.
+// It calls the reference's own public entry points (loadScene, Octree::rebuild, RayTracer::trace /
+// visible / samplePhotons / radiance / tracePhotons / run, PhotonMap::rebuild / getInRange,
+// Halton_sampler::sample, Halton_enum::get_index) and writes raw little-endian arrays that the
+// tests compare with oracle/gi_oracle.c (the restatement) and with the CUDA path.
+//
+// Knobs that are compile-time #defines in the reference (util.h:22-23 MIN_DEPTH / MAX_DEPTH) become
+// run-time variables here by re-defining the macros AFTER util.h was included (its include guard keeps
+// the later includes from re-defining them); no reference file is edited or copied.
+//
+// Determinism: time() is interposed (returns $GI_REF_TIME or 1234567) because drand() seeds a
+// thread_local xorshift64* with std::time(0) (util.h:52-80); with OMP_NUM_THREADS=1 the output is
+// reproducible run-to-run.
+#include <algorithm>
+#include <array>
+#include <chrono>
+#include <cmath>
+#include <cstdint>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <ctime>
+#include <iostream>
+#include <map>
+#include <memory>
+#include <random>
+#include <set>
+#include <sstream>
+#include <string>
+#include <unordered_map>
+#include <vector>
+#include <omp.h>
+
+#include <glm/glm.hpp>
+#include "util.h"
+#undef MAX_DEPTH
+#undef MIN_DEPTH
+int g_max_depth = 64;
+int g_min_depth = 2;
+#define MAX_DEPTH g_max_depth
+#define MIN_DEPTH g_min_depth
+#define private public
+#include "raytracer.h"
+#undef private
+#include "sceneLoader.h"
+#include "meshLoader.h"
+
+// ---- time() interposer -------------------------------------------------------------------------
+extern "C" time_t time(time_t* out)
+{
+    static time_t fixed = 0;
+    if (!fixed) {
+        const char* e = getenv("GI_REF_TIME");
+        fixed = e ? (time_t)atoll(e) : (time_t)1234567;
+    }
+    if (out) *out = fixed;
+    return fixed;
+}
+
+// ---- per-thread ray / query counters via ld --wrap (see oracle/Makefile) ------------------------
+// The three octree/photon-map entry points are each called exactly once per trace / visible /
+// samplePhotons (raytracer.h:389, :283, :538), so wrapping them counts rays and gather queries without
+// touching the reference sources.
+static thread_local unsigned long long t_ntrace = 0, t_nshadow = 0, t_ngather = 0;
+static unsigned long long g_ntrace = 0, g_nshadow = 0, g_ngather = 0;
+typedef std::vector<std::pair<const Octree::Node*, double>> SortedVec;
+extern "C++" {
+SortedVec real_intersectSorted(const Octree*, const Ray&, double, double) asm("__real__ZNK6Octree15intersectSortedERK3Raydd");
+SortedVec wrap_intersectSorted(const Octree*, const Ray&, double, double) asm("__wrap__ZNK6Octree15intersectSortedERK3Raydd");
+std::vector<Entity*> real_intersect(const Octree*, const Ray&, double, double) asm("__real__ZNK6Octree9intersectERK3Raydd");
+std::vector<Entity*> wrap_intersect(const Octree*, const Ray&, double, double) asm("__wrap__ZNK6Octree9intersectERK3Raydd");
+std::vector<Photon*> real_getInRange(const PhotonMap*, glm::dvec3&, double&, double) asm("__real__ZNK9PhotonMap10getInRangeERN3glm5tvec3IdLNS0_9precisionE0EEERdd");
+std::vector<Photon*> wrap_getInRange(const PhotonMap*, glm::dvec3&, double&, double) asm("__wrap__ZNK9PhotonMap10getInRangeERN3glm5tvec3IdLNS0_9precisionE0EEERdd");
+}
+SortedVec wrap_intersectSorted(const Octree* o, const Ray& r, double a, double b) { ++t_ntrace; return real_intersectSorted(o, r, a, b); }
+std::vector<Entity*> wrap_intersect(const Octree* o, const Ray& r, double a, double b) { ++t_nshadow; return real_intersect(o, r, a, b); }
+std::vector<Photon*> wrap_getInRange(const PhotonMap* m, glm::dvec3& p, double& s, double d) { ++t_ngather; return real_getInRange(m, p, s, d); }
+
+static void counters_reset() { g_ntrace = g_nshadow = g_ngather = 0; }
+static void counters_collect()
+{
+    // every OpenMP thread adds its thread-local tallies (and clears them)
+#pragma omp parallel
+    {
+#pragma omp critical(cnt)
+        {
+            g_ntrace += t_ntrace; g_nshadow += t_nshadow; g_ngather += t_ngather;
+            t_ntrace = t_nshadow = t_ngather = 0;
+        }
+    }
+}
+
+// ---- raw array writers ---------------------------------------------------------------------------
+static std::string g_out;
+template <typename T> static void dump(const std::string& name, const std::vector<T>& v)
+{
+    std::string p = g_out + "/" + name;
+    FILE* f = fopen(p.c_str(), "wb");
+    if (!f) { fprintf(stderr, "cannot write %s\n", p.c_str()); exit(2); }
+    if (!v.empty()) fwrite(v.data(), sizeof(T), v.size(), f);
+    fclose(f);
+}
+static void push3(std::vector<double>& v, const glm::dvec3& a) { v.push_back(a.x); v.push_back(a.y); v.push_back(a.z); }
+static void push2(std::vector<double>& v, const glm::dvec2& a) { v.push_back(a.x); v.push_back(a.y); }
+
+static std::unordered_map<const Entity*, uint32_t> g_eid;
+static std::vector<Entity*> g_ents;
+
+// ---- scene dump -----------------------------------------------------------------------------------
+static void walk_nodes(const Octree::Node* n, std::vector<double>& box, std::vector<uint8_t>& mask,
+                       std::vector<uint32_t>& cnt, std::vector<uint32_t>& refs)
+{
+    push3(box, n->_bbox.min); push3(box, n->_bbox.max);
+    uint8_t m = 0;
+    for (int i = 0; i < 8; i++) if (n->_children[i]) m |= (uint8_t)(1u << i);
+    mask.push_back(m);
+    cnt.push_back((uint32_t)n->_entities.size());
+    for (Entity* e : n->_entities) refs.push_back(g_eid.at(e));
+    for (int i = 0; i < 8; i++) if (n->_children[i]) walk_nodes(n->_children[i].get(), box, mask, cnt, refs);
+}
+
+static void dump_scene(Octree* scene, RayTracer& rt, std::ostringstream& meta)
+{
+    std::vector<uint8_t> type;
+    std::vector<double> tpos, tnrm, tuv, tfn, sph, cn, matv;
+    std::vector<uint32_t> difid, emid;
+    std::map<const texture*, uint32_t> texid;
+    std::vector<double> texcol;
+    auto tid = [&](texture* t) -> uint32_t {
+        auto it = texid.find(t);
+        if (it != texid.end()) return it->second;
+        uint32_t id = (uint32_t)texid.size();
+        texid[t] = id;
+        push3(texcol, t->color);
+        return id;
+    };
+    for (Entity* e : g_ents) {
+        matv.push_back(e->material.roughness); matv.push_back(e->material.opacity); matv.push_back(e->material.IOR);
+        difid.push_back(tid(e->material.diffuse)); emid.push_back(tid(e->material.emissive));
+        if (triangle* t = dynamic_cast<triangle*>(e)) {
+            type.push_back(0);
+            for (int k = 0; k < 3; k++) { push3(tpos, t->vertices[k].pos); push3(tnrm, t->vertices[k].norm); push2(tuv, t->vertices[k].texCoord); }
+            push3(tfn, t->norm);
+        } else if (sphere* s = dynamic_cast<sphere*>(e)) {
+            type.push_back(1);
+            for (int k = 0; k < 9; k++) { tpos.push_back(0); tnrm.push_back(0); }
+            for (int k = 0; k < 6; k++) tuv.push_back(0);
+            push3(tfn, glm::dvec3(0));
+            tpos[tpos.size() - 9] = s->pos.x; tpos[tpos.size() - 8] = s->pos.y; tpos[tpos.size() - 7] = s->pos.z; tpos[tpos.size() - 6] = s->rad;
+        } else if (cone* c = dynamic_cast<cone*>(e)) {
+            type.push_back(2);
+            for (int k = 0; k < 9; k++) { tpos.push_back(0); tnrm.push_back(0); }
+            for (int k = 0; k < 6; k++) tuv.push_back(0);
+            push3(tfn, glm::dvec3(0));
+            size_t b = tpos.size() - 9;
+            tpos[b] = c->pos.x; tpos[b + 1] = c->pos.y; tpos[b + 2] = c->pos.z; tpos[b + 3] = c->rad; tpos[b + 4] = c->height;
+            size_t nb = tnrm.size() - 9; // column-major 3x3 (glm storage order) of the inverse rotation
+            for (int col = 0; col < 3; col++) for (int row = 0; row < 3; row++) tnrm[nb + col * 3 + row] = c->rot[col][row];
+        } else {
+            type.push_back(255);
+            for (int k = 0; k < 9; k++) { tpos.push_back(0); tnrm.push_back(0); }
+            for (int k = 0; k < 6; k++) tuv.push_back(0);
+            push3(tfn, glm::dvec3(0));
+        }
+    }
+    dump("ent_type.u8", type); dump("ent_pos.f64", tpos); dump("ent_nrm.f64", tnrm); dump("ent_uv.f64", tuv);
+    dump("ent_fnorm.f64", tfn); dump("ent_mat.f64", matv); dump("ent_diftex.u32", difid); dump("ent_emtex.u32", emid);
+    dump("tex_color.f64", texcol);
+
+    std::vector<double> box; std::vector<uint8_t> mask; std::vector<uint32_t> cnt, refs;
+    walk_nodes(&scene->_root, box, mask, cnt, refs);
+    dump("node_box.f64", box); dump("node_mask.u8", mask); dump("node_cnt.u32", cnt); dump("node_refs.u32", refs);
+
+    std::vector<double> lights;
+    for (Light* l : scene->lights) { push3(lights, l->pos); push3(lights, l->col); lights.push_back(l->rad); push3(lights, l->dir); lights.push_back(l->angle); }
+    dump("lights.f64", lights);
+    std::vector<double> cam;
+    push3(cam, rt._camera.pos); push3(cam, rt._camera.forward); push3(cam, rt._camera.up); push3(cam, rt._camera.right);
+    cam.push_back(rt._camera.sensorDiag); cam.push_back(rt._camera.focalDist);
+    dump("camera.f64", cam);
+    std::vector<double> knobs = { (double)rt.photons, (double)rt.photon_depth, (double)rt.min_samples, (double)rt.max_samples,
+                                  rt.noise_thresh, rt.ambient.x, rt.ambient.y, rt.ambient.z };
+    dump("knobs.f64", knobs);
+    meta << "entities=" << g_ents.size() << "\nnodes=" << mask.size() << "\nleaf_refs=" << refs.size() << "\nlights=" << scene->lights.size() << "\n";
+}
+
+// ---- Halton known-answer tables ---------------------------------------------------------------------
+static void dump_halton(int w, int h)
+{
+    Halton_sampler sampler; sampler.init_faure();
+    // sample(d, i) for all 256 dims over a spread of indices (small, large, powers, wrap-around values)
+    std::vector<uint32_t> idx;
+    for (uint32_t i = 0; i < 512; i++) idx.push_back(i);
+    uint32_t x = 0x9E3779B9u;
+    for (int i = 0; i < 1024; i++) { x ^= x << 13; x ^= x >> 17; x ^= x << 5; idx.push_back(x); }
+    for (int b = 0; b < 32; b++) { idx.push_back(1u << b); idx.push_back((1u << b) - 1u); }
+    idx.push_back(0xFFFFFFFFu); idx.push_back(3486784401u); idx.push_back(3486784400u); idx.push_back(4243659659u);
+    std::vector<float> val;
+    for (unsigned d = 0; d < 256; d++) for (uint32_t i : idx) val.push_back(sampler.sample(d, i));
+    dump("halton_idx.u32", idx); dump("halton_val.f32", val);
+    // get_index at the five BASELINE resolutions plus the requested one; s includes values past the u32 wrap
+    const int res[6][2] = { { 512, 512 }, { 1024, 1024 }, { 1920, 1080 }, { 3840, 2160 }, { 64, 64 }, { w, h } };
+    std::vector<uint32_t> q, out;
+    std::vector<float> sc;
+    for (int r = 0; r < 6; r++) {
+        Halton_enum he(res[r][0], res[r][1]);
+        uint32_t z = 0x1234567u + r;
+        for (int k = 0; k < 512; k++) {
+            z ^= z << 13; z ^= z >> 17; z ^= z << 5;
+            uint32_t px = z % res[r][0], py = (z >> 12) % res[r][1], s = (k < 256) ? (uint32_t)k : (z >> 22);
+            uint32_t id = he.get_index(s, px, py);
+            q.push_back(res[r][0]); q.push_back(res[r][1]); q.push_back(s); q.push_back(px); q.push_back(py);
+            out.push_back(id);
+            sc.push_back(he.scale_x(sampler.sample(0, id))); sc.push_back(he.scale_y(sampler.sample(1, id)));
+        }
+    }
+    dump("henum_query.u32", q); dump("henum_index.u32", out); dump("henum_scaled.f32", sc);
+}
+
+// ---- camera rays exactly as RayTracer::run builds them (raytracer.h:74-78,112-129) -------------------
+struct Frame {
+    double halfW, halfH; glm::dvec3 center, right;
+    Frame(const Camera& c, int w, int h) {
+        halfW = (c.sensorDiag * w) / (sqrt((double)w * w + h * h));
+        halfH = halfW * ((double)h / w);
+        center = c.pos + c.focalDist * c.forward;
+        right = glm::normalize(glm::cross(c.forward, c.up));
+    }
+};
+static Ray camera_ray(const RayTracer& rt, const Frame& fr, const Halton_sampler& sampler, const Halton_enum& he, int w, int h, int x, int y, int s, int& idx_out)
+{
+    int idx = he.get_index(s, x, y);
+    double xr = sampler.sample(0, idx);
+    double yr = sampler.sample(1, idx);
+    double dx = he.scale_x(xr);
+    double dy = he.scale_y(yr);
+    glm::dvec3 pixelPos = fr.center + (fr.halfW * (dx / w - .5)) * fr.right - (fr.halfH * (dy / h - .5)) * rt._camera.up;
+    glm::dvec3 eyePos = rt._camera.pos + FOCAL_BLUR * (xr - .5) * fr.right + FOCAL_BLUR * (yr - .5) * rt._camera.up;
+    idx_out = idx;
+    return Ray(eyePos, glm::normalize(pixelPos - eyePos));
+}
+
+int main(int argc, char** argv)
+{
+    if (argc < 3) {
+        fprintf(stderr, "usage: gi_ref <scene.scn> <outdir> [--w W --h H --s0 A --s1 B --max-depth D --min-depth M --photons P --samples N --x0 --y0 --x1 --y1 --repeat R] cmd...\n"
+                        "cmds: scene halton primary shadow photons gather radiance run time-frame time-gather\n");
+        return 1;
+    }
+    const char* scn = argv[1];
+    g_out = argv[2];
+    int w = 64, h = 64, s0 = 0, s1 = 1, photons_override = -1, samples = -1, x0 = 0, y0 = 0, x1 = -1, y1 = -1, repeat = 1;
+    std::vector<std::string> cmds;
+    for (int i = 3; i < argc; i++) {
+        std::string a = argv[i];
+        auto next = [&]() { return atoi(argv[++i]); };
+        if (a == "--w") w = next(); else if (a == "--h") h = next(); else if (a == "--s0") s0 = next(); else if (a == "--s1") s1 = next();
+        else if (a == "--max-depth") g_max_depth = next(); else if (a == "--min-depth") g_min_depth = next();
+        else if (a == "--photons") photons_override = next(); else if (a == "--samples") samples = next();
+        else if (a == "--x0") x0 = next(); else if (a == "--y0") y0 = next(); else if (a == "--x1") x1 = next(); else if (a == "--y1") y1 = next();
+        else if (a == "--repeat") repeat = next();
+        else cmds.push_back(a);
+    }
+    if (x1 < 0) x1 = w;
+    if (y1 < 0) y1 = h;
+    auto has = [&](const char* c) { return std::find(cmds.begin(), cmds.end(), std::string(c)) != cmds.end(); };
+    std::ostringstream meta;
+    meta << "threads=" << omp_get_max_threads() << "\nw=" << w << "\nh=" << h << "\nmax_depth=" << g_max_depth << "\nmin_depth=" << g_min_depth << "\n";
+
+    srand(std::time(0));
+    Camera camera({ 10, 5, 0 }, { 0, 0, 0 });     // main.cpp:30
+    RayTracer rt(camera);                           // main.cpp:32
+    Octree* scene = new Octree();                   // main.cpp:36
+    loadScene(scene, rt, scn);                      // main.cpp:38
+    if (photons_override >= 0) rt.photons = photons_override;
+    if (samples > 0) { rt.min_samples = samples; rt.max_samples = samples; }
+    g_ents = scene->_root._entities;                // insertion order = primitive id (root list is cleared by partition)
+    for (uint32_t i = 0; i < g_ents.size(); i++) g_eid[g_ents[i]] = i;
+    rt.setScene(scene);                             // main.cpp:41
+    rt.start();
+    auto tb0 = std::chrono::high_resolution_clock::now();
+    if (!g_ents.empty()) scene->rebuild(); else scene->valid = true;
+    auto tb1 = std::chrono::high_resolution_clock::now();
+    meta << "octree_build_s=" << std::chrono::duration<double>(tb1 - tb0).count() << "\n";
+
+    Halton_sampler sampler; sampler.init_faure();
+    Halton_enum he(w, h);
+    Frame fr(rt._camera, w, h);
+
+    if (has("scene")) dump_scene(scene, rt, meta);
+    if (has("halton")) dump_halton(w, h);
+
+    // -- primary rays + closest hit ------------------------------------------------------------------
+    std::vector<double> hit_pos, hit_nrm, hit_uv, ray_o, ray_d;
+    std::vector<uint32_t> hit_id, ray_idx;
+    if (has("primary") || has("shadow") || has("gather")) {
+        for (int s = s0; s < s1; s++) for (int y = y0; y < y1; y++) for (int x = x0; x < x1; x++) {
+            int idx; Ray ray = camera_ray(rt, fr, sampler, he, w, h, x, y, s, idx);
+            glm::dvec3 p(0), n(0); glm::dvec2 uv(0); Entity* cur = nullptr;
+            bool ok = rt.trace(ray, p, n, uv, cur);
+            push3(ray_o, ray.origin); push3(ray_d, ray.dir); ray_idx.push_back((uint32_t)idx);
+            hit_id.push_back(ok ? g_eid.at(cur) : 0xFFFFFFFFu);
+            if (!ok) { p = glm::dvec3(0); n = glm::dvec3(0); uv = glm::dvec2(0); }
+            push3(hit_pos, p); push3(hit_nrm, n); push2(hit_uv, uv);
+        }
+        if (has("primary")) {
+            dump("ray_o.f64", ray_o); dump("ray_d.f64", ray_d); dump("ray_idx.u32", ray_idx);
+            dump("hit_id.u32", hit_id); dump("hit_pos.f64", hit_pos); dump("hit_nrm.f64", hit_nrm); dump("hit_uv.f64", hit_uv);
+        }
+        meta << "primary_rays=" << hit_id.size() << "\n";
+    }
+
+    // -- shadow rays from the primary hits toward Halton-chosen light points ------------------------
+    if (has("shadow")) {
+        std::vector<double> so, sd, smt; std::vector<uint8_t> vis;
+        for (size_t i = 0; i < hit_id.size(); i++) {
+            if (hit_id[i] == 0xFFFFFFFFu) continue;
+            glm::dvec3 p(hit_pos[3 * i], hit_pos[3 * i + 1], hit_pos[3 * i + 2]), n(hit_nrm[3 * i], hit_nrm[3 * i + 1], hit_nrm[3 * i + 2]);
+            glm::dvec3 rd(ray_d[3 * i], ray_d[3 * i + 1], ray_d[3 * i + 2]);
+            if (glm::dot(n, rd) > 0) n *= -1.0;                                   // raytracer.h:325-329
+            for (Light* light : scene->lights) {
+                double u = sampler.sample(2, ray_idx[i]), v = sampler.sample(3, ray_idx[i]);
+                glm::dvec3 lightDir = light->getPoint(u, v) - (p + SHADOW_BIAS * n);   // raytracer.h:233
+                double maxt = vecLengthSquared(lightDir);
+                Ray sr(p + SHADOW_BIAS * n, lightDir);                              // raytracer.h:241
+                bool v_ = rt.visible(sr, maxt);
+                push3(so, sr.origin); push3(sd, lightDir); smt.push_back(maxt); vis.push_back(v_ ? 1 : 0);
+            }
+        }
+        dump("sh_o.f64", so); dump("sh_d.f64", sd); dump("sh_maxt2.f64", smt); dump("sh_vis.u8", vis);
+        meta << "shadow_rays=" << vis.size() << "\n";
+    }
+
+    // -- photons ----------------------------------------------------------------------------------------
+    double photon_s = 0;
+    if (has("photons") || has("gather") || has("run") || has("time-frame") || has("time-gather") || has("radiance")) {
+        counters_collect(); counters_reset();
+        auto t0 = std::chrono::high_resolution_clock::now();
+        rt.tracePhotons(5, rt.photons, sampler, he);                                 // raytracer.h:65
+        auto t1 = std::chrono::high_resolution_clock::now();
+        counters_collect();
+        meta << "photon_traces=" << g_ntrace << "\n";
+        std::vector<Photon*> ph = rt._photon_map->_root._entities;                   // order before partition clears it
+        std::unordered_map<const Photon*, uint32_t> pid;
+        std::vector<double> pv;
+        for (uint32_t i = 0; i < ph.size(); i++) { pid[ph[i]] = i; push3(pv, ph[i]->origin); push3(pv, ph[i]->dir); push3(pv, ph[i]->col); }
+        auto t2 = std::chrono::high_resolution_clock::now();
+        rt._photon_map->rebuild();                                                    // raytracer.h:70
+        auto t3 = std::chrono::high_resolution_clock::now();
+        photon_s = std::chrono::duration<double>(t1 - t0).count();
+        meta << "photons_stored=" << ph.size() << "\nphoton_trace_s=" << photon_s << "\nphoton_build_s=" << std::chrono::duration<double>(t3 - t2).count() << "\n";
+        if (has("photons")) {
+            dump("photons.f64", pv);
+            // photon-map structure, DFS preorder: box, leaf flag, photon ids
+            std::vector<double> box; std::vector<uint8_t> leaf; std::vector<uint32_t> cnt, refs;
+            std::vector<const PhotonMap::Node*> st = { &rt._photon_map->_root };
+            while (!st.empty()) {
+                const PhotonMap::Node* n = st.back(); st.pop_back();
+                push3(box, n->_bbox.min); push3(box, n->_bbox.max);
+                leaf.push_back(n->is_leaf() ? 1 : 0);
+                cnt.push_back((uint32_t)n->_entities.size());
+                for (Photon* p : n->_entities) refs.push_back(pid.at(p));
+                if (!n->is_leaf()) for (int i = 7; i >= 0; i--) st.push_back(n->_children[i].get());
+            }
+            dump("pm_box.f64", box); dump("pm_leaf.u8", leaf); dump("pm_cnt.u32", cnt); dump("pm_refs.u32", refs);
+            meta << "pm_nodes=" << leaf.size() << "\n";
+        }
+        // -- gather on primary-hit queries ----------------------------------------------------------------
+        if (has("gather") || has("time-gather")) {
+            std::vector<double> qpos, qdir;
+            for (size_t i = 0; i < hit_id.size(); i++) {
+                if (hit_id[i] == 0xFFFFFFFFu) continue;
+                glm::dvec3 p(hit_pos[3 * i], hit_pos[3 * i + 1], hit_pos[3 * i + 2]), n(hit_nrm[3 * i], hit_nrm[3 * i + 1], hit_nrm[3 * i + 2]);
+                glm::dvec3 rd(ray_d[3 * i], ray_d[3 * i + 1], ray_d[3 * i + 2]);
+                if (glm::dot(n, rd) > 0) n *= -1.0;
+                glm::dvec3 dir = glm::reflect(rd, n);
+                push3(qpos, p); push3(qdir, dir);
+            }
+            size_t nq = qpos.size() / 3;
+            if (has("gather")) {
+                std::vector<double> est; std::vector<uint32_t> cand_off = { 0 }, cand, knn;
+                for (size_t i = 0; i < nq; i++) {
+                    glm::dvec3 p(qpos[3 * i], qpos[3 * i + 1], qpos[3 * i + 2]), d(qdir[3 * i], qdir[3 * i + 1], qdir[3 * i + 2]);
+                    double scale = 0;
+                    std::vector<Photon*> c = rt._photon_map->getInRange(p, scale, 0);   // raytracer.h:538
+                    for (Photon* q : c) cand.push_back(pid.at(q));
+                    cand_off.push_back((uint32_t)cand.size());
+                    int count = std::min(32, (int)c.size());
+                    std::partial_sort(c.begin(), c.begin() + count, c.end(), [p](const Photon* l, const Photon* r) { return vecLengthSquared(l->origin - p) < vecLengthSquared(r->origin - p); });
+                    for (int k = 0; k < 32; k++) knn.push_back(k < count ? pid.at(c[k]) : 0xFFFFFFFFu);
+                    push3(est, rt.samplePhotons(p, d, 32));                                  // raytracer.h:532
+                }
+                dump("q_pos.f64", qpos); dump("q_dir.f64", qdir); dump("q_est.f64", est);
+                dump("q_cand_off.u32", cand_off); dump("q_cand.u32", cand); dump("q_knn.u32", knn);
+                meta << "gather_queries=" << nq << "\n";
+            }
+            if (has("time-gather")) {
+                double best = 1e30;
+                for (int r = 0; r < repeat; r++) {
+                    auto g0 = std::chrono::high_resolution_clock::now();
+                    double acc = 0;
+#pragma omp parallel for schedule(dynamic, 256) reduction(+ : acc)
+                    for (long i = 0; i < (long)nq; i++) {
+                        glm::dvec3 p(qpos[3 * i], qpos[3 * i + 1], qpos[3 * i + 2]), d(qdir[3 * i], qdir[3 * i + 1], qdir[3 * i + 2]);
+                        acc += rt.samplePhotons(p, d, 32).x;
+                    }
+                    auto g1 = std::chrono::high_resolution_clock::now();
+                    best = std::min(best, std::chrono::duration<double>(g1 - g0).count());
+                    if (acc == 12345.678) printf("!");
+                }
+                meta << "time_gather_queries=" << nq << "\ntime_gather_s=" << best << "\n";
+            }
+        }
+    }
+
+    // -- fp64 radiance per pixel: the row loop of run() restated around the reference's radiance() ------
+    if (has("radiance")) {
+        int ns = rt.max_samples;
+        std::vector<double> img((size_t)(y1 - y0) * (x1 - x0) * 3);
+#pragma omp parallel for schedule(dynamic, 4)
+        for (int y = y0; y < y1; ++y) for (int x = x0; x < x1; ++x) {
+            glm::dvec3 color(0.5, 0.5, 0.5);
+            for (int s = 0; s < ns; s++) {
+                int idx; Ray ray = camera_ray(rt, fr, sampler, he, w, h, x, y, s, idx);
+                glm::dvec3 L = rt.radiance(ray, 0, sampler, he, idx, glm::dvec3(1, 1, 1));
+                color = (s == 0) ? L : (1.0 * s * color + L) * (1.0 / (s + 1));      // raytracer.h:131-134
+            }
+            size_t o = ((size_t)(y - y0) * (x1 - x0) + (x - x0)) * 3;
+            img[o] = color.x; img[o + 1] = color.y; img[o + 2] = color.z;
+        }
+        dump("radiance.f64", img);
+        meta << "radiance_spp=" << ns << "\n";
+    }
+
+    // -- the reference's own frame loop, timed (second call semantics: photon map already valid) -------
+    if (has("run") || has("time-frame")) {
+        double best = 1e30;
+        for (int r = 0; r < repeat; r++) {
+            counters_collect(); counters_reset();
+            auto f0 = std::chrono::high_resolution_clock::now();
+            rt.run(w, h);
+            auto f1 = std::chrono::high_resolution_clock::now();
+            counters_collect();
+            best = std::min(best, std::chrono::duration<double>(f1 - f0).count());
+        }
+        meta << "frame_s=" << best << "\nframe_trace_rays=" << g_ntrace << "\nframe_shadow_rays=" << g_nshadow << "\nframe_gathers=" << g_ngather << "\n";
+        std::vector<uint8_t> rgb((size_t)w * h * 3);
+        std::shared_ptr<Image> im = rt.getImage();
+        for (int y = 0; y < h; y++) for (int x = 0; x < w; x++) {
+            QRgb p = im->_image.pixel(x, y);
+            rgb[((size_t)y * w + x) * 3] = (uint8_t)qRed(p); rgb[((size_t)y * w + x) * 3 + 1] = (uint8_t)qGreen(p); rgb[((size_t)y * w + x) * 3 + 2] = (uint8_t)qBlue(p);
+        }
+        dump("image.u8", rgb);
+    }
+
+    std::string mp = g_out + "/meta.txt";
+    FILE* mf = fopen(mp.c_str(), "w");
+    fputs(meta.str().c_str(), mf);
+    fclose(mf);
+    return 0;
+}
