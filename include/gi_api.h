@@ -1,0 +1,222 @@
+/* gi_api.h — the C ABI of libgi_b200.so: the B200-native rendering hot path behind GI_Raytracer's
+ * C++ scene API.
+ *
+ * The reference (moepforfreedom/GI_Raytracer) has no FFI layer; its hot path is reached through C++ member
+ * functions.  Each entry point below replaces one of them (reference file:line given per function) and is what
+ * a maintainer binds from the preserved C++ classes (see INTEGRATION.md for the stubs).
+ *
+ * Conventions
+ *   - plain C: pointers and sizes only; every function returns 0 (GI_OK) or a negative GI_ERR_* code and
+ *     gi_last_error(ctx) returns the text of the last failure;
+ *   - the caller owns every host buffer, the library owns every device buffer;
+ *   - "host" entry points take host pointers and copy (pinned staging) to/from the device; the "_dev" twins take
+ *     device pointers (e.g. torch tensors' data_ptr) and run on the context's stream without copies;
+ *   - one gi_ctx per device; a ctx is not thread-safe, different ctxs are independent;
+ *   - there is NO CPU fallback: without a usable CUDA device gi_create fails with GI_ERR_NO_DEVICE.
+ *
+ * Geometry, rays, hits and photons are fp64, exactly like the reference (glm::dvec3); Halton samples are fp32,
+ * like Halton_sampler::sample.  Device code on the parity path is compiled with -fmad=false and follows the
+ * reference's operation order, so primitive ids, hit points and photon index sets are bit-exact.
+ */
+#ifndef GI_API_H
+#define GI_API_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GI_OK 0
+#define GI_ERR_INVALID (-1)     /* bad argument / bad scene description            */
+#define GI_ERR_NO_DEVICE (-2)   /* no CUDA device, or the device is not sm_100     */
+#define GI_ERR_CUDA (-3)        /* a CUDA runtime call or kernel failed            */
+#define GI_ERR_NO_SCENE (-4)    /* call needs gi_scene_upload first                */
+#define GI_ERR_NO_PHOTONS (-5)  /* call needs a built photon map                   */
+#define GI_ERR_OOM (-6)
+
+#define GI_NO_HIT 0xFFFFFFFFu
+
+/* primitive kinds (entities.h:51 sphere, :144 cone, :329 triangle; box/quad/sphere/cone *meshes* are triangles) */
+#define GI_PRIM_TRIANGLE 0
+#define GI_PRIM_SPHERE 1
+#define GI_PRIM_CONE 2
+
+/* texture kinds (material.h:11 texture, :32 checkerboard, :51 imageTexture) */
+#define GI_TEX_CONST 0
+#define GI_TEX_CHECKER 1
+#define GI_TEX_IMAGE 2
+
+typedef struct gi_ctx gi_ctx;
+
+typedef struct gi_texture {
+    int32_t kind;          /* GI_TEX_*                                                              */
+    int32_t tiles;         /* checkerboard tile count (material.h:35)                               */
+    double a[3];           /* const colour, or checker colour a                                     */
+    double b[3];           /* checker colour b                                                      */
+    double tile_u, tile_v; /* imageTexture::tile (material.h:55)                                    */
+    int32_t width, height; /* image size                                                            */
+    int32_t has_alpha;     /* QImage::hasAlphaChannel()                                             */
+    int32_t _pad;
+    uint64_t pixel_offset; /* byte offset of this image's RGBA8 rows (top row first) in tex_pixels  */
+} gi_texture;
+
+typedef struct gi_material { /* material.h:84-100 */
+    uint32_t diffuse_tex, emissive_tex;
+    double roughness, opacity, ior;
+} gi_material;
+
+typedef struct gi_light { /* light.h:10-58; dir/angle are the caustic cone written by Octree::rebuild (octree.cpp:79-102) */
+    double pos[3], col[3], rad, dir[3], angle;
+} gi_light;
+
+typedef struct gi_camera { /* camera.h:7-31 */
+    double pos[3], forward[3], up[3], right[3], sensor_diag, focal_dist;
+} gi_camera;
+
+/* The scene octree flattened on the host (build stays on the host, only its output is uploaded).
+ * Nodes are stored breadth-first; the existing children of a node are contiguous, in the reference's child
+ * order 0..7 (octree.cpp:321-328), starting at node_child[n].  A node with child mask 0 is a leaf
+ * (Octree::Node::is_leaf, octree.cpp:386-393) and owns leaf_prims[node_prim_off[n] .. +node_prim_cnt[n]) in the
+ * reference's per-leaf entity order.  Primitive id = insertion index into Octree::_root._entities. */
+typedef struct gi_scene_desc {
+    uint32_t n_nodes;
+    const double* node_box;         /* [n_nodes][6]  min.xyz, max.xyz                                  */
+    const uint32_t* node_child;     /* [n_nodes]     index of the first existing child                 */
+    const uint8_t* node_mask;       /* [n_nodes]     bit i set = child i exists                        */
+    const uint32_t* node_prim_off;  /* [n_nodes]                                                        */
+    const uint32_t* node_prim_cnt;  /* [n_nodes]                                                        */
+    uint32_t n_refs;
+    const uint32_t* leaf_prims;     /* [n_refs]                                                         */
+
+    uint32_t n_prims;
+    const uint8_t* prim_type;       /* [n_prims] GI_PRIM_*                                              */
+    const double* prim_geom;        /* [n_prims][9]  tri: v0,v1,v2 | sphere: c.xyz,r | cone: pos.xyz,rad,height */
+    const double* prim_nrm;         /* [n_prims][9]  tri: vertex normals | cone: inverse rotation, column-major   */
+    const double* prim_uv;          /* [n_prims][6]  tri: vertex uvs                                    */
+    const double* prim_fnorm;       /* [n_prims][3]  tri: face normal (entities.h:339)                  */
+    const uint32_t* prim_mat;       /* [n_prims]                                                        */
+
+    uint32_t n_mats;
+    const gi_material* mats;
+    uint32_t n_tex;
+    const gi_texture* tex;
+    uint64_t tex_pixel_bytes;
+    const uint8_t* tex_pixels;
+
+    uint32_t n_lights;
+    const gi_light* lights;
+    gi_camera camera;
+    double ambient[3];              /* RayTracer::ambient (raytracer.h:726)                             */
+} gi_scene_desc;
+
+/* Run-time replacements for the reference's compile-time knobs (util.h:14-31) and RayTracer members. */
+typedef struct gi_render_params {
+    int32_t width, height;          /* frame size given to RayTracer::run(w,h)                          */
+    int32_t max_depth;              /* MAX_DEPTH 64  (util.h:23)                                        */
+    int32_t min_depth;              /* MIN_DEPTH 2   (util.h:22)                                        */
+    int32_t spp;                    /* fixed samples per pixel: `samples N N t` (raytracer.h:108)       */
+    int32_t k_photons;              /* 32 (raytracer.h:258)                                             */
+    int32_t caustic_max_depth;      /* 10 (raytracer.h:258)                                             */
+    int32_t _pad;
+    uint64_t seed;                  /* counter-based PRNG seed (replaces the time-seeded xorshift)      */
+} gi_render_params;
+
+/* per-phase counters filled by gi_render_tile / gi_photon_trace (device-side tallies) */
+typedef struct gi_stats {
+    uint64_t closest_rays;          /* trace() calls        (raytracer.h:389)                           */
+    uint64_t shadow_rays;           /* visible() calls      (raytracer.h:283)                           */
+    uint64_t gathers;               /* samplePhotons() calls(raytracer.h:538)                           */
+    uint64_t photon_tries;          /* emission tries       (raytracer.h:602)                           */
+    uint64_t photons_stored;
+    uint64_t kernel_launches;       /* kernels launched by the call                                     */
+    double trace_ms, shadow_ms, gather_ms, shade_ms, total_ms; /* CUDA-event times of the phases        */
+} gi_stats;
+
+/* ---- lifetime ------------------------------------------------------------------------------------------ */
+int gi_create(int device, gi_ctx** out);
+void gi_destroy(gi_ctx* ctx);
+const char* gi_last_error(const gi_ctx* ctx);
+const char* gi_version(void);
+/* the CUDA stream all work of this ctx is enqueued on (a cudaStream_t), for callers that time with events */
+void* gi_stream(gi_ctx* ctx);
+int gi_synchronize(gi_ctx* ctx);
+
+/* ---- scene: replaces Octree::push_back/rebuild as the producer of traversal data (octree.cpp:25-119,316-384):
+ *      the host builds the reference octree and hands it over flattened ----------------------------------- */
+int gi_scene_upload(gi_ctx* ctx, const gi_scene_desc* scene);
+
+/* ---- Halton (halton_sampler.h:626-888 sample, halton_enum.h:106-114 get_index) -------------------------- */
+int gi_halton_sample(gi_ctx* ctx, size_t n, const uint32_t* dim, const uint32_t* index, float* out);
+int gi_halton_index(gi_ctx* ctx, int width, int height, size_t n, const uint32_t* s, const uint32_t* x, const uint32_t* y,
+                    uint32_t* out_index);
+
+/* ---- camera rays: RayTracer::run lines 74-78 + 112-129.  One ray per (pixel, sample): pixels of the rectangle
+ *      [x0,x1) x [y0,y1), row-major, for each sample s in [s0,s1) (sample-major).  org/dir are [n][3] fp64 (dir as
+ *      stored in Ray::dir), index is the Halton index of the sample. ---------------------------------------- */
+int gi_camera_rays(gi_ctx* ctx, int width, int height, int x0, int y0, int x1, int y1, int s0, int s1,
+                   double* org, double* dir, uint32_t* index);
+
+/* ---- closest hit: RayTracer::trace (raytracer.h:382-478) over Octree::intersectSorted (octree.cpp:188-211,
+ *      285-313).  org/dir are Ray::origin / Ray::dir as the reference's Ray holds them (ray.h:7-17: dir already
+ *      normalised by the constructor; invDir = 1/dir is derived on the device).
+ *      Outputs (any may be NULL): prim id or GI_NO_HIT, hit point, un-normalised shading normal, uv.
+ *      `alpha_seed`: stream seed for the stochastic alpha cut-out (raytracer.h:455); irrelevant for opaque scenes. */
+int gi_trace_closest(gi_ctx* ctx, size_t n, const double* org, const double* dir, uint64_t alpha_seed,
+                     uint32_t* prim, double* hit, double* normal, double* uv);
+int gi_trace_closest_dev(gi_ctx* ctx, size_t n, const double* org, const double* dir, uint64_t alpha_seed,
+                         uint32_t* prim, double* hit, double* normal, double* uv);
+
+/* ---- any hit: RayTracer::visible (raytracer.h:280-319) over Octree::intersect (octree.cpp:150-185,256-282).
+ *      maxt2 = squared distance bound `mt`; vis[i] = 1 if nothing blocks the segment. ----------------------- */
+int gi_trace_any(gi_ctx* ctx, size_t n, const double* org, const double* dir, const double* maxt2, uint64_t alpha_seed,
+                 uint8_t* vis);
+int gi_trace_any_dev(gi_ctx* ctx, size_t n, const double* org, const double* dir, const double* maxt2, uint64_t alpha_seed,
+                     uint8_t* vis);
+
+/* ---- photons: RayTracer::tracePhotons (raytracer.h:582-715); photons are {origin, dir, col} = 9 fp64 (photon.h) */
+int gi_photon_trace(gi_ctx* ctx, int count, int max_depth, uint64_t seed, uint64_t* n_stored, gi_stats* stats);
+int gi_photon_upload(gi_ctx* ctx, size_t n, const double* photons9);
+int gi_photon_count(gi_ctx* ctx, size_t* n);
+int gi_photon_download(gi_ctx* ctx, size_t n, double* photons9);
+
+/* ---- photon map: PhotonMap::rebuild / Node::partition (photonMap.cpp:33-47,137-192), built on the device over
+ *      the photons currently held by the ctx; root box = scene root box (raytracer.h:38) unless box6 != NULL. - */
+int gi_photon_map_build(gi_ctx* ctx, const double* box6);
+/* structure readback for parity tests: nodes in DFS pre-order like the reference's recursion */
+int gi_photon_map_info(gi_ctx* ctx, uint32_t* n_nodes, uint32_t* n_leaves, uint32_t* n_kept_photons, uint32_t* max_depth);
+int gi_photon_map_download(gi_ctx* ctx, double* node_box6, uint8_t* node_is_leaf, uint32_t* node_count,
+                           uint32_t* photon_ids);
+/* serialise / adopt a built map as one slab (what gets broadcast to the other GPUs) */
+int gi_photon_map_slab_size(gi_ctx* ctx, size_t* bytes);
+int gi_photon_map_slab_ptr(gi_ctx* ctx, void** dev_ptr);
+int gi_photon_map_adopt_slab(gi_ctx* ctx, size_t bytes);   /* after the slab bytes were written to slab_ptr */
+int gi_photon_map_reserve_slab(gi_ctx* ctx, size_t bytes, void** dev_ptr);
+
+/* ---- gather: RayTracer::samplePhotons (raytracer.h:532-579) over PhotonMap::getInRange (photonMap.cpp:50-92,
+ *      115-134).  rgb [n][3]; knn (optional) [n][k] photon ids in ascending distance, GI_NO_HIT padded;
+ *      n_cand (optional) [n] candidate count returned by getInRange. ------------------------------------------ */
+int gi_photon_gather(gi_ctx* ctx, size_t n, const double* pos, const double* dir, int k, double* rgb, uint32_t* knn,
+                     uint32_t* n_cand);
+int gi_photon_gather_dev(gi_ctx* ctx, size_t n, const double* pos, const double* dir, int k, double* rgb, uint32_t* knn,
+                         uint32_t* n_cand);
+
+/* ---- frame: the row loop of RayTracer::run (raytracer.h:93-160) for the pixel rectangle and sample range.
+ *      accum [(y1-y0)*(x1-x0)][3] fp64 receives the SUM over s in [s0,s1) of radiance(); host pointer. ---------- */
+int gi_render_tile(gi_ctx* ctx, const gi_render_params* p, int x0, int y0, int x1, int y1, int s0, int s1, double* accum,
+                   gi_stats* stats);
+int gi_render_tile_dev(gi_ctx* ctx, const gi_render_params* p, int x0, int y0, int x1, int y1, int s0, int s1, double* accum,
+                       gi_stats* stats);
+/* ---- resolve: mean -> gamma 2.2 -> clamp -> (int)(255*c)  (raytracer.h:150-156, util.h:94-97, image.h:14-16) */
+int gi_resolve(gi_ctx* ctx, size_t n_pixels, const double* accum, int spp, uint8_t* rgb8);
+int gi_resolve_dev(gi_ctx* ctx, size_t n_pixels, const double* accum, int spp, uint8_t* rgb8);
+
+/* ---- kernel-level hooks for bench.py's roofline (device buffers owned by the ctx) -------------------------- */
+/* average duration (ms) of the last launches of the named kernel family, measured with CUDA events on gi_stream */
+int gi_last_kernel_ms(gi_ctx* ctx, const char* family, double* ms, uint64_t* launches);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GI_API_H */

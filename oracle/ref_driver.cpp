@@ -218,6 +218,31 @@ static void dump_halton(int w, int h)
     dump("henum_query.u32", q); dump("henum_index.u32", out); dump("henum_scaled.f32", sc);
 }
 
+
+// ---- sampler known-answer tables (util.h / util.cpp functions used by secondaryRay, lights, photons) ----
+static void dump_samplers()
+{
+    uint64_t st = 0x853c49e6748fea9bull;
+    auto rnd = [&]() { st = st * 6364136223846793005ull + 1442695040888963407ull; return (double)(st >> 11) * (1.0 / 9007199254740992.0); };
+    std::vector<double> in, out;
+    for (int i = 0; i < 4000; i++) {
+        glm::dvec3 n = glm::normalize(glm::dvec3(2 * rnd() - 1, 2 * rnd() - 1, 2 * rnd() - 1));
+        glm::dvec3 inc = glm::normalize(glm::dvec3(2 * rnd() - 1, 2 * rnd() - 1, 2 * rnd() - 1));
+        if (i % 7 == 0) n = glm::dvec3(0, 0, (i % 14) ? 1 : -1);
+        float u = (float)rnd(), v = (float)rnd();
+        double frac = rnd(), rough = 0.05 + 0.85 * rnd(), eta = (i & 1) ? 1.0 / (1.0 + rnd()) : 1.0 + rnd(), a = rnd(), b = 0.25 + 3 * rnd();
+        push3(in, n); push3(in, inc); in.push_back(u); in.push_back(v); in.push_back(frac); in.push_back(rough); in.push_back(eta); in.push_back(a); in.push_back(b);
+        push3(out, hemisphereSample_cos(n, u, v, 2));
+        push3(out, sample_phong(glm::reflect(inc, n), n, (1.0 / rough) + 1, u, v));
+        push3(out, sphereCapSample_cos(n, u, v, 2, frac));
+        push3(out, sphereCapSample_cos(n, u, v, 1, frac));
+        push3(out, randomUnitVec(u, v));
+        push3(out, refr(inc, n, eta));
+        out.push_back(fastPrecisePow(a, b)); out.push_back(fastPrecisePow(1.0f - u, 1.0f / 2.0));
+    }
+    dump("kat_in.f64", in); dump("kat_out.f64", out);
+}
+
 // ---- camera rays exactly as RayTracer::run builds them (raytracer.h:74-78,112-129) -------------------
 struct Frame {
     double halfW, halfH; glm::dvec3 center, right;
@@ -245,7 +270,7 @@ int main(int argc, char** argv)
 {
     if (argc < 3) {
         fprintf(stderr, "usage: gi_ref <scene.scn> <outdir> [--w W --h H --s0 A --s1 B --max-depth D --min-depth M --photons P --samples N --x0 --y0 --x1 --y1 --repeat R] cmd...\n"
-                        "cmds: scene halton primary shadow photons gather radiance run time-frame time-gather\n");
+                        "cmds: scene halton samplers primary shadow photons gather radiance run time-frame time-gather\n");
         return 1;
     }
     const char* scn = argv[1];
@@ -290,6 +315,7 @@ int main(int argc, char** argv)
 
     if (has("scene")) dump_scene(scene, rt, meta);
     if (has("halton")) dump_halton(w, h);
+    if (has("samplers")) dump_samplers();
 
     // -- primary rays + closest hit ------------------------------------------------------------------
     std::vector<double> hit_pos, hit_nrm, hit_uv, ray_o, ray_d;
@@ -325,7 +351,7 @@ int main(int argc, char** argv)
                 double maxt = vecLengthSquared(lightDir);
                 Ray sr(p + SHADOW_BIAS * n, lightDir);                              // raytracer.h:241
                 bool v_ = rt.visible(sr, maxt);
-                push3(so, sr.origin); push3(sd, lightDir); smt.push_back(maxt); vis.push_back(v_ ? 1 : 0);
+                push3(so, sr.origin); push3(sd, sr.dir); smt.push_back(maxt); vis.push_back(v_ ? 1 : 0);
             }
         }
         dump("sh_o.f64", so); dump("sh_d.f64", sd); dump("sh_maxt2.f64", smt); dump("sh_vis.u8", vis);
