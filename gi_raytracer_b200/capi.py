@@ -1,0 +1,275 @@
+"""ctypes binding of libgi_b200.so — the C ABI declared in include/gi_api.h.
+
+`Context` wraps one gi_ctx (one CUDA device).  Host-pointer methods take/return numpy arrays; `*_dev` methods take raw
+device pointers (e.g. torch tensors' data_ptr()).  There is no CPU fallback: if the library or a B200 is missing the
+constructor raises.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+from .abi import GiRenderParams, GiSceneDesc, GiStats, SceneArrays
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libgi_b200.so")
+
+# every symbol include/gi_api.h declares (tests check that the library exports each one)
+API_SYMBOLS = [
+    "gi_create", "gi_destroy", "gi_last_error", "gi_version", "gi_stream", "gi_synchronize", "gi_scene_upload",
+    "gi_halton_sample", "gi_halton_index", "gi_camera_rays", "gi_trace_closest", "gi_trace_closest_dev", "gi_trace_any",
+    "gi_trace_any_dev", "gi_photon_trace", "gi_photon_upload", "gi_photon_count", "gi_photon_download",
+    "gi_photon_map_build", "gi_photon_map_info", "gi_photon_map_download", "gi_photon_map_slab_size",
+    "gi_photon_map_slab_ptr", "gi_photon_map_adopt_slab", "gi_photon_map_reserve_slab", "gi_photon_gather",
+    "gi_photon_gather_dev", "gi_render_tile", "gi_render_tile_dev", "gi_resolve", "gi_resolve_dev", "gi_last_kernel_ms",
+]
+
+_LIB = None
+
+
+class GiError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(f"gi error {code}: {msg}")
+        self.code = code
+
+
+def load_library():
+    """dlopen libgi_b200.so (built in-tree by gi_raytracer_b200.build).  Fails loudly when it is missing."""
+    global _LIB
+    if _LIB is not None:
+        return _LIB
+    if not os.path.exists(LIB_PATH):
+        raise FileNotFoundError(f"{LIB_PATH} is missing: run `python -m gi_raytracer_b200.build` (there is no CPU fallback)")
+    L = C.CDLL(LIB_PATH)
+    vp, u64, sz, u32, i32 = C.c_void_p, C.c_uint64, C.c_size_t, C.c_uint32, C.c_int
+    L.gi_create.argtypes = [i32, C.POINTER(vp)]
+    L.gi_destroy.argtypes = [vp]
+    L.gi_destroy.restype = None
+    L.gi_last_error.argtypes = [vp]
+    L.gi_last_error.restype = C.c_char_p
+    L.gi_version.restype = C.c_char_p
+    L.gi_stream.argtypes = [vp]
+    L.gi_stream.restype = vp
+    L.gi_synchronize.argtypes = [vp]
+    L.gi_scene_upload.argtypes = [vp, C.POINTER(GiSceneDesc)]
+    L.gi_halton_sample.argtypes = [vp, sz, vp, vp, vp]
+    L.gi_halton_index.argtypes = [vp, i32, i32, sz, vp, vp, vp, vp]
+    L.gi_camera_rays.argtypes = [vp, i32, i32, i32, i32, i32, i32, i32, i32, vp, vp, vp]
+    for f in (L.gi_trace_closest, L.gi_trace_closest_dev):
+        f.argtypes = [vp, sz, vp, vp, u64, vp, vp, vp, vp]
+    for f in (L.gi_trace_any, L.gi_trace_any_dev):
+        f.argtypes = [vp, sz, vp, vp, vp, u64, vp]
+    L.gi_photon_trace.argtypes = [vp, i32, i32, u64, C.POINTER(u64), C.POINTER(GiStats)]
+    L.gi_photon_upload.argtypes = [vp, sz, vp]
+    L.gi_photon_count.argtypes = [vp, C.POINTER(sz)]
+    L.gi_photon_download.argtypes = [vp, sz, vp]
+    L.gi_photon_map_build.argtypes = [vp, vp]
+    L.gi_photon_map_info.argtypes = [vp, C.POINTER(u32), C.POINTER(u32), C.POINTER(u32), C.POINTER(u32)]
+    L.gi_photon_map_download.argtypes = [vp, vp, vp, vp, vp]
+    L.gi_photon_map_slab_size.argtypes = [vp, C.POINTER(sz)]
+    L.gi_photon_map_slab_ptr.argtypes = [vp, C.POINTER(vp)]
+    L.gi_photon_map_adopt_slab.argtypes = [vp, sz]
+    L.gi_photon_map_reserve_slab.argtypes = [vp, sz, C.POINTER(vp)]
+    for f in (L.gi_photon_gather, L.gi_photon_gather_dev):
+        f.argtypes = [vp, sz, vp, vp, i32, vp, vp, vp]
+    for f in (L.gi_render_tile, L.gi_render_tile_dev):
+        f.argtypes = [vp, C.POINTER(GiRenderParams), i32, i32, i32, i32, i32, i32, vp, C.POINTER(GiStats)]
+    for f in (L.gi_resolve, L.gi_resolve_dev):
+        f.argtypes = [vp, sz, vp, i32, vp]
+    L.gi_last_kernel_ms.argtypes = [vp, C.c_char_p, C.POINTER(C.c_double), C.POINTER(u64)]
+    # host-side scene facade (same library)
+    L.gih_scene_load.argtypes = [C.c_char_p, i32, C.POINTER(vp)]
+    L.gih_scene_desc.argtypes = [vp]
+    L.gih_scene_desc.restype = C.POINTER(GiSceneDesc)
+    L.gih_scene_knobs.argtypes = [vp, C.POINTER(i32), C.POINTER(i32), C.POINTER(i32), C.POINTER(i32), C.POINTER(C.c_double)]
+    L.gih_scene_knobs.restype = None
+    L.gih_scene_free.argtypes = [vp]
+    L.gih_scene_free.restype = None
+    L.gih_render_scene.argtypes = [C.c_char_p, i32, i32, i32, i32, i32, i32, u64, C.c_char_p, vp, C.POINTER(GiStats), C.POINTER(GiStats),
+                                   C.POINTER(C.c_double), C.POINTER(C.c_double)]
+    _LIB = L
+    return L
+
+
+def _p(a):
+    return a.ctypes.data if a is not None else None
+
+
+def _f64(a, cols):
+    return np.ascontiguousarray(a, dtype=np.float64).reshape(-1, cols)
+
+
+class Context:
+    """One gi_ctx on one CUDA device."""
+
+    def __init__(self, device=0):
+        self.L = load_library()
+        h = C.c_void_p()
+        rc = self.L.gi_create(device, C.byref(h))
+        if rc != 0:
+            raise GiError(rc, "gi_create failed: no usable sm_100 CUDA device (there is no CPU fallback)")
+        self.h = h
+        self.device = device
+        self._scene_keepalive = None
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.L.gi_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _ck(self, rc):
+        if rc != 0:
+            raise GiError(rc, self.L.gi_last_error(self.h).decode())
+
+    @property
+    def stream(self):
+        return self.L.gi_stream(self.h)
+
+    def synchronize(self):
+        self._ck(self.L.gi_synchronize(self.h))
+
+    def kernel_ms(self, family):
+        ms, n = C.c_double(), C.c_uint64()
+        self._ck(self.L.gi_last_kernel_ms(self.h, family.encode(), C.byref(ms), C.byref(n)))
+        return ms.value, n.value
+
+    # -- scene ------------------------------------------------------------------------------------------------
+    def upload_scene(self, scene: SceneArrays):
+        d = scene.desc()
+        self._ck(self.L.gi_scene_upload(self.h, C.byref(d)))
+
+    # -- Halton / camera ------------------------------------------------------------------------------------------
+    def halton_sample(self, dims, idx):
+        dims = np.ascontiguousarray(dims, dtype=np.uint32).ravel()
+        idx = np.ascontiguousarray(idx, dtype=np.uint32).ravel()
+        out = np.empty(dims.size, dtype=np.float32)
+        self._ck(self.L.gi_halton_sample(self.h, dims.size, _p(dims), _p(idx), _p(out)))
+        return out
+
+    def halton_index(self, w, h, s, x, y):
+        s, x, y = (np.ascontiguousarray(a, dtype=np.uint32).ravel() for a in (s, x, y))
+        out = np.empty(s.size, dtype=np.uint32)
+        self._ck(self.L.gi_halton_index(self.h, w, h, s.size, _p(s), _p(x), _p(y), _p(out)))
+        return out
+
+    def camera_rays(self, w, h, x0, y0, x1, y1, s0, s1):
+        n = (x1 - x0) * (y1 - y0) * (s1 - s0)
+        org, d, idx = np.empty((n, 3)), np.empty((n, 3)), np.empty(n, dtype=np.uint32)
+        self._ck(self.L.gi_camera_rays(self.h, w, h, x0, y0, x1, y1, s0, s1, _p(org), _p(d), _p(idx)))
+        return org, d, idx
+
+    # -- rays --------------------------------------------------------------------------------------------------------
+    def trace_closest(self, org, d, alpha_seed=0):
+        org, d = _f64(org, 3), _f64(d, 3)
+        n = org.shape[0]
+        prim = np.empty(n, dtype=np.uint32)
+        hit, nrm, uv = np.empty((n, 3)), np.empty((n, 3)), np.empty((n, 2))
+        self._ck(self.L.gi_trace_closest(self.h, n, _p(org), _p(d), alpha_seed, _p(prim), _p(hit), _p(nrm), _p(uv)))
+        return prim, hit, nrm, uv
+
+    def trace_any(self, org, d, maxt2, alpha_seed=0):
+        org, d = _f64(org, 3), _f64(d, 3)
+        maxt2 = np.ascontiguousarray(maxt2, dtype=np.float64).ravel()
+        n = org.shape[0]
+        vis = np.empty(n, dtype=np.uint8)
+        self._ck(self.L.gi_trace_any(self.h, n, _p(org), _p(d), _p(maxt2), alpha_seed, _p(vis)))
+        return vis
+
+    def trace_closest_dev(self, n, org_ptr, dir_ptr, prim_ptr, hit_ptr=None, nrm_ptr=None, uv_ptr=None, alpha_seed=0):
+        self._ck(self.L.gi_trace_closest_dev(self.h, n, org_ptr, dir_ptr, alpha_seed, prim_ptr, hit_ptr, nrm_ptr, uv_ptr))
+
+    def trace_any_dev(self, n, org_ptr, dir_ptr, maxt2_ptr, vis_ptr, alpha_seed=0):
+        self._ck(self.L.gi_trace_any_dev(self.h, n, org_ptr, dir_ptr, maxt2_ptr, alpha_seed, vis_ptr))
+
+    # -- photons -------------------------------------------------------------------------------------------------------
+    def photon_trace(self, count, max_depth=5, seed=1):
+        n, st = C.c_uint64(), GiStats()
+        self._ck(self.L.gi_photon_trace(self.h, count, max_depth, seed, C.byref(n), C.byref(st)))
+        return n.value, st
+
+    def photon_upload(self, photons9):
+        ph = _f64(photons9, 9)
+        self._ck(self.L.gi_photon_upload(self.h, ph.shape[0], _p(ph)))
+
+    def photon_count(self):
+        n = C.c_size_t()
+        self._ck(self.L.gi_photon_count(self.h, C.byref(n)))
+        return n.value
+
+    def photon_download(self):
+        n = self.photon_count()
+        out = np.empty((n, 9))
+        self._ck(self.L.gi_photon_download(self.h, n, _p(out)))
+        return out
+
+    def photon_map_build(self, box6=None):
+        b = np.ascontiguousarray(box6, dtype=np.float64) if box6 is not None else None
+        self._ck(self.L.gi_photon_map_build(self.h, _p(b)))
+
+    def photon_map_info(self):
+        v = [C.c_uint32() for _ in range(4)]
+        self._ck(self.L.gi_photon_map_info(self.h, *[C.byref(x) for x in v]))
+        return dict(n_nodes=v[0].value, n_leaves=v[1].value, n_kept=v[2].value, max_depth=v[3].value)
+
+    def photon_map_download(self):
+        inf = self.photon_map_info()
+        box = np.empty((inf["n_nodes"], 6))
+        leaf = np.empty(inf["n_nodes"], dtype=np.uint8)
+        cnt = np.empty(inf["n_nodes"], dtype=np.uint32)
+        ids = np.empty(max(inf["n_kept"], 1), dtype=np.uint32)
+        self._ck(self.L.gi_photon_map_download(self.h, _p(box), _p(leaf), _p(cnt), _p(ids)))
+        return box, leaf, cnt, ids[:inf["n_kept"]]
+
+    def photon_map_slab(self):
+        """(device pointer, bytes) of the built map's slab — what rank 0 broadcasts."""
+        n, p = C.c_size_t(), C.c_void_p()
+        self._ck(self.L.gi_photon_map_slab_size(self.h, C.byref(n)))
+        self._ck(self.L.gi_photon_map_slab_ptr(self.h, C.byref(p)))
+        return p.value, n.value
+
+    def photon_map_reserve_slab(self, nbytes):
+        p = C.c_void_p()
+        self._ck(self.L.gi_photon_map_reserve_slab(self.h, nbytes, C.byref(p)))
+        return p.value
+
+    def photon_map_adopt_slab(self, nbytes):
+        self._ck(self.L.gi_photon_map_adopt_slab(self.h, nbytes))
+
+    def gather(self, pos, d, k=32, want_knn=True):
+        pos, d = _f64(pos, 3), _f64(d, 3)
+        n = pos.shape[0]
+        rgb = np.empty((n, 3))
+        knn = np.empty((n, k), dtype=np.uint32) if want_knn else None
+        nc = np.empty(n, dtype=np.uint32)
+        self._ck(self.L.gi_photon_gather(self.h, n, _p(pos), _p(d), k, _p(rgb), _p(knn), _p(nc)))
+        return rgb, knn, nc
+
+    def gather_dev(self, n, pos_ptr, dir_ptr, rgb_ptr, k=32, knn_ptr=None, ncand_ptr=None):
+        self._ck(self.L.gi_photon_gather_dev(self.h, n, pos_ptr, dir_ptr, k, rgb_ptr, knn_ptr, ncand_ptr))
+
+    # -- frame -----------------------------------------------------------------------------------------------------------
+    def render_tile(self, params: GiRenderParams, x0, y0, x1, y1, s0, s1):
+        acc = np.empty(((y1 - y0) * (x1 - x0), 3))
+        st = GiStats()
+        self._ck(self.L.gi_render_tile(self.h, C.byref(params), x0, y0, x1, y1, s0, s1, _p(acc), C.byref(st)))
+        return acc, st
+
+    def render_tile_dev(self, params: GiRenderParams, x0, y0, x1, y1, s0, s1, accum_ptr):
+        st = GiStats()
+        self._ck(self.L.gi_render_tile_dev(self.h, C.byref(params), x0, y0, x1, y1, s0, s1, accum_ptr, C.byref(st)))
+        return st
+
+    def resolve(self, accum, spp):
+        accum = _f64(accum, 3)
+        out = np.empty((accum.shape[0], 3), dtype=np.uint8)
+        self._ck(self.L.gi_resolve(self.h, accum.shape[0], _p(accum), spp, _p(out)))
+        return out
+
+    def resolve_dev(self, n_pixels, accum_ptr, spp, rgb8_ptr):
+        self._ck(self.L.gi_resolve_dev(self.h, n_pixels, accum_ptr, spp, rgb8_ptr))

@@ -1,0 +1,870 @@
+// gi_api.cu — the C ABI of libgi_b200.so (include/gi_api.h): context, scene upload, and the host side of every kernel
+// launch.  All work of a context is enqueued on one CUDA stream; kernel families are timed with CUDA events on that
+// stream (gi_last_kernel_ms).  There is no CPU fallback: every compute entry point needs a CUDA device.
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "gi_kernels.cuh"
+
+#define GI_VERSION "gi_b200 0.1.0 (sm_100a)"
+#define GI_MAX_PATHS (1u << 23)   // paths in flight per chunk of the wavefront
+
+// ---- small RAII-free device buffer helper -------------------------------------------------------------------------------------
+struct DevBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+    cudaError_t reserve(size_t bytes)
+    {
+        if (bytes <= cap) return cudaSuccess;
+        if (p) cudaFree(p);
+        p = nullptr; cap = 0;
+        size_t want = bytes + bytes / 4 + 256;
+        cudaError_t e = cudaMalloc(&p, want);
+        if (e == cudaSuccess) cap = want;
+        return e;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+    template <typename T> T* as() const { return reinterpret_cast<T*>(p); }
+};
+
+struct FamStat { double ms = 0; uint64_t launches = 0; };
+struct TimedLaunch { std::string fam; cudaEvent_t a, b; };
+
+struct gi_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    std::string err;
+    // scene
+    bool has_scene = false;
+    DScene S{};
+    double root_box[6] = { 0, 0, 0, 0, 0, 0 };
+    DevBuf b_nodes, b_refs, b_geom, b_nrm, b_uv, b_fnorm, b_pmat, b_ptype, b_mats, b_tex, b_texpx, b_lights, b_htab, b_hdims;
+    // photons + photon map
+    DevBuf b_photons; size_t n_photons = 0;
+    bool has_map = false;
+    DevBuf b_slab;          // compact map: header | nodes | pos | dircol | pid
+    size_t slab_bytes = 0;
+    uint32_t pm_nodes = 0, pm_kept = 0, pm_leaves = 0, pm_depth = 0;
+    DGatherMap G{};
+    // workspaces
+    DevBuf w0, w1, w2, w3, w4, w5, w6, w7, w8, w9;           // API staging
+    DevBuf q_a[5], q_b[5], hl[7], ps[3], b_cnt, b_accum, b_scan0, b_scan1, b_misc;
+    // timing
+    std::vector<TimedLaunch> pending;
+    std::vector<cudaEvent_t> event_pool;
+    std::map<std::string, FamStat> fam;
+};
+
+static int fail(gi_ctx* c, int code, const std::string& msg)
+{
+    if (c) c->err = msg;
+    return code;
+}
+#define CK(call)                                                                                                   \
+    do {                                                                                                           \
+        cudaError_t e_ = (call);                                                                                   \
+        if (e_ != cudaSuccess) return fail(ctx, e_ == cudaErrorMemoryAllocation ? GI_ERR_OOM : GI_ERR_CUDA,       \
+                                           std::string(#call) + ": " + cudaGetErrorString(e_));                    \
+    } while (0)
+
+static inline unsigned grid_for(size_t n, unsigned block) { return (unsigned)((n + block - 1) / block); }
+
+static cudaEvent_t get_event(gi_ctx* ctx)
+{
+    if (!ctx->event_pool.empty()) { cudaEvent_t e = ctx->event_pool.back(); ctx->event_pool.pop_back(); return e; }
+    cudaEvent_t e; cudaEventCreate(&e); return e;
+}
+struct ScopedTimer {   // records an event pair around the launches issued in its scope
+    gi_ctx* ctx; TimedLaunch t;
+    ScopedTimer(gi_ctx* c, const char* fam) : ctx(c) { t.fam = fam; t.a = get_event(c); t.b = get_event(c); cudaEventRecord(t.a, c->stream); }
+    ~ScopedTimer() { cudaEventRecord(t.b, ctx->stream); ctx->pending.push_back(t); }
+};
+static void fam_reset(gi_ctx* ctx, const char* fam) { ctx->fam[fam] = FamStat(); }
+static void collect_timers(gi_ctx* ctx)   // after a stream sync
+{
+    for (auto& t : ctx->pending) {
+        float ms = 0;
+        if (cudaEventElapsedTime(&ms, t.a, t.b) == cudaSuccess) { ctx->fam[t.fam].ms += ms; ctx->fam[t.fam].launches++; }
+        ctx->event_pool.push_back(t.a); ctx->event_pool.push_back(t.b);
+    }
+    ctx->pending.clear();
+}
+
+// ---- Halton tables (host): Faure permutations + digit-block tables, the rule behind halton_sampler.h:573-603, 890-1414 ----------
+static void build_halton(std::vector<uint16_t>& tab, std::vector<DHaltonDim>& dims)
+{
+    const unsigned max_base = 1619;
+    std::vector<std::vector<uint16_t>> perms(max_base + 1);
+    for (unsigned k = 1; k <= 3; ++k) { perms[k].resize(k); for (unsigned i = 0; i < k; ++i) perms[k][i] = (uint16_t)i; }
+    for (unsigned base = 4; base <= max_base; ++base) {
+        perms[base].resize(base);
+        const unsigned b = base / 2;
+        if (base & 1) {
+            for (unsigned i = 0; i < base - 1; ++i) perms[base][i + (i >= b)] = (uint16_t)(perms[base - 1][i] + (perms[base - 1][i] >= b));
+            perms[base][b] = (uint16_t)b;
+        } else {
+            for (unsigned i = 0; i < b; ++i) { perms[base][i] = (uint16_t)(2 * perms[b][i]); perms[base][b + i] = (uint16_t)(2 * perms[b][i] + 1); }
+        }
+    }
+    dims.assign(256, DHaltonDim());
+    tab.clear();
+    unsigned found = 0;
+    for (unsigned c = 2; found < 256; c++) {
+        bool prime = true;
+        for (unsigned d = 2; d * d <= c; d++) if (c % d == 0) { prime = false; break; }
+        if (!prime) continue;
+        unsigned digits = 1; uint64_t bk = c;
+        while (bk * c <= 500) { bk *= c; digits++; }          // digits per table block (3^5, 5^3, 7^3, 11^2 .. 19^2, then 1)
+        unsigned nb = 1; uint64_t pw = bk;
+        while (pw * bk <= 0xFFFFFFFFull) { pw *= bk; nb++; }   // blocks so that base^(digits*nb) < 2^32
+        DHaltonDim& D = dims[found];
+        D.base = c; D.block = (uint32_t)bk; D.nblocks = nb; D.table_off = (uint32_t)tab.size();
+        D.scale = (float)(0.9999998807907104 / (double)pw);
+        if (found > 0)
+            for (uint32_t i = 0; i < bk; i++) {
+                uint32_t idx = i, r = 0;
+                for (unsigned k = 0; k < digits; k++) { r = r * c + perms[c][idx % c]; idx /= c; }
+                tab.push_back((uint16_t)r);
+            }
+        found++;
+    }
+}
+
+static DHEnum make_henum(uint32_t width, uint32_t height)   // Halton_enum::Halton_enum (halton_enum.h:69-104)
+{
+    DHEnum he{};
+    uint32_t w = 1; while (w < width) { ++he.p2; w *= 2; }
+    uint32_t h = 1; while (h < height) { ++he.p3; h *= 3; }
+    he.scale_x = (float)w; he.scale_y = (float)h; he.inc = w * h;
+    // extended Euclid for the two modular inverses
+    long long a = h, b = w, s0 = 1, s1 = 0, t0 = 0, t1 = 1;
+    while (b) { long long q = a / b, r = a % b; a = b; b = r; long long s2 = s0 - q * s1; s0 = s1; s1 = s2; long long t2 = t0 - q * t1; t0 = t1; t1 = t2; }
+    long long i1 = s0, i2 = t0;   // h*i1 + w*i2 = 1
+    uint32_t inv2 = (i1 < 0) ? (uint32_t)(i1 + (long long)w) : (uint32_t)(i1 % (long long)w);
+    uint32_t inv3 = (i2 < 0) ? (uint32_t)(i2 + (long long)h) : (uint32_t)(i2 % (long long)h);
+    he.mx = h * inv2; he.my = w * inv3;
+    return he;
+}
+
+static DFrame make_frame(const gi_ctx* ctx, int w, int h, int x0, int y0, int x1, int y1)
+{
+    DFrame F{};
+    const gi_camera& c = ctx->S.cam;
+    F.w = w; F.h = h; F.x0 = x0; F.y0 = y0; F.tw = x1 - x0; F.th = y1 - y0;
+    F.halfW = (c.sensor_diag * w) / (std::sqrt((double)w * w + h * h));   // raytracer.h:74-75
+    F.halfH = F.halfW * ((double)h / w);
+    auto v = [](const double* p) { d3 r; r.x = p[0]; r.y = p[1]; r.z = p[2]; return r; };
+    F.pos = v(c.pos); F.up = v(c.up);
+    d3 fw = v(c.forward);
+    F.center.x = F.pos.x + fw.x * c.focal_dist; F.center.y = F.pos.y + fw.y * c.focal_dist; F.center.z = F.pos.z + fw.z * c.focal_dist;   // :77
+    d3 cr; cr.x = fw.y * F.up.z - F.up.y * fw.z; cr.y = fw.z * F.up.x - F.up.z * fw.x; cr.z = fw.x * F.up.y - F.up.x * fw.y;               // cross(forward, up)
+    double il = 1.0 / std::sqrt(cr.x * cr.x + cr.y * cr.y + cr.z * cr.z);
+    F.right.x = cr.x * il; F.right.y = cr.y * il; F.right.z = cr.z * il;                                                                       // :78
+    F.he = make_henum((uint32_t)w, (uint32_t)h);
+    return F;
+}
+
+// ---- lifetime -----------------------------------------------------------------------------------------------------------------------
+extern "C" const char* gi_version(void) { return GI_VERSION; }
+
+extern "C" int gi_create(int device, gi_ctx** out)
+{
+    if (!out) return GI_ERR_INVALID;
+    *out = nullptr;
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess || n <= 0 || device < 0 || device >= n) return GI_ERR_NO_DEVICE;
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return GI_ERR_NO_DEVICE;
+    if (prop.major != 10) return GI_ERR_NO_DEVICE;   // the kernels are built for sm_100a only
+    if (cudaSetDevice(device) != cudaSuccess) return GI_ERR_NO_DEVICE;
+    gi_ctx* ctx = new gi_ctx();
+    ctx->device = device;
+    if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return GI_ERR_CUDA; }
+    // Halton tables are scene independent
+    std::vector<uint16_t> tab; std::vector<DHaltonDim> dims;
+    build_halton(tab, dims);
+    if (ctx->b_htab.reserve(tab.size() * 2) != cudaSuccess || ctx->b_hdims.reserve(dims.size() * sizeof(DHaltonDim)) != cudaSuccess) { delete ctx; return GI_ERR_OOM; }
+    cudaMemcpy(ctx->b_htab.p, tab.data(), tab.size() * 2, cudaMemcpyHostToDevice);
+    cudaMemcpy(ctx->b_hdims.p, dims.data(), dims.size() * sizeof(DHaltonDim), cudaMemcpyHostToDevice);
+    ctx->S.halton_tab = ctx->b_htab.as<uint16_t>();
+    ctx->S.halton_dims = ctx->b_hdims.as<DHaltonDim>();
+    // deep local stacks (96 x u32 per thread) need no extra configuration; prefer L1 over shared for the traversal kernels
+    *out = ctx;
+    return GI_OK;
+}
+
+extern "C" void gi_destroy(gi_ctx* ctx)
+{
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    DevBuf* all[] = { &ctx->b_nodes, &ctx->b_refs, &ctx->b_geom, &ctx->b_nrm, &ctx->b_uv, &ctx->b_fnorm, &ctx->b_pmat, &ctx->b_ptype, &ctx->b_mats, &ctx->b_tex, &ctx->b_texpx,
+                      &ctx->b_lights, &ctx->b_htab, &ctx->b_hdims, &ctx->b_photons, &ctx->b_slab, &ctx->w0, &ctx->w1, &ctx->w2, &ctx->w3, &ctx->w4, &ctx->w5, &ctx->w6, &ctx->w7,
+                      &ctx->w8, &ctx->w9, &ctx->b_cnt, &ctx->b_accum, &ctx->b_scan0, &ctx->b_scan1, &ctx->b_misc };
+    for (DevBuf* b : all) b->release();
+    for (auto& b : ctx->q_a) b.release();
+    for (auto& b : ctx->q_b) b.release();
+    for (auto& b : ctx->hl) b.release();
+    for (auto& b : ctx->ps) b.release();
+    for (auto& t : ctx->pending) { cudaEventDestroy(t.a); cudaEventDestroy(t.b); }
+    for (auto& e : ctx->event_pool) cudaEventDestroy(e);
+    cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
+
+extern "C" const char* gi_last_error(const gi_ctx* ctx) { return ctx ? ctx->err.c_str() : "null context"; }
+extern "C" void* gi_stream(gi_ctx* ctx) { return ctx ? (void*)ctx->stream : nullptr; }
+extern "C" int gi_synchronize(gi_ctx* ctx)
+{
+    if (!ctx) return GI_ERR_INVALID;
+    CK(cudaStreamSynchronize(ctx->stream));
+    collect_timers(ctx);
+    return GI_OK;
+}
+extern "C" int gi_last_kernel_ms(gi_ctx* ctx, const char* family, double* ms, uint64_t* launches)
+{
+    if (!ctx || !family) return GI_ERR_INVALID;
+    auto it = ctx->fam.find(family);
+    if (it == ctx->fam.end() || it->second.launches == 0) { if (ms) *ms = 0; if (launches) *launches = 0; return GI_OK; }
+    if (ms) *ms = it->second.ms / (double)it->second.launches;
+    if (launches) *launches = it->second.launches;
+    return GI_OK;
+}
+
+// ---- scene upload ---------------------------------------------------------------------------------------------------------------------
+template <typename T> static cudaError_t upload(DevBuf& b, const T* src, size_t n, cudaStream_t st)
+{
+    cudaError_t e = b.reserve(std::max<size_t>(n, 1) * sizeof(T));
+    if (e != cudaSuccess) return e;
+    if (n) e = cudaMemcpyAsync(b.p, src, n * sizeof(T), cudaMemcpyHostToDevice, st);
+    return e;
+}
+
+extern "C" int gi_scene_upload(gi_ctx* ctx, const gi_scene_desc* sc)
+{
+    if (!ctx || !sc) return GI_ERR_INVALID;
+    CK(cudaSetDevice(ctx->device));
+    if (sc->n_nodes == 0 || !sc->node_box) return fail(ctx, GI_ERR_INVALID, "scene has no octree nodes (an empty scene still has a root)");
+    // validate topology so that a malformed description cannot make a kernel read out of bounds
+    for (uint32_t i = 0; i < sc->n_nodes; i++) {
+        uint32_t m = sc->node_mask[i];
+        if (m) { uint32_t nc = (uint32_t)__builtin_popcount(m); if ((uint64_t)sc->node_child[i] + nc > sc->n_nodes || sc->node_child[i] <= i) return fail(ctx, GI_ERR_INVALID, "node child range out of bounds"); }
+        if ((uint64_t)sc->node_prim_off[i] + sc->node_prim_cnt[i] > sc->n_refs) return fail(ctx, GI_ERR_INVALID, "leaf primitive range out of bounds");
+    }
+    for (uint32_t i = 0; i < sc->n_refs; i++) if (sc->leaf_prims[i] >= sc->n_prims) return fail(ctx, GI_ERR_INVALID, "leaf primitive id out of bounds");
+    for (uint32_t i = 0; i < sc->n_prims; i++) if (sc->prim_mat[i] >= sc->n_mats || sc->prim_type[i] > GI_PRIM_CONE) return fail(ctx, GI_ERR_INVALID, "primitive material/type out of bounds");
+    for (uint32_t i = 0; i < sc->n_mats; i++) if (sc->mats[i].diffuse_tex >= sc->n_tex || sc->mats[i].emissive_tex >= sc->n_tex) return fail(ctx, GI_ERR_INVALID, "material texture out of bounds");
+    for (uint32_t i = 0; i < sc->n_tex; i++) {
+        const gi_texture& t = sc->tex[i];
+        if (t.kind == GI_TEX_IMAGE && (t.width <= 0 || t.height <= 0 || t.pixel_offset + (uint64_t)t.width * t.height * 4 > sc->tex_pixel_bytes)) return fail(ctx, GI_ERR_INVALID, "image texture out of bounds or empty");
+        if (t.kind < 0 || t.kind > GI_TEX_IMAGE) return fail(ctx, GI_ERR_INVALID, "unknown texture kind");
+    }
+    // nodes: SoA description -> 64-byte records
+    std::vector<DNode> nodes(sc->n_nodes);
+    for (uint32_t i = 0; i < sc->n_nodes; i++) {
+        DNode& n = nodes[i];
+        for (int k = 0; k < 3; k++) { n.bmin[k] = sc->node_box[6 * (size_t)i + k]; n.bmax[k] = sc->node_box[6 * (size_t)i + 3 + k]; }
+        n.child = sc->node_child[i]; n.mask = sc->node_mask[i]; n.prim_off = sc->node_prim_off[i]; n.prim_cnt = sc->node_prim_cnt[i];
+    }
+    // leaf references: the primitive's geometry is replicated per (leaf, primitive) occurrence, in leaf order, so that a
+    // leaf is one contiguous run of 80-byte records
+    bool full = false;
+    std::vector<uint8_t> mat_alpha(sc->n_mats, 0);
+    for (uint32_t i = 0; i < sc->n_mats; i++) {
+        const gi_material& m = sc->mats[i];
+        const gi_texture& t = sc->tex[m.diffuse_tex];
+        bool may_fail = (m.ior == 1) && (m.opacity < 1.0 || (t.kind == GI_TEX_IMAGE && t.has_alpha));
+        mat_alpha[i] = may_fail ? 1 : 0;
+    }
+    std::vector<uint32_t> pflags(sc->n_prims);
+    for (uint32_t i = 0; i < sc->n_prims; i++) {
+        uint32_t f = sc->prim_type[i];
+        bool writes_uv = false;
+        if (sc->prim_type[i] == GI_PRIM_TRIANGLE) {
+            const double* nn = sc->prim_nrm + 9 * (size_t)i;
+            auto l2 = [](const double* v) { return v[0] * v[0] + v[1] * v[1] + v[2] * v[2]; };
+            writes_uv = l2(nn) > 0 && l2(nn + 3) > 0 && l2(nn + 6) > 0;
+        } else if (sc->prim_type[i] == GI_PRIM_SPHERE) writes_uv = true;
+        if (writes_uv) f |= LF_WRITES_UV; else full = true;
+        if (mat_alpha[sc->prim_mat[i]]) { f |= LF_ALPHA; full = true; }
+        pflags[i] = f;
+    }
+    std::vector<DLeafRef> refs(sc->n_refs);
+    for (uint32_t i = 0; i < sc->n_refs; i++) {
+        uint32_t p = sc->leaf_prims[i];
+        std::memcpy(refs[i].g, sc->prim_geom + 9 * (size_t)p, 9 * sizeof(double));
+        refs[i].prim = p; refs[i].flags = pflags[p];
+    }
+    cudaStream_t st = ctx->stream;
+    CK(upload(ctx->b_nodes, nodes.data(), nodes.size(), st));
+    CK(upload(ctx->b_refs, refs.data(), refs.size(), st));
+    CK(upload(ctx->b_geom, sc->prim_geom, (size_t)sc->n_prims * 9, st));
+    CK(upload(ctx->b_nrm, sc->prim_nrm, (size_t)sc->n_prims * 9, st));
+    CK(upload(ctx->b_uv, sc->prim_uv, (size_t)sc->n_prims * 6, st));
+    CK(upload(ctx->b_fnorm, sc->prim_fnorm, (size_t)sc->n_prims * 3, st));
+    CK(upload(ctx->b_pmat, sc->prim_mat, (size_t)sc->n_prims, st));
+    CK(upload(ctx->b_ptype, sc->prim_type, (size_t)sc->n_prims, st));
+    CK(upload(ctx->b_mats, sc->mats, (size_t)sc->n_mats, st));
+    CK(upload(ctx->b_tex, sc->tex, (size_t)sc->n_tex, st));
+    CK(upload(ctx->b_texpx, sc->tex_pixels, (size_t)sc->tex_pixel_bytes, st));
+    CK(upload(ctx->b_lights, sc->lights, (size_t)sc->n_lights, st));
+    CK(cudaStreamSynchronize(st));   // the host staging vectors die at return
+    DScene& S = ctx->S;
+    S.nodes = ctx->b_nodes.as<DNode>(); S.refs = ctx->b_refs.as<DLeafRef>();
+    S.n_nodes = sc->n_nodes; S.n_refs = sc->n_refs; S.n_prims = sc->n_prims;
+    S.prim_geom = ctx->b_geom.as<double>(); S.prim_nrm = ctx->b_nrm.as<double>(); S.prim_uv = ctx->b_uv.as<double>(); S.prim_fnorm = ctx->b_fnorm.as<double>();
+    S.prim_mat = ctx->b_pmat.as<uint32_t>(); S.prim_type = ctx->b_ptype.as<uint8_t>();
+    S.mats = ctx->b_mats.as<gi_material>(); S.tex = ctx->b_tex.as<gi_texture>(); S.tex_pixels = ctx->b_texpx.as<uint8_t>();
+    S.lights = ctx->b_lights.as<gi_light>(); S.n_lights = sc->n_lights; S.n_mats = sc->n_mats; S.n_tex = sc->n_tex;
+    S.cam = sc->camera;
+    for (int k = 0; k < 3; k++) S.ambient[k] = sc->ambient[k];
+    S.full = full ? 1u : 0u;
+    for (int k = 0; k < 6; k++) ctx->root_box[k] = sc->node_box[k];
+    ctx->has_scene = true;
+    ctx->has_map = false;
+    ctx->n_photons = 0;
+    return GI_OK;
+}
+
+// ---- Halton entry points --------------------------------------------------------------------------------------------------------------
+extern "C" int gi_halton_sample(gi_ctx* ctx, size_t n, const uint32_t* dim, const uint32_t* index, float* out)
+{
+    if (!ctx || (n && (!dim || !index || !out))) return GI_ERR_INVALID;
+    if (!n) return GI_OK;
+    CK(cudaSetDevice(ctx->device));
+    CK(ctx->w0.reserve(n * 4)); CK(ctx->w1.reserve(n * 4)); CK(ctx->w2.reserve(n * 4));
+    CK(cudaMemcpyAsync(ctx->w0.p, dim, n * 4, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->w1.p, index, n * 4, cudaMemcpyHostToDevice, ctx->stream));
+    k_halton_sample<<<grid_for(n, 256), 256, 0, ctx->stream>>>(ctx->S, n, ctx->w0.as<uint32_t>(), ctx->w1.as<uint32_t>(), ctx->w2.as<float>());
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(out, ctx->w2.p, n * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return GI_OK;
+}
+
+extern "C" int gi_halton_index(gi_ctx* ctx, int width, int height, size_t n, const uint32_t* s, const uint32_t* x, const uint32_t* y, uint32_t* out)
+{
+    if (!ctx || width <= 0 || height <= 0 || (n && (!s || !x || !y || !out))) return GI_ERR_INVALID;
+    if (!n) return GI_OK;
+    CK(cudaSetDevice(ctx->device));
+    CK(ctx->w0.reserve(n * 4)); CK(ctx->w1.reserve(n * 4)); CK(ctx->w2.reserve(n * 4)); CK(ctx->w3.reserve(n * 4));
+    CK(cudaMemcpyAsync(ctx->w0.p, s, n * 4, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->w1.p, x, n * 4, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->w2.p, y, n * 4, cudaMemcpyHostToDevice, ctx->stream));
+    k_halton_index<<<grid_for(n, 256), 256, 0, ctx->stream>>>(make_henum((uint32_t)width, (uint32_t)height), n, ctx->w0.as<uint32_t>(), ctx->w1.as<uint32_t>(), ctx->w2.as<uint32_t>(), ctx->w3.as<uint32_t>());
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(out, ctx->w3.p, n * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return GI_OK;
+}
+
+extern "C" int gi_camera_rays(gi_ctx* ctx, int width, int height, int x0, int y0, int x1, int y1, int s0, int s1, double* org, double* dir, uint32_t* index)
+{
+    if (!ctx || width <= 0 || height <= 0 || x1 <= x0 || y1 <= y0 || s1 <= s0 || !org || !dir) return GI_ERR_INVALID;
+    if (!ctx->has_scene) return fail(ctx, GI_ERR_NO_SCENE, "gi_camera_rays needs gi_scene_upload (camera)");
+    CK(cudaSetDevice(ctx->device));
+    size_t n = (size_t)(x1 - x0) * (y1 - y0) * (s1 - s0);
+    CK(ctx->w0.reserve(n * 24)); CK(ctx->w1.reserve(n * 24)); CK(ctx->w2.reserve(n * 4));
+    DFrame F = make_frame(ctx, width, height, x0, y0, x1, y1);
+    k_camera_rays<<<grid_for(n, 256), 256, 0, ctx->stream>>>(ctx->S, F, s0, n, ctx->w0.as<double>(), ctx->w1.as<double>(), ctx->w2.as<uint32_t>());
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(org, ctx->w0.p, n * 24, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaMemcpyAsync(dir, ctx->w1.p, n * 24, cudaMemcpyDeviceToHost, ctx->stream));
+    if (index) CK(cudaMemcpyAsync(index, ctx->w2.p, n * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return GI_OK;
+}
+
+// ---- closest / any hit ------------------------------------------------------------------------------------------------------------------
+extern "C" int gi_trace_closest_dev(gi_ctx* ctx, size_t n, const double* org, const double* dir, uint64_t alpha_seed, uint32_t* prim, double* hit, double* normal, double* uv)
+{
+    if (!ctx || (n && (!org || !dir))) return GI_ERR_INVALID;
+    if (!ctx->has_scene) return fail(ctx, GI_ERR_NO_SCENE, "gi_trace_closest needs gi_scene_upload");
+    if (!n) return GI_OK;
+    CK(cudaSetDevice(ctx->device));
+    fam_reset(ctx, "trace_closest");
+    {
+        ScopedTimer t(ctx, "trace_closest");
+        if (ctx->S.full) k_trace_closest<true><<<grid_for(n, GI_BLOCK), GI_BLOCK, 0, ctx->stream>>>(ctx->S, n, org, dir, alpha_seed, prim, hit, normal, uv);
+        else k_trace_closest<false><<<grid_for(n, GI_BLOCK), GI_BLOCK, 0, ctx->stream>>>(ctx->S, n, org, dir, alpha_seed, prim, hit, normal, uv);
+    }
+    CK(cudaGetLastError());
+    return GI_OK;
+}
+extern "C" int gi_trace_closest(gi_ctx* ctx, size_t n, const double* org, const double* dir, uint64_t alpha_seed, uint32_t* prim, double* hit, double* normal, double* uv)
+{
+    if (!ctx || (n && (!org || !dir))) return GI_ERR_INVALID;
+    if (!ctx->has_scene) return fail(ctx, GI_ERR_NO_SCENE, "gi_trace_closest needs gi_scene_upload");
+    if (!n) return GI_OK;
+    CK(cudaSetDevice(ctx->device));
+    CK(ctx->w0.reserve(n * 24)); CK(ctx->w1.reserve(n * 24)); CK(ctx->w2.reserve(n * 4)); CK(ctx->w3.reserve(n * 24)); CK(ctx->w4.reserve(n * 24)); CK(ctx->w5.reserve(n * 16));
+    CK(cudaMemcpyAsync(ctx->w0.p, org, n * 24, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->w1.p, dir, n * 24, cudaMemcpyHostToDevice, ctx->stream));
+    int rc = gi_trace_closest_dev(ctx, n, ctx->w0.as<double>(), ctx->w1.as<double>(), alpha_seed, ctx->w2.as<uint32_t>(), hit ? ctx->w3.as<double>() : nullptr,
+                                  normal ? ctx->w4.as<double>() : nullptr, uv ? ctx->w5.as<double>() : nullptr);
+    if (rc != GI_OK) return rc;
+    if (prim) CK(cudaMemcpyAsync(prim, ctx->w2.p, n * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    if (hit) CK(cudaMemcpyAsync(hit, ctx->w3.p, n * 24, cudaMemcpyDeviceToHost, ctx->stream));
+    if (normal) CK(cudaMemcpyAsync(normal, ctx->w4.p, n * 24, cudaMemcpyDeviceToHost, ctx->stream));
+    if (uv) CK(cudaMemcpyAsync(uv, ctx->w5.p, n * 16, cudaMemcpyDeviceToHost, ctx->stream));
+    return gi_synchronize(ctx);
+}
+
+extern "C" int gi_trace_any_dev(gi_ctx* ctx, size_t n, const double* org, const double* dir, const double* maxt2, uint64_t alpha_seed, uint8_t* vis)
+{
+    if (!ctx || (n && (!org || !dir || !maxt2 || !vis))) return GI_ERR_INVALID;
+    if (!ctx->has_scene) return fail(ctx, GI_ERR_NO_SCENE, "gi_trace_any needs gi_scene_upload");
+    if (!n) return GI_OK;
+    CK(cudaSetDevice(ctx->device));
+    fam_reset(ctx, "trace_any");
+    {
+        ScopedTimer t(ctx, "trace_any");
+        if (ctx->S.full) k_trace_any<true><<<grid_for(n, GI_BLOCK), GI_BLOCK, 0, ctx->stream>>>(ctx->S, n, org, dir, maxt2, alpha_seed, vis);
+        else k_trace_any<false><<<grid_for(n, GI_BLOCK), GI_BLOCK, 0, ctx->stream>>>(ctx->S, n, org, dir, maxt2, alpha_seed, vis);
+    }
+    CK(cudaGetLastError());
+    return GI_OK;
+}
+extern "C" int gi_trace_any(gi_ctx* ctx, size_t n, const double* org, const double* dir, const double* maxt2, uint64_t alpha_seed, uint8_t* vis)
+{
+    if (!ctx || (n && (!org || !dir || !maxt2 || !vis))) return GI_ERR_INVALID;
+    if (!ctx->has_scene) return fail(ctx, GI_ERR_NO_SCENE, "gi_trace_any needs gi_scene_upload");
+    if (!n) return GI_OK;
+    CK(cudaSetDevice(ctx->device));
+    CK(ctx->w0.reserve(n * 24)); CK(ctx->w1.reserve(n * 24)); CK(ctx->w2.reserve(n * 8)); CK(ctx->w3.reserve(n));
+    CK(cudaMemcpyAsync(ctx->w0.p, org, n * 24, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->w1.p, dir, n * 24, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->w2.p, maxt2, n * 8, cudaMemcpyHostToDevice, ctx->stream));
+    int rc = gi_trace_any_dev(ctx, n, ctx->w0.as<double>(), ctx->w1.as<double>(), ctx->w2.as<double>(), alpha_seed, ctx->w3.as<uint8_t>());
+    if (rc != GI_OK) return rc;
+    CK(cudaMemcpyAsync(vis, ctx->w3.p, n, cudaMemcpyDeviceToHost, ctx->stream));
+    return gi_synchronize(ctx);
+}
+
+// ---- device-side exclusive scan helper (k_scan_*) -----------------------------------------------------------------------------------------
+static int scan_exclusive(gi_ctx* ctx, const uint32_t* in, int stride_words, uint32_t n, uint32_t* out, uint32_t* total_dev)
+{
+    uint32_t nb = (n + GI_SCAN_BLOCK - 1) / GI_SCAN_BLOCK;
+    CK(ctx->b_scan1.reserve((size_t)std::max<uint32_t>(nb, 1) * 4));
+    if (n) {
+        k_scan_block<<<nb, GI_SCAN_BLOCK, 0, ctx->stream>>>(in, n, out, ctx->b_scan1.as<uint32_t>(), stride_words);
+        k_scan_sums<<<1, 1, 0, ctx->stream>>>(ctx->b_scan1.as<uint32_t>(), nb, total_dev);
+        k_scan_apply<<<nb, GI_SCAN_BLOCK, 0, ctx->stream>>>(out, n, ctx->b_scan1.as<uint32_t>());
+    } else if (total_dev) CK(cudaMemsetAsync(total_dev, 0, 4, ctx->stream));
+    CK(cudaGetLastError());
+    return GI_OK;
+}
+
+// ---- photons ------------------------------------------------------------------------------------------------------------------------------
+extern "C" int gi_photon_upload(gi_ctx* ctx, size_t n, const double* photons9)
+{
+    if (!ctx || (n && !photons9)) return GI_ERR_INVALID;
+    CK(cudaSetDevice(ctx->device));
+    CK(ctx->b_photons.reserve(std::max<size_t>(n, 1) * 72));
+    if (n) CK(cudaMemcpyAsync(ctx->b_photons.p, photons9, n * 72, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    ctx->n_photons = n;
+    ctx->has_map = false;
+    return GI_OK;
+}
+extern "C" int gi_photon_count(gi_ctx* ctx, size_t* n)
+{
+    if (!ctx || !n) return GI_ERR_INVALID;
+    *n = ctx->n_photons;
+    return GI_OK;
+}
+extern "C" int gi_photon_download(gi_ctx* ctx, size_t n, double* photons9)
+{
+    if (!ctx || (n && !photons9) || n > ctx->n_photons) return GI_ERR_INVALID;
+    CK(cudaSetDevice(ctx->device));
+    if (n) CK(cudaMemcpyAsync(photons9, ctx->b_photons.p, n * 72, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return GI_OK;
+}
+
+extern "C" int gi_photon_trace(gi_ctx* ctx, int count, int max_depth, uint64_t seed, uint64_t* n_stored, gi_stats* stats)
+{
+    if (!ctx || count < 0 || max_depth < 0) return GI_ERR_INVALID;
+    if (!ctx->has_scene) return fail(ctx, GI_ERR_NO_SCENE, "gi_photon_trace needs gi_scene_upload");
+    CK(cudaSetDevice(ctx->device));
+    size_t slots = (size_t)count * ctx->S.n_lights;
+    ctx->has_map = false;
+    ctx->n_photons = 0;
+    if (stats) std::memset(stats, 0, sizeof(*stats));
+    if (n_stored) *n_stored = 0;
+    if (!slots) return GI_OK;
+    if (slots > 0xFFFFFFF0ull) return fail(ctx, GI_ERR_INVALID, "too many photons");
+    CK(ctx->w0.reserve(slots * 72)); CK(ctx->w1.reserve(slots)); CK(ctx->w2.reserve(slots * 4)); CK(ctx->b_scan0.reserve(slots * 4)); CK(ctx->b_misc.reserve(64));
+    CK(ctx->b_photons.reserve(slots * 72));
+    CK(cudaMemsetAsync(ctx->w1.p, 0, slots, ctx->stream));
+    CK(cudaMemsetAsync(ctx->b_misc.p, 0, 64, ctx->stream));
+    DPhotonOut O{ ctx->w0.as<double>(), ctx->w1.as<uint8_t>(), ctx->b_misc.as<unsigned long long>(), ctx->b_misc.as<unsigned long long>() + 1 };
+    fam_reset(ctx, "photon_trace");
+    cudaEvent_t e0 = get_event(ctx), e1 = get_event(ctx);
+    cudaEventRecord(e0, ctx->stream);
+    {
+        ScopedTimer t(ctx, "photon_trace");
+        if (ctx->S.full) k_photon_trace<true><<<grid_for(count, GI_BLOCK), GI_BLOCK, 0, ctx->stream>>>(ctx->S, count, max_depth, seed, O);
+        else k_photon_trace<false><<<grid_for(count, GI_BLOCK), GI_BLOCK, 0, ctx->stream>>>(ctx->S, count, max_depth, seed, O);
+    }
+    CK(cudaGetLastError());
+    // canonical (i, light) order: flags -> exclusive scan -> scatter
+    k_flags_to_u32<<<grid_for(slots, 256), 256, 0, ctx->stream>>>(ctx->w1.as<uint8_t>(), (uint32_t)slots, ctx->w2.as<uint32_t>());
+    uint32_t* total_dev = reinterpret_cast<uint32_t*>(ctx->b_misc.as<unsigned long long>() + 2);
+    int rc = scan_exclusive(ctx, ctx->w2.as<uint32_t>(), 1, (uint32_t)slots, ctx->b_scan0.as<uint32_t>(), total_dev);
+    if (rc != GI_OK) return rc;
+    k_photon_compact<<<grid_for(slots, 256), 256, 0, ctx->stream>>>(ctx->w0.as<double>(), ctx->w1.as<uint8_t>(), ctx->b_scan0.as<uint32_t>(), (uint32_t)slots, ctx->b_photons.as<double>());
+    CK(cudaGetLastError());
+    cudaEventRecord(e1, ctx->stream);
+    unsigned long long host[3];
+    CK(cudaMemcpyAsync(host, ctx->b_misc.p, 24, cudaMemcpyDeviceToHost, ctx->stream));
+    rc = gi_synchronize(ctx);
+    if (rc != GI_OK) return rc;
+    float ms = 0; cudaEventElapsedTime(&ms, e0, e1);
+    ctx->event_pool.push_back(e0); ctx->event_pool.push_back(e1);
+    ctx->n_photons = (uint32_t)host[2];
+    if (n_stored) *n_stored = ctx->n_photons;
+    if (stats) { stats->photon_tries = host[0]; stats->closest_rays = host[1]; stats->photons_stored = ctx->n_photons; stats->kernel_launches = 6; stats->total_ms = ms; stats->trace_ms = ctx->fam["photon_trace"].ms; }
+    return GI_OK;
+}
+
+// ---- photon map ---------------------------------------------------------------------------------------------------------------------------
+struct SlabHeader { uint32_t magic, n_nodes, n_kept, n_leaves, max_depth, pad[3]; uint64_t off_nodes, off_pos, off_dircol, off_pid, total; };
+#define GI_SLAB_MAGIC 0x47495031u   // "GIP1"
+static inline size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
+
+static void bind_slab(gi_ctx* ctx, const SlabHeader& h)
+{
+    char* base = ctx->b_slab.as<char>();
+    ctx->G.nodes = reinterpret_cast<const DNode*>(base + h.off_nodes);
+    ctx->G.pos = reinterpret_cast<const double*>(base + h.off_pos);
+    ctx->G.dircol = reinterpret_cast<const double*>(base + h.off_dircol);
+    ctx->G.pid = reinterpret_cast<const uint32_t*>(base + h.off_pid);
+    ctx->G.n_nodes = h.n_nodes;
+    ctx->pm_nodes = h.n_nodes; ctx->pm_kept = h.n_kept; ctx->pm_leaves = h.n_leaves; ctx->pm_depth = h.max_depth;
+    ctx->slab_bytes = h.total;
+    ctx->has_map = true;
+}
+
+extern "C" int gi_photon_map_build(gi_ctx* ctx, const double* box6)
+{
+    if (!ctx) return GI_ERR_INVALID;
+    if (!box6 && !ctx->has_scene) return fail(ctx, GI_ERR_NO_SCENE, "gi_photon_map_build needs a root box (scene or box6)");
+    CK(cudaSetDevice(ctx->device));
+    const uint32_t n = (uint32_t)ctx->n_photons;
+    double box[6];
+    for (int k = 0; k < 6; k++) box[k] = box6 ? box6[k] : ctx->root_box[k];
+    const uint32_t cap_nodes = std::max<uint32_t>(4u * n + 1024u, 1024u);
+    // build workspace
+    CK(ctx->w0.reserve((size_t)cap_nodes * sizeof(DNode)));    // nodes
+    CK(ctx->w1.reserve(std::max<size_t>(n, 1) * 4));           // pnode
+    CK(ctx->w2.reserve(std::max<size_t>(n, 1) * 4));           // pid (leaf order)
+    CK(ctx->w3.reserve(64));                                   // counters: n_nodes, n_kept, overflow
+    CK(ctx->w4.reserve(48));                                   // box
+    CK(ctx->b_photons.reserve(72));
+    CK(cudaMemcpyAsync(ctx->w4.p, box, 48, cudaMemcpyHostToDevice, ctx->stream));
+    DPMap M{};
+    M.nodes = ctx->w0.as<DNode>(); M.n_nodes = ctx->w3.as<uint32_t>(); M.cap_nodes = cap_nodes; M.ph = ctx->b_photons.as<double>(); M.n_photons = n;
+    M.pnode = ctx->w1.as<uint32_t>(); M.pid = ctx->w2.as<uint32_t>(); M.n_kept = ctx->w3.as<uint32_t>() + 1; M.overflow = ctx->w3.as<uint32_t>() + 2;
+    fam_reset(ctx, "pm_build");
+    cudaEvent_t e0 = get_event(ctx), e1 = get_event(ctx);
+    cudaEventRecord(e0, ctx->stream);
+    k_pm_init<<<grid_for(std::max<uint32_t>(n, 1), 256), 256, 0, ctx->stream>>>(M, ctx->w4.as<double>());
+    CK(cudaGetLastError());
+    uint32_t lb = 0, le = 1, depth = 0;
+    uint32_t host_cnt[3] = { 1, 0, 0 };
+    while (le > lb && depth < 128) {
+        k_pm_split<<<grid_for(le - lb, 128), 128, 0, ctx->stream>>>(M, lb, le);
+        if (n) k_pm_assign<<<grid_for(n, 256), 256, 0, ctx->stream>>>(M, lb, le);
+        CK(cudaGetLastError());
+        CK(cudaMemcpyAsync(host_cnt, ctx->w3.p, 12, cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+        if (host_cnt[2]) return fail(ctx, GI_ERR_OOM, "photon map node pool exhausted");
+        lb = le; le = host_cnt[0];
+        if (le > lb) depth++;
+    }
+    const uint32_t n_nodes = host_cnt[0];
+    // leaf offsets = exclusive scan of the per-node counts (interior nodes hold 0)
+    CK(ctx->b_scan0.reserve((size_t)n_nodes * 4)); CK(ctx->w5.reserve((size_t)n_nodes * 4));
+    int rc = scan_exclusive(ctx, &M.nodes[0].prim_cnt, (int)(sizeof(DNode) / 4), n_nodes, ctx->b_scan0.as<uint32_t>(), M.n_kept);
+    if (rc != GI_OK) return rc;
+    k_pm_set_offsets<<<grid_for(n_nodes, 256), 256, 0, ctx->stream>>>(M, n_nodes, ctx->b_scan0.as<uint32_t>(), ctx->w5.as<uint32_t>());
+    if (n) k_pm_scatter<<<grid_for(n, 256), 256, 0, ctx->stream>>>(M, ctx->w5.as<uint32_t>());
+    k_pm_order_leaf<<<grid_for(n_nodes, 128), 128, 0, ctx->stream>>>(M, n_nodes);
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(host_cnt, ctx->w3.p, 12, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    const uint32_t n_kept = host_cnt[1];
+    // compact slab: header | nodes | pos | dircol | pid
+    SlabHeader h{};
+    h.magic = GI_SLAB_MAGIC; h.n_nodes = n_nodes; h.n_kept = n_kept; h.max_depth = depth;
+    h.off_nodes = 256; h.off_pos = align256(h.off_nodes + (size_t)n_nodes * sizeof(DNode)); h.off_dircol = align256(h.off_pos + (size_t)n_kept * 24);
+    h.off_pid = align256(h.off_dircol + (size_t)n_kept * 48); h.total = align256(h.off_pid + (size_t)n_kept * 4);
+    CK(ctx->b_slab.reserve(h.total));
+    char* base = ctx->b_slab.as<char>();
+    CK(cudaMemcpyAsync(base + h.off_nodes, M.nodes, (size_t)n_nodes * sizeof(DNode), cudaMemcpyDeviceToDevice, ctx->stream));
+    if (n_kept) CK(cudaMemcpyAsync(base + h.off_pid, M.pid, (size_t)n_kept * 4, cudaMemcpyDeviceToDevice, ctx->stream));
+    M.pos = reinterpret_cast<double*>(base + h.off_pos); M.dircol = reinterpret_cast<double*>(base + h.off_dircol);
+    if (n_kept) k_pm_payload<<<grid_for(n_kept, 256), 256, 0, ctx->stream>>>(M, n_kept);
+    CK(cudaGetLastError());
+    // leaves are counted on the host from the node records (also validates the build)
+    std::vector<DNode> hn(n_nodes);
+    CK(cudaMemcpyAsync(hn.data(), M.nodes, (size_t)n_nodes * sizeof(DNode), cudaMemcpyDeviceToHost, ctx->stream));
+    cudaEventRecord(e1, ctx->stream);
+    CK(cudaStreamSynchronize(ctx->stream));
+    uint32_t leaves = 0;
+    for (auto& nd : hn) if (nd.mask == 0) leaves++;
+    h.n_leaves = leaves;
+    CK(cudaMemcpyAsync(base, &h, sizeof(h), cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    float ms = 0; cudaEventElapsedTime(&ms, e0, e1);
+    ctx->event_pool.push_back(e0); ctx->event_pool.push_back(e1);
+    ctx->fam["pm_build"].ms = ms; ctx->fam["pm_build"].launches = 1;
+    bind_slab(ctx, h);
+    return GI_OK;
+}
+
+extern "C" int gi_photon_map_info(gi_ctx* ctx, uint32_t* n_nodes, uint32_t* n_leaves, uint32_t* n_kept, uint32_t* max_depth)
+{
+    if (!ctx) return GI_ERR_INVALID;
+    if (!ctx->has_map) return fail(ctx, GI_ERR_NO_PHOTONS, "no photon map");
+    if (n_nodes) *n_nodes = ctx->pm_nodes;
+    if (n_leaves) *n_leaves = ctx->pm_leaves;
+    if (n_kept) *n_kept = ctx->pm_kept;
+    if (max_depth) *max_depth = ctx->pm_depth;
+    return GI_OK;
+}
+
+extern "C" int gi_photon_map_download(gi_ctx* ctx, double* node_box6, uint8_t* node_is_leaf, uint32_t* node_count, uint32_t* photon_ids)
+{
+    if (!ctx) return GI_ERR_INVALID;
+    if (!ctx->has_map) return fail(ctx, GI_ERR_NO_PHOTONS, "no photon map");
+    CK(cudaSetDevice(ctx->device));
+    std::vector<DNode> hn(ctx->pm_nodes);
+    std::vector<uint32_t> pid(std::max<uint32_t>(ctx->pm_kept, 1));
+    CK(cudaMemcpy(hn.data(), ctx->G.nodes, (size_t)ctx->pm_nodes * sizeof(DNode), cudaMemcpyDeviceToHost));
+    if (ctx->pm_kept) CK(cudaMemcpy(pid.data(), ctx->G.pid, (size_t)ctx->pm_kept * 4, cudaMemcpyDeviceToHost));
+    // DFS pre-order, children 0..7, like the reference's recursion
+    std::vector<uint32_t> st = { 0 };
+    size_t ni = 0, pi = 0;
+    while (!st.empty()) {
+        uint32_t i = st.back(); st.pop_back();
+        const DNode& nd = hn[i];
+        if (node_box6) for (int k = 0; k < 3; k++) { node_box6[6 * ni + k] = nd.bmin[k]; node_box6[6 * ni + 3 + k] = nd.bmax[k]; }
+        if (node_is_leaf) node_is_leaf[ni] = nd.mask == 0;
+        if (node_count) node_count[ni] = nd.prim_cnt;
+        ni++;
+        if (nd.mask == 0) { if (photon_ids) for (uint32_t k = 0; k < nd.prim_cnt; k++) photon_ids[pi + k] = pid[nd.prim_off + k]; pi += nd.prim_cnt; }
+        else for (int c = 7; c >= 0; c--) st.push_back(nd.child + c);
+    }
+    return GI_OK;
+}
+
+extern "C" int gi_photon_map_slab_size(gi_ctx* ctx, size_t* bytes)
+{
+    if (!ctx || !bytes) return GI_ERR_INVALID;
+    if (!ctx->has_map) return fail(ctx, GI_ERR_NO_PHOTONS, "no photon map");
+    *bytes = ctx->slab_bytes;
+    return GI_OK;
+}
+extern "C" int gi_photon_map_slab_ptr(gi_ctx* ctx, void** dev_ptr)
+{
+    if (!ctx || !dev_ptr) return GI_ERR_INVALID;
+    if (!ctx->has_map) return fail(ctx, GI_ERR_NO_PHOTONS, "no photon map");
+    *dev_ptr = ctx->b_slab.p;
+    return GI_OK;
+}
+extern "C" int gi_photon_map_reserve_slab(gi_ctx* ctx, size_t bytes, void** dev_ptr)
+{
+    if (!ctx || !dev_ptr || bytes < 256) return GI_ERR_INVALID;
+    CK(cudaSetDevice(ctx->device));
+    ctx->has_map = false;
+    CK(ctx->b_slab.reserve(bytes));
+    *dev_ptr = ctx->b_slab.p;
+    return GI_OK;
+}
+extern "C" int gi_photon_map_adopt_slab(gi_ctx* ctx, size_t bytes)
+{
+    if (!ctx || bytes < 256 || bytes > ctx->b_slab.cap) return GI_ERR_INVALID;
+    CK(cudaSetDevice(ctx->device));
+    SlabHeader h;
+    CK(cudaMemcpy(&h, ctx->b_slab.p, sizeof(h), cudaMemcpyDeviceToHost));
+    if (h.magic != GI_SLAB_MAGIC || h.total != bytes || h.off_pid + (uint64_t)h.n_kept * 4 > bytes) return fail(ctx, GI_ERR_INVALID, "bad photon map slab");
+    bind_slab(ctx, h);
+    return GI_OK;
+}
+
+// ---- gather ---------------------------------------------------------------------------------------------------------------------------------
+#define GI_GATHER_WARPS 4
+extern "C" int gi_photon_gather_dev(gi_ctx* ctx, size_t n, const double* pos, const double* dir, int k, double* rgb, uint32_t* knn, uint32_t* n_cand)
+{
+    if (!ctx || (n && (!pos || !dir)) || k < 1 || k > 32) return GI_ERR_INVALID;
+    if (!ctx->has_map) return fail(ctx, GI_ERR_NO_PHOTONS, "gi_photon_gather needs gi_photon_map_build");
+    if (!n) return GI_OK;
+    CK(cudaSetDevice(ctx->device));
+    fam_reset(ctx, "gather");
+    {
+        ScopedTimer t(ctx, "gather");
+        k_gather<GI_GATHER_WARPS><<<grid_for(n, GI_GATHER_WARPS), GI_GATHER_WARPS * 32, 0, ctx->stream>>>(ctx->G, n, pos, dir, k, rgb, knn, n_cand, nullptr, nullptr, nullptr);
+    }
+    CK(cudaGetLastError());
+    return GI_OK;
+}
+extern "C" int gi_photon_gather(gi_ctx* ctx, size_t n, const double* pos, const double* dir, int k, double* rgb, uint32_t* knn, uint32_t* n_cand)
+{
+    if (!ctx || (n && (!pos || !dir)) || k < 1 || k > 32) return GI_ERR_INVALID;
+    if (!ctx->has_map) return fail(ctx, GI_ERR_NO_PHOTONS, "gi_photon_gather needs gi_photon_map_build");
+    if (!n) return GI_OK;
+    CK(cudaSetDevice(ctx->device));
+    CK(ctx->w0.reserve(n * 24)); CK(ctx->w1.reserve(n * 24)); CK(ctx->w2.reserve(n * 24)); CK(ctx->w3.reserve(n * 4 * (size_t)k)); CK(ctx->w4.reserve(n * 4));
+    CK(cudaMemcpyAsync(ctx->w0.p, pos, n * 24, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->w1.p, dir, n * 24, cudaMemcpyHostToDevice, ctx->stream));
+    int rc = gi_photon_gather_dev(ctx, n, ctx->w0.as<double>(), ctx->w1.as<double>(), k, ctx->w2.as<double>(), knn ? ctx->w3.as<uint32_t>() : nullptr, n_cand ? ctx->w4.as<uint32_t>() : nullptr);
+    if (rc != GI_OK) return rc;
+    if (rgb) CK(cudaMemcpyAsync(rgb, ctx->w2.p, n * 24, cudaMemcpyDeviceToHost, ctx->stream));
+    if (knn) CK(cudaMemcpyAsync(knn, ctx->w3.p, n * 4 * (size_t)k, cudaMemcpyDeviceToHost, ctx->stream));
+    if (n_cand) CK(cudaMemcpyAsync(n_cand, ctx->w4.p, n * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    return gi_synchronize(ctx);
+}
+
+// ---- frame ------------------------------------------------------------------------------------------------------------------------------------
+static int render_device(gi_ctx* ctx, const gi_render_params* P, int x0, int y0, int x1, int y1, int s0, int s1, double* accum_dev, gi_stats* stats)
+{
+    const size_t npx = (size_t)(x1 - x0) * (y1 - y0);
+    const uint64_t total_paths = (uint64_t)npx * (uint64_t)(s1 - s0);
+    const uint32_t chunk_cap = (uint32_t)std::min<uint64_t>(total_paths, GI_MAX_PATHS);
+    // queues (double buffered), hit list, per-path state
+    for (int b = 0; b < 4; b++) { CK(ctx->q_a[b].reserve((size_t)chunk_cap * 24)); CK(ctx->q_b[b].reserve((size_t)chunk_cap * 24)); }
+    CK(ctx->q_a[4].reserve((size_t)chunk_cap * 4)); CK(ctx->q_b[4].reserve((size_t)chunk_cap * 4));
+    for (int b = 0; b < 5; b++) CK(ctx->hl[b].reserve((size_t)chunk_cap * 24));
+    CK(ctx->hl[5].reserve((size_t)chunk_cap * 8)); CK(ctx->hl[6].reserve((size_t)chunk_cap * 4));
+    CK(ctx->ps[0].reserve((size_t)chunk_cap * 4)); CK(ctx->ps[1].reserve((size_t)chunk_cap * 8)); CK(ctx->ps[2].reserve((size_t)chunk_cap * 24));
+    CK(ctx->b_cnt.reserve(sizeof(DCounters)));
+    DQueue qa{ ctx->q_a[0].as<double>(), ctx->q_a[1].as<double>(), ctx->q_a[2].as<double>(), ctx->q_a[3].as<double>(), ctx->q_a[4].as<uint32_t>() };
+    DQueue qb{ ctx->q_b[0].as<double>(), ctx->q_b[1].as<double>(), ctx->q_b[2].as<double>(), ctx->q_b[3].as<double>(), ctx->q_b[4].as<uint32_t>() };
+    DHitList H{ ctx->hl[0].as<double>(), ctx->hl[1].as<double>(), ctx->hl[2].as<double>(), ctx->hl[3].as<double>(), ctx->hl[4].as<double>(), ctx->hl[5].as<double>(), ctx->hl[6].as<uint32_t>() };
+    DPathState PS{ ctx->ps[0].as<uint32_t>(), ctx->ps[1].as<uint64_t>(), ctx->ps[2].as<double>() };
+    DCounters* C = ctx->b_cnt.as<DCounters>();
+    DFrame F = make_frame(ctx, P->width, P->height, x0, y0, x1, y1);
+    const bool full = ctx->S.full != 0;
+    const bool have_map = ctx->has_map && ctx->pm_kept > 0;
+    uint64_t n_closest = 0, n_shadow = 0, n_gather = 0, launches = 0;
+    for (const char* f : { "bounce", "direct", "gather" }) fam_reset(ctx, f);
+    cudaEvent_t e0 = get_event(ctx), e1 = get_event(ctx);
+    cudaEventRecord(e0, ctx->stream);
+    CK(cudaMemsetAsync(accum_dev, 0, npx * 24, ctx->stream));
+    for (uint64_t c0 = 0; c0 < total_paths; c0 += chunk_cap) {
+        uint32_t n = (uint32_t)std::min<uint64_t>(chunk_cap, total_paths - c0);
+        k_generate<<<grid_for(n, 256), 256, 0, ctx->stream>>>(ctx->S, F, s0, c0, n, qa, PS);
+        launches++;
+        DQueue in = qa, out = qb;
+        uint32_t n_active = n;
+        for (int depth = 0; n_active > 0 && depth <= P->max_depth; depth++) {
+            CK(cudaMemsetAsync(C, 0, sizeof(DCounters), ctx->stream));
+            {
+                ScopedTimer t(ctx, "bounce");
+                if (full) k_bounce<true><<<grid_for(n_active, GI_BLOCK), GI_BLOCK, 0, ctx->stream>>>(ctx->S, *P, depth, n_active, in, out, H, PS, C);
+                else k_bounce<false><<<grid_for(n_active, GI_BLOCK), GI_BLOCK, 0, ctx->stream>>>(ctx->S, *P, depth, n_active, in, out, H, PS, C);
+            }
+            CK(cudaGetLastError());
+            DCounters hc;
+            CK(cudaMemcpyAsync(&hc, C, sizeof(DCounters), cudaMemcpyDeviceToHost, ctx->stream));
+            CK(cudaStreamSynchronize(ctx->stream));
+            launches++;
+            n_closest += n_active;
+            if (hc.n_hits) {
+                if (ctx->S.n_lights) {
+                    ScopedTimer t(ctx, "direct");
+                    if (full) k_direct<true><<<grid_for(hc.n_hits, GI_BLOCK), GI_BLOCK, 0, ctx->stream>>>(ctx->S, *P, depth, hc.n_hits, H, PS);
+                    else k_direct<false><<<grid_for(hc.n_hits, GI_BLOCK), GI_BLOCK, 0, ctx->stream>>>(ctx->S, *P, depth, hc.n_hits, H, PS);
+                    launches++;
+                    n_shadow += (uint64_t)hc.n_hits * ctx->S.n_lights;
+                }
+                if (depth <= P->caustic_max_depth) {
+                    n_gather += hc.n_hits;   // samplePhotons is called whether or not photons exist (raytracer.h:258)
+                    if (have_map) {
+                        ScopedTimer t(ctx, "gather");
+                        k_gather<GI_GATHER_WARPS><<<grid_for(hc.n_hits, GI_GATHER_WARPS), GI_GATHER_WARPS * 32, 0, ctx->stream>>>(ctx->G, hc.n_hits, H.p, H.refdir, P->k_photons, nullptr, nullptr,
+                                                                                                                          nullptr, H.wcaustic, PS.L, H.path);
+                        launches++;
+                    }
+                }
+                CK(cudaGetLastError());
+            }
+            n_active = hc.n_next;
+            std::swap(in, out);
+        }
+        k_accumulate<<<grid_for(npx, 256), 256, 0, ctx->stream>>>(c0, n, npx, PS.L, accum_dev);
+        launches++;
+        CK(cudaGetLastError());
+    }
+    cudaEventRecord(e1, ctx->stream);
+    int rc = gi_synchronize(ctx);
+    if (rc != GI_OK) return rc;
+    float ms = 0; cudaEventElapsedTime(&ms, e0, e1);
+    ctx->event_pool.push_back(e0); ctx->event_pool.push_back(e1);
+    if (stats) {
+        std::memset(stats, 0, sizeof(*stats));
+        stats->closest_rays = n_closest; stats->shadow_rays = n_shadow; stats->gathers = n_gather; stats->kernel_launches = launches;
+        stats->trace_ms = ctx->fam["bounce"].ms; stats->shadow_ms = ctx->fam["direct"].ms; stats->gather_ms = ctx->fam["gather"].ms; stats->total_ms = ms;
+    }
+    return GI_OK;
+}
+
+static int check_render_args(gi_ctx* ctx, const gi_render_params* P, int x0, int y0, int x1, int y1, int s0, int s1, const double* accum)
+{
+    if (!ctx || !P || !accum) return GI_ERR_INVALID;
+    if (P->width <= 0 || P->height <= 0 || x0 < 0 || y0 < 0 || x1 > P->width || y1 > P->height || x1 <= x0 || y1 <= y0 || s1 <= s0 || s0 < 0) return fail(ctx, GI_ERR_INVALID, "bad tile / sample range");
+    if (P->k_photons < 1 || P->k_photons > 32 || P->max_depth < 0 || P->max_depth > 126) return fail(ctx, GI_ERR_INVALID, "k_photons must be 1..32 and max_depth 0..126");
+    if (!ctx->has_scene) return fail(ctx, GI_ERR_NO_SCENE, "gi_render_tile needs gi_scene_upload");
+    return GI_OK;
+}
+
+extern "C" int gi_render_tile_dev(gi_ctx* ctx, const gi_render_params* P, int x0, int y0, int x1, int y1, int s0, int s1, double* accum, gi_stats* stats)
+{
+    int rc = check_render_args(ctx, P, x0, y0, x1, y1, s0, s1, accum);
+    if (rc != GI_OK) return rc;
+    CK(cudaSetDevice(ctx->device));
+    return render_device(ctx, P, x0, y0, x1, y1, s0, s1, accum, stats);
+}
+extern "C" int gi_render_tile(gi_ctx* ctx, const gi_render_params* P, int x0, int y0, int x1, int y1, int s0, int s1, double* accum, gi_stats* stats)
+{
+    int rc = check_render_args(ctx, P, x0, y0, x1, y1, s0, s1, accum);
+    if (rc != GI_OK) return rc;
+    CK(cudaSetDevice(ctx->device));
+    size_t npx = (size_t)(x1 - x0) * (y1 - y0);
+    CK(ctx->b_accum.reserve(npx * 24));
+    rc = render_device(ctx, P, x0, y0, x1, y1, s0, s1, ctx->b_accum.as<double>(), stats);
+    if (rc != GI_OK) return rc;
+    CK(cudaMemcpyAsync(accum, ctx->b_accum.p, npx * 24, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return GI_OK;
+}
+
+extern "C" int gi_resolve_dev(gi_ctx* ctx, size_t n_pixels, const double* accum, int spp, uint8_t* rgb8)
+{
+    if (!ctx || !accum || !rgb8 || spp <= 0) return GI_ERR_INVALID;
+    if (!n_pixels) return GI_OK;
+    CK(cudaSetDevice(ctx->device));
+    k_resolve<<<grid_for(n_pixels * 3, 256), 256, 0, ctx->stream>>>(n_pixels * 3, accum, spp, rgb8);
+    CK(cudaGetLastError());
+    return GI_OK;
+}
+extern "C" int gi_resolve(gi_ctx* ctx, size_t n_pixels, const double* accum, int spp, uint8_t* rgb8)
+{
+    if (!ctx || !accum || !rgb8 || spp <= 0) return GI_ERR_INVALID;
+    if (!n_pixels) return GI_OK;
+    CK(cudaSetDevice(ctx->device));
+    CK(ctx->w0.reserve(n_pixels * 24)); CK(ctx->w1.reserve(n_pixels * 3));
+    CK(cudaMemcpyAsync(ctx->w0.p, accum, n_pixels * 24, cudaMemcpyHostToDevice, ctx->stream));
+    int rc = gi_resolve_dev(ctx, n_pixels, ctx->w0.as<double>(), spp, ctx->w1.as<uint8_t>());
+    if (rc != GI_OK) return rc;
+    CK(cudaMemcpyAsync(rgb8, ctx->w1.p, n_pixels * 3, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return GI_OK;
+}

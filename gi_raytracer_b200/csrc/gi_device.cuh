@@ -1,0 +1,609 @@
+// gi_device.cuh — device-side building blocks of the B200 (sm_100a) hot path: fp64 vector math in the reference's
+// operation order, the counter PRNG, Halton sampling, slab / primitive tests, materials, samplers and the two octree
+// traversals.  Compiled with -fmad=false: no FMA contraction anywhere, so every fp64 result that the reference
+// computes without libm is reproduced bit-for-bit (SURVEY §7 "hard parts").  Reference file:line cited per function.
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+#include "../../include/gi_api.h"
+
+#define GI_D_EPSILON 0.00001     // util.h:18
+#define GI_D_SHADOW_BIAS 0.0001  // util.h:20
+#define GI_D_PI 3.14159265358979323846
+#define GI_STACK_MAX 96          // >= 3*depth+8 entries; octree depth is bounded by MIN_LEAF_SIZE (<= ~20 levels)
+
+// ---- device scene ------------------------------------------------------------------------------------------------------
+struct __align__(16) DNode {   // 64 B: one record per octree node (SURVEY §8d bytes model: 6 x fp64 box + 16 B topology)
+    double bmin[3], bmax[3];
+    uint32_t child;            // first existing child (children contiguous, reference child order)
+    uint32_t prim_off;         // first leaf reference
+    uint32_t prim_cnt;
+    uint32_t mask;             // bit i = child i exists; 0 = leaf
+};
+struct __align__(16) DLeafRef {  // 80 B: one record per (leaf, primitive) occurrence, stored in leaf order
+    double g[9];               // triangle v0,v1,v2 | sphere c,r | cone pos,rad,height
+    uint32_t prim;             // primitive id (insertion order)
+    uint32_t flags;            // bits 0-1 kind, bit 2 writes uv, bit 3 needs the stochastic alpha test
+};
+#define LF_KIND(f) ((f)&3u)
+#define LF_WRITES_UV 4u
+#define LF_ALPHA 8u
+
+struct DHaltonDim { uint32_t base, block, nblocks, table_off; float scale; };
+
+struct DScene {
+    const DNode* nodes;
+    const DLeafRef* refs;
+    uint32_t n_nodes, n_refs, n_prims;
+    const double* prim_geom;   // [n][9]
+    const double* prim_nrm;    // [n][9]
+    const double* prim_uv;     // [n][6]
+    const double* prim_fnorm;  // [n][3]
+    const uint32_t* prim_mat;
+    const uint8_t* prim_type;
+    const gi_material* mats;
+    const gi_texture* tex;
+    const uint8_t* tex_pixels;
+    const gi_light* lights;
+    uint32_t n_lights, n_mats, n_tex;
+    gi_camera cam;
+    double ambient[3];
+    const uint16_t* halton_tab;
+    const DHaltonDim* halton_dims;   // [256]
+    uint32_t full;                   // scene needs the FULL traversal (alpha materials or primitives that do not write uv)
+};
+
+// ---- fp64 vectors in glm's evaluation order -------------------------------------------------------------
+struct d3 { double x, y, z; };
+__device__ __forceinline__ d3 mk3(double x, double y, double z) { d3 r; r.x = x; r.y = y; r.z = z; return r; }
+__device__ __forceinline__ d3 ld3(const double* p) { return mk3(p[0], p[1], p[2]); }
+__device__ __forceinline__ void st3(double* p, d3 a) { p[0] = a.x; p[1] = a.y; p[2] = a.z; }
+__device__ __forceinline__ d3 operator+(d3 a, d3 b) { return mk3(a.x + b.x, a.y + b.y, a.z + b.z); }
+__device__ __forceinline__ d3 operator-(d3 a, d3 b) { return mk3(a.x - b.x, a.y - b.y, a.z - b.z); }
+__device__ __forceinline__ d3 operator*(d3 a, d3 b) { return mk3(a.x * b.x, a.y * b.y, a.z * b.z); }
+__device__ __forceinline__ d3 operator*(d3 a, double s) { return mk3(a.x * s, a.y * s, a.z * s); }
+__device__ __forceinline__ double dot3(d3 a, d3 b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
+__device__ __forceinline__ d3 cross3(d3 x, d3 y) { return mk3(x.y * y.z - y.y * x.z, x.z * y.x - y.z * x.x, x.x * y.y - y.x * x.y); }
+__device__ __forceinline__ d3 normalize3(d3 a) { return a * (1.0 / sqrt(dot3(a, a))); }
+__device__ __forceinline__ d3 reflect3(d3 I, d3 N) { double d = dot3(N, I); return I - (N * d) * 2.0; }
+__device__ __forceinline__ double len2(d3 a) { return a.x * a.x + a.y * a.y + a.z * a.z; }  // vecLengthSquared, util.h:35-38
+
+struct DRay { d3 o, d, inv; };
+// Ray::Ray -> setDir (ray.h:7-17)
+__device__ __forceinline__ DRay make_ray(d3 o, d3 dir_raw)
+{
+    DRay r; r.o = o; r.d = normalize3(dir_raw);
+    r.inv = mk3(1.0 / r.d.x, 1.0 / r.d.y, 1.0 / r.d.z);
+    return r;
+}
+__device__ __forceinline__ DRay ray_as_stored(d3 o, d3 dir)
+{
+    DRay r; r.o = o; r.d = dir;
+    r.inv = mk3(1.0 / dir.x, 1.0 / dir.y, 1.0 / dir.z);
+    return r;
+}
+
+// ---- counter PRNG (the specification the CPU checker restates too; replaces util.h:52-80) ----------------------------
+__host__ __device__ __forceinline__ uint64_t gi_mix64(uint64_t z)
+{
+    z += 0x9E3779B97F4A7C15ull;
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    return z ^ (z >> 31);
+}
+__host__ __device__ __forceinline__ double gi_rand(uint64_t seed, uint64_t path, uint64_t depth, uint64_t site)
+{
+    uint64_t h = gi_mix64(seed ^ gi_mix64(path ^ gi_mix64(depth ^ gi_mix64(site))));
+    return (double)(h >> 11) * (1.0 / 9007199254740992.0);
+}
+#define SITE_LIGHT_U 0ull
+#define SITE_LIGHT_V 1ull
+#define SITE_TYPE_A 2ull
+#define SITE_TYPE_B 3ull
+#define SITE_RR 4ull
+#define SITE_ALPHA_TRACE 5ull
+#define SITE_ALPHA_SHADOW 6ull
+#define SITE_PH_DIR_U 7ull
+#define SITE_PH_DIR_V 8ull
+#define SITE_PH_SEC_U 9ull
+#define SITE_PH_SEC_V 10ull
+#define SITE(s, c) (((uint64_t)(s) << 56) | (uint64_t)(c))
+#define PHOTON_PATH_BIT (1ull << 63)
+
+// ---- Halton (halton_sampler.h:626-888, 1417-3286) -----------------------------------------------------------------------
+__device__ __forceinline__ float halton_sample(const DScene& S, uint32_t dim, uint32_t index)
+{
+    if (dim == 0) {  // halton2: bit reversal into the mantissa (halton_sampler.h:1417-1431)
+        uint32_t rev = __brev(index);
+        return __uint_as_float(0x3f800000u | (rev >> 9)) - 1.f;
+    }
+    if (dim >= 256) return 0.f;
+    DHaltonDim D = S.halton_dims[dim];
+    const uint16_t* T = S.halton_tab + D.table_off;
+    uint32_t sum = 0, idx = index, mult = 1;
+    // digit block j (least significant first) is weighted by block^(n-1-j): accumulate with Horner from the top instead
+    // of the reference's explicit constants — identical u32 arithmetic (no overflow: the total is < 2^32)
+    uint32_t blk[8];
+#pragma unroll
+    for (int j = 0; j < 8; j++) {
+        if (j < (int)D.nblocks) { blk[j] = T[idx % D.block]; idx /= D.block; } else blk[j] = 0;
+    }
+    (void)mult;
+#pragma unroll
+    for (int j = 0; j < 8; j++)
+        if (j < (int)D.nblocks) sum = sum * D.block + blk[j];
+    return __fmul_rn(__uint2float_rn(sum), D.scale);
+}
+
+// Halton_enum (halton_enum.h:69-155); the constants are computed on the host
+struct DHEnum { uint32_t p2, p3, mx, my, inc; float scale_x, scale_y; };
+__device__ __forceinline__ uint32_t henum_index(const DHEnum& he, uint32_t s, uint32_t x, uint32_t y)
+{
+    uint64_t hx = he.p2 ? (uint64_t)(__brev(x) >> (32 - he.p2)) : 0ull;   // halton2_inverse (halton_enum.h:136-144)
+    uint32_t r3 = 0, yy = y;
+    for (uint32_t d = 0; d < he.p3; ++d) { r3 = r3 * 3 + yy % 3; yy /= 3; }  // halton3_inverse (halton_enum.h:146-155)
+    uint64_t hy = r3;
+    uint32_t offset = (uint32_t)((hx * he.mx + hy * he.my) % he.inc);
+    return offset + s * he.inc;  // u32 wrap-around kept
+}
+
+// ---- boxes (bbox.h) ----------------------------------------------------------------------------------------------------------
+// BoundingBox::intersect(ray, tmin, tmax, t0, t1) (bbox.h:47-73).  Returns entry t (>= tmin) or -1 when rejected.
+__device__ __forceinline__ double box_entry(const double* bmin, const double* bmax, const DRay& r, double tmin, double tmax)
+{
+    {
+        double t0 = (bmin[0] - r.o.x) * r.inv.x, t1 = (bmax[0] - r.o.x) * r.inv.x;
+        if (r.inv.x < 0.0) { double tmp = t0; t0 = t1; t1 = tmp; }
+        tmin = t0 > tmin ? t0 : tmin; tmax = t1 < tmax ? t1 : tmax;
+        if (tmax <= tmin) return -1.0;
+    }
+    {
+        double t0 = (bmin[1] - r.o.y) * r.inv.y, t1 = (bmax[1] - r.o.y) * r.inv.y;
+        if (r.inv.y < 0.0) { double tmp = t0; t0 = t1; t1 = tmp; }
+        tmin = t0 > tmin ? t0 : tmin; tmax = t1 < tmax ? t1 : tmax;
+        if (tmax <= tmin) return -1.0;
+    }
+    {
+        double t0 = (bmin[2] - r.o.z) * r.inv.z, t1 = (bmax[2] - r.o.z) * r.inv.z;
+        if (r.inv.z < 0.0) { double tmp = t0; t0 = t1; t1 = tmp; }
+        tmin = t0 > tmin ? t0 : tmin; tmax = t1 < tmax ? t1 : tmax;
+        if (tmax <= tmin) return -1.0;
+    }
+    return tmin;
+}
+// BoundingBox::contains (bbox.h:41-44), half-open
+__device__ __forceinline__ bool box_contains(const double* bmin, const double* bmax, d3 p)
+{
+    return p.x >= bmin[0] && p.y >= bmin[1] && p.z >= bmin[2] && p.x < bmax[0] && p.y < bmax[1] && p.z < bmax[2];
+}
+
+__device__ __forceinline__ DNode load_node(const DNode* nodes, uint32_t i)
+{
+    // 4 x 16-byte vector loads through the read-only path
+    const double2* p = reinterpret_cast<const double2*>(nodes + i);
+    double2 a = __ldg(p), b = __ldg(p + 1), c = __ldg(p + 2);
+    uint4 t = __ldg(reinterpret_cast<const uint4*>(p + 3));
+    DNode n;
+    n.bmin[0] = a.x; n.bmin[1] = a.y; n.bmin[2] = b.x; n.bmax[0] = b.y; n.bmax[1] = c.x; n.bmax[2] = c.y;
+    n.child = t.x; n.prim_off = t.y; n.prim_cnt = t.z; n.mask = t.w;
+    return n;
+}
+
+// ---- primitives (entities.h) ---------------------------------------------------------------------------------------------
+// triangle::intersect, geometric part (entities.h:443-478): returns t > 0 or -1; u, v barycentrics
+__device__ __forceinline__ double tri_hit(const double* g, const DRay& r, double& uo, double& vo)
+{
+    d3 v0 = mk3(g[0], g[1], g[2]);
+    d3 edge1 = mk3(g[3], g[4], g[5]) - v0, edge2 = mk3(g[6], g[7], g[8]) - v0;
+    d3 p = cross3(r.d, edge2);
+    double det = dot3(edge1, p);
+    if (det < GI_D_EPSILON && det > -GI_D_EPSILON) return -1.0;
+    double inv_det = 1.0 / det;
+    d3 tvec = r.o - v0;
+    double u = dot3(tvec, p) * inv_det;
+    if (u < 0 || u > 1) return -1.0;
+    d3 q = cross3(tvec, edge1);
+    double v = dot3(r.d, q) * inv_det;
+    if (v < 0 || u + v > 1) return -1.0;
+    double t = dot3(edge2, q) * inv_det;
+    if (t <= 0) return -1.0;
+    uo = u; vo = v;
+    return t;
+}
+// sphere::intersect, geometric part (entities.h:60-84): hit point = o + d*t; returns 1 on hit.  pow(x,2) is x*x (what
+// GCC emits for the reference at -O2)
+__device__ __forceinline__ bool sphere_hit(const double* g, const DRay& r, double& t_out)
+{
+    d3 pos = mk3(g[0], g[1], g[2]); double rad = g[3];
+    d3 oc = r.o - pos;
+    double d = dot3(r.d, oc);
+    double rr = (d * d - len2(oc) + rad * rad);
+    if (rr < 0) return false;
+    double sr = sqrt(rr);
+    double t_1 = -1 * d - sr, t_2 = -1 * d + sr;
+    if (t_1 < 0 && t_2 < 0) return false;
+    t_out = ((t_1 < t_2 && t_1 > 0) || t_2 < 0) ? t_1 : t_2;
+    return true;
+}
+// cone::intersect (entities.h:158-258); rot = cone::rot column-major; v*rot is glm's row-vector product
+__device__ __forceinline__ d3 vec_mat(d3 v, const double* m)
+{
+    return mk3(m[0] * v.x + m[1] * v.y + m[2] * v.z, m[3] * v.x + m[4] * v.y + m[5] * v.z, m[6] * v.x + m[7] * v.y + m[8] * v.z);
+}
+__device__ __noinline__ bool cone_hit(const double* g, const double* rot, const DRay& r, double& t_out, d3& n_out)
+{
+    d3 pos = mk3(g[0], g[1], g[2]); double rad = g[3], height = g[4];
+    d3 origin = vec_mat(r.o - pos, rot), dir = vec_mat(r.d, rot);
+    double phiMax = 2 * GI_D_PI;
+    double kq = (rad / height) * (rad / height);
+    double A = dir.x * dir.x + dir.y * dir.y - kq * dir.z * dir.z;
+    double B = 2 * (dir.x * origin.x + dir.y * origin.y - kq * dir.z * (origin.z - height));
+    double C = origin.x * origin.x + origin.y * origin.y - kq * (origin.z - height) * (origin.z - height);
+    double discrim = B * B - 4.0 * A * C;
+    if (discrim < 0) return false;
+    double rootDiscrim = sqrt(discrim);
+    double q = (B < 0) ? -.5 * (B - rootDiscrim) : -.5 * (B + rootDiscrim);
+    double t_1 = q / A, t_2 = C / q;
+    if (t_1 < 0 && t_2 < 0) return false;
+    if (t_1 > t_2) { double tmp = t_1; t_1 = t_2; t_2 = tmp; }
+    double thit = t_1;
+    if (t_1 < 0) thit = t_2; else if (t_2 < 0) thit = t_1;
+    d3 phit = origin + dir * thit;
+    double phi = atan2(phit.y, phit.x);
+    if (phi < 0.) phi += 2.0 * GI_D_PI;
+    if (phit.z < 0 || phit.z > height || phi > phiMax) {
+        if (thit == t_2) return false;
+        thit = t_2;
+        phit = origin + dir * thit;
+        phi = atan2(phit.y, phit.x);
+        if (phi < 0.) phi += 2.0 * GI_D_PI;
+        if (phit.z < 0 || phit.z > height || phi > phiMax) return false;
+    }
+    double vpar = phit.z / height;
+    d3 dpdu = mk3(-phiMax * phit.y, phiMax * phit.x, 0);
+    d3 dpdv = mk3(-phit.x / (1.0 - vpar), -phit.y / (1.0 - vpar), height);
+    n_out = normalize3(cross3(dpdu, dpdv));
+    t_out = thit;
+    return true;
+}
+
+// ---- textures / materials (material.h) -----------------------------------------------------------------------------------
+__device__ __forceinline__ const uint8_t* tex_pixel(const DScene& S, const gi_texture& t, double u, double v)
+{
+    int x = abs((int)(u * t.width * t.tile_u) % t.width);                              // material.h:65
+    int y = t.height - abs((int)(v * t.height * t.tile_v) % t.height) - 1;
+    return S.tex_pixels + t.pixel_offset + ((size_t)y * t.width + x) * 4;
+}
+__device__ __forceinline__ d3 tex_get(const DScene& S, uint32_t id, double u, double v)
+{
+    const gi_texture& t = S.tex[id];
+    if (t.kind == GI_TEX_CONST) return ld3(t.a);
+    if (t.kind == GI_TEX_CHECKER) {
+        if ((((int)(u * t.tiles) % 2 == 0) ^ ((int)(v * t.tiles) % 2 == 0))) return ld3(t.a);
+        return ld3(t.b);
+    }
+    const uint8_t* p = tex_pixel(S, t, u, v);
+    double e = 1.0 / (1.0 / 2.2);                                                       // gamma(c, 1/GAMMA): material.h:67, util.h:94-97
+    return mk3(pow(p[0] / 255.0, e), pow(p[1] / 255.0, e), pow(p[2] / 255.0, e));
+}
+__device__ __forceinline__ double tex_alpha(const DScene& S, uint32_t id, double u, double v)
+{
+    const gi_texture& t = S.tex[id];
+    if (t.kind != GI_TEX_IMAGE || !t.has_alpha) return 1;
+    return tex_pixel(S, t, u, v)[3] / 255.0;
+}
+// `drand() < material.getAlpha(uv) || IOR != 1` (raytracer.h:455,:297) with an occurrence-keyed counter draw
+__device__ __forceinline__ bool alpha_pass(const DScene& S, uint32_t prim, uint32_t node, double u, double v, uint64_t seed, uint64_t path, uint64_t depth, uint64_t site)
+{
+    const gi_material& m = S.mats[S.prim_mat[prim]];
+    if (m.ior != 1) return true;
+    double a = m.opacity * tex_alpha(S, m.diffuse_tex, u, v);
+    if (a >= 1.0) return true;
+    return gi_rand(seed, path, depth, SITE(site, ((uint64_t)node << 28) ^ prim)) < a;
+}
+
+// uv of a uv-writing primitive at barycentrics (u,v) (entities.h:482 for triangles, :93-96 for spheres)
+__device__ __forceinline__ void prim_uv_at(const DScene& S, uint32_t prim, d3 hit, double u, double v, double& tu, double& tv)
+{
+    if (S.prim_type[prim] == GI_PRIM_TRIANGLE) {
+        const double* t2 = S.prim_uv + 6 * (size_t)prim;
+        double w = 1 - u - v;
+        tu = (w * t2[0] + u * t2[2]) + v * t2[4];
+        tv = (w * t2[1] + u * t2[3]) + v * t2[5];
+    } else {  // sphere
+        const double* g = S.prim_geom + 9 * (size_t)prim;
+        double rad = g[3];
+        d3 dd = mk3((g[0] - hit.x) / rad, (g[1] - hit.y) / rad, (g[2] - hit.z) / rad);
+        tv = .5 + asin(dd.y) / GI_D_PI;
+        tu = .5 + atan2(dd.z, dd.x) / (2 * GI_D_PI);
+    }
+}
+
+// ---- closest hit: RayTracer::trace (raytracer.h:382-478) as an ordered stack traversal -----------------------------------------
+// Leaves are visited in ascending entry distance, ties in child order (= the reference's sorted leaf list,
+// octree.cpp:285-313 + SURVEY §A.3); inside a leaf every primitive is tested in stored order; a candidate is accepted if
+// it is the first or STRICTLY closer in |hit-o|^2; the walk stops after the first leaf in which an accepted hit lies
+// inside the leaf box (raytracer.h:446-472).  There is deliberately no pruning against the best distance: the reference
+// has none, and keeping its exact visiting rule is what makes ids bit-identical.
+struct DHit {
+    uint32_t prim;     // GI_NO_HIT on miss
+    double t, u, v;    // ray parameter and barycentrics (triangles)
+    double tu, tv;     // uv as RayTracer::trace returns it (FULL traversal only; otherwise derived from prim,u,v)
+    d3 n;              // cone normal (cones only)
+};
+
+template <bool FULL>
+__device__ __forceinline__ void trace_closest(const DScene& S, const DRay& r, uint64_t seed, uint64_t path, uint64_t depth, DHit& out)
+{
+    uint32_t stack[GI_STACK_MAX];
+    int sp = 0;
+    out.prim = GI_NO_HIT; out.t = 0; out.u = 0; out.v = 0; out.tu = 0; out.tv = 0; out.n = mk3(0, 0, 0);
+    double best_d2 = 0;
+    double cur_tu = 0, cur_tv = 0;  // `uv` local of RayTracer::trace: survives across candidates (raytracer.h:385)
+    if (S.n_nodes == 0) return;
+    {
+        DNode root = load_node(S.nodes, 0);
+        if (box_entry(root.bmin, root.bmax, r, 0.0, CUDART_INF) < 0.0) return;
+        stack[sp++] = 0;
+    }
+    bool term = false;
+    while (sp > 0 && !term) {
+        uint32_t ni = stack[--sp];
+        DNode nd = load_node(S.nodes, ni);
+        if (nd.mask == 0) {
+            const DLeafRef* refs = S.refs + nd.prim_off;
+            for (uint32_t k = 0; k < nd.prim_cnt; k++) {
+                const double2* rp = reinterpret_cast<const double2*>(refs + k);
+                double g[9];
+                double2 a0 = __ldg(rp), a1 = __ldg(rp + 1), a2 = __ldg(rp + 2), a3 = __ldg(rp + 3);
+                g[0] = a0.x; g[1] = a0.y; g[2] = a1.x; g[3] = a1.y; g[4] = a2.x; g[5] = a2.y; g[6] = a3.x; g[7] = a3.y;
+                uint4 tail = __ldg(reinterpret_cast<const uint4*>(rp + 4));
+                g[8] = __hiloint2double((int)tail.y, (int)tail.x);
+                uint32_t prim = tail.z, flags = tail.w;
+                double t, u = 0, v = 0; d3 cn = mk3(0, 0, 0);
+                bool ok;
+                uint32_t kind = LF_KIND(flags);
+                if (kind == GI_PRIM_TRIANGLE) { t = tri_hit(g, r, u, v); ok = t > 0; }
+                else if (kind == GI_PRIM_SPHERE) ok = sphere_hit(g, r, t);
+                else ok = cone_hit(g, S.prim_nrm + 9 * (size_t)prim, r, t, cn);
+                if (!ok) continue;
+                d3 hit = r.o + r.d * t;
+                if (FULL) {
+                    if (flags & LF_WRITES_UV) prim_uv_at(S, prim, hit, u, v, cur_tu, cur_tv);
+                    if ((flags & LF_ALPHA) && !alpha_pass(S, prim, ni, cur_tu, cur_tv, seed, path, depth, SITE_ALPHA_TRACE)) continue;
+                }
+                double d2 = len2(hit - r.o);
+                if (out.prim == GI_NO_HIT || d2 < best_d2) {
+                    out.prim = prim; out.t = t; out.u = u; out.v = v; out.n = cn; best_d2 = d2;
+                    if (FULL) { out.tu = cur_tu; out.tv = cur_tv; }
+                    if (box_contains(nd.bmin, nd.bmax, hit)) term = true;
+                }
+            }
+            continue;
+        }
+        // interior: entry distance of every existing child, then push far-to-near (ties: higher child index first,
+        // so that equal-distance children pop in child order)
+        double t0c[8];
+        uint32_t c = nd.child;
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+            t0c[i] = -1.0;
+            if (nd.mask & (1u << i)) {
+                DNode ch = load_node(S.nodes, c);
+                t0c[i] = box_entry(ch.bmin, ch.bmax, r, 0.0, CUDART_INF);
+                c++;
+            }
+        }
+        for (;;) {
+            double bt = -1.0; int bi = -1;
+#pragma unroll
+            for (int i = 0; i < 8; i++) if (t0c[i] >= bt && t0c[i] >= 0.0) { bt = t0c[i]; bi = i; }
+            if (bi < 0) break;
+            if (sp < GI_STACK_MAX) stack[sp++] = nd.child + __popc(nd.mask & ((1u << bi) - 1u));
+#pragma unroll
+            for (int i = 0; i < 8; i++) if (i == bi) t0c[i] = -1.0;
+        }
+    }
+}
+
+// ---- any hit: RayTracer::visible (raytracer.h:280-319) over Octree::Node::intersect (octree.cpp:256-282) -------------------------
+// Returns true when nothing blocks the segment.  Visiting order is free: the alpha draw is keyed by the (leaf, primitive)
+// occurrence, so the outcome equals the reference's first-blocker search for any order.
+template <bool FULL>
+__device__ __forceinline__ bool trace_visible(const DScene& S, const DRay& r, double mt, uint64_t seed, uint64_t path, uint64_t depth, uint64_t light)
+{
+    if (S.n_nodes == 0) return true;
+    const double tmax = sqrt(mt) - GI_D_SHADOW_BIAS;   // raytracer.h:283
+    uint32_t stack[GI_STACK_MAX];
+    int sp = 0;
+    {
+        DNode root = load_node(S.nodes, 0);
+        if (box_entry(root.bmin, root.bmax, r, 0.0, tmax) < 0.0) return true;
+        stack[sp++] = 0;
+    }
+    while (sp > 0) {
+        uint32_t ni = stack[--sp];
+        DNode nd = load_node(S.nodes, ni);
+        if (nd.mask == 0) {
+            const DLeafRef* refs = S.refs + nd.prim_off;
+            for (uint32_t k = 0; k < nd.prim_cnt; k++) {
+                const double2* rp = reinterpret_cast<const double2*>(refs + k);
+                double g[9];
+                double2 a0 = __ldg(rp), a1 = __ldg(rp + 1), a2 = __ldg(rp + 2), a3 = __ldg(rp + 3);
+                g[0] = a0.x; g[1] = a0.y; g[2] = a1.x; g[3] = a1.y; g[4] = a2.x; g[5] = a2.y; g[6] = a3.x; g[7] = a3.y;
+                uint4 tail = __ldg(reinterpret_cast<const uint4*>(rp + 4));
+                g[8] = __hiloint2double((int)tail.y, (int)tail.x);
+                uint32_t prim = tail.z, flags = tail.w;
+                double t, u = 0, v = 0; d3 cn;
+                bool ok;
+                uint32_t kind = LF_KIND(flags);
+                if (kind == GI_PRIM_TRIANGLE) { t = tri_hit(g, r, u, v); ok = t > 0; }
+                else if (kind == GI_PRIM_SPHERE) ok = sphere_hit(g, r, t);
+                else ok = cone_hit(g, S.prim_nrm + 9 * (size_t)prim, r, t, cn);
+                if (!ok) continue;
+                d3 pos = r.o + r.d * t;
+                if (FULL && (flags & LF_ALPHA)) {
+                    double tu = 0, tv = 0;   // `uv` is a fresh (0,0) per candidate in visible() (raytracer.h:295)
+                    if (flags & LF_WRITES_UV) prim_uv_at(S, prim, pos, u, v, tu, tv);
+                    if (!alpha_pass(S, prim, ni, tu, tv, seed, path, depth, SITE_ALPHA_SHADOW + (light << 8))) continue;
+                }
+                double t_shadow = len2(pos - r.o);
+                if ((t_shadow < mt) && (t_shadow > 0)) return false;
+            }
+            continue;
+        }
+        uint32_t c = nd.child;
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+            if (nd.mask & (1u << i)) {
+                DNode ch = load_node(S.nodes, c);
+                if (box_entry(ch.bmin, ch.bmax, r, 0.0, tmax) >= 0.0 && sp < GI_STACK_MAX) stack[sp++] = c;
+                c++;
+            }
+        }
+    }
+    return true;
+}
+
+// ---- hit reconstruction: what RayTracer::trace hands back (hit point, shading normal, uv) from (prim, t, u, v) --------------
+__device__ __forceinline__ void hit_surface(const DScene& S, const DRay& r, const DHit& h, bool full, d3& p, d3& n, double& tu, double& tv)
+{
+    p = r.o + r.d * h.t;
+    tu = 0; tv = 0;
+    uint32_t kind = S.prim_type[h.prim];
+    if (kind == GI_PRIM_TRIANGLE) {
+        const double* nn = S.prim_nrm + 9 * (size_t)h.prim;
+        d3 n0 = ld3(nn), n1 = ld3(nn + 3), n2 = ld3(nn + 6);
+        if (len2(n0) > 0 && len2(n1) > 0 && len2(n2) > 0) {                    // entities.h:480-487
+            double w = 1 - h.u - h.v;
+            n = (n0 * w + n1 * h.u) + n2 * h.v;
+            prim_uv_at(S, h.prim, p, h.u, h.v, tu, tv);
+        } else n = ld3(S.prim_fnorm + 3 * (size_t)h.prim);
+    } else if (kind == GI_PRIM_SPHERE) {
+        const double* g = S.prim_geom + 9 * (size_t)h.prim;
+        n = normalize3(p - mk3(g[0], g[1], g[2]));                            // entities.h:86-91
+        prim_uv_at(S, h.prim, p, 0, 0, tu, tv);
+    } else n = h.n;
+    if (full) { tu = h.tu; tv = h.tv; }
+}
+
+// ---- samplers (util.h / util.cpp) -----------------------------------------------------------------------------------------------
+// fastPrecisePow(double,double) (util.h:113-136)
+__device__ __forceinline__ double fast_precise_pow(double a, double b)
+{
+    int e = (int)b;
+    int hi = __double2hiint(a);
+    hi = (int)((b - e) * (hi - 1072632447) + 1072632447);
+    double frac = __hiloint2double(hi, 0);
+    double rr = 1.0;
+    while (e) { if (e & 1) rr *= a; a *= a; e >>= 1; }
+    return rr * frac;
+}
+// the tangent frame of util.cpp:41-45 applied to v (glm column-major mat * vec)
+__device__ __forceinline__ d3 frame_apply(d3 n, d3 v)
+{
+    double z = fabs(n.z);
+    double k = (1.0 / (1 + z));
+    double c0x = z + k * -n.y * -n.y, c0y = k * (n.x * -n.y), c0z = -n.x;
+    double c1x = k * (n.x * -n.y), c1y = z + k * -n.x * -n.x, c1z = -n.y;
+    double c2x = n.x, c2y = n.y, c2z = z;
+    return mk3(c0x * v.x + c1x * v.y + c2x * v.z, c0y * v.x + c1y * v.y + c2y * v.z, c0z * v.x + c1z * v.y + c2z * v.z);
+}
+// phi / cosTheta / sinTheta are float in the reference; cos, sin, sqrt are the double versions of float values
+__device__ __forceinline__ d3 lobe_dir(float v, float cosTheta)
+{
+    float phi = (float)((double)(v * 2.0f) * GI_D_PI);
+    float sinTheta = (float)sqrt((double)(1.0f - cosTheta * cosTheta));
+    return mk3(cos((double)phi) * (double)sinTheta, sin((double)phi) * (double)sinTheta, (double)cosTheta);
+}
+__device__ __forceinline__ d3 hemisphere_cos(d3 n, float u, float v, double power)   // util.cpp:38-58
+{
+    float cosTheta = (float)fast_precise_pow((double)(1.0f - u), (1.0f / power));
+    d3 res = frame_apply(n, lobe_dir(v, cosTheta));
+    if (n.z < 0) res.z *= -1.0;
+    return res;
+}
+__device__ __forceinline__ d3 sphere_cap_cos(d3 n, float u, float v, double power, double frac)   // util.cpp:60-83
+{
+    float cosTheta = (float)(frac * fast_precise_pow((double)(1.0f - u), (1.0f / power)) + (1 - frac));
+    d3 res = frame_apply(n, lobe_dir(v, cosTheta));
+    if (n.z < 0) res.z *= -1.0;
+    return res;
+}
+__device__ __forceinline__ d3 sample_phong(d3 outdir, double power, double sx, double sy)   // util.cpp:91-107
+{
+    float u = (float)sx, v = (float)sy;
+    float cosTheta = (float)fast_precise_pow((double)(1.0f - u), (1.0f / power));
+    d3 res = frame_apply(outdir, lobe_dir(v, cosTheta));
+    if (outdir.z < 0) res.z *= -1.0;
+    return res;
+}
+__device__ __forceinline__ d3 random_unit_vec(double x, double y)   // util.h:183-188
+{
+    double theta = acos(2 * y - 1);
+    return mk3(sin(theta) * cos(2 * x * GI_D_PI), sin(theta) * sin(2 * x * GI_D_PI), cos(theta));
+}
+__device__ __forceinline__ d3 refr3(d3 I, d3 N, double eta)   // util.h:173-181
+{
+    double d = dot3(N, I);
+    double k = 1.0 - eta * eta * (1.0 - d * d);
+    if (k < GI_D_EPSILON) return reflect3(I, N);
+    return I * eta - N * (eta * d + sqrt(k));
+}
+// pow(x, 2) / pow(x, 5) with small integer exponents and pow(d, 1/roughness): libm calls in the reference.  CUDA's pow is
+// within 2 ulp of glibc's (<1 ulp); exponent 1 is returned exactly like glibc does.
+__device__ __forceinline__ double pow_like_libm(double x, double y) { return y == 1.0 ? x : pow(x, y); }
+
+// Light::getPoint (light.h:42-45) / getPointInRange (light.h:47-53)
+__device__ __forceinline__ d3 light_point(const gi_light& l, double x, double y) { return ld3(l.pos) + random_unit_vec(x, y) * l.rad; }
+__device__ __forceinline__ d3 light_point_in_range(const gi_light& l, double x, double y)
+{
+    if (l.angle < 1) return ld3(l.pos) + sphere_cap_cos(ld3(l.dir), (float)x, (float)y, 1, l.angle) * l.rad;
+    return light_point(l, x, y);
+}
+
+// RayTracer::rayType (raytracer.h:481-506)
+__device__ __forceinline__ int ray_type(const DScene& S, const gi_material& m, const DRay& r, d3 norm, double tu, double tv, uint64_t seed, uint64_t path, uint64_t depth)
+{
+    int type = 2;
+    double IOR = m.ior;
+    double opacity = tex_alpha(S, m.diffuse_tex, tu, tv) * m.opacity;
+    double q0 = (1 - IOR) / (1 + IOR);
+    double r0 = q0 * q0;
+    double fs = r0 + (1 - r0) * pow(1 - dot3(reflect3(r.d, norm), norm), 5.0);
+    if (m.roughness < .001) type = 0;
+    if (gi_rand(seed, path, depth, SITE(SITE_TYPE_A, 0)) > opacity) {
+        if (gi_rand(seed, path, depth, SITE(SITE_TYPE_B, 0)) < fs) type = 0; else type = 1;
+    }
+    return type;
+}
+// RayTracer::secondaryRay (raytracer.h:321-379): flips norm in place, returns refDir, updates f / contrib / offset
+__device__ __forceinline__ d3 secondary_ray(const DScene& S, const gi_material& m, const DRay& r, d3& norm, double tu, double tv, double sx, double sy, d3 color, d3& f, d3& contrib,
+                                            double& offset, uint64_t seed, uint64_t path, uint64_t depth)
+{
+    bool backface = false;
+    if (dot3(norm, r.d) > 0) { norm = norm * -1.0; backface = true; }
+    int type = ray_type(S, m, r, norm, tu, tv, seed, path, depth);
+    d3 refDir;
+    if (type == 1) {
+        refDir = refr3(r.d, norm, backface ? m.ior : 1.0 / m.ior);
+        offset *= -1;
+        contrib = mk3(1, 1, 1);
+        f = color * 1.0;
+    } else if (type == 0) {
+        refDir = reflect3(r.d, norm);
+        contrib = mk3(1, 1, 1);
+        f = color * 1.0;
+    } else {
+        refDir = hemisphere_cos(norm, (float)sx, (float)sy, 2);
+        if (m.roughness < .9) {
+            refDir = sample_phong(reflect3(r.d, norm), (1.0 / (m.roughness)) + 1, sx, sy);
+            if (dot3(refDir, norm) < 0) refDir = reflect3(refDir, norm);
+        }
+        f = color * 1.0;
+        contrib = contrib * color;
+        contrib = contrib + (color - contrib) * 0.5;   // glm::mix(contrib, inf, 0.5)
+    }
+    return refDir;
+}

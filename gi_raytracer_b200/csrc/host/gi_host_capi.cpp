@@ -1,0 +1,85 @@
+// gi_host_capi.cpp — a small C facade over the host scene classes for the Python harness (tests, bench.py):
+// load a .scn through loadScene, rebuild the octree, flatten, and expose the arrays.  No device work here.
+#include <cstring>
+#include <iostream>
+#include <sstream>
+
+#include "gi_scene.hpp"
+
+struct gih_scene {
+    Octree* octree;
+    RayTracer* rt;
+    FlatScene flat;
+    gi_scene_desc desc;
+};
+
+extern "C" {
+
+// Load + rebuild + flatten.  quiet != 0 silences the loader's std::cout chatter.
+int gih_scene_load(const char* path, int quiet, gih_scene** out)
+{
+    if (!path || !out) return GI_ERR_INVALID;
+    std::streambuf* old = nullptr;
+    std::ostringstream sink;
+    if (quiet) old = std::cout.rdbuf(sink.rdbuf());
+    gih_scene* s = new gih_scene();
+    Camera camera(gi::dvec3(10, 5, 0), gi::dvec3(0, 0, 0));  // main.cpp:30 default camera
+    s->rt = new RayTracer(camera);
+    s->octree = new Octree();
+    loadScene(s->octree, *s->rt, path);
+    if (!s->octree->entities().empty()) s->octree->rebuild(); else s->octree->valid = true;
+    s->octree->flatten(s->rt->_camera, s->rt->ambient, s->flat);
+    s->desc = s->flat.desc();
+    if (quiet) std::cout.rdbuf(old);
+    *out = s;
+    return GI_OK;
+}
+
+const gi_scene_desc* gih_scene_desc(const gih_scene* s) { return s ? &s->desc : nullptr; }
+
+// photons, photon_depth, min_samples, max_samples, noise_thresh
+void gih_scene_knobs(const gih_scene* s, int* photons, int* photon_depth, int* min_samples, int* max_samples, double* noise_thresh)
+{
+    if (photons) *photons = s->rt->photons;
+    if (photon_depth) *photon_depth = s->rt->photon_depth;
+    if (min_samples) *min_samples = s->rt->min_samples;
+    if (max_samples) *max_samples = s->rt->max_samples;
+    if (noise_thresh) *noise_thresh = s->rt->noise_thresh;
+}
+
+void gih_scene_free(gih_scene* s)
+{
+    if (!s) return;
+    delete s->rt;
+    delete s->octree;  // entities/materials/textures are never freed, like the reference (SURVEY §8b ownership)
+    delete s;
+}
+
+// Headless equivalent of the reference's main(): load, run(w,h) on `device`, write a PPM.  Returns 0 or GI_ERR_*.
+int gih_render_scene(const char* path, int w, int h, int device, int max_depth, int spp_override, int photons_override, uint64_t seed,
+                     const char* out_ppm, uint8_t* rgb_out, gi_stats* frame_stats, gi_stats* photon_stats, double* photon_ms, double* frame_ms)
+{
+    Camera camera(gi::dvec3(10, 5, 0), gi::dvec3(0, 0, 0));
+    RayTracer rt(camera);
+    Octree* scene = new Octree();
+    loadScene(scene, rt, path);
+    rt.setScene(scene);
+    rt.device = device;
+    rt.seed = seed;
+    if (max_depth >= 0) rt.max_depth = max_depth;
+    if (spp_override > 0) { rt.min_samples = rt.max_samples = spp_override; }
+    if (photons_override >= 0) rt.photons = photons_override;
+    rt.start();
+    int rc = rt.run(w, h);
+    if (rc != GI_OK) { delete scene; return rc; }
+    if (out_ppm && *out_ppm) rt.getImage()->writePPM(out_ppm);
+    if (rgb_out) std::memcpy(rgb_out, rt.getImage()->rgb.data(), rt.getImage()->rgb.size());
+    if (frame_stats) *frame_stats = rt.last_frame_stats;
+    if (photon_stats) *photon_stats = rt.last_photon_stats;
+    if (photon_ms) *photon_ms = rt.last_photon_ms;
+    if (frame_ms) *frame_ms = rt.last_frame_ms;
+    delete scene;
+    return GI_OK;
+}
+
+}  // extern "C"

@@ -101,8 +101,20 @@ def preorder_to_bfs(box, mask, cnt, refs):
 
 
 def scene_from_dump(d):
-    """SceneArrays from a `gi_ref ... scene` dump.  Textures come out as constant colours (the dump records
-    texture::color only), which is exact for scenes without imTex/checkerboardTex."""
+    """SceneArrays from a `gi_ref ... scene` dump directory."""
+    return scene_from_arrays(lambda name: load(d, name))
+
+
+def scene_from_npz(z):
+    """SceneArrays from a tests/golden/*.npz fixture (same arrays, '.' replaced by '_' in the names)."""
+    return scene_from_arrays(lambda name: z[name.replace(".", "_")])
+
+
+def scene_from_arrays(load_):
+    """Textures come out as constant colours (the dump records texture::color only), which is exact for scenes
+    without imTex/checkerboardTex."""
+    d = None
+    load = lambda _d, name: load_(name)  # noqa: E731
     box = load(d, "node_box.f64")
     mask = load(d, "node_mask.u8")
     cnt = load(d, "node_cnt.u32")

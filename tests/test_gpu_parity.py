@@ -1,0 +1,292 @@
+"""GPU parity: the CUDA path (through the C ABI, gi_raytracer_b200.capi) against (1) fixtures produced by the reference
+itself and (2) the CPU restatement on the same seeded inputs.  Bars: bit-exact for Halton values/indices, camera rays,
+hit primitive ids, hit points / normals / uvs, shadow bits, photon-map cells and k-nearest index sets; 1e-12 relative for the
+radiance estimate (summation order is fixed, ties may reorder); stated tolerances for PRNG/libm-dependent radiance."""
+import os
+
+import numpy as np
+import pytest
+
+import oracle_lib as O
+import refdump as R
+from conftest import bits_equal, have_assets, scene_path
+from gi_raytracer_b200.abi import render_params
+
+pytestmark = pytest.mark.gpu
+
+
+def random_rays(scene, n, seed):
+    """Rays with origins inside the (slightly grown) scene box and uniform directions, normalised like Ray::setDir."""
+    rng = np.random.RandomState(seed)
+    lo, hi = scene.root_box[:3], scene.root_box[3:]
+    pad = 0.1 * (hi - lo)
+    o = lo - pad + rng.rand(n, 3) * (hi - lo + 2 * pad)
+    d = rng.randn(n, 3)
+    d = d * (1.0 / np.sqrt(d[:, 0:1] * d[:, 0:1] + d[:, 1:2] * d[:, 1:2] + d[:, 2:3] * d[:, 2:3]))
+    # a few axis-parallel directions: invDir = +-inf and NaN slabs
+    d[:8] = np.array([[1, 0, 0], [-1, 0, 0], [0, 1, 0], [0, -1, 0], [0, 0, 1], [0, 0, -1], [0, 1, 0], [1, 0, 0]], dtype=np.float64)
+    return np.ascontiguousarray(o), np.ascontiguousarray(d)
+
+
+# ---- against the reference's own outputs (golden fixtures) ----------------------------------------------------------------
+def test_halton_sample_bit_exact(ctx, golden_cornell):
+    g = golden_cornell
+    idx, val = g["halton_idx_u32"], g["halton_val_f32"]
+    dims = np.repeat(np.arange(256, dtype=np.uint32), idx.size)
+    got = ctx.halton_sample(dims, np.tile(idx, 256)).reshape(256, -1)
+    assert bits_equal(got, val)
+
+
+def test_halton_index_bit_exact_incl_u32_wrap(ctx, golden_cornell):
+    g = golden_cornell
+    q, ref = g["henum_query_u32"].reshape(-1, 5), g["henum_index_u32"]
+    for w, h in sorted(set((int(a), int(b)) for a, b in q[:, :2])):
+        m = (q[:, 0] == w) & (q[:, 1] == h)
+        got = ctx.halton_index(w, h, q[m, 2], q[m, 3], q[m, 4])
+        assert bits_equal(got, ref[m]), (w, h)
+
+
+@pytest.mark.parametrize("which", ["cornell", "caustics"])
+def test_golden_rays_hits_shadows_gather(ctx, which, golden_cornell, golden_caustics):
+    g = golden_cornell if which == "cornell" else golden_caustics
+    sc = R.scene_from_npz(g)
+    ctx.upload_scene(sc)
+    w, h, s0, s1 = [int(v) for v in g["meta_w_h_s0_s1"]]
+    o, d, ix = ctx.camera_rays(w, h, 0, 0, w, h, s0, s1)
+    ro, rd = g["ray_o_f64"].reshape(-1, 3), g["ray_d_f64"].reshape(-1, 3)
+    assert bits_equal(ix, g["ray_idx_u32"]) and bits_equal(o, ro) and bits_equal(d, rd)
+    prim, hit, nrm, uv = ctx.trace_closest(ro, rd)
+    assert bits_equal(prim, g["hit_id_u32"])
+    assert bits_equal(hit, g["hit_pos_f64"].reshape(-1, 3)) and bits_equal(nrm, g["hit_nrm_f64"].reshape(-1, 3)) and bits_equal(uv, g["hit_uv_f64"].reshape(-1, 2))
+    vis = ctx.trace_any(g["sh_o_f64"].reshape(-1, 3), g["sh_d_f64"].reshape(-1, 3), g["sh_maxt2_f64"])
+    assert bits_equal(vis, g["sh_vis_u8"])
+    # photon map built on the device from the reference's photons: identical cells, identical per-leaf photon order
+    ctx.photon_upload(g["photons_f64"].reshape(-1, 9))
+    ctx.photon_map_build(sc.root_box)
+    box, leaf, cnt, ids = ctx.photon_map_download()
+    assert bits_equal(box, g["pm_box_f64"].reshape(-1, 6)) and bits_equal(leaf, g["pm_leaf_u8"]) and bits_equal(cnt, g["pm_cnt_u32"]) and bits_equal(ids, g["pm_refs_u32"])
+    rgb, knn, nc = ctx.gather(g["q_pos_f64"].reshape(-1, 3), g["q_dir_f64"].reshape(-1, 3), 32)
+    assert bits_equal(nc, np.diff(g["q_cand_off_u32"]).astype(np.uint32))
+    rknn = g["q_knn_u32"].reshape(-1, 32)
+    assert all(set(a) == set(b) for a, b in zip(knn, rknn))
+    assert np.allclose(rgb, g["q_est_f64"].reshape(-1, 3), rtol=1e-12, atol=0)
+
+
+# ---- against the CPU restatement on seeded inputs ------------------------------------------------------------------------------
+def _load(name, synth_dir):
+    from gi_raytracer_b200 import host
+    if name in ("mixed", "cards", "small", "atrium"):
+        return host.load_scene(os.path.join(synth_dir, name + ".scn"))
+    if not have_assets(name):
+        pytest.skip(f"assets for {name} not staged")
+    return host.load_scene(scene_path(name))
+
+
+@pytest.mark.parametrize("name,res", [("mixed", 96), ("cards", 96), ("small", 64), ("atrium", 96), ("cornell", 128), ("glass", 160)])
+def test_closest_and_any_hit_vs_oracle(ctx, synth_dir, name, res):
+    sc = _load(name, synth_dir)
+    ctx.upload_scene(sc)
+    o, d, ix = ctx.camera_rays(res, res, 0, 0, res, res, 0, 2)
+    o2, d2, _ = O.camera_rays(sc, res, res, 0, 0, res, res, 0, 2)
+    assert bits_equal(o, o2) and bits_equal(d, d2)
+    ro, rdir = random_rays(sc, 20000, seed=hash(name) % 1000)
+    o, d = np.concatenate([o, ro]), np.concatenate([d, rdir])
+    for seed in (0, 12345):
+        prim, hit, nrm, uv = ctx.trace_closest(o, d, alpha_seed=seed)
+        p2, h2, n2, uv2 = O.trace_closest(sc, o, d, alpha_seed=seed)
+        assert bits_equal(prim, p2), f"{name}: {(prim != p2).sum()} ids differ"
+        assert bits_equal(hit, h2) and bits_equal(nrm, n2) and bits_equal(uv, uv2)
+    assert (prim != 0xFFFFFFFF).mean() > 0.3
+    # shadow segments from the hits toward the first light (or a fixed point)
+    m = prim != 0xFFFFFFFF
+    target = sc.lights[0, :3] if sc.lights.shape[0] else sc.root_box[3:] + 1.0
+    so = hit[m] + 1e-4 * nrm[m]
+    sd = target[None, :] - so
+    mt = (sd * sd).sum(axis=1)
+    sd = sd * (1.0 / np.sqrt(mt))[:, None]
+    for seed in (0, 999):
+        vis = ctx.trace_any(so, sd, mt, alpha_seed=seed)
+        v2 = O.trace_any(sc, so, sd, mt, alpha_seed=seed)
+        assert bits_equal(vis, v2), f"{name}: {(vis != v2).sum()} shadow bits differ"
+
+
+def test_cone_primitive_vs_oracle(ctx):
+    """cones exist only through the C++ API (no .scn keyword) and only survive in an un-partitioned root leaf."""
+    from gi_raytracer_b200.abi import SceneArrays
+    ang = 0.4
+    c, s = np.cos(ang), np.sin(ang)
+    rot = np.array([[1, 0, 0], [0, c, s], [0, -s, c]], dtype=np.float64)   # column-major 3x3
+    geom = np.zeros((2, 9)); nrm = np.zeros((2, 9))
+    geom[0, :5] = [0.0, 0.0, 0.0, 0.8, 2.0]; nrm[0] = rot.T.ravel()
+    geom[1, :4] = [1.5, 0.2, 0.3, 0.6]
+    mats = np.zeros(1, dtype=SceneArrays.MAT_DTYPE); mats["roughness"] = 1; mats["opacity"] = 1; mats["ior"] = 1
+    tex = np.zeros(1, dtype=SceneArrays.TEX_DTYPE); tex["a"] = [[0.5, 0.5, 0.5]]
+    cam = np.array([5, 2, 0, -1, 0, 0, 0, 1, 0, 0, 0, 1, 16.8, 9.6], dtype=np.float64)
+    sc = SceneArrays(node_box=[[-3, -3, -3, 3, 3, 3]], node_child=[0], node_mask=[0], node_prim_off=[0], node_prim_cnt=[2], leaf_prims=[0, 1],
+                     prim_type=[2, 1], prim_geom=geom, prim_nrm=nrm, prim_uv=np.zeros((2, 6)), prim_fnorm=np.zeros((2, 3)), prim_mat=[0, 0], mats=mats, tex=tex,
+                     tex_pixels=np.zeros(0, np.uint8), lights=np.zeros((0, 11)), camera=cam, ambient=[0, 0, 0])
+    ctx.upload_scene(sc)
+    o, d = random_rays(sc, 30000, 3)
+    prim, hit, nrm_, uv = ctx.trace_closest(o, d)
+    p2, h2, n2, uv2 = O.trace_closest(sc, o, d)
+    assert bits_equal(prim, p2)
+    assert (prim == 0).sum() > 500 and (prim == 1).sum() > 500
+    # cone/sphere hits go through atan2/asin (libm vs CUDA): positions must agree to rounding, uv within 1e-12
+    assert np.allclose(hit, h2, rtol=0, atol=1e-12) and np.allclose(nrm_, n2, rtol=0, atol=1e-12) and np.allclose(uv, uv2, rtol=0, atol=1e-12)
+
+
+def test_photon_map_and_gather_vs_oracle_random_cloud(ctx):
+    """Photon clouds with clusters, duplicates and points on cell faces; queries inside and outside the root box."""
+    rng = np.random.RandomState(5)
+    box = np.array([-2.0, -1.0, -3.0, 2.0, 3.0, 1.0])
+    n = 60000
+    pos = box[:3] + rng.rand(n, 3) * (box[3:] - box[:3])
+    pos[:5000] = np.array([0.3, 0.7, -1.1]) + 0.01 * rng.randn(5000, 3)       # dense cluster
+    pos[5000:5040] = np.array([1.0, 1.0, -1.0])                                # > 16 coincident photons: deep degenerate split
+    pos[5040:5100, 0] = 0.0                                                    # on the root's x mid-plane
+    pos[5100:5110] = box[3:]                                                   # on the max corner: dropped by the half-open test
+    ph = np.concatenate([pos, rng.randn(n, 3), rng.rand(n, 3)], axis=1)
+    ctx.photon_upload(ph)
+    ctx.photon_map_build(box)
+    pm = O.PMap(ph, box)
+    b1, l1, c1, i1 = ctx.photon_map_download()
+    b2, l2, c2, i2 = pm.dump()
+    assert ctx.photon_map_info()["n_nodes"] == pm.info()["n_nodes"]
+    assert bits_equal(b1, b2) and bits_equal(l1, l2) and bits_equal(c1, c2) and bits_equal(i1, i2)
+    q = box[:3] - 0.2 + rng.rand(20000, 3) * (box[3:] - box[:3] + 0.4)
+    q[:2000] = pos[rng.randint(0, n, 2000)] + 1e-3 * rng.randn(2000, 3)
+    qd = rng.randn(20000, 3)
+    for k in (32, 7):
+        rgb, knn, nc = ctx.gather(q, qd, k)
+        r2, k2, n2, _ = pm.gather(q, qd, k)
+        assert bits_equal(nc, n2)
+        assert bits_equal(knn, k2), f"{(knn != k2).any(axis=1).sum()} queries differ"
+        assert np.allclose(rgb, r2, rtol=1e-12, atol=0)
+    assert (nc == 0).sum() > 100 and nc.max() > 200
+
+
+def test_empty_and_tiny_photon_maps(ctx):
+    box = np.array([0.0, 0.0, 0.0, 1.0, 1.0, 1.0])
+    q = np.array([[0.5, 0.5, 0.5], [2.0, 2.0, 2.0]])
+    ctx.photon_upload(np.zeros((0, 9)))
+    ctx.photon_map_build(box)
+    rgb, knn, nc = ctx.gather(q, q, 32)
+    assert (nc == 0).all() and (rgb == 0).all() and (knn == 0xFFFFFFFF).all()
+    ph = np.random.RandomState(1).rand(9, 9)
+    ctx.photon_upload(ph)
+    ctx.photon_map_build(box)
+    rgb, knn, nc = ctx.gather(q, q, 32)
+    r2, k2, n2, _ = O.PMap(ph, box).gather(q, q, 32)
+    assert bits_equal(nc, n2) and bits_equal(knn, k2) and np.allclose(rgb, r2, rtol=1e-12, atol=0)
+
+
+@pytest.mark.parametrize("name", ["mixed", "cornell"])
+def test_photon_trace_vs_oracle(ctx, synth_dir, name):
+    sc = _load(name, synth_dir)
+    ctx.upload_scene(sc)
+    count = 3000
+    n, st = ctx.photon_trace(count, 5, seed=42)
+    got = ctx.photon_download()
+    ref, tries, traces = O.trace_photons(sc, count, 5, seed=42)
+    assert n == got.shape[0] and n > 0.5 * count
+    # same PRNG, same Halton points; only libm (sin/cos/acos/pow) differs by ulps, so nearly every photon coincides
+    assert abs(int(n) - ref.shape[0]) <= max(3, count // 500)
+    assert abs(int(st.photon_tries) - tries) <= max(20, tries // 200)
+    if n == ref.shape[0]:
+        close = np.isclose(got, ref, rtol=1e-7, atol=1e-9).all(axis=1)
+        assert close.mean() > 0.99, close.mean()
+    # the device map over the device photons equals the CPU map over the same photons
+    ctx.photon_map_build(None)
+    pm = O.PMap(got, sc.root_box)
+    b1, l1, c1, i1 = ctx.photon_map_download()
+    b2, l2, c2, i2 = pm.dump()
+    assert bits_equal(b1, b2) and bits_equal(i1, i2)
+
+
+@pytest.mark.parametrize("name,res,spp,depth", [("mixed", 40, 4, 8), ("cards", 32, 4, 4), ("cornell", 48, 4, 4), ("small", 24, 2, 3)])
+def test_render_radiance_vs_oracle(ctx, synth_dir, name, res, spp, depth):
+    """Same counter PRNG on both sides: per-pixel radiance agrees except where an ulp-level libm difference flips a
+    discrete decision.  Tolerance: >= 97 % of pixels within 1e-6 relative, mean luminance within 1 %."""
+    sc = _load(name, synth_dir)
+    ctx.upload_scene(sc)
+    nph = 3000 if sc.knobs.get("photons", 0) > 0 else 0
+    pm = None
+    if nph:
+        ctx.photon_trace(nph, 5, seed=7)
+        ph = ctx.photon_download()
+        ctx.photon_map_build(None)
+        pm = O.PMap(ph, sc.root_box)
+    else:
+        ctx.photon_upload(np.zeros((0, 9)))
+        ctx.photon_map_build(None)
+    P = render_params(res, res, spp, max_depth=depth, seed=99)
+    acc, st = ctx.render_tile(P, 0, 0, res, res, 0, spp)
+    ref, st2 = O.render(sc, pm, P, 0, 0, res, res, 0, spp)
+    assert st.closest_rays > 0 and abs(int(st.closest_rays) - int(st2.closest_rays)) <= 0.002 * st2.closest_rays + 4
+    assert abs(int(st.shadow_rays) - int(st2.shadow_rays)) <= 0.002 * st2.shadow_rays + 4
+    rel = np.abs(acc - ref).max(axis=1) / (np.abs(ref).max(axis=1) + 1e-12)
+    assert (rel < 1e-6).mean() >= 0.97, (rel < 1e-6).mean()
+    assert abs(acc.mean() - ref.mean()) <= 0.01 * abs(ref.mean()) + 1e-12
+    # resolve: 8-bit output within one level (pow differs by ulps)
+    img = ctx.resolve(acc, spp)
+    img2 = O.resolve(acc, spp)
+    assert np.abs(img.astype(int) - img2.astype(int)).max() <= 1
+
+
+def test_render_tiles_and_sample_ranges_compose(ctx, synth_dir):
+    """Size-independent properties: a frame equals the union of its tiles bit-for-bit, and sample ranges add up."""
+    sc = _load("mixed", synth_dir)
+    ctx.upload_scene(sc)
+    ctx.photon_trace(2000, 5, seed=3)
+    ctx.photon_map_build(None)
+    res, spp = 64, 4
+    P = render_params(res, res, spp, max_depth=6, seed=5)
+    full, _ = ctx.render_tile(P, 0, 0, res, res, 0, spp)
+    again, _ = ctx.render_tile(P, 0, 0, res, res, 0, spp)
+    assert bits_equal(full, again)
+    full = full.reshape(res, res, 3)
+    top, _ = ctx.render_tile(P, 0, 0, res, 24, 0, spp)
+    rest, _ = ctx.render_tile(P, 8, 24, 56, res, 0, spp)
+    assert bits_equal(top.reshape(24, res, 3), full[:24].copy())
+    assert bits_equal(rest.reshape(res - 24, 48, 3), full[24:, 8:56].copy())
+    a, _ = ctx.render_tile(P, 0, 0, res, res, 0, 1)
+    b, _ = ctx.render_tile(P, 0, 0, res, res, 1, spp)
+    assert np.allclose((a + b).reshape(res, res, 3), full, rtol=1e-13, atol=1e-300)
+
+
+@pytest.mark.skipif(not have_assets("cornell"), reason="assets not staged")
+def test_c1_full_size_primary_ids_vs_oracle(ctx):
+    """BASELINE config 1 at full size: every primary ray of the 512x512 frame (s = 0): ids and hit points bit-exact."""
+    from gi_raytracer_b200 import host
+    sc = host.load_scene(scene_path("cornell"))
+    ctx.upload_scene(sc)
+    o, d, ix = ctx.camera_rays(512, 512, 0, 0, 512, 512, 0, 1)
+    prim, hit, nrm, uv = ctx.trace_closest(o, d)
+    p2, h2, n2, uv2 = O.trace_closest(sc, o, d)
+    assert bits_equal(prim, p2) and bits_equal(hit, h2) and bits_equal(nrm, n2) and bits_equal(uv, uv2)
+
+
+def test_error_codes_and_empty_inputs(lib_built):
+    from gi_raytracer_b200.capi import Context, GiError
+    c = Context(0)
+    try:
+        with pytest.raises(GiError) as e:
+            c.trace_closest(np.zeros((4, 3)), np.ones((4, 3)))
+        assert e.value.code == -4   # GI_ERR_NO_SCENE
+        with pytest.raises(GiError) as e:
+            c.gather(np.zeros((4, 3)), np.ones((4, 3)))
+        assert e.value.code == -5   # GI_ERR_NO_PHOTONS
+        sc = R.scene_from_npz(np.load(os.path.join(os.path.dirname(__file__), "golden", "caustics_small.npz")))
+        c.upload_scene(sc)
+        prim, hit, nrm, uv = c.trace_closest(np.zeros((0, 3)), np.zeros((0, 3)))
+        assert prim.size == 0
+        with pytest.raises(GiError) as e:
+            c.render_tile(render_params(16, 16, 1), 0, 0, 32, 16, 0, 1)   # tile outside the frame
+        assert e.value.code == -1
+        bad = R.scene_from_npz(np.load(os.path.join(os.path.dirname(__file__), "golden", "caustics_small.npz")))
+        bad.leaf_prims[0] = 10 ** 9
+        with pytest.raises(GiError) as e:
+            c.upload_scene(bad)
+        assert e.value.code == -1
+    finally:
+        c.close()

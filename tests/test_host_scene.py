@@ -1,0 +1,72 @@
+"""Host-side scene path (csrc/host: loadScene, loadOBJ, Octree::rebuild/partition, flatten) against the reference's
+own loader and octree: golden dump for cornell, live oracle/_ref runs for the other scenes when it is available."""
+import os
+
+import numpy as np
+import pytest
+
+import refdump as R
+from conftest import bits_equal, have_assets, scene_path
+
+FIELDS = ("node_box", "node_child", "node_mask", "node_prim_off", "node_prim_cnt", "leaf_prims", "prim_type", "prim_geom", "prim_nrm", "prim_uv",
+          "prim_fnorm", "lights", "camera", "ambient")
+
+
+def assert_same_scene(mine, ref, textures_const=True):
+    for f in FIELDS:
+        assert bits_equal(getattr(mine, f), getattr(ref, f)), f
+    ma, mb = mine.mats[mine.prim_mat], ref.mats[ref.prim_mat]
+    for k in ("roughness", "opacity", "ior"):
+        assert np.array_equal(ma[k], mb[k]), k
+    if textures_const:
+        assert np.array_equal(mine.tex["a"][ma["diffuse_tex"]], ref.tex["a"][mb["diffuse_tex"]])
+
+
+@pytest.mark.skipif(not have_assets("cornell"), reason="reference assets not staged (make -C oracle assets)")
+def test_cornell_matches_reference_dump(lib_built, golden_cornell):
+    from gi_raytracer_b200 import host
+    mine = host.load_scene(scene_path("cornell"))
+    ref = R.scene_from_npz(golden_cornell)
+    assert_same_scene(mine, ref)
+    assert mine.knobs["photons"] == 750000 and mine.knobs["min_samples"] == 16 and mine.knobs["max_samples"] == 16
+
+
+@pytest.mark.ref
+@pytest.mark.skipif(not R.have_ref(), reason="oracle/_ref/gi_ref not built")
+@pytest.mark.parametrize("name", ["mixed", "cards", "small", "atrium"])
+def test_synthetic_scenes_match_reference_loader(lib_built, synth_dir, name):
+    """box / sphere keywords, checkerboard + image textures, root-leaf scenes, sliver geometry."""
+    from gi_raytracer_b200 import host
+    p = os.path.join(synth_dir, name + ".scn")
+    mine = host.load_scene(p)
+    d, meta = R.run_ref(p, ["scene"])
+    ref = R.scene_from_dump(d)
+    assert meta["entities"] == mine.n_prims and meta["nodes"] == mine.n_nodes
+    assert_same_scene(mine, ref, textures_const=(name in ("small", "atrium")))
+
+
+@pytest.mark.ref
+@pytest.mark.skipif(not (R.have_ref() and have_assets("glass")), reason="needs oracle/_ref and staged assets")
+@pytest.mark.parametrize("name", ["caustics", "glass"])
+def test_reference_scenes_match_reference_loader(lib_built, name):
+    from gi_raytracer_b200 import host
+    mine = host.load_scene(scene_path(name))
+    d, meta = R.run_ref(scene_path(name), ["scene"])
+    ref = R.scene_from_dump(d)
+    assert_same_scene(mine, ref, textures_const=(name != "glass"))
+
+
+def test_missing_scene_file_gives_empty_scene(lib_built):
+    """Like the reference, a missing file prints and continues (sceneLoader.cpp:29-33): the result is an empty scene."""
+    from gi_raytracer_b200 import host
+    sc = host.load_scene("/nonexistent/none.scn")
+    assert sc.n_prims == 0 and sc.n_nodes == 1 and sc.lights.shape[0] == 0
+
+
+def test_loader_tokenises_comments(tmp_path, lib_built):
+    """A scene keyword inside a comment is acted upon, as in the reference — here a stray `photons 123`."""
+    from gi_raytracer_b200 import host
+    p = tmp_path / "c.scn"
+    p.write_text("# stray photons 123 7 words\ncolorTex 1 1 1\nmat 0 0 1 1 1\nbox 0 0 0 1 1 1 0 0 0 0\n")
+    sc = host.load_scene(str(p))
+    assert sc.knobs["photons"] == 123 and sc.n_prims == 12

@@ -1,0 +1,98 @@
+"""The CPU restatement (oracle/gi_oracle.c) against fixtures produced by the reference itself (tests/golden/*.npz,
+written by tests/golden/make_golden.py from oracle/_ref/gi_ref).  Everything here is PRNG-free and must be bit-exact."""
+import numpy as np
+import pytest
+
+import oracle_lib as O
+import refdump as R
+from conftest import bits_equal
+
+
+def test_halton_sample_all_dims(golden_cornell):
+    g = golden_cornell
+    idx, val = g["halton_idx_u32"], g["halton_val_f32"]
+    L = O.lib()
+    for dim in range(256):
+        mine = np.array([L.go_halton_sample(dim, int(i)) for i in idx[::2]], dtype=np.float32)
+        assert bits_equal(mine, val[dim, ::2].copy()), f"Halton dim {dim}"
+
+
+def test_halton_enum_index_incl_wrap(golden_cornell):
+    g = golden_cornell
+    q, ref = g["henum_query_u32"].reshape(-1, 5), g["henum_index_u32"]
+    mine = np.concatenate([O.henum_index(int(w), int(h), [s], [x], [y]) for w, h, s, x, y in q])
+    assert bits_equal(mine, ref)
+    # the 3840x2160 rows include sample numbers past the u32 wrap
+    big = q[(q[:, 0] == 3840) & (q[:, 2] >= 480)]
+    assert big.shape[0] > 0
+
+
+def test_sampler_known_answers(golden_cornell):
+    g = golden_cornell
+    i, o = g["kat_in_f64"].reshape(-1, 13), g["kat_out_f64"].reshape(-1, 20)
+    L = O.lib()
+    mine = np.zeros_like(o)
+    buf = np.zeros(3)
+    p = lambda a: a.ctypes.data
+    for k in range(i.shape[0]):
+        n = np.ascontiguousarray(i[k, 0:3]); inc = np.ascontiguousarray(i[k, 3:6]); u, v, frac, rough, eta, a, b = i[k, 6:13]
+        L.go_hemisphere_cos(p(n), u, v, 2.0, p(buf)); mine[k, 0:3] = buf
+        d = float(n[0] * inc[0] + n[1] * inc[1] + n[2] * inc[2]); refl = np.ascontiguousarray(inc - n * d * 2.0)
+        L.go_sample_phong(p(refl), p(n), (1.0 / rough) + 1, float(u), float(v), p(buf)); mine[k, 3:6] = buf
+        L.go_sphere_cap_cos(p(n), u, v, 2.0, frac, p(buf)); mine[k, 6:9] = buf
+        L.go_sphere_cap_cos(p(n), u, v, 1.0, frac, p(buf)); mine[k, 9:12] = buf
+        L.go_random_unit_vec(float(u), float(v), p(buf)); mine[k, 12:15] = buf
+        L.go_refr(p(inc), p(n), eta, p(buf)); mine[k, 15:18] = buf
+        mine[k, 18] = L.go_fast_precise_pow(a, b); mine[k, 19] = L.go_fast_precise_pow(float(np.float32(1.0) - np.float32(u)), 0.5)
+    assert bits_equal(mine, o)
+
+
+@pytest.mark.parametrize("which", ["cornell", "caustics"])
+def test_rays_hits_shadows_photonmap_gather(which, golden_cornell, golden_caustics):
+    g = golden_cornell if which == "cornell" else golden_caustics
+    sc = R.scene_from_npz(g)
+    w, h, s0, s1 = [int(v) for v in g["meta_w_h_s0_s1"]]
+    # camera rays
+    o, d, ix = O.camera_rays(sc, w, h, 0, 0, w, h, s0, s1)
+    ro, rd = g["ray_o_f64"].reshape(-1, 3), g["ray_d_f64"].reshape(-1, 3)
+    assert bits_equal(ix, g["ray_idx_u32"]) and bits_equal(o, ro) and bits_equal(d, rd)
+    # closest hit: ids, hit points, shading normals, uvs — both the reference-order restatement and the ordered traversal
+    prim, hit, nrm, uv = O.trace_closest(sc, ro, rd)
+    assert bits_equal(prim, g["hit_id_u32"])
+    assert bits_equal(hit, g["hit_pos_f64"].reshape(-1, 3)) and bits_equal(nrm, g["hit_nrm_f64"].reshape(-1, 3)) and bits_equal(uv, g["hit_uv_f64"].reshape(-1, 2))
+    p2, h2, nn, npr = O.trace_closest_cot(sc, ro, rd)
+    assert bits_equal(p2, prim) and bits_equal(h2, hit)
+    assert nn.mean() > 5 and npr.mean() > 1
+    # shadow rays
+    vis = O.trace_any(sc, g["sh_o_f64"].reshape(-1, 3), g["sh_d_f64"].reshape(-1, 3), g["sh_maxt2_f64"])
+    assert bits_equal(vis, g["sh_vis_u8"])
+    # photon map cells (DFS pre-order) and contents
+    pm = O.PMap(g["photons_f64"].reshape(-1, 9), sc.root_box)
+    box, leaf, cnt, ids = pm.dump()
+    assert bits_equal(box, g["pm_box_f64"].reshape(-1, 6)) and bits_equal(leaf, g["pm_leaf_u8"]) and bits_equal(cnt, g["pm_cnt_u32"]) and bits_equal(ids, g["pm_refs_u32"])
+    # gather: candidate lists, 32-nearest sets, estimates
+    qp, qd = g["q_pos_f64"].reshape(-1, 3), g["q_dir_f64"].reshape(-1, 3)
+    rgb, knn, nc, dl = pm.gather(qp, qd)
+    off, cand = g["q_cand_off_u32"], g["q_cand_u32"]
+    assert bits_equal(nc, np.diff(off).astype(np.uint32))
+    for i in range(0, qp.shape[0], 17):
+        assert np.array_equal(pm.candidates(qp[i]), cand[off[i]:off[i + 1]])
+    rknn = g["q_knn_u32"].reshape(-1, 32)
+    assert all(set(a) == set(b) for a, b in zip(knn, rknn))
+    assert np.allclose(rgb, g["q_est_f64"].reshape(-1, 3), rtol=1e-12, atol=0)
+
+
+def test_child_boxes_tile_parent():
+    L = O.lib()
+    box = np.array([-1.25, 0.5, -3.0, 2.75, 4.5, 1.0])
+    out = np.zeros((8, 6))
+    L.go_child_boxes(box.ctypes.data, out.ctypes.data)
+    assert np.all(out[0, :3] == box[:3]) and np.all(out[7, 3:] == box[3:])
+    assert out[1, 0] == out[0, 3] and out[2, 2] == out[0, 5] and out[4, 1] == out[0, 4]
+
+
+def test_counter_rng_range_and_determinism():
+    L = O.lib()
+    v = np.array([L.go_rand(7, i, 3, 11) for i in range(2000)])
+    assert v.min() >= 0.0 and v.max() < 1.0 and abs(v.mean() - 0.5) < 0.03
+    assert L.go_rand(7, 5, 3, 11) == L.go_rand(7, 5, 3, 11) and L.go_rand(7, 5, 3, 11) != L.go_rand(8, 5, 3, 11)
