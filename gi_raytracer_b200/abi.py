@@ -56,6 +56,9 @@ class GiRenderParams(C.Structure):
 class GiStats(C.Structure):
     _fields_ = [("closest_rays", C.c_uint64), ("shadow_rays", C.c_uint64), ("gathers", C.c_uint64),
                 ("photon_tries", C.c_uint64), ("photons_stored", C.c_uint64), ("kernel_launches", C.c_uint64),
+                ("closest_node_tests", C.c_uint64), ("closest_prim_tests", C.c_uint64), ("shadow_node_tests", C.c_uint64),
+                ("shadow_prim_tests", C.c_uint64), ("gather_leaf_depth", C.c_uint64), ("gather_candidates", C.c_uint64),
+                ("gather_selected", C.c_uint64),
                 ("trace_ms", C.c_double), ("shadow_ms", C.c_double), ("gather_ms", C.c_double),
                 ("shade_ms", C.c_double), ("total_ms", C.c_double)]
 

@@ -22,6 +22,7 @@ API_SYMBOLS = [
     "gi_photon_map_build", "gi_photon_map_info", "gi_photon_map_download", "gi_photon_map_slab_size",
     "gi_photon_map_slab_ptr", "gi_photon_map_adopt_slab", "gi_photon_map_reserve_slab", "gi_photon_gather",
     "gi_photon_gather_dev", "gi_render_tile", "gi_render_tile_dev", "gi_resolve", "gi_resolve_dev", "gi_last_kernel_ms",
+    "gi_last_work",
 ]
 
 _LIB = None
@@ -77,6 +78,7 @@ def load_library():
     for f in (L.gi_resolve, L.gi_resolve_dev):
         f.argtypes = [vp, sz, vp, i32, vp]
     L.gi_last_kernel_ms.argtypes = [vp, C.c_char_p, C.POINTER(C.c_double), C.POINTER(u64)]
+    L.gi_last_work.argtypes = [vp, C.c_char_p, C.POINTER(u64 * 4)]
     # host-side scene facade (same library)
     L.gih_scene_load.argtypes = [C.c_char_p, i32, C.POINTER(vp)]
     L.gih_scene_desc.argtypes = [vp]
@@ -138,6 +140,11 @@ class Context:
         ms, n = C.c_double(), C.c_uint64()
         self._ck(self.L.gi_last_kernel_ms(self.h, family.encode(), C.byref(ms), C.byref(n)))
         return ms.value, n.value
+
+    def last_work(self, family):
+        out = (C.c_uint64 * 4)()
+        self._ck(self.L.gi_last_work(self.h, family.encode(), C.byref(out)))
+        return [int(v) for v in out]
 
     # -- scene ------------------------------------------------------------------------------------------------
     def upload_scene(self, scene: SceneArrays):

@@ -53,7 +53,8 @@ struct gi_ctx {
     DGatherMap G{};
     // workspaces
     DevBuf w0, w1, w2, w3, w4, w5, w6, w7, w8, w9;           // API staging
-    DevBuf q_a[5], q_b[5], hl[7], ps[3], b_cnt, b_accum, b_scan0, b_scan1, b_misc;
+    DevBuf q_a[5], q_b[5], hl[7], ps[3], b_cnt, b_accum, b_scan0, b_scan1, b_misc, b_work;
+    unsigned long long work_host[16] = { 0 };   // [0,1] closest nodes/prims, [2,3] any-hit, [4..6] gather depth/cand/sel, [8] rays, [9] shadow rays, [10] queries
     // timing
     std::vector<TimedLaunch> pending;
     std::vector<cudaEvent_t> event_pool;
@@ -85,8 +86,10 @@ struct ScopedTimer {   // records an event pair around the launches issued in it
     ~ScopedTimer() { cudaEventRecord(t.b, ctx->stream); ctx->pending.push_back(t); }
 };
 static void fam_reset(gi_ctx* ctx, const char* fam) { ctx->fam[fam] = FamStat(); }
+static unsigned long long* work_ptr(gi_ctx* ctx, int slot) { return ctx->b_work.as<unsigned long long>() + slot; }
 static void collect_timers(gi_ctx* ctx)   // after a stream sync
 {
+    if (ctx->b_work.p) cudaMemcpy(ctx->work_host, ctx->b_work.p, 8 * sizeof(unsigned long long), cudaMemcpyDeviceToHost);
     for (auto& t : ctx->pending) {
         float ms = 0;
         if (cudaEventElapsedTime(&ms, t.a, t.b) == cudaSuccess) { ctx->fam[t.fam].ms += ms; ctx->fam[t.fam].launches++; }
@@ -191,6 +194,8 @@ extern "C" int gi_create(int device, gi_ctx** out)
     if (ctx->b_htab.reserve(tab.size() * 2) != cudaSuccess || ctx->b_hdims.reserve(dims.size() * sizeof(DHaltonDim)) != cudaSuccess) { delete ctx; return GI_ERR_OOM; }
     cudaMemcpy(ctx->b_htab.p, tab.data(), tab.size() * 2, cudaMemcpyHostToDevice);
     cudaMemcpy(ctx->b_hdims.p, dims.data(), dims.size() * sizeof(DHaltonDim), cudaMemcpyHostToDevice);
+    if (ctx->b_work.reserve(16 * sizeof(unsigned long long)) != cudaSuccess) { delete ctx; return GI_ERR_OOM; }
+    cudaMemset(ctx->b_work.p, 0, 16 * sizeof(unsigned long long));
     ctx->S.halton_tab = ctx->b_htab.as<uint16_t>();
     ctx->S.halton_dims = ctx->b_hdims.as<DHaltonDim>();
     // deep local stacks (96 x u32 per thread) need no extra configuration; prefer L1 over shared for the traversal kernels
@@ -205,7 +210,7 @@ extern "C" void gi_destroy(gi_ctx* ctx)
     cudaStreamSynchronize(ctx->stream);
     DevBuf* all[] = { &ctx->b_nodes, &ctx->b_refs, &ctx->b_geom, &ctx->b_nrm, &ctx->b_uv, &ctx->b_fnorm, &ctx->b_pmat, &ctx->b_ptype, &ctx->b_mats, &ctx->b_tex, &ctx->b_texpx,
                       &ctx->b_lights, &ctx->b_htab, &ctx->b_hdims, &ctx->b_photons, &ctx->b_slab, &ctx->w0, &ctx->w1, &ctx->w2, &ctx->w3, &ctx->w4, &ctx->w5, &ctx->w6, &ctx->w7,
-                      &ctx->w8, &ctx->w9, &ctx->b_cnt, &ctx->b_accum, &ctx->b_scan0, &ctx->b_scan1, &ctx->b_misc };
+                      &ctx->w8, &ctx->w9, &ctx->b_cnt, &ctx->b_accum, &ctx->b_scan0, &ctx->b_scan1, &ctx->b_misc, &ctx->b_work };
     for (DevBuf* b : all) b->release();
     for (auto& b : ctx->q_a) b.release();
     for (auto& b : ctx->q_b) b.release();
@@ -224,6 +229,17 @@ extern "C" int gi_synchronize(gi_ctx* ctx)
     if (!ctx) return GI_ERR_INVALID;
     CK(cudaStreamSynchronize(ctx->stream));
     collect_timers(ctx);
+    return GI_OK;
+}
+extern "C" int gi_last_work(gi_ctx* ctx, const char* family, uint64_t out[4])
+{
+    if (!ctx || !family || !out) return GI_ERR_INVALID;
+    std::string f = family;
+    const unsigned long long* w = ctx->work_host;
+    if (f == "trace_closest") { out[0] = w[8]; out[1] = w[0]; out[2] = w[1]; out[3] = 0; }
+    else if (f == "trace_any") { out[0] = w[9]; out[1] = w[2]; out[2] = w[3]; out[3] = 0; }
+    else if (f == "gather") { out[0] = w[10]; out[1] = w[4]; out[2] = w[5]; out[3] = w[6]; }
+    else return GI_ERR_INVALID;
     return GI_OK;
 }
 extern "C" int gi_last_kernel_ms(gi_ctx* ctx, const char* family, double* ms, uint64_t* launches)
@@ -325,10 +341,8 @@ extern "C" int gi_scene_upload(gi_ctx* ctx, const gi_scene_desc* sc)
     for (int k = 0; k < 3; k++) S.ambient[k] = sc->ambient[k];
     S.full = full ? 1u : 0u;
     for (int k = 0; k < 6; k++) ctx->root_box[k] = sc->node_box[k];
-    ctx->has_scene = true;
-    ctx->has_map = false;
-    ctx->n_photons = 0;
-    return GI_OK;
+    ctx->has_scene = true;   // photons / photon map are independent state and survive a re-upload (the reference keeps its
+    return GI_OK;            // map across run() calls, raytracer.h:61); rebuild it explicitly when the geometry changed
 }
 
 // ---- Halton entry points --------------------------------------------------------------------------------------------------------------
@@ -388,10 +402,12 @@ extern "C" int gi_trace_closest_dev(gi_ctx* ctx, size_t n, const double* org, co
     if (!n) return GI_OK;
     CK(cudaSetDevice(ctx->device));
     fam_reset(ctx, "trace_closest");
+    CK(cudaMemsetAsync(work_ptr(ctx, 0), 0, 16, ctx->stream));
+    ctx->work_host[8] = n;
     {
         ScopedTimer t(ctx, "trace_closest");
-        if (ctx->S.full) k_trace_closest<true><<<grid_for(n, GI_BLOCK), GI_BLOCK, 0, ctx->stream>>>(ctx->S, n, org, dir, alpha_seed, prim, hit, normal, uv);
-        else k_trace_closest<false><<<grid_for(n, GI_BLOCK), GI_BLOCK, 0, ctx->stream>>>(ctx->S, n, org, dir, alpha_seed, prim, hit, normal, uv);
+        if (ctx->S.full) k_trace_closest<true><<<grid_for(n, GI_BLOCK), GI_BLOCK, 0, ctx->stream>>>(ctx->S, n, org, dir, alpha_seed, prim, hit, normal, uv, work_ptr(ctx, 0));
+        else k_trace_closest<false><<<grid_for(n, GI_BLOCK), GI_BLOCK, 0, ctx->stream>>>(ctx->S, n, org, dir, alpha_seed, prim, hit, normal, uv, work_ptr(ctx, 0));
     }
     CK(cudaGetLastError());
     return GI_OK;
@@ -422,10 +438,12 @@ extern "C" int gi_trace_any_dev(gi_ctx* ctx, size_t n, const double* org, const 
     if (!n) return GI_OK;
     CK(cudaSetDevice(ctx->device));
     fam_reset(ctx, "trace_any");
+    CK(cudaMemsetAsync(work_ptr(ctx, 2), 0, 16, ctx->stream));
+    ctx->work_host[9] = n;
     {
         ScopedTimer t(ctx, "trace_any");
-        if (ctx->S.full) k_trace_any<true><<<grid_for(n, GI_BLOCK), GI_BLOCK, 0, ctx->stream>>>(ctx->S, n, org, dir, maxt2, alpha_seed, vis);
-        else k_trace_any<false><<<grid_for(n, GI_BLOCK), GI_BLOCK, 0, ctx->stream>>>(ctx->S, n, org, dir, maxt2, alpha_seed, vis);
+        if (ctx->S.full) k_trace_any<true><<<grid_for(n, GI_BLOCK), GI_BLOCK, 0, ctx->stream>>>(ctx->S, n, org, dir, maxt2, alpha_seed, vis, work_ptr(ctx, 2));
+        else k_trace_any<false><<<grid_for(n, GI_BLOCK), GI_BLOCK, 0, ctx->stream>>>(ctx->S, n, org, dir, maxt2, alpha_seed, vis, work_ptr(ctx, 2));
     }
     CK(cudaGetLastError());
     return GI_OK;
@@ -503,7 +521,8 @@ extern "C" int gi_photon_trace(gi_ctx* ctx, int count, int max_depth, uint64_t s
     CK(ctx->b_photons.reserve(slots * 72));
     CK(cudaMemsetAsync(ctx->w1.p, 0, slots, ctx->stream));
     CK(cudaMemsetAsync(ctx->b_misc.p, 0, 64, ctx->stream));
-    DPhotonOut O{ ctx->w0.as<double>(), ctx->w1.as<uint8_t>(), ctx->b_misc.as<unsigned long long>(), ctx->b_misc.as<unsigned long long>() + 1 };
+    DPhotonOut O{ ctx->w0.as<double>(), ctx->w1.as<uint8_t>(), ctx->b_misc.as<unsigned long long>(), ctx->b_misc.as<unsigned long long>() + 1, work_ptr(ctx, 0) };
+    CK(cudaMemsetAsync(work_ptr(ctx, 0), 0, 16, ctx->stream));
     fam_reset(ctx, "photon_trace");
     cudaEvent_t e0 = get_event(ctx), e1 = get_event(ctx);
     cudaEventRecord(e0, ctx->stream);
@@ -529,7 +548,11 @@ extern "C" int gi_photon_trace(gi_ctx* ctx, int count, int max_depth, uint64_t s
     ctx->event_pool.push_back(e0); ctx->event_pool.push_back(e1);
     ctx->n_photons = (uint32_t)host[2];
     if (n_stored) *n_stored = ctx->n_photons;
-    if (stats) { stats->photon_tries = host[0]; stats->closest_rays = host[1]; stats->photons_stored = ctx->n_photons; stats->kernel_launches = 6; stats->total_ms = ms; stats->trace_ms = ctx->fam["photon_trace"].ms; }
+    ctx->work_host[8] = host[1];
+    if (stats) {
+        stats->photon_tries = host[0]; stats->closest_rays = host[1]; stats->photons_stored = ctx->n_photons; stats->kernel_launches = 6; stats->total_ms = ms;
+        stats->trace_ms = ctx->fam["photon_trace"].ms; stats->closest_node_tests = ctx->work_host[0]; stats->closest_prim_tests = ctx->work_host[1];
+    }
     return GI_OK;
 }
 
@@ -708,9 +731,11 @@ extern "C" int gi_photon_gather_dev(gi_ctx* ctx, size_t n, const double* pos, co
     if (!n) return GI_OK;
     CK(cudaSetDevice(ctx->device));
     fam_reset(ctx, "gather");
+    CK(cudaMemsetAsync(work_ptr(ctx, 4), 0, 24, ctx->stream));
+    ctx->work_host[10] = n;
     {
         ScopedTimer t(ctx, "gather");
-        k_gather<GI_GATHER_WARPS><<<grid_for(n, GI_GATHER_WARPS), GI_GATHER_WARPS * 32, 0, ctx->stream>>>(ctx->G, n, pos, dir, k, rgb, knn, n_cand, nullptr, nullptr, nullptr);
+        k_gather<GI_GATHER_WARPS><<<grid_for(n, GI_GATHER_WARPS), GI_GATHER_WARPS * 32, 0, ctx->stream>>>(ctx->G, n, pos, dir, k, rgb, knn, n_cand, nullptr, nullptr, nullptr, work_ptr(ctx, 4));
     }
     CK(cudaGetLastError());
     return GI_OK;
@@ -755,6 +780,7 @@ static int render_device(gi_ctx* ctx, const gi_render_params* P, int x0, int y0,
     const bool have_map = ctx->has_map && ctx->pm_kept > 0;
     uint64_t n_closest = 0, n_shadow = 0, n_gather = 0, launches = 0;
     for (const char* f : { "bounce", "direct", "gather" }) fam_reset(ctx, f);
+    CK(cudaMemsetAsync(work_ptr(ctx, 0), 0, 8 * sizeof(unsigned long long), ctx->stream));
     cudaEvent_t e0 = get_event(ctx), e1 = get_event(ctx);
     cudaEventRecord(e0, ctx->stream);
     CK(cudaMemsetAsync(accum_dev, 0, npx * 24, ctx->stream));
@@ -768,8 +794,8 @@ static int render_device(gi_ctx* ctx, const gi_render_params* P, int x0, int y0,
             CK(cudaMemsetAsync(C, 0, sizeof(DCounters), ctx->stream));
             {
                 ScopedTimer t(ctx, "bounce");
-                if (full) k_bounce<true><<<grid_for(n_active, GI_BLOCK), GI_BLOCK, 0, ctx->stream>>>(ctx->S, *P, depth, n_active, in, out, H, PS, C);
-                else k_bounce<false><<<grid_for(n_active, GI_BLOCK), GI_BLOCK, 0, ctx->stream>>>(ctx->S, *P, depth, n_active, in, out, H, PS, C);
+                if (full) k_bounce<true><<<grid_for(n_active, GI_BLOCK), GI_BLOCK, 0, ctx->stream>>>(ctx->S, *P, depth, n_active, in, out, H, PS, C, work_ptr(ctx, 0));
+                else k_bounce<false><<<grid_for(n_active, GI_BLOCK), GI_BLOCK, 0, ctx->stream>>>(ctx->S, *P, depth, n_active, in, out, H, PS, C, work_ptr(ctx, 0));
             }
             CK(cudaGetLastError());
             DCounters hc;
@@ -780,8 +806,8 @@ static int render_device(gi_ctx* ctx, const gi_render_params* P, int x0, int y0,
             if (hc.n_hits) {
                 if (ctx->S.n_lights) {
                     ScopedTimer t(ctx, "direct");
-                    if (full) k_direct<true><<<grid_for(hc.n_hits, GI_BLOCK), GI_BLOCK, 0, ctx->stream>>>(ctx->S, *P, depth, hc.n_hits, H, PS);
-                    else k_direct<false><<<grid_for(hc.n_hits, GI_BLOCK), GI_BLOCK, 0, ctx->stream>>>(ctx->S, *P, depth, hc.n_hits, H, PS);
+                    if (full) k_direct<true><<<grid_for(hc.n_hits, GI_BLOCK), GI_BLOCK, 0, ctx->stream>>>(ctx->S, *P, depth, hc.n_hits, H, PS, work_ptr(ctx, 2));
+                    else k_direct<false><<<grid_for(hc.n_hits, GI_BLOCK), GI_BLOCK, 0, ctx->stream>>>(ctx->S, *P, depth, hc.n_hits, H, PS, work_ptr(ctx, 2));
                     launches++;
                     n_shadow += (uint64_t)hc.n_hits * ctx->S.n_lights;
                 }
@@ -790,7 +816,7 @@ static int render_device(gi_ctx* ctx, const gi_render_params* P, int x0, int y0,
                     if (have_map) {
                         ScopedTimer t(ctx, "gather");
                         k_gather<GI_GATHER_WARPS><<<grid_for(hc.n_hits, GI_GATHER_WARPS), GI_GATHER_WARPS * 32, 0, ctx->stream>>>(ctx->G, hc.n_hits, H.p, H.refdir, P->k_photons, nullptr, nullptr,
-                                                                                                                          nullptr, H.wcaustic, PS.L, H.path);
+                                                                                                                          nullptr, H.wcaustic, PS.L, H.path, work_ptr(ctx, 4));
                         launches++;
                     }
                 }
@@ -812,6 +838,9 @@ static int render_device(gi_ctx* ctx, const gi_render_params* P, int x0, int y0,
         std::memset(stats, 0, sizeof(*stats));
         stats->closest_rays = n_closest; stats->shadow_rays = n_shadow; stats->gathers = n_gather; stats->kernel_launches = launches;
         stats->trace_ms = ctx->fam["bounce"].ms; stats->shadow_ms = ctx->fam["direct"].ms; stats->gather_ms = ctx->fam["gather"].ms; stats->total_ms = ms;
+        const unsigned long long* w = ctx->work_host;
+        stats->closest_node_tests = w[0]; stats->closest_prim_tests = w[1]; stats->shadow_node_tests = w[2]; stats->shadow_prim_tests = w[3];
+        stats->gather_leaf_depth = w[4]; stats->gather_candidates = w[5]; stats->gather_selected = w[6];
     }
     return GI_OK;
 }

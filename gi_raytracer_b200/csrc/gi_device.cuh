@@ -334,7 +334,7 @@ struct DHit {
 };
 
 template <bool FULL>
-__device__ __forceinline__ void trace_closest(const DScene& S, const DRay& r, uint64_t seed, uint64_t path, uint64_t depth, DHit& out)
+__device__ __forceinline__ void trace_closest(const DScene& S, const DRay& r, uint64_t seed, uint64_t path, uint64_t depth, DHit& out, uint32_t& n_node, uint32_t& n_prim)
 {
     uint32_t stack[GI_STACK_MAX];
     int sp = 0;
@@ -344,6 +344,7 @@ __device__ __forceinline__ void trace_closest(const DScene& S, const DRay& r, ui
     if (S.n_nodes == 0) return;
     {
         DNode root = load_node(S.nodes, 0);
+        n_node++;
         if (box_entry(root.bmin, root.bmax, r, 0.0, CUDART_INF) < 0.0) return;
         stack[sp++] = 0;
     }
@@ -353,6 +354,7 @@ __device__ __forceinline__ void trace_closest(const DScene& S, const DRay& r, ui
         DNode nd = load_node(S.nodes, ni);
         if (nd.mask == 0) {
             const DLeafRef* refs = S.refs + nd.prim_off;
+            n_prim += nd.prim_cnt;
             for (uint32_t k = 0; k < nd.prim_cnt; k++) {
                 const double2* rp = reinterpret_cast<const double2*>(refs + k);
                 double g[9];
@@ -386,6 +388,7 @@ __device__ __forceinline__ void trace_closest(const DScene& S, const DRay& r, ui
         // so that equal-distance children pop in child order)
         double t0c[8];
         uint32_t c = nd.child;
+        n_node += __popc(nd.mask);
 #pragma unroll
         for (int i = 0; i < 8; i++) {
             t0c[i] = -1.0;
@@ -411,7 +414,7 @@ __device__ __forceinline__ void trace_closest(const DScene& S, const DRay& r, ui
 // Returns true when nothing blocks the segment.  Visiting order is free: the alpha draw is keyed by the (leaf, primitive)
 // occurrence, so the outcome equals the reference's first-blocker search for any order.
 template <bool FULL>
-__device__ __forceinline__ bool trace_visible(const DScene& S, const DRay& r, double mt, uint64_t seed, uint64_t path, uint64_t depth, uint64_t light)
+__device__ __forceinline__ bool trace_visible(const DScene& S, const DRay& r, double mt, uint64_t seed, uint64_t path, uint64_t depth, uint64_t light, uint32_t& n_node, uint32_t& n_prim)
 {
     if (S.n_nodes == 0) return true;
     const double tmax = sqrt(mt) - GI_D_SHADOW_BIAS;   // raytracer.h:283
@@ -419,6 +422,7 @@ __device__ __forceinline__ bool trace_visible(const DScene& S, const DRay& r, do
     int sp = 0;
     {
         DNode root = load_node(S.nodes, 0);
+        n_node++;
         if (box_entry(root.bmin, root.bmax, r, 0.0, tmax) < 0.0) return true;
         stack[sp++] = 0;
     }
@@ -437,6 +441,7 @@ __device__ __forceinline__ bool trace_visible(const DScene& S, const DRay& r, do
                 uint32_t prim = tail.z, flags = tail.w;
                 double t, u = 0, v = 0; d3 cn;
                 bool ok;
+                n_prim++;
                 uint32_t kind = LF_KIND(flags);
                 if (kind == GI_PRIM_TRIANGLE) { t = tri_hit(g, r, u, v); ok = t > 0; }
                 else if (kind == GI_PRIM_SPHERE) ok = sphere_hit(g, r, t);
@@ -454,6 +459,7 @@ __device__ __forceinline__ bool trace_visible(const DScene& S, const DRay& r, do
             continue;
         }
         uint32_t c = nd.child;
+        n_node += __popc(nd.mask);
 #pragma unroll
         for (int i = 0; i < 8; i++) {
             if (nd.mask & (1u << i)) {
@@ -464,6 +470,16 @@ __device__ __forceinline__ bool trace_visible(const DScene& S, const DRay& r, do
         }
     }
     return true;
+}
+
+// add a per-thread pair of work counters into two global u64 tallies: warp shuffle reduction, one atomic pair per warp.
+// Must be called by all 32 lanes of the warp (inactive lanes pass zeros).
+__device__ __forceinline__ void tally2(unsigned long long* dst, uint32_t a, uint32_t b)
+{
+    unsigned long long x = a, y = b;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) { x += __shfl_down_sync(0xffffffffu, x, o); y += __shfl_down_sync(0xffffffffu, y, o); }
+    if ((threadIdx.x & 31) == 0 && dst) { if (x) atomicAdd(dst, x); if (y) atomicAdd(dst + 1, y); }
 }
 
 // ---- hit reconstruction: what RayTracer::trace hands back (hit point, shading normal, uv) from (prim, t, u, v) --------------

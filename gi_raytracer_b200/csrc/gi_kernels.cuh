@@ -53,29 +53,36 @@ __global__ void k_camera_rays(DScene S, DFrame F, int s0, size_t n, double* org,
 // ---- K2/K3 (API form): batch closest hit / any hit over caller-supplied rays --------------------------------------------------------
 template <bool FULL>
 __global__ void __launch_bounds__(GI_BLOCK) k_trace_closest(DScene S, size_t n, const double* __restrict__ org, const double* __restrict__ dir, uint64_t seed,
-                                                           uint32_t* __restrict__ prim, double* __restrict__ hit, double* __restrict__ normal, double* __restrict__ uv)
+                                                           uint32_t* __restrict__ prim, double* __restrict__ hit, double* __restrict__ normal, double* __restrict__ uv,
+                                                           unsigned long long* work)
 {
     size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    DRay r = ray_as_stored(ld3(org + 3 * i), ld3(dir + 3 * i));
-    DHit h;
-    trace_closest<FULL>(S, r, seed, (uint64_t)i, 0, h);
-    if (prim) prim[i] = h.prim;
-    d3 p = mk3(0, 0, 0), nn = mk3(0, 0, 0); double tu = 0, tv = 0;
-    if (h.prim != GI_NO_HIT) hit_surface(S, r, h, FULL, p, nn, tu, tv);
-    if (hit) st3(hit + 3 * i, p);
-    if (normal) st3(normal + 3 * i, nn);
-    if (uv) { uv[2 * i] = tu; uv[2 * i + 1] = tv; }
+    uint32_t nn_ = 0, np_ = 0;
+    if (i < n) {
+        DRay r = ray_as_stored(ld3(org + 3 * i), ld3(dir + 3 * i));
+        DHit h;
+        trace_closest<FULL>(S, r, seed, (uint64_t)i, 0, h, nn_, np_);
+        if (prim) prim[i] = h.prim;
+        d3 p = mk3(0, 0, 0), nn = mk3(0, 0, 0); double tu = 0, tv = 0;
+        if (h.prim != GI_NO_HIT) hit_surface(S, r, h, FULL, p, nn, tu, tv);
+        if (hit) st3(hit + 3 * i, p);
+        if (normal) st3(normal + 3 * i, nn);
+        if (uv) { uv[2 * i] = tu; uv[2 * i + 1] = tv; }
+    }
+    tally2(work, nn_, np_);
 }
 
 template <bool FULL>
 __global__ void __launch_bounds__(GI_BLOCK) k_trace_any(DScene S, size_t n, const double* __restrict__ org, const double* __restrict__ dir, const double* __restrict__ maxt2,
-                                                       uint64_t seed, uint8_t* __restrict__ vis)
+                                                       uint64_t seed, uint8_t* __restrict__ vis, unsigned long long* work)
 {
     size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    DRay r = ray_as_stored(ld3(org + 3 * i), ld3(dir + 3 * i));
-    vis[i] = trace_visible<FULL>(S, r, maxt2[i], seed, (uint64_t)i, 0, 0) ? 1 : 0;
+    uint32_t nn_ = 0, np_ = 0;
+    if (i < n) {
+        DRay r = ray_as_stored(ld3(org + 3 * i), ld3(dir + 3 * i));
+        vis[i] = trace_visible<FULL>(S, r, maxt2[i], seed, (uint64_t)i, 0, 0, nn_, np_) ? 1 : 0;
+    }
+    tally2(work, nn_, np_);
 }
 
 // ---- photon map (K6): level-synchronous build of PhotonMap::Node::partition (photonMap.cpp:137-192) --------------------------------
@@ -268,7 +275,8 @@ __device__ __forceinline__ void warp_merge32(double& d, uint32_t& id, uint32_t& 
 template <int WARPS>
 __global__ void __launch_bounds__(WARPS * 32) k_gather(DGatherMap M, size_t n, const double* __restrict__ qpos, const double* __restrict__ qdir, int k,
                                                      double* __restrict__ rgb, uint32_t* __restrict__ knn, uint32_t* __restrict__ ncand,
-                                                     const double* __restrict__ weight, double* __restrict__ accum, const uint32_t* __restrict__ accum_idx)
+                                                     const double* __restrict__ weight, double* __restrict__ accum, const uint32_t* __restrict__ accum_idx,
+                                                     unsigned long long* work)
 {
     __shared__ uint32_t s_stack[WARPS][GI_GATHER_STACK];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
@@ -276,10 +284,11 @@ __global__ void __launch_bounds__(WARPS * 32) k_gather(DGatherMap M, size_t n, c
     if (q >= n) return;
     d3 p = ld3(qpos + 3 * q), dq = ld3(qdir + 3 * q);
     // -- getBounds (photonMap.cpp:115-134): descend to the leaf whose half-open box contains p
-    uint32_t node = 0;
+    uint32_t node = 0, leaf_depth = 0;
     bool found = M.n_nodes > 0;
     DNode nd = load_node(M.nodes, 0);
     while (found && nd.mask != 0) {
+        leaf_depth++;
         bool in = false;
         if (lane < 8) { DNode ch = load_node(M.nodes, nd.child + lane); in = box_contains(ch.bmin, ch.bmax, p); }
         uint32_t b = __ballot_sync(0xffffffffu, in) & 0xffu;
@@ -355,6 +364,7 @@ __global__ void __launch_bounds__(WARPS * 32) k_gather(DGatherMap M, size_t n, c
     }
     if (knn && lane < k) knn[q * (size_t)k + lane] = lane < count ? best_id : GI_NO_HIT;
     if (lane == 0) {
+        if (work) { atomicAdd(work, (unsigned long long)leaf_depth); atomicAdd(work + 1, (unsigned long long)total); atomicAdd(work + 2, (unsigned long long)count); }
         if (rgb) st3(rgb + 3 * q, res);
         if (ncand) ncand[q] = total;
         if (accum) {   // render pipeline: L[path] += weight * caustic
@@ -381,14 +391,15 @@ struct DPathState { uint32_t* sample; uint64_t* key; double* L; };
 struct DCounters { uint32_t n_next, n_hits; unsigned long long closest, shadow, gathers; };
 
 template <bool FULL>
-__global__ void __launch_bounds__(GI_BLOCK) k_bounce(DScene S, gi_render_params P, int depth, uint32_t n, DQueue in, DQueue out, DHitList H, DPathState PS, DCounters* C)
+__global__ void __launch_bounds__(GI_BLOCK) k_bounce(DScene S, gi_render_params P, int depth, uint32_t n, DQueue in, DQueue out, DHitList H, DPathState PS, DCounters* C,
+                                                     unsigned long long* work)
 {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     bool active = i < n;
     bool is_hit = false, cont = false;
     d3 hp, hn, refDir, wdir, wcau, Tn, contrib;
     double rough = 1, offset = GI_D_SHADOW_BIAS;
-    uint32_t path = 0;
+    uint32_t path = 0, wn = 0, wp = 0;
     if (active) {
         path = in.path[i];
         DRay r = ray_as_stored(ld3(in.o + 3 * (size_t)i), ld3(in.d + 3 * (size_t)i));
@@ -398,7 +409,7 @@ __global__ void __launch_bounds__(GI_BLOCK) k_bounce(DScene S, gi_render_params 
         float sx = halton_sample(S, (uint32_t)(2 + 2 * depth), sample);     // raytracer.h:172-173
         float sy = halton_sample(S, (uint32_t)(3 + 2 * depth), sample);
         DHit h;
-        trace_closest<FULL>(S, r, P.seed, key, (uint64_t)depth, h);          // :190
+        trace_closest<FULL>(S, r, P.seed, key, (uint64_t)depth, h, wn, wp);  // :190
         double* L = PS.L + 3 * (size_t)path;
         if (h.prim == GI_NO_HIT) {
             d3 a = T * ld3(S.ambient);                                       // :275
@@ -426,6 +437,7 @@ __global__ void __launch_bounds__(GI_BLOCK) k_bounce(DScene S, gi_render_params 
             }
         }
     }
+    tally2(work, wn, wp);
     // queue compaction: warp ballot + prefix popcount, one atomic per warp and list
     const unsigned lane = threadIdx.x & 31u;
     unsigned mh = __ballot_sync(0xffffffffu, is_hit), mc = __ballot_sync(0xffffffffu, cont);
@@ -450,10 +462,11 @@ __global__ void __launch_bounds__(GI_BLOCK) k_bounce(DScene S, gi_render_params 
 
 // ---- K3 in the pipeline: direct light with one shadow ray per light (raytracer.h:230-256) -----------------------------------------
 template <bool FULL>
-__global__ void __launch_bounds__(GI_BLOCK) k_direct(DScene S, gi_render_params P, int depth, uint32_t n, DHitList H, DPathState PS)
+__global__ void __launch_bounds__(GI_BLOCK) k_direct(DScene S, gi_render_params P, int depth, uint32_t n, DHitList H, DPathState PS, unsigned long long* work)
 {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
+    uint32_t wn = 0, wp = 0;
+    if (i >= n) { tally2(work, 0, 0); return; }
     uint32_t path = H.path[i];
     uint64_t key = PS.key[path];
     d3 p = ld3(H.p + 3 * (size_t)i), nn = ld3(H.n + 3 * (size_t)i);
@@ -466,7 +479,7 @@ __global__ void __launch_bounds__(GI_BLOCK) k_direct(DScene S, gi_render_params 
         double maxt = len2(lightDir);
         double hfrac = 1 / (GI_D_PI * len2(ld3(light.pos) - p));                                                             // :238
         DRay sr = make_ray(sp, lightDir);                                                                                     // :241
-        if (trace_visible<FULL>(S, sr, maxt, P.seed, key, (uint64_t)depth, l)) {                                              // :243
+        if (trace_visible<FULL>(S, sr, maxt, P.seed, key, (uint64_t)depth, l, wn, wp)) {                                      // :243
             double d = dot3(nn, normalize3(ld3(light.pos) - p));
             if (d < 0) d = 0;
             double lv = pow_like_libm(d, (1.0 / rough));                                                                      // :252
@@ -476,6 +489,7 @@ __global__ void __launch_bounds__(GI_BLOCK) k_direct(DScene S, gi_render_params 
     d3 w = ld3(H.wdirect + 3 * (size_t)i) * li;
     double* L = PS.L + 3 * (size_t)path;
     L[0] += w.x; L[1] += w.y; L[2] += w.z;
+    tally2(work, wn, wp);
 }
 
 // generate the camera paths of one chunk (path-linear range [c0, c0+n) of the tile's sample-major path space)
@@ -529,13 +543,14 @@ __global__ void k_resolve(size_t n3, const double* accum, int spp, uint8_t* rgb8
 }
 
 // ---- K5: photon emission and tracing (raytracer.h:582-715) ----------------------------------------------------------------------------
-struct DPhotonOut { double* ph; uint8_t* stored; unsigned long long* tries; unsigned long long* traces; };
+struct DPhotonOut { double* ph; uint8_t* stored; unsigned long long* tries; unsigned long long* traces; unsigned long long* work; };
 
 template <bool FULL>
 __global__ void __launch_bounds__(GI_BLOCK) k_photon_trace(DScene S, int count, int max_depth, uint64_t seed, DPhotonOut O)
 {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     unsigned long long my_tries = 0, my_traces = 0;
+    uint32_t wn = 0, wp = 0;
     for (uint32_t li = 0; li < S.n_lights && i < count; li++) {
         const gi_light& l = S.lights[li];
         int tries = 0; bool stored = false;
@@ -551,14 +566,14 @@ __global__ void __launch_bounds__(GI_BLOCK) k_photon_trace(DScene S, int count, 
             d3 col = ld3(l.col) * ((1.0 / count) * .5 * l.angle);                               // :618
             int depth = 0; bool term = false, isCaustic = false;
             DHit h;
-            trace_closest<FULL>(S, r, seed, path, 0, h); my_traces++;
+            trace_closest<FULL>(S, r, seed, path, 0, h, wn, wp); my_traces++;
             if (h.prim == GI_NO_HIT) { tries++; continue; }                                     // :626-630
             uint32_t cur = h.prim;
             d3 hit = mk3(0, 0, 0);
             while (depth < max_depth && !term) {                                                // :633
                 double roughness = S.mats[S.prim_mat[cur]].roughness;
                 if (roughness < 0.1) {
-                    trace_closest<FULL>(S, r, seed, path, (uint64_t)(depth + 1), h); my_traces++;   // :640
+                    trace_closest<FULL>(S, r, seed, path, (uint64_t)(depth + 1), h, wn, wp); my_traces++;   // :640
                     if (h.prim == GI_NO_HIT) { term = true; continue; }
                     cur = h.prim;
                     d3 norm; double tu, tv;
@@ -590,6 +605,7 @@ __global__ void __launch_bounds__(GI_BLOCK) k_photon_trace(DScene S, int count, 
     // warp-aggregated tallies
     for (int o = 16; o > 0; o >>= 1) { my_tries += __shfl_down_sync(0xffffffffu, my_tries, o); my_traces += __shfl_down_sync(0xffffffffu, my_traces, o); }
     if ((threadIdx.x & 31) == 0) { atomicAdd(O.tries, my_tries); atomicAdd(O.traces, my_traces); }
+    tally2(O.work, wn, wp);
 }
 
 // stable compaction of the stored photons into (i, light) order: flags -> exclusive scan (k_scan_*) -> scatter

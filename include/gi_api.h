@@ -131,6 +131,11 @@ typedef struct gi_stats {
     uint64_t photon_tries;          /* emission tries       (raytracer.h:602)                           */
     uint64_t photons_stored;
     uint64_t kernel_launches;       /* kernels launched by the call                                     */
+    /* work of the canonical ordered traversal, tallied on the device: box tests / primitive tests    */
+    uint64_t closest_node_tests, closest_prim_tests;
+    uint64_t shadow_node_tests, shadow_prim_tests;
+    /* gather: sum of containing-leaf depths, of candidate counts C, and of min(k, C)                              */
+    uint64_t gather_leaf_depth, gather_candidates, gather_selected;
     double trace_ms, shadow_ms, gather_ms, shade_ms, total_ms; /* CUDA-event times of the phases        */
 } gi_stats;
 
@@ -215,6 +220,9 @@ int gi_resolve_dev(gi_ctx* ctx, size_t n_pixels, const double* accum, int spp, u
 /* ---- kernel-level hooks for bench.py's roofline (device buffers owned by the ctx) -------------------------- */
 /* average duration (ms) of the last launches of the named kernel family, measured with CUDA events on gi_stream */
 int gi_last_kernel_ms(gi_ctx* ctx, const char* family, double* ms, uint64_t* launches);
+/* device-side work tallies of the last call of a family: "trace_closest"/"trace_any": out = {rays, box tests, primitive
+ * tests, 0}; "gather": out = {queries, sum leaf depth, sum candidates, sum selected} */
+int gi_last_work(gi_ctx* ctx, const char* family, uint64_t out[4]);
 
 #ifdef __cplusplus
 }

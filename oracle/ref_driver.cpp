@@ -270,7 +270,7 @@ int main(int argc, char** argv)
 {
     if (argc < 3) {
         fprintf(stderr, "usage: gi_ref <scene.scn> <outdir> [--w W --h H --s0 A --s1 B --max-depth D --min-depth M --photons P --samples N --x0 --y0 --x1 --y1 --repeat R] cmd...\n"
-                        "cmds: scene halton samplers primary shadow photons gather radiance run time-frame time-gather\n");
+                        "cmds: scene halton samplers primary shadow photons gather radiance run time-frame time-gather bench-frame\n");
         return 1;
     }
     const char* scn = argv[1];
@@ -320,7 +320,7 @@ int main(int argc, char** argv)
     // -- primary rays + closest hit ------------------------------------------------------------------
     std::vector<double> hit_pos, hit_nrm, hit_uv, ray_o, ray_d;
     std::vector<uint32_t> hit_id, ray_idx;
-    if (has("primary") || has("shadow") || has("gather")) {
+    if (has("primary") || has("shadow") || has("gather") || has("time-gather")) {
         for (int s = s0; s < s1; s++) for (int y = y0; y < y1; y++) for (int x = x0; x < x1; x++) {
             int idx; Ray ray = camera_ray(rt, fr, sampler, he, w, h, x, y, s, idx);
             glm::dvec3 p(0), n(0); glm::dvec2 uv(0); Entity* cur = nullptr;
@@ -360,7 +360,7 @@ int main(int argc, char** argv)
 
     // -- photons ----------------------------------------------------------------------------------------
     double photon_s = 0;
-    if (has("photons") || has("gather") || has("run") || has("time-frame") || has("time-gather") || has("radiance")) {
+    if (has("photons") || has("gather") || has("run") || has("time-frame") || has("time-gather") || has("radiance") || has("bench-frame")) {
         counters_collect(); counters_reset();
         auto t0 = std::chrono::high_resolution_clock::now();
         rt.tracePhotons(5, rt.photons, sampler, he);                                 // raytracer.h:65
@@ -433,6 +433,7 @@ int main(int argc, char** argv)
                     }
                     auto g1 = std::chrono::high_resolution_clock::now();
                     best = std::min(best, std::chrono::duration<double>(g1 - g0).count());
+                    meta << "time_gather_s_" << r << "=" << std::chrono::duration<double>(g1 - g0).count() << "\n";
                     if (acc == 12345.678) printf("!");
                 }
                 meta << "time_gather_queries=" << nq << "\ntime_gather_s=" << best << "\n";
@@ -457,6 +458,33 @@ int main(int argc, char** argv)
         }
         dump("radiance.f64", img);
         meta << "radiance_spp=" << ns << "\n";
+    }
+
+    // -- CPU baseline for bench.py: the row loop of run() (raytracer.h:93-160) restricted to a tile of the w x h frame,
+    //    all OpenMP threads, photon map already valid; one timing per repeat ---------------------------------------
+    if (has("bench-frame")) {
+        int ns = rt.max_samples;
+        std::vector<double> img((size_t)(y1 - y0) * (x1 - x0) * 3);
+        for (int r = 0; r < repeat; r++) {
+            counters_collect(); counters_reset();
+            auto f0 = std::chrono::high_resolution_clock::now();
+#pragma omp parallel for schedule(dynamic, 10)
+            for (int y = y0; y < y1; ++y) for (int x = x0; x < x1; ++x) {
+                glm::dvec3 color(0.5, 0.5, 0.5);
+                for (int s = 0; s < ns; s++) {
+                    int idx; Ray ray = camera_ray(rt, fr, sampler, he, w, h, x, y, s, idx);
+                    glm::dvec3 L = rt.radiance(ray, 0, sampler, he, idx, glm::dvec3(1, 1, 1));
+                    color = (s == 0) ? L : (1.0 * s * color + L) * (1.0 / (s + 1));
+                }
+                size_t o = ((size_t)(y - y0) * (x1 - x0) + (x - x0)) * 3;
+                img[o] = color.x; img[o + 1] = color.y; img[o + 2] = color.z;
+            }
+            auto f1 = std::chrono::high_resolution_clock::now();
+            counters_collect();
+            meta << "bench_frame_s_" << r << "=" << std::chrono::duration<double>(f1 - f0).count() << "\n";
+            meta << "bench_frame_trace_rays_" << r << "=" << g_ntrace << "\nbench_frame_shadow_rays_" << r << "=" << g_nshadow << "\nbench_frame_gathers_" << r << "=" << g_ngather << "\n";
+        }
+        dump("bench_radiance.f64", img);
     }
 
     // -- the reference's own frame loop, timed (second call semantics: photon map already valid) -------
