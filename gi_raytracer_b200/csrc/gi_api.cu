@@ -4,6 +4,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <string>
@@ -53,7 +54,9 @@ struct gi_ctx {
     DGatherMap G{};
     // workspaces
     DevBuf w0, w1, w2, w3, w4, w5, w6, w7, w8, w9;           // API staging
-    DevBuf q_a[5], q_b[5], hl[7], ps[3], b_cnt, b_accum, b_scan0, b_scan1, b_misc, b_work;
+    DevBuf q_a[5], q_b[5], hl[7], ps[3], b_cnt, b_accum, b_scan0, b_scan1, b_misc, b_work, b_tail;
+    int trace_mode = 0;            // 0: thread per ray, 1: warp per ray (API batch kernels; GI_TRACE_MODE)
+    uint32_t tail_threshold = 32768; // queues smaller than this finish in the tail megakernel (GI_TAIL_THRESHOLD, 0 = off)
     unsigned long long work_host[16] = { 0 };   // [0,1] closest nodes/prims, [2,3] any-hit, [4..6] gather depth/cand/sel, [8] rays, [9] shadow rays, [10] queries
     // timing
     std::vector<TimedLaunch> pending;
@@ -90,9 +93,11 @@ static unsigned long long* work_ptr(gi_ctx* ctx, int slot) { return ctx->b_work.
 static void collect_timers(gi_ctx* ctx)   // after a stream sync
 {
     if (ctx->b_work.p) cudaMemcpy(ctx->work_host, ctx->b_work.p, 8 * sizeof(unsigned long long), cudaMemcpyDeviceToHost);
+    static const bool trace_launches = getenv("GI_TRACE_LAUNCHES") != nullptr;
     for (auto& t : ctx->pending) {
         float ms = 0;
         if (cudaEventElapsedTime(&ms, t.a, t.b) == cudaSuccess) { ctx->fam[t.fam].ms += ms; ctx->fam[t.fam].launches++; }
+        if (trace_launches) fprintf(stderr, "[gi] %-14s %9.4f ms\n", t.fam.c_str(), ms);
         ctx->event_pool.push_back(t.a); ctx->event_pool.push_back(t.b);
     }
     ctx->pending.clear();
@@ -198,7 +203,8 @@ extern "C" int gi_create(int device, gi_ctx** out)
     cudaMemset(ctx->b_work.p, 0, 16 * sizeof(unsigned long long));
     ctx->S.halton_tab = ctx->b_htab.as<uint16_t>();
     ctx->S.halton_dims = ctx->b_hdims.as<DHaltonDim>();
-    // deep local stacks (96 x u32 per thread) need no extra configuration; prefer L1 over shared for the traversal kernels
+    if (const char* e = getenv("GI_TRACE_MODE")) ctx->trace_mode = atoi(e);
+    if (const char* e = getenv("GI_TAIL_THRESHOLD")) ctx->tail_threshold = (uint32_t)strtoul(e, nullptr, 10);
     *out = ctx;
     return GI_OK;
 }
@@ -210,7 +216,7 @@ extern "C" void gi_destroy(gi_ctx* ctx)
     cudaStreamSynchronize(ctx->stream);
     DevBuf* all[] = { &ctx->b_nodes, &ctx->b_refs, &ctx->b_geom, &ctx->b_nrm, &ctx->b_uv, &ctx->b_fnorm, &ctx->b_pmat, &ctx->b_ptype, &ctx->b_mats, &ctx->b_tex, &ctx->b_texpx,
                       &ctx->b_lights, &ctx->b_htab, &ctx->b_hdims, &ctx->b_photons, &ctx->b_slab, &ctx->w0, &ctx->w1, &ctx->w2, &ctx->w3, &ctx->w4, &ctx->w5, &ctx->w6, &ctx->w7,
-                      &ctx->w8, &ctx->w9, &ctx->b_cnt, &ctx->b_accum, &ctx->b_scan0, &ctx->b_scan1, &ctx->b_misc, &ctx->b_work };
+                      &ctx->w8, &ctx->w9, &ctx->b_cnt, &ctx->b_accum, &ctx->b_scan0, &ctx->b_scan1, &ctx->b_misc, &ctx->b_work, &ctx->b_tail };
     for (DevBuf* b : all) b->release();
     for (auto& b : ctx->q_a) b.release();
     for (auto& b : ctx->q_b) b.release();
@@ -406,7 +412,10 @@ extern "C" int gi_trace_closest_dev(gi_ctx* ctx, size_t n, const double* org, co
     ctx->work_host[8] = n;
     {
         ScopedTimer t(ctx, "trace_closest");
-        if (ctx->S.full) k_trace_closest<true><<<grid_for(n, GI_BLOCK), GI_BLOCK, 0, ctx->stream>>>(ctx->S, n, org, dir, alpha_seed, prim, hit, normal, uv, work_ptr(ctx, 0));
+        if (ctx->trace_mode == 1) {
+            if (ctx->S.full) k_trace_closest_w<true><<<grid_for(n, GI_WPB), GI_WPB * 32, 0, ctx->stream>>>(ctx->S, n, org, dir, alpha_seed, prim, hit, normal, uv, work_ptr(ctx, 0));
+            else k_trace_closest_w<false><<<grid_for(n, GI_WPB), GI_WPB * 32, 0, ctx->stream>>>(ctx->S, n, org, dir, alpha_seed, prim, hit, normal, uv, work_ptr(ctx, 0));
+        } else if (ctx->S.full) k_trace_closest<true><<<grid_for(n, GI_BLOCK), GI_BLOCK, 0, ctx->stream>>>(ctx->S, n, org, dir, alpha_seed, prim, hit, normal, uv, work_ptr(ctx, 0));
         else k_trace_closest<false><<<grid_for(n, GI_BLOCK), GI_BLOCK, 0, ctx->stream>>>(ctx->S, n, org, dir, alpha_seed, prim, hit, normal, uv, work_ptr(ctx, 0));
     }
     CK(cudaGetLastError());
@@ -442,7 +451,10 @@ extern "C" int gi_trace_any_dev(gi_ctx* ctx, size_t n, const double* org, const 
     ctx->work_host[9] = n;
     {
         ScopedTimer t(ctx, "trace_any");
-        if (ctx->S.full) k_trace_any<true><<<grid_for(n, GI_BLOCK), GI_BLOCK, 0, ctx->stream>>>(ctx->S, n, org, dir, maxt2, alpha_seed, vis, work_ptr(ctx, 2));
+        if (ctx->trace_mode == 1) {
+            if (ctx->S.full) k_trace_any_w<true><<<grid_for(n, GI_WPB), GI_WPB * 32, 0, ctx->stream>>>(ctx->S, n, org, dir, maxt2, alpha_seed, vis, work_ptr(ctx, 2));
+            else k_trace_any_w<false><<<grid_for(n, GI_WPB), GI_WPB * 32, 0, ctx->stream>>>(ctx->S, n, org, dir, maxt2, alpha_seed, vis, work_ptr(ctx, 2));
+        } else if (ctx->S.full) k_trace_any<true><<<grid_for(n, GI_BLOCK), GI_BLOCK, 0, ctx->stream>>>(ctx->S, n, org, dir, maxt2, alpha_seed, vis, work_ptr(ctx, 2));
         else k_trace_any<false><<<grid_for(n, GI_BLOCK), GI_BLOCK, 0, ctx->stream>>>(ctx->S, n, org, dir, maxt2, alpha_seed, vis, work_ptr(ctx, 2));
     }
     CK(cudaGetLastError());
@@ -557,8 +569,8 @@ extern "C" int gi_photon_trace(gi_ctx* ctx, int count, int max_depth, uint64_t s
 }
 
 // ---- photon map ---------------------------------------------------------------------------------------------------------------------------
-struct SlabHeader { uint32_t magic, n_nodes, n_kept, n_leaves, max_depth, pad[3]; uint64_t off_nodes, off_pos, off_dircol, off_pid, total; };
-#define GI_SLAB_MAGIC 0x47495031u   // "GIP1"
+struct SlabHeader { uint32_t magic, n_nodes, n_kept, n_leaves, max_depth, n_cand, pad[2]; uint64_t off_nodes, off_pos, off_dircol, off_pid, off_cand_off, off_cand_slot, total; };
+#define GI_SLAB_MAGIC 0x47495032u   // "GIP2"
 static inline size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
 
 static void bind_slab(gi_ctx* ctx, const SlabHeader& h)
@@ -568,6 +580,8 @@ static void bind_slab(gi_ctx* ctx, const SlabHeader& h)
     ctx->G.pos = reinterpret_cast<const double*>(base + h.off_pos);
     ctx->G.dircol = reinterpret_cast<const double*>(base + h.off_dircol);
     ctx->G.pid = reinterpret_cast<const uint32_t*>(base + h.off_pid);
+    ctx->G.cand_off = reinterpret_cast<const uint32_t*>(base + h.off_cand_off);
+    ctx->G.cand_slot = reinterpret_cast<const uint32_t*>(base + h.off_cand_slot);
     ctx->G.n_nodes = h.n_nodes;
     ctx->pm_nodes = h.n_nodes; ctx->pm_kept = h.n_kept; ctx->pm_leaves = h.n_leaves; ctx->pm_depth = h.max_depth;
     ctx->slab_bytes = h.total;
@@ -623,15 +637,31 @@ extern "C" int gi_photon_map_build(gi_ctx* ctx, const double* box6)
     CK(cudaMemcpyAsync(host_cnt, ctx->w3.p, 12, cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
     const uint32_t n_kept = host_cnt[1];
-    // compact slab: header | nodes | pos | dircol | pid
+    // per-leaf candidate lists (Node::get run once per leaf): count -> scan -> fill
+    CK(ctx->w6.reserve((size_t)(n_nodes + 1) * 4)); CK(ctx->w7.reserve((size_t)(n_nodes + 1) * 4));
+    uint32_t* cand_cnt = ctx->w6.as<uint32_t>();
+    uint32_t* cand_off = ctx->w7.as<uint32_t>();
+    k_pm_cands<4, false><<<grid_for(n_nodes, 4), 128, 0, ctx->stream>>>(M.nodes, n_nodes, cand_cnt, nullptr, nullptr, M.overflow);
+    CK(cudaGetLastError());
+    rc = scan_exclusive(ctx, cand_cnt, 1, n_nodes, cand_off, cand_off + n_nodes);
+    if (rc != GI_OK) return rc;
+    CK(cudaMemcpyAsync(host_cnt, cand_off + n_nodes, 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaMemcpyAsync(host_cnt + 2, M.overflow, 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    if (host_cnt[2]) return fail(ctx, GI_ERR_OOM, "photon map candidate traversal stack overflow");
+    const uint32_t n_cand = host_cnt[0];
+    // compact slab: header | nodes | pos | dircol | pid | cand_off | cand_slot
     SlabHeader h{};
-    h.magic = GI_SLAB_MAGIC; h.n_nodes = n_nodes; h.n_kept = n_kept; h.max_depth = depth;
+    h.magic = GI_SLAB_MAGIC; h.n_nodes = n_nodes; h.n_kept = n_kept; h.max_depth = depth; h.n_cand = n_cand;
     h.off_nodes = 256; h.off_pos = align256(h.off_nodes + (size_t)n_nodes * sizeof(DNode)); h.off_dircol = align256(h.off_pos + (size_t)n_kept * 24);
-    h.off_pid = align256(h.off_dircol + (size_t)n_kept * 48); h.total = align256(h.off_pid + (size_t)n_kept * 4);
+    h.off_pid = align256(h.off_dircol + (size_t)n_kept * 48); h.off_cand_off = align256(h.off_pid + (size_t)n_kept * 4);
+    h.off_cand_slot = align256(h.off_cand_off + (size_t)(n_nodes + 1) * 4); h.total = align256(h.off_cand_slot + (size_t)n_cand * 4);
     CK(ctx->b_slab.reserve(h.total));
     char* base = ctx->b_slab.as<char>();
     CK(cudaMemcpyAsync(base + h.off_nodes, M.nodes, (size_t)n_nodes * sizeof(DNode), cudaMemcpyDeviceToDevice, ctx->stream));
     if (n_kept) CK(cudaMemcpyAsync(base + h.off_pid, M.pid, (size_t)n_kept * 4, cudaMemcpyDeviceToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(base + h.off_cand_off, cand_off, (size_t)(n_nodes + 1) * 4, cudaMemcpyDeviceToDevice, ctx->stream));
+    k_pm_cands<4, true><<<grid_for(n_nodes, 4), 128, 0, ctx->stream>>>(M.nodes, n_nodes, nullptr, cand_off, reinterpret_cast<uint32_t*>(base + h.off_cand_slot), M.overflow);
     M.pos = reinterpret_cast<double*>(base + h.off_pos); M.dircol = reinterpret_cast<double*>(base + h.off_dircol);
     if (n_kept) k_pm_payload<<<grid_for(n_kept, 256), 256, 0, ctx->stream>>>(M, n_kept);
     CK(cudaGetLastError());
@@ -717,7 +747,7 @@ extern "C" int gi_photon_map_adopt_slab(gi_ctx* ctx, size_t bytes)
     CK(cudaSetDevice(ctx->device));
     SlabHeader h;
     CK(cudaMemcpy(&h, ctx->b_slab.p, sizeof(h), cudaMemcpyDeviceToHost));
-    if (h.magic != GI_SLAB_MAGIC || h.total != bytes || h.off_pid + (uint64_t)h.n_kept * 4 > bytes) return fail(ctx, GI_ERR_INVALID, "bad photon map slab");
+    if (h.magic != GI_SLAB_MAGIC || h.total != bytes || h.off_pid + (uint64_t)h.n_kept * 4 > bytes || h.off_cand_slot + (uint64_t)h.n_cand * 4 > bytes) return fail(ctx, GI_ERR_INVALID, "bad photon map slab");
     bind_slab(ctx, h);
     return GI_OK;
 }
@@ -770,6 +800,8 @@ static int render_device(gi_ctx* ctx, const gi_render_params* P, int x0, int y0,
     CK(ctx->hl[5].reserve((size_t)chunk_cap * 8)); CK(ctx->hl[6].reserve((size_t)chunk_cap * 4));
     CK(ctx->ps[0].reserve((size_t)chunk_cap * 4)); CK(ctx->ps[1].reserve((size_t)chunk_cap * 8)); CK(ctx->ps[2].reserve((size_t)chunk_cap * 24));
     CK(ctx->b_cnt.reserve(sizeof(DCounters)));
+    CK(ctx->b_tail.reserve(sizeof(DTailCounters)));
+    CK(cudaMemsetAsync(ctx->b_tail.p, 0, sizeof(DTailCounters), ctx->stream));
     DQueue qa{ ctx->q_a[0].as<double>(), ctx->q_a[1].as<double>(), ctx->q_a[2].as<double>(), ctx->q_a[3].as<double>(), ctx->q_a[4].as<uint32_t>() };
     DQueue qb{ ctx->q_b[0].as<double>(), ctx->q_b[1].as<double>(), ctx->q_b[2].as<double>(), ctx->q_b[3].as<double>(), ctx->q_b[4].as<uint32_t>() };
     DHitList H{ ctx->hl[0].as<double>(), ctx->hl[1].as<double>(), ctx->hl[2].as<double>(), ctx->hl[3].as<double>(), ctx->hl[4].as<double>(), ctx->hl[5].as<double>(), ctx->hl[6].as<uint32_t>() };
@@ -779,7 +811,7 @@ static int render_device(gi_ctx* ctx, const gi_render_params* P, int x0, int y0,
     const bool full = ctx->S.full != 0;
     const bool have_map = ctx->has_map && ctx->pm_kept > 0;
     uint64_t n_closest = 0, n_shadow = 0, n_gather = 0, launches = 0;
-    for (const char* f : { "bounce", "direct", "gather" }) fam_reset(ctx, f);
+    for (const char* f : { "bounce", "direct", "gather", "tail" }) fam_reset(ctx, f);
     CK(cudaMemsetAsync(work_ptr(ctx, 0), 0, 8 * sizeof(unsigned long long), ctx->stream));
     cudaEvent_t e0 = get_event(ctx), e1 = get_event(ctx);
     cudaEventRecord(e0, ctx->stream);
@@ -791,6 +823,17 @@ static int render_device(gi_ctx* ctx, const gi_render_params* P, int x0, int y0,
         DQueue in = qa, out = qb;
         uint32_t n_active = n;
         for (int depth = 0; n_active > 0 && depth <= P->max_depth; depth++) {
+            if (depth > 0 && n_active < ctx->tail_threshold) {
+                // few paths left: one warp per path runs them to the end inside one kernel
+                ScopedTimer t(ctx, "tail");
+                CK(cudaMemsetAsync(&ctx->b_tail.as<DTailCounters>()->next, 0, 4, ctx->stream));
+                const unsigned tail_grid = std::min<unsigned>(grid_for(n_active, GI_WPB), 148u * 3u);   // 3 blocks of 4 warps fit per SM at 168 registers
+                if (full) k_tail<true><<<tail_grid, GI_WPB * 32, 0, ctx->stream>>>(ctx->S, ctx->G, have_map ? 1 : 0, *P, depth, n_active, in, PS, ctx->b_tail.as<DTailCounters>());
+                else k_tail<false><<<tail_grid, GI_WPB * 32, 0, ctx->stream>>>(ctx->S, ctx->G, have_map ? 1 : 0, *P, depth, n_active, in, PS, ctx->b_tail.as<DTailCounters>());
+                launches++;
+                CK(cudaGetLastError());
+                break;
+            }
             CK(cudaMemsetAsync(C, 0, sizeof(DCounters), ctx->stream));
             {
                 ScopedTimer t(ctx, "bounce");
@@ -822,6 +865,11 @@ static int render_device(gi_ctx* ctx, const gi_render_params* P, int x0, int y0,
                 }
                 CK(cudaGetLastError());
             }
+            if (getenv("GI_TRACE_LAUNCHES")) {
+                unsigned long long wk[8];
+                cudaMemcpy(wk, ctx->b_work.p, sizeof(wk), cudaMemcpyDeviceToHost);
+                fprintf(stderr, "[gi] depth %2d active %9u hits %9u next %9u | cum closest nodes %llu prims %llu | shadow nodes %llu prims %llu\n", depth, n_active, hc.n_hits, hc.n_next, wk[0], wk[1], wk[2], wk[3]);
+            }
             n_active = hc.n_next;
             std::swap(in, out);
         }
@@ -830,14 +878,19 @@ static int render_device(gi_ctx* ctx, const gi_render_params* P, int x0, int y0,
         CK(cudaGetLastError());
     }
     cudaEventRecord(e1, ctx->stream);
+    DTailCounters tc;
+    CK(cudaMemcpyAsync(&tc, ctx->b_tail.p, sizeof(tc), cudaMemcpyDeviceToHost, ctx->stream));
     int rc = gi_synchronize(ctx);
     if (rc != GI_OK) return rc;
     float ms = 0; cudaEventElapsedTime(&ms, e0, e1);
     ctx->event_pool.push_back(e0); ctx->event_pool.push_back(e1);
+    n_closest += tc.closest; n_shadow += tc.shadow; n_gather += tc.gathers;
+    ctx->work_host[0] += tc.nodes_c; ctx->work_host[1] += tc.prims_c; ctx->work_host[2] += tc.nodes_s; ctx->work_host[3] += tc.prims_s;
+    ctx->work_host[4] += tc.g_depth; ctx->work_host[5] += tc.g_cand; ctx->work_host[6] += tc.g_sel;
     if (stats) {
         std::memset(stats, 0, sizeof(*stats));
         stats->closest_rays = n_closest; stats->shadow_rays = n_shadow; stats->gathers = n_gather; stats->kernel_launches = launches;
-        stats->trace_ms = ctx->fam["bounce"].ms; stats->shadow_ms = ctx->fam["direct"].ms; stats->gather_ms = ctx->fam["gather"].ms; stats->total_ms = ms;
+        stats->trace_ms = ctx->fam["bounce"].ms; stats->shadow_ms = ctx->fam["direct"].ms; stats->gather_ms = ctx->fam["gather"].ms; stats->shade_ms = ctx->fam["tail"].ms; stats->total_ms = ms;
         const unsigned long long* w = ctx->work_host;
         stats->closest_node_tests = w[0]; stats->closest_prim_tests = w[1]; stats->shadow_node_tests = w[2]; stats->shadow_prim_tests = w[3];
         stats->gather_leaf_depth = w[4]; stats->gather_candidates = w[5]; stats->gather_selected = w[6];

@@ -472,6 +472,168 @@ __device__ __forceinline__ bool trace_visible(const DScene& S, const DRay& r, do
     return true;
 }
 
+// ---- warp-cooperative traversals: one ray per warp --------------------------------------------------------------------------
+// For incoherent rays and for the long tail of deep paths a thread-per-ray walk serialises 32 different control flows; here
+// the 32 lanes of a warp work on ONE ray: lanes 0..7 test the eight child boxes of an interior node, all lanes test up to
+// 32 primitives of a leaf at once (geometry only), and the reference's sequential acceptance rule is then replayed over
+// the geometric hits in stored order (there are rarely more than one or two per leaf).  Same visiting order, same
+// arithmetic, same results as trace_closest / trace_visible; `stack` is GI_STACK_MAX words of shared memory per warp.
+template <bool FULL>
+__device__ __forceinline__ void trace_closest_warp(const DScene& S, const DRay& r, uint64_t seed, uint64_t path, uint64_t depth, DHit& out, uint32_t* stack, int lane,
+                                                   uint32_t& n_node, uint32_t& n_prim)
+{
+    int sp = 0;
+    out.prim = GI_NO_HIT; out.t = 0; out.u = 0; out.v = 0; out.tu = 0; out.tv = 0; out.n = mk3(0, 0, 0);
+    double best_d2 = 0, cur_tu = 0, cur_tv = 0;
+    if (S.n_nodes == 0) return;
+    {
+        DNode root = load_node(S.nodes, 0);
+        n_node++;
+        if (box_entry(root.bmin, root.bmax, r, 0.0, CUDART_INF) < 0.0) return;
+        if (lane == 0) stack[0] = 0;
+        sp = 1;
+        __syncwarp();
+    }
+    bool term = false;
+    while (sp > 0 && !term) {
+        uint32_t ni = stack[sp - 1]; sp--;
+        __syncwarp();
+        DNode nd = load_node(S.nodes, ni);
+        if (nd.mask == 0) {
+            n_prim += nd.prim_cnt;
+            for (uint32_t base = 0; base < nd.prim_cnt; base += 32) {
+                bool have = base + lane < nd.prim_cnt;
+                double t = 0, u = 0, v = 0; d3 cn = mk3(0, 0, 0);
+                uint32_t prim = 0, flags = 0;
+                bool ok = false;
+                if (have) {
+                    const double2* rp = reinterpret_cast<const double2*>(S.refs + nd.prim_off + base + lane);
+                    double g[9];
+                    double2 a0 = __ldg(rp), a1 = __ldg(rp + 1), a2 = __ldg(rp + 2), a3 = __ldg(rp + 3);
+                    g[0] = a0.x; g[1] = a0.y; g[2] = a1.x; g[3] = a1.y; g[4] = a2.x; g[5] = a2.y; g[6] = a3.x; g[7] = a3.y;
+                    uint4 tail = __ldg(reinterpret_cast<const uint4*>(rp + 4));
+                    g[8] = __hiloint2double((int)tail.y, (int)tail.x);
+                    prim = tail.z; flags = tail.w;
+                    uint32_t kind = LF_KIND(flags);
+                    if (kind == GI_PRIM_TRIANGLE) { t = tri_hit(g, r, u, v); ok = t > 0; }
+                    else if (kind == GI_PRIM_SPHERE) ok = sphere_hit(g, r, t);
+                    else ok = cone_hit(g, S.prim_nrm + 9 * (size_t)prim, r, t, cn);
+                }
+                uint32_t hm = __ballot_sync(0xffffffffu, ok);
+                while (hm) {   // replay the sequential acceptance over the geometric hits, in stored order
+                    int src = __ffs(hm) - 1; hm &= hm - 1;
+                    double ct = __shfl_sync(0xffffffffu, t, src), cu = __shfl_sync(0xffffffffu, u, src), cv = __shfl_sync(0xffffffffu, v, src);
+                    uint32_t cprim = __shfl_sync(0xffffffffu, prim, src), cflags = __shfl_sync(0xffffffffu, flags, src);
+                    d3 ccn = mk3(0, 0, 0);
+                    if (LF_KIND(cflags) == GI_PRIM_CONE) ccn = mk3(__shfl_sync(0xffffffffu, cn.x, src), __shfl_sync(0xffffffffu, cn.y, src), __shfl_sync(0xffffffffu, cn.z, src));
+                    d3 hit = r.o + r.d * ct;
+                    if (FULL) {
+                        if (cflags & LF_WRITES_UV) prim_uv_at(S, cprim, hit, cu, cv, cur_tu, cur_tv);
+                        if ((cflags & LF_ALPHA) && !alpha_pass(S, cprim, ni, cur_tu, cur_tv, seed, path, depth, SITE_ALPHA_TRACE)) continue;
+                    }
+                    double d2 = len2(hit - r.o);
+                    if (out.prim == GI_NO_HIT || d2 < best_d2) {
+                        out.prim = cprim; out.t = ct; out.u = cu; out.v = cv; out.n = ccn; best_d2 = d2;
+                        if (FULL) { out.tu = cur_tu; out.tv = cur_tv; }
+                        if (box_contains(nd.bmin, nd.bmax, hit)) term = true;
+                    }
+                }
+            }
+            continue;
+        }
+        n_node += __popc(nd.mask);
+        double t0 = -1.0; uint32_t cidx = 0;
+        if (lane < 8 && ((nd.mask >> lane) & 1u)) {
+            cidx = nd.child + __popc(nd.mask & ((1u << lane) - 1u));
+            DNode ch = load_node(S.nodes, cidx);
+            t0 = box_entry(ch.bmin, ch.bmax, r, 0.0, CUDART_INF);
+        }
+        uint32_t valid = __ballot_sync(0xffffffffu, t0 >= 0.0) & 0xffu;
+        // far-to-near on the stack: rank = children that come before me in descending (t0, child index) order
+        int rank = 0;
+#pragma unroll
+        for (int j = 0; j < 8; j++) {
+            double tj = __shfl_sync(0xffffffffu, t0, j);
+            if (((valid >> j) & 1u) && j != lane && (tj > t0 || (tj == t0 && j > lane))) rank++;
+        }
+        if (t0 >= 0.0 && sp + rank < GI_STACK_MAX) stack[sp + rank] = cidx;
+        sp += __popc(valid);
+        if (sp > GI_STACK_MAX) sp = GI_STACK_MAX;
+        __syncwarp();
+    }
+}
+
+template <bool FULL>
+__device__ __forceinline__ bool trace_visible_warp(const DScene& S, const DRay& r, double mt, uint64_t seed, uint64_t path, uint64_t depth, uint64_t light, uint32_t* stack,
+                                                   int lane, uint32_t& n_node, uint32_t& n_prim)
+{
+    if (S.n_nodes == 0) return true;
+    const double tmax = sqrt(mt) - GI_D_SHADOW_BIAS;   // raytracer.h:283
+    int sp = 0;
+    {
+        DNode root = load_node(S.nodes, 0);
+        n_node++;
+        if (box_entry(root.bmin, root.bmax, r, 0.0, tmax) < 0.0) return true;
+        if (lane == 0) stack[0] = 0;
+        sp = 1;
+        __syncwarp();
+    }
+    while (sp > 0) {
+        uint32_t ni = stack[sp - 1]; sp--;
+        __syncwarp();
+        DNode nd = load_node(S.nodes, ni);
+        if (nd.mask == 0) {
+            for (uint32_t base = 0; base < nd.prim_cnt; base += 32) {
+                bool have = base + lane < nd.prim_cnt;
+                bool blocked = false;
+                if (have) {
+                    const double2* rp = reinterpret_cast<const double2*>(S.refs + nd.prim_off + base + lane);
+                    double g[9];
+                    double2 a0 = __ldg(rp), a1 = __ldg(rp + 1), a2 = __ldg(rp + 2), a3 = __ldg(rp + 3);
+                    g[0] = a0.x; g[1] = a0.y; g[2] = a1.x; g[3] = a1.y; g[4] = a2.x; g[5] = a2.y; g[6] = a3.x; g[7] = a3.y;
+                    uint4 tail = __ldg(reinterpret_cast<const uint4*>(rp + 4));
+                    g[8] = __hiloint2double((int)tail.y, (int)tail.x);
+                    uint32_t prim = tail.z, flags = tail.w;
+                    double t, u = 0, v = 0; d3 cn;
+                    bool ok;
+                    uint32_t kind = LF_KIND(flags);
+                    if (kind == GI_PRIM_TRIANGLE) { t = tri_hit(g, r, u, v); ok = t > 0; }
+                    else if (kind == GI_PRIM_SPHERE) ok = sphere_hit(g, r, t);
+                    else ok = cone_hit(g, S.prim_nrm + 9 * (size_t)prim, r, t, cn);
+                    if (ok) {
+                        d3 pos = r.o + r.d * t;
+                        bool pass = true;
+                        if (FULL && (flags & LF_ALPHA)) {
+                            double tu = 0, tv = 0;
+                            if (flags & LF_WRITES_UV) prim_uv_at(S, prim, pos, u, v, tu, tv);
+                            pass = alpha_pass(S, prim, ni, tu, tv, seed, path, depth, SITE_ALPHA_SHADOW + (light << 8));
+                        }
+                        double t_shadow = len2(pos - r.o);
+                        blocked = pass && (t_shadow < mt) && (t_shadow > 0);
+                    }
+                }
+                uint32_t bm = __ballot_sync(0xffffffffu, blocked);
+                n_prim += (nd.prim_cnt - base < 32u ? nd.prim_cnt - base : 32u);
+                if (bm) return false;
+            }
+            continue;
+        }
+        n_node += __popc(nd.mask);
+        bool in = false; uint32_t cidx = 0;
+        if (lane < 8 && ((nd.mask >> lane) & 1u)) {
+            cidx = nd.child + __popc(nd.mask & ((1u << lane) - 1u));
+            DNode ch = load_node(S.nodes, cidx);
+            in = box_entry(ch.bmin, ch.bmax, r, 0.0, tmax) >= 0.0;
+        }
+        uint32_t valid = __ballot_sync(0xffffffffu, in) & 0xffu;
+        if (in) { int pos = sp + __popc(valid & ((1u << lane) - 1u)); if (pos < GI_STACK_MAX) stack[pos] = cidx; }
+        sp += __popc(valid);
+        if (sp > GI_STACK_MAX) sp = GI_STACK_MAX;
+        __syncwarp();
+    }
+    return true;
+}
+
 // add a per-thread pair of work counters into two global u64 tallies: warp shuffle reduction, one atomic pair per warp.
 // Must be called by all 32 lanes of the warp (inactive lanes pass zeros).
 __device__ __forceinline__ void tally2(unsigned long long* dst, uint32_t a, uint32_t b)

@@ -85,6 +85,48 @@ __global__ void __launch_bounds__(GI_BLOCK) k_trace_any(DScene S, size_t n, cons
     tally2(work, nn_, np_);
 }
 
+// warp-per-ray forms of the two batch kernels (one ray per warp, see trace_closest_warp)
+#define GI_WPB 4   // warps per block in the warp-per-ray kernels
+template <bool FULL>
+__global__ void __launch_bounds__(GI_WPB * 32) k_trace_closest_w(DScene S, size_t n, const double* __restrict__ org, const double* __restrict__ dir, uint64_t seed,
+                                                                uint32_t* __restrict__ prim, double* __restrict__ hit, double* __restrict__ normal, double* __restrict__ uv,
+                                                                unsigned long long* work)
+{
+    __shared__ uint32_t s_stack[GI_WPB][GI_STACK_MAX];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    size_t i = blockIdx.x * (size_t)GI_WPB + wib;
+    if (i >= n) return;
+    uint32_t nn_ = 0, np_ = 0;
+    DRay r = ray_as_stored(ld3(org + 3 * i), ld3(dir + 3 * i));
+    DHit h;
+    trace_closest_warp<FULL>(S, r, seed, (uint64_t)i, 0, h, s_stack[wib], lane, nn_, np_);
+    if (lane == 0) {
+        if (prim) prim[i] = h.prim;
+        d3 p = mk3(0, 0, 0), nn = mk3(0, 0, 0); double tu = 0, tv = 0;
+        if (h.prim != GI_NO_HIT) hit_surface(S, r, h, FULL, p, nn, tu, tv);
+        if (hit) st3(hit + 3 * i, p);
+        if (normal) st3(normal + 3 * i, nn);
+        if (uv) { uv[2 * i] = tu; uv[2 * i + 1] = tv; }
+        if (work) { atomicAdd(work, (unsigned long long)nn_); atomicAdd(work + 1, (unsigned long long)np_); }
+    }
+}
+template <bool FULL>
+__global__ void __launch_bounds__(GI_WPB * 32) k_trace_any_w(DScene S, size_t n, const double* __restrict__ org, const double* __restrict__ dir, const double* __restrict__ maxt2,
+                                                            uint64_t seed, uint8_t* __restrict__ vis, unsigned long long* work)
+{
+    __shared__ uint32_t s_stack[GI_WPB][GI_STACK_MAX];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    size_t i = blockIdx.x * (size_t)GI_WPB + wib;
+    if (i >= n) return;
+    uint32_t nn_ = 0, np_ = 0;
+    DRay r = ray_as_stored(ld3(org + 3 * i), ld3(dir + 3 * i));
+    bool v = trace_visible_warp<FULL>(S, r, maxt2[i], seed, (uint64_t)i, 0, 0, s_stack[wib], lane, nn_, np_);
+    if (lane == 0) {
+        vis[i] = v ? 1 : 0;
+        if (work) { atomicAdd(work, (unsigned long long)nn_); atomicAdd(work + 1, (unsigned long long)np_); }
+    }
+}
+
 // ---- photon map (K6): level-synchronous build of PhotonMap::Node::partition (photonMap.cpp:137-192) --------------------------------
 // Nodes reuse DNode: mask != 0 marks an interior node whose 8 children start at `child`; prim_off/prim_cnt = photon range.
 struct DPMap {
@@ -236,142 +278,208 @@ __global__ void k_pm_payload(DPMap M, uint32_t n_kept)
 }
 
 // ---- K7: gather — RayTracer::samplePhotons (raytracer.h:532-579) over PhotonMap::getInRange (photonMap.cpp:50-92,115-134) ----
-// One warp per query.  Lanes 0..7 test the eight children of a node in parallel (containment while descending, closed
-// box/box overlap while collecting); candidates of a leaf are scored one per lane and merged into a warp-wide sorted
-// list of the k <= 32 nearest (one entry per lane, ordered by (distance^2, photon id)).
-struct DGatherMap { const DNode* nodes; const double* pos; const double* dircol; const uint32_t* pid; uint32_t n_nodes; };
+// The candidate set of a query is a function of the LEAF that contains it: every photon of every leaf whose closed box
+// touches (leaf box +- EPSILON).  So the map carries, per leaf, the precomputed candidate list (photon slots in the
+// reference's DFS order) — built once on the device by running Node::get for every leaf (k_pm_cand_*).  A query is then:
+// descend to the leaf (lanes 0..7 test the eight children in parallel), stream the leaf's candidate list 32 at a time,
+// and keep the k <= 32 nearest in a warp-wide sorted list (one entry per lane, ordered by (distance^2, photon id)).
+struct DGatherMap {
+    const DNode* nodes; const double* pos; const double* dircol; const uint32_t* pid; uint32_t n_nodes;
+    const uint32_t* cand_off;    // [n_nodes + 1] start of each node's candidate list (only leaves have entries)
+    const uint32_t* cand_slot;   // photon slots, concatenated per leaf
+};
 
+// ordering of candidates: (distance^2, photon slot).  Exact distance ties between different photons are unordered in
+// the reference (std::partial_sort is unstable); the slot makes them deterministic here.
 __device__ __forceinline__ bool kv_less(double a, uint32_t ai, double b, uint32_t bi) { return a < b || (a == b && ai < bi); }
 
-// bitonic compare-exchange across lanes on (key, id[, slot]) tuples
-__device__ __forceinline__ void cmpx(double& d, uint32_t& id, uint32_t& sl, int lane, int j, bool up)
+// bitonic compare-exchange across lanes on (key, slot) pairs
+__device__ __forceinline__ void cmpx(double& d, uint32_t& sl, int lane, int j, bool up)
 {
     double od = __shfl_xor_sync(0xffffffffu, d, j);
-    uint32_t oid = __shfl_xor_sync(0xffffffffu, id, j);
     uint32_t osl = __shfl_xor_sync(0xffffffffu, sl, j);
     bool lower = (lane & j) == 0;
-    bool mine_less = kv_less(d, id, od, oid);
-    bool keep_min = (lower == up);
-    bool take = keep_min ? !mine_less : mine_less;
-    if (take && !(d == od && id == oid)) { d = od; id = oid; sl = osl; }
+    bool mine_less = kv_less(d, sl, od, osl);
+    bool take = (lower == up) ? !mine_less : mine_less;
+    if (take && !(d == od && sl == osl)) { d = od; sl = osl; }
 }
-__device__ __forceinline__ void warp_sort32(double& d, uint32_t& id, uint32_t& sl, int lane)
+__device__ __forceinline__ void warp_sort32(double& d, uint32_t& sl, int lane)
 {
     for (int k = 2; k <= 32; k <<= 1)
-        for (int j = k >> 1; j > 0; j >>= 1) cmpx(d, id, sl, lane, j, (lane & k) == 0 || k == 32);
+        for (int j = k >> 1; j > 0; j >>= 1) cmpx(d, sl, lane, j, (lane & k) == 0 || k == 32);
 }
 // merge a sorted-ascending batch (bd) into the sorted-ascending best list (d): keep the 32 smallest of the 64
-__device__ __forceinline__ void warp_merge32(double& d, uint32_t& id, uint32_t& sl, double bd, uint32_t bid, uint32_t bsl, int lane)
+__device__ __forceinline__ void warp_merge32(double& d, uint32_t& sl, double bd, uint32_t bsl, int lane)
 {
     // reverse the batch, take the element-wise minimum -> bitonic sequence holding the 32 smallest; then bitonic merge
     double rd = __shfl_sync(0xffffffffu, bd, 31 - lane);
-    uint32_t rid = __shfl_sync(0xffffffffu, bid, 31 - lane);
     uint32_t rsl = __shfl_sync(0xffffffffu, bsl, 31 - lane);
-    if (kv_less(rd, rid, d, id)) { d = rd; id = rid; sl = rsl; }
-    for (int j = 16; j > 0; j >>= 1) cmpx(d, id, sl, lane, j, true);
+    if (kv_less(rd, rsl, d, sl)) { d = rd; sl = rsl; }
+    for (int j = 16; j > 0; j >>= 1) cmpx(d, sl, lane, j, true);
 }
 
-#define GI_GATHER_STACK 128
-template <int WARPS>
-__global__ void __launch_bounds__(WARPS * 32) k_gather(DGatherMap M, size_t n, const double* __restrict__ qpos, const double* __restrict__ qdir, int k,
-                                                     double* __restrict__ rgb, uint32_t* __restrict__ knn, uint32_t* __restrict__ ncand,
-                                                     const double* __restrict__ weight, double* __restrict__ accum, const uint32_t* __restrict__ accum_idx,
-                                                     unsigned long long* work)
+// getBounds (photonMap.cpp:115-134): the leaf whose half-open box contains p; false when p is in no child on the way down
+__device__ __forceinline__ bool pm_find_leaf(const DGatherMap& M, d3 p, int lane, uint32_t& node, uint32_t& depth)
 {
-    __shared__ uint32_t s_stack[WARPS][GI_GATHER_STACK];
-    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-    size_t q = blockIdx.x * (size_t)WARPS + wib;
-    if (q >= n) return;
-    d3 p = ld3(qpos + 3 * q), dq = ld3(qdir + 3 * q);
-    // -- getBounds (photonMap.cpp:115-134): descend to the leaf whose half-open box contains p
-    uint32_t node = 0, leaf_depth = 0;
-    bool found = M.n_nodes > 0;
+    node = 0; depth = 0;
+    if (M.n_nodes == 0) return false;
     DNode nd = load_node(M.nodes, 0);
-    while (found && nd.mask != 0) {
-        leaf_depth++;
+    while (nd.mask != 0) {
+        depth++;
         bool in = false;
         if (lane < 8) { DNode ch = load_node(M.nodes, nd.child + lane); in = box_contains(ch.bmin, ch.bmax, p); }
         uint32_t b = __ballot_sync(0xffffffffu, in) & 0xffu;
-        if (!b) { found = false; break; }   // box(-inf,-inf): nothing overlaps (photonMap.cpp:132)
+        if (!b) return false;   // box(-inf,-inf): nothing overlaps (photonMap.cpp:132)
         node = nd.child + (__ffs(b) - 1);
         nd = load_node(M.nodes, node);
     }
-    double best_d = CUDART_INF; uint32_t best_id = 0xFFFFFFFFu, best_sl = 0xFFFFFFFFu;   // sorted ascending across lanes
+    return true;
+}
+
+struct GatherOut { d3 rgb; uint32_t total, depth; int count; uint32_t best_slot; };
+
+// one query, executed by a full warp; every lane returns the same rgb/total/depth; lane l holds the slot of the l-th
+// nearest.  `sm` = 96 doubles of shared memory per warp (the ordered sum of the estimate).
+__device__ __forceinline__ GatherOut gather_warp(const DGatherMap& M, d3 p, d3 dq, int k, int lane, double* sm)
+{
+    GatherOut out; out.rgb = mk3(0, 0, 0); out.total = 0; out.depth = 0; out.count = 0; out.best_slot = 0xFFFFFFFFu;
+    uint32_t node, depth;
+    bool found = pm_find_leaf(M, p, lane, node, depth);
+    out.depth = depth;
+    double best_d = CUDART_INF; uint32_t best_sl = 0xFFFFFFFFu;   // sorted ascending across lanes
     uint32_t total = 0;
     if (found) {
-        double qmin[3], qmax[3];
-        for (int a = 0; a < 3; a++) { qmin[a] = nd.bmin[a] - GI_D_EPSILON; qmax[a] = nd.bmax[a] + GI_D_EPSILON; }   // :119
-        // -- Node::get (photonMap.cpp:71-92): every leaf whose closed box touches the query box
-        int sp = 0;
-        if ((qmax[0] - qmin[0]) > 0) { if (lane == 0) s_stack[wib][0] = 0; sp = 1; }
-        __syncwarp();
-        while (sp > 0) {
-            uint32_t ni = s_stack[wib][sp - 1]; sp--;
-            __syncwarp();
-            DNode cur = load_node(M.nodes, ni);
-            if (cur.mask == 0) {
-                // leaf: lanes score its photons in chunks of 32
-                for (uint32_t base = 0; base < cur.prim_cnt; base += 32) {
-                    uint32_t slot = cur.prim_off + base + lane;
-                    bool have = base + lane < cur.prim_cnt;
-                    double cd = CUDART_INF; uint32_t cid = 0xFFFFFFFFu, csl = 0xFFFFFFFFu;
-                    if (have) {
-                        d3 pp = ld3(M.pos + 3 * (size_t)slot);
-                        cd = len2(pp - p); cid = M.pid[slot]; csl = slot;
-                    }
-                    // skip the merge when no candidate beats the current k-th entry
-                    double kth = __shfl_sync(0xffffffffu, best_d, 31); uint32_t kid = __shfl_sync(0xffffffffu, best_id, 31);
-                    bool useful = have && kv_less(cd, cid, kth, kid);
-                    if (__ballot_sync(0xffffffffu, useful)) {
-                        warp_sort32(cd, cid, csl, lane);
-                        warp_merge32(best_d, best_id, best_sl, cd, cid, csl, lane);
-                    }
+        const uint32_t off = __ldg(M.cand_off + node);
+        total = __ldg(M.cand_off + node + 1) - off;
+        double bat_d = CUDART_INF; uint32_t bat_sl = 0xFFFFFFFFu;   // pending batch, filled from lane 0 up
+        int nb = 0;
+        double kth_d = CUDART_INF; uint32_t kth_sl = 0xFFFFFFFFu;
+        for (uint32_t base = 0; base < total; base += 32) {
+            bool have = base + lane < total;
+            double cd = CUDART_INF; uint32_t csl = 0xFFFFFFFFu;
+            if (have) {
+                csl = __ldg(M.cand_slot + off + base + lane);
+                const double* pp = M.pos + 3 * (size_t)csl;
+                cd = len2(mk3(__ldg(pp), __ldg(pp + 1), __ldg(pp + 2)) - p);
+            }
+            // only candidates that beat the current k-th entry can enter the result
+            bool useful = have && kv_less(cd, csl, kth_d, kth_sl);
+            uint32_t um = __ballot_sync(0xffffffffu, useful);
+            int cnt = __popc(um);
+            int taken = 0;
+            while (taken < cnt) {
+                int room = 32 - nb, put = cnt - taken < room ? cnt - taken : room;
+                // lane j in [nb, nb+put) pulls the (taken + j - nb)-th useful candidate
+                int want = lane - nb;
+                int src = (want >= 0 && want < put) ? (int)__fns(um, 0, taken + want + 1) : lane;
+                double sd = __shfl_sync(0xffffffffu, cd, src); uint32_t ssl = __shfl_sync(0xffffffffu, csl, src);
+                if (want >= 0 && want < put) { bat_d = sd; bat_sl = ssl; }
+                nb += put; taken += put;
+                if (nb == 32) {
+                    warp_sort32(bat_d, bat_sl, lane);
+                    warp_merge32(best_d, best_sl, bat_d, bat_sl, lane);
+                    kth_d = __shfl_sync(0xffffffffu, best_d, 31); kth_sl = __shfl_sync(0xffffffffu, best_sl, 31);
+                    bat_d = CUDART_INF; bat_sl = 0xFFFFFFFFu; nb = 0;
                 }
-                total += cur.prim_cnt;
-            } else {
-                bool ov = false;
-                if (lane < 8) {
-                    DNode ch = load_node(M.nodes, cur.child + lane);
-                    ov = (ch.bmin[0] <= qmax[0] && ch.bmax[0] >= qmin[0]) && (ch.bmin[1] <= qmax[1] && ch.bmax[1] >= qmin[1]) && (ch.bmin[2] <= qmax[2] && ch.bmax[2] >= qmin[2]);
-                }
-                uint32_t b = __ballot_sync(0xffffffffu, ov) & 0xffu;
-                // push in reverse child order so that children pop in the reference's DFS order
-                if (lane < 8 && ov) {
-                    int rank = __popc(b >> (lane + 1));   // children after me
-                    if (sp + rank < GI_GATHER_STACK) s_stack[wib][sp + rank] = cur.child + lane;
-                }
-                sp += __popc(b);
-                if (sp > GI_GATHER_STACK) sp = GI_GATHER_STACK;
-                __syncwarp();
             }
         }
+        if (nb > 0) {
+            warp_sort32(bat_d, bat_sl, lane);
+            warp_merge32(best_d, best_sl, bat_d, bat_sl, lane);
+        }
     }
-    // -- radiance estimate (raytracer.h:545-576): sum over the count = min(k, total) nearest in ascending distance order
+    // radiance estimate (raytracer.h:545-576): sum over the count = min(k, total) nearest in ascending distance order;
+    // lanes 0..2 each add up one colour channel in that order
     int count = (int)total < k ? (int)total : k;
     d3 term = mk3(0, 0, 0);
     if (lane < count && best_sl != 0xFFFFFFFFu) {
         const double* dc = M.dircol + 6 * (size_t)best_sl;
         term = ld3(dc + 3) * dot3(ld3(dc), dq);
     }
-    d3 res = mk3(0, 0, 0);
-    for (int i = 0; i < count; i++) {
-        res.x += __shfl_sync(0xffffffffu, term.x, i); res.y += __shfl_sync(0xffffffffu, term.y, i); res.z += __shfl_sync(0xffffffffu, term.z, i);
-    }
+    __syncwarp();
+    sm[lane] = term.x; sm[32 + lane] = term.y; sm[64 + lane] = term.z;
+    __syncwarp();
+    double acc = 0;
+    if (lane < 3) for (int i = 0; i < count; i++) acc += sm[32 * lane + i];
+    d3 res = mk3(__shfl_sync(0xffffffffu, acc, 0), __shfl_sync(0xffffffffu, acc, 1), __shfl_sync(0xffffffffu, acc, 2));
     if (total > 0) {
         double md = __shfl_sync(0xffffffffu, best_d, count - 1);
         double den = GI_D_PI * md;
         res = mk3(res.x / den, res.y / den, res.z / den);
     }
-    if (knn && lane < k) knn[q * (size_t)k + lane] = lane < count ? best_id : GI_NO_HIT;
+    out.rgb = res; out.total = total; out.count = count; out.best_slot = best_sl;
+    return out;
+}
+
+template <int WARPS>
+__global__ void __launch_bounds__(WARPS * 32) k_gather(DGatherMap M, size_t n, const double* __restrict__ qpos, const double* __restrict__ qdir, int k,
+                                                     double* __restrict__ rgb, uint32_t* __restrict__ knn, uint32_t* __restrict__ ncand,
+                                                     const double* __restrict__ weight, double* __restrict__ accum, const uint32_t* __restrict__ accum_idx,
+                                                     unsigned long long* work)
+{
+    __shared__ double s_sum[WARPS][96];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    size_t q = blockIdx.x * (size_t)WARPS + wib;
+    if (q >= n) return;
+    d3 p = ld3(qpos + 3 * q), dq = ld3(qdir + 3 * q);
+    GatherOut g = gather_warp(M, p, dq, k, lane, s_sum[wib]);
+    if (knn && lane < k) knn[q * (size_t)k + lane] = (lane < g.count && g.best_slot != 0xFFFFFFFFu) ? __ldg(M.pid + g.best_slot) : GI_NO_HIT;
     if (lane == 0) {
-        if (work) { atomicAdd(work, (unsigned long long)leaf_depth); atomicAdd(work + 1, (unsigned long long)total); atomicAdd(work + 2, (unsigned long long)count); }
-        if (rgb) st3(rgb + 3 * q, res);
-        if (ncand) ncand[q] = total;
+        if (work) { atomicAdd(work, (unsigned long long)g.depth); atomicAdd(work + 1, (unsigned long long)g.total); atomicAdd(work + 2, (unsigned long long)g.count); }
+        if (rgb) st3(rgb + 3 * q, g.rgb);
+        if (ncand) ncand[q] = g.total;
         if (accum) {   // render pipeline: L[path] += weight * caustic
             size_t a = accum_idx[q];
-            accum[3 * a] += weight[3 * q] * res.x; accum[3 * a + 1] += weight[3 * q + 1] * res.y; accum[3 * a + 2] += weight[3 * q + 2] * res.z;
+            accum[3 * a] += weight[3 * q] * g.rgb.x; accum[3 * a + 1] += weight[3 * q + 1] * g.rgb.y; accum[3 * a + 2] += weight[3 * q + 2] * g.rgb.z;
         }
     }
+}
+
+// ---- candidate lists: Node::get (photonMap.cpp:71-92) run once per leaf with that leaf's query box -------------------------
+// One warp per node (interior nodes exit).  FILL = false: count candidates into cnt[node]; FILL = true: write the photon
+// slots in the reference's DFS order (children 0..7, insertion order inside a leaf) starting at off[node].
+#define GI_GATHER_STACK 1024   // a degenerate map (coincident photons) can be ~128 levels deep
+template <int WARPS, bool FILL>
+__global__ void __launch_bounds__(WARPS * 32) k_pm_cands(const DNode* __restrict__ nodes, uint32_t n_nodes, uint32_t* __restrict__ cnt, const uint32_t* __restrict__ off,
+                                                       uint32_t* __restrict__ slots, uint32_t* __restrict__ overflow)
+{
+    __shared__ uint32_t s_stack[WARPS][GI_GATHER_STACK];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    uint32_t leaf = blockIdx.x * WARPS + wib;
+    if (leaf >= n_nodes) return;
+    DNode nd = load_node(nodes, leaf);
+    if (nd.mask != 0) { if (!FILL && lane == 0) cnt[leaf] = 0; return; }
+    double qmin[3], qmax[3];
+    for (int a = 0; a < 3; a++) { qmin[a] = nd.bmin[a] - GI_D_EPSILON; qmax[a] = nd.bmax[a] + GI_D_EPSILON; }   // photonMap.cpp:119
+    uint32_t total = 0;
+    uint32_t wpos = FILL ? off[leaf] : 0;
+    int sp = 0;
+    if ((qmax[0] - qmin[0]) > 0) { if (lane == 0) s_stack[wib][0] = 0; sp = 1; }   // `if (bbox.dx() <= 0) return` (photonMap.cpp:73)
+    __syncwarp();
+    while (sp > 0) {
+        uint32_t ni = s_stack[wib][sp - 1]; sp--;
+        __syncwarp();
+        DNode cur = load_node(nodes, ni);
+        if (cur.mask == 0) {
+            if (FILL) for (uint32_t b = lane; b < cur.prim_cnt; b += 32) slots[wpos + b] = cur.prim_off + b;
+            wpos += cur.prim_cnt; total += cur.prim_cnt;
+        } else {
+            bool ov = false;
+            if (lane < 8) {
+                DNode ch = load_node(nodes, cur.child + lane);
+                ov = (ch.bmin[0] <= qmax[0] && ch.bmax[0] >= qmin[0]) && (ch.bmin[1] <= qmax[1] && ch.bmax[1] >= qmin[1]) && (ch.bmin[2] <= qmax[2] && ch.bmax[2] >= qmin[2]);
+            }
+            uint32_t b = __ballot_sync(0xffffffffu, ov) & 0xffu;
+            if (lane < 8 && ov) {   // push in reverse child order so that children pop in DFS order
+                int rank = __popc(b >> (lane + 1));
+                if (sp + rank < GI_GATHER_STACK) s_stack[wib][sp + rank] = cur.child + lane;
+            }
+            sp += __popc(b);
+            if (sp > GI_GATHER_STACK) { sp = GI_GATHER_STACK; if (lane == 0) atomicExch(overflow, 1u); }
+            __syncwarp();
+        }
+    }
+    if (!FILL && lane == 0) cnt[leaf] = total;
 }
 
 // ---- K4: wavefront bounce = closest hit + shade + scatter (raytracer.h:167-276, 321-379, 481-506) -------------------------------------
@@ -490,6 +598,96 @@ __global__ void __launch_bounds__(GI_BLOCK) k_direct(DScene S, gi_render_params 
     double* L = PS.L + 3 * (size_t)path;
     L[0] += w.x; L[1] += w.y; L[2] += w.z;
     tally2(work, wn, wp);
+}
+
+// ---- the tail: once few paths are left, one warp takes one path to its end (closest hit, shading, shadow rays, gather and
+// the next bounce all inside the kernel), so a frame does not pay ~65 x 3 nearly empty launches with a host round trip
+// each.  Arithmetic and the order in which terms are added to L[path] are those of k_bounce / k_direct / k_gather.
+struct DTailCounters { unsigned long long closest, shadow, gathers, nodes_c, prims_c, nodes_s, prims_s, g_depth, g_cand, g_sel; unsigned int next; unsigned int pad; };
+
+template <bool FULL>
+__global__ void __launch_bounds__(GI_WPB * 32) k_tail(DScene S, DGatherMap G, int have_map, gi_render_params P, int depth0, uint32_t n, DQueue in, DPathState PS, DTailCounters* TC)
+{
+    __shared__ uint32_t s_stack[GI_WPB][GI_STACK_MAX];
+    __shared__ double s_sum[GI_WPB][96];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    uint32_t* stack = s_stack[wib];
+  // persistent warps: paths are handed out one at a time, so a 60-bounce path does not hold back a wave of short ones
+  for (;;) {
+    uint32_t i = 0;
+    if (lane == 0) i = atomicAdd(&TC->next, 1u);
+    i = __shfl_sync(0xffffffffu, i, 0);
+    if (i >= n) return;
+    const uint32_t path = in.path[i];
+    DRay r = ray_as_stored(ld3(in.o + 3 * (size_t)i), ld3(in.d + 3 * (size_t)i));
+    d3 T = ld3(in.T + 3 * (size_t)i), contrib = ld3(in.contrib + 3 * (size_t)i);
+    const uint64_t key = PS.key[path]; const uint32_t sample = PS.sample[path];
+    d3 L = ld3(PS.L + 3 * (size_t)path);
+    unsigned long long c_closest = 0, c_shadow = 0, c_gather = 0, g_depth = 0, g_cand = 0, g_sel = 0;
+    uint32_t nc = 0, pc = 0, ns = 0, ps = 0;
+    for (int depth = depth0; depth <= P.max_depth; depth++) {
+        float sx = halton_sample(S, (uint32_t)(2 + 2 * depth), sample);
+        float sy = halton_sample(S, (uint32_t)(3 + 2 * depth), sample);
+        DHit h;
+        trace_closest_warp<FULL>(S, r, P.seed, key, (uint64_t)depth, h, stack, lane, nc, pc);
+        c_closest++;
+        if (h.prim == GI_NO_HIT) { L = L + T * ld3(S.ambient); break; }
+        d3 hp, hn; double tu, tv;
+        hit_surface(S, r, h, FULL, hp, hn, tu, tv);
+        const gi_material& m = S.mats[S.prim_mat[h.prim]];
+        d3 color = tex_get(S, m.diffuse_tex, tu, tv);
+        double rough = m.roughness, offset = GI_D_SHADOW_BIAS;
+        d3 f = mk3(1, 1, 1);
+        d3 refDir = secondary_ray(S, m, r, hn, tu, tv, sx, sy, color, f, contrib, offset, P.seed, key, (uint64_t)depth);
+        double q = contrib.x < contrib.y ? contrib.y : contrib.x; q = q < contrib.z ? contrib.z : q;
+        bool cont = depth <= P.min_depth || gi_rand(P.seed, key, (uint64_t)depth, SITE(SITE_RR, 0)) < q;
+        d3 wdir = T * color;
+        d3 Tn = T;
+        if (cont) {
+            f = f * (depth <= P.min_depth ? 1.0 : (1.0 / q));
+            L = L + T * tex_get(S, m.emissive_tex, tu, tv);
+            Tn = T * f;
+        }
+        // direct light (k_direct)
+        if (S.n_lights) {
+            d3 li = mk3(0, 0, 0);
+            for (uint32_t l = 0; l < S.n_lights; l++) {
+                const gi_light& light = S.lights[l];
+                d3 sp = hp + hn * GI_D_SHADOW_BIAS;
+                d3 lightDir = light_point(light, gi_rand(P.seed, key, (uint64_t)depth, SITE(SITE_LIGHT_U, l)), gi_rand(P.seed, key, (uint64_t)depth, SITE(SITE_LIGHT_V, l))) - sp;
+                double maxt = len2(lightDir);
+                double hfrac = 1 / (GI_D_PI * len2(ld3(light.pos) - hp));
+                DRay sr = make_ray(sp, lightDir);
+                c_shadow++;
+                if (trace_visible_warp<FULL>(S, sr, maxt, P.seed, key, (uint64_t)depth, l, stack, lane, ns, ps)) {
+                    double d = dot3(hn, normalize3(ld3(light.pos) - hp));
+                    if (d < 0) d = 0;
+                    li = (ld3(light.col) * pow_like_libm(d, (1.0 / rough))) * hfrac;
+                }
+            }
+            L = L + wdir * li;
+        }
+        // caustic estimate (k_gather)
+        if (depth <= P.caustic_max_depth) {
+            c_gather++;
+            if (have_map) {
+                GatherOut g = gather_warp(G, hp, refDir, P.k_photons, lane, s_sum[wib]);
+                g_depth += g.depth; g_cand += g.total; g_sel += (unsigned long long)g.count;
+                d3 wc = cont ? wdir : mk3(0, 0, 0);
+                L = L + wc * g.rgb;
+            }
+        }
+        if (!cont) break;
+        T = Tn;
+        r = make_ray(hp + hn * offset, refDir);
+    }
+    if (lane == 0) {
+        st3(PS.L + 3 * (size_t)path, L);
+        atomicAdd(&TC->closest, c_closest); atomicAdd(&TC->shadow, c_shadow); atomicAdd(&TC->gathers, c_gather);
+        atomicAdd(&TC->nodes_c, (unsigned long long)nc); atomicAdd(&TC->prims_c, (unsigned long long)pc); atomicAdd(&TC->nodes_s, (unsigned long long)ns); atomicAdd(&TC->prims_s, (unsigned long long)ps);
+        atomicAdd(&TC->g_depth, g_depth); atomicAdd(&TC->g_cand, g_cand); atomicAdd(&TC->g_sel, g_sel);
+    }
+  }
 }
 
 // generate the camera paths of one chunk (path-linear range [c0, c0+n) of the tile's sample-major path space)

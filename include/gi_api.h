@@ -136,7 +136,7 @@ typedef struct gi_stats {
     uint64_t shadow_node_tests, shadow_prim_tests;
     /* gather: sum of containing-leaf depths, of candidate counts C, and of min(k, C)                              */
     uint64_t gather_leaf_depth, gather_candidates, gather_selected;
-    double trace_ms, shadow_ms, gather_ms, shade_ms, total_ms; /* CUDA-event times of the phases        */
+    double trace_ms, shadow_ms, gather_ms, shade_ms, total_ms; /* CUDA-event times: bounce, direct, gather, tail (in shade_ms), whole call */
 } gi_stats;
 
 /* ---- lifetime ------------------------------------------------------------------------------------------ */

@@ -162,12 +162,25 @@ def test_photon_map_and_gather_vs_oracle_random_cloud(ctx):
     q = box[:3] - 0.2 + rng.rand(20000, 3) * (box[3:] - box[:3] + 0.4)
     q[:2000] = pos[rng.randint(0, n, 2000)] + 1e-3 * rng.randn(2000, 3)
     qd = rng.randn(20000, 3)
+    def knn_d2(ids, qq):
+        ok = ids != 0xFFFFFFFF
+        dd = np.full(ids.shape, np.inf)
+        pp = pos[np.where(ok, ids, 0)] - qq[:, None, :]
+        d2 = pp[..., 0] * pp[..., 0] + pp[..., 1] * pp[..., 1] + pp[..., 2] * pp[..., 2]
+        dd[ok] = d2[ok]
+        return dd
+
     for k in (32, 7):
         rgb, knn, nc = ctx.gather(q, qd, k)
         r2, k2, n2, _ = pm.gather(q, qd, k)
         assert bits_equal(nc, n2)
-        assert bits_equal(knn, k2), f"{(knn != k2).any(axis=1).sum()} queries differ"
-        assert np.allclose(rgb, r2, rtol=1e-12, atol=0)
+        # exact distance ties (the coincident photons) are unordered in the reference (unstable partial_sort): the selected
+        # DISTANCES must agree everywhere, the ids wherever there is no tie
+        assert np.array_equal(knn_d2(knn, q), knn_d2(k2, q))
+        same = (np.sort(knn, axis=1) == np.sort(k2, axis=1)).all(axis=1)
+        assert same.mean() > 0.995, same.mean()
+        assert bits_equal(knn[same], k2[same])
+        assert np.allclose(rgb[same], r2[same], rtol=1e-12, atol=0)
     assert (nc == 0).sum() > 100 and nc.max() > 200
 
 
@@ -325,3 +338,59 @@ def test_device_work_tallies_equal_canonical_traversal_counts(ctx, golden_cornel
     q, dsum, csum, ssum = ctx.last_work("gather")
     _, _, nc, dl = O.PMap(g["photons_f64"].reshape(-1, 9), sc.root_box).gather(qp, qd, 32)
     assert q == qp.shape[0] and csum == int(nc.sum()) and ssum == int(np.minimum(nc, 32).sum()) and dsum == int(dl.sum())
+
+
+def test_warp_per_ray_kernels_equal_thread_per_ray(lib_built, synth_dir, monkeypatch):
+    """The warp-cooperative traversals (one ray per warp) must return exactly what the thread-per-ray ones return."""
+    from gi_raytracer_b200.capi import Context
+    monkeypatch.setenv("GI_TRACE_MODE", "1")
+    cw = Context(0)
+    monkeypatch.setenv("GI_TRACE_MODE", "0")
+    ct = Context(0)
+    try:
+        for name in ("mixed", "cards", "atrium"):
+            sc = _load(name, synth_dir)
+            cw.upload_scene(sc); ct.upload_scene(sc)
+            o, d, _ = ct.camera_rays(64, 64, 0, 0, 64, 64, 0, 1)
+            ro, rdir = random_rays(sc, 15000, seed=11)
+            o, d = np.concatenate([o, ro]), np.concatenate([d, rdir])
+            a = cw.trace_closest(o, d, alpha_seed=5)
+            b = ct.trace_closest(o, d, alpha_seed=5)
+            c = O.trace_closest(sc, o, d, alpha_seed=5)
+            assert all(bits_equal(x, y) for x, y in zip(a, b)), name
+            assert bits_equal(a[0], c[0]) and bits_equal(a[1], c[1])
+            assert cw.last_work("trace_closest") == ct.last_work("trace_closest")
+            m = a[0] != 0xFFFFFFFF
+            so = a[1][m] + 1e-4 * a[2][m]
+            sd = sc.lights[0, :3][None, :] - so
+            mt = (sd * sd).sum(axis=1)
+            sd = sd * (1.0 / np.sqrt(mt))[:, None]
+            assert bits_equal(cw.trace_any(so, sd, mt, alpha_seed=9), ct.trace_any(so, sd, mt, alpha_seed=9)), name
+    finally:
+        cw.close(); ct.close()
+
+
+def test_tail_kernel_equals_wavefront(lib_built, synth_dir, monkeypatch):
+    """Paths finished by the tail megakernel must equal, bit for bit, the same paths run through the wavefront kernels."""
+    from gi_raytracer_b200.capi import Context
+    monkeypatch.setenv("GI_TAIL_THRESHOLD", "0")
+    c0 = Context(0)
+    monkeypatch.setenv("GI_TAIL_THRESHOLD", "100000000")
+    c1 = Context(0)
+    try:
+        for name, depth in (("mixed", 12), ("cards", 5)):
+            sc = _load(name, synth_dir)
+            outs = []
+            for c in (c0, c1):
+                c.upload_scene(sc)
+                c.photon_trace(2500 if name == "mixed" else 0, 5, seed=2)
+                c.photon_map_build(None)
+                P = render_params(48, 48, 3, max_depth=depth, seed=17)
+                outs.append(c.render_tile(P, 0, 0, 48, 48, 0, 3))
+            (a, sa), (b, sb) = outs
+            assert bits_equal(a, b), f"{name}: {np.abs(a - b).max()}"
+            for f in ("closest_rays", "shadow_rays", "gathers", "closest_node_tests", "closest_prim_tests", "gather_candidates", "gather_selected", "gather_leaf_depth"):
+                assert getattr(sa, f) == getattr(sb, f), f
+            assert sb.shade_ms > 0 and sa.shade_ms == 0
+    finally:
+        c0.close(); c1.close()
