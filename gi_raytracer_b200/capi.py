@@ -22,7 +22,7 @@ API_SYMBOLS = [
     "gi_photon_map_build", "gi_photon_map_info", "gi_photon_map_download", "gi_photon_map_slab_size",
     "gi_photon_map_slab_ptr", "gi_photon_map_adopt_slab", "gi_photon_map_reserve_slab", "gi_photon_gather",
     "gi_photon_gather_dev", "gi_render_tile", "gi_render_tile_dev", "gi_resolve", "gi_resolve_dev", "gi_last_kernel_ms",
-    "gi_last_work",
+    "gi_last_work", "gi_scene_info",
 ]
 
 _LIB = None
@@ -79,6 +79,7 @@ def load_library():
         f.argtypes = [vp, sz, vp, i32, vp]
     L.gi_last_kernel_ms.argtypes = [vp, C.c_char_p, C.POINTER(C.c_double), C.POINTER(u64)]
     L.gi_last_work.argtypes = [vp, C.c_char_p, C.POINTER(u64 * 4)]
+    L.gi_scene_info.argtypes = [vp, C.POINTER(u32 * 4)]
     # host-side scene facade (same library)
     L.gih_scene_load.argtypes = [C.c_char_p, i32, C.POINTER(vp)]
     L.gih_scene_desc.argtypes = [vp]
@@ -140,6 +141,11 @@ class Context:
         ms, n = C.c_double(), C.c_uint64()
         self._ck(self.L.gi_last_kernel_ms(self.h, family.encode(), C.byref(ms), C.byref(n)))
         return ms.value, n.value
+
+    def scene_info(self):
+        out = (C.c_uint32 * 4)()
+        self._ck(self.L.gi_scene_info(self.h, C.byref(out)))
+        return dict(full=int(out[0]), implicit_boxes=int(out[1]), n_nodes=int(out[2]), n_leaf_refs=int(out[3]))
 
     def last_work(self, family):
         out = (C.c_uint64 * 4)()

@@ -55,6 +55,7 @@ struct gi_ctx {
     // workspaces
     DevBuf w0, w1, w2, w3, w4, w5, w6, w7, w8, w9;           // API staging
     DevBuf q_a[5], q_b[5], hl[7], ps[3], b_cnt, b_accum, b_scan0, b_scan1, b_misc, b_work, b_tail;
+    bool no_implicit = false;      // GI_NO_IMPLICIT_BOXES at gi_create: always load child boxes (for A/B tests)
     int trace_mode = 0;            // 0: thread per ray, 1: warp per ray (API batch kernels; GI_TRACE_MODE)
     uint32_t tail_threshold = 32768; // queues smaller than this finish in the tail megakernel (GI_TAIL_THRESHOLD, 0 = off)
     unsigned long long work_host[16] = { 0 };   // [0,1] closest nodes/prims, [2,3] any-hit, [4..6] gather depth/cand/sel, [8] rays, [9] shadow rays, [10] queries
@@ -74,6 +75,18 @@ static int fail(gi_ctx* c, int code, const std::string& msg)
         cudaError_t e_ = (call);                                                                                   \
         if (e_ != cudaSuccess) return fail(ctx, e_ == cudaErrorMemoryAllocation ? GI_ERR_OOM : GI_ERR_CUDA,       \
                                            std::string(#call) + ": " + cudaGetErrorString(e_));                    \
+    } while (0)
+
+// launch KERNEL<FULL, IMPL> for the scene's traversal variant
+#define GI_LAUNCH(KERNEL, GRID, BLOCK, ...)                                                                                  \
+    do {                                                                                                                     \
+        if (ctx->S.full) {                                                                                                   \
+            if (ctx->S.implicit_boxes) KERNEL<true, true><<<(GRID), (BLOCK), 0, ctx->stream>>>(__VA_ARGS__);                \
+            else KERNEL<true, false><<<(GRID), (BLOCK), 0, ctx->stream>>>(__VA_ARGS__);                                     \
+        } else {                                                                                                             \
+            if (ctx->S.implicit_boxes) KERNEL<false, true><<<(GRID), (BLOCK), 0, ctx->stream>>>(__VA_ARGS__);               \
+            else KERNEL<false, false><<<(GRID), (BLOCK), 0, ctx->stream>>>(__VA_ARGS__);                                    \
+        }                                                                                                                    \
     } while (0)
 
 static inline unsigned grid_for(size_t n, unsigned block) { return (unsigned)((n + block - 1) / block); }
@@ -203,6 +216,7 @@ extern "C" int gi_create(int device, gi_ctx** out)
     cudaMemset(ctx->b_work.p, 0, 16 * sizeof(unsigned long long));
     ctx->S.halton_tab = ctx->b_htab.as<uint16_t>();
     ctx->S.halton_dims = ctx->b_hdims.as<DHaltonDim>();
+    if (getenv("GI_NO_IMPLICIT_BOXES")) ctx->no_implicit = true;
     if (const char* e = getenv("GI_TRACE_MODE")) ctx->trace_mode = atoi(e);
     if (const char* e = getenv("GI_TAIL_THRESHOLD")) ctx->tail_threshold = (uint32_t)strtoul(e, nullptr, 10);
     *out = ctx;
@@ -293,6 +307,29 @@ extern "C" int gi_scene_upload(gi_ctx* ctx, const gi_scene_desc* sc)
         for (int k = 0; k < 3; k++) { n.bmin[k] = sc->node_box[6 * (size_t)i + k]; n.bmax[k] = sc->node_box[6 * (size_t)i + 3 + k]; }
         n.child = sc->node_child[i]; n.mask = sc->node_mask[i]; n.prim_off = sc->node_prim_off[i]; n.prim_cnt = sc->node_prim_cnt[i];
     }
+    // do the child boxes follow the partition formula of their parent (octree.cpp:318-328)?  Then traversal derives them.
+    bool implicit = true;
+    for (uint32_t i = 0; i < sc->n_nodes && implicit; i++) {
+        const DNode& n = nodes[i];
+        if (!n.mask) continue;
+        const double* lo = n.bmin; const double* hi = n.bmax;
+        double mid[3], h[3];
+        for (int k = 0; k < 3; k++) { mid[k] = lo[k] + .5 * (hi[k] - lo[k]); h[k] = .5 * (hi[k] - lo[k]); }
+        uint32_t c = n.child;
+        for (int ci = 0; ci < 8; ci++) {
+            if (!(n.mask & (1u << ci))) continue;
+            double cmin[3], cmax[3];
+            const int bit[3] = { ci & 1, (ci >> 2) & 1, (ci >> 1) & 1 };   // x: bit0, y: bit2, z: bit1
+            for (int k = 0; k < 3; k++) {
+                if (ci == 7) { cmin[k] = mid[k]; cmax[k] = hi[k]; }
+                else if (bit[k]) { cmin[k] = lo[k] + h[k]; cmax[k] = mid[k] + h[k]; }
+                else { cmin[k] = lo[k]; cmax[k] = mid[k]; }
+            }
+            if (std::memcmp(cmin, nodes[c].bmin, 24) != 0 || std::memcmp(cmax, nodes[c].bmax, 24) != 0) { implicit = false; break; }
+            c++;
+        }
+    }
+    if (ctx->no_implicit) implicit = false;
     // leaf references: the primitive's geometry is replicated per (leaf, primitive) occurrence, in leaf order, so that a
     // leaf is one contiguous run of 80-byte records
     bool full = false;
@@ -346,9 +383,18 @@ extern "C" int gi_scene_upload(gi_ctx* ctx, const gi_scene_desc* sc)
     S.cam = sc->camera;
     for (int k = 0; k < 3; k++) S.ambient[k] = sc->ambient[k];
     S.full = full ? 1u : 0u;
+    S.implicit_boxes = implicit ? 1u : 0u;
     for (int k = 0; k < 6; k++) ctx->root_box[k] = sc->node_box[k];
     ctx->has_scene = true;   // photons / photon map are independent state and survive a re-upload (the reference keeps its
     return GI_OK;            // map across run() calls, raytracer.h:61); rebuild it explicitly when the geometry changed
+}
+
+extern "C" int gi_scene_info(gi_ctx* ctx, uint32_t out[4])
+{
+    if (!ctx || !out) return GI_ERR_INVALID;
+    if (!ctx->has_scene) return fail(ctx, GI_ERR_NO_SCENE, "no scene");
+    out[0] = ctx->S.full; out[1] = ctx->S.implicit_boxes; out[2] = ctx->S.n_nodes; out[3] = ctx->S.n_refs;
+    return GI_OK;
 }
 
 // ---- Halton entry points --------------------------------------------------------------------------------------------------------------
@@ -413,10 +459,9 @@ extern "C" int gi_trace_closest_dev(gi_ctx* ctx, size_t n, const double* org, co
     {
         ScopedTimer t(ctx, "trace_closest");
         if (ctx->trace_mode == 1) {
-            if (ctx->S.full) k_trace_closest_w<true><<<grid_for(n, GI_WPB), GI_WPB * 32, 0, ctx->stream>>>(ctx->S, n, org, dir, alpha_seed, prim, hit, normal, uv, work_ptr(ctx, 0));
-            else k_trace_closest_w<false><<<grid_for(n, GI_WPB), GI_WPB * 32, 0, ctx->stream>>>(ctx->S, n, org, dir, alpha_seed, prim, hit, normal, uv, work_ptr(ctx, 0));
-        } else if (ctx->S.full) k_trace_closest<true><<<grid_for(n, GI_BLOCK), GI_BLOCK, 0, ctx->stream>>>(ctx->S, n, org, dir, alpha_seed, prim, hit, normal, uv, work_ptr(ctx, 0));
-        else k_trace_closest<false><<<grid_for(n, GI_BLOCK), GI_BLOCK, 0, ctx->stream>>>(ctx->S, n, org, dir, alpha_seed, prim, hit, normal, uv, work_ptr(ctx, 0));
+            GI_LAUNCH(k_trace_closest_w, grid_for(n, GI_WPB), GI_WPB * 32, ctx->S, n, org, dir, alpha_seed, prim, hit, normal, uv, work_ptr(ctx, 0));
+            
+        } else GI_LAUNCH(k_trace_closest, grid_for(n, GI_BLOCK), GI_BLOCK, ctx->S, n, org, dir, alpha_seed, prim, hit, normal, uv, work_ptr(ctx, 0));
     }
     CK(cudaGetLastError());
     return GI_OK;
@@ -452,10 +497,9 @@ extern "C" int gi_trace_any_dev(gi_ctx* ctx, size_t n, const double* org, const 
     {
         ScopedTimer t(ctx, "trace_any");
         if (ctx->trace_mode == 1) {
-            if (ctx->S.full) k_trace_any_w<true><<<grid_for(n, GI_WPB), GI_WPB * 32, 0, ctx->stream>>>(ctx->S, n, org, dir, maxt2, alpha_seed, vis, work_ptr(ctx, 2));
-            else k_trace_any_w<false><<<grid_for(n, GI_WPB), GI_WPB * 32, 0, ctx->stream>>>(ctx->S, n, org, dir, maxt2, alpha_seed, vis, work_ptr(ctx, 2));
-        } else if (ctx->S.full) k_trace_any<true><<<grid_for(n, GI_BLOCK), GI_BLOCK, 0, ctx->stream>>>(ctx->S, n, org, dir, maxt2, alpha_seed, vis, work_ptr(ctx, 2));
-        else k_trace_any<false><<<grid_for(n, GI_BLOCK), GI_BLOCK, 0, ctx->stream>>>(ctx->S, n, org, dir, maxt2, alpha_seed, vis, work_ptr(ctx, 2));
+            GI_LAUNCH(k_trace_any_w, grid_for(n, GI_WPB), GI_WPB * 32, ctx->S, n, org, dir, maxt2, alpha_seed, vis, work_ptr(ctx, 2));
+            
+        } else GI_LAUNCH(k_trace_any, grid_for(n, GI_BLOCK), GI_BLOCK, ctx->S, n, org, dir, maxt2, alpha_seed, vis, work_ptr(ctx, 2));
     }
     CK(cudaGetLastError());
     return GI_OK;
@@ -540,8 +584,8 @@ extern "C" int gi_photon_trace(gi_ctx* ctx, int count, int max_depth, uint64_t s
     cudaEventRecord(e0, ctx->stream);
     {
         ScopedTimer t(ctx, "photon_trace");
-        if (ctx->S.full) k_photon_trace<true><<<grid_for(count, GI_BLOCK), GI_BLOCK, 0, ctx->stream>>>(ctx->S, count, max_depth, seed, O);
-        else k_photon_trace<false><<<grid_for(count, GI_BLOCK), GI_BLOCK, 0, ctx->stream>>>(ctx->S, count, max_depth, seed, O);
+        GI_LAUNCH(k_photon_trace, grid_for(count, GI_BLOCK), GI_BLOCK, ctx->S, count, max_depth, seed, O);
+        
     }
     CK(cudaGetLastError());
     // canonical (i, light) order: flags -> exclusive scan -> scatter
@@ -808,7 +852,6 @@ static int render_device(gi_ctx* ctx, const gi_render_params* P, int x0, int y0,
     DPathState PS{ ctx->ps[0].as<uint32_t>(), ctx->ps[1].as<uint64_t>(), ctx->ps[2].as<double>() };
     DCounters* C = ctx->b_cnt.as<DCounters>();
     DFrame F = make_frame(ctx, P->width, P->height, x0, y0, x1, y1);
-    const bool full = ctx->S.full != 0;
     const bool have_map = ctx->has_map && ctx->pm_kept > 0;
     uint64_t n_closest = 0, n_shadow = 0, n_gather = 0, launches = 0;
     for (const char* f : { "bounce", "direct", "gather", "tail" }) fam_reset(ctx, f);
@@ -828,8 +871,7 @@ static int render_device(gi_ctx* ctx, const gi_render_params* P, int x0, int y0,
                 ScopedTimer t(ctx, "tail");
                 CK(cudaMemsetAsync(&ctx->b_tail.as<DTailCounters>()->next, 0, 4, ctx->stream));
                 const unsigned tail_grid = std::min<unsigned>(grid_for(n_active, GI_WPB), 148u * 3u);   // 3 blocks of 4 warps fit per SM at 168 registers
-                if (full) k_tail<true><<<tail_grid, GI_WPB * 32, 0, ctx->stream>>>(ctx->S, ctx->G, have_map ? 1 : 0, *P, depth, n_active, in, PS, ctx->b_tail.as<DTailCounters>());
-                else k_tail<false><<<tail_grid, GI_WPB * 32, 0, ctx->stream>>>(ctx->S, ctx->G, have_map ? 1 : 0, *P, depth, n_active, in, PS, ctx->b_tail.as<DTailCounters>());
+                GI_LAUNCH(k_tail, tail_grid, GI_WPB * 32, ctx->S, ctx->G, have_map ? 1 : 0, *P, depth, n_active, in, PS, ctx->b_tail.as<DTailCounters>());
                 launches++;
                 CK(cudaGetLastError());
                 break;
@@ -837,8 +879,7 @@ static int render_device(gi_ctx* ctx, const gi_render_params* P, int x0, int y0,
             CK(cudaMemsetAsync(C, 0, sizeof(DCounters), ctx->stream));
             {
                 ScopedTimer t(ctx, "bounce");
-                if (full) k_bounce<true><<<grid_for(n_active, GI_BLOCK), GI_BLOCK, 0, ctx->stream>>>(ctx->S, *P, depth, n_active, in, out, H, PS, C, work_ptr(ctx, 0));
-                else k_bounce<false><<<grid_for(n_active, GI_BLOCK), GI_BLOCK, 0, ctx->stream>>>(ctx->S, *P, depth, n_active, in, out, H, PS, C, work_ptr(ctx, 0));
+                GI_LAUNCH(k_bounce, grid_for(n_active, GI_BLOCK), GI_BLOCK, ctx->S, *P, depth, n_active, in, out, H, PS, C, work_ptr(ctx, 0));
             }
             CK(cudaGetLastError());
             DCounters hc;
@@ -849,8 +890,7 @@ static int render_device(gi_ctx* ctx, const gi_render_params* P, int x0, int y0,
             if (hc.n_hits) {
                 if (ctx->S.n_lights) {
                     ScopedTimer t(ctx, "direct");
-                    if (full) k_direct<true><<<grid_for(hc.n_hits, GI_BLOCK), GI_BLOCK, 0, ctx->stream>>>(ctx->S, *P, depth, hc.n_hits, H, PS, work_ptr(ctx, 2));
-                    else k_direct<false><<<grid_for(hc.n_hits, GI_BLOCK), GI_BLOCK, 0, ctx->stream>>>(ctx->S, *P, depth, hc.n_hits, H, PS, work_ptr(ctx, 2));
+                    GI_LAUNCH(k_direct, grid_for(hc.n_hits, GI_BLOCK), GI_BLOCK, ctx->S, *P, depth, hc.n_hits, H, PS, work_ptr(ctx, 2));
                     launches++;
                     n_shadow += (uint64_t)hc.n_hits * ctx->S.n_lights;
                 }

@@ -52,6 +52,7 @@ struct DScene {
     const uint16_t* halton_tab;
     const DHaltonDim* halton_dims;   // [256]
     uint32_t full;                   // scene needs the FULL traversal (alpha materials or primitives that do not write uv)
+    uint32_t implicit_boxes;         // every child box equals the partition formula of its parent box (checked at upload)
 };
 
 // ---- fp64 vectors in glm's evaluation order -------------------------------------------------------------
@@ -176,6 +177,43 @@ __device__ __forceinline__ double box_entry(const double* bmin, const double* bm
 __device__ __forceinline__ bool box_contains(const double* bmin, const double* bmax, d3 p)
 {
     return p.x >= bmin[0] && p.y >= bmin[1] && p.z >= bmin[2] && p.x < bmax[0] && p.y < bmax[1] && p.z < bmax[2];
+}
+
+
+// ---- implicit child boxes ----------------------------------------------------------------------------------------------------
+// Octree::Node::partition (octree.cpp:318-328) derives the eight child boxes from the parent box alone: per axis the planes
+// are P0 = min, P1 = mid = min + .5*(max-min) (bit-identical to min + .5*d), P2 = mid + .5*d and P3 = max; the lower half is
+// [P0,P1], the upper half [P1,P2], and child 7 is [mid,max] = [P1,P3] on every axis.  When the uploaded tree obeys this
+// (verified bit-for-bit in gi_scene_upload) a traversal step needs only the parent's record: the slab parameter of each of
+// the 12 planes is computed once — the same (plane - o) * inv the reference computes per child — and shared by the children,
+// instead of loading eight 64-byte child records.
+struct PlaneT { double x[4], y[4], z[4]; };
+__device__ __forceinline__ void plane_params(const DNode& nd, const DRay& r, PlaneT& T)
+{
+    double mx = nd.bmin[0] + .5 * (nd.bmax[0] - nd.bmin[0]), my = nd.bmin[1] + .5 * (nd.bmax[1] - nd.bmin[1]), mz = nd.bmin[2] + .5 * (nd.bmax[2] - nd.bmin[2]);
+    double hx = .5 * (nd.bmax[0] - nd.bmin[0]), hy = .5 * (nd.bmax[1] - nd.bmin[1]), hz = .5 * (nd.bmax[2] - nd.bmin[2]);
+    T.x[0] = (nd.bmin[0] - r.o.x) * r.inv.x; T.x[1] = (mx - r.o.x) * r.inv.x; T.x[2] = ((mx + hx) - r.o.x) * r.inv.x; T.x[3] = (nd.bmax[0] - r.o.x) * r.inv.x;
+    T.y[0] = (nd.bmin[1] - r.o.y) * r.inv.y; T.y[1] = (my - r.o.y) * r.inv.y; T.y[2] = ((my + hy) - r.o.y) * r.inv.y; T.y[3] = (nd.bmax[1] - r.o.y) * r.inv.y;
+    T.z[0] = (nd.bmin[2] - r.o.z) * r.inv.z; T.z[1] = (mz - r.o.z) * r.inv.z; T.z[2] = ((mz + hz) - r.o.z) * r.inv.z; T.z[3] = (nd.bmax[2] - r.o.z) * r.inv.z;
+}
+// slab test of child i (bit0 = +x, bit1 = +z, bit2 = +y) from the shared plane parameters; same comparisons as bbox.h:47-73
+// (the per-axis early rejects of the reference are equivalent to one final test: tmin only grows, tmax only shrinks)
+__device__ __forceinline__ double child_entry(const PlaneT& T, int i, const DRay& r, double tmin, double tmax)
+{
+    const bool ux = i & 1, uz = i & 2, uy = i & 4, last = i == 7;
+    double a0 = ux ? T.x[1] : T.x[0], a1 = ux ? (last ? T.x[3] : T.x[2]) : T.x[1];
+    double b0 = uy ? T.y[1] : T.y[0], b1 = uy ? (last ? T.y[3] : T.y[2]) : T.y[1];
+    double c0 = uz ? T.z[1] : T.z[0], c1 = uz ? (last ? T.z[3] : T.z[2]) : T.z[1];
+    if (r.inv.x < 0.0) { double t = a0; a0 = a1; a1 = t; }
+    if (r.inv.y < 0.0) { double t = b0; b0 = b1; b1 = t; }
+    if (r.inv.z < 0.0) { double t = c0; c0 = c1; c1 = t; }
+    tmin = a0 > tmin ? a0 : tmin; tmax = a1 < tmax ? a1 : tmax;
+    if (tmax <= tmin) return -1.0;
+    tmin = b0 > tmin ? b0 : tmin; tmax = b1 < tmax ? b1 : tmax;
+    if (tmax <= tmin) return -1.0;
+    tmin = c0 > tmin ? c0 : tmin; tmax = c1 < tmax ? c1 : tmax;
+    if (tmax <= tmin) return -1.0;
+    return tmin;
 }
 
 __device__ __forceinline__ DNode load_node(const DNode* nodes, uint32_t i)
@@ -333,7 +371,7 @@ struct DHit {
     d3 n;              // cone normal (cones only)
 };
 
-template <bool FULL>
+template <bool FULL, bool IMPL>
 __device__ __forceinline__ void trace_closest(const DScene& S, const DRay& r, uint64_t seed, uint64_t path, uint64_t depth, DHit& out, uint32_t& n_node, uint32_t& n_prim)
 {
     uint32_t stack[GI_STACK_MAX];
@@ -349,63 +387,76 @@ __device__ __forceinline__ void trace_closest(const DScene& S, const DRay& r, ui
         stack[sp++] = 0;
     }
     bool term = false;
+    // "while-while": every lane first walks interior nodes until a leaf is on top (the warp re-converges after that
+    // inner loop), then all lanes test primitives together — instead of mixing leaf work and interior work in one loop.
     while (sp > 0 && !term) {
         uint32_t ni = stack[--sp];
         DNode nd = load_node(S.nodes, ni);
-        if (nd.mask == 0) {
-            const DLeafRef* refs = S.refs + nd.prim_off;
-            n_prim += nd.prim_cnt;
-            for (uint32_t k = 0; k < nd.prim_cnt; k++) {
-                const double2* rp = reinterpret_cast<const double2*>(refs + k);
-                double g[9];
-                double2 a0 = __ldg(rp), a1 = __ldg(rp + 1), a2 = __ldg(rp + 2), a3 = __ldg(rp + 3);
-                g[0] = a0.x; g[1] = a0.y; g[2] = a1.x; g[3] = a1.y; g[4] = a2.x; g[5] = a2.y; g[6] = a3.x; g[7] = a3.y;
-                uint4 tail = __ldg(reinterpret_cast<const uint4*>(rp + 4));
-                g[8] = __hiloint2double((int)tail.y, (int)tail.x);
-                uint32_t prim = tail.z, flags = tail.w;
-                double t, u = 0, v = 0; d3 cn = mk3(0, 0, 0);
-                bool ok;
-                uint32_t kind = LF_KIND(flags);
-                if (kind == GI_PRIM_TRIANGLE) { t = tri_hit(g, r, u, v); ok = t > 0; }
-                else if (kind == GI_PRIM_SPHERE) ok = sphere_hit(g, r, t);
-                else ok = cone_hit(g, S.prim_nrm + 9 * (size_t)prim, r, t, cn);
-                if (!ok) continue;
-                d3 hit = r.o + r.d * t;
-                if (FULL) {
-                    if (flags & LF_WRITES_UV) prim_uv_at(S, prim, hit, u, v, cur_tu, cur_tv);
-                    if ((flags & LF_ALPHA) && !alpha_pass(S, prim, ni, cur_tu, cur_tv, seed, path, depth, SITE_ALPHA_TRACE)) continue;
-                }
-                double d2 = len2(hit - r.o);
-                if (out.prim == GI_NO_HIT || d2 < best_d2) {
-                    out.prim = prim; out.t = t; out.u = u; out.v = v; out.n = cn; best_d2 = d2;
-                    if (FULL) { out.tu = cur_tu; out.tv = cur_tv; }
-                    if (box_contains(nd.bmin, nd.bmax, hit)) term = true;
+        bool have_leaf = true;
+        while (nd.mask != 0) {
+            // interior: entry distance of every existing child, then push far-to-near (ties: higher child index first,
+            // so that equal-distance children pop in child order)
+            double t0c[8];
+            n_node += __popc(nd.mask);
+            if (IMPL) {
+                PlaneT T;
+                plane_params(nd, r, T);
+#pragma unroll
+                for (int i = 0; i < 8; i++) t0c[i] = (nd.mask & (1u << i)) ? child_entry(T, i, r, 0.0, CUDART_INF) : -1.0;
+            } else {
+                uint32_t c = nd.child;
+#pragma unroll
+                for (int i = 0; i < 8; i++) {
+                    t0c[i] = -1.0;
+                    if (nd.mask & (1u << i)) {
+                        DNode ch = load_node(S.nodes, c);
+                        t0c[i] = box_entry(ch.bmin, ch.bmax, r, 0.0, CUDART_INF);
+                        c++;
+                    }
                 }
             }
-            continue;
-        }
-        // interior: entry distance of every existing child, then push far-to-near (ties: higher child index first,
-        // so that equal-distance children pop in child order)
-        double t0c[8];
-        uint32_t c = nd.child;
-        n_node += __popc(nd.mask);
+            for (;;) {
+                double bt = -1.0; int bi = -1;
 #pragma unroll
-        for (int i = 0; i < 8; i++) {
-            t0c[i] = -1.0;
-            if (nd.mask & (1u << i)) {
-                DNode ch = load_node(S.nodes, c);
-                t0c[i] = box_entry(ch.bmin, ch.bmax, r, 0.0, CUDART_INF);
-                c++;
+                for (int i = 0; i < 8; i++) if (t0c[i] >= bt && t0c[i] >= 0.0) { bt = t0c[i]; bi = i; }
+                if (bi < 0) break;
+                if (sp < GI_STACK_MAX) stack[sp++] = nd.child + __popc(nd.mask & ((1u << bi) - 1u));
+#pragma unroll
+                for (int i = 0; i < 8; i++) if (i == bi) t0c[i] = -1.0;
             }
+            if (sp == 0) { have_leaf = false; break; }
+            ni = stack[--sp];
+            nd = load_node(S.nodes, ni);
         }
-        for (;;) {
-            double bt = -1.0; int bi = -1;
-#pragma unroll
-            for (int i = 0; i < 8; i++) if (t0c[i] >= bt && t0c[i] >= 0.0) { bt = t0c[i]; bi = i; }
-            if (bi < 0) break;
-            if (sp < GI_STACK_MAX) stack[sp++] = nd.child + __popc(nd.mask & ((1u << bi) - 1u));
-#pragma unroll
-            for (int i = 0; i < 8; i++) if (i == bi) t0c[i] = -1.0;
+        if (!have_leaf) break;
+        const DLeafRef* refs = S.refs + nd.prim_off;
+        n_prim += nd.prim_cnt;
+        for (uint32_t k = 0; k < nd.prim_cnt; k++) {
+            const double2* rp = reinterpret_cast<const double2*>(refs + k);
+            double g[9];
+            double2 a0 = __ldg(rp), a1 = __ldg(rp + 1), a2 = __ldg(rp + 2), a3 = __ldg(rp + 3);
+            g[0] = a0.x; g[1] = a0.y; g[2] = a1.x; g[3] = a1.y; g[4] = a2.x; g[5] = a2.y; g[6] = a3.x; g[7] = a3.y;
+            uint4 tail = __ldg(reinterpret_cast<const uint4*>(rp + 4));
+            g[8] = __hiloint2double((int)tail.y, (int)tail.x);
+            uint32_t prim = tail.z, flags = tail.w;
+            double t, u = 0, v = 0; d3 cn = mk3(0, 0, 0);
+            bool ok;
+            uint32_t kind = LF_KIND(flags);
+            if (kind == GI_PRIM_TRIANGLE) { t = tri_hit(g, r, u, v); ok = t > 0; }
+            else if (kind == GI_PRIM_SPHERE) ok = sphere_hit(g, r, t);
+            else ok = cone_hit(g, S.prim_nrm + 9 * (size_t)prim, r, t, cn);
+            if (!ok) continue;
+            d3 hit = r.o + r.d * t;
+            if (FULL) {
+                if (flags & LF_WRITES_UV) prim_uv_at(S, prim, hit, u, v, cur_tu, cur_tv);
+                if ((flags & LF_ALPHA) && !alpha_pass(S, prim, ni, cur_tu, cur_tv, seed, path, depth, SITE_ALPHA_TRACE)) continue;
+            }
+            double d2 = len2(hit - r.o);
+            if (out.prim == GI_NO_HIT || d2 < best_d2) {
+                out.prim = prim; out.t = t; out.u = u; out.v = v; out.n = cn; best_d2 = d2;
+                if (FULL) { out.tu = cur_tu; out.tv = cur_tv; }
+                if (box_contains(nd.bmin, nd.bmax, hit)) term = true;
+            }
         }
     }
 }
@@ -413,7 +464,7 @@ __device__ __forceinline__ void trace_closest(const DScene& S, const DRay& r, ui
 // ---- any hit: RayTracer::visible (raytracer.h:280-319) over Octree::Node::intersect (octree.cpp:256-282) -------------------------
 // Returns true when nothing blocks the segment.  Visiting order is free: the alpha draw is keyed by the (leaf, primitive)
 // occurrence, so the outcome equals the reference's first-blocker search for any order.
-template <bool FULL>
+template <bool FULL, bool IMPL>
 __device__ __forceinline__ bool trace_visible(const DScene& S, const DRay& r, double mt, uint64_t seed, uint64_t path, uint64_t depth, uint64_t light, uint32_t& n_node, uint32_t& n_prim)
 {
     if (S.n_nodes == 0) return true;
@@ -429,44 +480,60 @@ __device__ __forceinline__ bool trace_visible(const DScene& S, const DRay& r, do
     while (sp > 0) {
         uint32_t ni = stack[--sp];
         DNode nd = load_node(S.nodes, ni);
-        if (nd.mask == 0) {
-            const DLeafRef* refs = S.refs + nd.prim_off;
-            for (uint32_t k = 0; k < nd.prim_cnt; k++) {
-                const double2* rp = reinterpret_cast<const double2*>(refs + k);
-                double g[9];
-                double2 a0 = __ldg(rp), a1 = __ldg(rp + 1), a2 = __ldg(rp + 2), a3 = __ldg(rp + 3);
-                g[0] = a0.x; g[1] = a0.y; g[2] = a1.x; g[3] = a1.y; g[4] = a2.x; g[5] = a2.y; g[6] = a3.x; g[7] = a3.y;
-                uint4 tail = __ldg(reinterpret_cast<const uint4*>(rp + 4));
-                g[8] = __hiloint2double((int)tail.y, (int)tail.x);
-                uint32_t prim = tail.z, flags = tail.w;
-                double t, u = 0, v = 0; d3 cn;
-                bool ok;
-                n_prim++;
-                uint32_t kind = LF_KIND(flags);
-                if (kind == GI_PRIM_TRIANGLE) { t = tri_hit(g, r, u, v); ok = t > 0; }
-                else if (kind == GI_PRIM_SPHERE) ok = sphere_hit(g, r, t);
-                else ok = cone_hit(g, S.prim_nrm + 9 * (size_t)prim, r, t, cn);
-                if (!ok) continue;
-                d3 pos = r.o + r.d * t;
-                if (FULL && (flags & LF_ALPHA)) {
-                    double tu = 0, tv = 0;   // `uv` is a fresh (0,0) per candidate in visible() (raytracer.h:295)
-                    if (flags & LF_WRITES_UV) prim_uv_at(S, prim, pos, u, v, tu, tv);
-                    if (!alpha_pass(S, prim, ni, tu, tv, seed, path, depth, SITE_ALPHA_SHADOW + (light << 8))) continue;
-                }
-                double t_shadow = len2(pos - r.o);
-                if ((t_shadow < mt) && (t_shadow > 0)) return false;
-            }
-            continue;
-        }
-        uint32_t c = nd.child;
-        n_node += __popc(nd.mask);
+        bool have_leaf = true;
+        while (nd.mask != 0) {
+            uint32_t c = nd.child;
+            n_node += __popc(nd.mask);
+            if (IMPL) {
+                PlaneT T;
+                plane_params(nd, r, T);
 #pragma unroll
-        for (int i = 0; i < 8; i++) {
-            if (nd.mask & (1u << i)) {
-                DNode ch = load_node(S.nodes, c);
-                if (box_entry(ch.bmin, ch.bmax, r, 0.0, tmax) >= 0.0 && sp < GI_STACK_MAX) stack[sp++] = c;
-                c++;
+                for (int i = 0; i < 8; i++) {
+                    if (nd.mask & (1u << i)) {
+                        if (child_entry(T, i, r, 0.0, tmax) >= 0.0 && sp < GI_STACK_MAX) stack[sp++] = c;
+                        c++;
+                    }
+                }
+            } else {
+#pragma unroll
+                for (int i = 0; i < 8; i++) {
+                    if (nd.mask & (1u << i)) {
+                        DNode ch = load_node(S.nodes, c);
+                        if (box_entry(ch.bmin, ch.bmax, r, 0.0, tmax) >= 0.0 && sp < GI_STACK_MAX) stack[sp++] = c;
+                        c++;
+                    }
+                }
             }
+            if (sp == 0) { have_leaf = false; break; }
+            ni = stack[--sp];
+            nd = load_node(S.nodes, ni);
+        }
+        if (!have_leaf) break;
+        const DLeafRef* refs = S.refs + nd.prim_off;
+        for (uint32_t k = 0; k < nd.prim_cnt; k++) {
+            const double2* rp = reinterpret_cast<const double2*>(refs + k);
+            double g[9];
+            double2 a0 = __ldg(rp), a1 = __ldg(rp + 1), a2 = __ldg(rp + 2), a3 = __ldg(rp + 3);
+            g[0] = a0.x; g[1] = a0.y; g[2] = a1.x; g[3] = a1.y; g[4] = a2.x; g[5] = a2.y; g[6] = a3.x; g[7] = a3.y;
+            uint4 tail = __ldg(reinterpret_cast<const uint4*>(rp + 4));
+            g[8] = __hiloint2double((int)tail.y, (int)tail.x);
+            uint32_t prim = tail.z, flags = tail.w;
+            double t, u = 0, v = 0; d3 cn;
+            bool ok;
+            n_prim++;
+            uint32_t kind = LF_KIND(flags);
+            if (kind == GI_PRIM_TRIANGLE) { t = tri_hit(g, r, u, v); ok = t > 0; }
+            else if (kind == GI_PRIM_SPHERE) ok = sphere_hit(g, r, t);
+            else ok = cone_hit(g, S.prim_nrm + 9 * (size_t)prim, r, t, cn);
+            if (!ok) continue;
+            d3 pos = r.o + r.d * t;
+            if (FULL && (flags & LF_ALPHA)) {
+                double tu = 0, tv = 0;   // `uv` is a fresh (0,0) per candidate in visible() (raytracer.h:295)
+                if (flags & LF_WRITES_UV) prim_uv_at(S, prim, pos, u, v, tu, tv);
+                if (!alpha_pass(S, prim, ni, tu, tv, seed, path, depth, SITE_ALPHA_SHADOW + (light << 8))) continue;
+            }
+            double t_shadow = len2(pos - r.o);
+            if ((t_shadow < mt) && (t_shadow > 0)) return false;
         }
     }
     return true;
@@ -478,7 +545,7 @@ __device__ __forceinline__ bool trace_visible(const DScene& S, const DRay& r, do
 // 32 primitives of a leaf at once (geometry only), and the reference's sequential acceptance rule is then replayed over
 // the geometric hits in stored order (there are rarely more than one or two per leaf).  Same visiting order, same
 // arithmetic, same results as trace_closest / trace_visible; `stack` is GI_STACK_MAX words of shared memory per warp.
-template <bool FULL>
+template <bool FULL, bool IMPL>
 __device__ __forceinline__ void trace_closest_warp(const DScene& S, const DRay& r, uint64_t seed, uint64_t path, uint64_t depth, DHit& out, uint32_t* stack, int lane,
                                                    uint32_t& n_node, uint32_t& n_prim)
 {
@@ -545,8 +612,8 @@ __device__ __forceinline__ void trace_closest_warp(const DScene& S, const DRay& 
         double t0 = -1.0; uint32_t cidx = 0;
         if (lane < 8 && ((nd.mask >> lane) & 1u)) {
             cidx = nd.child + __popc(nd.mask & ((1u << lane) - 1u));
-            DNode ch = load_node(S.nodes, cidx);
-            t0 = box_entry(ch.bmin, ch.bmax, r, 0.0, CUDART_INF);
+            if (IMPL) { PlaneT T; plane_params(nd, r, T); t0 = child_entry(T, lane, r, 0.0, CUDART_INF); }
+            else { DNode ch = load_node(S.nodes, cidx); t0 = box_entry(ch.bmin, ch.bmax, r, 0.0, CUDART_INF); }
         }
         uint32_t valid = __ballot_sync(0xffffffffu, t0 >= 0.0) & 0xffu;
         // far-to-near on the stack: rank = children that come before me in descending (t0, child index) order
@@ -563,7 +630,7 @@ __device__ __forceinline__ void trace_closest_warp(const DScene& S, const DRay& 
     }
 }
 
-template <bool FULL>
+template <bool FULL, bool IMPL>
 __device__ __forceinline__ bool trace_visible_warp(const DScene& S, const DRay& r, double mt, uint64_t seed, uint64_t path, uint64_t depth, uint64_t light, uint32_t* stack,
                                                    int lane, uint32_t& n_node, uint32_t& n_prim)
 {
@@ -622,8 +689,8 @@ __device__ __forceinline__ bool trace_visible_warp(const DScene& S, const DRay& 
         bool in = false; uint32_t cidx = 0;
         if (lane < 8 && ((nd.mask >> lane) & 1u)) {
             cidx = nd.child + __popc(nd.mask & ((1u << lane) - 1u));
-            DNode ch = load_node(S.nodes, cidx);
-            in = box_entry(ch.bmin, ch.bmax, r, 0.0, tmax) >= 0.0;
+            if (IMPL) { PlaneT T; plane_params(nd, r, T); in = child_entry(T, lane, r, 0.0, tmax) >= 0.0; }
+            else { DNode ch = load_node(S.nodes, cidx); in = box_entry(ch.bmin, ch.bmax, r, 0.0, tmax) >= 0.0; }
         }
         uint32_t valid = __ballot_sync(0xffffffffu, in) & 0xffu;
         if (in) { int pos = sp + __popc(valid & ((1u << lane) - 1u)); if (pos < GI_STACK_MAX) stack[pos] = cidx; }

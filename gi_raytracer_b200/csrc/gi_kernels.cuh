@@ -51,7 +51,7 @@ __global__ void k_camera_rays(DScene S, DFrame F, int s0, size_t n, double* org,
 }
 
 // ---- K2/K3 (API form): batch closest hit / any hit over caller-supplied rays --------------------------------------------------------
-template <bool FULL>
+template <bool FULL, bool IMPL>
 __global__ void __launch_bounds__(GI_BLOCK) k_trace_closest(DScene S, size_t n, const double* __restrict__ org, const double* __restrict__ dir, uint64_t seed,
                                                            uint32_t* __restrict__ prim, double* __restrict__ hit, double* __restrict__ normal, double* __restrict__ uv,
                                                            unsigned long long* work)
@@ -61,7 +61,7 @@ __global__ void __launch_bounds__(GI_BLOCK) k_trace_closest(DScene S, size_t n, 
     if (i < n) {
         DRay r = ray_as_stored(ld3(org + 3 * i), ld3(dir + 3 * i));
         DHit h;
-        trace_closest<FULL>(S, r, seed, (uint64_t)i, 0, h, nn_, np_);
+        trace_closest<FULL, IMPL>(S, r, seed, (uint64_t)i, 0, h, nn_, np_);
         if (prim) prim[i] = h.prim;
         d3 p = mk3(0, 0, 0), nn = mk3(0, 0, 0); double tu = 0, tv = 0;
         if (h.prim != GI_NO_HIT) hit_surface(S, r, h, FULL, p, nn, tu, tv);
@@ -72,7 +72,7 @@ __global__ void __launch_bounds__(GI_BLOCK) k_trace_closest(DScene S, size_t n, 
     tally2(work, nn_, np_);
 }
 
-template <bool FULL>
+template <bool FULL, bool IMPL>
 __global__ void __launch_bounds__(GI_BLOCK) k_trace_any(DScene S, size_t n, const double* __restrict__ org, const double* __restrict__ dir, const double* __restrict__ maxt2,
                                                        uint64_t seed, uint8_t* __restrict__ vis, unsigned long long* work)
 {
@@ -80,14 +80,14 @@ __global__ void __launch_bounds__(GI_BLOCK) k_trace_any(DScene S, size_t n, cons
     uint32_t nn_ = 0, np_ = 0;
     if (i < n) {
         DRay r = ray_as_stored(ld3(org + 3 * i), ld3(dir + 3 * i));
-        vis[i] = trace_visible<FULL>(S, r, maxt2[i], seed, (uint64_t)i, 0, 0, nn_, np_) ? 1 : 0;
+        vis[i] = trace_visible<FULL, IMPL>(S, r, maxt2[i], seed, (uint64_t)i, 0, 0, nn_, np_) ? 1 : 0;
     }
     tally2(work, nn_, np_);
 }
 
 // warp-per-ray forms of the two batch kernels (one ray per warp, see trace_closest_warp)
 #define GI_WPB 4   // warps per block in the warp-per-ray kernels
-template <bool FULL>
+template <bool FULL, bool IMPL>
 __global__ void __launch_bounds__(GI_WPB * 32) k_trace_closest_w(DScene S, size_t n, const double* __restrict__ org, const double* __restrict__ dir, uint64_t seed,
                                                                 uint32_t* __restrict__ prim, double* __restrict__ hit, double* __restrict__ normal, double* __restrict__ uv,
                                                                 unsigned long long* work)
@@ -99,7 +99,7 @@ __global__ void __launch_bounds__(GI_WPB * 32) k_trace_closest_w(DScene S, size_
     uint32_t nn_ = 0, np_ = 0;
     DRay r = ray_as_stored(ld3(org + 3 * i), ld3(dir + 3 * i));
     DHit h;
-    trace_closest_warp<FULL>(S, r, seed, (uint64_t)i, 0, h, s_stack[wib], lane, nn_, np_);
+    trace_closest_warp<FULL, IMPL>(S, r, seed, (uint64_t)i, 0, h, s_stack[wib], lane, nn_, np_);
     if (lane == 0) {
         if (prim) prim[i] = h.prim;
         d3 p = mk3(0, 0, 0), nn = mk3(0, 0, 0); double tu = 0, tv = 0;
@@ -110,7 +110,7 @@ __global__ void __launch_bounds__(GI_WPB * 32) k_trace_closest_w(DScene S, size_
         if (work) { atomicAdd(work, (unsigned long long)nn_); atomicAdd(work + 1, (unsigned long long)np_); }
     }
 }
-template <bool FULL>
+template <bool FULL, bool IMPL>
 __global__ void __launch_bounds__(GI_WPB * 32) k_trace_any_w(DScene S, size_t n, const double* __restrict__ org, const double* __restrict__ dir, const double* __restrict__ maxt2,
                                                             uint64_t seed, uint8_t* __restrict__ vis, unsigned long long* work)
 {
@@ -120,7 +120,7 @@ __global__ void __launch_bounds__(GI_WPB * 32) k_trace_any_w(DScene S, size_t n,
     if (i >= n) return;
     uint32_t nn_ = 0, np_ = 0;
     DRay r = ray_as_stored(ld3(org + 3 * i), ld3(dir + 3 * i));
-    bool v = trace_visible_warp<FULL>(S, r, maxt2[i], seed, (uint64_t)i, 0, 0, s_stack[wib], lane, nn_, np_);
+    bool v = trace_visible_warp<FULL, IMPL>(S, r, maxt2[i], seed, (uint64_t)i, 0, 0, s_stack[wib], lane, nn_, np_);
     if (lane == 0) {
         vis[i] = v ? 1 : 0;
         if (work) { atomicAdd(work, (unsigned long long)nn_); atomicAdd(work + 1, (unsigned long long)np_); }
@@ -323,15 +323,20 @@ __device__ __forceinline__ bool pm_find_leaf(const DGatherMap& M, d3 p, int lane
 {
     node = 0; depth = 0;
     if (M.n_nodes == 0) return false;
-    DNode nd = load_node(M.nodes, 0);
-    while (nd.mask != 0) {
+    uint4 top = __ldg(reinterpret_cast<const uint4*>(M.nodes) + 3);   // root topology: child, prim_off, prim_cnt, mask
+    uint32_t child = top.x, mask = top.w;
+    while (mask != 0) {
         depth++;
         bool in = false;
-        if (lane < 8) { DNode ch = load_node(M.nodes, nd.child + lane); in = box_contains(ch.bmin, ch.bmax, p); }
+        uint32_t cchild = 0, cmask = 0;
+        if (lane < 8) { DNode ch = load_node(M.nodes, child + lane); in = box_contains(ch.bmin, ch.bmax, p); cchild = ch.child; cmask = ch.mask; }
         uint32_t b = __ballot_sync(0xffffffffu, in) & 0xffu;
         if (!b) return false;   // box(-inf,-inf): nothing overlaps (photonMap.cpp:132)
-        node = nd.child + (__ffs(b) - 1);
-        nd = load_node(M.nodes, node);
+        int src = __ffs(b) - 1;
+        node = child + src;
+        // the lane that owns the containing child already holds its topology: one dependent load per level, not two
+        child = __shfl_sync(0xffffffffu, cchild, src);
+        mask = __shfl_sync(0xffffffffu, cmask, src);
     }
     return true;
 }
@@ -498,7 +503,7 @@ struct DHitList {
 struct DPathState { uint32_t* sample; uint64_t* key; double* L; };
 struct DCounters { uint32_t n_next, n_hits; unsigned long long closest, shadow, gathers; };
 
-template <bool FULL>
+template <bool FULL, bool IMPL>
 __global__ void __launch_bounds__(GI_BLOCK) k_bounce(DScene S, gi_render_params P, int depth, uint32_t n, DQueue in, DQueue out, DHitList H, DPathState PS, DCounters* C,
                                                      unsigned long long* work)
 {
@@ -517,7 +522,7 @@ __global__ void __launch_bounds__(GI_BLOCK) k_bounce(DScene S, gi_render_params 
         float sx = halton_sample(S, (uint32_t)(2 + 2 * depth), sample);     // raytracer.h:172-173
         float sy = halton_sample(S, (uint32_t)(3 + 2 * depth), sample);
         DHit h;
-        trace_closest<FULL>(S, r, P.seed, key, (uint64_t)depth, h, wn, wp);  // :190
+        trace_closest<FULL, IMPL>(S, r, P.seed, key, (uint64_t)depth, h, wn, wp);  // :190
         double* L = PS.L + 3 * (size_t)path;
         if (h.prim == GI_NO_HIT) {
             d3 a = T * ld3(S.ambient);                                       // :275
@@ -569,7 +574,7 @@ __global__ void __launch_bounds__(GI_BLOCK) k_bounce(DScene S, gi_render_params 
 }
 
 // ---- K3 in the pipeline: direct light with one shadow ray per light (raytracer.h:230-256) -----------------------------------------
-template <bool FULL>
+template <bool FULL, bool IMPL>
 __global__ void __launch_bounds__(GI_BLOCK) k_direct(DScene S, gi_render_params P, int depth, uint32_t n, DHitList H, DPathState PS, unsigned long long* work)
 {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -587,7 +592,7 @@ __global__ void __launch_bounds__(GI_BLOCK) k_direct(DScene S, gi_render_params 
         double maxt = len2(lightDir);
         double hfrac = 1 / (GI_D_PI * len2(ld3(light.pos) - p));                                                             // :238
         DRay sr = make_ray(sp, lightDir);                                                                                     // :241
-        if (trace_visible<FULL>(S, sr, maxt, P.seed, key, (uint64_t)depth, l, wn, wp)) {                                      // :243
+        if (trace_visible<FULL, IMPL>(S, sr, maxt, P.seed, key, (uint64_t)depth, l, wn, wp)) {                                      // :243
             double d = dot3(nn, normalize3(ld3(light.pos) - p));
             if (d < 0) d = 0;
             double lv = pow_like_libm(d, (1.0 / rough));                                                                      // :252
@@ -605,7 +610,7 @@ __global__ void __launch_bounds__(GI_BLOCK) k_direct(DScene S, gi_render_params 
 // each.  Arithmetic and the order in which terms are added to L[path] are those of k_bounce / k_direct / k_gather.
 struct DTailCounters { unsigned long long closest, shadow, gathers, nodes_c, prims_c, nodes_s, prims_s, g_depth, g_cand, g_sel; unsigned int next; unsigned int pad; };
 
-template <bool FULL>
+template <bool FULL, bool IMPL>
 __global__ void __launch_bounds__(GI_WPB * 32) k_tail(DScene S, DGatherMap G, int have_map, gi_render_params P, int depth0, uint32_t n, DQueue in, DPathState PS, DTailCounters* TC)
 {
     __shared__ uint32_t s_stack[GI_WPB][GI_STACK_MAX];
@@ -629,7 +634,7 @@ __global__ void __launch_bounds__(GI_WPB * 32) k_tail(DScene S, DGatherMap G, in
         float sx = halton_sample(S, (uint32_t)(2 + 2 * depth), sample);
         float sy = halton_sample(S, (uint32_t)(3 + 2 * depth), sample);
         DHit h;
-        trace_closest_warp<FULL>(S, r, P.seed, key, (uint64_t)depth, h, stack, lane, nc, pc);
+        trace_closest_warp<FULL, IMPL>(S, r, P.seed, key, (uint64_t)depth, h, stack, lane, nc, pc);
         c_closest++;
         if (h.prim == GI_NO_HIT) { L = L + T * ld3(S.ambient); break; }
         d3 hp, hn; double tu, tv;
@@ -659,7 +664,7 @@ __global__ void __launch_bounds__(GI_WPB * 32) k_tail(DScene S, DGatherMap G, in
                 double hfrac = 1 / (GI_D_PI * len2(ld3(light.pos) - hp));
                 DRay sr = make_ray(sp, lightDir);
                 c_shadow++;
-                if (trace_visible_warp<FULL>(S, sr, maxt, P.seed, key, (uint64_t)depth, l, stack, lane, ns, ps)) {
+                if (trace_visible_warp<FULL, IMPL>(S, sr, maxt, P.seed, key, (uint64_t)depth, l, stack, lane, ns, ps)) {
                     double d = dot3(hn, normalize3(ld3(light.pos) - hp));
                     if (d < 0) d = 0;
                     li = (ld3(light.col) * pow_like_libm(d, (1.0 / rough))) * hfrac;
@@ -743,7 +748,7 @@ __global__ void k_resolve(size_t n3, const double* accum, int spp, uint8_t* rgb8
 // ---- K5: photon emission and tracing (raytracer.h:582-715) ----------------------------------------------------------------------------
 struct DPhotonOut { double* ph; uint8_t* stored; unsigned long long* tries; unsigned long long* traces; unsigned long long* work; };
 
-template <bool FULL>
+template <bool FULL, bool IMPL>
 __global__ void __launch_bounds__(GI_BLOCK) k_photon_trace(DScene S, int count, int max_depth, uint64_t seed, DPhotonOut O)
 {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -764,14 +769,14 @@ __global__ void __launch_bounds__(GI_BLOCK) k_photon_trace(DScene S, int count, 
             d3 col = ld3(l.col) * ((1.0 / count) * .5 * l.angle);                               // :618
             int depth = 0; bool term = false, isCaustic = false;
             DHit h;
-            trace_closest<FULL>(S, r, seed, path, 0, h, wn, wp); my_traces++;
+            trace_closest<FULL, IMPL>(S, r, seed, path, 0, h, wn, wp); my_traces++;
             if (h.prim == GI_NO_HIT) { tries++; continue; }                                     // :626-630
             uint32_t cur = h.prim;
             d3 hit = mk3(0, 0, 0);
             while (depth < max_depth && !term) {                                                // :633
                 double roughness = S.mats[S.prim_mat[cur]].roughness;
                 if (roughness < 0.1) {
-                    trace_closest<FULL>(S, r, seed, path, (uint64_t)(depth + 1), h, wn, wp); my_traces++;   // :640
+                    trace_closest<FULL, IMPL>(S, r, seed, path, (uint64_t)(depth + 1), h, wn, wp); my_traces++;   // :640
                     if (h.prim == GI_NO_HIT) { term = true; continue; }
                     cur = h.prim;
                     d3 norm; double tu, tv;

@@ -152,6 +152,11 @@ int gi_synchronize(gi_ctx* ctx);
  *      the host builds the reference octree and hands it over flattened ----------------------------------- */
 int gi_scene_upload(gi_ctx* ctx, const gi_scene_desc* scene);
 
+/* traversal variant chosen for the uploaded scene: out = {full, implicit_boxes, n_nodes, n_leaf_refs}.  full = 1 when a material
+ * can fail the alpha test or a primitive does not write uv (the general kernels are used); implicit_boxes = 1 when every child
+ * box equals the partition formula of its parent, so the traversal derives child boxes instead of loading them. */
+int gi_scene_info(gi_ctx* ctx, uint32_t out[4]);
+
 /* ---- Halton (halton_sampler.h:626-888 sample, halton_enum.h:106-114 get_index) -------------------------- */
 int gi_halton_sample(gi_ctx* ctx, size_t n, const uint32_t* dim, const uint32_t* index, float* out);
 int gi_halton_index(gi_ctx* ctx, int width, int height, size_t n, const uint32_t* s, const uint32_t* x, const uint32_t* y,

@@ -394,3 +394,37 @@ def test_tail_kernel_equals_wavefront(lib_built, synth_dir, monkeypatch):
             assert sb.shade_ms > 0 and sa.shade_ms == 0
     finally:
         c0.close(); c1.close()
+
+
+def test_implicit_child_boxes_equal_loaded_boxes(lib_built, synth_dir, monkeypatch):
+    """Traversal with child boxes derived from the parent (the default for trees built by Octree::partition) must equal the
+    traversal that loads every child box, bit for bit; reference-built trees must qualify for the implicit path."""
+    from gi_raytracer_b200.capi import Context
+    monkeypatch.setenv("GI_NO_IMPLICIT_BOXES", "1")
+    ce = Context(0)
+    monkeypatch.delenv("GI_NO_IMPLICIT_BOXES")
+    ci = Context(0)
+    try:
+        for name in ("atrium", "mixed", "cornell_golden"):
+            sc = R.scene_from_npz(np.load(os.path.join(os.path.dirname(__file__), "golden", "cornell_small.npz"))) if name == "cornell_golden" else _load(name, synth_dir)
+            ce.upload_scene(sc); ci.upload_scene(sc)
+            assert ci.scene_info()["implicit_boxes"] == 1 and ce.scene_info()["implicit_boxes"] == 0
+            o, d, _ = ci.camera_rays(64, 64, 0, 0, 64, 64, 0, 1)
+            ro, rdir = random_rays(sc, 20000, seed=21)
+            o, d = np.concatenate([o, ro]), np.concatenate([d, rdir])
+            a, b = ci.trace_closest(o, d, alpha_seed=3), ce.trace_closest(o, d, alpha_seed=3)
+            assert all(bits_equal(x, y) for x, y in zip(a, b)), name
+            assert ci.last_work("trace_closest") == ce.last_work("trace_closest")
+            m = a[0] != 0xFFFFFFFF
+            so = a[1][m] + 1e-4 * a[2][m]
+            sd = sc.lights[0, :3][None, :] - so
+            mt = (sd * sd).sum(axis=1)
+            sd = sd * (1.0 / np.sqrt(mt))[:, None]
+            assert bits_equal(ci.trace_any(so, sd, mt), ce.trace_any(so, sd, mt)), name
+        # a hand-made tree whose child boxes do not follow the formula must fall back to loading them
+        sc = _load("mixed", synth_dir)
+        sc.node_box[1, 3] += 1e-9
+        ci.upload_scene(sc)
+        assert ci.scene_info()["implicit_boxes"] == 0
+    finally:
+        ce.close(); ci.close()
