@@ -6,6 +6,9 @@
 #include "gi_device.cuh"
 
 #define GI_BLOCK 128
+#ifndef GI_MINB
+#define GI_MINB 1   // minimum resident blocks per SM requested from ptxas for the thread-per-ray traversal kernels
+#endif
 #define GI_PM_LEAF_MAX 16   // MAX_PHOTONS_PER_LEAF (util.h:15)
 
 // ---- K0: Halton known-answer entry points -----------------------------------------------------------------------------------
@@ -52,7 +55,7 @@ __global__ void k_camera_rays(DScene S, DFrame F, int s0, size_t n, double* org,
 
 // ---- K2/K3 (API form): batch closest hit / any hit over caller-supplied rays --------------------------------------------------------
 template <bool FULL, bool IMPL>
-__global__ void __launch_bounds__(GI_BLOCK) k_trace_closest(DScene S, size_t n, const double* __restrict__ org, const double* __restrict__ dir, uint64_t seed,
+__global__ void __launch_bounds__(GI_BLOCK, GI_MINB) k_trace_closest(DScene S, size_t n, const double* __restrict__ org, const double* __restrict__ dir, uint64_t seed,
                                                            uint32_t* __restrict__ prim, double* __restrict__ hit, double* __restrict__ normal, double* __restrict__ uv,
                                                            unsigned long long* work)
 {
@@ -73,7 +76,7 @@ __global__ void __launch_bounds__(GI_BLOCK) k_trace_closest(DScene S, size_t n, 
 }
 
 template <bool FULL, bool IMPL>
-__global__ void __launch_bounds__(GI_BLOCK) k_trace_any(DScene S, size_t n, const double* __restrict__ org, const double* __restrict__ dir, const double* __restrict__ maxt2,
+__global__ void __launch_bounds__(GI_BLOCK, GI_MINB) k_trace_any(DScene S, size_t n, const double* __restrict__ org, const double* __restrict__ dir, const double* __restrict__ maxt2,
                                                        uint64_t seed, uint8_t* __restrict__ vis, unsigned long long* work)
 {
     size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
@@ -504,7 +507,7 @@ struct DPathState { uint32_t* sample; uint64_t* key; double* L; };
 struct DCounters { uint32_t n_next, n_hits; unsigned long long closest, shadow, gathers; };
 
 template <bool FULL, bool IMPL>
-__global__ void __launch_bounds__(GI_BLOCK) k_bounce(DScene S, gi_render_params P, int depth, uint32_t n, DQueue in, DQueue out, DHitList H, DPathState PS, DCounters* C,
+__global__ void __launch_bounds__(GI_BLOCK, GI_MINB) k_bounce(DScene S, gi_render_params P, int depth, uint32_t n, DQueue in, DQueue out, DHitList H, DPathState PS, DCounters* C,
                                                      unsigned long long* work)
 {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -575,7 +578,7 @@ __global__ void __launch_bounds__(GI_BLOCK) k_bounce(DScene S, gi_render_params 
 
 // ---- K3 in the pipeline: direct light with one shadow ray per light (raytracer.h:230-256) -----------------------------------------
 template <bool FULL, bool IMPL>
-__global__ void __launch_bounds__(GI_BLOCK) k_direct(DScene S, gi_render_params P, int depth, uint32_t n, DHitList H, DPathState PS, unsigned long long* work)
+__global__ void __launch_bounds__(GI_BLOCK, GI_MINB) k_direct(DScene S, gi_render_params P, int depth, uint32_t n, DHitList H, DPathState PS, unsigned long long* work)
 {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     uint32_t wn = 0, wp = 0;
