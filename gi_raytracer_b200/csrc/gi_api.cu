@@ -54,10 +54,11 @@ struct gi_ctx {
     DGatherMap G{};
     // workspaces
     DevBuf w0, w1, w2, w3, w4, w5, w6, w7, w8, w9;           // API staging
-    DevBuf q_a[5], q_b[5], hl[7], ps[3], b_cnt, b_accum, b_scan0, b_scan1, b_misc, b_work, b_tail;
+    DevBuf q_a[5], q_b[5], hl[7], ps[3], b_cnt, b_accum, b_scan0, b_scan1, b_misc, b_work, b_tail, b_binkey, b_binperm, b_binhist, b_bincur, b_gnode, b_gperm, b_ghist, b_gcur, b_gheavy;
     bool no_implicit = false;      // GI_NO_IMPLICIT_BOXES at gi_create: always load child boxes (for A/B tests)
     int trace_mode = 0;            // 0: thread per ray, 1: warp per ray (API batch kernels; GI_TRACE_MODE)
     uint32_t tail_threshold = 32768; // queues smaller than this finish in the tail megakernel (GI_TAIL_THRESHOLD, 0 = off)
+    uint32_t bin_threshold = 65536;  // queues at least this long are binned by origin cell / direction octant before the next bounce (GI_BIN_THRESHOLD, 0 = off)
     unsigned long long work_host[16] = { 0 };   // [0,1] closest nodes/prims, [2,3] any-hit, [4..6] gather depth/cand/sel, [8] rays, [9] shadow rays, [10] queries
     // timing
     std::vector<TimedLaunch> pending;
@@ -219,6 +220,7 @@ extern "C" int gi_create(int device, gi_ctx** out)
     if (getenv("GI_NO_IMPLICIT_BOXES")) ctx->no_implicit = true;
     if (const char* e = getenv("GI_TRACE_MODE")) ctx->trace_mode = atoi(e);
     if (const char* e = getenv("GI_TAIL_THRESHOLD")) ctx->tail_threshold = (uint32_t)strtoul(e, nullptr, 10);
+    if (const char* e = getenv("GI_BIN_THRESHOLD")) ctx->bin_threshold = (uint32_t)strtoul(e, nullptr, 10);
     *out = ctx;
     return GI_OK;
 }
@@ -230,7 +232,8 @@ extern "C" void gi_destroy(gi_ctx* ctx)
     cudaStreamSynchronize(ctx->stream);
     DevBuf* all[] = { &ctx->b_nodes, &ctx->b_refs, &ctx->b_geom, &ctx->b_nrm, &ctx->b_uv, &ctx->b_fnorm, &ctx->b_pmat, &ctx->b_ptype, &ctx->b_mats, &ctx->b_tex, &ctx->b_texpx,
                       &ctx->b_lights, &ctx->b_htab, &ctx->b_hdims, &ctx->b_photons, &ctx->b_slab, &ctx->w0, &ctx->w1, &ctx->w2, &ctx->w3, &ctx->w4, &ctx->w5, &ctx->w6, &ctx->w7,
-                      &ctx->w8, &ctx->w9, &ctx->b_cnt, &ctx->b_accum, &ctx->b_scan0, &ctx->b_scan1, &ctx->b_misc, &ctx->b_work, &ctx->b_tail };
+                      &ctx->w8, &ctx->w9, &ctx->b_cnt, &ctx->b_accum, &ctx->b_scan0, &ctx->b_scan1, &ctx->b_misc, &ctx->b_work, &ctx->b_tail, &ctx->b_binkey, &ctx->b_binperm,
+                      &ctx->b_binhist, &ctx->b_bincur, &ctx->b_gnode, &ctx->b_gperm, &ctx->b_ghist, &ctx->b_gcur, &ctx->b_gheavy };
     for (DevBuf* b : all) b->release();
     for (auto& b : ctx->q_a) b.release();
     for (auto& b : ctx->q_b) b.release();
@@ -527,7 +530,7 @@ static int scan_exclusive(gi_ctx* ctx, const uint32_t* in, int stride_words, uin
     CK(ctx->b_scan1.reserve((size_t)std::max<uint32_t>(nb, 1) * 4));
     if (n) {
         k_scan_block<<<nb, GI_SCAN_BLOCK, 0, ctx->stream>>>(in, n, out, ctx->b_scan1.as<uint32_t>(), stride_words);
-        k_scan_sums<<<1, 1, 0, ctx->stream>>>(ctx->b_scan1.as<uint32_t>(), nb, total_dev);
+        k_scan_sums<<<1, GI_SCAN_BLOCK, 0, ctx->stream>>>(ctx->b_scan1.as<uint32_t>(), nb, total_dev);
         k_scan_apply<<<nb, GI_SCAN_BLOCK, 0, ctx->stream>>>(out, n, ctx->b_scan1.as<uint32_t>());
     } else if (total_dev) CK(cudaMemsetAsync(total_dev, 0, 4, ctx->stream));
     CK(cudaGetLastError());
@@ -613,19 +616,20 @@ extern "C" int gi_photon_trace(gi_ctx* ctx, int count, int max_depth, uint64_t s
 }
 
 // ---- photon map ---------------------------------------------------------------------------------------------------------------------------
-struct SlabHeader { uint32_t magic, n_nodes, n_kept, n_leaves, max_depth, n_cand, pad[2]; uint64_t off_nodes, off_pos, off_dircol, off_pid, off_cand_off, off_cand_slot, total; };
-#define GI_SLAB_MAGIC 0x47495032u   // "GIP2"
+struct SlabHeader { uint32_t magic, n_nodes, n_kept, n_leaves, max_depth, n_cand, pad[2]; uint64_t off_nodes, off_pos, off_dircol, off_pid, off_cand_off, off_cand_slot, off_cand_key, total; };
+#define GI_SLAB_MAGIC 0x47495034u   // "GIP4"
 static inline size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
 
 static void bind_slab(gi_ctx* ctx, const SlabHeader& h)
 {
     char* base = ctx->b_slab.as<char>();
     ctx->G.nodes = reinterpret_cast<const DNode*>(base + h.off_nodes);
-    ctx->G.pos = reinterpret_cast<const double*>(base + h.off_pos);
+    ctx->G.pos4 = reinterpret_cast<const double*>(base + h.off_pos);
     ctx->G.dircol = reinterpret_cast<const double*>(base + h.off_dircol);
     ctx->G.pid = reinterpret_cast<const uint32_t*>(base + h.off_pid);
     ctx->G.cand_off = reinterpret_cast<const uint32_t*>(base + h.off_cand_off);
     ctx->G.cand_slot = reinterpret_cast<const uint32_t*>(base + h.off_cand_slot);
+    ctx->G.cand_key = reinterpret_cast<const float*>(base + h.off_cand_key);
     ctx->G.n_nodes = h.n_nodes;
     ctx->pm_nodes = h.n_nodes; ctx->pm_kept = h.n_kept; ctx->pm_leaves = h.n_leaves; ctx->pm_depth = h.max_depth;
     ctx->slab_bytes = h.total;
@@ -694,21 +698,41 @@ extern "C" int gi_photon_map_build(gi_ctx* ctx, const double* box6)
     CK(cudaStreamSynchronize(ctx->stream));
     if (host_cnt[2]) return fail(ctx, GI_ERR_OOM, "photon map candidate traversal stack overflow");
     const uint32_t n_cand = host_cnt[0];
-    // compact slab: header | nodes | pos | dircol | pid | cand_off | cand_slot
+    // compact slab: header | nodes | pos4 | dircol | pid | cand_off | cand_slot | cand_key
     SlabHeader h{};
     h.magic = GI_SLAB_MAGIC; h.n_nodes = n_nodes; h.n_kept = n_kept; h.max_depth = depth; h.n_cand = n_cand;
-    h.off_nodes = 256; h.off_pos = align256(h.off_nodes + (size_t)n_nodes * sizeof(DNode)); h.off_dircol = align256(h.off_pos + (size_t)n_kept * 24);
+    h.off_nodes = 256; h.off_pos = align256(h.off_nodes + (size_t)n_nodes * sizeof(DNode)); h.off_dircol = align256(h.off_pos + (size_t)n_kept * 32);
     h.off_pid = align256(h.off_dircol + (size_t)n_kept * 48); h.off_cand_off = align256(h.off_pid + (size_t)n_kept * 4);
-    h.off_cand_slot = align256(h.off_cand_off + (size_t)(n_nodes + 1) * 4); h.total = align256(h.off_cand_slot + (size_t)n_cand * 4);
+    h.off_cand_slot = align256(h.off_cand_off + (size_t)(n_nodes + 1) * 4); h.off_cand_key = align256(h.off_cand_slot + (size_t)n_cand * 4);
+    h.total = align256(h.off_cand_key + (size_t)n_cand * 4);
     CK(ctx->b_slab.reserve(h.total));
     char* base = ctx->b_slab.as<char>();
     CK(cudaMemcpyAsync(base + h.off_nodes, M.nodes, (size_t)n_nodes * sizeof(DNode), cudaMemcpyDeviceToDevice, ctx->stream));
     if (n_kept) CK(cudaMemcpyAsync(base + h.off_pid, M.pid, (size_t)n_kept * 4, cudaMemcpyDeviceToDevice, ctx->stream));
     CK(cudaMemcpyAsync(base + h.off_cand_off, cand_off, (size_t)(n_nodes + 1) * 4, cudaMemcpyDeviceToDevice, ctx->stream));
     k_pm_cands<4, true><<<grid_for(n_nodes, 4), 128, 0, ctx->stream>>>(M.nodes, n_nodes, nullptr, cand_off, reinterpret_cast<uint32_t*>(base + h.off_cand_slot), M.overflow);
-    M.pos = reinterpret_cast<double*>(base + h.off_pos); M.dircol = reinterpret_cast<double*>(base + h.off_dircol);
+    M.pos4 = reinterpret_cast<double*>(base + h.off_pos); M.dircol = reinterpret_cast<double*>(base + h.off_dircol);
     if (n_kept) k_pm_payload<<<grid_for(n_kept, 256), 256, 0, ctx->stream>>>(M, n_kept);
     CK(cudaGetLastError());
+    // order every candidate list by distance from its leaf centre (the gather's early stop): short lists with small blocks,
+    // long ones with up to 96 KB of shared memory per block
+    if (n_cand) {
+        const uint32_t SHORT_LEN = 512, LONG_LEN = 8192;
+        if (getenv("GI_TRACE_LAUNCHES")) {
+            std::vector<uint32_t> hc(n_nodes);
+            cudaMemcpy(hc.data(), cand_cnt, (size_t)n_nodes * 4, cudaMemcpyDeviceToHost);
+            uint64_t n512 = 0, n8k = 0, n64k = 0, mx = 0, s8k = 0;
+            for (uint32_t v : hc) { n512 += v > 512; n8k += v > 8192; n64k += v > 65536; mx = std::max<uint64_t>(mx, v); if (v > 8192) s8k += v; }
+            fprintf(stderr, "[gi] candidate lists: %u total entries, max %llu, >512: %llu, >8192: %llu (sum %llu), >65536: %llu\n", n_cand, (unsigned long long)mx, (unsigned long long)n512,
+                    (unsigned long long)n8k, (unsigned long long)s8k, (unsigned long long)n64k);
+        }
+        CK(cudaFuncSetAttribute(k_pm_cand_order, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(LONG_LEN * 12)));
+        uint32_t* cslot = reinterpret_cast<uint32_t*>(base + h.off_cand_slot);
+        float* ckey = reinterpret_cast<float*>(base + h.off_cand_key);
+        k_pm_cand_order<<<n_nodes, 64, SHORT_LEN * 12, ctx->stream>>>(M.nodes, n_nodes, M.pos4, cand_off, cslot, ckey, 0u, SHORT_LEN, LONG_LEN);
+        k_pm_cand_order<<<n_nodes, 256, LONG_LEN * 12, ctx->stream>>>(M.nodes, n_nodes, M.pos4, cand_off, cslot, ckey, SHORT_LEN, 0xFFFFFFFFu, LONG_LEN);
+        CK(cudaGetLastError());
+    }
     // leaves are counted on the host from the node records (also validates the build)
     std::vector<DNode> hn(n_nodes);
     CK(cudaMemcpyAsync(hn.data(), M.nodes, (size_t)n_nodes * sizeof(DNode), cudaMemcpyDeviceToHost, ctx->stream));
@@ -791,13 +815,37 @@ extern "C" int gi_photon_map_adopt_slab(gi_ctx* ctx, size_t bytes)
     CK(cudaSetDevice(ctx->device));
     SlabHeader h;
     CK(cudaMemcpy(&h, ctx->b_slab.p, sizeof(h), cudaMemcpyDeviceToHost));
-    if (h.magic != GI_SLAB_MAGIC || h.total != bytes || h.off_pid + (uint64_t)h.n_kept * 4 > bytes || h.off_cand_slot + (uint64_t)h.n_cand * 4 > bytes) return fail(ctx, GI_ERR_INVALID, "bad photon map slab");
+    if (h.magic != GI_SLAB_MAGIC || h.total != bytes || h.off_pid + (uint64_t)h.n_kept * 4 > bytes || h.off_cand_key + (uint64_t)h.n_cand * 4 > bytes) return fail(ctx, GI_ERR_INVALID, "bad photon map slab");
     bind_slab(ctx, h);
     return GI_OK;
 }
 
 // ---- gather ---------------------------------------------------------------------------------------------------------------------------------
-#define GI_GATHER_WARPS 4
+// the gather pipeline on device pointers: locate -> order by leaf (counting sort) -> one thread per query
+#define GI_GATHER_SORT_MIN 2048u   // shorter queues skip the ordering
+static int run_gather(gi_ctx* ctx, uint32_t n, const double* pos, const double* dir, int k, double* rgb, uint32_t* knn, uint32_t* n_cand, const double* weight, double* accum,
+                      const uint32_t* accum_idx, uint64_t* launches)
+{
+    const uint32_t nk = ctx->G.n_nodes + 1;   // keys: leaf node id, n_nodes = "in no leaf"
+    const bool order = n >= GI_GATHER_SORT_MIN;
+    CK(ctx->b_gnode.reserve((size_t)n * 4)); CK(ctx->b_gheavy.reserve((size_t)n * 4 + 16));
+    uint32_t* heavy_cnt = ctx->b_gheavy.as<uint32_t>();      // [0] queued, [1] next; the queue starts at [4]
+    CK(cudaMemsetAsync(heavy_cnt, 0, 16, ctx->stream));
+    if (order) { CK(ctx->b_gperm.reserve((size_t)n * 4)); CK(ctx->b_ghist.reserve((size_t)nk * 4)); CK(ctx->b_gcur.reserve((size_t)nk * 4)); CK(cudaMemsetAsync(ctx->b_ghist.p, 0, (size_t)nk * 4, ctx->stream)); }
+    k_gather_locate<<<grid_for(n, 256), 256, 0, ctx->stream>>>(ctx->G, n, pos, ctx->b_gnode.as<uint32_t>(), order ? ctx->b_ghist.as<uint32_t>() : nullptr, work_ptr(ctx, 4));
+    if (order) {
+        int rc = scan_exclusive(ctx, ctx->b_ghist.as<uint32_t>(), 1, nk, ctx->b_gcur.as<uint32_t>(), nullptr);
+        if (rc != GI_OK) return rc;
+        k_bin_scatter<<<grid_for(n, 256), 256, 0, ctx->stream>>>(n, ctx->b_gnode.as<uint32_t>(), ctx->b_gcur.as<uint32_t>(), ctx->b_gperm.as<uint32_t>());
+    }
+    k_gather_sorted<<<grid_for(n, GI_GS_BLOCK), GI_GS_BLOCK, 0, ctx->stream>>>(ctx->G, n, order ? ctx->b_gperm.as<uint32_t>() : nullptr, ctx->b_gnode.as<uint32_t>(), pos, dir, k, rgb, knn, n_cand,
+                                                                              weight, accum, accum_idx, work_ptr(ctx, 4), heavy_cnt + 4, heavy_cnt);
+    k_gather_heavy<<<148 * 4, GI_WPB * 32, 0, ctx->stream>>>(ctx->G, heavy_cnt + 4, heavy_cnt, heavy_cnt + 1, ctx->b_gnode.as<uint32_t>(), pos, dir, k, rgb, knn, n_cand, weight, accum, accum_idx);
+    CK(cudaGetLastError());
+    if (launches) *launches += order ? 7 : 3;
+    return GI_OK;
+}
+
 extern "C" int gi_photon_gather_dev(gi_ctx* ctx, size_t n, const double* pos, const double* dir, int k, double* rgb, uint32_t* knn, uint32_t* n_cand)
 {
     if (!ctx || (n && (!pos || !dir)) || k < 1 || k > 32) return GI_ERR_INVALID;
@@ -809,7 +857,9 @@ extern "C" int gi_photon_gather_dev(gi_ctx* ctx, size_t n, const double* pos, co
     ctx->work_host[10] = n;
     {
         ScopedTimer t(ctx, "gather");
-        k_gather<GI_GATHER_WARPS><<<grid_for(n, GI_GATHER_WARPS), GI_GATHER_WARPS * 32, 0, ctx->stream>>>(ctx->G, n, pos, dir, k, rgb, knn, n_cand, nullptr, nullptr, nullptr, work_ptr(ctx, 4));
+        if (n > 0xFFFFFFF0ull) return fail(ctx, GI_ERR_INVALID, "too many queries in one call");
+        int rc = run_gather(ctx, (uint32_t)n, pos, dir, k, rgb, knn, n_cand, nullptr, nullptr, nullptr, nullptr);
+        if (rc != GI_OK) return rc;
     }
     CK(cudaGetLastError());
     return GI_OK;
@@ -846,6 +896,11 @@ static int render_device(gi_ctx* ctx, const gi_render_params* P, int x0, int y0,
     CK(ctx->b_cnt.reserve(sizeof(DCounters)));
     CK(ctx->b_tail.reserve(sizeof(DTailCounters)));
     CK(cudaMemsetAsync(ctx->b_tail.p, 0, sizeof(DTailCounters), ctx->stream));
+    const bool binning = ctx->bin_threshold > 0 && chunk_cap >= ctx->bin_threshold;
+    if (binning) { CK(ctx->b_binkey.reserve((size_t)chunk_cap * 4)); CK(ctx->b_binperm.reserve((size_t)chunk_cap * 4)); CK(ctx->b_binhist.reserve((size_t)GI_SORT_BINS * 4)); CK(ctx->b_bincur.reserve((size_t)GI_SORT_BINS * 4)); }
+    d3 bin_min, bin_inv;
+    bin_min.x = ctx->root_box[0]; bin_min.y = ctx->root_box[1]; bin_min.z = ctx->root_box[2];
+    bin_inv.x = 32.0 / std::max(ctx->root_box[3] - ctx->root_box[0], 1e-300); bin_inv.y = 32.0 / std::max(ctx->root_box[4] - ctx->root_box[1], 1e-300); bin_inv.z = 32.0 / std::max(ctx->root_box[5] - ctx->root_box[2], 1e-300);
     DQueue qa{ ctx->q_a[0].as<double>(), ctx->q_a[1].as<double>(), ctx->q_a[2].as<double>(), ctx->q_a[3].as<double>(), ctx->q_a[4].as<uint32_t>() };
     DQueue qb{ ctx->q_b[0].as<double>(), ctx->q_b[1].as<double>(), ctx->q_b[2].as<double>(), ctx->q_b[3].as<double>(), ctx->q_b[4].as<uint32_t>() };
     DHitList H{ ctx->hl[0].as<double>(), ctx->hl[1].as<double>(), ctx->hl[2].as<double>(), ctx->hl[3].as<double>(), ctx->hl[4].as<double>(), ctx->hl[5].as<double>(), ctx->hl[6].as<uint32_t>() };
@@ -854,7 +909,7 @@ static int render_device(gi_ctx* ctx, const gi_render_params* P, int x0, int y0,
     DFrame F = make_frame(ctx, P->width, P->height, x0, y0, x1, y1);
     const bool have_map = ctx->has_map && ctx->pm_kept > 0;
     uint64_t n_closest = 0, n_shadow = 0, n_gather = 0, launches = 0;
-    for (const char* f : { "bounce", "direct", "gather", "tail" }) fam_reset(ctx, f);
+    for (const char* f : { "bounce", "direct", "gather", "tail", "bin" }) fam_reset(ctx, f);
     CK(cudaMemsetAsync(work_ptr(ctx, 0), 0, 8 * sizeof(unsigned long long), ctx->stream));
     cudaEvent_t e0 = get_event(ctx), e1 = get_event(ctx);
     cudaEventRecord(e0, ctx->stream);
@@ -865,6 +920,7 @@ static int render_device(gi_ctx* ctx, const gi_render_params* P, int x0, int y0,
         launches++;
         DQueue in = qa, out = qb;
         uint32_t n_active = n;
+        const uint32_t* perm = nullptr;
         for (int depth = 0; n_active > 0 && depth <= P->max_depth; depth++) {
             if (depth > 0 && n_active < ctx->tail_threshold) {
                 // few paths left: one warp per path runs them to the end inside one kernel
@@ -879,7 +935,7 @@ static int render_device(gi_ctx* ctx, const gi_render_params* P, int x0, int y0,
             CK(cudaMemsetAsync(C, 0, sizeof(DCounters), ctx->stream));
             {
                 ScopedTimer t(ctx, "bounce");
-                GI_LAUNCH(k_bounce, grid_for(n_active, GI_BLOCK), GI_BLOCK, ctx->S, *P, depth, n_active, in, out, H, PS, C, work_ptr(ctx, 0));
+                GI_LAUNCH(k_bounce, grid_for(n_active, GI_BLOCK), GI_BLOCK, ctx->S, *P, depth, n_active, in, perm, out, H, PS, C, work_ptr(ctx, 0));
             }
             CK(cudaGetLastError());
             DCounters hc;
@@ -898,9 +954,8 @@ static int render_device(gi_ctx* ctx, const gi_render_params* P, int x0, int y0,
                     n_gather += hc.n_hits;   // samplePhotons is called whether or not photons exist (raytracer.h:258)
                     if (have_map) {
                         ScopedTimer t(ctx, "gather");
-                        k_gather<GI_GATHER_WARPS><<<grid_for(hc.n_hits, GI_GATHER_WARPS), GI_GATHER_WARPS * 32, 0, ctx->stream>>>(ctx->G, hc.n_hits, H.p, H.refdir, P->k_photons, nullptr, nullptr,
-                                                                                                                          nullptr, H.wcaustic, PS.L, H.path, work_ptr(ctx, 4));
-                        launches++;
+                        int rcg = run_gather(ctx, hc.n_hits, H.p, H.refdir, P->k_photons, nullptr, nullptr, nullptr, H.wcaustic, PS.L, H.path, &launches);
+                        if (rcg != GI_OK) return rcg;
                     }
                 }
                 CK(cudaGetLastError());
@@ -912,6 +967,19 @@ static int render_device(gi_ctx* ctx, const gi_render_params* P, int x0, int y0,
             }
             n_active = hc.n_next;
             std::swap(in, out);
+            perm = nullptr;
+            if (binning && n_active >= ctx->bin_threshold && depth + 1 <= P->max_depth) {
+                // bin the scattered rays by origin cell and direction octant (k_bin_*): the next bounce reads them through `perm`
+                ScopedTimer t(ctx, "bin");
+                CK(cudaMemsetAsync(ctx->b_binhist.p, 0, (size_t)GI_SORT_BINS * 4, ctx->stream));
+                k_bin_keys<<<grid_for(n_active, 256), 256, 0, ctx->stream>>>(n_active, in.o, in.d, bin_min, bin_inv, ctx->b_binkey.as<uint32_t>(), ctx->b_binhist.as<uint32_t>());
+                int rcs = scan_exclusive(ctx, ctx->b_binhist.as<uint32_t>(), 1, GI_SORT_BINS, ctx->b_bincur.as<uint32_t>(), nullptr);
+                if (rcs != GI_OK) return rcs;
+                k_bin_scatter<<<grid_for(n_active, 256), 256, 0, ctx->stream>>>(n_active, ctx->b_binkey.as<uint32_t>(), ctx->b_bincur.as<uint32_t>(), ctx->b_binperm.as<uint32_t>());
+                CK(cudaGetLastError());
+                launches += 5;
+                perm = ctx->b_binperm.as<uint32_t>();
+            }
         }
         k_accumulate<<<grid_for(npx, 256), 256, 0, ctx->stream>>>(c0, n, npx, PS.L, accum_dev);
         launches++;

@@ -140,7 +140,7 @@ struct DPMap {
     uint32_t n_photons;
     uint32_t* pnode;            // node of each photon during the build (0xFFFFFFFF = dropped)
     // leaf-ordered photon storage (after finalize)
-    double* pos;                // [kept][3]
+    double* pos4;               // [kept][4]: x, y, z, pad — 32-byte records, two aligned 16-byte loads per candidate
     double* dircol;             // [kept][6]
     uint32_t* pid;              // [kept] original photon index
     uint32_t* n_kept;
@@ -230,10 +230,29 @@ __global__ void k_scan_block(const uint32_t* in_stride16, uint32_t n, uint32_t* 
 }
 __global__ void k_scan_sums(uint32_t* block_sums, uint32_t nb, uint32_t* total)
 {
-    // single thread: nb is at most a few thousand
-    uint32_t acc = 0;
-    for (uint32_t b = 0; b < nb; b++) { uint32_t v = block_sums[b]; block_sums[b] = acc; acc += v; }
-    if (total) *total = acc;
+    // one block: exclusive scan of the block sums, GI_SCAN_BLOCK at a time with a running carry
+    __shared__ uint32_t sh[GI_SCAN_BLOCK];
+    __shared__ uint32_t carry;
+    if (threadIdx.x == 0) carry = 0;
+    __syncthreads();
+    for (uint32_t base = 0; base < nb; base += GI_SCAN_BLOCK) {
+        uint32_t i = base + threadIdx.x;
+        uint32_t v = i < nb ? block_sums[i] : 0u;
+        sh[threadIdx.x] = v;
+        __syncthreads();
+        for (int off = 1; off < GI_SCAN_BLOCK; off <<= 1) {
+            uint32_t t = threadIdx.x >= off ? sh[threadIdx.x - off] : 0u;
+            __syncthreads();
+            sh[threadIdx.x] += t;
+            __syncthreads();
+        }
+        uint32_t c = carry;
+        if (i < nb) block_sums[i] = c + sh[threadIdx.x] - v;
+        __syncthreads();
+        if (threadIdx.x == GI_SCAN_BLOCK - 1) carry = c + sh[threadIdx.x];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0 && total) *total = carry;
 }
 __global__ void k_scan_apply(uint32_t* out, uint32_t n, const uint32_t* block_sums)
 {
@@ -276,39 +295,55 @@ __global__ void k_pm_payload(DPMap M, uint32_t n_kept)
     uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= n_kept) return;
     const double* src = M.ph + 9 * (size_t)M.pid[s];
-    for (int k = 0; k < 3; k++) M.pos[3 * (size_t)s + k] = src[k];
+    for (int k = 0; k < 3; k++) M.pos4[4 * (size_t)s + k] = src[k];
+    M.pos4[4 * (size_t)s + 3] = 0.0;
     for (int k = 0; k < 6; k++) M.dircol[6 * (size_t)s + k] = src[3 + k];
 }
 
 // ---- K7: gather — RayTracer::samplePhotons (raytracer.h:532-579) over PhotonMap::getInRange (photonMap.cpp:50-92,115-134) ----
 // The candidate set of a query is a function of the LEAF that contains it: every photon of every leaf whose closed box
 // touches (leaf box +- EPSILON).  So the map carries, per leaf, the precomputed candidate list (photon slots in the
-// reference's DFS order) — built once on the device by running Node::get for every leaf (k_pm_cand_*).  A query is then:
-// descend to the leaf (lanes 0..7 test the eight children in parallel), stream the leaf's candidate list 32 at a time,
-// and keep the k <= 32 nearest in a warp-wide sorted list (one entry per lane, ordered by (distance^2, photon id)).
+// reference's DFS order) — built once on the device by running Node::get for every leaf (k_pm_cands).  A query is then:
+//   1. locate the leaf (getBounds).  Batch kernel: one THREAD per query walks down with child boxes derived from the
+//      parent box (the map is built by that very formula), one 16-byte topology load per level.  Single-query form
+//      (tail kernel): lanes 0..7 test the eight children.
+//   2. the warp loads the leaf's candidates into registers (<= 8 per lane) and computes the squared distances;
+//   3. SELECT, not sort: the k-th smallest distance is bracketed by bisection on the value — each step is one compare
+//      per register + one REDUX — until exactly k candidates lie at or below the pivot.  That set is the reference's
+//      partial_sort prefix.  (Exact distance ties across the k-th place, or > 256 candidates, take the streaming
+//      sort/merge path below, which orders by (distance, slot).)
+//   4. the k selected are compacted to one per lane through shared memory, ordered by ONE 32-wide bitonic sort, and the
+//      estimate is summed in ascending-distance order like the reference does.
 struct DGatherMap {
-    const DNode* nodes; const double* pos; const double* dircol; const uint32_t* pid; uint32_t n_nodes;
+    const DNode* nodes; const double* pos4; const double* dircol; const uint32_t* pid; uint32_t n_nodes;
     const uint32_t* cand_off;    // [n_nodes + 1] start of each node's candidate list (only leaves have entries)
-    const uint32_t* cand_slot;   // photon slots, concatenated per leaf
+    const uint32_t* cand_slot;   // photon slots, concatenated per leaf, each list ordered by distance from the leaf centre
+    const float* cand_key;       // squared distance of each candidate from the centre of its leaf, rounded down (0 = list not ordered)
 };
+#define GI_GATHER_REGS 8   // candidates per lane held in registers by the select path (8 x 32 = 256 per query)
+#ifndef GI_GATHER_MINB
+#define GI_GATHER_MINB 6   // resident blocks (of 4 warps) per SM asked of ptxas for k_gather: 6 -> 80 registers, no spills
+#endif
 
 // ordering of candidates: (distance^2, photon slot).  Exact distance ties between different photons are unordered in
 // the reference (std::partial_sort is unstable); the slot makes them deterministic here.
 __device__ __forceinline__ bool kv_less(double a, uint32_t ai, double b, uint32_t bi) { return a < b || (a == b && ai < bi); }
 
-// bitonic compare-exchange across lanes on (key, slot) pairs
+// bitonic compare-exchange across lanes on (key, slot) pairs.  Squared distances are >= +0 (or +inf padding), so their
+// bit patterns order like unsigned integers: the three-word comparison (hi, lo, slot) needs no fp64 pipe.
 __device__ __forceinline__ void cmpx(double& d, uint32_t& sl, int lane, int j, bool up)
 {
-    double od = __shfl_xor_sync(0xffffffffu, d, j);
-    uint32_t osl = __shfl_xor_sync(0xffffffffu, sl, j);
-    bool lower = (lane & j) == 0;
-    bool mine_less = kv_less(d, sl, od, osl);
-    bool take = (lower == up) ? !mine_less : mine_less;
-    if (take && !(d == od && sl == osl)) { d = od; sl = osl; }
+    const uint32_t hi = (uint32_t)__double2hiint(d), lo = (uint32_t)__double2loint(d);
+    const uint32_t ohi = __shfl_xor_sync(0xffffffffu, hi, j), olo = __shfl_xor_sync(0xffffffffu, lo, j), osl = __shfl_xor_sync(0xffffffffu, sl, j);
+    const bool mine_less = hi < ohi || (hi == ohi && (lo < olo || (lo == olo && sl < osl)));
+    const bool keep_min = ((lane & j) == 0) == up;
+    if (mine_less != keep_min) { d = __hiloint2double((int)ohi, (int)olo); sl = osl; }
 }
 __device__ __forceinline__ void warp_sort32(double& d, uint32_t& sl, int lane)
 {
+#pragma unroll
     for (int k = 2; k <= 32; k <<= 1)
+#pragma unroll
         for (int j = k >> 1; j > 0; j >>= 1) cmpx(d, sl, lane, j, (lane & k) == 0 || k == 32);
 }
 // merge a sorted-ascending batch (bd) into the sorted-ascending best list (d): keep the 32 smallest of the 64
@@ -321,7 +356,14 @@ __device__ __forceinline__ void warp_merge32(double& d, uint32_t& sl, double bd,
     for (int j = 16; j > 0; j >>= 1) cmpx(d, sl, lane, j, true);
 }
 
-// getBounds (photonMap.cpp:115-134): the leaf whose half-open box contains p; false when p is in no child on the way down
+__device__ __forceinline__ double cand_dist2(const DGatherMap& M, uint32_t slot, d3 p)
+{
+    const double2* pp = reinterpret_cast<const double2*>(M.pos4 + 4 * (size_t)slot);
+    double2 a = __ldg(pp), b = __ldg(pp + 1);
+    return len2(mk3(a.x, a.y, b.x) - p);
+}
+
+// getBounds (photonMap.cpp:115-134), warp form: the leaf whose half-open box contains p; false when p is in no child
 __device__ __forceinline__ bool pm_find_leaf(const DGatherMap& M, d3 p, int lane, uint32_t& node, uint32_t& depth)
 {
     node = 0; depth = 0;
@@ -344,103 +386,521 @@ __device__ __forceinline__ bool pm_find_leaf(const DGatherMap& M, d3 p, int lane
     return true;
 }
 
+// getBounds, thread form: one query per thread.  The map's child boxes ARE the partition formula of the parent box
+// (k_pm_split writes child_box()), so the walk keeps the current box in registers and derives the child that contains p
+// with the same doubles: per axis the lower half is [min, mid), the upper half [min + h, mid + h) (min + h == mid bit for
+// bit), and child 7 is [mid, max).  Children are disjoint, so "first containing child in 0..7 order" is "the containing
+// child".  One 16-byte topology load per level.
+__device__ __forceinline__ bool pm_find_leaf_thread(const DGatherMap& M, d3 p, uint32_t& node, uint32_t& depth)
+{
+    node = 0; depth = 0;
+    if (M.n_nodes == 0) return false;
+    DNode root = load_node(M.nodes, 0);
+    double lo[3] = { root.bmin[0], root.bmin[1], root.bmin[2] }, hi[3] = { root.bmax[0], root.bmax[1], root.bmax[2] };
+    const double pp[3] = { p.x, p.y, p.z };
+    uint32_t child = root.child, mask = root.mask;
+    while (mask != 0) {
+        depth++;
+        double m[3], mh[3];
+        bool low[3], up[3], up7[3];
+#pragma unroll
+        for (int a = 0; a < 3; a++) {
+            double h = .5 * (hi[a] - lo[a]);
+            m[a] = lo[a] + .5 * (hi[a] - lo[a]);
+            mh[a] = m[a] + h;
+            low[a] = pp[a] >= lo[a] && pp[a] < m[a];
+            up[a] = pp[a] >= lo[a] + h && pp[a] < mh[a];
+            up7[a] = pp[a] >= m[a] && pp[a] < hi[a];
+        }
+        int c;
+        const bool all_up = up[0] && up[1] && up[2];
+        if ((low[0] || up[0]) && (low[1] || up[1]) && (low[2] || up[2]) && !all_up) c = (up[0] ? 1 : 0) | (up[2] ? 2 : 0) | (up[1] ? 4 : 0);   // bit0 = +x, bit1 = +z, bit2 = +y
+        else if (up7[0] && up7[1] && up7[2]) c = 7;
+        else return false;   // box(-inf,-inf): nothing overlaps (photonMap.cpp:132)
+#pragma unroll
+        for (int a = 0; a < 3; a++) {
+            const bool u = a == 0 ? (c & 1) : (a == 1 ? (c & 4) : (c & 2));
+            if (c == 7) lo[a] = m[a];
+            else if (u) { lo[a] = m[a]; hi[a] = mh[a]; }   // lo + h == mid
+            else hi[a] = m[a];
+        }
+        node = child + c;
+        uint4 top = __ldg(reinterpret_cast<const uint4*>(M.nodes + node) + 3);
+        child = top.x; mask = top.w;
+    }
+    return true;
+}
+
 struct GatherOut { d3 rgb; uint32_t total, depth; int count; uint32_t best_slot; };
 
-// one query, executed by a full warp; every lane returns the same rgb/total/depth; lane l holds the slot of the l-th
-// nearest.  `sm` = 96 doubles of shared memory per warp (the ordered sum of the estimate).
-__device__ __forceinline__ GatherOut gather_warp(const DGatherMap& M, d3 p, d3 dq, int k, int lane, double* sm)
+__device__ __forceinline__ void warp_order32(double& d, uint32_t& sl, int count, int lane);
+
+// streaming top-k (any candidate count, total order (distance, slot)): candidates 32 at a time; those that beat the current
+// 32nd entry are appended to a batch in shared memory (ballot + prefix popcount); a full batch is ordered and merged into the
+// warp-wide sorted list (one entry per lane).  `delta` >= 0: half diagonal of the query's leaf — the list is ordered by
+// distance from the leaf centre and the scan stops once no later candidate can beat the current 32nd (see k_gather_sorted);
+// delta < 0: scan everything.  `sm` = 48 doubles of shared memory of this warp.
+__device__ __noinline__ void gather_topk_stream(const DGatherMap& M, uint32_t off, uint32_t total, d3 p, int lane, double delta, double* sm, double& best_d, uint32_t& best_sl)
+{
+    float bound = CUDART_INF_F;
+    uint32_t* sms = reinterpret_cast<uint32_t*>(sm + 32);
+    best_d = CUDART_INF; best_sl = 0xFFFFFFFFu;
+    int nb = 0;   // entries in the pending batch
+    double kth_d = CUDART_INF; uint32_t kth_sl = 0xFFFFFFFFu;
+    const uint32_t lt = (1u << lane) - 1u;
+    __syncwarp();
+    for (uint32_t base = 0; base < total; base += 32) {
+        if (delta >= 0 && __ldg(M.cand_key + off + base) > bound) break;
+        const bool have = base + lane < total;
+        double cd = CUDART_INF; uint32_t csl = 0xFFFFFFFFu;
+        if (have) { csl = __ldg(M.cand_slot + off + base + lane); cd = cand_dist2(M, csl, p); }
+        const bool useful = have && kv_less(cd, csl, kth_d, kth_sl);
+        const uint32_t um = __ballot_sync(0xffffffffu, useful);
+        if (!um) continue;
+        const int pos = nb + __popc(um & lt), cnt = __popc(um);
+        if (useful && pos < 32) { sm[pos] = cd; sms[pos] = csl; }
+        if (nb + cnt >= 32) {
+            __syncwarp();
+            double bd = sm[lane]; uint32_t bs = sms[lane];
+            __syncwarp();
+            warp_order32(bd, bs, 32, lane);
+            warp_merge32(best_d, best_sl, bd, bs, lane);
+            kth_d = __shfl_sync(0xffffffffu, best_d, 31); kth_sl = __shfl_sync(0xffffffffu, best_sl, 31);
+            if (delta >= 0 && kth_d < CUDART_INF) { const double b = sqrt(kth_d) + delta; bound = __double2float_ru(b * b * (1.0 + 1e-9)); }
+            if (useful && pos >= 32) { sm[pos - 32] = cd; sms[pos - 32] = csl; }   // the overflow opens the next batch
+            nb = nb + cnt - 32;
+        } else nb += cnt;
+    }
+    if (nb > 0) {
+        __syncwarp();
+        double bd = lane < nb ? sm[lane] : CUDART_INF; uint32_t bs = lane < nb ? sms[lane] : 0xFFFFFFFFu;
+        __syncwarp();
+        warp_order32(bd, bs, nb, lane);
+        warp_merge32(best_d, best_sl, bd, bs, lane);
+    }
+}
+
+// ---- select: a pivot with exactly k of the register-held candidates at or below it ------------------------------------------
+// Pivots come from interpolating the counts at the bracket ends (photon density is close to uniform in d^2 on a surface);
+// every third step is a plain bisection so that the bracket always shrinks; the first pivot is the previous query's
+// threshold when that query sat in the same leaf (neighbouring pixels: nearly the same k-th distance).  NB = registers in
+// use (unused ones hold +inf): one DSETP + one add per register and one REDUX per step, no branches.
+template <int NB>
+__device__ __forceinline__ bool select_pivot(const double (&cd)[GI_GATHER_REGS], int k, uint32_t total, double lo, double hi, double first, double& thr)
+{
+    int clo = 0, chi = (int)total;
+    double pivot = first;
+    for (int it = 0; it < 96; it++) {
+        const double mid = lo + .5 * (hi - lo);
+        const bool inside = (pivot > lo) & (pivot < hi);
+        pivot = inside ? pivot : mid;
+        if (!((pivot > lo) & (pivot < hi))) return false;   // no double left between the bounds: a tie straddles the k-th place
+        int c = 0;
+#pragma unroll
+        for (int j = 0; j < NB; j++) c += cd[j] <= pivot ? 1 : 0;
+        c = __reduce_add_sync(0xffffffffu, c);
+        if (c == k) { thr = pivot; return true; }
+        const bool below = c < k;
+        lo = below ? pivot : lo; clo = below ? c : clo;
+        hi = below ? hi : pivot; chi = below ? chi : c;
+        const double ip = lo + (hi - lo) * (double)__fdividef((float)(k - clo) + .5f, (float)(chi - clo));
+        pivot = (it % 3 == 2) ? hi : ip;   // `hi` is not inside the bracket: the next step bisects
+    }
+    return false;
+}
+
+// ---- order: sort <= 32 (distance, slot) pairs held one per lane (lanes >= count hold +inf) -------------------------------------------
+// The bitonic network runs on ONE 32-bit word per lane: the distance bits, rebased to the smallest binade present and
+// shifted down to 26 bits (monotone in the distance), with the lane number in the low 5 bits — SHFL + min/max per stage.
+// The pairs are then fetched from their source lanes.  Two distances that fall into the same 26-bit cell come out in lane
+// order instead of (distance, slot) order; a neighbour check detects that (an unsorted run always has an inverted adjacent
+// pair) and the exact three-word network below redoes the sort.
+__device__ __forceinline__ void warp_order32(double& d, uint32_t& sl, int count, int lane)
+{
+    const bool valid = lane < count;
+    const uint32_t hw = (uint32_t)__double2hiint(d);
+    const uint32_t hmn = __reduce_min_sync(0xffffffffu, valid ? hw : 0xFFFFFFFFu), hmx = __reduce_max_sync(0xffffffffu, valid ? hw : 0u);
+    const unsigned long long kbase = (unsigned long long)hmn << 32, range = ((unsigned long long)(hmx - hmn) + 1ull) << 32;
+    int sh = 38 - __clzll((long long)range); sh = sh < 0 ? 0 : sh;   // (range >> sh) < 2^26
+    uint32_t key = valid ? ((uint32_t)(((unsigned long long)__double_as_longlong(d) - kbase) >> sh) << 5) | (uint32_t)lane : 0xFFFFFFFFu;
+#pragma unroll
+    for (int k2 = 2; k2 <= 32; k2 <<= 1)
+#pragma unroll
+        for (int j = k2 >> 1; j > 0; j >>= 1) {
+            const uint32_t o = __shfl_xor_sync(0xffffffffu, key, j);
+            const bool keep_min = ((lane & j) == 0) == ((lane & k2) == 0 || k2 == 32);
+            key = keep_min ? min(key, o) : max(key, o);
+        }
+    const int src = (int)(key & 31u);
+    double sd = __shfl_sync(0xffffffffu, d, src); uint32_t ssl = __shfl_sync(0xffffffffu, sl, src);
+    if (!valid) { sd = CUDART_INF; ssl = 0xFFFFFFFFu; }
+    const double nd = __shfl_down_sync(0xffffffffu, sd, 1); const uint32_t nsl = __shfl_down_sync(0xffffffffu, ssl, 1);
+    const bool inverted = (lane + 1 < count) & !kv_less(sd, ssl, nd, nsl);
+    d = sd; sl = ssl;
+    if (__any_sync(0xffffffffu, inverted)) warp_sort32(d, sl, lane);
+}
+
+// One query at a known leaf, executed by a full warp; every lane returns the same rgb/total; lane l holds the slot of
+// the l-th nearest.  `sm` = 96 doubles of shared memory per warp (compaction scratch, then the ordered sum).  `csl` /
+// `csl_node` / `thr_cache` carry the candidate slots and the threshold of the previous query of this warp (consecutive
+// queries often share a leaf).
+__device__ __forceinline__ GatherOut gather_at_leaf(const DGatherMap& M, bool found, uint32_t node, d3 p, d3 dq, int k, int lane, double* sm,
+                                                    uint32_t (&csl)[GI_GATHER_REGS], uint32_t& csl_node, double& thr_cache, double delta = -1.0)
 {
     GatherOut out; out.rgb = mk3(0, 0, 0); out.total = 0; out.depth = 0; out.count = 0; out.best_slot = 0xFFFFFFFFu;
-    uint32_t node, depth;
-    bool found = pm_find_leaf(M, p, lane, node, depth);
-    out.depth = depth;
     double best_d = CUDART_INF; uint32_t best_sl = 0xFFFFFFFFu;   // sorted ascending across lanes
     uint32_t total = 0;
     if (found) {
         const uint32_t off = __ldg(M.cand_off + node);
         total = __ldg(M.cand_off + node + 1) - off;
-        double bat_d = CUDART_INF; uint32_t bat_sl = 0xFFFFFFFFu;   // pending batch, filled from lane 0 up
-        int nb = 0;
-        double kth_d = CUDART_INF; uint32_t kth_sl = 0xFFFFFFFFu;
-        for (uint32_t base = 0; base < total; base += 32) {
-            bool have = base + lane < total;
-            double cd = CUDART_INF; uint32_t csl = 0xFFFFFFFFu;
-            if (have) {
-                csl = __ldg(M.cand_slot + off + base + lane);
-                const double* pp = M.pos + 3 * (size_t)csl;
-                cd = len2(mk3(__ldg(pp), __ldg(pp + 1), __ldg(pp + 2)) - p);
+    }
+    const int count = (int)total < k ? (int)total : k;
+    if (total > 32u * GI_GATHER_REGS) gather_topk_stream(M, __ldg(M.cand_off + node), total, p, lane, delta, sm, best_d, best_sl);
+    else if (total > 0) {
+        const int nb = (int)((total + 31u) >> 5);
+        double cd[GI_GATHER_REGS];
+        const bool warm = csl_node == node;
+        if (!warm) {
+            const uint32_t off = __ldg(M.cand_off + node);
+#pragma unroll
+            for (int j = 0; j < GI_GATHER_REGS; j++) csl[j] = (j < nb && (uint32_t)(j * 32 + lane) < total) ? __ldg(M.cand_slot + off + j * 32 + lane) : 0xFFFFFFFFu;
+            csl_node = node;
+        }
+#pragma unroll
+        for (int j = 0; j < GI_GATHER_REGS; j++) cd[j] = (j < nb && csl[j] != 0xFFFFFFFFu) ? cand_dist2(M, csl[j], p) : CUDART_INF;
+        bool sorted = false;
+        if (total <= (uint32_t)k) { best_d = cd[0]; best_sl = csl[0]; }   // k <= 32: everything is selected
+        else {
+            // bracket the k-th smallest distance between the binades of the smallest and the largest lane minimum: every
+            // lane that holds candidates has one at or below the upper bound, so >= min(32, total) >= k lie below it
+            double mn = cd[0];
+#pragma unroll
+            for (int j = 1; j < GI_GATHER_REGS; j++) mn = cd[j] < mn ? cd[j] : mn;
+            const unsigned hw = (unsigned)__double2hiint(mn);
+            const bool fin = hw < 0x7FF00000u;
+            const unsigned hmax = __reduce_max_sync(0xffffffffu, fin ? hw : 0u), hmin = __reduce_min_sync(0xffffffffu, fin ? hw : 0x7FF00000u);
+            const double hi = __hiloint2double((int)(hmax + 1u), 0), lo = __hiloint2double((int)hmin, 0);
+            const double first = (warm && thr_cache > lo && thr_cache < hi) ? thr_cache : lo + (hi - lo) * (double)fminf(0.9f, __fdividef(1.7f * ((float)k + .5f), (float)total));
+            double thr = 0; bool ok;
+            switch (nb) {
+            case 1: ok = select_pivot<1>(cd, k, total, lo, hi, first, thr); break;
+            case 2: ok = select_pivot<2>(cd, k, total, lo, hi, first, thr); break;
+            case 3: ok = select_pivot<3>(cd, k, total, lo, hi, first, thr); break;
+            case 4: ok = select_pivot<4>(cd, k, total, lo, hi, first, thr); break;
+            case 5: ok = select_pivot<5>(cd, k, total, lo, hi, first, thr); break;
+            case 6: ok = select_pivot<6>(cd, k, total, lo, hi, first, thr); break;
+            default: ok = select_pivot<8>(cd, k, total, lo, hi, first, thr); break;
             }
-            // only candidates that beat the current k-th entry can enter the result
-            bool useful = have && kv_less(cd, csl, kth_d, kth_sl);
-            uint32_t um = __ballot_sync(0xffffffffu, useful);
-            int cnt = __popc(um);
-            int taken = 0;
-            while (taken < cnt) {
-                int room = 32 - nb, put = cnt - taken < room ? cnt - taken : room;
-                // lane j in [nb, nb+put) pulls the (taken + j - nb)-th useful candidate
-                int want = lane - nb;
-                int src = (want >= 0 && want < put) ? (int)__fns(um, 0, taken + want + 1) : lane;
-                double sd = __shfl_sync(0xffffffffu, cd, src); uint32_t ssl = __shfl_sync(0xffffffffu, csl, src);
-                if (want >= 0 && want < put) { bat_d = sd; bat_sl = ssl; }
-                nb += put; taken += put;
-                if (nb == 32) {
-                    warp_sort32(bat_d, bat_sl, lane);
-                    warp_merge32(best_d, best_sl, bat_d, bat_sl, lane);
-                    kth_d = __shfl_sync(0xffffffffu, best_d, 31); kth_sl = __shfl_sync(0xffffffffu, best_sl, 31);
-                    bat_d = CUDART_INF; bat_sl = 0xFFFFFFFFu; nb = 0;
+            if (!ok) { gather_topk_stream(M, __ldg(M.cand_off + node), total, p, lane, delta, sm, best_d, best_sl); sorted = true; }
+            else {
+                thr_cache = thr;
+                // compact the k selected to one per lane (their order is restored by warp_order32)
+                uint32_t* sms = reinterpret_cast<uint32_t*>(sm + 32);
+                int base = 0;
+                __syncwarp();
+#pragma unroll
+                for (int j = 0; j < GI_GATHER_REGS; j++) {
+                    if (j < nb) {
+                        const bool sel = cd[j] <= thr;
+                        const uint32_t m = __ballot_sync(0xffffffffu, sel);
+                        if (sel) { int pos = base + __popc(m & ((1u << lane) - 1u)); sm[pos] = cd[j]; sms[pos] = csl[j]; }
+                        base += __popc(m);
+                    }
                 }
+                __syncwarp();
+                if (lane < k) { best_d = sm[lane]; best_sl = sms[lane]; }
+                __syncwarp();
             }
         }
-        if (nb > 0) {
-            warp_sort32(bat_d, bat_sl, lane);
-            warp_merge32(best_d, best_sl, bat_d, bat_sl, lane);
-        }
+        if (!sorted) warp_order32(best_d, best_sl, count, lane);
     }
     // radiance estimate (raytracer.h:545-576): sum over the count = min(k, total) nearest in ascending distance order;
     // lanes 0..2 each add up one colour channel in that order
-    int count = (int)total < k ? (int)total : k;
-    d3 term = mk3(0, 0, 0);
-    if (lane < count && best_sl != 0xFFFFFFFFu) {
-        const double* dc = M.dircol + 6 * (size_t)best_sl;
-        term = ld3(dc + 3) * dot3(ld3(dc), dq);
-    }
-    __syncwarp();
-    sm[lane] = term.x; sm[32 + lane] = term.y; sm[64 + lane] = term.z;
-    __syncwarp();
     double acc = 0;
-    if (lane < 3) for (int i = 0; i < count; i++) acc += sm[32 * lane + i];
-    d3 res = mk3(__shfl_sync(0xffffffffu, acc, 0), __shfl_sync(0xffffffffu, acc, 1), __shfl_sync(0xffffffffu, acc, 2));
     if (total > 0) {
-        double md = __shfl_sync(0xffffffffu, best_d, count - 1);
-        double den = GI_D_PI * md;
-        res = mk3(res.x / den, res.y / den, res.z / den);
+        d3 term = mk3(0, 0, 0);
+        if (lane < count && best_sl != 0xFFFFFFFFu) {
+            const double2* dc = reinterpret_cast<const double2*>(M.dircol + 6 * (size_t)best_sl);
+            double2 a = __ldg(dc), b = __ldg(dc + 1), c = __ldg(dc + 2);
+            term = mk3(b.y, c.x, c.y) * dot3(mk3(a.x, a.y, b.x), dq);
+        }
+        __syncwarp();
+        sm[lane] = term.x; sm[32 + lane] = term.y; sm[64 + lane] = term.z;
+        __syncwarp();
+        // terms past `count` are +0.0 and leave the sum unchanged, so the loop is a fixed 32 steps of 16-byte loads; the
+        // division by pi*r^2 (raytracer.h:572-576) is done once, by the lane that owns the channel
+        const double2* s2 = reinterpret_cast<const double2*>(sm + 32 * (lane < 3 ? lane : 0));
+#pragma unroll
+        for (int i = 0; i < 16; i++) { double2 v = s2[i]; acc += v.x; acc += v.y; }
+        const double md = __shfl_sync(0xffffffffu, best_d, count - 1);
+        acc = acc / (GI_D_PI * md);
     }
-    out.rgb = res; out.total = total; out.count = count; out.best_slot = best_sl;
+    out.rgb = mk3(__shfl_sync(0xffffffffu, acc, 0), __shfl_sync(0xffffffffu, acc, 1), __shfl_sync(0xffffffffu, acc, 2));
+    out.total = total; out.count = count; out.best_slot = best_sl;
     return out;
 }
 
-template <int WARPS>
-__global__ void __launch_bounds__(WARPS * 32) k_gather(DGatherMap M, size_t n, const double* __restrict__ qpos, const double* __restrict__ qdir, int k,
-                                                     double* __restrict__ rgb, uint32_t* __restrict__ knn, uint32_t* __restrict__ ncand,
-                                                     const double* __restrict__ weight, double* __restrict__ accum, const uint32_t* __restrict__ accum_idx,
-                                                     unsigned long long* work)
+// one query per warp, leaf located by the warp (tail kernel)
+__device__ __forceinline__ GatherOut gather_warp(const DGatherMap& M, d3 p, d3 dq, int k, int lane, double* sm)
 {
-    __shared__ double s_sum[WARPS][96];
+    uint32_t node, depth;
+    bool found = pm_find_leaf(M, p, lane, node, depth);
+    uint32_t csl[GI_GATHER_REGS]; uint32_t csl_node = 0xFFFFFFFFu; double thr_cache = 0;
+    GatherOut g = gather_at_leaf(M, found, node, p, dq, k, lane, sm, csl, csl_node, thr_cache);
+    g.depth = depth;
+    return g;
+}
+
+// `qpw` (a power of two <= 32) consecutive queries per warp: lane l < qpw locates the leaf of query l with the thread-form
+// walk, then the warp serves the queries one after the other.  The host picks qpw = 32 for long queues (walk cost amortised
+// 32x, neighbouring queries reuse the candidate slots and the threshold) and smaller values for short queues, where
+// parallelism matters more.
+template <int WARPS>
+__global__ void __launch_bounds__(WARPS * 32, GI_GATHER_MINB) k_gather(DGatherMap M, size_t n, int qpw, const double* __restrict__ qpos, const double* __restrict__ qdir, int k,
+                                                                    double* __restrict__ rgb, uint32_t* __restrict__ knn, uint32_t* __restrict__ ncand,
+                                                                    const double* __restrict__ weight, double* __restrict__ accum, const uint32_t* __restrict__ accum_idx,
+                                                                    unsigned long long* work)
+{
+    __shared__ __align__(16) double s_sum[WARPS][96];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-    size_t q = blockIdx.x * (size_t)WARPS + wib;
-    if (q >= n) return;
-    d3 p = ld3(qpos + 3 * q), dq = ld3(qdir + 3 * q);
-    GatherOut g = gather_warp(M, p, dq, k, lane, s_sum[wib]);
-    if (knn && lane < k) knn[q * (size_t)k + lane] = (lane < g.count && g.best_slot != 0xFFFFFFFFu) ? __ldg(M.pid + g.best_slot) : GI_NO_HIT;
-    if (lane == 0) {
-        if (work) { atomicAdd(work, (unsigned long long)g.depth); atomicAdd(work + 1, (unsigned long long)g.total); atomicAdd(work + 2, (unsigned long long)g.count); }
-        if (rgb) st3(rgb + 3 * q, g.rgb);
-        if (ncand) ncand[q] = g.total;
-        if (accum) {   // render pipeline: L[path] += weight * caustic
-            size_t a = accum_idx[q];
-            accum[3 * a] += weight[3 * q] * g.rgb.x; accum[3 * a + 1] += weight[3 * q + 1] * g.rgb.y; accum[3 * a + 2] += weight[3 * q + 2] * g.rgb.z;
+    const size_t q0 = (blockIdx.x * (size_t)WARPS + wib) * (size_t)qpw;
+    if (q0 >= n) return;
+    const size_t q = q0 + lane;
+    const bool have = lane < qpw && q < n;
+    uint32_t node = 0, depth = 0;
+    bool found = false;
+    if (have) found = pm_find_leaf_thread(M, ld3(qpos + 3 * q), node, depth);
+    const uint32_t found_mask = __ballot_sync(0xffffffffu, found);
+    const int nq = (int)(n - q0 < (size_t)qpw ? n - q0 : (size_t)qpw);
+    uint32_t w_total = 0, w_count = 0;   // warp-uniform tallies
+    uint32_t csl[GI_GATHER_REGS]; uint32_t csl_node = 0xFFFFFFFFu; double thr_cache = 0;
+    for (int i = 0; i < nq; i++) {
+        const size_t qi = q0 + i;
+        const d3 pi = ld3(qpos + 3 * qi), di = ld3(qdir + 3 * qi);   // warp-uniform (broadcast) loads, L1 hits after the walk
+        const uint32_t ni = __shfl_sync(0xffffffffu, node, i);
+        GatherOut g = gather_at_leaf(M, (found_mask >> i) & 1u, ni, pi, di, k, lane, s_sum[wib], csl, csl_node, thr_cache);
+        w_total += g.total; w_count += (uint32_t)g.count;
+        if (knn && lane < k) knn[qi * (size_t)k + lane] = (lane < g.count && g.best_slot != 0xFFFFFFFFu) ? __ldg(M.pid + g.best_slot) : GI_NO_HIT;
+        if (lane == 0) {
+            if (rgb) st3(rgb + 3 * qi, g.rgb);
+            if (ncand) ncand[qi] = g.total;
+            if (accum) {   // render pipeline: L[path] += weight * caustic
+                const size_t a = accum_idx[qi];
+                accum[3 * a] += weight[3 * qi] * g.rgb.x; accum[3 * a + 1] += weight[3 * qi + 1] * g.rgb.y; accum[3 * a + 2] += weight[3 * qi + 2] * g.rgb.z;
+            }
         }
     }
+    if (work) {
+        unsigned long long wd = have ? depth : 0;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) wd += __shfl_down_sync(0xffffffffu, wd, o);
+        if (lane == 0) { atomicAdd(work, wd); atomicAdd(work + 1, (unsigned long long)w_total); atomicAdd(work + 2, (unsigned long long)w_count); }
+    }
+}
+
+// ---- K7, sorted form: queries ordered by leaf, one THREAD per query ------------------------------------------------------------
+// The warp-cooperative form above spends its time waiting: every step of a query (shuffle network, REDUX, ordered sum) hangs
+// on the one before it, and a warp carries a single such chain (ncu: issue slots 35-55 % busy, stalls spread evenly over the
+// whole instruction stream).  Queries are independent, so the wavefront form turns the problem around:
+//   k_gather_locate   one thread per query walks to its leaf (thread form of getBounds) and counts the leaf in a histogram;
+//   scan + k_bin_scatter order the queries by leaf (counting sort, permutation only);
+//   k_gather_sorted   one thread per query, in leaf order.  The 32 lanes of a warp now sit in the same leaf (or two): they
+//                     run through the SAME candidate list in lockstep — the slot and position loads are warp-wide broadcasts
+//                     served by L1 — each against its own query point, with 32 independent dependency chains per warp.
+//                     SELECT is the same interpolation/bisection on "how many candidates lie at or below the pivot", one
+//                     pass over the list per step, all state in registers; the k selected are then insertion-sorted by
+//                     (distance, slot) into a per-thread column of shared memory ([k][thread]: conflict-free for any mix of
+//                     row indices) and summed in ascending order like the reference.  Exact distance ties across the k-th
+//                     place cannot be resolved by a pivot: those queries are handed to gather_at_leaf, one at a time.
+__global__ void k_gather_locate(DGatherMap M, uint32_t n, const double* __restrict__ qpos, uint32_t* __restrict__ qnode, uint32_t* __restrict__ hist, unsigned long long* work)
+{
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    uint32_t depth = 0;
+    if (i < n) {
+        uint32_t node;
+        bool found = pm_find_leaf_thread(M, ld3(qpos + 3 * (size_t)i), node, depth);
+        uint32_t key = found ? node : M.n_nodes;   // queries outside every leaf go last
+        qnode[i] = key;
+        if (hist) atomicAdd(hist + key, 1u);
+    }
+    if (work) {
+        unsigned long long wd = depth;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) wd += __shfl_down_sync(0xffffffffu, wd, o);
+        if ((threadIdx.x & 31) == 0 && wd) atomicAdd(work, wd);
+    }
+}
+
+#define GI_GS_MAX_CANDS 256u   // longer candidate lists are streamed by the whole warp
+#define GI_GS_BLOCK 64   // 64 columns x 32 rows x 12 B = 24 KB of shared memory per block
+
+// Each leaf's candidate list is stored in ascending distance from the CENTRE of the leaf box (k_pm_cand_order), with that
+// squared distance (rounded down) beside it.  A query point q lies inside the leaf box, so for a candidate c
+//     |q - c| >= |centre - c| - delta,     delta = half diagonal of the leaf box  >= |q - centre|.
+// The thread keeps the k nearest so far as a sorted column of shared memory ([rank][thread]: conflict-free for any mix of
+// ranks); tau = the k-th distance.  Once |centre - c| - delta > sqrt(tau) no later candidate of the (ordered) list can enter,
+// and the scan stops — typically after k plus a thin shell of candidates, also in the lists of thousands that a large leaf
+// next to a dense region carries.  Candidates arrive almost in order, so the insertion shifts are short.  Order and ties are
+// exactly (distance^2, slot); the bound is inflated by 1e-9 relative against rounding.
+__global__ void __launch_bounds__(GI_GS_BLOCK) k_gather_sorted(DGatherMap M, uint32_t n, const uint32_t* __restrict__ perm, const uint32_t* __restrict__ qnode,
+                                                                 const double* __restrict__ qpos, const double* __restrict__ qdir, int k, double* __restrict__ rgb,
+                                                                 uint32_t* __restrict__ knn, uint32_t* __restrict__ ncand, const double* __restrict__ weight,
+                                                                 double* __restrict__ accum, const uint32_t* __restrict__ accum_idx, unsigned long long* work,
+                                                                 uint32_t* __restrict__ heavy, uint32_t* __restrict__ heavy_n)
+{
+    __shared__ double s_d[32][GI_GS_BLOCK];     // per-thread sorted list: row = rank, column = thread
+    __shared__ uint32_t s_sl[32][GI_GS_BLOCK];
+    const int t = threadIdx.x, lane = t & 31;
+    const uint32_t i = blockIdx.x * GI_GS_BLOCK + t;
+    const bool have = i < n;
+    uint32_t q = 0, total = 0, off = 0, node = 0xFFFFFFFFu;
+    d3 p = mk3(0, 0, 0), dq = mk3(0, 0, 0);
+    double delta = 0;
+    if (have) {
+        q = perm ? perm[i] : i;
+        node = qnode[q];
+        p = ld3(qpos + 3 * (size_t)q); dq = ld3(qdir + 3 * (size_t)q);
+        if (node < M.n_nodes) {
+            off = __ldg(M.cand_off + node); total = __ldg(M.cand_off + node + 1) - off;
+            const DNode nd = load_node(M.nodes, node);
+            const double ex = nd.bmax[0] - nd.bmin[0], ey = nd.bmax[1] - nd.bmin[1], ez = nd.bmax[2] - nd.bmin[2];
+            delta = .5 * sqrt(ex * ex + ey * ey + ez * ez) * (1.0 + 1e-9);
+        }
+    }
+    const int count = (int)total < k ? (int)total : k;
+    int m = 0;                       // rows in use
+    double tau = CUDART_INF;         // k-th distance^2 once m == k
+    float bound = CUDART_INF_F;      // scan stops at the first key above it
+    // long lists (a large leaf next to a dense region touches thousands of small ones) are streamed by the whole warp, 32
+    // candidates per step, instead of by one thread
+    const bool hard = total > GI_GS_MAX_CANDS;
+    for (uint32_t j = 0; j < (hard ? 0u : total); j++) {
+        if (__ldg(M.cand_key + off + j) > bound) break;
+        const uint32_t sl = __ldg(M.cand_slot + off + j);
+        const double d = cand_dist2(M, sl, p);
+        if (m == k && !kv_less(d, sl, tau, s_sl[k - 1][t])) continue;
+        int r = m < k ? m : k - 1;   // the last row is dropped when the list is full
+        while (r > 0) {
+            const double pd = s_d[r - 1][t]; const uint32_t ps = s_sl[r - 1][t];
+            if (!kv_less(d, sl, pd, ps)) break;
+            s_d[r][t] = pd; s_sl[r][t] = ps; r--;
+        }
+        s_d[r][t] = d; s_sl[r][t] = sl;
+        if (m < k) m++;
+        if (m == k) {
+            tau = s_d[k - 1][t];
+            const double b = sqrt(tau) + delta;
+            bound = __double2float_ru(b * b * (1.0 + 1e-9));
+        }
+    }
+    d3 res = mk3(0, 0, 0);
+    if (total > 0 && !hard) {
+        // radiance estimate (raytracer.h:545-576), ascending distance
+        for (int r = 0; r < count; r++) {
+            const double2* dc = reinterpret_cast<const double2*>(M.dircol + 6 * (size_t)s_sl[r][t]);
+            double2 a = __ldg(dc), b = __ldg(dc + 1), c = __ldg(dc + 2);
+            res = res + mk3(b.y, c.x, c.y) * dot3(mk3(a.x, a.y, b.x), dq);
+        }
+        const double den = GI_D_PI * s_d[count - 1][t];
+        res = mk3(res.x / den, res.y / den, res.z / den);
+    }
+    if (have && knn && !hard) for (int r = 0; r < k; r++) knn[(size_t)q * k + r] = r < count ? __ldg(M.pid + s_sl[r][t]) : GI_NO_HIT;
+    // long lists: queue the query for k_gather_heavy (one warp per query, taken from a shared counter — in leaf order these
+    // queries sit next to each other, and 32 of them in one warp would be a serial chain of milliseconds)
+    {
+        const uint32_t hm = __ballot_sync(0xffffffffu, hard);
+        if (hm) {
+            uint32_t base = 0;
+            if (lane == 0) base = atomicAdd(heavy_n, (uint32_t)__popc(hm));
+            base = __shfl_sync(0xffffffffu, base, 0);
+            if (hard) heavy[base + __popc(hm & ((1u << lane) - 1u))] = q;
+        }
+    }
+    if (have && !hard) {
+        if (rgb) st3(rgb + 3 * (size_t)q, res);
+        if (ncand) ncand[q] = total;
+        if (accum) {   // render pipeline: L[path] += weight * caustic
+            const size_t a = accum_idx[q];
+            accum[3 * a] += weight[3 * (size_t)q] * res.x; accum[3 * a + 1] += weight[3 * (size_t)q + 1] * res.y; accum[3 * a + 2] += weight[3 * (size_t)q + 2] * res.z;
+        }
+    }
+    if (work) {
+        unsigned long long wt = total, wc = (unsigned long long)count;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) { wt += __shfl_down_sync(0xffffffffu, wt, o); wc += __shfl_down_sync(0xffffffffu, wc, o); }
+        if (lane == 0) { if (wt) atomicAdd(work + 1, wt); if (wc) atomicAdd(work + 2, wc); }
+    }
+}
+
+// the long candidate lists: persistent warps take one queued query at a time and stream its list 32 candidates per step
+// (gather_at_leaf -> gather_topk_stream, with the ordered-list early stop)
+__global__ void __launch_bounds__(GI_WPB * 32) k_gather_heavy(DGatherMap M, const uint32_t* __restrict__ heavy, const uint32_t* __restrict__ heavy_n, uint32_t* __restrict__ next,
+                                                             const uint32_t* __restrict__ qnode, const double* __restrict__ qpos, const double* __restrict__ qdir, int k,
+                                                             double* __restrict__ rgb, uint32_t* __restrict__ knn, uint32_t* __restrict__ ncand, const double* __restrict__ weight,
+                                                             double* __restrict__ accum, const uint32_t* __restrict__ accum_idx)
+{
+    __shared__ __align__(16) double s_sum[GI_WPB][96];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const uint32_t nh = *heavy_n;
+    for (;;) {
+        uint32_t i = 0;
+        if (lane == 0) i = atomicAdd(next, 1u);
+        i = __shfl_sync(0xffffffffu, i, 0);
+        if (i >= nh) return;
+        const uint32_t q = heavy[i], node = qnode[q];
+        const d3 p = ld3(qpos + 3 * (size_t)q), dq = ld3(qdir + 3 * (size_t)q);
+        const DNode nd = load_node(M.nodes, node);
+        const double ex = nd.bmax[0] - nd.bmin[0], ey = nd.bmax[1] - nd.bmin[1], ez = nd.bmax[2] - nd.bmin[2];
+        const double delta = .5 * sqrt(ex * ex + ey * ey + ez * ez) * (1.0 + 1e-9);
+        uint32_t csl[GI_GATHER_REGS]; uint32_t csl_node = 0xFFFFFFFFu; double thr_cache = 0;
+        GatherOut g = gather_at_leaf(M, true, node, p, dq, k, lane, s_sum[wib], csl, csl_node, thr_cache, delta);
+        if (knn && lane < k) knn[(size_t)q * k + lane] = (lane < g.count && g.best_slot != 0xFFFFFFFFu) ? __ldg(M.pid + g.best_slot) : GI_NO_HIT;
+        if (lane == 0) {
+            if (rgb) st3(rgb + 3 * (size_t)q, g.rgb);
+            if (ncand) ncand[q] = g.total;
+            if (accum) {
+                const size_t a = accum_idx[q];
+                accum[3 * a] += weight[3 * (size_t)q] * g.rgb.x; accum[3 * a + 1] += weight[3 * (size_t)q + 1] * g.rgb.y; accum[3 * a + 2] += weight[3 * (size_t)q + 2] * g.rgb.z;
+            }
+        }
+    }
+}
+
+// order every leaf's candidate list by distance from the centre of the leaf box and write the keys (see k_gather_sorted).
+// One block per leaf; lists of LO < length <= HI entries are sorted by a bitonic network in shared memory ((distance^2,
+// slot) pairs, padded to a power of two); longer lists keep the DFS order with key 0, which never stops a scan.
+__global__ void k_pm_cand_order(const DNode* __restrict__ nodes, uint32_t n_nodes, const double* __restrict__ pos4, const uint32_t* __restrict__ cand_off, uint32_t* __restrict__ cand_slot,
+                                float* __restrict__ cand_key, uint32_t lo_len, uint32_t hi_len, uint32_t max_sortable)
+{
+    extern __shared__ __align__(16) unsigned char s_raw[];
+    const uint32_t leaf = blockIdx.x;
+    if (leaf >= n_nodes) return;
+    const uint32_t off = cand_off[leaf], total = cand_off[leaf + 1] - off;
+    if (total <= lo_len || total > hi_len) return;
+    if (total > max_sortable) { for (uint32_t j = threadIdx.x; j < total; j += blockDim.x) cand_key[off + j] = 0.f; return; }
+    uint32_t np2 = 1; while (np2 < total) np2 <<= 1;
+    double* kd = reinterpret_cast<double*>(s_raw);
+    uint32_t* ks = reinterpret_cast<uint32_t*>(s_raw + (size_t)np2 * 8);
+    const DNode nd = load_node(nodes, leaf);
+    const d3 c = mk3(nd.bmin[0] + .5 * (nd.bmax[0] - nd.bmin[0]), nd.bmin[1] + .5 * (nd.bmax[1] - nd.bmin[1]), nd.bmin[2] + .5 * (nd.bmax[2] - nd.bmin[2]));
+    for (uint32_t j = threadIdx.x; j < np2; j += blockDim.x) {
+        if (j < total) { const uint32_t sl = cand_slot[off + j]; const double* pp = pos4 + 4 * (size_t)sl; kd[j] = len2(mk3(pp[0], pp[1], pp[2]) - c); ks[j] = sl; }
+        else { kd[j] = CUDART_INF; ks[j] = 0xFFFFFFFFu; }
+    }
+    __syncthreads();
+    for (uint32_t k2 = 2; k2 <= np2; k2 <<= 1)
+        for (uint32_t j = k2 >> 1; j > 0; j >>= 1) {
+            for (uint32_t x = threadIdx.x; x < np2; x += blockDim.x) {
+                const uint32_t y = x ^ j;
+                if (y > x) {
+                    const bool up = (x & k2) == 0;
+                    const double a = kd[x], b = kd[y]; const uint32_t sa = ks[x], sb = ks[y];
+                    if (kv_less(b, sb, a, sa) == up) { kd[x] = b; kd[y] = a; ks[x] = sb; ks[y] = sa; }
+                }
+            }
+            __syncthreads();
+        }
+    for (uint32_t j = threadIdx.x; j < total; j += blockDim.x) { cand_slot[off + j] = ks[j]; cand_key[off + j] = __double2float_rd(kd[j]); }
 }
 
 // ---- candidate lists: Node::get (photonMap.cpp:71-92) run once per leaf with that leaf's query box -------------------------
@@ -490,6 +950,41 @@ __global__ void __launch_bounds__(WARPS * 32) k_pm_cands(const DNode* __restrict
     if (!FILL && lane == 0) cnt[leaf] = total;
 }
 
+// ---- ray binning: restore coherence after a scattering bounce ---------------------------------------------------------------------
+// Rays leave a diffuse bounce in random directions; a warp of 32 unrelated rays walks 32 different parts of the octree
+// (measured: 5.8 of 32 lanes active in k_bounce at depth 1).  Before the next bounce the queue is therefore binned by
+// (Morton cell of the origin in the root box, 5 bits per axis | direction octant): a counting sort that only builds a
+// permutation — histogram with REDs, exclusive scan, scatter of indices — which the next k_bounce reads its rays through.
+// Order inside a bin is arbitrary (atomics); no result depends on queue order: every path owns its accumulator and its
+// PRNG key.
+#define GI_SORT_BITS 18
+#define GI_SORT_BINS (1u << GI_SORT_BITS)
+__device__ __forceinline__ uint32_t spread5(uint32_t v)   // abcde -> a00b00c00d00e
+{
+    v &= 31u;
+    v = (v | (v << 8)) & 0x100Fu;
+    v = (v | (v << 4)) & 0x10C3u;
+    v = (v | (v << 2)) & 0x1249u;
+    return v;
+}
+__global__ void k_bin_keys(uint32_t n, const double* __restrict__ org, const double* __restrict__ dir, d3 bmin, d3 inv_ext, uint32_t* __restrict__ key, uint32_t* __restrict__ hist)
+{
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    d3 o = ld3(org + 3 * (size_t)i), d = ld3(dir + 3 * (size_t)i);
+    int cx = (int)((o.x - bmin.x) * inv_ext.x), cy = (int)((o.y - bmin.y) * inv_ext.y), cz = (int)((o.z - bmin.z) * inv_ext.z);
+    cx = cx < 0 ? 0 : (cx > 31 ? 31 : cx); cy = cy < 0 ? 0 : (cy > 31 ? 31 : cy); cz = cz < 0 ? 0 : (cz > 31 ? 31 : cz);
+    uint32_t k = ((spread5((uint32_t)cx) | (spread5((uint32_t)cy) << 1) | (spread5((uint32_t)cz) << 2)) << 3) | (d.x < 0 ? 1u : 0u) | (d.y < 0 ? 2u : 0u) | (d.z < 0 ? 4u : 0u);
+    key[i] = k;
+    atomicAdd(hist + k, 1u);
+}
+__global__ void k_bin_scatter(uint32_t n, const uint32_t* __restrict__ key, uint32_t* __restrict__ cursor, uint32_t* __restrict__ perm)
+{
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    perm[atomicAdd(cursor + key[i], 1u)] = i;
+}
+
 // ---- K4: wavefront bounce = closest hit + shade + scatter (raytracer.h:167-276, 321-379, 481-506) -------------------------------------
 // Queue entry (SoA): ray origin/dir, throughput T, Russian-roulette weight contrib, path id.  Per path: Halton index, PRNG
 // key, radiance sum L.  Per hit (compacted "hit list"): what the shadow and gather kernels need.
@@ -507,11 +1002,12 @@ struct DPathState { uint32_t* sample; uint64_t* key; double* L; };
 struct DCounters { uint32_t n_next, n_hits; unsigned long long closest, shadow, gathers; };
 
 template <bool FULL, bool IMPL>
-__global__ void __launch_bounds__(GI_BLOCK, GI_MINB) k_bounce(DScene S, gi_render_params P, int depth, uint32_t n, DQueue in, DQueue out, DHitList H, DPathState PS, DCounters* C,
-                                                     unsigned long long* work)
+__global__ void __launch_bounds__(GI_BLOCK, GI_MINB) k_bounce(DScene S, gi_render_params P, int depth, uint32_t n, DQueue in, const uint32_t* __restrict__ perm, DQueue out, DHitList H,
+                                                     DPathState PS, DCounters* C, unsigned long long* work)
 {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     bool active = i < n;
+    if (active && perm) i = perm[i];   // binned order (k_bin_*)
     bool is_hit = false, cont = false;
     d3 hp, hn, refDir, wdir, wcau, Tn, contrib;
     double rough = 1, offset = GI_D_SHADOW_BIAS;

@@ -181,7 +181,9 @@ def test_photon_map_and_gather_vs_oracle_random_cloud(ctx):
         assert same.mean() > 0.995, same.mean()
         assert bits_equal(knn[same], k2[same])
         assert np.allclose(rgb[same], r2[same], rtol=1e-12, atol=0)
-    assert (nc == 0).sum() > 100 and nc.max() > 200
+    # every selection path is exercised: everything selected (<= k), bisection select in registers (k < n <= 256), the
+    # streaming sort/merge (> 256 candidates, and the coincident-photon ties)
+    assert (nc == 0).sum() > 100 and ((nc > 32) & (nc <= 256)).sum() > 1000 and (nc > 256).any()
 
 
 def test_empty_and_tiny_photon_maps(ctx):
@@ -197,6 +199,22 @@ def test_empty_and_tiny_photon_maps(ctx):
     rgb, knn, nc = ctx.gather(q, q, 32)
     r2, k2, n2, _ = O.PMap(ph, box).gather(q, q, 32)
     assert bits_equal(nc, n2) and bits_equal(knn, k2) and np.allclose(rgb, r2, rtol=1e-12, atol=0)
+    # sparse maps: fewer candidates than k (everything selected), and k < candidates < 32 (select with idle lanes); query
+    # counts that are not multiples of the queries-per-warp batch
+    rng = np.random.RandomState(2)
+    for nph, nq, k in ((60, 1, 32), (60, 33, 5), (150, 1000, 7), (150, 2049, 3), (400, 5000, 32)):
+        ph = rng.rand(nph, 9)
+        qq = rng.rand(nq, 3) * 1.2 - 0.1
+        ctx.photon_upload(ph)
+        ctx.photon_map_build(box)
+        rgb, knn, nc = ctx.gather(qq, rng.randn(nq, 3), k)
+        ctx.photon_map_build(box)
+        qd = rng.randn(nq, 3)
+        rgb, knn, nc = ctx.gather(qq, qd, k)
+        r2, k2, n2, _ = O.PMap(ph, box).gather(qq, qd, k)
+        assert bits_equal(nc, n2) and bits_equal(knn, k2) and np.allclose(rgb, r2, rtol=1e-12, atol=0), (nph, nq, k)
+        if nph == 150:
+            assert ((nc > k) & (nc < 32)).any()
 
 
 @pytest.mark.parametrize("name", ["mixed", "cornell"])
@@ -392,6 +410,34 @@ def test_tail_kernel_equals_wavefront(lib_built, synth_dir, monkeypatch):
             for f in ("closest_rays", "shadow_rays", "gathers", "closest_node_tests", "closest_prim_tests", "gather_candidates", "gather_selected", "gather_leaf_depth"):
                 assert getattr(sa, f) == getattr(sb, f), f
             assert sb.shade_ms > 0 and sa.shade_ms == 0
+    finally:
+        c0.close(); c1.close()
+
+
+def test_ray_binning_does_not_change_results(lib_built, synth_dir, monkeypatch):
+    """Binning the ray queue by origin cell / direction octant between bounces only permutes the processing order: the
+    frame, the ray counts and the work tallies must be bit-identical with and without it."""
+    from gi_raytracer_b200.capi import Context
+    monkeypatch.setenv("GI_TAIL_THRESHOLD", "0")
+    monkeypatch.setenv("GI_BIN_THRESHOLD", "0")
+    c0 = Context(0)
+    monkeypatch.setenv("GI_BIN_THRESHOLD", "1")
+    c1 = Context(0)
+    try:
+        for name, depth in (("mixed", 10), ("atrium", 5)):
+            sc = _load(name, synth_dir)
+            outs = []
+            for c in (c0, c1):
+                c.upload_scene(sc)
+                c.photon_trace(2500 if name == "mixed" else 0, 5, seed=2)
+                c.photon_map_build(None)
+                P = render_params(64, 48, 3, max_depth=depth, seed=23)
+                outs.append(c.render_tile(P, 0, 0, 64, 48, 0, 3))
+            (a, sa), (b, sb) = outs
+            assert bits_equal(a, b), f"{name}: {np.abs(a - b).max()}"
+            for f in ("closest_rays", "shadow_rays", "gathers", "closest_node_tests", "closest_prim_tests", "shadow_node_tests", "shadow_prim_tests", "gather_candidates"):
+                assert getattr(sa, f) == getattr(sb, f), f
+            assert c1.kernel_ms("bin")[1] > 0 and c0.kernel_ms("bin")[1] == 0
     finally:
         c0.close(); c1.close()
 
