@@ -311,11 +311,20 @@ def main():
     if rank == 0:
         peak, peak_kind = load_peaks()
         last = stats[-1]
+        g = lambda f: int(getattr(last, f))   # noqa: E731
+        # the wavefront kernels' share of the work = totals minus what the tail kernel (one warp per path, deep bounces) did
         fam = {
-            "bounce": (float(last.trace_ms), bytes_closest(int(last.closest_rays), int(last.closest_node_tests), int(last.closest_prim_tests))),
-            "direct": (float(last.shadow_ms), bytes_shadow(int(last.shadow_rays), int(last.shadow_node_tests), int(last.shadow_prim_tests))),
-            "gather": (float(last.gather_ms), bytes_gather(int(last.gathers), int(last.gather_leaf_depth), int(last.gather_candidates), int(last.gather_selected))),
+            "bounce": (float(last.trace_ms), bytes_closest(g("closest_rays") - g("tail_closest_rays"), g("closest_node_tests") - g("tail_closest_node_tests"),
+                                                           g("closest_prim_tests") - g("tail_closest_prim_tests"))),
+            "direct": (float(last.shadow_ms), bytes_shadow(g("shadow_rays") - g("tail_shadow_rays"), g("shadow_node_tests") - g("tail_shadow_node_tests"),
+                                                           g("shadow_prim_tests") - g("tail_shadow_prim_tests"))),
+            "gather": (float(last.gather_ms), bytes_gather(g("gathers") - g("tail_gathers"), g("gather_leaf_depth") - g("tail_gather_leaf_depth"),
+                                                           g("gather_candidates") - g("tail_gather_candidates"), g("gather_selected") - g("tail_gather_selected"))),
         }
+        tail_bytes = (bytes_closest(g("tail_closest_rays"), g("tail_closest_node_tests"), g("tail_closest_prim_tests"))
+                      + bytes_shadow(g("tail_shadow_rays"), g("tail_shadow_node_tests"), g("tail_shadow_prim_tests"))
+                      + bytes_gather(g("tail_gathers"), g("tail_gather_leaf_depth"), g("tail_gather_candidates"), g("tail_gather_selected")))
+        frame_bytes = sum(v[1] for v in fam.values()) + tail_bytes
         dom = max(fam, key=lambda k: fam[k][0])
         dom_ms, dom_bytes = fam[dom]
         n_launch = {"bounce": ctx.kernel_ms("bounce")[1], "direct": ctx.kernel_ms("direct")[1], "gather": ctx.kernel_ms("gather")[1]}
@@ -333,6 +342,11 @@ def main():
                     "algorithmic_bytes_per_step": dom_bytes, "kernel_ms_per_step": dom_ms, "launches_per_step": n_launch[dom],
                     "families": {k: {"ms_per_step": v[0], "algorithmic_GBps": (v[1] / (v[0] * 1e-3) / 1e9 if v[0] > 0 else 0.0), "frac": (v[1] / (v[0] * 1e-3) / 1e9 / peak if v[0] > 0 else 0.0)}
                                  for k, v in fam.items()},
+                    "tail": {"ms_per_step": float(last.shade_ms), "algorithmic_GBps": tail_bytes / (float(last.shade_ms) * 1e-3) / 1e9 if last.shade_ms > 0 else 0.0,
+                             "rays": g("tail_closest_rays") + g("tail_shadow_rays"), "gathers": g("tail_gathers")},
+                    "bin_ms_per_step": float(last.bin_ms),
+                    "frame": {"algorithmic_bytes": frame_bytes, "ms": float(last.total_ms), "algorithmic_GBps": frame_bytes / (float(last.total_ms) * 1e-3) / 1e9,
+                              "frac": frame_bytes / (float(last.total_ms) * 1e-3) / 1e9 / peak},
                     "gather_isolated": {"ms": gather_ms, "queries": nq, "algorithmic_GBps": gather_bytes / (gather_ms * 1e-3) / 1e9, "frac": gather_bytes / (gather_ms * 1e-3) / 1e9 / peak}}
         cpu = None
         if not args.no_cpu_baseline and world == 1:

@@ -60,7 +60,11 @@ class GiStats(C.Structure):
                 ("shadow_prim_tests", C.c_uint64), ("gather_leaf_depth", C.c_uint64), ("gather_candidates", C.c_uint64),
                 ("gather_selected", C.c_uint64),
                 ("trace_ms", C.c_double), ("shadow_ms", C.c_double), ("gather_ms", C.c_double),
-                ("shade_ms", C.c_double), ("total_ms", C.c_double)]
+                ("shade_ms", C.c_double), ("total_ms", C.c_double),
+                ("tail_closest_rays", C.c_uint64), ("tail_shadow_rays", C.c_uint64), ("tail_gathers", C.c_uint64),
+                ("tail_closest_node_tests", C.c_uint64), ("tail_closest_prim_tests", C.c_uint64), ("tail_shadow_node_tests", C.c_uint64),
+                ("tail_shadow_prim_tests", C.c_uint64), ("tail_gather_leaf_depth", C.c_uint64), ("tail_gather_candidates", C.c_uint64),
+                ("tail_gather_selected", C.c_uint64), ("bin_ms", C.c_double)]
 
     def as_dict(self):
         return {n: getattr(self, n) for n, _ in self._fields_}

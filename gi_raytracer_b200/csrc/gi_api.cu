@@ -1002,6 +1002,10 @@ static int render_device(gi_ctx* ctx, const gi_render_params* P, int x0, int y0,
         const unsigned long long* w = ctx->work_host;
         stats->closest_node_tests = w[0]; stats->closest_prim_tests = w[1]; stats->shadow_node_tests = w[2]; stats->shadow_prim_tests = w[3];
         stats->gather_leaf_depth = w[4]; stats->gather_candidates = w[5]; stats->gather_selected = w[6];
+        stats->tail_closest_rays = tc.closest; stats->tail_shadow_rays = tc.shadow; stats->tail_gathers = tc.gathers;
+        stats->tail_closest_node_tests = tc.nodes_c; stats->tail_closest_prim_tests = tc.prims_c; stats->tail_shadow_node_tests = tc.nodes_s; stats->tail_shadow_prim_tests = tc.prims_s;
+        stats->tail_gather_leaf_depth = tc.g_depth; stats->tail_gather_candidates = tc.g_cand; stats->tail_gather_selected = tc.g_sel;
+        stats->bin_ms = ctx->fam["bin"].ms;
     }
     return GI_OK;
 }

@@ -137,6 +137,12 @@ typedef struct gi_stats {
     /* gather: sum of containing-leaf depths, of candidate counts C, and of min(k, C)                              */
     uint64_t gather_leaf_depth, gather_candidates, gather_selected;
     double trace_ms, shadow_ms, gather_ms, shade_ms, total_ms; /* CUDA-event times: bounce, direct, gather, tail (in shade_ms), whole call */
+    /* the part of the totals above that was done inside the tail kernel (one warp per path, time in shade_ms); the
+       bounce / direct / gather kernels did the rest in trace_ms / shadow_ms / gather_ms                              */
+    uint64_t tail_closest_rays, tail_shadow_rays, tail_gathers;
+    uint64_t tail_closest_node_tests, tail_closest_prim_tests, tail_shadow_node_tests, tail_shadow_prim_tests;
+    uint64_t tail_gather_leaf_depth, tail_gather_candidates, tail_gather_selected;
+    double bin_ms;                  /* ray binning between bounces (k_bin_*)                             */
 } gi_stats;
 
 /* ---- lifetime ------------------------------------------------------------------------------------------ */
