@@ -616,8 +616,8 @@ extern "C" int gi_photon_trace(gi_ctx* ctx, int count, int max_depth, uint64_t s
 }
 
 // ---- photon map ---------------------------------------------------------------------------------------------------------------------------
-struct SlabHeader { uint32_t magic, n_nodes, n_kept, n_leaves, max_depth, n_cand, pad[2]; uint64_t off_nodes, off_pos, off_dircol, off_pid, off_cand_off, off_cand_slot, off_cand_key, total; };
-#define GI_SLAB_MAGIC 0x47495034u   // "GIP4"
+struct SlabHeader { uint32_t magic, n_nodes, n_kept, n_leaves, max_depth, n_cand, pad[2]; uint64_t off_nodes, off_pos, off_dircol, off_pid, off_cand_off, off_cand_rec, total; };
+#define GI_SLAB_MAGIC 0x47495035u   // "GIP5"
 static inline size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
 
 static void bind_slab(gi_ctx* ctx, const SlabHeader& h)
@@ -628,8 +628,7 @@ static void bind_slab(gi_ctx* ctx, const SlabHeader& h)
     ctx->G.dircol = reinterpret_cast<const double*>(base + h.off_dircol);
     ctx->G.pid = reinterpret_cast<const uint32_t*>(base + h.off_pid);
     ctx->G.cand_off = reinterpret_cast<const uint32_t*>(base + h.off_cand_off);
-    ctx->G.cand_slot = reinterpret_cast<const uint32_t*>(base + h.off_cand_slot);
-    ctx->G.cand_key = reinterpret_cast<const float*>(base + h.off_cand_key);
+    ctx->G.cand_rec = reinterpret_cast<const double*>(base + h.off_cand_rec);
     ctx->G.n_nodes = h.n_nodes;
     ctx->pm_nodes = h.n_nodes; ctx->pm_kept = h.n_kept; ctx->pm_leaves = h.n_leaves; ctx->pm_depth = h.max_depth;
     ctx->slab_bytes = h.total;
@@ -698,19 +697,19 @@ extern "C" int gi_photon_map_build(gi_ctx* ctx, const double* box6)
     CK(cudaStreamSynchronize(ctx->stream));
     if (host_cnt[2]) return fail(ctx, GI_ERR_OOM, "photon map candidate traversal stack overflow");
     const uint32_t n_cand = host_cnt[0];
-    // compact slab: header | nodes | pos4 | dircol | pid | cand_off | cand_slot | cand_key
+    // compact slab: header | nodes | pos4 | dircol | pid | cand_off | cand_rec
     SlabHeader h{};
     h.magic = GI_SLAB_MAGIC; h.n_nodes = n_nodes; h.n_kept = n_kept; h.max_depth = depth; h.n_cand = n_cand;
     h.off_nodes = 256; h.off_pos = align256(h.off_nodes + (size_t)n_nodes * sizeof(DNode)); h.off_dircol = align256(h.off_pos + (size_t)n_kept * 32);
     h.off_pid = align256(h.off_dircol + (size_t)n_kept * 48); h.off_cand_off = align256(h.off_pid + (size_t)n_kept * 4);
-    h.off_cand_slot = align256(h.off_cand_off + (size_t)(n_nodes + 1) * 4); h.off_cand_key = align256(h.off_cand_slot + (size_t)n_cand * 4);
-    h.total = align256(h.off_cand_key + (size_t)n_cand * 4);
+    h.off_cand_rec = align256(h.off_cand_off + (size_t)(n_nodes + 1) * 4); h.total = align256(h.off_cand_rec + (size_t)n_cand * 32);
+    CK(ctx->w8.reserve(std::max<size_t>(n_cand, 1) * 4));   // candidate slots in DFS order (scratch; the slab holds the ordered records)
     CK(ctx->b_slab.reserve(h.total));
     char* base = ctx->b_slab.as<char>();
     CK(cudaMemcpyAsync(base + h.off_nodes, M.nodes, (size_t)n_nodes * sizeof(DNode), cudaMemcpyDeviceToDevice, ctx->stream));
     if (n_kept) CK(cudaMemcpyAsync(base + h.off_pid, M.pid, (size_t)n_kept * 4, cudaMemcpyDeviceToDevice, ctx->stream));
     CK(cudaMemcpyAsync(base + h.off_cand_off, cand_off, (size_t)(n_nodes + 1) * 4, cudaMemcpyDeviceToDevice, ctx->stream));
-    k_pm_cands<4, true><<<grid_for(n_nodes, 4), 128, 0, ctx->stream>>>(M.nodes, n_nodes, nullptr, cand_off, reinterpret_cast<uint32_t*>(base + h.off_cand_slot), M.overflow);
+    k_pm_cands<4, true><<<grid_for(n_nodes, 4), 128, 0, ctx->stream>>>(M.nodes, n_nodes, nullptr, cand_off, ctx->w8.as<uint32_t>(), M.overflow);
     M.pos4 = reinterpret_cast<double*>(base + h.off_pos); M.dircol = reinterpret_cast<double*>(base + h.off_dircol);
     if (n_kept) k_pm_payload<<<grid_for(n_kept, 256), 256, 0, ctx->stream>>>(M, n_kept);
     CK(cudaGetLastError());
@@ -727,10 +726,10 @@ extern "C" int gi_photon_map_build(gi_ctx* ctx, const double* box6)
                     (unsigned long long)n8k, (unsigned long long)s8k, (unsigned long long)n64k);
         }
         CK(cudaFuncSetAttribute(k_pm_cand_order, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(LONG_LEN * 12)));
-        uint32_t* cslot = reinterpret_cast<uint32_t*>(base + h.off_cand_slot);
-        float* ckey = reinterpret_cast<float*>(base + h.off_cand_key);
-        k_pm_cand_order<<<n_nodes, 64, SHORT_LEN * 12, ctx->stream>>>(M.nodes, n_nodes, M.pos4, cand_off, cslot, ckey, 0u, SHORT_LEN, LONG_LEN);
-        k_pm_cand_order<<<n_nodes, 256, LONG_LEN * 12, ctx->stream>>>(M.nodes, n_nodes, M.pos4, cand_off, cslot, ckey, SHORT_LEN, 0xFFFFFFFFu, LONG_LEN);
+        const uint32_t* cslot = ctx->w8.as<uint32_t>();
+        double* crec = reinterpret_cast<double*>(base + h.off_cand_rec);
+        k_pm_cand_order<<<n_nodes, 64, SHORT_LEN * 12, ctx->stream>>>(M.nodes, n_nodes, M.pos4, cand_off, cslot, crec, 0u, SHORT_LEN, LONG_LEN);
+        k_pm_cand_order<<<n_nodes, 256, LONG_LEN * 12, ctx->stream>>>(M.nodes, n_nodes, M.pos4, cand_off, cslot, crec, SHORT_LEN, 0xFFFFFFFFu, LONG_LEN);
         CK(cudaGetLastError());
     }
     // leaves are counted on the host from the node records (also validates the build)
@@ -815,7 +814,7 @@ extern "C" int gi_photon_map_adopt_slab(gi_ctx* ctx, size_t bytes)
     CK(cudaSetDevice(ctx->device));
     SlabHeader h;
     CK(cudaMemcpy(&h, ctx->b_slab.p, sizeof(h), cudaMemcpyDeviceToHost));
-    if (h.magic != GI_SLAB_MAGIC || h.total != bytes || h.off_pid + (uint64_t)h.n_kept * 4 > bytes || h.off_cand_key + (uint64_t)h.n_cand * 4 > bytes) return fail(ctx, GI_ERR_INVALID, "bad photon map slab");
+    if (h.magic != GI_SLAB_MAGIC || h.total != bytes || h.off_pid + (uint64_t)h.n_kept * 4 > bytes || h.off_cand_rec + (uint64_t)h.n_cand * 32 > bytes) return fail(ctx, GI_ERR_INVALID, "bad photon map slab");
     bind_slab(ctx, h);
     return GI_OK;
 }

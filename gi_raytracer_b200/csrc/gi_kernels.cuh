@@ -7,8 +7,8 @@
 
 #define GI_BLOCK 128
 #ifndef GI_MINB
-#define GI_MINB 1   // minimum resident blocks per SM requested from ptxas for the thread-per-ray traversal kernels
-#endif
+#define GI_MINB 6   // resident blocks of 128 threads per SM asked of ptxas for the thread-per-ray traversal kernels: 80 registers.
+#endif              // measured on the C2 frame (bounce + direct ms): 1-3 blocks (136-142 regs) 23.1, 4 (128) 19.4, 5 (96) 18.8, 6 (80) 17.9, 8 (64) 19.1
 #define GI_PM_LEAF_MAX 16   // MAX_PHOTONS_PER_LEAF (util.h:15)
 
 // ---- K0: Halton known-answer entry points -----------------------------------------------------------------------------------
@@ -317,9 +317,19 @@ __global__ void k_pm_payload(DPMap M, uint32_t n_kept)
 struct DGatherMap {
     const DNode* nodes; const double* pos4; const double* dircol; const uint32_t* pid; uint32_t n_nodes;
     const uint32_t* cand_off;    // [n_nodes + 1] start of each node's candidate list (only leaves have entries)
-    const uint32_t* cand_slot;   // photon slots, concatenated per leaf, each list ordered by distance from the leaf centre
-    const float* cand_key;       // squared distance of each candidate from the centre of its leaf, rounded down (0 = list not ordered)
+    // the candidate lists, concatenated per leaf, each ordered by distance from the leaf centre: one 32-byte record per
+    // candidate = position x, y, z | photon slot (u32) | squared distance from the centre of the leaf, rounded down (f32; 0 =
+    // list not ordered).  A list is read front to back with two aligned 16-byte loads per candidate and no indirection.
+    const double* cand_rec;
 };
+struct Cand { d3 pos; uint32_t slot; float key; };
+__device__ __forceinline__ Cand load_cand(const DGatherMap& M, uint32_t idx)
+{
+    const double2* r = reinterpret_cast<const double2*>(M.cand_rec) + 2 * (size_t)idx;
+    const double2 a = __ldg(r), b = __ldg(r + 1);
+    Cand c; c.pos = mk3(a.x, a.y, b.x); c.slot = (uint32_t)__double2loint(b.y); c.key = __int_as_float(__double2hiint(b.y));
+    return c;
+}
 #define GI_GATHER_REGS 8   // candidates per lane held in registers by the select path (8 x 32 = 256 per query)
 #ifndef GI_GATHER_MINB
 #define GI_GATHER_MINB 6   // resident blocks (of 4 warps) per SM asked of ptxas for k_gather: 6 -> 80 registers, no spills
@@ -354,13 +364,6 @@ __device__ __forceinline__ void warp_merge32(double& d, uint32_t& sl, double bd,
     uint32_t rsl = __shfl_sync(0xffffffffu, bsl, 31 - lane);
     if (kv_less(rd, rsl, d, sl)) { d = rd; sl = rsl; }
     for (int j = 16; j > 0; j >>= 1) cmpx(d, sl, lane, j, true);
-}
-
-__device__ __forceinline__ double cand_dist2(const DGatherMap& M, uint32_t slot, d3 p)
-{
-    const double2* pp = reinterpret_cast<const double2*>(M.pos4 + 4 * (size_t)slot);
-    double2 a = __ldg(pp), b = __ldg(pp + 1);
-    return len2(mk3(a.x, a.y, b.x) - p);
 }
 
 // getBounds (photonMap.cpp:115-134), warp form: the leaf whose half-open box contains p; false when p is in no child
@@ -450,10 +453,10 @@ __device__ __noinline__ void gather_topk_stream(const DGatherMap& M, uint32_t of
     const uint32_t lt = (1u << lane) - 1u;
     __syncwarp();
     for (uint32_t base = 0; base < total; base += 32) {
-        if (delta >= 0 && __ldg(M.cand_key + off + base) > bound) break;
         const bool have = base + lane < total;
-        double cd = CUDART_INF; uint32_t csl = 0xFFFFFFFFu;
-        if (have) { csl = __ldg(M.cand_slot + off + base + lane); cd = cand_dist2(M, csl, p); }
+        double cd = CUDART_INF; uint32_t csl = 0xFFFFFFFFu; float key = 0.f;
+        if (have) { const Cand c = load_cand(M, off + base + lane); csl = c.slot; cd = len2(c.pos - p); key = c.key; }
+        if (delta >= 0 && __shfl_sync(0xffffffffu, key, 0) > bound) break;   // lane 0 holds the smallest key of the step
         const bool useful = have && kv_less(cd, csl, kth_d, kth_sl);
         const uint32_t um = __ballot_sync(0xffffffffu, useful);
         if (!um) continue;
@@ -560,14 +563,15 @@ __device__ __forceinline__ GatherOut gather_at_leaf(const DGatherMap& M, bool fo
         const int nb = (int)((total + 31u) >> 5);
         double cd[GI_GATHER_REGS];
         const bool warm = csl_node == node;
-        if (!warm) {
+        csl_node = node;
+        {
             const uint32_t off = __ldg(M.cand_off + node);
 #pragma unroll
-            for (int j = 0; j < GI_GATHER_REGS; j++) csl[j] = (j < nb && (uint32_t)(j * 32 + lane) < total) ? __ldg(M.cand_slot + off + j * 32 + lane) : 0xFFFFFFFFu;
-            csl_node = node;
+            for (int j = 0; j < GI_GATHER_REGS; j++) {
+                cd[j] = CUDART_INF; csl[j] = 0xFFFFFFFFu;
+                if (j < nb && (uint32_t)(j * 32 + lane) < total) { const Cand c = load_cand(M, off + j * 32 + lane); csl[j] = c.slot; cd[j] = len2(c.pos - p); }
+            }
         }
-#pragma unroll
-        for (int j = 0; j < GI_GATHER_REGS; j++) cd[j] = (j < nb && csl[j] != 0xFFFFFFFFu) ? cand_dist2(M, csl[j], p) : CUDART_INF;
         bool sorted = false;
         if (total <= (uint32_t)k) { best_d = cd[0]; best_sl = csl[0]; }   // k <= 32: everything is selected
         else {
@@ -731,17 +735,40 @@ __global__ void k_gather_locate(DGatherMap M, uint32_t n, const double* __restri
     }
 }
 
-#define GI_GS_MAX_CANDS 256u   // longer candidate lists are streamed by the whole warp
+#ifndef GI_GS_MAX_CANDS
+#define GI_GS_MAX_CANDS 256u
+#endif
+// GI_GS_MAX_CANDS:   // longer candidate lists are streamed by the whole warp ...
+#ifndef GI_GS_MIN_GROUP
+#define GI_GS_MIN_GROUP 33
+#endif
+// GI_GS_MIN_GROUP:       // ... unless at least this many lanes of the warp share the list
 #define GI_GS_BLOCK 64   // 64 columns x 32 rows x 12 B = 24 KB of shared memory per block
+
+// max-heap of (distance^2, slot) pairs in one thread's column of shared memory: put (d, sl) into the hole at `i` of a heap of
+// `n` rows and sift it down
+__device__ __forceinline__ void heap_sift(double (*sd)[GI_GS_BLOCK], uint32_t (*ss)[GI_GS_BLOCK], int t, int n, int i, double d, uint32_t sl)
+{
+    for (;;) {
+        int c = 2 * i + 1;
+        if (c >= n) break;
+        double cd = sd[c][t]; uint32_t cs = ss[c][t];
+        if (c + 1 < n) { const double d2 = sd[c + 1][t]; const uint32_t s2 = ss[c + 1][t]; if (kv_less(cd, cs, d2, s2)) { c++; cd = d2; cs = s2; } }
+        if (!kv_less(d, sl, cd, cs)) break;
+        sd[i][t] = cd; ss[i][t] = cs; i = c;
+    }
+    sd[i][t] = d; ss[i][t] = sl;
+}
 
 // Each leaf's candidate list is stored in ascending distance from the CENTRE of the leaf box (k_pm_cand_order), with that
 // squared distance (rounded down) beside it.  A query point q lies inside the leaf box, so for a candidate c
 //     |q - c| >= |centre - c| - delta,     delta = half diagonal of the leaf box  >= |q - centre|.
-// The thread keeps the k nearest so far as a sorted column of shared memory ([rank][thread]: conflict-free for any mix of
-// ranks); tau = the k-th distance.  Once |centre - c| - delta > sqrt(tau) no later candidate of the (ordered) list can enter,
-// and the scan stops — typically after k plus a thin shell of candidates, also in the lists of thousands that a large leaf
-// next to a dense region carries.  Candidates arrive almost in order, so the insertion shifts are short.  Order and ties are
-// exactly (distance^2, slot); the bound is inflated by 1e-9 relative against rounding.
+// The thread keeps the k nearest so far as a MAX-HEAP in its column of shared memory ([row][thread]: conflict-free for any mix
+// of rows); tau = the root = the k-th distance.  A candidate below tau replaces the root and sifts down (<= 5 levels, whatever
+// the arrival order — an insertion-sorted list degenerates to k shifts per candidate when distances keep falling along the
+// list).  Once |centre - c| - delta > sqrt(tau) no later candidate of the (ordered) list can enter, and the scan stops.  At the
+// end an in-place heap sort leaves the column in ascending (distance^2, slot) order for the sum.  The bound is inflated by
+// 1e-9 relative against rounding.
 __global__ void __launch_bounds__(GI_GS_BLOCK) k_gather_sorted(DGatherMap M, uint32_t n, const uint32_t* __restrict__ perm, const uint32_t* __restrict__ qnode,
                                                                  const double* __restrict__ qpos, const double* __restrict__ qdir, int k, double* __restrict__ rgb,
                                                                  uint32_t* __restrict__ knn, uint32_t* __restrict__ ncand, const double* __restrict__ weight,
@@ -769,28 +796,46 @@ __global__ void __launch_bounds__(GI_GS_BLOCK) k_gather_sorted(DGatherMap M, uin
     }
     const int count = (int)total < k ? (int)total : k;
     int m = 0;                       // rows in use
-    double tau = CUDART_INF;         // k-th distance^2 once m == k
+    double tau = CUDART_INF; uint32_t tau_sl = 0xFFFFFFFFu;   // the k-th (distance^2, slot) once m == k
     float bound = CUDART_INF_F;      // scan stops at the first key above it
     // long lists (a large leaf next to a dense region touches thousands of small ones) are streamed by the whole warp, 32
     // candidates per step, instead of by one thread
-    const bool hard = total > GI_GS_MAX_CANDS;
-    for (uint32_t j = 0; j < (hard ? 0u : total); j++) {
-        if (__ldg(M.cand_key + off + j) > bound) break;
-        const uint32_t sl = __ldg(M.cand_slot + off + j);
-        const double d = cand_dist2(M, sl, p);
-        if (m == k && !kv_less(d, sl, tau, s_sl[k - 1][t])) continue;
-        int r = m < k ? m : k - 1;   // the last row is dropped when the list is full
-        while (r > 0) {
-            const double pd = s_d[r - 1][t]; const uint32_t ps = s_sl[r - 1][t];
-            if (!kv_less(d, sl, pd, ps)) break;
-            s_d[r][t] = pd; s_sl[r][t] = ps; r--;
-        }
-        s_d[r][t] = d; s_sl[r][t] = sl;
-        if (m < k) m++;
-        if (m == k) {
-            tau = s_d[k - 1][t];
+    // ... unless several lanes of this warp sit in that same leaf (in leaf order they usually do): one pass over the list then
+    // serves all of them, each lane against its own point
+    const uint32_t same_leaf = __match_any_sync(0xffffffffu, node);
+    const bool hard = total > GI_GS_MAX_CANDS && __popc(same_leaf) < GI_GS_MIN_GROUP;
+    // the list is read four records ahead of their use (eight independent 16-byte loads in flight per thread); the stop test
+    // is made once per group, so the scan may run up to three candidates past the bound — they are simply rejected
+    const uint32_t n_scan = hard ? 0u : total;
+    for (uint32_t j0 = 0; j0 < n_scan; j0 += 4) {
+        Cand cs[4];
+#pragma unroll
+        for (int u = 0; u < 4; u++) cs[u] = load_cand(M, off + (j0 + u < n_scan ? j0 + u : n_scan - 1));
+        if (cs[0].key > bound) break;
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            if (j0 + u >= n_scan) break;
+            const uint32_t sl = cs[u].slot;
+            const double d = len2(cs[u].pos - p);
+            if (m == k) {
+                if (!kv_less(d, sl, tau, tau_sl)) continue;
+                heap_sift(s_d, s_sl, t, k, 0, d, sl);           // replaces the root
+            } else {
+                s_d[m][t] = d; s_sl[m][t] = sl; m++;
+                if (m < k) continue;
+                for (int i = k / 2 - 1; i >= 0; i--) heap_sift(s_d, s_sl, t, k, i, s_d[i][t], s_sl[i][t]);   // k rows filled: heapify
+            }
+            tau = s_d[0][t]; tau_sl = s_sl[0][t];
             const double b = sqrt(tau) + delta;
             bound = __double2float_ru(b * b * (1.0 + 1e-9));
+        }
+    }
+    if (!hard && m > 1) {
+        if (m < k) for (int i = m / 2 - 1; i >= 0; i--) heap_sift(s_d, s_sl, t, m, i, s_d[i][t], s_sl[i][t]);   // fewer than k candidates: not a heap yet
+        for (int n2 = m - 1; n2 > 0; n2--) {   // heap sort: the largest goes to the end, the rest is re-heaped
+            const double ld = s_d[n2][t]; const uint32_t ls = s_sl[n2][t];
+            s_d[n2][t] = s_d[0][t]; s_sl[n2][t] = s_sl[0][t];
+            heap_sift(s_d, s_sl, t, n2, 0, ld, ls);
         }
     }
     d3 res = mk3(0, 0, 0);
@@ -869,15 +914,20 @@ __global__ void __launch_bounds__(GI_WPB * 32) k_gather_heavy(DGatherMap M, cons
 // order every leaf's candidate list by distance from the centre of the leaf box and write the keys (see k_gather_sorted).
 // One block per leaf; lists of LO < length <= HI entries are sorted by a bitonic network in shared memory ((distance^2,
 // slot) pairs, padded to a power of two); longer lists keep the DFS order with key 0, which never stops a scan.
-__global__ void k_pm_cand_order(const DNode* __restrict__ nodes, uint32_t n_nodes, const double* __restrict__ pos4, const uint32_t* __restrict__ cand_off, uint32_t* __restrict__ cand_slot,
-                                float* __restrict__ cand_key, uint32_t lo_len, uint32_t hi_len, uint32_t max_sortable)
+__global__ void k_pm_cand_order(const DNode* __restrict__ nodes, uint32_t n_nodes, const double* __restrict__ pos4, const uint32_t* __restrict__ cand_off, const uint32_t* __restrict__ cand_slot,
+                                double* __restrict__ cand_rec, uint32_t lo_len, uint32_t hi_len, uint32_t max_sortable)
 {
     extern __shared__ __align__(16) unsigned char s_raw[];
     const uint32_t leaf = blockIdx.x;
     if (leaf >= n_nodes) return;
     const uint32_t off = cand_off[leaf], total = cand_off[leaf + 1] - off;
     if (total <= lo_len || total > hi_len) return;
-    if (total > max_sortable) { for (uint32_t j = threadIdx.x; j < total; j += blockDim.x) cand_key[off + j] = 0.f; return; }
+    auto put = [&](uint32_t j, uint32_t sl, float key) {
+        const double* pp = pos4 + 4 * (size_t)sl;
+        double* r = cand_rec + 4 * (size_t)(off + j);
+        r[0] = pp[0]; r[1] = pp[1]; r[2] = pp[2]; r[3] = __hiloint2double(__float_as_int(key), (int)sl);
+    };
+    if (total > max_sortable) { for (uint32_t j = threadIdx.x; j < total; j += blockDim.x) put(j, cand_slot[off + j], 0.f); return; }
     uint32_t np2 = 1; while (np2 < total) np2 <<= 1;
     double* kd = reinterpret_cast<double*>(s_raw);
     uint32_t* ks = reinterpret_cast<uint32_t*>(s_raw + (size_t)np2 * 8);
@@ -900,7 +950,7 @@ __global__ void k_pm_cand_order(const DNode* __restrict__ nodes, uint32_t n_node
             }
             __syncthreads();
         }
-    for (uint32_t j = threadIdx.x; j < total; j += blockDim.x) { cand_slot[off + j] = ks[j]; cand_key[off + j] = __double2float_rd(kd[j]); }
+    for (uint32_t j = threadIdx.x; j < total; j += blockDim.x) put(j, ks[j], __double2float_rd(kd[j]));
 }
 
 // ---- candidate lists: Node::get (photonMap.cpp:71-92) run once per leaf with that leaf's query box -------------------------
