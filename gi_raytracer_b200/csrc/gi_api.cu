@@ -713,10 +713,12 @@ extern "C" int gi_photon_map_build(gi_ctx* ctx, const double* box6)
     M.pos4 = reinterpret_cast<double*>(base + h.off_pos); M.dircol = reinterpret_cast<double*>(base + h.off_dircol);
     if (n_kept) k_pm_payload<<<grid_for(n_kept, 256), 256, 0, ctx->stream>>>(M, n_kept);
     CK(cudaGetLastError());
-    // order every candidate list by distance from its leaf centre (the gather's early stop): short lists with small blocks,
-    // long ones with up to 96 KB of shared memory per block
+    // candidate records.  Lists the gather scans per thread (<= GI_GS_MAX_CANDS entries) are ordered by distance from their
+    // leaf centre (early stop); longer lists are streamed by whole warps and keep the DFS order: along a centre-ordered list
+    // of a large, nearly empty leaf the distances to an off-centre query keep FALLING, so every candidate would beat the
+    // running k-th and force a merge, while in DFS order only ~k ln(C/k) do
     if (n_cand) {
-        const uint32_t SHORT_LEN = 512, LONG_LEN = 8192;
+        const uint32_t SHORT_LEN = GI_GS_MAX_CANDS, LONG_LEN = GI_GS_MAX_CANDS;
         if (getenv("GI_TRACE_LAUNCHES")) {
             std::vector<uint32_t> hc(n_nodes);
             cudaMemcpy(hc.data(), cand_cnt, (size_t)n_nodes * 4, cudaMemcpyDeviceToHost);
@@ -725,11 +727,10 @@ extern "C" int gi_photon_map_build(gi_ctx* ctx, const double* box6)
             fprintf(stderr, "[gi] candidate lists: %u total entries, max %llu, >512: %llu, >8192: %llu (sum %llu), >65536: %llu\n", n_cand, (unsigned long long)mx, (unsigned long long)n512,
                     (unsigned long long)n8k, (unsigned long long)s8k, (unsigned long long)n64k);
         }
-        CK(cudaFuncSetAttribute(k_pm_cand_order, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(LONG_LEN * 12)));
         const uint32_t* cslot = ctx->w8.as<uint32_t>();
         double* crec = reinterpret_cast<double*>(base + h.off_cand_rec);
         k_pm_cand_order<<<n_nodes, 64, SHORT_LEN * 12, ctx->stream>>>(M.nodes, n_nodes, M.pos4, cand_off, cslot, crec, 0u, SHORT_LEN, LONG_LEN);
-        k_pm_cand_order<<<n_nodes, 256, LONG_LEN * 12, ctx->stream>>>(M.nodes, n_nodes, M.pos4, cand_off, cslot, crec, SHORT_LEN, 0xFFFFFFFFu, LONG_LEN);
+        k_pm_cand_order<<<n_nodes, 256, 0, ctx->stream>>>(M.nodes, n_nodes, M.pos4, cand_off, cslot, crec, SHORT_LEN, 0xFFFFFFFFu, LONG_LEN);
         CK(cudaGetLastError());
     }
     // leaves are counted on the host from the node records (also validates the build)
