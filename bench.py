@@ -231,12 +231,23 @@ def main():
             gd.reduce_accum(accum, 0)
         return st
 
+    # clocks / throttle reasons are sampled from the first warm-up step to the end of the timed region (same load throughout);
+    # nvidia-smi needs a moment to start, so warm-up continues (beyond W steps, at most 3 s) until it has delivered a sample
     clocks = ClockSampler(local)
-    for _ in range(Wm):
-        step_device()
-    barrier_sync()
     if rank == 0:
         clocks.start()
+    t_w = time.time()
+    done = 0
+    while True:
+        step_device()
+        done += 1
+        ctx.synchronize()
+        ready = torch.tensor([1 if (rank != 0 or clocks.lines or clocks.proc is None or time.time() - t_w > 3.0) else 0], device=dev)
+        if world > 1:
+            dist.broadcast(ready, src=0)
+        if done >= Wm and int(ready.item()):
+            break
+    barrier_sync()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record(stream)
     stats = []

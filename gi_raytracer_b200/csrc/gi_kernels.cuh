@@ -302,18 +302,10 @@ __global__ void k_pm_payload(DPMap M, uint32_t n_kept)
 
 // ---- K7: gather — RayTracer::samplePhotons (raytracer.h:532-579) over PhotonMap::getInRange (photonMap.cpp:50-92,115-134) ----
 // The candidate set of a query is a function of the LEAF that contains it: every photon of every leaf whose closed box
-// touches (leaf box +- EPSILON).  So the map carries, per leaf, the precomputed candidate list (photon slots in the
-// reference's DFS order) — built once on the device by running Node::get for every leaf (k_pm_cands).  A query is then:
-//   1. locate the leaf (getBounds).  Batch kernel: one THREAD per query walks down with child boxes derived from the
-//      parent box (the map is built by that very formula), one 16-byte topology load per level.  Single-query form
-//      (tail kernel): lanes 0..7 test the eight children.
-//   2. the warp loads the leaf's candidates into registers (<= 8 per lane) and computes the squared distances;
-//   3. SELECT, not sort: the k-th smallest distance is bracketed by bisection on the value — each step is one compare
-//      per register + one REDUX — until exactly k candidates lie at or below the pivot.  That set is the reference's
-//      partial_sort prefix.  (Exact distance ties across the k-th place, or > 256 candidates, take the streaming
-//      sort/merge path below, which orders by (distance, slot).)
-//   4. the k selected are compacted to one per lane through shared memory, ordered by ONE 32-wide bitonic sort, and the
-//      estimate is summed in ascending-distance order like the reference does.
+// touches (leaf box +- EPSILON).  So the map carries, per leaf, the precomputed candidate list — built once on the device by
+// running Node::get for every leaf (k_pm_cands, k_pm_cand_order).  Two forms of the query follow: the warp-cooperative one
+// right below (one query per warp: tail kernel and long lists) and the sorted wavefront form (one thread per query in leaf
+// order: k_gather_locate / k_gather_sorted / k_gather_heavy, further down).
 struct DGatherMap {
     const DNode* nodes; const double* pos4; const double* dircol; const uint32_t* pid; uint32_t n_nodes;
     const uint32_t* cand_off;    // [n_nodes + 1] start of each node's candidate list (only leaves have entries)
@@ -330,11 +322,6 @@ __device__ __forceinline__ Cand load_cand(const DGatherMap& M, uint32_t idx)
     Cand c; c.pos = mk3(a.x, a.y, b.x); c.slot = (uint32_t)__double2loint(b.y); c.key = __int_as_float(__double2hiint(b.y));
     return c;
 }
-#define GI_GATHER_REGS 8   // candidates per lane held in registers by the select path (8 x 32 = 256 per query)
-#ifndef GI_GATHER_MINB
-#define GI_GATHER_MINB 6   // resident blocks (of 4 warps) per SM asked of ptxas for k_gather: 6 -> 80 registers, no spills
-#endif
-
 // ordering of candidates: (distance^2, photon slot).  Exact distance ties between different photons are unordered in
 // the reference (std::partial_sort is unstable); the slot makes them deterministic here.
 __device__ __forceinline__ bool kv_less(double a, uint32_t ai, double b, uint32_t bi) { return a < b || (a == b && ai < bi); }
@@ -483,35 +470,6 @@ __device__ __noinline__ void gather_topk_stream(const DGatherMap& M, uint32_t of
     }
 }
 
-// ---- select: a pivot with exactly k of the register-held candidates at or below it ------------------------------------------
-// Pivots come from interpolating the counts at the bracket ends (photon density is close to uniform in d^2 on a surface);
-// every third step is a plain bisection so that the bracket always shrinks; the first pivot is the previous query's
-// threshold when that query sat in the same leaf (neighbouring pixels: nearly the same k-th distance).  NB = registers in
-// use (unused ones hold +inf): one DSETP + one add per register and one REDUX per step, no branches.
-template <int NB>
-__device__ __forceinline__ bool select_pivot(const double (&cd)[GI_GATHER_REGS], int k, uint32_t total, double lo, double hi, double first, double& thr)
-{
-    int clo = 0, chi = (int)total;
-    double pivot = first;
-    for (int it = 0; it < 96; it++) {
-        const double mid = lo + .5 * (hi - lo);
-        const bool inside = (pivot > lo) & (pivot < hi);
-        pivot = inside ? pivot : mid;
-        if (!((pivot > lo) & (pivot < hi))) return false;   // no double left between the bounds: a tie straddles the k-th place
-        int c = 0;
-#pragma unroll
-        for (int j = 0; j < NB; j++) c += cd[j] <= pivot ? 1 : 0;
-        c = __reduce_add_sync(0xffffffffu, c);
-        if (c == k) { thr = pivot; return true; }
-        const bool below = c < k;
-        lo = below ? pivot : lo; clo = below ? c : clo;
-        hi = below ? hi : pivot; chi = below ? chi : c;
-        const double ip = lo + (hi - lo) * (double)__fdividef((float)(k - clo) + .5f, (float)(chi - clo));
-        pivot = (it % 3 == 2) ? hi : ip;   // `hi` is not inside the bracket: the next step bisects
-    }
-    return false;
-}
-
 // ---- order: sort <= 32 (distance, slot) pairs held one per lane (lanes >= count hold +inf) -------------------------------------------
 // The bitonic network runs on ONE 32-bit word per lane: the distance bits, rebased to the smallest binade present and
 // shifted down to 26 bits (monotone in the distance), with the lane number in the low 5 bits — SHFL + min/max per stage.
@@ -543,85 +501,20 @@ __device__ __forceinline__ void warp_order32(double& d, uint32_t& sl, int count,
     if (__any_sync(0xffffffffu, inverted)) warp_sort32(d, sl, lane);
 }
 
-// One query at a known leaf, executed by a full warp; every lane returns the same rgb/total; lane l holds the slot of
-// the l-th nearest.  `sm` = 96 doubles of shared memory per warp (compaction scratch, then the ordered sum).  `csl` /
-// `csl_node` / `thr_cache` carry the candidate slots and the threshold of the previous query of this warp (consecutive
-// queries often share a leaf).
-__device__ __forceinline__ GatherOut gather_at_leaf(const DGatherMap& M, bool found, uint32_t node, d3 p, d3 dq, int k, int lane, double* sm,
-                                                    uint32_t (&csl)[GI_GATHER_REGS], uint32_t& csl_node, double& thr_cache, double delta = -1.0)
+// One query at a known leaf, executed by a full warp (tail kernel, long candidate lists): the list is streamed by
+// gather_topk_stream, then the estimate (raytracer.h:545-576) is summed over the count = min(k, total) nearest in ascending
+// distance order.  Every lane returns the same rgb/total; lane l holds the slot of the l-th nearest.  `sm` = 96 doubles of
+// shared memory per warp (batch scratch, then the ordered sum).
+__device__ __forceinline__ GatherOut gather_at_leaf(const DGatherMap& M, bool found, uint32_t node, d3 p, d3 dq, int k, int lane, double* sm, double delta = -1.0)
 {
     GatherOut out; out.rgb = mk3(0, 0, 0); out.total = 0; out.depth = 0; out.count = 0; out.best_slot = 0xFFFFFFFFu;
     double best_d = CUDART_INF; uint32_t best_sl = 0xFFFFFFFFu;   // sorted ascending across lanes
-    uint32_t total = 0;
-    if (found) {
-        const uint32_t off = __ldg(M.cand_off + node);
-        total = __ldg(M.cand_off + node + 1) - off;
-    }
+    uint32_t total = 0, off = 0;
+    if (found) { off = __ldg(M.cand_off + node); total = __ldg(M.cand_off + node + 1) - off; }
     const int count = (int)total < k ? (int)total : k;
-    if (total > 32u * GI_GATHER_REGS) gather_topk_stream(M, __ldg(M.cand_off + node), total, p, lane, delta, sm, best_d, best_sl);
-    else if (total > 0) {
-        const int nb = (int)((total + 31u) >> 5);
-        double cd[GI_GATHER_REGS];
-        const bool warm = csl_node == node;
-        csl_node = node;
-        {
-            const uint32_t off = __ldg(M.cand_off + node);
-#pragma unroll
-            for (int j = 0; j < GI_GATHER_REGS; j++) {
-                cd[j] = CUDART_INF; csl[j] = 0xFFFFFFFFu;
-                if (j < nb && (uint32_t)(j * 32 + lane) < total) { const Cand c = load_cand(M, off + j * 32 + lane); csl[j] = c.slot; cd[j] = len2(c.pos - p); }
-            }
-        }
-        bool sorted = false;
-        if (total <= (uint32_t)k) { best_d = cd[0]; best_sl = csl[0]; }   // k <= 32: everything is selected
-        else {
-            // bracket the k-th smallest distance between the binades of the smallest and the largest lane minimum: every
-            // lane that holds candidates has one at or below the upper bound, so >= min(32, total) >= k lie below it
-            double mn = cd[0];
-#pragma unroll
-            for (int j = 1; j < GI_GATHER_REGS; j++) mn = cd[j] < mn ? cd[j] : mn;
-            const unsigned hw = (unsigned)__double2hiint(mn);
-            const bool fin = hw < 0x7FF00000u;
-            const unsigned hmax = __reduce_max_sync(0xffffffffu, fin ? hw : 0u), hmin = __reduce_min_sync(0xffffffffu, fin ? hw : 0x7FF00000u);
-            const double hi = __hiloint2double((int)(hmax + 1u), 0), lo = __hiloint2double((int)hmin, 0);
-            const double first = (warm && thr_cache > lo && thr_cache < hi) ? thr_cache : lo + (hi - lo) * (double)fminf(0.9f, __fdividef(1.7f * ((float)k + .5f), (float)total));
-            double thr = 0; bool ok;
-            switch (nb) {
-            case 1: ok = select_pivot<1>(cd, k, total, lo, hi, first, thr); break;
-            case 2: ok = select_pivot<2>(cd, k, total, lo, hi, first, thr); break;
-            case 3: ok = select_pivot<3>(cd, k, total, lo, hi, first, thr); break;
-            case 4: ok = select_pivot<4>(cd, k, total, lo, hi, first, thr); break;
-            case 5: ok = select_pivot<5>(cd, k, total, lo, hi, first, thr); break;
-            case 6: ok = select_pivot<6>(cd, k, total, lo, hi, first, thr); break;
-            default: ok = select_pivot<8>(cd, k, total, lo, hi, first, thr); break;
-            }
-            if (!ok) { gather_topk_stream(M, __ldg(M.cand_off + node), total, p, lane, delta, sm, best_d, best_sl); sorted = true; }
-            else {
-                thr_cache = thr;
-                // compact the k selected to one per lane (their order is restored by warp_order32)
-                uint32_t* sms = reinterpret_cast<uint32_t*>(sm + 32);
-                int base = 0;
-                __syncwarp();
-#pragma unroll
-                for (int j = 0; j < GI_GATHER_REGS; j++) {
-                    if (j < nb) {
-                        const bool sel = cd[j] <= thr;
-                        const uint32_t m = __ballot_sync(0xffffffffu, sel);
-                        if (sel) { int pos = base + __popc(m & ((1u << lane) - 1u)); sm[pos] = cd[j]; sms[pos] = csl[j]; }
-                        base += __popc(m);
-                    }
-                }
-                __syncwarp();
-                if (lane < k) { best_d = sm[lane]; best_sl = sms[lane]; }
-                __syncwarp();
-            }
-        }
-        if (!sorted) warp_order32(best_d, best_sl, count, lane);
-    }
-    // radiance estimate (raytracer.h:545-576): sum over the count = min(k, total) nearest in ascending distance order;
-    // lanes 0..2 each add up one colour channel in that order
     double acc = 0;
     if (total > 0) {
+        gather_topk_stream(M, off, total, p, lane, delta, sm, best_d, best_sl);
         d3 term = mk3(0, 0, 0);
         if (lane < count && best_sl != 0xFFFFFFFFu) {
             const double2* dc = reinterpret_cast<const double2*>(M.dircol + 6 * (size_t)best_sl);
@@ -631,8 +524,8 @@ __device__ __forceinline__ GatherOut gather_at_leaf(const DGatherMap& M, bool fo
         __syncwarp();
         sm[lane] = term.x; sm[32 + lane] = term.y; sm[64 + lane] = term.z;
         __syncwarp();
-        // terms past `count` are +0.0 and leave the sum unchanged, so the loop is a fixed 32 steps of 16-byte loads; the
-        // division by pi*r^2 (raytracer.h:572-576) is done once, by the lane that owns the channel
+        // lanes 0..2 each add up one colour channel; terms past `count` are +0.0 and leave the sum unchanged, so the loop is a
+        // fixed 32 steps of 16-byte loads; the division by pi*r^2 is done once, by the lane that owns the channel
         const double2* s2 = reinterpret_cast<const double2*>(sm + 32 * (lane < 3 ? lane : 0));
 #pragma unroll
         for (int i = 0; i < 16; i++) { double2 v = s2[i]; acc += v.x; acc += v.y; }
@@ -649,57 +542,9 @@ __device__ __forceinline__ GatherOut gather_warp(const DGatherMap& M, d3 p, d3 d
 {
     uint32_t node, depth;
     bool found = pm_find_leaf(M, p, lane, node, depth);
-    uint32_t csl[GI_GATHER_REGS]; uint32_t csl_node = 0xFFFFFFFFu; double thr_cache = 0;
-    GatherOut g = gather_at_leaf(M, found, node, p, dq, k, lane, sm, csl, csl_node, thr_cache);
+    GatherOut g = gather_at_leaf(M, found, node, p, dq, k, lane, sm);
     g.depth = depth;
     return g;
-}
-
-// `qpw` (a power of two <= 32) consecutive queries per warp: lane l < qpw locates the leaf of query l with the thread-form
-// walk, then the warp serves the queries one after the other.  The host picks qpw = 32 for long queues (walk cost amortised
-// 32x, neighbouring queries reuse the candidate slots and the threshold) and smaller values for short queues, where
-// parallelism matters more.
-template <int WARPS>
-__global__ void __launch_bounds__(WARPS * 32, GI_GATHER_MINB) k_gather(DGatherMap M, size_t n, int qpw, const double* __restrict__ qpos, const double* __restrict__ qdir, int k,
-                                                                    double* __restrict__ rgb, uint32_t* __restrict__ knn, uint32_t* __restrict__ ncand,
-                                                                    const double* __restrict__ weight, double* __restrict__ accum, const uint32_t* __restrict__ accum_idx,
-                                                                    unsigned long long* work)
-{
-    __shared__ __align__(16) double s_sum[WARPS][96];
-    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-    const size_t q0 = (blockIdx.x * (size_t)WARPS + wib) * (size_t)qpw;
-    if (q0 >= n) return;
-    const size_t q = q0 + lane;
-    const bool have = lane < qpw && q < n;
-    uint32_t node = 0, depth = 0;
-    bool found = false;
-    if (have) found = pm_find_leaf_thread(M, ld3(qpos + 3 * q), node, depth);
-    const uint32_t found_mask = __ballot_sync(0xffffffffu, found);
-    const int nq = (int)(n - q0 < (size_t)qpw ? n - q0 : (size_t)qpw);
-    uint32_t w_total = 0, w_count = 0;   // warp-uniform tallies
-    uint32_t csl[GI_GATHER_REGS]; uint32_t csl_node = 0xFFFFFFFFu; double thr_cache = 0;
-    for (int i = 0; i < nq; i++) {
-        const size_t qi = q0 + i;
-        const d3 pi = ld3(qpos + 3 * qi), di = ld3(qdir + 3 * qi);   // warp-uniform (broadcast) loads, L1 hits after the walk
-        const uint32_t ni = __shfl_sync(0xffffffffu, node, i);
-        GatherOut g = gather_at_leaf(M, (found_mask >> i) & 1u, ni, pi, di, k, lane, s_sum[wib], csl, csl_node, thr_cache);
-        w_total += g.total; w_count += (uint32_t)g.count;
-        if (knn && lane < k) knn[qi * (size_t)k + lane] = (lane < g.count && g.best_slot != 0xFFFFFFFFu) ? __ldg(M.pid + g.best_slot) : GI_NO_HIT;
-        if (lane == 0) {
-            if (rgb) st3(rgb + 3 * qi, g.rgb);
-            if (ncand) ncand[qi] = g.total;
-            if (accum) {   // render pipeline: L[path] += weight * caustic
-                const size_t a = accum_idx[qi];
-                accum[3 * a] += weight[3 * qi] * g.rgb.x; accum[3 * a + 1] += weight[3 * qi + 1] * g.rgb.y; accum[3 * a + 2] += weight[3 * qi + 2] * g.rgb.z;
-            }
-        }
-    }
-    if (work) {
-        unsigned long long wd = have ? depth : 0;
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) wd += __shfl_down_sync(0xffffffffu, wd, o);
-        if (lane == 0) { atomicAdd(work, wd); atomicAdd(work + 1, (unsigned long long)w_total); atomicAdd(work + 2, (unsigned long long)w_count); }
-    }
 }
 
 // ---- K7, sorted form: queries ordered by leaf, one THREAD per query ------------------------------------------------------------
@@ -711,11 +556,9 @@ __global__ void __launch_bounds__(WARPS * 32, GI_GATHER_MINB) k_gather(DGatherMa
 //   k_gather_sorted   one thread per query, in leaf order.  The 32 lanes of a warp now sit in the same leaf (or two): they
 //                     run through the SAME candidate list in lockstep — the slot and position loads are warp-wide broadcasts
 //                     served by L1 — each against its own query point, with 32 independent dependency chains per warp.
-//                     SELECT is the same interpolation/bisection on "how many candidates lie at or below the pivot", one
-//                     pass over the list per step, all state in registers; the k selected are then insertion-sorted by
-//                     (distance, slot) into a per-thread column of shared memory ([k][thread]: conflict-free for any mix of
-//                     row indices) and summed in ascending order like the reference.  Exact distance ties across the k-th
-//                     place cannot be resolved by a pivot: those queries are handed to gather_at_leaf, one at a time.
+//                     The k nearest so far are a max-heap in a per-thread column of shared memory; the scan of the
+//                     (centre-ordered) list stops early; a heap sort orders the k for the sum (details at the kernel).
+//   k_gather_heavy    lists longer than GI_GS_MAX_CANDS: persistent warps stream them, 32 candidates per step.
 __global__ void k_gather_locate(DGatherMap M, uint32_t n, const double* __restrict__ qpos, uint32_t* __restrict__ qnode, uint32_t* __restrict__ hist, unsigned long long* work)
 {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -897,8 +740,7 @@ __global__ void __launch_bounds__(GI_WPB * 32) k_gather_heavy(DGatherMap M, cons
         const DNode nd = load_node(M.nodes, node);
         const double ex = nd.bmax[0] - nd.bmin[0], ey = nd.bmax[1] - nd.bmin[1], ez = nd.bmax[2] - nd.bmin[2];
         const double delta = .5 * sqrt(ex * ex + ey * ey + ez * ez) * (1.0 + 1e-9);
-        uint32_t csl[GI_GATHER_REGS]; uint32_t csl_node = 0xFFFFFFFFu; double thr_cache = 0;
-        GatherOut g = gather_at_leaf(M, true, node, p, dq, k, lane, s_sum[wib], csl, csl_node, thr_cache, delta);
+        GatherOut g = gather_at_leaf(M, true, node, p, dq, k, lane, s_sum[wib], delta);
         if (knn && lane < k) knn[(size_t)q * k + lane] = (lane < g.count && g.best_slot != 0xFFFFFFFFu) ? __ldg(M.pid + g.best_slot) : GI_NO_HIT;
         if (lane == 0) {
             if (rgb) st3(rgb + 3 * (size_t)q, g.rgb);
