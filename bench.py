@@ -344,7 +344,7 @@ def main():
         tp = os.path.join(ROOT, "profiles", "traffic.json")
         if os.path.exists(tp):
             try:
-                traffic = json.load(open(tp)).get(dom)
+                traffic = json.load(open(tp)).get(dom)   # DRAM bytes per frame of the dominant family, from the committed ncu captures
             except Exception:
                 traffic = None
         gather_bytes = bytes_gather(gwork[0], gwork[1], gwork[2], gwork[3])
