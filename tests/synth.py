@@ -69,14 +69,14 @@ def uv_sphere(path, center, radius, seg=20, rings=12):
     return len(faces)
 
 
-def cards(path, count=400, seed=11, area=6.0, h=0.9, y0=0.0):
+def cards(path, count=400, seed=11, area=6.0, h=0.9, y0=0.0, wscale=1.0):
     """Alpha cards: upright quads with random orientation (foliage stand-in); uv covers the full texture."""
     rng = np.random.RandomState(seed)
     verts, norms, uvs, faces = [], [], [(0, 0), (1, 0), (0, 1), (1, 1)], []
     for k in range(count):
         cx, cz = (rng.rand(2) - 0.5) * area
         ang = rng.rand() * math.pi
-        w = 0.25 + 0.35 * rng.rand(); hh = h * (0.5 + rng.rand())
+        w = (0.25 + 0.35 * rng.rand()) * wscale; hh = h * (0.5 + rng.rand())
         dx, dz = math.cos(ang) * w, math.sin(ang) * w
         n = (-math.sin(ang), 0.0, math.cos(ang))
         b = len(verts)
