@@ -585,10 +585,30 @@ extern "C" int gi_photon_trace(gi_ctx* ctx, int count, int max_depth, uint64_t s
     fam_reset(ctx, "photon_trace");
     cudaEvent_t e0 = get_event(ctx), e1 = get_event(ctx);
     cudaEventRecord(e0, ctx->stream);
+    uint64_t launches = 4;
     {
+        // rounds of `width` speculative tries per active slot (k_photon_round); width grows as the survivor list shrinks
         ScopedTimer t(ctx, "photon_trace");
-        GI_LAUNCH(k_photon_trace, grid_for(count, GI_BLOCK), GI_BLOCK, ctx->S, count, max_depth, seed, O);
-        
+        uint32_t* lists[2] = { ctx->w2.as<uint32_t>(), ctx->b_scan0.as<uint32_t>() };   // survivor lists (both buffers are reused by the compaction below)
+        uint32_t* n_out = reinterpret_cast<uint32_t*>(ctx->b_misc.as<unsigned long long>() + 4);
+        const uint32_t* in = nullptr;
+        uint32_t n_active = (uint32_t)slots;
+        int base_try = 0;
+        for (int round = 0; base_try < 500 && n_active > 0; round++) {
+            int width = 1;
+            while (width < 32 && (uint64_t)n_active * (uint64_t)(2 * width) <= (1u << 19)) width *= 2;
+            CK(cudaMemsetAsync(n_out, 0, 4, ctx->stream));
+            uint32_t* out = lists[round & 1];
+            GI_LAUNCH(k_photon_round, grid_for((size_t)n_active * width, GI_BLOCK), GI_BLOCK, ctx->S, count, max_depth, seed, base_try, width, n_active, in, out, n_out, O);
+            launches++;
+            CK(cudaGetLastError());
+            const uint32_t was = n_active;
+            CK(cudaMemcpyAsync(&n_active, n_out, 4, cudaMemcpyDeviceToHost, ctx->stream));
+            CK(cudaStreamSynchronize(ctx->stream));
+            if (getenv("GI_TRACE_LAUNCHES")) fprintf(stderr, "[gi] photon round %3d tries %3d..%3d active %9u -> %9u\n", round, base_try, base_try + width - 1, was, n_active);
+            in = out;
+            base_try += width;
+        }
     }
     CK(cudaGetLastError());
     // canonical (i, light) order: flags -> exclusive scan -> scatter
@@ -609,7 +629,7 @@ extern "C" int gi_photon_trace(gi_ctx* ctx, int count, int max_depth, uint64_t s
     if (n_stored) *n_stored = ctx->n_photons;
     ctx->work_host[8] = host[1];
     if (stats) {
-        stats->photon_tries = host[0]; stats->closest_rays = host[1]; stats->photons_stored = ctx->n_photons; stats->kernel_launches = 6; stats->total_ms = ms;
+        stats->photon_tries = host[0]; stats->closest_rays = host[1]; stats->photons_stored = ctx->n_photons; stats->kernel_launches = launches; stats->total_ms = ms;
         stats->trace_ms = ctx->fam["photon_trace"].ms; stats->closest_node_tests = ctx->work_host[0]; stats->closest_prim_tests = ctx->work_host[1];
     }
     return GI_OK;
@@ -900,7 +920,7 @@ static int render_device(gi_ctx* ctx, const gi_render_params* P, int x0, int y0,
     if (binning) { CK(ctx->b_binkey.reserve((size_t)chunk_cap * 4)); CK(ctx->b_binperm.reserve((size_t)chunk_cap * 4)); CK(ctx->b_binhist.reserve((size_t)GI_SORT_BINS * 4)); CK(ctx->b_bincur.reserve((size_t)GI_SORT_BINS * 4)); }
     d3 bin_min, bin_inv;
     bin_min.x = ctx->root_box[0]; bin_min.y = ctx->root_box[1]; bin_min.z = ctx->root_box[2];
-    bin_inv.x = 32.0 / std::max(ctx->root_box[3] - ctx->root_box[0], 1e-300); bin_inv.y = 32.0 / std::max(ctx->root_box[4] - ctx->root_box[1], 1e-300); bin_inv.z = 32.0 / std::max(ctx->root_box[5] - ctx->root_box[2], 1e-300);
+    bin_inv.x = (double)(1 << GI_BIN_AXIS_BITS) / std::max(ctx->root_box[3] - ctx->root_box[0], 1e-300); bin_inv.y = (double)(1 << GI_BIN_AXIS_BITS) / std::max(ctx->root_box[4] - ctx->root_box[1], 1e-300); bin_inv.z = (double)(1 << GI_BIN_AXIS_BITS) / std::max(ctx->root_box[5] - ctx->root_box[2], 1e-300);
     DQueue qa{ ctx->q_a[0].as<double>(), ctx->q_a[1].as<double>(), ctx->q_a[2].as<double>(), ctx->q_a[3].as<double>(), ctx->q_a[4].as<uint32_t>() };
     DQueue qb{ ctx->q_b[0].as<double>(), ctx->q_b[1].as<double>(), ctx->q_b[2].as<double>(), ctx->q_b[3].as<double>(), ctx->q_b[4].as<uint32_t>() };
     DHitList H{ ctx->hl[0].as<double>(), ctx->hl[1].as<double>(), ctx->hl[2].as<double>(), ctx->hl[3].as<double>(), ctx->hl[4].as<double>(), ctx->hl[5].as<double>(), ctx->hl[6].as<uint32_t>() };

@@ -216,6 +216,89 @@ __device__ __forceinline__ double child_entry(const PlaneT& T, int i, const DRay
     return tmin;
 }
 
+// entry distances of all eight implicit children at once.  The reference folds, per child, tmin = ((tmin0 (+) x) (+) y) (+) z with
+// a (+) b = b > a ? b : a, and tmax likewise with b < a (bbox.h:47-73; the per-axis early rejects equal one final test, see
+// child_entry).  Children share those prefixes: the near/far plane of each half is picked once per axis by the sign of the
+// inverse direction, the x-then-y prefix exists for 4 combinations, the full fold for 8 — the same operations in the same
+// order as eight separate slab tests, at a third of the instructions.  Child 7 = [mid, max] has its own far (or, for a
+// negative direction, near) planes.  t0c[i] = entry distance, or -1 when the child is absent or missed.
+#define GI_UP(a, b) ((b) > (a) ? (b) : (a))
+#define GI_DN(a, b) ((b) < (a) ? (b) : (a))
+__device__ __forceinline__ void children_entry(const DNode& nd, const DRay& r, double tmin0, double tmax0, double (&t0c)[8])
+{
+    PlaneT T;
+    plane_params(nd, r, T);
+    const bool sx = r.inv.x < 0.0, sy = r.inv.y < 0.0, sz = r.inv.z < 0.0;
+    // [0] lower half, [1] upper half, [2] child 7
+    const double nx[3] = { sx ? T.x[1] : T.x[0], sx ? T.x[2] : T.x[1], sx ? T.x[3] : T.x[1] }, fx[3] = { sx ? T.x[0] : T.x[1], sx ? T.x[1] : T.x[2], sx ? T.x[1] : T.x[3] };
+    const double ny[3] = { sy ? T.y[1] : T.y[0], sy ? T.y[2] : T.y[1], sy ? T.y[3] : T.y[1] }, fy[3] = { sy ? T.y[0] : T.y[1], sy ? T.y[1] : T.y[2], sy ? T.y[1] : T.y[3] };
+    const double nz[3] = { sz ? T.z[1] : T.z[0], sz ? T.z[2] : T.z[1], sz ? T.z[3] : T.z[1] }, fz[3] = { sz ? T.z[0] : T.z[1], sz ? T.z[1] : T.z[2], sz ? T.z[1] : T.z[3] };
+    double ex[2], lx[2];   // after the x axis
+#pragma unroll
+    for (int a = 0; a < 2; a++) { ex[a] = GI_UP(tmin0, nx[a]); lx[a] = GI_DN(tmax0, fx[a]); }
+    double exy[2][2], lxy[2][2];   // [x half][y half]
+#pragma unroll
+    for (int a = 0; a < 2; a++)
+#pragma unroll
+        for (int b = 0; b < 2; b++) { exy[a][b] = GI_UP(ex[a], ny[b]); lxy[a][b] = GI_DN(lx[a], fy[b]); }
+#pragma unroll
+    for (int i = 0; i < 7; i++) {   // bit0 = +x, bit1 = +z, bit2 = +y
+        const int bx = i & 1, bz = (i >> 1) & 1, by = (i >> 2) & 1;
+        const double en = GI_UP(exy[bx][by], nz[bz]), lv = GI_DN(lxy[bx][by], fz[bz]);
+        t0c[i] = ((nd.mask >> i) & 1u) && !(lv <= en) ? en : -1.0;
+    }
+    {
+        const double en = GI_UP(GI_UP(GI_UP(tmin0, nx[2]), ny[2]), nz[2]), lv = GI_DN(GI_DN(GI_DN(tmax0, fx[2]), fy[2]), fz[2]);
+        t0c[7] = ((nd.mask >> 7) & 1u) && !(lv <= en) ? en : -1.0;
+    }
+}
+
+// push the hit children (t0c[i] >= 0) far-to-near, ties with the higher child index first, so that they pop in ascending
+// (entry distance, child index) order — the reference's sorted leaf order (octree.cpp:297-300).  A line meets at
+// most four octants: up to four hits are insertion-sorted in registers; more (grazing edges) take the general selection loop.
+__device__ __forceinline__ void push_children_ordered(const DNode& nd, double (&t0c)[8], uint32_t* stack, int& sp)
+{
+    double h0 = 0, h1 = 0, h2 = 0, h3 = 0;   // sorted ascending; children arrive in index order, so ties stay in index order
+    int c0 = 0, c1 = 0, c2 = 0, c3 = 0, n = 0;
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+        const double t = t0c[i];
+        if (t >= 0.0) {
+            if (n < 4) {
+                // the new entry goes behind every entry <= it: shift the larger ones up
+                const bool b2 = n > 2 && t < h2, b1 = n > 1 && t < h1, b0 = n > 0 && t < h0;
+                if (b2) { h3 = h2; c3 = c2; }
+                if (b1) { h2 = h1; c2 = c1; }
+                if (b0) { h1 = h0; c1 = c0; }
+                if (b0) { h0 = t; c0 = i; }
+                else if (b1) { h1 = t; c1 = i; }
+                else if (b2) { h2 = t; c2 = i; }
+                else if (n == 3) { h3 = t; c3 = i; }
+                else if (n == 2) { h2 = t; c2 = i; }
+                else if (n == 1) { h1 = t; c1 = i; }
+                else { h0 = t; c0 = i; }
+            }
+            n++;
+        }
+    }
+    if (n <= 4) {
+        if (n > 3 && sp < GI_STACK_MAX) stack[sp++] = nd.child + __popc(nd.mask & ((1u << c3) - 1u));
+        if (n > 2 && sp < GI_STACK_MAX) stack[sp++] = nd.child + __popc(nd.mask & ((1u << c2) - 1u));
+        if (n > 1 && sp < GI_STACK_MAX) stack[sp++] = nd.child + __popc(nd.mask & ((1u << c1) - 1u));
+        if (n > 0 && sp < GI_STACK_MAX) stack[sp++] = nd.child + __popc(nd.mask & ((1u << c0) - 1u));
+        return;
+    }
+    for (;;) {
+        double bt = -1.0; int bi = -1;
+#pragma unroll
+        for (int i = 0; i < 8; i++) if (t0c[i] >= bt && t0c[i] >= 0.0) { bt = t0c[i]; bi = i; }
+        if (bi < 0) break;
+        if (sp < GI_STACK_MAX) stack[sp++] = nd.child + __popc(nd.mask & ((1u << bi) - 1u));
+#pragma unroll
+        for (int i = 0; i < 8; i++) if (i == bi) t0c[i] = -1.0;
+    }
+}
+
 __device__ __forceinline__ DNode load_node(const DNode* nodes, uint32_t i)
 {
     // 4 x 16-byte vector loads through the read-only path
@@ -398,12 +481,8 @@ __device__ __forceinline__ void trace_closest(const DScene& S, const DRay& r, ui
             // so that equal-distance children pop in child order)
             double t0c[8];
             n_node += __popc(nd.mask);
-            if (IMPL) {
-                PlaneT T;
-                plane_params(nd, r, T);
-#pragma unroll
-                for (int i = 0; i < 8; i++) t0c[i] = (nd.mask & (1u << i)) ? child_entry(T, i, r, 0.0, CUDART_INF) : -1.0;
-            } else {
+            if (IMPL) children_entry(nd, r, 0.0, CUDART_INF, t0c);
+            else {
                 uint32_t c = nd.child;
 #pragma unroll
                 for (int i = 0; i < 8; i++) {
@@ -415,15 +494,7 @@ __device__ __forceinline__ void trace_closest(const DScene& S, const DRay& r, ui
                     }
                 }
             }
-            for (;;) {
-                double bt = -1.0; int bi = -1;
-#pragma unroll
-                for (int i = 0; i < 8; i++) if (t0c[i] >= bt && t0c[i] >= 0.0) { bt = t0c[i]; bi = i; }
-                if (bi < 0) break;
-                if (sp < GI_STACK_MAX) stack[sp++] = nd.child + __popc(nd.mask & ((1u << bi) - 1u));
-#pragma unroll
-                for (int i = 0; i < 8; i++) if (i == bi) t0c[i] = -1.0;
-            }
+            push_children_ordered(nd, t0c, stack, sp);
             if (sp == 0) { have_leaf = false; break; }
             ni = stack[--sp];
             nd = load_node(S.nodes, ni);
@@ -485,12 +556,12 @@ __device__ __forceinline__ bool trace_visible(const DScene& S, const DRay& r, do
             uint32_t c = nd.child;
             n_node += __popc(nd.mask);
             if (IMPL) {
-                PlaneT T;
-                plane_params(nd, r, T);
+                double t0c[8];
+                children_entry(nd, r, 0.0, tmax, t0c);
 #pragma unroll
                 for (int i = 0; i < 8; i++) {
                     if (nd.mask & (1u << i)) {
-                        if (child_entry(T, i, r, 0.0, tmax) >= 0.0 && sp < GI_STACK_MAX) stack[sp++] = c;
+                        if (t0c[i] >= 0.0 && sp < GI_STACK_MAX) stack[sp++] = c;
                         c++;
                     }
                 }

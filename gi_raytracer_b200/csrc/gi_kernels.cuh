@@ -849,24 +849,29 @@ __global__ void __launch_bounds__(WARPS * 32) k_pm_cands(const DNode* __restrict
 // permutation — histogram with REDs, exclusive scan, scatter of indices — which the next k_bounce reads its rays through.
 // Order inside a bin is arbitrary (atomics); no result depends on queue order: every path owns its accumulator and its
 // PRNG key.
-#define GI_SORT_BITS 18
+#ifndef GI_BIN_AXIS_BITS
+#define GI_BIN_AXIS_BITS 6   // cells per axis = 2^bits (C2 frame: 4 bits 30.8 ms, 5 29.8, 6 29.5, 7 29.9)
+#endif
+#define GI_SORT_BITS (3 * GI_BIN_AXIS_BITS + 3)
 #define GI_SORT_BINS (1u << GI_SORT_BITS)
-__device__ __forceinline__ uint32_t spread5(uint32_t v)   // abcde -> a00b00c00d00e
+__device__ __forceinline__ uint32_t spread3(uint32_t v)   // ...cba -> ..c00b00a (Morton interleave of up to 10 bits)
 {
-    v &= 31u;
-    v = (v | (v << 8)) & 0x100Fu;
-    v = (v | (v << 4)) & 0x10C3u;
-    v = (v | (v << 2)) & 0x1249u;
+    v &= 0x3FFu;
+    v = (v | (v << 16)) & 0x030000FFu;
+    v = (v | (v << 8)) & 0x0300F00Fu;
+    v = (v | (v << 4)) & 0x030C30C3u;
+    v = (v | (v << 2)) & 0x09249249u;
     return v;
 }
 __global__ void k_bin_keys(uint32_t n, const double* __restrict__ org, const double* __restrict__ dir, d3 bmin, d3 inv_ext, uint32_t* __restrict__ key, uint32_t* __restrict__ hist)
 {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
+    const int C = (1 << GI_BIN_AXIS_BITS) - 1;
     d3 o = ld3(org + 3 * (size_t)i), d = ld3(dir + 3 * (size_t)i);
     int cx = (int)((o.x - bmin.x) * inv_ext.x), cy = (int)((o.y - bmin.y) * inv_ext.y), cz = (int)((o.z - bmin.z) * inv_ext.z);
-    cx = cx < 0 ? 0 : (cx > 31 ? 31 : cx); cy = cy < 0 ? 0 : (cy > 31 ? 31 : cy); cz = cz < 0 ? 0 : (cz > 31 ? 31 : cz);
-    uint32_t k = ((spread5((uint32_t)cx) | (spread5((uint32_t)cy) << 1) | (spread5((uint32_t)cz) << 2)) << 3) | (d.x < 0 ? 1u : 0u) | (d.y < 0 ? 2u : 0u) | (d.z < 0 ? 4u : 0u);
+    cx = cx < 0 ? 0 : (cx > C ? C : cx); cy = cy < 0 ? 0 : (cy > C ? C : cy); cz = cz < 0 ? 0 : (cz > C ? C : cz);
+    uint32_t k = ((spread3((uint32_t)cx) | (spread3((uint32_t)cy) << 1) | (spread3((uint32_t)cz) << 2)) << 3) | (d.x < 0 ? 1u : 0u) | (d.y < 0 ? 2u : 0u) | (d.z < 0 ? 4u : 0u);
     key[i] = k;
     atomicAdd(hist + k, 1u);
 }
@@ -1139,66 +1144,102 @@ __global__ void k_resolve(size_t n3, const double* accum, int spp, uint8_t* rgb8
 // ---- K5: photon emission and tracing (raytracer.h:582-715) ----------------------------------------------------------------------------
 struct DPhotonOut { double* ph; uint8_t* stored; unsigned long long* tries; unsigned long long* traces; unsigned long long* work; };
 
+// one emission try of photon index i at light li (raytracer.h:604-695): true when a photon was stored into `out`
 template <bool FULL, bool IMPL>
-__global__ void __launch_bounds__(GI_BLOCK) k_photon_trace(DScene S, int count, int max_depth, uint64_t seed, DPhotonOut O)
+__device__ __forceinline__ bool photon_try(const DScene& S, int count, int max_depth, uint64_t seed, int i, uint32_t li, int tries, d3& ph_pos, d3& ph_dir, d3& ph_col, unsigned long long& n_traces,
+                                           uint32_t& wn, uint32_t& wp)
 {
-    int i = blockIdx.x * blockDim.x + threadIdx.x;
-    unsigned long long my_tries = 0, my_traces = 0;
-    uint32_t wn = 0, wp = 0;
-    for (uint32_t li = 0; li < S.n_lights && i < count; li++) {
-        const gi_light& l = S.lights[li];
-        int tries = 0; bool stored = false;
-        while (!stored && tries < 500) {                                                        // :602
-            uint64_t path = PHOTON_PATH_BIT | ((uint64_t)li << 48) | (uint64_t)((uint64_t)i * 500u + (uint64_t)tries);
-            float sx = halton_sample(S, 0, (uint32_t)(i * 500 + tries));                        // :604-605
-            float sy = halton_sample(S, 1, (uint32_t)(i * 500 + tries));
-            d3 pos = light_point_in_range(l, sx, sy);                                           // :612
-            float du = (float)fmod(gi_rand(seed, path, 0, SITE(SITE_PH_DIR_U, 0)) + 5 * i, 1.0);
-            float dv = (float)fmod(gi_rand(seed, path, 0, SITE(SITE_PH_DIR_V, 0)) + 13 * i, 1.0);
-            d3 dir = sphere_cap_cos(normalize3(pos - ld3(l.pos)), du, dv, 2, l.angle);          // :613
-            DRay r = make_ray(pos, dir);
-            d3 col = ld3(l.col) * ((1.0 / count) * .5 * l.angle);                               // :618
-            int depth = 0; bool term = false, isCaustic = false;
-            DHit h;
-            trace_closest<FULL, IMPL>(S, r, seed, path, 0, h, wn, wp); my_traces++;
-            if (h.prim == GI_NO_HIT) { tries++; continue; }                                     // :626-630
-            uint32_t cur = h.prim;
-            d3 hit = mk3(0, 0, 0);
-            while (depth < max_depth && !term) {                                                // :633
-                double roughness = S.mats[S.prim_mat[cur]].roughness;
-                if (roughness < 0.1) {
-                    trace_closest<FULL, IMPL>(S, r, seed, path, (uint64_t)(depth + 1), h, wn, wp); my_traces++;   // :640
-                    if (h.prim == GI_NO_HIT) { term = true; continue; }
-                    cur = h.prim;
-                    d3 norm; double tu, tv;
-                    hit_surface(S, r, h, FULL, hit, norm, tu, tv);
-                    const gi_material& m = S.mats[S.prim_mat[cur]];
-                    roughness = m.roughness;
-                    d3 f = mk3(0, 0, 0), contrib = mk3(0, 0, 0); double offset = GI_D_SHADOW_BIAS;
-                    double su = fmod(gi_rand(seed, path, (uint64_t)(depth + 1), SITE(SITE_PH_SEC_U, 0)) + 5 * i, 1.0);
-                    double sv = fmod(gi_rand(seed, path, (uint64_t)(depth + 1), SITE(SITE_PH_SEC_V, 0)) + 13 * i, 1.0);
-                    d3 color = tex_get(S, m.diffuse_tex, tu, tv);
-                    d3 refDir = secondary_ray(S, m, r, norm, tu, tv, su, sv, color, f, contrib, offset, seed, path, (uint64_t)(depth + 1));   // :656
-                    col = col * f;                                                              // :677
-                    r = make_ray(hit + norm * offset, refDir);                                  // :679-680
-                    isCaustic = true;
-                }
-                if (depth > 0 && isCaustic && roughness >= 0.1) {                               // :685-692
-                    size_t slot = (size_t)i * S.n_lights + li;
-                    double* out = O.ph + 9 * slot;
-                    st3(out, hit); st3(out + 3, r.d); st3(out + 6, col);
-                    O.stored[slot] = 1;
-                    term = true; stored = true;
-                }
-                depth++;
-            }
-            tries++;
+    const gi_light& l = S.lights[li];
+    uint64_t path = PHOTON_PATH_BIT | ((uint64_t)li << 48) | (uint64_t)((uint64_t)i * 500u + (uint64_t)tries);
+    float sx = halton_sample(S, 0, (uint32_t)(i * 500 + tries));                        // :604-605
+    float sy = halton_sample(S, 1, (uint32_t)(i * 500 + tries));
+    d3 pos = light_point_in_range(l, sx, sy);                                           // :612
+    float du = (float)fmod(gi_rand(seed, path, 0, SITE(SITE_PH_DIR_U, 0)) + 5 * i, 1.0);
+    float dv = (float)fmod(gi_rand(seed, path, 0, SITE(SITE_PH_DIR_V, 0)) + 13 * i, 1.0);
+    d3 dir = sphere_cap_cos(normalize3(pos - ld3(l.pos)), du, dv, 2, l.angle);          // :613
+    DRay r = make_ray(pos, dir);
+    d3 col = ld3(l.col) * ((1.0 / count) * .5 * l.angle);                               // :618
+    int depth = 0; bool term = false, isCaustic = false;
+    DHit h;
+    trace_closest<FULL, IMPL>(S, r, seed, path, 0, h, wn, wp); n_traces++;
+    if (h.prim == GI_NO_HIT) return false;                                              // :626-630
+    uint32_t cur = h.prim;
+    d3 hit = mk3(0, 0, 0);
+    while (depth < max_depth && !term) {                                                // :633
+        double roughness = S.mats[S.prim_mat[cur]].roughness;
+        if (roughness < 0.1) {
+            trace_closest<FULL, IMPL>(S, r, seed, path, (uint64_t)(depth + 1), h, wn, wp); n_traces++;   // :640
+            if (h.prim == GI_NO_HIT) { term = true; continue; }
+            cur = h.prim;
+            d3 norm; double tu, tv;
+            hit_surface(S, r, h, FULL, hit, norm, tu, tv);
+            const gi_material& m = S.mats[S.prim_mat[cur]];
+            roughness = m.roughness;
+            d3 f = mk3(0, 0, 0), contrib = mk3(0, 0, 0); double offset = GI_D_SHADOW_BIAS;
+            double su = fmod(gi_rand(seed, path, (uint64_t)(depth + 1), SITE(SITE_PH_SEC_U, 0)) + 5 * i, 1.0);
+            double sv = fmod(gi_rand(seed, path, (uint64_t)(depth + 1), SITE(SITE_PH_SEC_V, 0)) + 13 * i, 1.0);
+            d3 color = tex_get(S, m.diffuse_tex, tu, tv);
+            d3 refDir = secondary_ray(S, m, r, norm, tu, tv, su, sv, color, f, contrib, offset, seed, path, (uint64_t)(depth + 1));   // :656
+            col = col * f;                                                              // :677
+            r = make_ray(hit + norm * offset, refDir);                                  // :679-680
+            isCaustic = true;
         }
-        my_tries += (unsigned long long)tries;
+        if (depth > 0 && isCaustic && roughness >= 0.1) {                               // :685-692
+            ph_pos = hit; ph_dir = r.d; ph_col = col;
+            return true;
+        }
+        depth++;
     }
-    // warp-aggregated tallies
+    return false;
+}
+
+// The reference gives every photon index up to 500 emission tries (raytracer.h:602) and stores the FIRST that lands on a
+// caustic caster (one try in ten on caustics, one in forty on glass).  A thread that loops over its tries keeps 31 finished
+// lanes waiting for the unluckiest one; and one try can be slow (a photon ray that misses everything walks every leaf along
+// the whole line: the closest-hit rule has no early exit for a miss), so a kernel per try pays that latency 500 times.
+// Tries are therefore run in ROUNDS of `width` speculative tries per active (photon index, light) slot: `width` adjacent
+// lanes make tries base .. base+width-1 of the same slot at once, the lowest successful try wins (ballot + ffs) and writes
+// the photon, slots without a winner are compacted (ballot + prefix popcount) into the next round's list.  All active slots
+// have consumed the same number of tries, so the survivor list is all the state there is.  The host grows `width` as the
+// list shrinks (1, 2, 4 .. 32) and keeps ~half a million lanes busy: ~25 rounds instead of 500.  Tries and traces are
+// tallied as the sequential loop would have made them (up to and including the winner); same try, same counter-PRNG keys,
+// same photons.
+template <bool FULL, bool IMPL>
+__global__ void __launch_bounds__(GI_BLOCK, GI_MINB) k_photon_round(DScene S, int count, int max_depth, uint64_t seed, int base_try, int width, uint32_t n_active, const uint32_t* __restrict__ in_list,
+                                                                  uint32_t* __restrict__ out_list, uint32_t* __restrict__ n_out, DPhotonOut O)
+{
+    const uint32_t gt = blockIdx.x * blockDim.x + threadIdx.x;
+    const unsigned lane = threadIdx.x & 31u;
+    const uint32_t j = gt / (uint32_t)width;       // active-list entry
+    const int k = (int)(gt % (uint32_t)width);      // which of the round's tries
+    const int tries = base_try + k;
+    unsigned long long my_traces = 0;
+    uint32_t wn = 0, wp = 0, slot = 0;
+    bool stored = false;
+    d3 pp = mk3(0, 0, 0), pd = pp, pc = pp;
+    const bool live = j < n_active && tries < 500;
+    if (j < n_active) slot = in_list ? in_list[j] : j;
+    if (live) {
+        const int i = (int)(slot / S.n_lights); const uint32_t li = slot % S.n_lights;
+        stored = photon_try<FULL, IMPL>(S, count, max_depth, seed, i, li, tries, pp, pd, pc, my_traces, wn, wp);
+    }
+    // the slot's lanes are adjacent: lowest successful try wins
+    const unsigned sm = __ballot_sync(0xffffffffu, stored);
+    const unsigned gshift = lane & ~(unsigned)(width - 1), gmask = width == 32 ? 0xffffffffu : ((1u << width) - 1u);
+    const unsigned gbits = (sm >> gshift) & gmask;
+    const int winner = gbits ? __ffs(gbits) - 1 : -1;
+    if (stored && k == winner) { double* out = O.ph + 9 * (size_t)slot; st3(out, pp); st3(out + 3, pd); st3(out + 6, pc); O.stored[slot] = 1; }
+    const bool counted = live && (winner < 0 || k <= winner);       // the tries the sequential loop would have made
+    const bool retry = j < n_active && k == 0 && winner < 0 && base_try + width < 500;
+    const unsigned rm = __ballot_sync(0xffffffffu, retry);
+    uint32_t base = 0;
+    if (lane == 0 && rm) base = atomicAdd(n_out, (uint32_t)__popc(rm));
+    base = __shfl_sync(0xffffffffu, base, 0);
+    if (retry) out_list[base + __popc(rm & ((1u << lane) - 1u))] = slot;
+    unsigned long long my_tries = counted ? 1ull : 0ull;
+    if (!counted) { my_traces = 0; wn = 0; wp = 0; }
     for (int o = 16; o > 0; o >>= 1) { my_tries += __shfl_down_sync(0xffffffffu, my_tries, o); my_traces += __shfl_down_sync(0xffffffffu, my_traces, o); }
-    if ((threadIdx.x & 31) == 0) { atomicAdd(O.tries, my_tries); atomicAdd(O.traces, my_traces); }
+    if (lane == 0 && my_tries) { atomicAdd(O.tries, my_tries); atomicAdd(O.traces, my_traces); }
     tally2(O.work, wn, wp);
 }
 
