@@ -58,6 +58,11 @@ struct gi_ctx {
     bool no_implicit = false;      // GI_NO_IMPLICIT_BOXES at gi_create: always load child boxes (for A/B tests)
     int trace_mode = 0;            // 0: thread per ray, 1: warp per ray (API batch kernels; GI_TRACE_MODE)
     uint32_t tail_threshold = 32768; // queues smaller than this finish in the tail megakernel (GI_TAIL_THRESHOLD, 0 = off)
+    int bounce_mode = 0;             // 0: pick per scene, 1: always one ray per thread, 2: always persistent warps with refetch (GI_BOUNCE_MODE)
+    double nodes_per_ray = 0;        // node tests per closest-hit ray of the last frame rendered with the current scene
+    // per-scene choice between the two bounce kernels: the first full-size frame runs the form guessed from the tree, the
+    // second the other one, later frames the faster of the two (bounce ms per closest-hit ray)
+    uint64_t tune_sig = 0; int tune_frames = 0; double tune_cost[2] = { 0, 0 };
     uint32_t bin_threshold = 65536;  // queues at least this long are binned by origin cell / direction octant before the next bounce (GI_BIN_THRESHOLD, 0 = off)
     unsigned long long work_host[16] = { 0 };   // [0,1] closest nodes/prims, [2,3] any-hit, [4..6] gather depth/cand/sel, [8] rays, [9] shadow rays, [10] queries
     // timing
@@ -221,6 +226,7 @@ extern "C" int gi_create(int device, gi_ctx** out)
     if (const char* e = getenv("GI_TRACE_MODE")) ctx->trace_mode = atoi(e);
     if (const char* e = getenv("GI_TAIL_THRESHOLD")) ctx->tail_threshold = (uint32_t)strtoul(e, nullptr, 10);
     if (const char* e = getenv("GI_BIN_THRESHOLD")) ctx->bin_threshold = (uint32_t)strtoul(e, nullptr, 10);
+    if (const char* e = getenv("GI_BOUNCE_MODE")) ctx->bounce_mode = atoi(e);
     *out = ctx;
     return GI_OK;
 }
@@ -388,6 +394,12 @@ extern "C" int gi_scene_upload(gi_ctx* ctx, const gi_scene_desc* sc)
     S.full = full ? 1u : 0u;
     S.implicit_boxes = implicit ? 1u : 0u;
     for (int k = 0; k < 6; k++) ctx->root_box[k] = sc->node_box[k];
+    ctx->nodes_per_ray = 0;
+    {
+        uint64_t sig = gi_mix64(((uint64_t)sc->n_nodes << 32) ^ sc->n_refs) ^ gi_mix64(((uint64_t)sc->n_prims << 20) ^ sc->n_lights);
+        for (int k = 0; k < 6; k++) { uint64_t b; std::memcpy(&b, &sc->node_box[k], 8); sig = gi_mix64(sig ^ b); }
+        if (sig != ctx->tune_sig) { ctx->tune_sig = sig; ctx->tune_frames = 0; ctx->tune_cost[0] = ctx->tune_cost[1] = 0; }
+    }
     ctx->has_scene = true;   // photons / photon map are independent state and survive a re-upload (the reference keeps its
     return GI_OK;            // map across run() calls, raytracer.h:61); rebuild it explicitly when the geometry changed
 }
@@ -913,7 +925,7 @@ static int render_device(gi_ctx* ctx, const gi_render_params* P, int x0, int y0,
     for (int b = 0; b < 5; b++) CK(ctx->hl[b].reserve((size_t)chunk_cap * 24));
     CK(ctx->hl[5].reserve((size_t)chunk_cap * 8)); CK(ctx->hl[6].reserve((size_t)chunk_cap * 4));
     CK(ctx->ps[0].reserve((size_t)chunk_cap * 4)); CK(ctx->ps[1].reserve((size_t)chunk_cap * 8)); CK(ctx->ps[2].reserve((size_t)chunk_cap * 24));
-    CK(ctx->b_cnt.reserve(sizeof(DCounters)));
+    CK(ctx->b_cnt.reserve(sizeof(DCounters))); CK(ctx->b_misc.reserve(64));
     CK(ctx->b_tail.reserve(sizeof(DTailCounters)));
     CK(cudaMemsetAsync(ctx->b_tail.p, 0, sizeof(DTailCounters), ctx->stream));
     const bool binning = ctx->bin_threshold > 0 && chunk_cap >= ctx->bin_threshold;
@@ -928,6 +940,15 @@ static int render_device(gi_ctx* ctx, const gi_render_params* P, int x0, int y0,
     DCounters* C = ctx->b_cnt.as<DCounters>();
     DFrame F = make_frame(ctx, P->width, P->height, x0, y0, x1, y1);
     const bool have_map = ctx->has_map && ctx->pm_kept > 0;
+    // long, uneven walks (deep trees): persistent warps with ray refetch; short ones: one ray per thread, launch per queue.
+    // Decided from the node tests per closest-hit ray of the previous frame of this scene (first frame: from the tree size).
+    const bool guess = ctx->S.n_nodes > 200000u;
+    const bool tunable = ctx->bounce_mode == 0 && total_paths >= (1u << 20);   // small calls neither explore nor count
+    bool persistent = ctx->bounce_mode == 2 || (ctx->bounce_mode == 0 && guess);
+    if (tunable) {
+        if (ctx->tune_frames == 1) persistent = !guess;
+        else if (ctx->tune_frames >= 2) persistent = ctx->tune_cost[1] < ctx->tune_cost[0];
+    }
     uint64_t n_closest = 0, n_shadow = 0, n_gather = 0, launches = 0;
     for (const char* f : { "bounce", "direct", "gather", "tail", "bin" }) fam_reset(ctx, f);
     CK(cudaMemsetAsync(work_ptr(ctx, 0), 0, 8 * sizeof(unsigned long long), ctx->stream));
@@ -953,9 +974,13 @@ static int render_device(gi_ctx* ctx, const gi_render_params* P, int x0, int y0,
                 break;
             }
             CK(cudaMemsetAsync(C, 0, sizeof(DCounters), ctx->stream));
+            CK(cudaMemsetAsync(ctx->b_misc.p, 0, 4, ctx->stream));   // the persistent warps' ray counter
             {
                 ScopedTimer t(ctx, "bounce");
-                GI_LAUNCH(k_bounce, grid_for(n_active, GI_BLOCK), GI_BLOCK, ctx->S, *P, depth, n_active, in, perm, out, H, PS, C, work_ptr(ctx, 0));
+                if (persistent) {
+                    const unsigned grid = std::min<unsigned>(grid_for(n_active, GI_BLOCK), 148u * GI_MINB);
+                    GI_LAUNCH(k_bounce_p, grid, GI_BLOCK, ctx->S, *P, depth, n_active, in, perm, out, H, PS, C, work_ptr(ctx, 0), ctx->b_misc.as<uint32_t>());
+                } else GI_LAUNCH(k_bounce, grid_for(n_active, GI_BLOCK), GI_BLOCK, ctx->S, *P, depth, n_active, in, perm, out, H, PS, C, work_ptr(ctx, 0));
             }
             CK(cudaGetLastError());
             DCounters hc;
@@ -1013,6 +1038,11 @@ static int render_device(gi_ctx* ctx, const gi_render_params* P, int x0, int y0,
     float ms = 0; cudaEventElapsedTime(&ms, e0, e1);
     ctx->event_pool.push_back(e0); ctx->event_pool.push_back(e1);
     n_closest += tc.closest; n_shadow += tc.shadow; n_gather += tc.gathers;
+    if (n_closest) ctx->nodes_per_ray = (double)(ctx->work_host[0] + tc.nodes_c) / (double)n_closest;
+    if (tunable && ctx->tune_frames < 2 && n_closest > tc.closest) {
+        ctx->tune_cost[persistent ? 1 : 0] = ctx->fam["bounce"].ms / (double)(n_closest - tc.closest);
+        ctx->tune_frames++;
+    }
     ctx->work_host[0] += tc.nodes_c; ctx->work_host[1] += tc.prims_c; ctx->work_host[2] += tc.nodes_s; ctx->work_host[3] += tc.prims_s;
     ctx->work_host[4] += tc.g_depth; ctx->work_host[5] += tc.g_cand; ctx->work_host[6] += tc.g_sel;
     if (stats) {

@@ -122,7 +122,7 @@ __device__ __forceinline__ float halton_sample(const DScene& S, uint32_t dim, ui
     if (dim >= 256) return 0.f;
     DHaltonDim D = S.halton_dims[dim];
     const uint16_t* T = S.halton_tab + D.table_off;
-    uint32_t sum = 0, idx = index, mult = 1;
+    uint32_t sum = 0, idx = index;
     // digit block j (least significant first) is weighted by block^(n-1-j): accumulate with Horner from the top instead
     // of the reference's explicit constants — identical u32 arithmetic (no overflow: the total is < 2^32)
     uint32_t blk[8];
@@ -130,7 +130,6 @@ __device__ __forceinline__ float halton_sample(const DScene& S, uint32_t dim, ui
     for (int j = 0; j < 8; j++) {
         if (j < (int)D.nblocks) { blk[j] = T[idx % D.block]; idx /= D.block; } else blk[j] = 0;
     }
-    (void)mult;
 #pragma unroll
     for (int j = 0; j < 8; j++)
         if (j < (int)D.nblocks) sum = sum * D.block + blk[j];
@@ -258,7 +257,7 @@ __device__ __forceinline__ void children_entry(const DNode& nd, const DRay& r, d
 // most four octants: up to four hits are insertion-sorted in registers; more (grazing edges) take the general selection loop.
 __device__ __forceinline__ void push_children_ordered(const DNode& nd, double (&t0c)[8], uint32_t* stack, int& sp)
 {
-    double h0 = 0, h1 = 0, h2 = 0, h3 = 0;   // sorted ascending; children arrive in index order, so ties stay in index order
+    double h0 = 0, h1 = 0, h2 = 0;           // sorted ascending (the fourth distance is never compared again); children arrive in index order, so ties stay in index order
     int c0 = 0, c1 = 0, c2 = 0, c3 = 0, n = 0;
 #pragma unroll
     for (int i = 0; i < 8; i++) {
@@ -267,13 +266,13 @@ __device__ __forceinline__ void push_children_ordered(const DNode& nd, double (&
             if (n < 4) {
                 // the new entry goes behind every entry <= it: shift the larger ones up
                 const bool b2 = n > 2 && t < h2, b1 = n > 1 && t < h1, b0 = n > 0 && t < h0;
-                if (b2) { h3 = h2; c3 = c2; }
+                if (b2) c3 = c2;
                 if (b1) { h2 = h1; c2 = c1; }
                 if (b0) { h1 = h0; c1 = c0; }
                 if (b0) { h0 = t; c0 = i; }
                 else if (b1) { h1 = t; c1 = i; }
                 else if (b2) { h2 = t; c2 = i; }
-                else if (n == 3) { h3 = t; c3 = i; }
+                else if (n == 3) c3 = i;
                 else if (n == 2) { h2 = t; c2 = i; }
                 else if (n == 1) { h1 = t; c1 = i; }
                 else { h0 = t; c0 = i; }
@@ -454,22 +453,31 @@ struct DHit {
     d3 n;              // cone normal (cones only)
 };
 
-template <bool FULL, bool IMPL>
-__device__ __forceinline__ void trace_closest(const DScene& S, const DRay& r, uint64_t seed, uint64_t path, uint64_t depth, DHit& out, uint32_t& n_node, uint32_t& n_prim)
+// The walk is resumable: its state is (stack, TraceState, out).  trace_begin tests the root, trace_walk pops leaves until the
+// ray is done (stack empty, or the stop rule fired) — or, with BAIL, until fewer than `min_active` lanes of the warp are still
+// walking (*warp_active, a shared-memory counter each lane decrements when its ray is done), so that a persistent kernel can
+// hand the idle lanes new rays (k_bounce).
+struct TraceState { int sp; bool term; double best_d2, cur_tu, cur_tv; };
+
+__device__ __forceinline__ bool trace_begin(const DScene& S, const DRay& r, DHit& out, TraceState& st, uint32_t* stack, uint32_t& n_node)
 {
-    uint32_t stack[GI_STACK_MAX];
-    int sp = 0;
+    st.sp = 0; st.term = false; st.best_d2 = 0;
+    st.cur_tu = 0; st.cur_tv = 0;   // `uv` local of RayTracer::trace: survives across candidates (raytracer.h:385)
     out.prim = GI_NO_HIT; out.t = 0; out.u = 0; out.v = 0; out.tu = 0; out.tv = 0; out.n = mk3(0, 0, 0);
-    double best_d2 = 0;
-    double cur_tu = 0, cur_tv = 0;  // `uv` local of RayTracer::trace: survives across candidates (raytracer.h:385)
-    if (S.n_nodes == 0) return;
-    {
-        DNode root = load_node(S.nodes, 0);
-        n_node++;
-        if (box_entry(root.bmin, root.bmax, r, 0.0, CUDART_INF) < 0.0) return;
-        stack[sp++] = 0;
-    }
-    bool term = false;
+    if (S.n_nodes == 0) return false;
+    DNode root = load_node(S.nodes, 0);
+    n_node++;
+    if (box_entry(root.bmin, root.bmax, r, 0.0, CUDART_INF) < 0.0) return false;
+    stack[st.sp++] = 0;
+    return true;
+}
+
+template <bool FULL, bool IMPL, bool BAIL>
+__device__ __forceinline__ void trace_walk(const DScene& S, const DRay& r, uint64_t seed, uint64_t path, uint64_t depth, DHit& out, TraceState& st, uint32_t* stack, uint32_t& n_node,
+                                           uint32_t& n_prim, volatile int* warp_active = nullptr, int min_active = 0)
+{
+    int sp = st.sp;
+    bool term = st.term;
     // "while-while": every lane first walks interior nodes until a leaf is on top (the warp re-converges after that
     // inner loop), then all lanes test primitives together — instead of mixing leaf work and interior work in one loop.
     while (sp > 0 && !term) {
@@ -499,37 +507,51 @@ __device__ __forceinline__ void trace_closest(const DScene& S, const DRay& r, ui
             ni = stack[--sp];
             nd = load_node(S.nodes, ni);
         }
-        if (!have_leaf) break;
-        const DLeafRef* refs = S.refs + nd.prim_off;
-        n_prim += nd.prim_cnt;
-        for (uint32_t k = 0; k < nd.prim_cnt; k++) {
-            const double2* rp = reinterpret_cast<const double2*>(refs + k);
-            double g[9];
-            double2 a0 = __ldg(rp), a1 = __ldg(rp + 1), a2 = __ldg(rp + 2), a3 = __ldg(rp + 3);
-            g[0] = a0.x; g[1] = a0.y; g[2] = a1.x; g[3] = a1.y; g[4] = a2.x; g[5] = a2.y; g[6] = a3.x; g[7] = a3.y;
-            uint4 tail = __ldg(reinterpret_cast<const uint4*>(rp + 4));
-            g[8] = __hiloint2double((int)tail.y, (int)tail.x);
-            uint32_t prim = tail.z, flags = tail.w;
-            double t, u = 0, v = 0; d3 cn = mk3(0, 0, 0);
-            bool ok;
-            uint32_t kind = LF_KIND(flags);
-            if (kind == GI_PRIM_TRIANGLE) { t = tri_hit(g, r, u, v); ok = t > 0; }
-            else if (kind == GI_PRIM_SPHERE) ok = sphere_hit(g, r, t);
-            else ok = cone_hit(g, S.prim_nrm + 9 * (size_t)prim, r, t, cn);
-            if (!ok) continue;
-            d3 hit = r.o + r.d * t;
-            if (FULL) {
-                if (flags & LF_WRITES_UV) prim_uv_at(S, prim, hit, u, v, cur_tu, cur_tv);
-                if ((flags & LF_ALPHA) && !alpha_pass(S, prim, ni, cur_tu, cur_tv, seed, path, depth, SITE_ALPHA_TRACE)) continue;
-            }
-            double d2 = len2(hit - r.o);
-            if (out.prim == GI_NO_HIT || d2 < best_d2) {
-                out.prim = prim; out.t = t; out.u = u; out.v = v; out.n = cn; best_d2 = d2;
-                if (FULL) { out.tu = cur_tu; out.tv = cur_tv; }
-                if (box_contains(nd.bmin, nd.bmax, hit)) term = true;
+        if (have_leaf) {
+            const DLeafRef* refs = S.refs + nd.prim_off;
+            n_prim += nd.prim_cnt;
+            for (uint32_t k = 0; k < nd.prim_cnt; k++) {
+                const double2* rp = reinterpret_cast<const double2*>(refs + k);
+                double g[9];
+                double2 a0 = __ldg(rp), a1 = __ldg(rp + 1), a2 = __ldg(rp + 2), a3 = __ldg(rp + 3);
+                g[0] = a0.x; g[1] = a0.y; g[2] = a1.x; g[3] = a1.y; g[4] = a2.x; g[5] = a2.y; g[6] = a3.x; g[7] = a3.y;
+                uint4 tail = __ldg(reinterpret_cast<const uint4*>(rp + 4));
+                g[8] = __hiloint2double((int)tail.y, (int)tail.x);
+                uint32_t prim = tail.z, flags = tail.w;
+                double t, u = 0, v = 0; d3 cn = mk3(0, 0, 0);
+                bool ok;
+                uint32_t kind = LF_KIND(flags);
+                if (kind == GI_PRIM_TRIANGLE) { t = tri_hit(g, r, u, v); ok = t > 0; }
+                else if (kind == GI_PRIM_SPHERE) ok = sphere_hit(g, r, t);
+                else ok = cone_hit(g, S.prim_nrm + 9 * (size_t)prim, r, t, cn);
+                if (!ok) continue;
+                d3 hit = r.o + r.d * t;
+                if (FULL) {
+                    if (flags & LF_WRITES_UV) prim_uv_at(S, prim, hit, u, v, st.cur_tu, st.cur_tv);
+                    if ((flags & LF_ALPHA) && !alpha_pass(S, prim, ni, st.cur_tu, st.cur_tv, seed, path, depth, SITE_ALPHA_TRACE)) continue;
+                }
+                double d2 = len2(hit - r.o);
+                if (out.prim == GI_NO_HIT || d2 < st.best_d2) {
+                    out.prim = prim; out.t = t; out.u = u; out.v = v; out.n = cn; st.best_d2 = d2;
+                    if (FULL) { out.tu = st.cur_tu; out.tv = st.cur_tv; }
+                    if (box_contains(nd.bmin, nd.bmax, hit)) term = true;
+                }
             }
         }
+        if (BAIL) {
+            if (sp == 0 || term) atomicSub((int*)warp_active, 1);   // this lane's ray is done
+            else if (*warp_active < min_active) break;             // too few lanes still walking: go and fetch rays
+        }
     }
+    st.sp = sp; st.term = term;
+}
+
+template <bool FULL, bool IMPL>
+__device__ __forceinline__ void trace_closest(const DScene& S, const DRay& r, uint64_t seed, uint64_t path, uint64_t depth, DHit& out, uint32_t& n_node, uint32_t& n_prim)
+{
+    uint32_t stack[GI_STACK_MAX];
+    TraceState st;
+    if (trace_begin(S, r, out, st, stack, n_node)) trace_walk<FULL, IMPL, false>(S, r, seed, path, depth, out, st, stack, n_node, n_prim);
 }
 
 // ---- any hit: RayTracer::visible (raytracer.h:280-319) over Octree::Node::intersect (octree.cpp:256-282) -------------------------

@@ -30,7 +30,7 @@ for name in (sys.argv[1:] or list(CFG)):
     P = render_params(w, h, spp, max_depth=depth, seed=1)
     acc = torch.zeros((w * h, 3), dtype=torch.float64, device="cuda")
     best = None
-    for rep in range(2):
+    for rep in range(3):   # frames 1 and 2 try the two bounce-kernel forms, frame 3 runs the faster one
         st = ctx.render_tile_dev(P, 0, 0, w, h, 0, spp, acc.data_ptr())
         if best is None or st.total_ms < best.total_ms:
             best = st

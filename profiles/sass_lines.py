@@ -42,10 +42,11 @@ def main(rep, sym, top=40):
     hdr_i = next(i for i, r in enumerate(rows) if r and r[0] == "Address")
     hdr = rows[hdr_i]
     ia, ii, isamp = hdr.index("Address"), hdr.index("Instructions Executed"), hdr.index("# Samples")
+    it = hdr.index("Thread Instructions Executed")
     lm = line_map(sym)
     body = [r for r in rows[hdr_i + 1:] if len(r) > isamp and r[ia].startswith("0x")]
     base = int(body[0][ia], 16)
-    per_line, per_op = defaultdict(lambda: [0, 0]), defaultdict(int)
+    per_line, per_op = defaultdict(lambda: [0, 0, 0]), defaultdict(int)
     tot_i = tot_s = 0
     for r in body:
         off = int(r[ia], 16) - base
@@ -53,13 +54,14 @@ def main(rep, sym, top=40):
         loc, ins = lm.get(off, (("?", 0), r[1].strip()))
         per_line[loc][0] += n
         per_line[loc][1] += s
+        per_line[loc][2] += int(r[it] or 0)
         per_op[ins.split()[0].lstrip("@!P0123456789 ") if not ins.startswith("@") else ins.split()[1]] += n
         tot_i += n
         tot_s += s
     print(f"total warp instructions {tot_i}, stall samples {tot_s}")
-    print("--- by source line (instructions, share, stall-sample share)")
+    print("--- by source line (warp instructions, share, stall-sample share, active lanes per instruction)")
     src_cache = {}
-    for loc, (n, s) in sorted(per_line.items(), key=lambda kv: -kv[1][0])[:top]:
+    for loc, (n, s, tn) in sorted(per_line.items(), key=lambda kv: -kv[1][0])[:top]:
         text = ""
         if loc and loc[0] != "?":
             p = os.path.join(ROOT, "gi_raytracer_b200", "csrc", loc[0])
@@ -67,7 +69,7 @@ def main(rep, sym, top=40):
                 src_cache[p] = open(p).read().splitlines()
             if p in src_cache and 0 < loc[1] <= len(src_cache[p]):
                 text = src_cache[p][loc[1] - 1].strip()[:90]
-        print(f"{loc[0] if loc else '?'}:{loc[1] if loc else 0:<5d} {n:>14d} {100 * n / tot_i:5.1f}% {100 * s / max(tot_s, 1):5.1f}%  {text}")
+        print(f"{loc[0] if loc else '?'}:{loc[1] if loc else 0:<5d} {n:>14d} {100 * n / tot_i:5.1f}% {100 * s / max(tot_s, 1):5.1f}% {tn / max(n, 1):5.1f}  {text}")
     print("--- by opcode")
     for op, n in sorted(per_op.items(), key=lambda kv: -kv[1])[:25]:
         print(f"{op:24s} {n:>14d} {100 * n / tot_i:5.1f}%")

@@ -442,6 +442,32 @@ def test_ray_binning_does_not_change_results(lib_built, synth_dir, monkeypatch):
         c0.close(); c1.close()
 
 
+def test_persistent_bounce_kernel_equals_launch_per_queue(lib_built, synth_dir, monkeypatch):
+    """k_bounce_p (persistent warps, finished lanes refetch rays) must give the frame, ray counts and work tallies of k_bounce
+    (one ray per thread) bit for bit: only the order in which rays are processed differs."""
+    from gi_raytracer_b200.capi import Context
+    monkeypatch.setenv("GI_BOUNCE_MODE", "1")
+    c1 = Context(0)
+    monkeypatch.setenv("GI_BOUNCE_MODE", "2")
+    c2 = Context(0)
+    try:
+        for name, depth in (("mixed", 10), ("atrium", 5), ("cards", 4)):
+            sc = _load(name, synth_dir)
+            outs = []
+            for c in (c1, c2):
+                c.upload_scene(sc)
+                c.photon_trace(2500 if name == "mixed" else 0, 5, seed=2)
+                c.photon_map_build(None)
+                P = render_params(72, 40, 3, max_depth=depth, seed=29)
+                outs.append(c.render_tile(P, 0, 0, 72, 40, 0, 3))
+            (a, sa), (b, sb) = outs
+            assert bits_equal(a, b), f"{name}: {np.abs(a - b).max()}"
+            for f in ("closest_rays", "shadow_rays", "gathers", "closest_node_tests", "closest_prim_tests", "shadow_node_tests", "shadow_prim_tests", "gather_candidates"):
+                assert getattr(sa, f) == getattr(sb, f), f
+    finally:
+        c1.close(); c2.close()
+
+
 def test_implicit_child_boxes_equal_loaded_boxes(lib_built, synth_dir, monkeypatch):
     """Traversal with child boxes derived from the parent (the default for trees built by Octree::partition) must equal the
     traversal that loads every child box, bit for bit; reference-built trees must qualify for the implicit path."""
