@@ -54,10 +54,11 @@ struct gi_ctx {
     DGatherMap G{};
     // workspaces
     DevBuf w0, w1, w2, w3, w4, w5, w6, w7, w8, w9;           // API staging
-    DevBuf q_a[5], q_b[5], hl[7], ps[3], b_cnt, b_accum, b_scan0, b_scan1, b_misc, b_work, b_tail, b_binkey, b_binperm, b_binhist, b_bincur, b_gnode, b_gperm, b_ghist, b_gcur, b_gheavy;
+    DevBuf q_a[5], q_b[5], hl[7], ps[4], tq[5], b_cnt, b_accum, b_scan0, b_scan1, b_misc, b_work, b_tail, b_binkey, b_binperm, b_binhist, b_bincur, b_gnode, b_gperm, b_ghist, b_gcur, b_gheavy;
     bool no_implicit = false;      // GI_NO_IMPLICIT_BOXES at gi_create: always load child boxes (for A/B tests)
     int trace_mode = 0;            // 0: thread per ray, 1: warp per ray (API batch kernels; GI_TRACE_MODE)
     uint32_t tail_threshold = 32768; // queues smaller than this finish in the tail megakernel (GI_TAIL_THRESHOLD, 0 = off)
+    int tail_mode = 0;               // tail gathers: 0 queued and served by one gather pipeline run, 1 inline in the tail kernel (GI_TAIL_MODE)
     int bounce_mode = 0;             // 0: pick per scene, 1: always one ray per thread, 2: always persistent warps with refetch (GI_BOUNCE_MODE)
     double nodes_per_ray = 0;        // node tests per closest-hit ray of the last frame rendered with the current scene
     // per-scene choice between the two bounce kernels: the first full-size frame runs the form guessed from the tree, the
@@ -227,6 +228,7 @@ extern "C" int gi_create(int device, gi_ctx** out)
     if (const char* e = getenv("GI_TAIL_THRESHOLD")) ctx->tail_threshold = (uint32_t)strtoul(e, nullptr, 10);
     if (const char* e = getenv("GI_BIN_THRESHOLD")) ctx->bin_threshold = (uint32_t)strtoul(e, nullptr, 10);
     if (const char* e = getenv("GI_BOUNCE_MODE")) ctx->bounce_mode = atoi(e);
+    if (const char* e = getenv("GI_TAIL_MODE")) ctx->tail_mode = atoi(e);
     *out = ctx;
     return GI_OK;
 }
@@ -245,6 +247,7 @@ extern "C" void gi_destroy(gi_ctx* ctx)
     for (auto& b : ctx->q_b) b.release();
     for (auto& b : ctx->hl) b.release();
     for (auto& b : ctx->ps) b.release();
+    for (auto& b : ctx->tq) b.release();
     for (auto& t : ctx->pending) { cudaEventDestroy(t.a); cudaEventDestroy(t.b); }
     for (auto& e : ctx->event_pool) cudaEventDestroy(e);
     cudaStreamDestroy(ctx->stream);
@@ -924,7 +927,7 @@ static int render_device(gi_ctx* ctx, const gi_render_params* P, int x0, int y0,
     CK(ctx->q_a[4].reserve((size_t)chunk_cap * 4)); CK(ctx->q_b[4].reserve((size_t)chunk_cap * 4));
     for (int b = 0; b < 5; b++) CK(ctx->hl[b].reserve((size_t)chunk_cap * 24));
     CK(ctx->hl[5].reserve((size_t)chunk_cap * 8)); CK(ctx->hl[6].reserve((size_t)chunk_cap * 4));
-    CK(ctx->ps[0].reserve((size_t)chunk_cap * 4)); CK(ctx->ps[1].reserve((size_t)chunk_cap * 8)); CK(ctx->ps[2].reserve((size_t)chunk_cap * 24));
+    CK(ctx->ps[0].reserve((size_t)chunk_cap * 4)); CK(ctx->ps[1].reserve((size_t)chunk_cap * 8)); CK(ctx->ps[2].reserve((size_t)chunk_cap * 24)); CK(ctx->ps[3].reserve((size_t)chunk_cap * 24));
     CK(ctx->b_cnt.reserve(sizeof(DCounters))); CK(ctx->b_misc.reserve(64));
     CK(ctx->b_tail.reserve(sizeof(DTailCounters)));
     CK(cudaMemsetAsync(ctx->b_tail.p, 0, sizeof(DTailCounters), ctx->stream));
@@ -936,7 +939,7 @@ static int render_device(gi_ctx* ctx, const gi_render_params* P, int x0, int y0,
     DQueue qa{ ctx->q_a[0].as<double>(), ctx->q_a[1].as<double>(), ctx->q_a[2].as<double>(), ctx->q_a[3].as<double>(), ctx->q_a[4].as<uint32_t>() };
     DQueue qb{ ctx->q_b[0].as<double>(), ctx->q_b[1].as<double>(), ctx->q_b[2].as<double>(), ctx->q_b[3].as<double>(), ctx->q_b[4].as<uint32_t>() };
     DHitList H{ ctx->hl[0].as<double>(), ctx->hl[1].as<double>(), ctx->hl[2].as<double>(), ctx->hl[3].as<double>(), ctx->hl[4].as<double>(), ctx->hl[5].as<double>(), ctx->hl[6].as<uint32_t>() };
-    DPathState PS{ ctx->ps[0].as<uint32_t>(), ctx->ps[1].as<uint64_t>(), ctx->ps[2].as<double>() };
+    DPathState PS{ ctx->ps[0].as<uint32_t>(), ctx->ps[1].as<uint64_t>(), ctx->ps[2].as<double>(), ctx->ps[3].as<double>() };
     DCounters* C = ctx->b_cnt.as<DCounters>();
     DFrame F = make_frame(ctx, P->width, P->height, x0, y0, x1, y1);
     const bool have_map = ctx->has_map && ctx->pm_kept > 0;
@@ -964,12 +967,35 @@ static int render_device(gi_ctx* ctx, const gi_render_params* P, int x0, int y0,
         const uint32_t* perm = nullptr;
         for (int depth = 0; n_active > 0 && depth <= P->max_depth; depth++) {
             if (depth > 0 && n_active < ctx->tail_threshold) {
-                // few paths left: one warp per path runs them to the end inside one kernel
-                ScopedTimer t(ctx, "tail");
-                CK(cudaMemsetAsync(&ctx->b_tail.as<DTailCounters>()->next, 0, 4, ctx->stream));
-                const unsigned tail_grid = std::min<unsigned>(grid_for(n_active, GI_WPB), 148u * 3u);   // 3 blocks of 4 warps fit per SM at 168 registers
-                GI_LAUNCH(k_tail, tail_grid, GI_WPB * 32, ctx->S, ctx->G, have_map ? 1 : 0, *P, depth, n_active, in, PS, ctx->b_tail.as<DTailCounters>());
-                launches++;
+                // few paths left: one warp per path runs them to the end inside one kernel; their gathers are queued and served
+                // by one gather pipeline run afterwards (GI_TAIL_MODE=1: gathers inline)
+                DTailQ Q{};
+                const int last_gather_depth = std::min(P->max_depth, P->caustic_max_depth);
+                Q.qmax = ctx->tail_mode == 0 && have_map && last_gather_depth >= depth ? (uint32_t)(last_gather_depth - depth + 1) : 0u;
+                const size_t slots = (size_t)n_active * Q.qmax;
+                if (Q.qmax) {
+                    if (slots > 0xFFFFFFF0ull) return fail(ctx, GI_ERR_INVALID, "too many tail gather slots");
+                    for (int b = 0; b < 4; b++) CK(ctx->tq[b].reserve(slots * 24));
+                    CK(ctx->tq[4].reserve((size_t)n_active * 4));
+                    Q.pos = ctx->tq[0].as<double>(); Q.dir = ctx->tq[1].as<double>(); Q.w = ctx->tq[2].as<double>(); Q.rgb = ctx->tq[3].as<double>(); Q.count = ctx->tq[4].as<uint32_t>();
+                }
+                {
+                    ScopedTimer t(ctx, "tail");
+                    CK(cudaMemsetAsync(&ctx->b_tail.as<DTailCounters>()->next, 0, 4, ctx->stream));
+                    const unsigned tail_grid = std::min<unsigned>(grid_for(n_active, GI_WPB), 148u * 3u);   // 3 blocks of 4 warps fit per SM at 168 registers
+                    GI_LAUNCH(k_tail, tail_grid, GI_WPB * 32, ctx->S, ctx->G, have_map ? 1 : 0, *P, depth, n_active, in, PS, ctx->b_tail.as<DTailCounters>(), Q);
+                    launches++;
+                }
+                if (Q.qmax) {
+                    {
+                        ScopedTimer t(ctx, "gather");
+                        int rcg = run_gather(ctx, (uint32_t)slots, Q.pos, Q.dir, P->k_photons, Q.rgb, nullptr, nullptr, nullptr, nullptr, nullptr, &launches);
+                        if (rcg != GI_OK) return rcg;
+                    }
+                    ScopedTimer t(ctx, "tail");
+                    k_tail_caustic<<<grid_for(n_active, 256), 256, 0, ctx->stream>>>(n_active, in, PS, Q);
+                    launches++;
+                }
                 CK(cudaGetLastError());
                 break;
             }
@@ -999,7 +1025,7 @@ static int render_device(gi_ctx* ctx, const gi_render_params* P, int x0, int y0,
                     n_gather += hc.n_hits;   // samplePhotons is called whether or not photons exist (raytracer.h:258)
                     if (have_map) {
                         ScopedTimer t(ctx, "gather");
-                        int rcg = run_gather(ctx, hc.n_hits, H.p, H.refdir, P->k_photons, nullptr, nullptr, nullptr, H.wcaustic, PS.L, H.path, &launches);
+                        int rcg = run_gather(ctx, hc.n_hits, H.p, H.refdir, P->k_photons, nullptr, nullptr, nullptr, H.wcaustic, PS.Lc, H.path, &launches);
                         if (rcg != GI_OK) return rcg;
                     }
                 }
@@ -1026,7 +1052,7 @@ static int render_device(gi_ctx* ctx, const gi_render_params* P, int x0, int y0,
                 perm = ctx->b_binperm.as<uint32_t>();
             }
         }
-        k_accumulate<<<grid_for(npx, 256), 256, 0, ctx->stream>>>(c0, n, npx, PS.L, accum_dev);
+        k_accumulate<<<grid_for(npx, 256), 256, 0, ctx->stream>>>(c0, n, npx, PS.L, PS.Lc, accum_dev);
         launches++;
         CK(cudaGetLastError());
     }
@@ -1052,7 +1078,8 @@ static int render_device(gi_ctx* ctx, const gi_render_params* P, int x0, int y0,
         const unsigned long long* w = ctx->work_host;
         stats->closest_node_tests = w[0]; stats->closest_prim_tests = w[1]; stats->shadow_node_tests = w[2]; stats->shadow_prim_tests = w[3];
         stats->gather_leaf_depth = w[4]; stats->gather_candidates = w[5]; stats->gather_selected = w[6];
-        stats->tail_closest_rays = tc.closest; stats->tail_shadow_rays = tc.shadow; stats->tail_gathers = tc.gathers;
+        stats->tail_closest_rays = tc.closest; stats->tail_shadow_rays = tc.shadow;
+        stats->tail_gathers = (ctx->tail_mode == 1 || !have_map) ? tc.gathers : 0;   // queued tail gathers are served (and tallied) by the gather pipeline
         stats->tail_closest_node_tests = tc.nodes_c; stats->tail_closest_prim_tests = tc.prims_c; stats->tail_shadow_node_tests = tc.nodes_s; stats->tail_shadow_prim_tests = tc.prims_s;
         stats->tail_gather_leaf_depth = tc.g_depth; stats->tail_gather_candidates = tc.g_cand; stats->tail_gather_selected = tc.g_sel;
         stats->bin_ms = ctx->fam["bin"].ms;

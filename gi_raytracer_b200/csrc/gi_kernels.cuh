@@ -384,7 +384,7 @@ __device__ __forceinline__ bool pm_find_leaf(const DGatherMap& M, d3 p, int lane
 __device__ __forceinline__ bool pm_find_leaf_thread(const DGatherMap& M, d3 p, uint32_t& node, uint32_t& depth)
 {
     node = 0; depth = 0;
-    if (M.n_nodes == 0) return false;
+    if (M.n_nodes == 0 || !(p.x < CUDART_INF)) return false;   // +inf marks an unused query slot (k_tail_t)
     DNode root = load_node(M.nodes, 0);
     double lo[3] = { root.bmin[0], root.bmin[1], root.bmin[2] }, hi[3] = { root.bmax[0], root.bmax[1], root.bmax[2] };
     const double pp[3] = { p.x, p.y, p.z };
@@ -895,7 +895,10 @@ struct DHitList {
     double* rough;    // roughness
     uint32_t* path;
 };
-struct DPathState { uint32_t* sample; uint64_t* key; double* L; };
+// per path: Halton index, PRNG key, and the radiance sum in two parts — L takes the ambient / emissive / direct terms in bounce
+// order, Lc the caustic terms in bounce order; the path's radiance is L + Lc.  (Keeping the caustic terms apart lets the tail
+// hand its gathers to one batched gather run without changing the order of any sum.)
+struct DPathState { uint32_t* sample; uint64_t* key; double* L; double* Lc; };
 struct DCounters { uint32_t n_next, n_hits; unsigned long long closest, shadow, gathers; };
 
 template <bool FULL, bool IMPL>
@@ -1120,10 +1123,20 @@ __global__ void __launch_bounds__(GI_BLOCK, GI_MINB) k_direct(DScene S, gi_rende
 // ---- the tail: once few paths are left, one warp takes one path to its end (closest hit, shading, shadow rays, gather and
 // the next bounce all inside the kernel), so a frame does not pay ~65 x 3 nearly empty launches with a host round trip
 // each.  Arithmetic and the order in which terms are added to L[path] are those of k_bounce / k_direct / k_gather.
+// ---- batched tail gathers ---------------------------------------------------------------------------------------------------------
+// The tail does not make its gathers inline: every gather query of a tail path goes into the path's own run of slots (one
+// slot per remaining gather depth), ONE gather pipeline run then serves all tail queries (leaf-ordered, thread per query —
+// instead of a warp streaming one candidate list at a time in the middle of a path), and k_tail_caustic adds weight x
+// estimate to Lc[path] in bounce order.  This keeps the latency chain of a deep path to closest hit + shading + shadow ray and
+// takes the gather code out of the tail kernel (ncu showed it starved for instructions: 45 KB of code, ~10 warps per SM).
+// (A one-THREAD-per-path tail was measured too: 14.6 ms instead of 4.2 — the tail is bound by the latency of its deepest
+// paths, and a warp walking one ray cooperatively has a third of the per-bounce latency of a thread.)
+struct DTailQ { double* pos; double* dir; double* w; double* rgb; uint32_t* count; uint32_t qmax; };
+
 struct DTailCounters { unsigned long long closest, shadow, gathers, nodes_c, prims_c, nodes_s, prims_s, g_depth, g_cand, g_sel; unsigned int next; unsigned int pad; };
 
 template <bool FULL, bool IMPL>
-__global__ void __launch_bounds__(GI_WPB * 32) k_tail(DScene S, DGatherMap G, int have_map, gi_render_params P, int depth0, uint32_t n, DQueue in, DPathState PS, DTailCounters* TC)
+__global__ void __launch_bounds__(GI_WPB * 32) k_tail(DScene S, DGatherMap G, int have_map, gi_render_params P, int depth0, uint32_t n, DQueue in, DPathState PS, DTailCounters* TC, DTailQ Q)
 {
     __shared__ uint32_t s_stack[GI_WPB][GI_STACK_MAX];
     __shared__ double s_sum[GI_WPB][96];
@@ -1139,7 +1152,8 @@ __global__ void __launch_bounds__(GI_WPB * 32) k_tail(DScene S, DGatherMap G, in
     DRay r = ray_as_stored(ld3(in.o + 3 * (size_t)i), ld3(in.d + 3 * (size_t)i));
     d3 T = ld3(in.T + 3 * (size_t)i), contrib = ld3(in.contrib + 3 * (size_t)i);
     const uint64_t key = PS.key[path]; const uint32_t sample = PS.sample[path];
-    d3 L = ld3(PS.L + 3 * (size_t)path);
+    d3 L = ld3(PS.L + 3 * (size_t)path), Lc = ld3(PS.Lc + 3 * (size_t)path);
+    uint32_t nq = 0;   // gather queries queued by this path
     unsigned long long c_closest = 0, c_shadow = 0, c_gather = 0, g_depth = 0, g_cand = 0, g_sel = 0;
     uint32_t nc = 0, pc = 0, ns = 0, ps = 0;
     for (int depth = depth0; depth <= P.max_depth; depth++) {
@@ -1187,11 +1201,17 @@ __global__ void __launch_bounds__(GI_WPB * 32) k_tail(DScene S, DGatherMap G, in
         // caustic estimate (k_gather)
         if (depth <= P.caustic_max_depth) {
             c_gather++;
-            if (have_map) {
+            if (have_map && Q.qmax) {   // queued for the batched gather run
+                if (lane == 0 && nq < Q.qmax) {
+                    const size_t s = (size_t)i * Q.qmax + nq;
+                    st3(Q.pos + 3 * s, hp); st3(Q.dir + 3 * s, refDir); st3(Q.w + 3 * s, cont ? wdir : mk3(0, 0, 0));
+                }
+                nq++;
+            } else if (have_map) {
                 GatherOut g = gather_warp(G, hp, refDir, P.k_photons, lane, s_sum[wib]);
                 g_depth += g.depth; g_cand += g.total; g_sel += (unsigned long long)g.count;
                 d3 wc = cont ? wdir : mk3(0, 0, 0);
-                L = L + wc * g.rgb;
+                Lc = Lc + wc * g.rgb;
             }
         }
         if (!cont) break;
@@ -1199,12 +1219,30 @@ __global__ void __launch_bounds__(GI_WPB * 32) k_tail(DScene S, DGatherMap G, in
         r = make_ray(hp + hn * offset, refDir);
     }
     if (lane == 0) {
-        st3(PS.L + 3 * (size_t)path, L);
+        st3(PS.L + 3 * (size_t)path, L); st3(PS.Lc + 3 * (size_t)path, Lc);
+        if (have_map && Q.qmax) {
+            Q.count[i] = nq < Q.qmax ? nq : Q.qmax;
+            for (uint32_t k = nq; k < Q.qmax; k++) st3(Q.pos + 3 * ((size_t)i * Q.qmax + k), mk3(CUDART_INF, CUDART_INF, CUDART_INF));   // unused slots: in no leaf
+        }
         atomicAdd(&TC->closest, c_closest); atomicAdd(&TC->shadow, c_shadow); atomicAdd(&TC->gathers, c_gather);
         atomicAdd(&TC->nodes_c, (unsigned long long)nc); atomicAdd(&TC->prims_c, (unsigned long long)pc); atomicAdd(&TC->nodes_s, (unsigned long long)ns); atomicAdd(&TC->prims_s, (unsigned long long)ps);
         atomicAdd(&TC->g_depth, g_depth); atomicAdd(&TC->g_cand, g_cand); atomicAdd(&TC->g_sel, g_sel);
     }
   }
+}
+
+__global__ void k_tail_caustic(uint32_t n, DQueue in, DPathState PS, DTailQ Q)
+{
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint32_t path = in.path[i];
+    d3 Lc = ld3(PS.Lc + 3 * (size_t)path);
+    const uint32_t nq = Q.count[i];
+    for (uint32_t k = 0; k < nq; k++) {
+        const size_t s = (size_t)i * Q.qmax + k;
+        Lc = Lc + ld3(Q.w + 3 * s) * ld3(Q.rgb + 3 * s);
+    }
+    st3(PS.Lc + 3 * (size_t)path, Lc);
 }
 
 // generate the camera paths of one chunk (path-linear range [c0, c0+n) of the tile's sample-major path space)
@@ -1225,10 +1263,11 @@ __global__ void k_generate(DScene S, DFrame F, int s0, uint64_t c0, uint32_t n, 
     PS.sample[i] = idx;
     PS.key[i] = ((uint64_t)((uint64_t)y * (uint64_t)F.w + (uint64_t)x) << 24) | (uint64_t)s;
     PS.L[3 * (size_t)i] = 0; PS.L[3 * (size_t)i + 1] = 0; PS.L[3 * (size_t)i + 2] = 0;
+    PS.Lc[3 * (size_t)i] = 0; PS.Lc[3 * (size_t)i + 1] = 0; PS.Lc[3 * (size_t)i + 2] = 0;
 }
 
 // add the chunk's per-path radiance into the tile accumulator, samples in ascending order per pixel
-__global__ void k_accumulate(uint64_t c0, uint32_t n, size_t npx, const double* L, double* accum)
+__global__ void k_accumulate(uint64_t c0, uint32_t n, size_t npx, const double* L, const double* Lc, double* accum)
 {
     size_t pix = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
     if (pix >= npx) return;
@@ -1240,7 +1279,7 @@ __global__ void k_accumulate(uint64_t c0, uint32_t n, size_t npx, const double* 
         uint64_t lin = k * npx + pix;
         if (lin >= c1) break;
         size_t i = (size_t)(lin - c0);
-        a0 += L[3 * i]; a1 += L[3 * i + 1]; a2 += L[3 * i + 2];
+        a0 += L[3 * i] + Lc[3 * i]; a1 += L[3 * i + 1] + Lc[3 * i + 1]; a2 += L[3 * i + 2] + Lc[3 * i + 2];
     }
     accum[3 * pix] = a0; accum[3 * pix + 1] = a1; accum[3 * pix + 2] = a2;
 }
