@@ -12,7 +12,7 @@ isolated photon gather over the frame's primary-hit queries.
   gather  photon-gather Mqueries/s (gi_photon_gather_dev) over the primary-hit queries, same frame
   N > 1   weak scaling by sample index: rank r renders samples [8r, 8r+8) of every pixel; photon map built on rank 0
           and broadcast over NCCL (outside the timed region, like the reference's cached map); per-step NCCL reduce of
-          the fp64 framebuffer sums (inside the timed region)
+          the fp64 framebuffer sums (inside the timed region, double-buffered: it overlaps the next frame's rendering)
 
 `--impl reference` times the reference's own OpenMP CPU path (oracle/_ref/gi_ref_fast, the unmodified reference
 sources) on a bounded sample of the same workload, on the host cores of this box.
@@ -220,15 +220,23 @@ def main():
 
     s0, s1 = gd.sample_ranges(SPP, world)[rank]
     P = render_params(W, H, SPP * world, max_depth=MAX_DEPTH, seed=1)
-    accum = torch.zeros((H * W, 3), dtype=torch.float64, device=dev)
+    # two framebuffers: the NCCL reduce of frame i (torch's stream) overlaps the rendering of frame i + 1 (the context's stream)
+    accums = [torch.zeros((H * W, 3), dtype=torch.float64, device=dev) for _ in range(2)]
+    reduced = [None, None]   # event: the reduce that last read accums[b] is done
+    step_no = [0]
 
     def step_device():
-        if world > 1:
-            stream.wait_stream(torch.cuda.current_stream(dev))   # the previous step's reduce reads accum
+        b = step_no[0] & 1
+        step_no[0] += 1
+        accum = accums[b]
+        if world > 1 and reduced[b] is not None:
+            stream.wait_event(reduced[b])                         # the reduce of two frames ago still reads this buffer
         st = ctx.render_tile_dev(P, 0, 0, W, H, s0, s1, accum.data_ptr())
-        if world > 1:
+        if world > 1 and not os.environ.get("GI_BENCH_NO_REDUCE"):   # (debug knob: time the frames without the collective)
             torch.cuda.current_stream(dev).wait_stream(stream)
             gd.reduce_accum(accum, 0)
+            reduced[b] = torch.cuda.Event()
+            reduced[b].record(torch.cuda.current_stream(dev))
         return st
 
     # clocks / throttle reasons are sampled from the first warm-up step to the end of the timed region (same load throughout);
@@ -254,7 +262,7 @@ def main():
     for _ in range(K):
         stats.append(step_device())
     if world > 1:
-        stream.wait_stream(torch.cuda.current_stream(dev))
+        stream.wait_stream(torch.cuda.current_stream(dev))   # the last reduces
     ev1.record(stream)
     barrier_sync()
     clk = clocks.stop() if rank == 0 else None

@@ -62,7 +62,7 @@ struct gi_ctx {
     int bounce_mode = 0;             // 0: pick per scene, 1: always one ray per thread, 2: always persistent warps with refetch (GI_BOUNCE_MODE)
     double nodes_per_ray = 0;        // node tests per closest-hit ray of the last frame rendered with the current scene
     // per-scene choice between the two bounce kernels: the first full-size frame runs the form guessed from the tree, the
-    // second the other one, later frames the faster of the two (bounce ms per closest-hit ray)
+    // second the other one, later frames the faster of the two (bounce + direct ms per closest-hit ray)
     uint64_t tune_sig = 0; int tune_frames = 0; double tune_cost[2] = { 0, 0 };
     uint32_t bin_threshold = 65536;  // queues at least this long are binned by origin cell / direction octant before the next bounce (GI_BIN_THRESHOLD, 0 = off)
     unsigned long long work_host[16] = { 0 };   // [0,1] closest nodes/prims, [2,3] any-hit, [4..6] gather depth/cand/sel, [8] rays, [9] shadow rays, [10] queries
@@ -950,7 +950,7 @@ static int render_device(gi_ctx* ctx, const gi_render_params* P, int x0, int y0,
     bool persistent = ctx->bounce_mode == 2 || (ctx->bounce_mode == 0 && guess);
     if (tunable) {
         if (ctx->tune_frames == 1) persistent = !guess;
-        else if (ctx->tune_frames >= 2) persistent = ctx->tune_cost[1] < ctx->tune_cost[0];
+        else if (ctx->tune_frames >= 2) persistent = ctx->tune_cost[1] < 0.97 * ctx->tune_cost[0];   // refetch also scrambles the hit list: it has to win clearly
     }
     uint64_t n_closest = 0, n_shadow = 0, n_gather = 0, launches = 0;
     for (const char* f : { "bounce", "direct", "gather", "tail", "bin" }) fam_reset(ctx, f);
@@ -1066,7 +1066,7 @@ static int render_device(gi_ctx* ctx, const gi_render_params* P, int x0, int y0,
     n_closest += tc.closest; n_shadow += tc.shadow; n_gather += tc.gathers;
     if (n_closest) ctx->nodes_per_ray = (double)(ctx->work_host[0] + tc.nodes_c) / (double)n_closest;
     if (tunable && ctx->tune_frames < 2 && n_closest > tc.closest) {
-        ctx->tune_cost[persistent ? 1 : 0] = ctx->fam["bounce"].ms / (double)(n_closest - tc.closest);
+        ctx->tune_cost[persistent ? 1 : 0] = (ctx->fam["bounce"].ms + ctx->fam["direct"].ms) / (double)(n_closest - tc.closest);   // the hit-list order the form leaves behind counts too
         ctx->tune_frames++;
     }
     ctx->work_host[0] += tc.nodes_c; ctx->work_host[1] += tc.prims_c; ctx->work_host[2] += tc.nodes_s; ctx->work_host[3] += tc.prims_s;
