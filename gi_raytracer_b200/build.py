@@ -12,7 +12,7 @@ NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 
 CU = [os.path.join(CSRC, "gi_api.cu")]
 CPP = [os.path.join(CSRC, "host", f) for f in ("gi_scene.cpp", "gi_loader.cpp", "gi_raytracer.cpp", "gi_host_capi.cpp")]
-HDR = [os.path.join(CSRC, f) for f in ("gi_device.cuh", "gi_kernels.cuh")] + [os.path.join(CSRC, "host", "gi_scene.hpp"),
+HDR = [os.path.join(CSRC, f) for f in ("gi_device.cuh", "gi_kernels.cuh", os.path.join("host", "api_scene.inc"))] + [os.path.join(CSRC, "host", "gi_scene.hpp"),
                                                                               os.path.join(HERE, "..", "include", "gi_api.h")]
 EXTRA = os.environ.get("GI_NVCC_EXTRA", "").split()
 FLAGS = EXTRA + ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-fmad=false",

@@ -3,6 +3,7 @@
 #include <cstring>
 #include <iostream>
 #include <sstream>
+#include <string>
 
 #include "gi_scene.hpp"
 
@@ -26,7 +27,16 @@ int gih_scene_load(const char* path, int quiet, gih_scene** out)
     Camera camera(gi::dvec3(10, 5, 0), gi::dvec3(0, 0, 0));  // main.cpp:30 default camera
     s->rt = new RayTracer(camera);
     s->octree = new Octree();
-    loadScene(s->octree, *s->rt, path);
+    std::string spath = path;
+    const bool api_scene = spath.size() > 4 && spath.compare(spath.size() - 4, 4, "#api") == 0;   // "<file>.scn#api": add the API-built primitives
+    if (api_scene) spath.resize(spath.size() - 4);
+    loadScene(s->octree, *s->rt, spath.c_str());
+    if (api_scene) {
+        Octree* o = s->octree;
+#define V3(x, y, z) gi::dvec3(x, y, z)
+#include "api_scene.inc"
+#undef V3
+    }
     if (!s->octree->entities().empty()) s->octree->rebuild(); else s->octree->valid = true;
     s->octree->flatten(s->rt->_camera, s->rt->ambient, s->flat);
     s->desc = s->flat.desc();

@@ -57,6 +57,37 @@ dmat3 inverse(const dmat3& in)
     return r;
 }
 
+// glm::inverse of the 4x4 matrix glm::eulerAngleXYZ returns (detail/func_matrix.inl:297-352), upper-left 3x3 of the
+// result: what `cone::rot = glm::inverse(glm::eulerAngleXYZ(..))` stores (entities.h:153).  Not the 3x3 formula: the
+// cofactor expansion differs in rounding and in the sign of zeros.
+dmat3 inverse_euler4(const dmat3& in)
+{
+    double m[4][4] = { { in.c[0][0], in.c[0][1], in.c[0][2], 0 }, { in.c[1][0], in.c[1][1], in.c[1][2], 0 }, { in.c[2][0], in.c[2][1], in.c[2][2], 0 }, { 0, 0, 0, 1 } };
+    double Coef00 = m[2][2] * m[3][3] - m[3][2] * m[2][3], Coef02 = m[1][2] * m[3][3] - m[3][2] * m[1][3], Coef03 = m[1][2] * m[2][3] - m[2][2] * m[1][3];
+    double Coef04 = m[2][1] * m[3][3] - m[3][1] * m[2][3], Coef06 = m[1][1] * m[3][3] - m[3][1] * m[1][3], Coef07 = m[1][1] * m[2][3] - m[2][1] * m[1][3];
+    double Coef08 = m[2][1] * m[3][2] - m[3][1] * m[2][2], Coef10 = m[1][1] * m[3][2] - m[3][1] * m[1][2], Coef11 = m[1][1] * m[2][2] - m[2][1] * m[1][2];
+    double Coef12 = m[2][0] * m[3][3] - m[3][0] * m[2][3], Coef14 = m[1][0] * m[3][3] - m[3][0] * m[1][3], Coef15 = m[1][0] * m[2][3] - m[2][0] * m[1][3];
+    double Coef16 = m[2][0] * m[3][2] - m[3][0] * m[2][2], Coef18 = m[1][0] * m[3][2] - m[3][0] * m[1][2], Coef19 = m[1][0] * m[2][2] - m[2][0] * m[1][2];
+    double Coef20 = m[2][0] * m[3][1] - m[3][0] * m[2][1], Coef22 = m[1][0] * m[3][1] - m[3][0] * m[1][1], Coef23 = m[1][0] * m[2][1] - m[2][0] * m[1][1];
+    const double Fac0[4] = { Coef00, Coef00, Coef02, Coef03 }, Fac1[4] = { Coef04, Coef04, Coef06, Coef07 }, Fac2[4] = { Coef08, Coef08, Coef10, Coef11 };
+    const double Fac3[4] = { Coef12, Coef12, Coef14, Coef15 }, Fac4[4] = { Coef16, Coef16, Coef18, Coef19 }, Fac5[4] = { Coef20, Coef20, Coef22, Coef23 };
+    const double Vec0[4] = { m[1][0], m[0][0], m[0][0], m[0][0] }, Vec1[4] = { m[1][1], m[0][1], m[0][1], m[0][1] };
+    const double Vec2[4] = { m[1][2], m[0][2], m[0][2], m[0][2] }, Vec3[4] = { m[1][3], m[0][3], m[0][3], m[0][3] };
+    const double SignA[4] = { +1, -1, +1, -1 }, SignB[4] = { -1, +1, -1, +1 };
+    double Inv[4][4];
+    for (int k = 0; k < 4; k++) {
+        Inv[0][k] = ((Vec1[k] * Fac0[k] - Vec2[k] * Fac1[k]) + Vec3[k] * Fac2[k]) * SignA[k];
+        Inv[1][k] = ((Vec0[k] * Fac0[k] - Vec2[k] * Fac3[k]) + Vec3[k] * Fac4[k]) * SignB[k];
+        Inv[2][k] = ((Vec0[k] * Fac1[k] - Vec1[k] * Fac3[k]) + Vec3[k] * Fac5[k]) * SignA[k];
+        Inv[3][k] = ((Vec0[k] * Fac2[k] - Vec1[k] * Fac4[k]) + Vec2[k] * Fac5[k]) * SignB[k];
+    }
+    const double Dot0[4] = { m[0][0] * Inv[0][0], m[0][1] * Inv[1][0], m[0][2] * Inv[2][0], m[0][3] * Inv[3][0] };
+    const double ood = 1.0 / ((Dot0[0] + Dot0[1]) + (Dot0[2] + Dot0[3]));
+    dmat3 r;
+    for (int c = 0; c < 3; c++) for (int k = 0; k < 3; k++) r.c[c][k] = Inv[c][k] * ood;
+    return r;
+}
+
 }  // namespace gi
 
 // ---- triangle / box overlap: Akenine-Möller separating-axis test as the reference uses it (util.cpp:187-330).
@@ -148,7 +179,7 @@ bool sphere::intersect(BoundingBox bbox)  // entities.h:108-141: squared distanc
 cone::cone(dvec3 position, dvec3 rotation, double radius, double h, const Material& m) : Entity(m), rad(radius), height(h)
 {
     pos = position;
-    rot = gi::inverse(gi::eulerAngleXYZ(rotation.x, rotation.y, rotation.z));  // entities.h:153
+    rot = gi::inverse_euler4(gi::eulerAngleXYZ(rotation.x, rotation.y, rotation.z));  // entities.h:153 (a 4x4 inverse in the reference)
 }
 
 BoundingBox cone::boundingBox() const  // entities.h:260-299: AABB of the bounding pyramid

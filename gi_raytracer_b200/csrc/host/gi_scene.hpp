@@ -75,6 +75,7 @@ inline dvec3 operator*(const dvec3& v, const dmat3& m)
 }
 dmat3 eulerAngleXYZ(double t1, double t2, double t3);   // upper-left 3x3 of glm::eulerAngleXYZ (gtx/euler_angles.inl:135-167)
 dmat3 inverse(const dmat3& m);                          // glm::inverse (detail/func_matrix.inl:272-294)
+dmat3 inverse_euler4(const dmat3& m);                   // glm::inverse of the 4x4 euler matrix, upper-left 3x3 (detail/func_matrix.inl:297-352)
 
 }  // namespace gi
 

@@ -275,7 +275,7 @@ int main(int argc, char** argv)
     }
     const char* scn = argv[1];
     g_out = argv[2];
-    int w = 64, h = 64, s0 = 0, s1 = 1, photons_override = -1, samples = -1, x0 = 0, y0 = 0, x1 = -1, y1 = -1, repeat = 1;
+    int w = 64, h = 64, s0 = 0, s1 = 1, photons_override = -1, samples = -1, x0 = 0, y0 = 0, x1 = -1, y1 = -1, repeat = 1, api_scene = 0;
     std::vector<std::string> cmds;
     for (int i = 3; i < argc; i++) {
         std::string a = argv[i];
@@ -284,7 +284,7 @@ int main(int argc, char** argv)
         else if (a == "--max-depth") g_max_depth = next(); else if (a == "--min-depth") g_min_depth = next();
         else if (a == "--photons") photons_override = next(); else if (a == "--samples") samples = next();
         else if (a == "--x0") x0 = next(); else if (a == "--y0") y0 = next(); else if (a == "--x1") x1 = next(); else if (a == "--y1") y1 = next();
-        else if (a == "--repeat") repeat = next();
+        else if (a == "--repeat") repeat = next(); else if (a == "--api-scene") api_scene = next();
         else cmds.push_back(a);
     }
     if (x1 < 0) x1 = w;
@@ -298,6 +298,12 @@ int main(int argc, char** argv)
     RayTracer rt(camera);                           // main.cpp:32
     Octree* scene = new Octree();                   // main.cpp:36
     loadScene(scene, rt, scn);                      // main.cpp:38
+    if (api_scene) {   // primitives that have no .scn keyword, added through the reference's C++ API
+        Octree* o = scene;
+#define V3(x, y, z) glm::dvec3(x, y, z)
+#include "../gi_raytracer_b200/csrc/host/api_scene.inc"
+#undef V3
+    }
     if (photons_override >= 0) rt.photons = photons_override;
     if (samples > 0) { rt.min_samples = samples; rt.max_samples = samples; }
     g_ents = scene->_root._entities;                // insertion order = primitive id (root list is cleared by partition)

@@ -56,6 +56,22 @@ def test_reference_scenes_match_reference_loader(lib_built, name):
     assert_same_scene(mine, ref, textures_const=(name != "glass"))
 
 
+@pytest.mark.ref
+@pytest.mark.skipif(not R.have_ref(), reason="oracle/_ref/gi_ref not built")
+def test_api_built_scene_matches_reference(lib_built, synth_dir):
+    """Primitives without a scene-file keyword — quadMesh, sphereMesh, coneMesh generators, analytic cones — built through
+    the C++ scene API (csrc/host/api_scene.inc, the same lines compiled against the reference's classes and against the
+    host mirror): identical triangles / spheres / cones, materials and octree."""
+    from gi_raytracer_b200 import host
+    p = os.path.join(synth_dir, "small.scn")
+    mine = host.load_scene(p + "#api")
+    d, meta = R.run_ref(p, ["scene"], api_scene=1)
+    ref = R.scene_from_dump(d)
+    assert meta["entities"] == mine.n_prims and meta["nodes"] == mine.n_nodes and mine.n_prims > 150
+    assert set(np.unique(mine.prim_type)) == {0, 1, 2}
+    assert_same_scene(mine, ref, textures_const=False)
+
+
 def test_missing_scene_file_gives_empty_scene(lib_built):
     """Like the reference, a missing file prints and continues (sceneLoader.cpp:29-33): the result is an empty scene."""
     from gi_raytracer_b200 import host
