@@ -22,7 +22,7 @@ API_SYMBOLS = [
     "gi_photon_map_build", "gi_photon_map_info", "gi_photon_map_download", "gi_photon_map_slab_size",
     "gi_photon_map_slab_ptr", "gi_photon_map_adopt_slab", "gi_photon_map_reserve_slab", "gi_photon_gather",
     "gi_photon_gather_dev", "gi_render_tile", "gi_render_tile_dev", "gi_resolve", "gi_resolve_dev", "gi_last_kernel_ms",
-    "gi_last_work", "gi_scene_info",
+    "gi_last_work", "gi_scene_info", "gi_render_adaptive", "gi_render_adaptive_dev",
 ]
 
 _LIB = None
@@ -75,6 +75,8 @@ def load_library():
         f.argtypes = [vp, sz, vp, vp, i32, vp, vp, vp]
     for f in (L.gi_render_tile, L.gi_render_tile_dev):
         f.argtypes = [vp, C.POINTER(GiRenderParams), i32, i32, i32, i32, i32, i32, vp, C.POINTER(GiStats)]
+    for f in (L.gi_render_adaptive, L.gi_render_adaptive_dev):
+        f.argtypes = [vp, C.POINTER(GiRenderParams), i32, i32, C.c_double, i32, i32, i32, i32, vp, vp, C.POINTER(GiStats)]
     for f in (L.gi_resolve, L.gi_resolve_dev):
         f.argtypes = [vp, sz, vp, i32, vp]
     L.gi_last_kernel_ms.argtypes = [vp, C.c_char_p, C.POINTER(C.c_double), C.POINTER(u64)]
@@ -272,6 +274,15 @@ class Context:
         st = GiStats()
         self._ck(self.L.gi_render_tile(self.h, C.byref(params), x0, y0, x1, y1, s0, s1, _p(acc), C.byref(st)))
         return acc, st
+
+    def render_adaptive(self, params: GiRenderParams, min_samples, max_samples, noise_thresh, x0, y0, x1, y1):
+        """gi_render_adaptive -> (colour [npx, 3] fp64 running means, samples taken [npx] u32, GiStats)."""
+        npx = (x1 - x0) * (y1 - y0)
+        col = np.empty((npx, 3), dtype=np.float64)
+        ns = np.empty(npx, dtype=np.uint32)
+        st = GiStats()
+        self._ck(self.L.gi_render_adaptive(self.h, C.byref(params), min_samples, max_samples, float(noise_thresh), x0, y0, x1, y1, col.ctypes.data, ns.ctypes.data, C.byref(st)))
+        return col, ns, st
 
     def render_tile_dev(self, params: GiRenderParams, x0, y0, x1, y1, s0, s1, accum_ptr):
         st = GiStats()

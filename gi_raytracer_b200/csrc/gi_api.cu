@@ -54,7 +54,7 @@ struct gi_ctx {
     DGatherMap G{};
     // workspaces
     DevBuf w0, w1, w2, w3, w4, w5, w6, w7, w8, w9;           // API staging
-    DevBuf q_a[5], q_b[5], hl[7], ps[4], tq[5], b_cnt, b_accum, b_scan0, b_scan1, b_misc, b_work, b_tail, b_binkey, b_binperm, b_binhist, b_bincur, b_gnode, b_gperm, b_ghist, b_gcur, b_gheavy;
+    DevBuf q_a[5], q_b[5], hl[7], ps[4], tq[5], ad[6], b_cnt, b_accum, b_scan0, b_scan1, b_misc, b_work, b_tail, b_binkey, b_binperm, b_binhist, b_bincur, b_gnode, b_gperm, b_ghist, b_gcur, b_gheavy;
     bool no_implicit = false;      // GI_NO_IMPLICIT_BOXES at gi_create: always load child boxes (for A/B tests)
     int trace_mode = 0;            // 0: thread per ray, 1: warp per ray (API batch kernels; GI_TRACE_MODE)
     uint32_t tail_threshold = 32768; // queues smaller than this finish in the tail megakernel (GI_TAIL_THRESHOLD, 0 = off)
@@ -248,6 +248,7 @@ extern "C" void gi_destroy(gi_ctx* ctx)
     for (auto& b : ctx->hl) b.release();
     for (auto& b : ctx->ps) b.release();
     for (auto& b : ctx->tq) b.release();
+    for (auto& b : ctx->ad) b.release();
     for (auto& t : ctx->pending) { cudaEventDestroy(t.a); cudaEventDestroy(t.b); }
     for (auto& e : ctx->event_pool) cudaEventDestroy(e);
     cudaStreamDestroy(ctx->stream);
@@ -917,10 +918,12 @@ extern "C" int gi_photon_gather(gi_ctx* ctx, size_t n, const double* pos, const 
 }
 
 // ---- frame ------------------------------------------------------------------------------------------------------------------------------------
-static int render_device(gi_ctx* ctx, const gi_render_params* P, int x0, int y0, int x1, int y1, int s0, int s1, double* accum_dev, gi_stats* stats)
+// Fixed sample range [s0, s1) into accum_dev (sums), or — with `adapt` — the reference's adaptive per-pixel loop: accum_dev then
+// receives the final running-mean colour of each pixel and adapt->s_done the samples taken.
+static int render_device(gi_ctx* ctx, const gi_render_params* P, int x0, int y0, int x1, int y1, int s0, int s1, double* accum_dev, gi_stats* stats, DAdapt* adapt = nullptr)
 {
     const size_t npx = (size_t)(x1 - x0) * (y1 - y0);
-    const uint64_t total_paths = (uint64_t)npx * (uint64_t)(s1 - s0);
+    const uint64_t total_paths = adapt ? (uint64_t)npx : (uint64_t)npx * (uint64_t)(s1 - s0);
     const uint32_t chunk_cap = (uint32_t)std::min<uint64_t>(total_paths, GI_MAX_PATHS);
     // queues (double buffered), hit list, per-path state
     for (int b = 0; b < 4; b++) { CK(ctx->q_a[b].reserve((size_t)chunk_cap * 24)); CK(ctx->q_b[b].reserve((size_t)chunk_cap * 24)); }
@@ -957,11 +960,8 @@ static int render_device(gi_ctx* ctx, const gi_render_params* P, int x0, int y0,
     CK(cudaMemsetAsync(work_ptr(ctx, 0), 0, 8 * sizeof(unsigned long long), ctx->stream));
     cudaEvent_t e0 = get_event(ctx), e1 = get_event(ctx);
     cudaEventRecord(e0, ctx->stream);
-    CK(cudaMemsetAsync(accum_dev, 0, npx * 24, ctx->stream));
-    for (uint64_t c0 = 0; c0 < total_paths; c0 += chunk_cap) {
-        uint32_t n = (uint32_t)std::min<uint64_t>(chunk_cap, total_paths - c0);
-        k_generate<<<grid_for(n, 256), 256, 0, ctx->stream>>>(ctx->S, F, s0, c0, n, qa, PS);
-        launches++;
+    // the bounce loop over one batch of n camera paths sitting in qa / PS
+    auto run_depths = [&](uint32_t n) -> int {
         DQueue in = qa, out = qb;
         uint32_t n_active = n;
         const uint32_t* perm = nullptr;
@@ -1052,9 +1052,41 @@ static int render_device(gi_ctx* ctx, const gi_render_params* P, int x0, int y0,
                 perm = ctx->b_binperm.as<uint32_t>();
             }
         }
+        return GI_OK;
+    };
+    if (adapt) {
+        // passes over the sample index; pass s renders sample s of the pixels that are still active (raytracer.h:108)
+        if (npx > chunk_cap) return fail(ctx, GI_ERR_INVALID, "adaptive tiles are limited to 2^23 pixels");
+        k_adapt_init<<<grid_for(npx, 256), 256, 0, ctx->stream>>>(npx, *adapt);
+        for (int s = 0; s < adapt->max_samples; s++) {
+            CK(cudaMemsetAsync(adapt->n_list, 0, 4, ctx->stream));
+            k_adapt_select<<<grid_for(npx, 256), 256, 0, ctx->stream>>>((uint32_t)npx, s, *adapt);
+            uint32_t n = 0;
+            CK(cudaMemcpyAsync(&n, adapt->n_list, 4, cudaMemcpyDeviceToHost, ctx->stream));
+            CK(cudaStreamSynchronize(ctx->stream));
+            launches += 2;
+            if (!n) break;
+            k_generate_list<<<grid_for(n, 256), 256, 0, ctx->stream>>>(ctx->S, F, s, n, adapt->list, qa, PS);
+            launches++;
+            int rcd = run_depths(n);
+            if (rcd != GI_OK) return rcd;
+            k_adapt_update<<<grid_for(n, 256), 256, 0, ctx->stream>>>(n, s, adapt->list, PS.L, PS.Lc, *adapt);
+            launches++;
+            CK(cudaGetLastError());
+        }
+        CK(cudaMemcpyAsync(accum_dev, adapt->color, npx * 24, cudaMemcpyDeviceToDevice, ctx->stream));
+    } else {
+    CK(cudaMemsetAsync(accum_dev, 0, npx * 24, ctx->stream));
+    for (uint64_t c0 = 0; c0 < total_paths; c0 += chunk_cap) {
+        uint32_t n = (uint32_t)std::min<uint64_t>(chunk_cap, total_paths - c0);
+        k_generate<<<grid_for(n, 256), 256, 0, ctx->stream>>>(ctx->S, F, s0, c0, n, qa, PS);
+        launches++;
+        int rcd = run_depths(n);
+        if (rcd != GI_OK) return rcd;
         k_accumulate<<<grid_for(npx, 256), 256, 0, ctx->stream>>>(c0, n, npx, PS.L, PS.Lc, accum_dev);
         launches++;
         CK(cudaGetLastError());
+    }
     }
     cudaEventRecord(e1, ctx->stream);
     DTailCounters tc;
@@ -1113,6 +1145,38 @@ extern "C" int gi_render_tile(gi_ctx* ctx, const gi_render_params* P, int x0, in
     rc = render_device(ctx, P, x0, y0, x1, y1, s0, s1, ctx->b_accum.as<double>(), stats);
     if (rc != GI_OK) return rc;
     CK(cudaMemcpyAsync(accum, ctx->b_accum.p, npx * 24, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return GI_OK;
+}
+
+extern "C" int gi_render_adaptive_dev(gi_ctx* ctx, const gi_render_params* P, int min_samples, int max_samples, double noise_thresh, int x0, int y0, int x1, int y1, double* color,
+                                      uint32_t* samples, gi_stats* stats)
+{
+    int rc = check_render_args(ctx, P, x0, y0, x1, y1, 0, 1, color);
+    if (rc != GI_OK) return rc;
+    if (min_samples < 0 || max_samples < 0) return fail(ctx, GI_ERR_INVALID, "negative sample counts");
+    CK(cudaSetDevice(ctx->device));
+    const size_t npx = (size_t)(x1 - x0) * (y1 - y0);
+    CK(ctx->ad[0].reserve(npx * 24)); CK(ctx->ad[1].reserve(npx * 8)); CK(ctx->ad[2].reserve(npx * 4)); CK(ctx->ad[3].reserve(npx * 4)); CK(ctx->ad[4].reserve(npx * 4)); CK(ctx->ad[5].reserve(16));
+    DAdapt A{ ctx->ad[0].as<double>(), ctx->ad[1].as<double>(), ctx->ad[2].as<int>(), ctx->ad[3].as<int>(), ctx->ad[4].as<uint32_t>(), ctx->ad[5].as<uint32_t>(), min_samples, max_samples, noise_thresh };
+    rc = render_device(ctx, P, x0, y0, x1, y1, 0, 1, color, stats, &A);
+    if (rc != GI_OK) return rc;
+    if (samples) CK(cudaMemcpyAsync(samples, A.s_done, npx * 4, cudaMemcpyDeviceToDevice, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return GI_OK;
+}
+extern "C" int gi_render_adaptive(gi_ctx* ctx, const gi_render_params* P, int min_samples, int max_samples, double noise_thresh, int x0, int y0, int x1, int y1, double* color,
+                                  uint32_t* samples, gi_stats* stats)
+{
+    int rc = check_render_args(ctx, P, x0, y0, x1, y1, 0, 1, color);
+    if (rc != GI_OK) return rc;
+    CK(cudaSetDevice(ctx->device));
+    const size_t npx = (size_t)(x1 - x0) * (y1 - y0);
+    CK(ctx->b_accum.reserve(npx * 24)); CK(ctx->w9.reserve(npx * 4));
+    rc = gi_render_adaptive_dev(ctx, P, min_samples, max_samples, noise_thresh, x0, y0, x1, y1, ctx->b_accum.as<double>(), ctx->w9.as<uint32_t>(), stats);
+    if (rc != GI_OK) return rc;
+    CK(cudaMemcpyAsync(color, ctx->b_accum.p, npx * 24, cudaMemcpyDeviceToHost, ctx->stream));
+    if (samples) CK(cudaMemcpyAsync(samples, ctx->w9.p, npx * 4, cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
     return GI_OK;
 }

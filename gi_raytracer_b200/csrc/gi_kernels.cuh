@@ -1266,6 +1266,67 @@ __global__ void k_generate(DScene S, DFrame F, int s0, uint64_t c0, uint32_t n, 
     PS.Lc[3 * (size_t)i] = 0; PS.Lc[3 * (size_t)i + 1] = 0; PS.Lc[3 * (size_t)i + 2] = 0;
 }
 
+// ---- adaptive sampling: the per-pixel loop of RayTracer::run (raytracer.h:100-148) as passes over the sample index --------------------
+// Per pixel the reference keeps (color = running mean, var = smoothed change of the mean, s = samples taken, samps) and goes on
+// while s < max_samples && samps < min_samples; every sample adds 1 to samps, a sample that leaves var above the threshold takes
+// 2 away again.  A pixel that stops never resumes, so pass s renders sample s of the pixels still active: k_adapt_select lists
+// them (ballot + prefix popcount), k_generate_list makes their camera paths, the wavefront runs as usual, k_adapt_update folds
+// the path radiance into the pixel state with the reference's arithmetic.
+struct DAdapt { double* color; double* var; int* samps; int* s_done; uint32_t* list; uint32_t* n_list; int min_samples, max_samples; double noise_thresh; };
+
+__global__ void k_adapt_init(size_t npx, DAdapt A)
+{
+    size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    if (i >= npx) return;
+    A.color[3 * i] = 0.5; A.color[3 * i + 1] = 0.5; A.color[3 * i + 2] = 0.5;   // raytracer.h:102
+    A.var[i] = 0; A.samps[i] = 0; A.s_done[i] = 0;
+}
+__global__ void k_adapt_select(uint32_t npx, int s, DAdapt A)
+{
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    const bool on = i < npx && A.s_done[i] == s && s < A.max_samples && A.samps[i] < A.min_samples;   // :108
+    const unsigned lane = threadIdx.x & 31u, m = __ballot_sync(0xffffffffu, on);
+    uint32_t base = 0;
+    if (lane == 0 && m) base = atomicAdd(A.n_list, (uint32_t)__popc(m));
+    base = __shfl_sync(0xffffffffu, base, 0);
+    if (on) A.list[base + __popc(m & ((1u << lane) - 1u))] = i;
+}
+// camera paths for sample s of the listed pixels (tile-linear pixel indices)
+__global__ void k_generate_list(DScene S, DFrame F, int s, uint32_t n, const uint32_t* __restrict__ list, DQueue q, DPathState PS)
+{
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint32_t pix = list[i];
+    int y = F.y0 + (int)(pix / F.tw), x = F.x0 + (int)(pix % F.tw);
+    uint32_t idx;
+    DRay r = camera_ray(S, F, x, y, s, idx);
+    st3(q.o + 3 * (size_t)i, r.o); st3(q.d + 3 * (size_t)i, r.d);
+    st3(q.T + 3 * (size_t)i, mk3(1, 1, 1)); st3(q.contrib + 3 * (size_t)i, mk3(1, 1, 1));
+    q.path[i] = i;
+    PS.sample[i] = idx;
+    PS.key[i] = ((uint64_t)((uint64_t)y * (uint64_t)F.w + (uint64_t)x) << 24) | (uint64_t)s;
+    PS.L[3 * (size_t)i] = 0; PS.L[3 * (size_t)i + 1] = 0; PS.L[3 * (size_t)i + 2] = 0;
+    PS.Lc[3 * (size_t)i] = 0; PS.Lc[3 * (size_t)i + 1] = 0; PS.Lc[3 * (size_t)i + 2] = 0;
+}
+__global__ void k_adapt_update(uint32_t n, int s, const uint32_t* __restrict__ list, const double* __restrict__ L, const double* __restrict__ Lc, DAdapt A)
+{
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint32_t pix = list[i];
+    const d3 rad = ld3(L + 3 * (size_t)i) + ld3(Lc + 3 * (size_t)i);
+    const d3 last = ld3(A.color + 3 * (size_t)pix);                                      // lastCol = color (:110)
+    d3 color = s == 0 ? rad : (last * (1.0 * s) + rad) * (1.0 / (s + 1));              // :131-134
+    double var = A.var[pix];
+    int samps = A.samps[pix];
+    if (s > 0) {
+        const d3 dc = color - last;
+        var = (1.0 * 5 * var + sqrt(dot3(dc, dc))) * (1.0 / (5 + 1));                   // :138 (glm::length)
+        if (var > A.noise_thresh) samps -= 2;                                            // :143-144
+    }
+    st3(A.color + 3 * (size_t)pix, color);
+    A.var[pix] = var; A.samps[pix] = samps + 1; A.s_done[pix] = s + 1;                   // :146-147
+}
+
 // add the chunk's per-path radiance into the tile accumulator, samples in ascending order per pixel
 __global__ void k_accumulate(uint64_t c0, uint32_t n, size_t npx, const double* L, const double* Lc, double* accum)
 {

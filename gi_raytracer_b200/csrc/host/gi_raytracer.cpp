@@ -72,14 +72,18 @@ int RayTracer::run(int w, int h)
         std::cout << "total photons: " << stored << "\n";
         if (!_photon_map->valid) { std::cout << "gi_photon_map_build: " << gi_last_error(ctx) << "\n"; return GI_ERR_CUDA; }
     }
-    // Fixed sample count: `samples N N t`.  The variance-driven adaptive count (raytracer.h:136-144) is a "next" row
-    // (SURVEY §8f rank 4); with min != max the frame is rendered at max_samples.
+    // `samples N N t`: a fixed count, rendered as one sample range.  `samples min max t` with min != max: the reference's
+    // variance-driven per-pixel loop (raytracer.h:100-148) -> gi_render_adaptive; the result is the running-mean colour.
     gi_render_params p;
     p.width = w; p.height = h; p.max_depth = max_depth; p.min_depth = min_depth; p.spp = max_samples; p.k_photons = 32; p.caustic_max_depth = 10; p._pad = 0; p.seed = seed;
     std::vector<double> accum((size_t)w * h * 3);
     auto f0 = std::chrono::high_resolution_clock::now();
-    if ((rc = gi_render_tile(ctx, &p, 0, 0, w, h, 0, p.spp, accum.data(), &last_frame_stats)) != GI_OK) { std::cout << "gi_render_tile: " << gi_last_error(ctx) << "\n"; return rc; }
-    if ((rc = gi_resolve(ctx, (size_t)w * h, accum.data(), p.spp, _image->rgb.data())) != GI_OK) { std::cout << "gi_resolve: " << gi_last_error(ctx) << "\n"; return rc; }
+    int resolve_spp = p.spp;
+    if (min_samples != max_samples) {
+        if ((rc = gi_render_adaptive(ctx, &p, min_samples, max_samples, noise_thresh, 0, 0, w, h, accum.data(), nullptr, &last_frame_stats)) != GI_OK) { std::cout << "gi_render_adaptive: " << gi_last_error(ctx) << "\n"; return rc; }
+        resolve_spp = 1;
+    } else if ((rc = gi_render_tile(ctx, &p, 0, 0, w, h, 0, p.spp, accum.data(), &last_frame_stats)) != GI_OK) { std::cout << "gi_render_tile: " << gi_last_error(ctx) << "\n"; return rc; }
+    if ((rc = gi_resolve(ctx, (size_t)w * h, accum.data(), resolve_spp, _image->rgb.data())) != GI_OK) { std::cout << "gi_resolve: " << gi_last_error(ctx) << "\n"; return rc; }
     auto f1 = std::chrono::high_resolution_clock::now();
     last_frame_ms = std::chrono::duration<double, std::milli>(f1 - f0).count();
     return GI_OK;

@@ -225,6 +225,14 @@ int gi_render_tile(gi_ctx* ctx, const gi_render_params* p, int x0, int y0, int x
 int gi_render_tile_dev(gi_ctx* ctx, const gi_render_params* p, int x0, int y0, int x1, int y1, int s0, int s1, double* accum,
                        gi_stats* stats);
 /* ---- resolve: mean -> gamma 2.2 -> clamp -> (int)(255*c)  (raytracer.h:150-156, util.h:94-97, image.h:14-16) */
+/* Adaptive sampling: the per-pixel loop of RayTracer::run (raytracer.h:100-148) with `samples min max thresh`.  Every pixel
+ * of the tile takes samples s = 0, 1, .. while s < max_samples && samps < min_samples (samps +1 per sample, -2 when the
+ * smoothed change of the running mean stays above noise_thresh).  color[n_pixels][3] receives the final running-mean colour
+ * (resolve it with spp = 1), samples[n_pixels] (may be NULL) the samples taken.  p->spp is ignored. */
+int gi_render_adaptive(gi_ctx* ctx, const gi_render_params* p, int min_samples, int max_samples, double noise_thresh, int x0, int y0, int x1, int y1,
+                       double* color, uint32_t* samples, gi_stats* stats);
+int gi_render_adaptive_dev(gi_ctx* ctx, const gi_render_params* p, int min_samples, int max_samples, double noise_thresh, int x0, int y0, int x1, int y1,
+                           double* color, uint32_t* samples, gi_stats* stats);
 int gi_resolve(gi_ctx* ctx, size_t n_pixels, const double* accum, int spp, uint8_t* rgb8);
 int gi_resolve_dev(gi_ctx* ctx, size_t n_pixels, const double* accum, int spp, uint8_t* rgb8);
 

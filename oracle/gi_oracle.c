@@ -1067,6 +1067,48 @@ void go_render(const gi_scene_desc* sc, const go_pmap* pm, const gi_render_param
     if (stats) { memset(stats, 0, sizeof(*stats)); stats->closest_rays = n_closest; stats->shadow_rays = n_shadow; stats->gathers = n_gather; }
 }
 
+/* The adaptive per-pixel loop of RayTracer::run (raytracer.h:100-148): running mean, smoothed change `var`, `samps` bookkeeping.
+ * color[n][3] = final running mean, samples[n] = samples taken. */
+void go_render_adaptive(const gi_scene_desc* sc, const go_pmap* pm, const gi_render_params* P, int min_samples, int max_samples, double noise_thresh, int x0, int y0, int x1, int y1,
+                        double* color_out, uint32_t* samples_out)
+{
+    go_halton_init();
+    go_henum he; go_henum_init(&he, (uint32_t)P->width, (uint32_t)P->height);
+    long tw = x1 - x0, th = y1 - y0;
+#pragma omp parallel
+    {
+        leaflist_t L = { 0, 0, 0 };
+        size_t gcap = 4096; uint32_t* gid = (uint32_t*)malloc(gcap * sizeof(uint32_t)); cand_t* gcd = (cand_t*)malloc(gcap * sizeof(cand_t));
+        tally_t tl = { 0, 0, 0 };
+#pragma omp for schedule(dynamic, 16)
+        for (long p = 0; p < tw * th; p++) {
+            int y = y0 + (int)(p / tw), x = x0 + (int)(p % tw);
+            v3 color = V(0.5, 0.5, 0.5), lastCol = V(0, 0, 0);          /* :102-103 */
+            double var = 0;
+            int samps = 0, s = 0;
+            while (s < max_samples && samps < min_samples) {            /* :108 */
+                lastCol = color;
+                double o[3], d[3]; uint32_t idx;
+                go_camera_ray(&sc->camera, &he, P->width, P->height, x, y, s, o, d, &idx);
+                ray_t ray = ray_as_stored(ld3(o), ld3(d));
+                uint64_t path = ((uint64_t)((uint64_t)y * (uint64_t)P->width + (uint64_t)x) << 24) | (uint64_t)s;
+                v3 rad = radiance_path(sc, pm, P, ray, idx, path, &L, &gid, &gcd, &gcap, &tl);
+                if (s == 0) color = rad;
+                else color = scale(add(scale(color, 1.0 * s), rad), 1.0 / (s + 1));   /* :131-134 */
+                if (s > 0) {
+                    v3 dc = sub(color, lastCol);
+                    var = (1.0 * 5 * var + sqrt(dot(dc, dc))) * (1.0 / (5 + 1));     /* :138 */
+                }
+                if (s > 0 && var > noise_thresh) samps -= 2;            /* :143-144 */
+                s++; samps++;
+            }
+            st3(color_out + 3 * p, color);
+            if (samples_out) samples_out[p] = (uint32_t)s;
+        }
+        free(L.v); free(gid); free(gcd);
+    }
+}
+
 /* gamma + clamp + 8-bit (raytracer.h:150-156, util.h:94-97, image.h:14-16); accum holds the sum of spp samples.
  * The reference keeps a running mean (raytracer.h:131-134) which equals sum/spp up to rounding. */
 void go_resolve(size_t n_pixels, const double* accum, int spp, uint8_t* rgb8)

@@ -87,6 +87,8 @@ size_t go_trace_photons(const gi_scene_desc* sc, int count, int max_depth, uint6
                         uint64_t* traces);
 
 /* frame (raytracer.h:93-160,167-276): SUM over s in [s0,s1) of radiance() per pixel of the rectangle */
+void go_render_adaptive(const gi_scene_desc* sc, const go_pmap* pm, const gi_render_params* p, int min_samples, int max_samples, double noise_thresh, int x0, int y0, int x1,
+                        int y1, double* color, uint32_t* samples);
 void go_render(const gi_scene_desc* sc, const go_pmap* pm, const gi_render_params* p, int x0, int y0, int x1, int y1, int s0, int s1,
                double* accum, gi_stats* stats);
 void go_resolve(size_t n_pixels, const double* accum, int spp, uint8_t* rgb8);

@@ -56,6 +56,7 @@ def lib():
     L.go_trace_photons.restype = sz
     L.go_trace_photons.argtypes = [vp, i32, i32, u64, vp, vp, vp]
     L.go_render.argtypes = [vp, vp, vp, i32, i32, i32, i32, i32, i32, vp, vp]
+    L.go_render_adaptive.argtypes = [vp, vp, vp, i32, i32, C.c_double, i32, i32, i32, i32, vp, vp]
     L.go_resolve.argtypes = [sz, vp, i32, vp]
     L.go_child_boxes.argtypes = [vp, vp]
     _LIB = L
@@ -219,6 +220,16 @@ def render(scene, pmap, params: GiRenderParams, x0, y0, x1, y1, s0, s1):
     desc = scene.desc()
     L.go_render(C.byref(desc), pmap.h if pmap is not None else None, C.byref(params), x0, y0, x1, y1, s0, s1, _p(acc), C.byref(st))
     return acc, st
+
+
+def render_adaptive(scene, pmap, params: GiRenderParams, min_samples, max_samples, noise_thresh, x0, y0, x1, y1):
+    L = lib()
+    npx = (y1 - y0) * (x1 - x0)
+    col = np.zeros((npx, 3))
+    ns = np.zeros(npx, dtype=np.uint32)
+    desc = scene.desc()
+    L.go_render_adaptive(C.byref(desc), pmap.h if pmap is not None else None, C.byref(params), min_samples, max_samples, float(noise_thresh), x0, y0, x1, y1, _p(col), _p(ns))
+    return col, ns
 
 
 def resolve(accum, spp):
