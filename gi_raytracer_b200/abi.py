@@ -29,6 +29,12 @@ class GiLight(C.Structure):
                 ("angle", C.c_double)]
 
 
+class GiFog(C.Structure):
+    _fields_ = [("pos", C.c_double * 3), ("size", C.c_double * 3), ("col", C.c_double * 3), ("density", C.c_double),
+                ("scatter", C.c_double), ("bmin", C.c_double * 3), ("bmax", C.c_double * 3), ("grid_offset", C.c_uint64),
+                ("grid_count", C.c_uint64)]
+
+
 class GiCamera(C.Structure):
     _fields_ = [("pos", C.c_double * 3), ("forward", C.c_double * 3), ("up", C.c_double * 3),
                 ("right", C.c_double * 3), ("sensor_diag", C.c_double), ("focal_dist", C.c_double)]
@@ -44,7 +50,8 @@ class GiSceneDesc(C.Structure):
                 ("n_mats", C.c_uint32), ("mats", C.c_void_p), ("n_tex", C.c_uint32), ("tex", C.c_void_p),
                 ("tex_pixel_bytes", C.c_uint64), ("tex_pixels", C.c_void_p),
                 ("n_lights", C.c_uint32), ("lights", C.c_void_p), ("camera", GiCamera),
-                ("ambient", C.c_double * 3)]
+                ("ambient", C.c_double * 3),
+                ("n_fog", C.c_uint32), ("fogs", C.c_void_p), ("fog_grid_count", C.c_uint64), ("fog_grid", C.c_void_p)]
 
 
 class GiRenderParams(C.Structure):
@@ -103,6 +110,8 @@ class SceneArrays:
     camera: np.ndarray         # [14] f64: pos, forward, up, right, sensor_diag, focal_dist
     ambient: np.ndarray        # [3]
     knobs: dict = field(default_factory=dict)   # photons, min_samples, max_samples, noise_thresh (from the .scn)
+    fogs: np.ndarray = None    # structured (GiFog layout): heightFog volumes
+    fog_grid: np.ndarray = None   # f64 noise grids of all fogs, concatenated
 
     MAT_DTYPE = np.dtype([("diffuse_tex", "<u4"), ("emissive_tex", "<u4"), ("roughness", "<f8"), ("opacity", "<f8"),
                           ("ior", "<f8")])
@@ -110,8 +119,14 @@ class SceneArrays:
                           ("tile_v", "<f8"), ("width", "<i4"), ("height", "<i4"), ("has_alpha", "<i4"), ("_pad", "<i4"),
                           ("pixel_offset", "<u8")])
 
+    FOG_DTYPE = np.dtype([("pos", "<f8", 3), ("size", "<f8", 3), ("col", "<f8", 3), ("density", "<f8"), ("scatter", "<f8"),
+                          ("bmin", "<f8", 3), ("bmax", "<f8", 3), ("grid_offset", "<u8"), ("grid_count", "<u8")])
+
     def __post_init__(self):
         assert self.MAT_DTYPE.itemsize == C.sizeof(GiMaterial) and self.TEX_DTYPE.itemsize == C.sizeof(GiTexture)
+        assert self.FOG_DTYPE.itemsize == C.sizeof(GiFog)
+        self.fogs = np.ascontiguousarray(self.fogs if self.fogs is not None else np.zeros(0, dtype=self.FOG_DTYPE), dtype=self.FOG_DTYPE)
+        self.fog_grid = _arr(self.fog_grid if self.fog_grid is not None else np.zeros(0), np.float64)
         self.node_box = _arr(self.node_box, np.float64, (-1, 6))
         self.node_child = _arr(self.node_child, np.uint32)
         self.node_mask = _arr(self.node_mask, np.uint8)
@@ -162,4 +177,6 @@ class SceneArrays:
         d.camera = GiCamera((C.c_double * 3)(*cam[0:3]), (C.c_double * 3)(*cam[3:6]), (C.c_double * 3)(*cam[6:9]),
                             (C.c_double * 3)(*cam[9:12]), cam[12], cam[13])
         d.ambient = (C.c_double * 3)(*self.ambient)
+        d.n_fog, d.fogs = int(self.fogs.size), p(self.fogs)
+        d.fog_grid_count, d.fog_grid = int(self.fog_grid.size), p(self.fog_grid)
         return d

@@ -145,9 +145,10 @@ void loadScene(Octree* o, RayTracer& r, const char* fname)  // sceneLoader.cpp:1
             std::fscanf(f, "%lf %lf %lf %lf %lf %lf %lf\n", &pos.x, &pos.y, &pos.z, &col.x, &col.y, &col.z, &rad);
             o->push_back(new Light(pos, dvec3(0, 0, 0), col, rad));
         } else if (std::strcmp(word, "heightFog") == 0) {
-            double v[12];  // atmosphere is a "next" row: parsed, not rendered
-            std::fscanf(f, "%lf %lf %lf %lf %lf %lf %lf %lf %lf %lf %lf %lf\n", v, v + 1, v + 2, v + 3, v + 4, v + 5, v + 6, v + 7, v + 8, v + 9, v + 10, v + 11);
-            std::cout << "heightFog is not supported by the GPU path yet; ignored\n";
+            dvec3 pos, size, col;   // sceneLoader.cpp:150-159
+            double density = 0, scatter = 0, scale = 0;
+            std::fscanf(f, "%lf %lf %lf %lf %lf %lf %lf %lf %lf %lf %lf %lf\n", &pos.x, &pos.y, &pos.z, &size.x, &size.y, &size.z, &col.x, &col.y, &col.z, &density, &scatter, &scale);
+            o->push_back(new HeightFog(pos, size, col, density, scatter, (int)scale));
         } else if (std::strcmp(word, "photons") == 0) {
             std::fscanf(f, "%d %d\n", &r.photons, &r.photon_depth);
         } else if (std::strcmp(word, "samples") == 0) {

@@ -421,7 +421,31 @@ gi_scene_desc FlatScene::desc() const
     d.n_lights = (uint32_t)lights.size(); d.lights = lights.data();
     d.camera = camera;
     for (int i = 0; i < 3; i++) d.ambient[i] = ambient[i];
+    d.n_fog = (uint32_t)fogs.size(); d.fogs = fogs.data();
+    d.fog_grid_count = fog_grid.size(); d.fog_grid = fog_grid.data();
     return d;
+}
+
+// the counter generator of the device (gi_device.cuh: gi_mix64 / gi_rand), restated for the fog noise grid
+static uint64_t mix64(uint64_t z)
+{
+    z += 0x9E3779B97F4A7C15ull;
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    return z ^ (z >> 31);
+}
+HeightFog::HeightFog(dvec3 position, dvec3 size, dvec3 color, double density, double scatter, int noiseScale)
+    : AtmosphereEntity(position, size, color, scatter), d(density), nscale(noiseScale), s(size)
+{
+    const long n = (long)((size.x + 1) * (size.y + 1) * (size.z + 1) * std::pow(noiseScale, 3));   // atmosphere.h:39-41
+    uint64_t ent = 0;   // stream id: a hash of the volume's own parameters, so a fog definition always gets the same grid
+    for (double v : { position.x, position.y, position.z, size.x, size.y, size.z, density, (double)noiseScale }) { uint64_t b; std::memcpy(&b, &v, 8); ent = mix64(ent ^ b); }
+    noiseGrid.reserve(n > 0 ? (size_t)n : 0);
+    for (long i = 0; i < n; i++) {
+        uint64_t h = mix64(0x5EEDF06ull ^ mix64(ent ^ mix64((uint64_t)i)));
+        noiseGrid.push_back((double)(h >> 11) * (1.0 / 9007199254740992.0));
+    }
+    nscale = 1;   // atmosphere.h:47
 }
 
 static void put3(double* p, const dvec3& v) { p[0] = v.x; p[1] = v.y; p[2] = v.z; }
@@ -429,6 +453,17 @@ static void put3(double* p, const dvec3& v) { p[0] = v.x; p[1] = v.y; p[2] = v.z
 void Octree::flatten(const Camera& cam, const dvec3& amb, FlatScene& out) const
 {
     out = FlatScene();
+    for (const AtmosphereEntity* a : at) {
+        const HeightFog* hf = dynamic_cast<const HeightFog*>(a);
+        if (!hf) continue;   // the base class has zero density (atmosphere.h:19-22)
+        gi_fog g;
+        std::memset(&g, 0, sizeof(g));
+        put3(g.pos, hf->pos); put3(g.size, hf->s); put3(g.col, hf->col); put3(g.bmin, hf->bbox.min); put3(g.bmax, hf->bbox.max);
+        g.density = hf->d; g.scatter = hf->sc;
+        g.grid_offset = out.fog_grid.size(); g.grid_count = hf->noiseGrid.size();
+        out.fog_grid.insert(out.fog_grid.end(), hf->noiseGrid.begin(), hf->noiseGrid.end());
+        out.fogs.push_back(g);
+    }
     std::unordered_map<const Entity*, uint32_t> eid;
     for (uint32_t i = 0; i < _all.size(); i++) eid[_all[i]] = i;
     // nodes, breadth-first; existing children contiguous in child order

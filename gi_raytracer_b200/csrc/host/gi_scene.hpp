@@ -214,6 +214,24 @@ struct Camera {  // camera.h:7-31
     Camera(const Camera&) = default;
 };
 
+// atmosphere.h:11-83.  The density field itself is evaluated on the device (fog_density, gi_device.cuh); the host keeps the
+// parameters and the noise grid.  The reference fills the grid from its time-seeded drand(); here the values come from the
+// counter generator (stream 0x5EEDF06, entity, cell), so a scene renders the same fog every run.
+struct AtmosphereEntity {
+    AtmosphereEntity(gi::dvec3 position, gi::dvec3 size, gi::dvec3 color, double scatter) : pos(position), col(color), bbox(position - .5 * size, position + .5 * size), sc(scatter) {}
+    virtual ~AtmosphereEntity() {}
+    gi::dvec3 pos, col;
+    BoundingBox bbox;
+    double sc = 0;
+};
+struct HeightFog : AtmosphereEntity {
+    HeightFog(gi::dvec3 position, gi::dvec3 size, gi::dvec3 color, double density, double scatter, int noiseScale);   // atmosphere.h:37-48
+    double d;
+    int nscale;
+    std::vector<double> noiseGrid;
+    gi::dvec3 s;
+};
+
 struct Photon {  // photon.h:5-15
     Photon(gi::dvec3 o, gi::dvec3 d, gi::dvec3 c) : origin(o), dir(d), col(c) {}
     gi::dvec3 origin, dir, col;
@@ -233,6 +251,8 @@ struct FlatScene {
     std::vector<gi_light> lights;
     gi_camera camera;
     double ambient[3] = { 0, 0, 0 };
+    std::vector<gi_fog> fogs;
+    std::vector<double> fog_grid;
     gi_scene_desc desc() const;
 };
 
@@ -248,6 +268,8 @@ class Octree {  // octree.h:17-65
     };
     Octree(gi::dvec3 mn = gi::dvec3(0, 0, 0), gi::dvec3 mx = gi::dvec3(0, 0, 0)) : _root(BoundingBox(mn, mx)) {}
     std::vector<Light*> lights;
+    std::vector<AtmosphereEntity*> at;   // octree.h:60
+    void push_back(AtmosphereEntity* a) { at.push_back(a); }   // octree.cpp:48-51
     void push_back(Entity* object);   // octree.cpp:25-38
     void push_back(Light* light);     // octree.cpp:41-46
     void rebuild();                   // octree.cpp:53-119

@@ -40,6 +40,7 @@ def load_scene(path, quiet=True) -> SceneArrays:
             mats=_np(d.mats, d.n_mats, SceneArrays.MAT_DTYPE), tex=_np(d.tex, d.n_tex, SceneArrays.TEX_DTYPE),
             tex_pixels=_np(d.tex_pixels, d.tex_pixel_bytes, np.uint8), lights=_np(d.lights, d.n_lights * 11, np.float64), camera=camera,
             ambient=np.array(list(d.ambient)),
+            fogs=_np(d.fogs, d.n_fog, SceneArrays.FOG_DTYPE), fog_grid=_np(d.fog_grid, d.fog_grid_count, np.float64),
             knobs=dict(photons=k[0].value, photon_depth=k[1].value, min_samples=k[2].value, max_samples=k[3].value, noise_thresh=nt.value))
     finally:
         L.gih_scene_free(h)

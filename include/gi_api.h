@@ -71,6 +71,15 @@ typedef struct gi_light { /* light.h:10-58; dir/angle are the caustic cone writt
     double pos[3], col[3], rad, dir[3], angle;
 } gi_light;
 
+/* HeightFog (atmosphere.h:30-83): an axis-aligned volume whose density is a noise grid (trilinear, ^7) times a height falloff.
+ * grid values live in gi_scene_desc.fog_grid[grid_offset .. grid_offset + grid_count). */
+typedef struct gi_fog {
+    double pos[3], size[3], col[3];
+    double density, scatter;        /* `d` and `sc` (scatter is stored by the reference, never read)              */
+    double bmin[3], bmax[3];        /* pos -+ size/2 (atmosphere.h:13)                                            */
+    uint64_t grid_offset, grid_count;
+} gi_fog;
+
 typedef struct gi_camera { /* camera.h:7-31 */
     double pos[3], forward[3], up[3], right[3], sensor_diag, focal_dist;
 } gi_camera;
@@ -109,6 +118,11 @@ typedef struct gi_scene_desc {
     const gi_light* lights;
     gi_camera camera;
     double ambient[3];              /* RayTracer::ambient (raytracer.h:726)                             */
+
+    uint32_t n_fog;                 /* Octree::at (octree.h:60): atmosphere entities, in push_back order */
+    const gi_fog* fogs;
+    uint64_t fog_grid_count;
+    const double* fog_grid;
 } gi_scene_desc;
 
 /* Run-time replacements for the reference's compile-time knobs (util.h:14-31) and RayTracer members. */
