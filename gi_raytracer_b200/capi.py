@@ -22,7 +22,7 @@ API_SYMBOLS = [
     "gi_photon_map_build", "gi_photon_map_info", "gi_photon_map_download", "gi_photon_map_slab_size",
     "gi_photon_map_slab_ptr", "gi_photon_map_adopt_slab", "gi_photon_map_reserve_slab", "gi_photon_gather",
     "gi_photon_gather_dev", "gi_render_tile", "gi_render_tile_dev", "gi_resolve", "gi_resolve_dev", "gi_last_kernel_ms",
-    "gi_last_work", "gi_scene_info", "gi_render_adaptive", "gi_render_adaptive_dev",
+    "gi_last_work", "gi_scene_info", "gi_render_adaptive", "gi_render_adaptive_dev", "gi_fog_density", "gi_raymarch",
 ]
 
 _LIB = None
@@ -60,6 +60,8 @@ def load_library():
         f.argtypes = [vp, sz, vp, vp, u64, vp, vp, vp, vp]
     for f in (L.gi_trace_any, L.gi_trace_any_dev):
         f.argtypes = [vp, sz, vp, vp, vp, u64, vp]
+    L.gi_fog_density.argtypes = [vp, sz, vp, vp, vp]
+    L.gi_raymarch.argtypes = [vp, sz, vp, vp, vp, u64, i32, vp, vp, vp, vp, vp]
     L.gi_photon_trace.argtypes = [vp, i32, i32, u64, C.POINTER(u64), C.POINTER(GiStats)]
     L.gi_photon_upload.argtypes = [vp, sz, vp]
     L.gi_photon_count.argtypes = [vp, C.POINTER(sz)]
@@ -195,6 +197,24 @@ class Context:
         vis = np.empty(n, dtype=np.uint8)
         self._ck(self.L.gi_trace_any(self.h, n, _p(org), _p(d), _p(maxt2), alpha_seed, _p(vis)))
         return vis
+
+    def fog_density(self, pos):
+        """Octree::atmosphereDensity at points -> (density incl. the step-size factor, colour of the last containing volume)."""
+        pos = _f64(pos, 3)
+        n = pos.shape[0]
+        dens, col = np.empty(n), np.empty((n, 3))
+        self._ck(self.L.gi_fog_density(self.h, n, _p(pos), _p(dens), _p(col)))
+        return dens, col
+
+    def raymarch(self, org, d, tmax, seed=1, march=True):
+        """Octree::atmosphereBounds (mint 0, maxt tmax) and, with march, RayTracer::raymarch -> (hit, t0, t1, pos, col)."""
+        org, d = _f64(org, 3), _f64(d, 3)
+        tmax = np.ascontiguousarray(tmax, dtype=np.float64)
+        n = org.shape[0]
+        hit, t0, t1 = np.empty(n, dtype=np.uint8), np.empty(n), np.empty(n)
+        pos, col = np.empty((n, 3)), np.empty((n, 3))
+        self._ck(self.L.gi_raymarch(self.h, n, _p(org), _p(d), _p(tmax), seed, 1 if march else 0, _p(hit), _p(t0), _p(t1), _p(pos), _p(col)))
+        return hit, t0, t1, pos, col
 
     def trace_closest_dev(self, n, org_ptr, dir_ptr, prim_ptr, hit_ptr=None, nrm_ptr=None, uv_ptr=None, alpha_seed=0):
         self._ck(self.L.gi_trace_closest_dev(self.h, n, org_ptr, dir_ptr, alpha_seed, prim_ptr, hit_ptr, nrm_ptr, uv_ptr))

@@ -44,7 +44,7 @@ struct gi_ctx {
     bool has_scene = false;
     DScene S{};
     double root_box[6] = { 0, 0, 0, 0, 0, 0 };
-    DevBuf b_nodes, b_refs, b_geom, b_nrm, b_uv, b_fnorm, b_pmat, b_ptype, b_mats, b_tex, b_texpx, b_lights, b_htab, b_hdims;
+    DevBuf b_nodes, b_refs, b_geom, b_nrm, b_uv, b_fnorm, b_pmat, b_ptype, b_mats, b_tex, b_texpx, b_lights, b_htab, b_hdims, b_fogs, b_foggrid;
     // photons + photon map
     DevBuf b_photons; size_t n_photons = 0;
     bool has_map = false;
@@ -93,6 +93,21 @@ static int fail(gi_ctx* c, int code, const std::string& msg)
         } else {                                                                                                             \
             if (ctx->S.implicit_boxes) KERNEL<false, true><<<(GRID), (BLOCK), 0, ctx->stream>>>(__VA_ARGS__);               \
             else KERNEL<false, false><<<(GRID), (BLOCK), 0, ctx->stream>>>(__VA_ARGS__);                                    \
+        }                                                                                                                    \
+    } while (0)
+
+// launch KERNEL<MODE, IMPL> for the wavefront / photon kernels: MODE 2 (atmosphere) when the scene holds fog volumes
+#define GI_LAUNCH_M(KERNEL, GRID, BLOCK, ...)                                                                                \
+    do {                                                                                                                     \
+        if (ctx->S.n_fog) {                                                                                                  \
+            if (ctx->S.implicit_boxes) KERNEL<2, true><<<(GRID), (BLOCK), 0, ctx->stream>>>(__VA_ARGS__);                   \
+            else KERNEL<2, false><<<(GRID), (BLOCK), 0, ctx->stream>>>(__VA_ARGS__);                                        \
+        } else if (ctx->S.full) {                                                                                            \
+            if (ctx->S.implicit_boxes) KERNEL<1, true><<<(GRID), (BLOCK), 0, ctx->stream>>>(__VA_ARGS__);                   \
+            else KERNEL<1, false><<<(GRID), (BLOCK), 0, ctx->stream>>>(__VA_ARGS__);                                        \
+        } else {                                                                                                             \
+            if (ctx->S.implicit_boxes) KERNEL<0, true><<<(GRID), (BLOCK), 0, ctx->stream>>>(__VA_ARGS__);                   \
+            else KERNEL<0, false><<<(GRID), (BLOCK), 0, ctx->stream>>>(__VA_ARGS__);                                        \
         }                                                                                                                    \
     } while (0)
 
@@ -239,7 +254,7 @@ extern "C" void gi_destroy(gi_ctx* ctx)
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
     DevBuf* all[] = { &ctx->b_nodes, &ctx->b_refs, &ctx->b_geom, &ctx->b_nrm, &ctx->b_uv, &ctx->b_fnorm, &ctx->b_pmat, &ctx->b_ptype, &ctx->b_mats, &ctx->b_tex, &ctx->b_texpx,
-                      &ctx->b_lights, &ctx->b_htab, &ctx->b_hdims, &ctx->b_photons, &ctx->b_slab, &ctx->w0, &ctx->w1, &ctx->w2, &ctx->w3, &ctx->w4, &ctx->w5, &ctx->w6, &ctx->w7,
+                      &ctx->b_lights, &ctx->b_htab, &ctx->b_hdims, &ctx->b_fogs, &ctx->b_foggrid, &ctx->b_photons, &ctx->b_slab, &ctx->w0, &ctx->w1, &ctx->w2, &ctx->w3, &ctx->w4, &ctx->w5, &ctx->w6, &ctx->w7,
                       &ctx->w8, &ctx->w9, &ctx->b_cnt, &ctx->b_accum, &ctx->b_scan0, &ctx->b_scan1, &ctx->b_misc, &ctx->b_work, &ctx->b_tail, &ctx->b_binkey, &ctx->b_binperm,
                       &ctx->b_binhist, &ctx->b_bincur, &ctx->b_gnode, &ctx->b_gperm, &ctx->b_ghist, &ctx->b_gcur, &ctx->b_gheavy };
     for (DevBuf* b : all) b->release();
@@ -313,6 +328,11 @@ extern "C" int gi_scene_upload(gi_ctx* ctx, const gi_scene_desc* sc)
         if (t.kind == GI_TEX_IMAGE && (t.width <= 0 || t.height <= 0 || t.pixel_offset + (uint64_t)t.width * t.height * 4 > sc->tex_pixel_bytes)) return fail(ctx, GI_ERR_INVALID, "image texture out of bounds or empty");
         if (t.kind < 0 || t.kind > GI_TEX_IMAGE) return fail(ctx, GI_ERR_INVALID, "unknown texture kind");
     }
+    for (uint32_t i = 0; i < sc->n_fog; i++) {
+        const gi_fog& g = sc->fogs[i];
+        if (g.grid_offset + g.grid_count > sc->fog_grid_count) return fail(ctx, GI_ERR_INVALID, "fog noise grid out of bounds");
+        if (!(g.size[1] != 0)) return fail(ctx, GI_ERR_INVALID, "fog volume with zero height");
+    }
     // nodes: SoA description -> 64-byte records
     std::vector<DNode> nodes(sc->n_nodes);
     for (uint32_t i = 0; i < sc->n_nodes; i++) {
@@ -385,6 +405,8 @@ extern "C" int gi_scene_upload(gi_ctx* ctx, const gi_scene_desc* sc)
     CK(upload(ctx->b_tex, sc->tex, (size_t)sc->n_tex, st));
     CK(upload(ctx->b_texpx, sc->tex_pixels, (size_t)sc->tex_pixel_bytes, st));
     CK(upload(ctx->b_lights, sc->lights, (size_t)sc->n_lights, st));
+    CK(upload(ctx->b_fogs, sc->fogs, (size_t)sc->n_fog, st));
+    CK(upload(ctx->b_foggrid, sc->fog_grid, (size_t)(sc->n_fog ? sc->fog_grid_count : 0), st));
     CK(cudaStreamSynchronize(st));   // the host staging vectors die at return
     DScene& S = ctx->S;
     S.nodes = ctx->b_nodes.as<DNode>(); S.refs = ctx->b_refs.as<DLeafRef>();
@@ -393,6 +415,7 @@ extern "C" int gi_scene_upload(gi_ctx* ctx, const gi_scene_desc* sc)
     S.prim_mat = ctx->b_pmat.as<uint32_t>(); S.prim_type = ctx->b_ptype.as<uint8_t>();
     S.mats = ctx->b_mats.as<gi_material>(); S.tex = ctx->b_tex.as<gi_texture>(); S.tex_pixels = ctx->b_texpx.as<uint8_t>();
     S.lights = ctx->b_lights.as<gi_light>(); S.n_lights = sc->n_lights; S.n_mats = sc->n_mats; S.n_tex = sc->n_tex;
+    S.n_fog = sc->n_fog; S.fogs = ctx->b_fogs.as<gi_fog>(); S.fog_grid = ctx->b_foggrid.as<double>();
     S.cam = sc->camera;
     for (int k = 0; k < 3; k++) S.ambient[k] = sc->ambient[k];
     S.full = full ? 1u : 0u;
@@ -414,6 +437,42 @@ extern "C" int gi_scene_info(gi_ctx* ctx, uint32_t out[4])
     if (!ctx->has_scene) return fail(ctx, GI_ERR_NO_SCENE, "no scene");
     out[0] = ctx->S.full; out[1] = ctx->S.implicit_boxes; out[2] = ctx->S.n_nodes; out[3] = ctx->S.n_refs;
     return GI_OK;
+}
+
+// ---- atmosphere, batch forms (host pointers) -------------------------------------------------------------------------------------------
+extern "C" int gi_fog_density(gi_ctx* ctx, size_t n, const double* pos, double* dens, double* col)
+{
+    if (!ctx || (n && (!pos || !dens))) return GI_ERR_INVALID;
+    if (!ctx->has_scene) return fail(ctx, GI_ERR_NO_SCENE, "gi_fog_density needs gi_scene_upload");
+    if (!n) return GI_OK;
+    CK(cudaSetDevice(ctx->device));
+    CK(ctx->w0.reserve(n * 24)); CK(ctx->w1.reserve(n * 8)); CK(ctx->w2.reserve(n * 24));
+    CK(cudaMemcpyAsync(ctx->w0.p, pos, n * 24, cudaMemcpyHostToDevice, ctx->stream));
+    k_fog_density<<<grid_for(n, 128), 128, 0, ctx->stream>>>(ctx->S, n, ctx->w0.as<double>(), ctx->w1.as<double>(), ctx->w2.as<double>());
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(dens, ctx->w1.p, n * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    if (col) CK(cudaMemcpyAsync(col, ctx->w2.p, n * 24, cudaMemcpyDeviceToHost, ctx->stream));
+    return gi_synchronize(ctx);
+}
+extern "C" int gi_raymarch(gi_ctx* ctx, size_t n, const double* org, const double* dir, const double* tmax, uint64_t seed, int march, uint8_t* hit, double* t0, double* t1, double* pos, double* col)
+{
+    if (!ctx || (n && (!org || !dir || !tmax || !hit))) return GI_ERR_INVALID;
+    if (!ctx->has_scene) return fail(ctx, GI_ERR_NO_SCENE, "gi_raymarch needs gi_scene_upload");
+    if (!n) return GI_OK;
+    CK(cudaSetDevice(ctx->device));
+    CK(ctx->w0.reserve(n * 24)); CK(ctx->w1.reserve(n * 24)); CK(ctx->w2.reserve(n * 8)); CK(ctx->w3.reserve(n)); CK(ctx->w4.reserve(n * 16)); CK(ctx->w5.reserve(n * 24)); CK(ctx->w6.reserve(n * 24));
+    CK(cudaMemcpyAsync(ctx->w0.p, org, n * 24, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->w1.p, dir, n * 24, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->w2.p, tmax, n * 8, cudaMemcpyHostToDevice, ctx->stream));
+    k_raymarch<<<grid_for(n, 128), 128, 0, ctx->stream>>>(ctx->S, n, ctx->w0.as<double>(), ctx->w1.as<double>(), ctx->w2.as<double>(), seed, march, ctx->w3.as<uint8_t>(), ctx->w4.as<double>(), ctx->w5.as<double>(),
+                                                          ctx->w6.as<double>());
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(hit, ctx->w3.p, n, cudaMemcpyDeviceToHost, ctx->stream));
+    if (t0) CK(cudaMemcpy2DAsync(t0, 8, ctx->w4.p, 16, 8, n, cudaMemcpyDeviceToHost, ctx->stream));
+    if (t1) CK(cudaMemcpy2DAsync(t1, 8, (const char*)ctx->w4.p + 8, 16, 8, n, cudaMemcpyDeviceToHost, ctx->stream));
+    if (pos) CK(cudaMemcpyAsync(pos, ctx->w5.p, n * 24, cudaMemcpyDeviceToHost, ctx->stream));
+    if (col) CK(cudaMemcpyAsync(col, ctx->w6.p, n * 24, cudaMemcpyDeviceToHost, ctx->stream));
+    return gi_synchronize(ctx);
 }
 
 // ---- Halton entry points --------------------------------------------------------------------------------------------------------------
@@ -615,7 +674,7 @@ extern "C" int gi_photon_trace(gi_ctx* ctx, int count, int max_depth, uint64_t s
             while (width < 32 && (uint64_t)n_active * (uint64_t)(2 * width) <= (1u << 19)) width *= 2;
             CK(cudaMemsetAsync(n_out, 0, 4, ctx->stream));
             uint32_t* out = lists[round & 1];
-            GI_LAUNCH(k_photon_round, grid_for((size_t)n_active * width, GI_BLOCK), GI_BLOCK, ctx->S, count, max_depth, seed, base_try, width, n_active, in, out, n_out, O);
+            GI_LAUNCH_M(k_photon_round, grid_for((size_t)n_active * width, GI_BLOCK), GI_BLOCK, ctx->S, count, max_depth, seed, base_try, width, n_active, in, out, n_out, O);
             launches++;
             CK(cudaGetLastError());
             const uint32_t was = n_active;
@@ -983,7 +1042,7 @@ static int render_device(gi_ctx* ctx, const gi_render_params* P, int x0, int y0,
                     ScopedTimer t(ctx, "tail");
                     CK(cudaMemsetAsync(&ctx->b_tail.as<DTailCounters>()->next, 0, 4, ctx->stream));
                     const unsigned tail_grid = std::min<unsigned>(grid_for(n_active, GI_WPB), 148u * 3u);   // 3 blocks of 4 warps fit per SM at 168 registers
-                    GI_LAUNCH(k_tail, tail_grid, GI_WPB * 32, ctx->S, ctx->G, have_map ? 1 : 0, *P, depth, n_active, in, PS, ctx->b_tail.as<DTailCounters>(), Q);
+                    GI_LAUNCH_M(k_tail, tail_grid, GI_WPB * 32, ctx->S, ctx->G, have_map ? 1 : 0, *P, depth, n_active, in, PS, ctx->b_tail.as<DTailCounters>(), Q);
                     launches++;
                 }
                 if (Q.qmax) {
@@ -1005,8 +1064,8 @@ static int render_device(gi_ctx* ctx, const gi_render_params* P, int x0, int y0,
                 ScopedTimer t(ctx, "bounce");
                 if (persistent) {
                     const unsigned grid = std::min<unsigned>(grid_for(n_active, GI_BLOCK), 148u * GI_MINB);
-                    GI_LAUNCH(k_bounce_p, grid, GI_BLOCK, ctx->S, *P, depth, n_active, in, perm, out, H, PS, C, work_ptr(ctx, 0), ctx->b_misc.as<uint32_t>());
-                } else GI_LAUNCH(k_bounce, grid_for(n_active, GI_BLOCK), GI_BLOCK, ctx->S, *P, depth, n_active, in, perm, out, H, PS, C, work_ptr(ctx, 0));
+                    GI_LAUNCH_M(k_bounce_p, grid, GI_BLOCK, ctx->S, *P, depth, n_active, in, perm, out, H, PS, C, work_ptr(ctx, 0), ctx->b_misc.as<uint32_t>());
+                } else GI_LAUNCH_M(k_bounce, grid_for(n_active, GI_BLOCK), GI_BLOCK, ctx->S, *P, depth, n_active, in, perm, out, H, PS, C, work_ptr(ctx, 0));
             }
             CK(cudaGetLastError());
             DCounters hc;
@@ -1017,7 +1076,7 @@ static int render_device(gi_ctx* ctx, const gi_render_params* P, int x0, int y0,
             if (hc.n_hits) {
                 if (ctx->S.n_lights) {
                     ScopedTimer t(ctx, "direct");
-                    GI_LAUNCH(k_direct, grid_for(hc.n_hits, GI_BLOCK), GI_BLOCK, ctx->S, *P, depth, hc.n_hits, H, PS, work_ptr(ctx, 2));
+                    GI_LAUNCH_M(k_direct, grid_for(hc.n_hits, GI_BLOCK), GI_BLOCK, ctx->S, *P, depth, hc.n_hits, H, PS, work_ptr(ctx, 2));
                     launches++;
                     n_shadow += (uint64_t)hc.n_hits * ctx->S.n_lights;
                 }

@@ -53,6 +53,9 @@ struct DScene {
     const DHaltonDim* halton_dims;   // [256]
     uint32_t full;                   // scene needs the FULL traversal (alpha materials or primitives that do not write uv)
     uint32_t implicit_boxes;         // every child box equals the partition formula of its parent box (checked at upload)
+    uint32_t n_fog;                  // Octree::at: HeightFog volumes (atmosphere.h), in push_back order
+    const gi_fog* fogs;
+    const double* fog_grid;          // noise grids of all volumes, concatenated
 };
 
 // ---- fp64 vectors in glm's evaluation order -------------------------------------------------------------
@@ -109,6 +112,11 @@ __host__ __device__ __forceinline__ double gi_rand(uint64_t seed, uint64_t path,
 #define SITE_PH_DIR_V 8ull
 #define SITE_PH_SEC_U 9ull
 #define SITE_PH_SEC_V 10ull
+#define SITE_FOG_RAD 11ull      // raymarch draws: counter = step (radiance), light << 32 | step (visible), step (photons)
+#define SITE_FOG_SHADOW 12ull
+#define SITE_FOG_PHOTON 13ull
+#define SITE_PH_FOG_U 14ull
+#define SITE_PH_FOG_V 15ull
 #define SITE(s, c) (((uint64_t)(s) << 56) | (uint64_t)(c))
 #define PHOTON_PATH_BIT (1ull << 63)
 
@@ -944,4 +952,112 @@ __device__ __forceinline__ d3 secondary_ray(const DScene& S, const gi_material& 
         contrib = contrib + (color - contrib) * 0.5;   // glm::mix(contrib, inf, 0.5)
     }
     return refDir;
+}
+
+// ---- atmosphere: HeightFog::density (atmosphere.h:50-81), Octree::atmosphereDensity / atmosphereBounds (octree.cpp:214-251),
+// RayTracer::raymarch (raytracer.h:509-529) --------------------------------------------------------------------------------------
+#define GI_D_RAYMARCH_STEPSIZE 0.04   // util.h:29
+// fastPow (util.h:100-111): exponent bit-hack on the high word, low word cleared.  The (int) cast of an out-of-range double is
+// what x86's cvttsd2si returns (INT_MIN), e.g. for a == 0.
+__device__ __forceinline__ double fast_pow(double a, double b)
+{
+    const double v = b * (double)(__double2hiint(a) - 1072632447) + 1072632447.0;
+    const int hi = (v >= 2147483648.0 || v < -2147483648.0 || v != v) ? (int)0x80000000 : (int)v;
+    return __hiloint2double(hi, 0);
+}
+// one noise-grid read: the reference indexes a std::vector<double> with a double expression (truncated to size_t); an index
+// past the end is undefined behaviour there and reads 0 here
+__device__ __forceinline__ double fog_cell(const DScene& S, const gi_fog& g, double idx)
+{
+    const unsigned long long i = (unsigned long long)idx;
+    return i < g.grid_count ? __ldg(S.fog_grid + g.grid_offset + i) : 0.0;
+}
+__device__ __forceinline__ double fog_density(const DScene& S, const gi_fog& g, d3 p)
+{
+    const double sx = g.size[0], sz = g.size[2];          // nscale == 1 after the constructor (atmosphere.h:47)
+    const double ymax = g.pos[1] + .5 * g.size[1];
+    const d3 rel = (p - ld3(g.bmin)) * 1.0;
+    const int ix = (int)rel.x, iy = (int)rel.y, iz = (int)rel.z;
+    const double dx = rel.x - ix, dy = rel.y - iy, dz = rel.z - iz;
+    // the row stride is s.x for both outer terms (atmosphere.h:61-71), kept as written
+    const double r0 = (ix * sx + iy) * sz + iz, r1 = ((ix + 1) * sx + iy) * sz + iz;
+    const double r2 = (ix * sx + (iy + 1)) * sz + iz, r3 = ((ix + 1) * sx + (iy + 1)) * sz + iz;
+    const double c00 = (1 - dx) * fog_cell(S, g, r0) + dx * fog_cell(S, g, r1);
+    const double c01 = (1 - dx) * fog_cell(S, g, r0 + 1) + dx * fog_cell(S, g, r1 + 1);
+    const double c10 = (1 - dx) * fog_cell(S, g, r2) + dx * fog_cell(S, g, r3);
+    const double c11 = (1 - dx) * fog_cell(S, g, r2 + 1) + dx * fog_cell(S, g, r3 + 1);
+    const double c0 = c00 * (1 - dy) + c10 * dy;
+    const double c1 = c01 * (1 - dy) + c11 * dy;
+    const double noise = fast_pow((1 - dz) * c0 + dz * c1, 7);
+    return g.density * noise * fast_pow((ymax - p.y) / g.size[1], 2);
+}
+// Octree::atmosphereDensity (octree.cpp:214-226): sum over the volumes containing pos; col = the last one's colour
+__device__ __forceinline__ double atmosphere_density(const DScene& S, d3 pos, d3& col)
+{
+    double d = 0;
+    for (uint32_t k = 0; k < S.n_fog; k++) {
+        const gi_fog& g = S.fogs[k];
+        if (box_contains(g.bmin, g.bmax, pos)) { col = ld3(g.col); d += GI_D_RAYMARCH_STEPSIZE * fog_density(S, g, pos); }
+    }
+    return d;
+}
+// Octree::atmosphereBounds (octree.cpp:229-251): `min` starts at 0 and can only shrink, `max` starts at 0 and can only grow, so
+// the march starts at the caller's mint and ends at the farthest exit, clipped to the caller's maxt
+__device__ __forceinline__ bool atmosphere_bounds(const DScene& S, const DRay& r, double& mint, double& maxt)
+{
+    double mn = 0, mx = 0; bool hit = false;
+    for (uint32_t k = 0; k < S.n_fog; k++) {
+        const gi_fog& g = S.fogs[k];
+        double tmin = mint, tmax = maxt; bool ok = true;
+        {
+            double t0 = (g.bmin[0] - r.o.x) * r.inv.x, t1 = (g.bmax[0] - r.o.x) * r.inv.x;
+            if (r.inv.x < 0.0) { double tmp = t0; t0 = t1; t1 = tmp; }
+            tmin = t0 > tmin ? t0 : tmin; tmax = t1 < tmax ? t1 : tmax;
+            if (tmax <= tmin) ok = false;
+        }
+        if (ok) {
+            double t0 = (g.bmin[1] - r.o.y) * r.inv.y, t1 = (g.bmax[1] - r.o.y) * r.inv.y;
+            if (r.inv.y < 0.0) { double tmp = t0; t0 = t1; t1 = tmp; }
+            tmin = t0 > tmin ? t0 : tmin; tmax = t1 < tmax ? t1 : tmax;
+            if (tmax <= tmin) ok = false;
+        }
+        if (ok) {
+            double t0 = (g.bmin[2] - r.o.z) * r.inv.z, t1 = (g.bmax[2] - r.o.z) * r.inv.z;
+            if (r.inv.z < 0.0) { double tmp = t0; t0 = t1; t1 = tmp; }
+            tmin = t0 > tmin ? t0 : tmin; tmax = t1 < tmax ? t1 : tmax;
+            if (tmax <= tmin) ok = false;
+        }
+        if (ok) { mn = tmin < mn ? tmin : mn; mx = mx < tmax ? tmax : mx; hit = true; }
+    }
+    mint = mint < mn ? mn : mint;
+    maxt = mx < maxt ? mx : maxt;
+    return hit;
+}
+// RayTracer::raymarch (raytracer.h:509-529); one counter draw per step.  Steps outside every volume have density 0 and can
+// never scatter (drand() < 0 is false), so only the position is advanced there — with the same sequential additions.
+__device__ __noinline__ bool raymarch(const DScene& S, const DRay& r, d3& hit, d3& col, double mint, double maxt, uint64_t seed, uint64_t path, uint64_t depth, uint64_t site, uint64_t hi)
+{
+    double t = mint + GI_D_SHADOW_BIAS;
+    d3 cur = r.o + r.d * mint;
+    const d3 stepv = r.d * GI_D_RAYMARCH_STEPSIZE;
+    for (uint64_t step = 0; t < maxt; step++) {
+        const double dens = atmosphere_density(S, cur, col);
+        if (dens > 0.0 && gi_rand(seed, path, depth, SITE(site, (hi << 32) | step)) < dens) { hit = cur; return true; }
+        cur = cur + stepv;
+        t += GI_D_RAYMARCH_STEPSIZE;
+    }
+    return false;
+}
+// the fog part of RayTracer::radiance (raytracer.h:209-228): true when the segment origin..surface hit scatters in a volume
+__device__ __forceinline__ bool fog_scatter(const DScene& S, const DRay& r, d3 surf_hit, d3& fhit, d3& fcol, uint64_t seed, uint64_t path, uint64_t depth, uint64_t site)
+{
+    double tmin = 0, tmax = sqrt(len2(surf_hit - r.o));   // glm::length
+    fcol = mk3(0, 0, 0);
+    return atmosphere_bounds(S, r, tmin, tmax) && raymarch(S, r, fhit, fcol, tmin, tmax, seed, path, depth, site, 0);
+}
+// the fog part of RayTracer::visible (raytracer.h:308-316): tmax is the SQUARED distance, as written
+__device__ __forceinline__ bool fog_blocks(const DScene& S, const DRay& r, double mt, uint64_t seed, uint64_t path, uint64_t depth, uint64_t light)
+{
+    double tmin = 0, tmax = mt; d3 h, c = mk3(0, 0, 0);
+    return atmosphere_bounds(S, r, tmin, tmax) && raymarch(S, r, h, c, tmin, tmax, seed, path, depth, SITE_FOG_SHADOW, light);
 }

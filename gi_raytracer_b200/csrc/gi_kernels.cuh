@@ -23,6 +23,30 @@ __global__ void k_halton_index(DHEnum he, size_t n, const uint32_t* s, const uin
     if (i < n) out[i] = henum_index(he, s[i], x[i], y[i]);
 }
 
+// ---- atmosphere, batch forms: Octree::atmosphereDensity at points; Octree::atmosphereBounds (+ RayTracer::raymarch) on rays --------------
+__global__ void k_fog_density(DScene S, size_t n, const double* __restrict__ pos, double* __restrict__ dens, double* __restrict__ col)
+{
+    size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    d3 c = mk3(0, 0, 0);
+    dens[i] = atmosphere_density(S, ld3(pos + 3 * i), c);
+    st3(col + 3 * i, c);
+}
+__global__ void k_raymarch(DScene S, size_t n, const double* __restrict__ org, const double* __restrict__ dir, const double* __restrict__ tmax, uint64_t seed, int march, uint8_t* __restrict__ hit,
+                           double* __restrict__ t01, double* __restrict__ pos, double* __restrict__ col)
+{
+    size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    DRay r = ray_as_stored(ld3(org + 3 * i), ld3(dir + 3 * i));
+    double a = 0, b = tmax[i];
+    d3 h = mk3(0, 0, 0), c = mk3(0, 0, 0);
+    bool ok = atmosphere_bounds(S, r, a, b);
+    t01[2 * i] = a; t01[2 * i + 1] = b;
+    if (march) { ok = ok && raymarch(S, r, h, c, a, b, seed, (uint64_t)i, 0, SITE_FOG_RAD, 0); if (!ok) { h = mk3(0, 0, 0); c = mk3(0, 0, 0); } }
+    hit[i] = ok ? 1 : 0;
+    st3(pos + 3 * i, h); st3(col + 3 * i, c);
+}
+
 // ---- K1: camera rays (raytracer.h:74-78, 112-129) ------------------------------------------------------------------------------
 struct DFrame { int w, h, x0, y0, tw, th; double halfW, halfH; d3 center, right, up, pos; DHEnum he; };
 
@@ -901,10 +925,11 @@ struct DHitList {
 struct DPathState { uint32_t* sample; uint64_t* key; double* L; double* Lc; };
 struct DCounters { uint32_t n_next, n_hits; unsigned long long closest, shadow, gathers; };
 
-template <bool FULL, bool IMPL>
+template <int MODE, bool IMPL>
 __global__ void __launch_bounds__(GI_BLOCK, GI_MINB) k_bounce(DScene S, gi_render_params P, int depth, uint32_t n, DQueue in, const uint32_t* __restrict__ perm, DQueue out, DHitList H,
                                                      DPathState PS, DCounters* C, unsigned long long* work)
 {
+    constexpr bool FULL = MODE != 0, FOG = MODE == 2;   // MODE 0: uv-writing opaque primitives only, 1: any scene, 2: any scene + atmosphere
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     bool active = i < n;
     if (active && perm) i = perm[i];   // binned order (k_bin_*)
@@ -935,6 +960,10 @@ __global__ void __launch_bounds__(GI_BLOCK, GI_MINB) k_bounce(DScene S, gi_rende
             rough = m.roughness;
             d3 f = mk3(1, 1, 1);
             refDir = secondary_ray(S, m, r, hn, tu, tv, sx, sy, color, f, contrib, offset, P.seed, key, (uint64_t)depth);   // :207
+            if (FOG) {   // raytracer.h:209-228: the segment scattered in a volume before reaching the surface
+                d3 fh, fc;
+                if (fog_scatter(S, r, hp, fh, fc, P.seed, key, (uint64_t)depth, SITE_FOG_RAD)) { hp = fh; refDir = random_unit_vec(sx, sy); f = fc; color = fc; contrib = fc; rough = 1; }
+            }
             double q = contrib.x < contrib.y ? contrib.y : contrib.x; q = q < contrib.z ? contrib.z : q;                   // compMax :263
             cont = depth <= P.min_depth || gi_rand(P.seed, key, (uint64_t)depth, SITE(SITE_RR, 0)) < q;                    // :265
             wdir = T * color;
@@ -983,10 +1012,11 @@ __global__ void __launch_bounds__(GI_BLOCK, GI_MINB) k_bounce(DScene S, gi_rende
 #ifndef GI_REFILL_MIN
 #define GI_REFILL_MIN 20
 #endif
-template <bool FULL, bool IMPL>
+template <int MODE, bool IMPL>
 __global__ void __launch_bounds__(GI_BLOCK, GI_MINB) k_bounce_p(DScene S, gi_render_params P, int depth, uint32_t n, DQueue in, const uint32_t* __restrict__ perm, DQueue out, DHitList H,
                                                        DPathState PS, DCounters* C, unsigned long long* work, uint32_t* next_ray)
 {
+    constexpr bool FULL = MODE != 0, FOG = MODE == 2;   // MODE 0: uv-writing opaque primitives only, 1: any scene, 2: any scene + atmosphere
     __shared__ int s_walking[GI_BLOCK / 32];
     const unsigned lane = threadIdx.x & 31u;
     const int wib = threadIdx.x >> 5;
@@ -1050,6 +1080,10 @@ __global__ void __launch_bounds__(GI_BLOCK, GI_MINB) k_bounce_p(DScene S, gi_ren
                 rough = m.roughness;
                 d3 f = mk3(1, 1, 1);
                 refDir = secondary_ray(S, m, r, hn, tu, tv, sx, sy, color, f, contrib, offset, P.seed, key, (uint64_t)depth);   // :207
+                if (FOG) {   // raytracer.h:209-228: the segment scattered in a volume before reaching the surface
+                    d3 fh, fc;
+                    if (fog_scatter(S, r, hp, fh, fc, P.seed, key, (uint64_t)depth, SITE_FOG_RAD)) { hp = fh; refDir = random_unit_vec(sx, sy); f = fc; color = fc; contrib = fc; rough = 1; }
+                }
                 double q = contrib.x < contrib.y ? contrib.y : contrib.x; q = q < contrib.z ? contrib.z : q;                   // compMax :263
                 cont = depth <= P.min_depth || gi_rand(P.seed, key, (uint64_t)depth, SITE(SITE_RR, 0)) < q;                    // :265
                 wdir = T * color;
@@ -1089,9 +1123,10 @@ __global__ void __launch_bounds__(GI_BLOCK, GI_MINB) k_bounce_p(DScene S, gi_ren
 }
 
 // ---- K3 in the pipeline: direct light with one shadow ray per light (raytracer.h:230-256) -----------------------------------------
-template <bool FULL, bool IMPL>
+template <int MODE, bool IMPL>
 __global__ void __launch_bounds__(GI_BLOCK, GI_MINB) k_direct(DScene S, gi_render_params P, int depth, uint32_t n, DHitList H, DPathState PS, unsigned long long* work)
 {
+    constexpr bool FULL = MODE != 0, FOG = MODE == 2;   // MODE 0: uv-writing opaque primitives only, 1: any scene, 2: any scene + atmosphere
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     uint32_t wn = 0, wp = 0;
     if (i >= n) { tally2(work, 0, 0); return; }
@@ -1107,7 +1142,9 @@ __global__ void __launch_bounds__(GI_BLOCK, GI_MINB) k_direct(DScene S, gi_rende
         double maxt = len2(lightDir);
         double hfrac = 1 / (GI_D_PI * len2(ld3(light.pos) - p));                                                             // :238
         DRay sr = make_ray(sp, lightDir);                                                                                     // :241
-        if (trace_visible<FULL, IMPL>(S, sr, maxt, P.seed, key, (uint64_t)depth, l, wn, wp)) {                                      // :243
+        bool vis = trace_visible<FULL, IMPL>(S, sr, maxt, P.seed, key, (uint64_t)depth, l, wn, wp);                                 // :243
+        if (FOG && vis && fog_blocks(S, sr, maxt, P.seed, key, (uint64_t)depth, l)) vis = false;                              // :308-316
+        if (vis) {
             double d = dot3(nn, normalize3(ld3(light.pos) - p));
             if (d < 0) d = 0;
             double lv = pow_like_libm(d, (1.0 / rough));                                                                      // :252
@@ -1135,9 +1172,10 @@ struct DTailQ { double* pos; double* dir; double* w; double* rgb; uint32_t* coun
 
 struct DTailCounters { unsigned long long closest, shadow, gathers, nodes_c, prims_c, nodes_s, prims_s, g_depth, g_cand, g_sel; unsigned int next; unsigned int pad; };
 
-template <bool FULL, bool IMPL>
+template <int MODE, bool IMPL>
 __global__ void __launch_bounds__(GI_WPB * 32) k_tail(DScene S, DGatherMap G, int have_map, gi_render_params P, int depth0, uint32_t n, DQueue in, DPathState PS, DTailCounters* TC, DTailQ Q)
 {
+    constexpr bool FULL = MODE != 0, FOG = MODE == 2;   // MODE 0: uv-writing opaque primitives only, 1: any scene, 2: any scene + atmosphere
     __shared__ uint32_t s_stack[GI_WPB][GI_STACK_MAX];
     __shared__ double s_sum[GI_WPB][96];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
@@ -1170,6 +1208,10 @@ __global__ void __launch_bounds__(GI_WPB * 32) k_tail(DScene S, DGatherMap G, in
         double rough = m.roughness, offset = GI_D_SHADOW_BIAS;
         d3 f = mk3(1, 1, 1);
         d3 refDir = secondary_ray(S, m, r, hn, tu, tv, sx, sy, color, f, contrib, offset, P.seed, key, (uint64_t)depth);
+        if (FOG) {   // raytracer.h:209-228: the segment scattered in a volume before reaching the surface
+            d3 fh, fc;
+            if (fog_scatter(S, r, hp, fh, fc, P.seed, key, (uint64_t)depth, SITE_FOG_RAD)) { hp = fh; refDir = random_unit_vec(sx, sy); f = fc; color = fc; contrib = fc; rough = 1; }
+        }
         double q = contrib.x < contrib.y ? contrib.y : contrib.x; q = q < contrib.z ? contrib.z : q;
         bool cont = depth <= P.min_depth || gi_rand(P.seed, key, (uint64_t)depth, SITE(SITE_RR, 0)) < q;
         d3 wdir = T * color;
@@ -1190,7 +1232,9 @@ __global__ void __launch_bounds__(GI_WPB * 32) k_tail(DScene S, DGatherMap G, in
                 double hfrac = 1 / (GI_D_PI * len2(ld3(light.pos) - hp));
                 DRay sr = make_ray(sp, lightDir);
                 c_shadow++;
-                if (trace_visible_warp<FULL, IMPL>(S, sr, maxt, P.seed, key, (uint64_t)depth, l, stack, lane, ns, ps)) {
+                bool vis = trace_visible_warp<FULL, IMPL>(S, sr, maxt, P.seed, key, (uint64_t)depth, l, stack, lane, ns, ps);
+                if (FOG && vis && fog_blocks(S, sr, maxt, P.seed, key, (uint64_t)depth, l)) vis = false;
+                if (vis) {
                     double d = dot3(hn, normalize3(ld3(light.pos) - hp));
                     if (d < 0) d = 0;
                     li = (ld3(light.col) * pow_like_libm(d, (1.0 / rough))) * hfrac;
@@ -1361,7 +1405,7 @@ __global__ void k_resolve(size_t n3, const double* accum, int spp, uint8_t* rgb8
 struct DPhotonOut { double* ph; uint8_t* stored; unsigned long long* tries; unsigned long long* traces; unsigned long long* work; };
 
 // one emission try of photon index i at light li (raytracer.h:604-695): true when a photon was stored into `out`
-template <bool FULL, bool IMPL>
+template <bool FULL, bool IMPL, bool FOG>
 __device__ __forceinline__ bool photon_try(const DScene& S, int count, int max_depth, uint64_t seed, int i, uint32_t li, int tries, d3& ph_pos, d3& ph_dir, d3& ph_col, unsigned long long& n_traces,
                                            uint32_t& wn, uint32_t& wp)
 {
@@ -1396,6 +1440,14 @@ __device__ __forceinline__ bool photon_try(const DScene& S, int count, int max_d
             double sv = fmod(gi_rand(seed, path, (uint64_t)(depth + 1), SITE(SITE_PH_SEC_V, 0)) + 13 * i, 1.0);
             d3 color = tex_get(S, m.diffuse_tex, tu, tv);
             d3 refDir = secondary_ray(S, m, r, norm, tu, tv, su, sv, color, f, contrib, offset, seed, path, (uint64_t)(depth + 1));   // :656
+            if (FOG) {                                                                  // :658-675
+                d3 ah, ac;
+                if (fog_scatter(S, r, hit, ah, ac, seed, path, (uint64_t)(depth + 1), SITE_FOG_PHOTON)) {
+                    const double fu = fmod(gi_rand(seed, path, (uint64_t)(depth + 1), SITE(SITE_PH_FOG_U, 0)) + 13 * i, 1.0);
+                    const double fv = fmod(gi_rand(seed, path, (uint64_t)(depth + 1), SITE(SITE_PH_FOG_V, 0)) + 7 * i, 1.0);
+                    hit = ah; refDir = random_unit_vec(fu, fv); f = ac; roughness = 1;
+                }
+            }
             col = col * f;                                                              // :677
             r = make_ray(hit + norm * offset, refDir);                                  // :679-680
             isCaustic = true;
@@ -1420,10 +1472,11 @@ __device__ __forceinline__ bool photon_try(const DScene& S, int count, int max_d
 // list shrinks (1, 2, 4 .. 32) and keeps ~half a million lanes busy: ~25 rounds instead of 500.  Tries and traces are
 // tallied as the sequential loop would have made them (up to and including the winner); same try, same counter-PRNG keys,
 // same photons.
-template <bool FULL, bool IMPL>
+template <int MODE, bool IMPL>
 __global__ void __launch_bounds__(GI_BLOCK, GI_MINB) k_photon_round(DScene S, int count, int max_depth, uint64_t seed, int base_try, int width, uint32_t n_active, const uint32_t* __restrict__ in_list,
                                                                   uint32_t* __restrict__ out_list, uint32_t* __restrict__ n_out, DPhotonOut O)
 {
+    constexpr bool FULL = MODE != 0, FOG = MODE == 2;   // MODE 0: uv-writing opaque primitives only, 1: any scene, 2: any scene + atmosphere
     const uint32_t gt = blockIdx.x * blockDim.x + threadIdx.x;
     const unsigned lane = threadIdx.x & 31u;
     const uint32_t j = gt / (uint32_t)width;       // active-list entry
@@ -1437,7 +1490,7 @@ __global__ void __launch_bounds__(GI_BLOCK, GI_MINB) k_photon_round(DScene S, in
     if (j < n_active) slot = in_list ? in_list[j] : j;
     if (live) {
         const int i = (int)(slot / S.n_lights); const uint32_t li = slot % S.n_lights;
-        stored = photon_try<FULL, IMPL>(S, count, max_depth, seed, i, li, tries, pp, pd, pc, my_traces, wn, wp);
+        stored = photon_try<FULL, IMPL, FOG>(S, count, max_depth, seed, i, li, tries, pp, pd, pc, my_traces, wn, wp);
     }
     // the slot's lanes are adjacent: lowest successful try wins
     const unsigned sm = __ballot_sync(0xffffffffu, stored);

@@ -205,6 +205,19 @@ int gi_trace_any(gi_ctx* ctx, size_t n, const double* org, const double* dir, co
 int gi_trace_any_dev(gi_ctx* ctx, size_t n, const double* org, const double* dir, const double* maxt2, uint64_t alpha_seed,
                      uint8_t* vis);
 
+/* ---- atmosphere.  The fog itself acts inside gi_render_* / gi_photon_trace (RayTracer::radiance
+ *      raytracer.h:209-228, ::visible :308-316, ::tracePhotons :658-675) whenever the uploaded scene has n_fog > 0; the
+ *      batch forms below expose its pieces for comparison with the reference.
+ *      gi_fog_density: Octree::atmosphereDensity (octree.cpp:214-226) = sum of RAYMARCH_STEPSIZE * HeightFog::density
+ *        (atmosphere.h:50-81) over the volumes containing pos; col (optional) = colour of the last containing volume.
+ *      gi_raymarch: Octree::atmosphereBounds (octree.cpp:229-251) with mint = 0, maxt = tmax[i] -> hit/t0/t1; with
+ *        march != 0 followed by RayTracer::raymarch (raytracer.h:509-529, counter PRNG: path = ray index, depth 0, one
+ *        draw per step) -> hit = scattered, pos = scatter point, col = volume colour (zeros when not scattered).
+ *      gi_trace_any stays the geometric part of RayTracer::visible. ------------------------------------------- */
+int gi_fog_density(gi_ctx* ctx, size_t n, const double* pos, double* dens, double* col);
+int gi_raymarch(gi_ctx* ctx, size_t n, const double* org, const double* dir, const double* tmax, uint64_t seed, int march,
+                uint8_t* hit, double* t0, double* t1, double* pos, double* col);
+
 /* ---- photons: RayTracer::tracePhotons (raytracer.h:582-715); photons are {origin, dir, col} = 9 fp64 (photon.h) */
 int gi_photon_trace(gi_ctx* ctx, int count, int max_depth, uint64_t seed, uint64_t* n_stored, gi_stats* stats);
 int gi_photon_upload(gi_ctx* ctx, size_t n, const double* photons9);

@@ -65,6 +65,11 @@ double go_rand(uint64_t seed, uint64_t path, uint64_t depth, uint64_t site)
 #define SITE_PH_DIR_V 8ull
 #define SITE_PH_SEC_U 9ull
 #define SITE_PH_SEC_V 10ull
+#define SITE_FOG_RAD 11ull    /* raymarch draws: counter = step (radiance), light<<32|step (visible), step (photons) */
+#define SITE_FOG_SHADOW 12ull
+#define SITE_FOG_PHOTON 13ull
+#define SITE_PH_FOG_U 14ull
+#define SITE_PH_FOG_V 15ull
 #define SITE(s, c) (((uint64_t)(s) << 56) | (uint64_t)(c))
 #define PHOTON_PATH_BIT (1ull << 63)
 
@@ -966,6 +971,128 @@ static v3 light_point_in_range(const gi_light* l, double x, double y)
     return light_point(l, x, y);
 }
 
+/* ------------------------------------------------------------------------------------------------------------
+ * atmosphere: HeightFog::density (atmosphere.h:50-81), Octree::atmosphereDensity / atmosphereBounds
+ * (octree.cpp:214-251), RayTracer::raymarch (raytracer.h:509-529)
+ * ---------------------------------------------------------------------------------------------------------- */
+#define GO_RAYMARCH_STEPSIZE 0.04 /* util.h:29 */
+/* fastPow (util.h:100-111): the exponent bit-hack on the high word, low word cleared */
+static inline double fast_pow(double a, double b)
+{
+    union { double d; int32_t x[2]; } u;
+    u.d = a;
+    u.x[1] = (int32_t)(b * (u.x[1] - 1072632447) + 1072632447);
+    u.x[0] = 0;
+    return u.d;
+}
+/* one noise-grid read.  The reference indexes std::vector<double> with a double expression (converted to size_t by
+ * truncation); an index past the end is undefined behaviour there and reads 0 here. */
+static inline double fog_cell(const gi_scene_desc* sc, const gi_fog* g, double idx)
+{
+    uint64_t i = (uint64_t)idx;
+    return i < g->grid_count ? sc->fog_grid[g->grid_offset + i] : 0.0;
+}
+static double fog_density(const gi_scene_desc* sc, const gi_fog* g, v3 p)
+{
+    const int nscale = 1;                                             /* atmosphere.h:47: the ctor resets nscale to 1 */
+    const double sx = g->size[0], sy = g->size[1], sz = g->size[2];
+    double ymax = g->pos[1] + .5 * sy;
+    v3 rel = scale(sub(p, ld3(g->bmin)), (double)nscale);
+    int ix = (int)rel.x, iy = (int)rel.y, iz = (int)rel.z;
+    double dx = nscale * (rel.x - ix), dy = nscale * (rel.y - iy), dz = nscale * (rel.z - iz);
+    (void)sy;
+    /* the row stride is s.x for BOTH outer terms (atmosphere.h:61-71), kept as written */
+    double c00 = (1 - dx) * fog_cell(sc, g, (ix * nscale * sx + iy) * nscale * sz + iz) + dx * fog_cell(sc, g, ((ix + 1) * nscale * sx + iy) * nscale * sz + iz);
+    double c01 = (1 - dx) * fog_cell(sc, g, (ix * nscale * sx + iy) * nscale * sz + iz + 1) + dx * fog_cell(sc, g, ((ix + 1) * nscale * sx + iy) * nscale * sz + iz + 1);
+    double c10 = (1 - dx) * fog_cell(sc, g, (ix * nscale * sx + (iy + 1)) * nscale * sz + iz) + dx * fog_cell(sc, g, ((ix + 1) * nscale * sx + (iy + 1)) * nscale * sz + iz);
+    double c11 = (1 - dx) * fog_cell(sc, g, (ix * nscale * sx + (iy + 1)) * nscale * sz + iz + 1) + dx * fog_cell(sc, g, ((ix + 1) * nscale * sx + (iy + 1)) * nscale * sz + iz + 1);
+    double c0 = c00 * (1 - dy) + c10 * dy;
+    double c1 = c01 * (1 - dy) + c11 * dy;
+    double noise = fast_pow((1 - dz) * c0 + dz * c1, 7);
+    return g->density * noise * fast_pow((ymax - p.y) / g->size[1], 2);
+}
+/* Octree::atmosphereDensity (octree.cpp:214-226): sum of STEPSIZE*density over the volumes containing pos; col = the last one's */
+static double atmosphere_density(const gi_scene_desc* sc, v3 pos, v3* col)
+{
+    double d = 0;
+    for (uint32_t k = 0; k < sc->n_fog; k++) {
+        const gi_fog* g = &sc->fogs[k];
+        if (box_contains(g->bmin, pos)) { *col = ld3(g->col); d += GO_RAYMARCH_STEPSIZE * fog_density(sc, g, pos); }
+    }
+    return d;
+}
+/* BoundingBox::intersect with both outputs (bbox.h:47-73); bmin/bmax are adjacent in gi_fog, i.e. one 6-double box */
+static inline int box_hit2(const double* b, const ray_t* r, double tmin, double tmax, double* t0o, double* t1o)
+{
+    const double* o = &r->o.x; const double* inv = &r->inv.x;
+    for (int i = 0; i < 3; i++) {
+        double t0 = (b[i] - o[i]) * inv[i];
+        double t1 = (b[3 + i] - o[i]) * inv[i];
+        if (inv[i] < 0.0) { double tmp = t0; t0 = t1; t1 = tmp; }
+        tmin = t0 > tmin ? t0 : tmin;
+        tmax = t1 < tmax ? t1 : tmax;
+        if (tmax <= tmin) return 0;
+    }
+    *t0o = tmin; *t1o = tmax;
+    return 1;
+}
+/* Octree::atmosphereBounds (octree.cpp:229-251).  `min` starts at 0 and only shrinks, `max` starts at 0 and only grows:
+ * the march therefore always starts at the caller's mint and ends at the farthest exit (clipped to the caller's maxt). */
+static int atmosphere_bounds(const gi_scene_desc* sc, const ray_t* r, double* mint, double* maxt)
+{
+    double mn = 0, mx = 0; int hit = 0;
+    for (uint32_t k = 0; k < sc->n_fog; k++) {
+        double a = 0, b = 0;
+        if (box_hit2(sc->fogs[k].bmin, r, *mint, *maxt, &a, &b)) { mn = a < mn ? a : mn; mx = mx < b ? b : mx; hit = 1; }   /* std::min / std::max */
+    }
+    *mint = *mint < mn ? mn : *mint;
+    *maxt = mx < *maxt ? mx : *maxt;
+    return hit;
+}
+/* RayTracer::raymarch (raytracer.h:509-529); one counter draw per step: site(step) */
+static int raymarch(const gi_scene_desc* sc, const ray_t* r, v3* hit, v3* col, double mint, double maxt, uint64_t seed, uint64_t path, uint64_t depth, uint64_t site, uint64_t hi)
+{
+    double t = mint + GO_SHADOW_BIAS;
+    v3 cur = add(r->o, scale(r->d, mint));
+    v3 stepv = scale(r->d, GO_RAYMARCH_STEPSIZE);
+    for (uint64_t step = 0; t < maxt; step++) {
+        if (go_rand(seed, path, depth, SITE(site, (hi << 32) | step)) < atmosphere_density(sc, cur, col)) { *hit = cur; return 1; }
+        cur = add(cur, stepv);
+        t += GO_RAYMARCH_STEPSIZE;
+    }
+    return 0;
+}
+/* the tail of RayTracer::visible (raytracer.h:308-316): tmax is the SQUARED distance, as written */
+static int fog_blocks(const gi_scene_desc* sc, const ray_t* r, double mt, uint64_t seed, uint64_t path, uint64_t depth, uint64_t site, uint64_t light)
+{
+    double tmin = 0, tmax = mt; v3 h, c = V(0, 0, 0);
+    if (!sc->n_fog) return 0;
+    return atmosphere_bounds(sc, r, &tmin, &tmax) && raymarch(sc, r, &h, &c, tmin, tmax, seed, path, depth, site, light);
+}
+void go_fog_density(const gi_scene_desc* sc, size_t n, const double* pos, double* dens, double* col)
+{
+    for (size_t i = 0; i < n; i++) { v3 c = V(0, 0, 0); dens[i] = atmosphere_density(sc, ld3(pos + 3 * i), &c); if (col) st3(col + 3 * i, c); }
+}
+void go_atmosphere_bounds(const gi_scene_desc* sc, size_t n, const double* org, const double* dir, const double* tmax_in, uint8_t* hit, double* mint, double* maxt)
+{
+    for (size_t i = 0; i < n; i++) {
+        ray_t r = ray_as_stored(ld3(org + 3 * i), ld3(dir + 3 * i));
+        double a = 0, b = tmax_in[i];
+        hit[i] = (uint8_t)atmosphere_bounds(sc, &r, &a, &b); mint[i] = a; maxt[i] = b;
+    }
+}
+void go_raymarch(const gi_scene_desc* sc, size_t n, const double* org, const double* dir, const double* tmax_in, uint64_t seed, uint8_t* hit, double* pos, double* col)
+{
+#pragma omp parallel for schedule(dynamic, 64)
+    for (long i = 0; i < (long)n; i++) {
+        ray_t r = ray_as_stored(ld3(org + 3 * i), ld3(dir + 3 * i));
+        double a = 0, b = tmax_in[i]; v3 h = V(0, 0, 0), c = V(0, 0, 0);
+        hit[i] = (uint8_t)(atmosphere_bounds(sc, &r, &a, &b) && raymarch(sc, &r, &h, &c, a, b, seed, (uint64_t)i, 0, SITE_FOG_RAD, 0));
+        if (!hit[i]) { h = V(0, 0, 0); c = V(0, 0, 0); }
+        st3(pos + 3 * i, h); st3(col + 3 * i, c);
+    }
+}
+
 typedef struct { uint64_t closest, shadow, gathers; } tally_t;
 
 /* samplePhotons for one query (same arithmetic as go_gather) */
@@ -1007,6 +1134,16 @@ static v3 radiance_path(const gi_scene_desc* sc, const go_pmap* pm, const gi_ren
         v3 f = V(1, 1, 1);
         v3 norm = c.n;
         v3 refDir = secondary_ray(sc, m, &ray, &norm, c.uv, sx, sy, &f, &contrib, &offset, P->seed, path, (uint64_t)depth); /* :207 */
+        if (sc->n_fog) {                                                                        /* :209-228 */
+            double tmin = 0, tmax = length3(sub(c.p, ray.o));
+            if (atmosphere_bounds(sc, &ray, &tmin, &tmax)) {
+                v3 fh, fcol = V(0, 0, 0);
+                if (raymarch(sc, &ray, &fh, &fcol, tmin, tmax, P->seed, path, (uint64_t)depth, SITE_FOG_RAD, 0)) {
+                    double u3[3]; go_random_unit_vec(sx, sy, u3);
+                    c.p = fh; refDir = ld3(u3); f = fcol; color = fcol; contrib = fcol; roughness = 1;   /* normal, uv, offset stay the surface's */
+                }
+            }
+        }
         for (uint32_t li = 0; li < sc->n_lights; li++) {                                        /* :230-256 */
             const gi_light* light = &sc->lights[li];
             v3 sp = add(c.p, scale(norm, GO_SHADOW_BIAS));
@@ -1015,6 +1152,7 @@ static v3 radiance_path(const gi_scene_desc* sc, const go_pmap* pm, const gi_ren
             double hfrac = 1 / (GO_PI * len2(sub(ld3(light->pos), c.p)));
             ray_t sr = make_ray(sp, lightDir);
             int vis = visible_one(sc, &sr, maxt, P->seed, path, (uint64_t)depth, li, NULL, NULL); tl->shadow++;
+            if (vis && fog_blocks(sc, &sr, maxt, P->seed, path, (uint64_t)depth, SITE_FOG_SHADOW, li)) vis = 0;   /* :308-316 */
             if (vis) {
                 double d = dot(norm, normalize(sub(ld3(light->pos), c.p)));
                 if (d < 0) d = 0;
@@ -1168,6 +1306,18 @@ size_t go_trace_photons(const gi_scene_desc* sc, int count, int max_depth, uint6
                             double su = fmod(go_rand(seed, path, (uint64_t)(depth + 1), SITE(SITE_PH_SEC_U, 0)) + 5 * (int)i, 1);
                             double sv = fmod(go_rand(seed, path, (uint64_t)(depth + 1), SITE(SITE_PH_SEC_V, 0)) + 13 * (int)i, 1);
                             v3 refDir = secondary_ray(sc, m, &r, &norm, uv, su, sv, &f, &contrib, &offset, seed, path, (uint64_t)(depth + 1)); /* :656 */
+                            if (sc->n_fog) {                                                         /* :658-675 */
+                                double tmin = 0, tmax = length3(sub(hit, r.o));
+                                if (atmosphere_bounds(sc, &r, &tmin, &tmax)) {
+                                    v3 ah, acol = V(0, 0, 0);
+                                    if (raymarch(sc, &r, &ah, &acol, tmin, tmax, seed, path, (uint64_t)(depth + 1), SITE_FOG_PHOTON, 0)) {
+                                        double u3[3];
+                                        go_random_unit_vec(fmod(go_rand(seed, path, (uint64_t)(depth + 1), SITE(SITE_PH_FOG_U, 0)) + 13 * (int)i, 1),
+                                                           fmod(go_rand(seed, path, (uint64_t)(depth + 1), SITE(SITE_PH_FOG_V, 0)) + 7 * (int)i, 1), u3);
+                                        hit = ah; refDir = ld3(u3); f = acol; roughness = 1;
+                                    }
+                                }
+                            }
                             col = mul(col, f);                                                       /* :677 */
                             r = make_ray(add(hit, scale(norm, offset)), refDir);                     /* :679-680 */
                             isCaustic = 1;

@@ -82,6 +82,14 @@ void go_random_unit_vec(double x, double y, double out[3]);                     
 void go_refr(const double inc[3], const double n[3], double eta, double out[3]);                   /* util.h:173-181 */
 double go_fast_precise_pow(double a, double b);                                                    /* util.h:113-136 */
 
+/* atmosphere (atmosphere.h:50-81, octree.cpp:214-251, raytracer.h:509-529), batch forms for known-answer tests:
+ * Octree::atmosphereDensity at points (includes the STEPSIZE factor; col = colour of the last containing volume),
+ * Octree::atmosphereBounds on rays with mint = 0 and maxt = tmax_in, and atmosphereBounds + raymarch with the counter
+ * PRNG (path = ray index, depth 0, one draw per step) */
+void go_fog_density(const gi_scene_desc* sc, size_t n, const double* pos, double* dens, double* col);
+void go_atmosphere_bounds(const gi_scene_desc* sc, size_t n, const double* org, const double* dir, const double* tmax_in, uint8_t* hit, double* mint, double* maxt);
+void go_raymarch(const gi_scene_desc* sc, size_t n, const double* org, const double* dir, const double* tmax_in, uint64_t seed, uint8_t* hit, double* pos, double* col);
+
 /* photon tracing (raytracer.h:582-715) with the counter PRNG; photons9 capacity = count * n_lights; returns stored */
 size_t go_trace_photons(const gi_scene_desc* sc, int count, int max_depth, uint64_t seed, double* photons9, uint64_t* tries,
                         uint64_t* traces);

@@ -182,6 +182,17 @@ static void dump_scene(Octree* scene, RayTracer& rt, std::ostringstream& meta)
     std::vector<double> knobs = { (double)rt.photons, (double)rt.photon_depth, (double)rt.min_samples, (double)rt.max_samples,
                                   rt.noise_thresh, rt.ambient.x, rt.ambient.y, rt.ambient.z };
     dump("knobs.f64", knobs);
+    // atmosphere entities (octree.h:60): parameters and the noise grid exactly as the reference's ctor filled it
+    std::vector<double> fogp, fogg;
+    for (AtmosphereEntity* a : scene->at) {
+        HeightFog* hf = dynamic_cast<HeightFog*>(a);
+        if (!hf) continue;
+        push3(fogp, hf->pos); push3(fogp, hf->s); push3(fogp, hf->col); fogp.push_back(hf->d); fogp.push_back(hf->sc);
+        push3(fogp, hf->bbox.min); push3(fogp, hf->bbox.max); fogp.push_back((double)fogg.size()); fogp.push_back((double)hf->noiseGrid.size());
+        fogg.insert(fogg.end(), hf->noiseGrid.begin(), hf->noiseGrid.end());
+    }
+    dump("fog_params.f64", fogp); dump("fog_grid.f64", fogg);
+    meta << "fogs=" << fogp.size() / 19 << "\n";
     meta << "entities=" << g_ents.size() << "\nnodes=" << mask.size() << "\nleaf_refs=" << refs.size() << "\nlights=" << scene->lights.size() << "\n";
 }
 
@@ -270,7 +281,7 @@ int main(int argc, char** argv)
 {
     if (argc < 3) {
         fprintf(stderr, "usage: gi_ref <scene.scn> <outdir> [--w W --h H --s0 A --s1 B --max-depth D --min-depth M --photons P --samples N --x0 --y0 --x1 --y1 --repeat R] cmd...\n"
-                        "cmds: scene halton samplers primary shadow photons gather radiance run time-frame time-gather bench-frame\n");
+                        "cmds: scene halton samplers primary fog shadow photons gather radiance run time-frame time-gather bench-frame\n");
         return 1;
     }
     const char* scn = argv[1];
@@ -326,7 +337,7 @@ int main(int argc, char** argv)
     // -- primary rays + closest hit ------------------------------------------------------------------
     std::vector<double> hit_pos, hit_nrm, hit_uv, ray_o, ray_d;
     std::vector<uint32_t> hit_id, ray_idx;
-    if (has("primary") || has("shadow") || has("gather") || has("time-gather")) {
+    if (has("primary") || has("shadow") || has("gather") || has("time-gather") || has("fog")) {
         for (int s = s0; s < s1; s++) for (int y = y0; y < y1; y++) for (int x = x0; x < x1; x++) {
             int idx; Ray ray = camera_ray(rt, fr, sampler, he, w, h, x, y, s, idx);
             glm::dvec3 p(0), n(0); glm::dvec2 uv(0); Entity* cur = nullptr;
@@ -341,6 +352,36 @@ int main(int argc, char** argv)
             dump("hit_id.u32", hit_id); dump("hit_pos.f64", hit_pos); dump("hit_nrm.f64", hit_nrm); dump("hit_uv.f64", hit_uv);
         }
         meta << "primary_rays=" << hit_id.size() << "\n";
+    }
+
+    // -- atmosphere known answers: Octree::atmosphereDensity at points, Octree::atmosphereBounds on the primary rays -------
+    if (has("fog")) {
+        std::vector<double> fp, fd, fc;
+        uint64_t st = 0x9E3779B97F4A7C15ull;
+        auto rnd = [&]() { st = st * 6364136223846793005ull + 1442695040888963407ull; return (double)(st >> 11) * (1.0 / 9007199254740992.0); };
+        for (AtmosphereEntity* a : scene->at) {
+            glm::dvec3 lo = a->bbox.min, ext = a->bbox.max - a->bbox.min;
+            for (int i = 0; i < 4000; i++) {
+                // mostly inside the volume, some on / outside its faces (half-open containment)
+                glm::dvec3 p = lo + ext * glm::dvec3(1.1 * rnd() - 0.05, 1.1 * rnd() - 0.05, 1.1 * rnd() - 0.05);
+                if (i % 97 == 0) p.x = lo.x; if (i % 89 == 0) p.y = a->bbox.max.y; if (i % 83 == 0) p.z = lo.z;
+                glm::dvec3 col(0); double sc = 0;
+                double d = scene->atmosphereDensity(p, col, sc);
+                push3(fp, p); fd.push_back(d); push3(fc, col);
+            }
+        }
+        dump("fog_pos.f64", fp); dump("fog_dens.f64", fd); dump("fog_col.f64", fc);
+        std::vector<double> bt; std::vector<uint8_t> bh;
+        size_t i = 0;
+        for (int s = s0; s < s1; s++) for (int y = y0; y < y1; y++) for (int x = x0; x < x1; x++, i++) {
+            int idx; Ray ray = camera_ray(rt, fr, sampler, he, w, h, x, y, s, idx);   // the very Ray object the primary loop traced
+            glm::dvec3 p(hit_pos[3 * i], hit_pos[3 * i + 1], hit_pos[3 * i + 2]);
+            double tmin = 0, tmax = hit_id[i] == 0xFFFFFFFFu ? 1e30 : glm::length(p - ray.origin);   // raytracer.h:209-212
+            bt.push_back(tmax);
+            bool ok = scene->atmosphereBounds(ray, tmin, tmax);
+            bh.push_back(ok ? 1 : 0); bt.push_back(tmin); bt.push_back(tmax);
+        }
+        dump("fogb_hit.u8", bh); dump("fogb_t.f64", bt);
     }
 
     // -- shadow rays from the primary hits toward Halton-chosen light points ------------------------

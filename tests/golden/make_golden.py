@@ -9,6 +9,9 @@ Fixtures (all raw outputs of the reference's own functions, OMP_NUM_THREADS=1, t
                      sampler KATs, camera rays, closest hits, shadow rays + visibility, 3000 photons, photon-map
                      cells, gather candidates / 32-nearest sets / radiance estimates.
   caustics_small.npz scenes/caustics/caustics.scn at 40x40: rays, hits, shadows, 2500 photons + gather.
+  fog_small.npz      scenes/caustics_fog_dense at 40x40 (same geometry, camera and rays as caustics_small): the HeightFog
+                     parameters and noise grid as the reference's constructor filled it, Octree::atmosphereDensity at 4000
+                     points, Octree::atmosphereBounds on the primary rays.
 """
 import os
 import sys
@@ -51,6 +54,10 @@ def main():
     out["meta_w_h_s0_s1"] = np.array([40, 40, 0, 1])
     np.savez_compressed(os.path.join(HERE, "caustics_small.npz"), **out)
     print("caustics_small", meta)
+    d, meta = R.run_ref(os.path.join(root, "scenes/caustics_fog_dense/caustics_fog_dense.scn"), ["scene", "primary", "fog"], w=40, h=40, s0=0, s1=1, photons=10)
+    out = pack(d, ["fog_params.f64", "fog_grid.f64", "fog_pos.f64", "fog_dens.f64", "fog_col.f64", "fogb_hit.u8", "fogb_t.f64"])
+    np.savez_compressed(os.path.join(HERE, "fog_small.npz"), **out)
+    print("fog_small", meta)
 
 
 if __name__ == "__main__":

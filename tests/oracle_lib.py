@@ -59,6 +59,9 @@ def lib():
     L.go_render_adaptive.argtypes = [vp, vp, vp, i32, i32, C.c_double, i32, i32, i32, i32, vp, vp]
     L.go_resolve.argtypes = [sz, vp, i32, vp]
     L.go_child_boxes.argtypes = [vp, vp]
+    L.go_fog_density.argtypes = [vp, sz, vp, vp, vp]
+    L.go_atmosphere_bounds.argtypes = [vp, sz, vp, vp, vp, vp, vp, vp]
+    L.go_raymarch.argtypes = [vp, sz, vp, vp, vp, u64, vp, vp, vp]
     _LIB = L
     return L
 
@@ -158,6 +161,39 @@ def trace_any_cot(scene, org, d, maxt2, alpha_seed=0):
     desc = scene.desc()
     L.go_trace_any_cot(C.byref(desc), n, _p(org), _p(d), _p(maxt2), alpha_seed, _p(vis), _p(nn), _p(npr))
     return vis, nn, npr
+
+
+def fog_density(scene, pos):
+    """Octree::atmosphereDensity at points: (density incl. the step-size factor, colour of the last containing volume)."""
+    L = lib()
+    pos = _f64(pos, 3)
+    n = pos.shape[0]
+    dens, col = np.empty(n), np.empty((n, 3))
+    desc = scene.desc()
+    L.go_fog_density(C.byref(desc), n, _p(pos), _p(dens), _p(col))
+    return dens, col
+
+
+def atmosphere_bounds(scene, org, d, tmax):
+    L = lib()
+    org, d = _f64(org, 3), _f64(d, 3)
+    tmax = np.ascontiguousarray(tmax, dtype=np.float64)
+    n = org.shape[0]
+    hit, t0, t1 = np.empty(n, dtype=np.uint8), np.empty(n), np.empty(n)
+    desc = scene.desc()
+    L.go_atmosphere_bounds(C.byref(desc), n, _p(org), _p(d), _p(tmax), _p(hit), _p(t0), _p(t1))
+    return hit, t0, t1
+
+
+def raymarch(scene, org, d, tmax, seed=1):
+    L = lib()
+    org, d = _f64(org, 3), _f64(d, 3)
+    tmax = np.ascontiguousarray(tmax, dtype=np.float64)
+    n = org.shape[0]
+    hit, pos, col = np.empty(n, dtype=np.uint8), np.empty((n, 3)), np.empty((n, 3))
+    desc = scene.desc()
+    L.go_raymarch(C.byref(desc), n, _p(org), _p(d), _p(tmax), seed, _p(hit), _p(pos), _p(col))
+    return hit, pos, col
 
 
 class PMap:

@@ -133,7 +133,17 @@ def scene_from_arrays(load_):
     tex["a"] = texcol
     cam = load(d, "camera.f64")
     knobs = load(d, "knobs.f64")
-    return SceneArrays(node_box=nb, node_child=child, node_mask=nm, node_prim_off=off, node_prim_cnt=nc, leaf_prims=lrefs,
+    fogs, fog_grid = None, None
+    try:
+        fp = load(d, "fog_params.f64").reshape(-1, 19)
+        fog_grid = load(d, "fog_grid.f64")
+    except (FileNotFoundError, KeyError):
+        fp = np.zeros((0, 19))
+    if fp.shape[0]:
+        fogs = np.zeros(fp.shape[0], dtype=SceneArrays.FOG_DTYPE)
+        fogs["pos"], fogs["size"], fogs["col"], fogs["density"], fogs["scatter"] = fp[:, 0:3], fp[:, 3:6], fp[:, 6:9], fp[:, 9], fp[:, 10]
+        fogs["bmin"], fogs["bmax"], fogs["grid_offset"], fogs["grid_count"] = fp[:, 11:14], fp[:, 14:17], fp[:, 17].astype(np.uint64), fp[:, 18].astype(np.uint64)
+    return SceneArrays(fogs=fogs, fog_grid=fog_grid, node_box=nb, node_child=child, node_mask=nm, node_prim_off=off, node_prim_cnt=nc, leaf_prims=lrefs,
                        prim_type=load(d, "ent_type.u8"), prim_geom=load(d, "ent_pos.f64"), prim_nrm=load(d, "ent_nrm.f64"),
                        prim_uv=load(d, "ent_uv.f64"), prim_fnorm=load(d, "ent_fnorm.f64"), prim_mat=inv.astype(np.uint32).ravel(),
                        mats=mats, tex=tex, tex_pixels=np.zeros(0, dtype=np.uint8), lights=load(d, "lights.f64"), camera=cam,
