@@ -22,7 +22,7 @@ API_SYMBOLS = [
     "gi_photon_map_build", "gi_photon_map_info", "gi_photon_map_download", "gi_photon_map_slab_size",
     "gi_photon_map_slab_ptr", "gi_photon_map_adopt_slab", "gi_photon_map_reserve_slab", "gi_photon_gather",
     "gi_photon_gather_dev", "gi_render_tile", "gi_render_tile_dev", "gi_resolve", "gi_resolve_dev", "gi_last_kernel_ms",
-    "gi_last_work", "gi_scene_info", "gi_render_adaptive", "gi_render_adaptive_dev", "gi_fog_density", "gi_raymarch",
+    "gi_last_work", "gi_scene_info", "gi_render_adaptive", "gi_render_adaptive_dev", "gi_fog_density", "gi_raymarch", "gi_octree_build", "gi_octree_download",
 ]
 
 _LIB = None
@@ -62,6 +62,10 @@ def load_library():
         f.argtypes = [vp, sz, vp, vp, vp, u64, vp]
     L.gi_fog_density.argtypes = [vp, sz, vp, vp, vp]
     L.gi_raymarch.argtypes = [vp, sz, vp, vp, vp, u64, i32, vp, vp, vp, vp, vp]
+    L.gi_octree_build.argtypes = [vp, u32, vp, vp, vp, vp, C.POINTER(u32), C.POINTER(u32), C.POINTER(C.c_double)]
+    L.gi_octree_download.argtypes = [vp, vp, vp, vp, vp, vp, vp]
+    L.gih_scene_prim_bbox.argtypes = [vp, vp]
+    L.gih_scene_rebuild_device.argtypes = [vp, vp, C.POINTER(C.c_double)]
     L.gi_photon_trace.argtypes = [vp, i32, i32, u64, C.POINTER(u64), C.POINTER(GiStats)]
     L.gi_photon_upload.argtypes = [vp, sz, vp]
     L.gi_photon_count.argtypes = [vp, C.POINTER(sz)]
@@ -215,6 +219,19 @@ class Context:
         pos, col = np.empty((n, 3)), np.empty((n, 3))
         self._ck(self.L.gi_raymarch(self.h, n, _p(org), _p(d), _p(tmax), seed, 1 if march else 0, _p(hit), _p(t0), _p(t1), _p(pos), _p(col)))
         return hit, t0, t1, pos, col
+
+    def octree_build(self, prim_type, prim_geom, prim_bbox, root_box):
+        """Octree::rebuild / Node::partition on the device -> (dict of gi_scene_desc node arrays, device ms)."""
+        prim_type = np.ascontiguousarray(prim_type, dtype=np.uint8)
+        prim_geom, prim_bbox = _f64(prim_geom, 9), _f64(prim_bbox, 6)
+        root_box = np.ascontiguousarray(root_box, dtype=np.float64)
+        nn, nr, ms = C.c_uint32(), C.c_uint32(), C.c_double()
+        self._ck(self.L.gi_octree_build(self.h, prim_type.size, _p(prim_type), _p(prim_geom), _p(prim_bbox), _p(root_box), C.byref(nn), C.byref(nr), C.byref(ms)))
+        out = dict(node_box=np.empty((nn.value, 6)), node_child=np.empty(nn.value, dtype=np.uint32), node_mask=np.empty(nn.value, dtype=np.uint8),
+                   node_prim_off=np.empty(nn.value, dtype=np.uint32), node_prim_cnt=np.empty(nn.value, dtype=np.uint32), leaf_prims=np.empty(nr.value, dtype=np.uint32))
+        self._ck(self.L.gi_octree_download(self.h, _p(out["node_box"]), _p(out["node_child"]), _p(out["node_mask"]), _p(out["node_prim_off"]), _p(out["node_prim_cnt"]),
+                                           _p(out["leaf_prims"]) if nr.value else None))
+        return out, ms.value
 
     def trace_closest_dev(self, n, org_ptr, dir_ptr, prim_ptr, hit_ptr=None, nrm_ptr=None, uv_ptr=None, alpha_seed=0):
         self._ck(self.L.gi_trace_closest_dev(self.h, n, org_ptr, dir_ptr, alpha_seed, prim_ptr, hit_ptr, nrm_ptr, uv_ptr))

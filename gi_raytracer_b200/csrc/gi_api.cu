@@ -11,6 +11,7 @@
 #include <vector>
 
 #include "gi_kernels.cuh"
+#include "gi_octree_build.cuh"
 
 #define GI_VERSION "gi_b200 0.1.0 (sm_100a)"
 #define GI_MAX_PATHS (1u << 23)   // paths in flight per chunk of the wavefront
@@ -55,6 +56,10 @@ struct gi_ctx {
     // workspaces
     DevBuf w0, w1, w2, w3, w4, w5, w6, w7, w8, w9;           // API staging
     DevBuf q_a[5], q_b[5], hl[7], ps[4], tq[5], ad[6], b_cnt, b_accum, b_scan0, b_scan1, b_misc, b_work, b_tail, b_binkey, b_binperm, b_binhist, b_bincur, b_gnode, b_gperm, b_ghist, b_gcur, b_gheavy;
+    // device octree build (gi_octree_build): inputs, outputs (gi_scene_desc layout), per-level work buffers
+    DevBuf ob_type, ob_geom, ob_bbox, ob_nodebox, ob_child, ob_mask, ob_poff, ob_pcnt, ob_leaf, ob_list[2], ob_owner[2], ob_flags, ob_pos, ob_abox[2], ob_anode[2], ob_astart[2], ob_acount[2],
+        ob_slotactive[2], ob_slot[5], ob_rank[3], ob_tot;
+    uint32_t ob_n_nodes = 0, ob_n_refs = 0; bool ob_valid = false;
     bool no_implicit = false;      // GI_NO_IMPLICIT_BOXES at gi_create: always load child boxes (for A/B tests)
     int trace_mode = 0;            // 0: thread per ray, 1: warp per ray (API batch kernels; GI_TRACE_MODE)
     uint32_t tail_threshold = 32768; // queues smaller than this finish in the tail megakernel (GI_TAIL_THRESHOLD, 0 = off)
@@ -258,6 +263,13 @@ extern "C" void gi_destroy(gi_ctx* ctx)
                       &ctx->w8, &ctx->w9, &ctx->b_cnt, &ctx->b_accum, &ctx->b_scan0, &ctx->b_scan1, &ctx->b_misc, &ctx->b_work, &ctx->b_tail, &ctx->b_binkey, &ctx->b_binperm,
                       &ctx->b_binhist, &ctx->b_bincur, &ctx->b_gnode, &ctx->b_gperm, &ctx->b_ghist, &ctx->b_gcur, &ctx->b_gheavy };
     for (DevBuf* b : all) b->release();
+    {
+        DevBuf* ob[] = { &ctx->ob_type, &ctx->ob_geom, &ctx->ob_bbox, &ctx->ob_nodebox, &ctx->ob_child, &ctx->ob_mask, &ctx->ob_poff, &ctx->ob_pcnt, &ctx->ob_leaf, &ctx->ob_flags, &ctx->ob_pos, &ctx->ob_tot };
+        for (DevBuf* b : ob) b->release();
+        for (int k = 0; k < 2; k++) { ctx->ob_list[k].release(); ctx->ob_owner[k].release(); ctx->ob_abox[k].release(); ctx->ob_anode[k].release(); ctx->ob_astart[k].release(); ctx->ob_acount[k].release(); ctx->ob_slotactive[k].release(); }
+        for (auto& b : ctx->ob_slot) b.release();
+        for (auto& b : ctx->ob_rank) b.release();
+    }
     for (auto& b : ctx->q_a) b.release();
     for (auto& b : ctx->q_b) b.release();
     for (auto& b : ctx->hl) b.release();
@@ -610,6 +622,125 @@ static int scan_exclusive(gi_ctx* ctx, const uint32_t* in, int stride_words, uin
     } else if (total_dev) CK(cudaMemsetAsync(total_dev, 0, 4, ctx->stream));
     CK(cudaGetLastError());
     return GI_OK;
+}
+
+// ---- scene octree build on the device (gi_octree_build.cuh) ---------------------------------------------------------------------------------
+// grow a device buffer and keep its first `keep` bytes
+static cudaError_t grow_keep(gi_ctx* ctx, DevBuf& b, size_t bytes, size_t keep)
+{
+    if (bytes <= b.cap) return cudaSuccess;
+    void* np = nullptr;
+    const size_t want = bytes * 2 + 256;
+    cudaError_t e = cudaMalloc(&np, want);
+    if (e != cudaSuccess) return e;
+    if (keep && b.p) { e = cudaMemcpyAsync(np, b.p, keep, cudaMemcpyDeviceToDevice, ctx->stream); if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream); }
+    if (b.p) cudaFree(b.p);
+    b.p = np; b.cap = want;
+    return e;
+}
+extern "C" int gi_octree_build(gi_ctx* ctx, uint32_t n_prims, const uint8_t* prim_type, const double* prim_geom, const double* prim_bbox, const double* root_box6, uint32_t* n_nodes_out,
+                               uint32_t* n_refs_out, double* build_ms)
+{
+    if (!ctx || !root_box6 || (n_prims && (!prim_type || !prim_geom || !prim_bbox))) return GI_ERR_INVALID;
+    CK(cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    ctx->ob_valid = false;
+    CK(ctx->ob_type.reserve(std::max<size_t>(n_prims, 1))); CK(ctx->ob_geom.reserve(std::max<size_t>(n_prims, 1) * 72)); CK(ctx->ob_bbox.reserve(std::max<size_t>(n_prims, 1) * 48));
+    if (n_prims) {
+        CK(cudaMemcpyAsync(ctx->ob_type.p, prim_type, n_prims, cudaMemcpyHostToDevice, st));
+        CK(cudaMemcpyAsync(ctx->ob_geom.p, prim_geom, (size_t)n_prims * 72, cudaMemcpyHostToDevice, st));
+        CK(cudaMemcpyAsync(ctx->ob_bbox.p, prim_bbox, (size_t)n_prims * 48, cudaMemcpyHostToDevice, st));
+    }
+    cudaEvent_t e0 = get_event(ctx), e1 = get_event(ctx);
+    cudaEventRecord(e0, st);
+    // root (octree.cpp:25-38 grew its box; :106: it is split only when it holds more than 16 entities)
+    uint32_t n_nodes = 1, leaf_base = 0;
+    CK(grow_keep(ctx, ctx->ob_nodebox, 48, 0)); CK(grow_keep(ctx, ctx->ob_child, 4, 0)); CK(grow_keep(ctx, ctx->ob_mask, 1, 0)); CK(grow_keep(ctx, ctx->ob_poff, 4, 0)); CK(grow_keep(ctx, ctx->ob_pcnt, 4, 0));
+    CK(grow_keep(ctx, ctx->ob_leaf, std::max<size_t>(n_prims, 1) * 4, 0));
+    CK(cudaMemcpyAsync(ctx->ob_nodebox.p, root_box6, 48, cudaMemcpyHostToDevice, st));
+    CK(cudaMemsetAsync(ctx->ob_child.p, 0, 4, st)); CK(cudaMemsetAsync(ctx->ob_mask.p, 0, 1, st)); CK(cudaMemsetAsync(ctx->ob_poff.p, 0, 4, st));
+    CK(cudaMemcpyAsync(ctx->ob_pcnt.p, &n_prims, 4, cudaMemcpyHostToDevice, st));
+    if (n_prims) k_ob_iota<<<grid_for(n_prims, 256), 256, 0, st>>>(n_prims, ctx->ob_leaf.as<uint32_t>());   // a root that stays a leaf owns every entity in insertion order
+    uint32_t n_items = n_prims, n_active = n_prims > GI_OB_MAX_LEAF ? 1u : 0u;
+    int cur = 0;
+    if (n_active) {
+        CK(ctx->ob_list[0].reserve((size_t)n_items * 4));
+        k_ob_iota<<<grid_for(n_items, 256), 256, 0, st>>>(n_items, ctx->ob_list[0].as<uint32_t>());
+        CK(ctx->ob_abox[0].reserve(48)); CK(ctx->ob_anode[0].reserve(4)); CK(ctx->ob_astart[0].reserve(4)); CK(ctx->ob_acount[0].reserve(4));
+        const uint32_t zero = 0;
+        CK(cudaMemcpyAsync(ctx->ob_abox[0].p, root_box6, 48, cudaMemcpyHostToDevice, st));
+        CK(cudaMemcpyAsync(ctx->ob_anode[0].p, &zero, 4, cudaMemcpyHostToDevice, st)); CK(cudaMemcpyAsync(ctx->ob_astart[0].p, &zero, 4, cudaMemcpyHostToDevice, st));
+        CK(cudaMemcpyAsync(ctx->ob_acount[0].p, &n_items, 4, cudaMemcpyHostToDevice, st));
+        leaf_base = 0;
+    } else leaf_base = n_prims;
+    CK(ctx->ob_tot.reserve(16));
+    int level = 0;
+    while (n_active) {
+        if ((uint64_t)n_items * 8ull + 1ull > 0xFFFFFFF0ull) return fail(ctx, GI_ERR_INVALID, "octree level too large for 32-bit positions");
+        DOBLevel L{};
+        L.n_items = n_items; L.n_active = n_active;
+        L.list = ctx->ob_list[cur].as<uint32_t>(); L.owner = level ? ctx->ob_owner[cur].as<uint32_t>() : nullptr; L.slot_active = level ? ctx->ob_slotactive[cur].as<uint32_t>() : nullptr;
+        L.a_box = ctx->ob_abox[cur].as<double>(); L.a_node = ctx->ob_anode[cur].as<uint32_t>(); L.a_start = ctx->ob_astart[cur].as<uint32_t>(); L.a_count = ctx->ob_acount[cur].as<uint32_t>();
+        const size_t nflag = (size_t)n_items * 8 + 1;
+        CK(ctx->ob_flags.reserve(nflag * 4)); CK(ctx->ob_pos.reserve(nflag * 4));
+        k_ob_classify<<<grid_for(n_items, 128), 128, 0, st>>>(L, ctx->ob_type.as<uint8_t>(), ctx->ob_geom.as<double>(), ctx->ob_bbox.as<double>(), ctx->ob_flags.as<uint32_t>());
+        uint32_t* tot = ctx->ob_tot.as<uint32_t>();
+        int rc = scan_exclusive(ctx, ctx->ob_flags.as<uint32_t>(), 1, (uint32_t)nflag, ctx->ob_pos.as<uint32_t>(), tot);
+        if (rc != GI_OK) return rc;
+        const size_t nslot = (size_t)n_active * 8;
+        for (auto& b : ctx->ob_slot) CK(b.reserve(nslot * 4));
+        for (auto& b : ctx->ob_rank) CK(b.reserve(nslot * 4));
+        DOBSlots S{ ctx->ob_slot[0].as<uint32_t>(), ctx->ob_slot[1].as<uint32_t>(), ctx->ob_slot[2].as<uint32_t>(), ctx->ob_slot[3].as<uint32_t>(), ctx->ob_slot[4].as<uint32_t>() };
+        k_ob_slots<<<grid_for(n_active, 128), 128, 0, st>>>(L, ctx->ob_pos.as<uint32_t>(), S);
+        if ((rc = scan_exclusive(ctx, S.exists, 1, (uint32_t)nslot, ctx->ob_rank[0].as<uint32_t>(), tot + 1)) != GI_OK) return rc;
+        if ((rc = scan_exclusive(ctx, S.cont, 1, (uint32_t)nslot, ctx->ob_rank[1].as<uint32_t>(), tot + 2)) != GI_OK) return rc;
+        if ((rc = scan_exclusive(ctx, S.final_cnt, 1, (uint32_t)nslot, ctx->ob_rank[2].as<uint32_t>(), tot + 3)) != GI_OK) return rc;
+        uint32_t h[4];
+        CK(cudaMemcpyAsync(h, tot, 16, cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        const uint32_t next_items = h[0], new_nodes = h[1], next_active = h[2], final_refs = h[3];
+        if ((uint64_t)n_nodes + new_nodes > 0xFFFFFFF0ull || (uint64_t)leaf_base + final_refs > 0xFFFFFFF0ull) return fail(ctx, GI_ERR_INVALID, "octree too large");
+        const size_t nn = (size_t)n_nodes + new_nodes;
+        CK(grow_keep(ctx, ctx->ob_nodebox, nn * 48, (size_t)n_nodes * 48)); CK(grow_keep(ctx, ctx->ob_child, nn * 4, (size_t)n_nodes * 4)); CK(grow_keep(ctx, ctx->ob_mask, nn, n_nodes));
+        CK(grow_keep(ctx, ctx->ob_poff, nn * 4, (size_t)n_nodes * 4)); CK(grow_keep(ctx, ctx->ob_pcnt, nn * 4, (size_t)n_nodes * 4));
+        CK(grow_keep(ctx, ctx->ob_leaf, ((size_t)leaf_base + final_refs + 1) * 4, (size_t)leaf_base * 4));
+        const int nxt = cur ^ 1;
+        CK(ctx->ob_list[nxt].reserve(std::max<size_t>(next_items, 1) * 4)); CK(ctx->ob_owner[nxt].reserve(std::max<size_t>(next_items, 1) * 4));
+        CK(ctx->ob_abox[nxt].reserve(std::max<size_t>(next_active, 1) * 48)); CK(ctx->ob_anode[nxt].reserve(std::max<size_t>(next_active, 1) * 4));
+        CK(ctx->ob_astart[nxt].reserve(std::max<size_t>(next_active, 1) * 4)); CK(ctx->ob_acount[nxt].reserve(std::max<size_t>(next_active, 1) * 4));
+        CK(ctx->ob_slotactive[nxt].reserve(nslot * 4));
+        DOBOut O{ ctx->ob_nodebox.as<double>(), ctx->ob_child.as<uint32_t>(), ctx->ob_mask.as<uint8_t>(), ctx->ob_poff.as<uint32_t>(), ctx->ob_pcnt.as<uint32_t>(), ctx->ob_leaf.as<uint32_t>() };
+        DOBNext N{ ctx->ob_abox[nxt].as<double>(), ctx->ob_anode[nxt].as<uint32_t>(), ctx->ob_astart[nxt].as<uint32_t>(), ctx->ob_acount[nxt].as<uint32_t>(), ctx->ob_slotactive[nxt].as<uint32_t>() };
+        k_ob_emit<<<grid_for(nslot, 128), 128, 0, st>>>(L, S, ctx->ob_rank[0].as<uint32_t>(), ctx->ob_rank[1].as<uint32_t>(), ctx->ob_rank[2].as<uint32_t>(), n_nodes, leaf_base, O, N);
+        k_ob_scatter<<<grid_for(n_items, 128), 128, 0, st>>>(L, ctx->ob_flags.as<uint32_t>(), ctx->ob_pos.as<uint32_t>(), S, ctx->ob_rank[2].as<uint32_t>(), leaf_base, ctx->ob_list[nxt].as<uint32_t>(),
+                                                              ctx->ob_owner[nxt].as<uint32_t>(), ctx->ob_leaf.as<uint32_t>());
+        CK(cudaGetLastError());
+        n_nodes += new_nodes; leaf_base += final_refs; n_items = next_items; n_active = next_active; cur = nxt; level++;
+        if (level > 64) return fail(ctx, GI_ERR_INVALID, "octree deeper than 64 levels");
+    }
+    cudaEventRecord(e1, st);
+    CK(cudaStreamSynchronize(st));
+    float ms = 0; cudaEventElapsedTime(&ms, e0, e1);
+    ctx->event_pool.push_back(e0); ctx->event_pool.push_back(e1);
+    ctx->ob_n_nodes = n_nodes; ctx->ob_n_refs = leaf_base; ctx->ob_valid = true;
+    if (n_nodes_out) *n_nodes_out = n_nodes;
+    if (n_refs_out) *n_refs_out = leaf_base;
+    if (build_ms) *build_ms = ms;
+    return GI_OK;
+}
+extern "C" int gi_octree_download(gi_ctx* ctx, double* node_box, uint32_t* node_child, uint8_t* node_mask, uint32_t* node_prim_off, uint32_t* node_prim_cnt, uint32_t* leaf_prims)
+{
+    if (!ctx) return GI_ERR_INVALID;
+    if (!ctx->ob_valid) return fail(ctx, GI_ERR_INVALID, "gi_octree_download needs gi_octree_build");
+    CK(cudaSetDevice(ctx->device));
+    const size_t n = ctx->ob_n_nodes, r = ctx->ob_n_refs;
+    if (node_box) CK(cudaMemcpyAsync(node_box, ctx->ob_nodebox.p, n * 48, cudaMemcpyDeviceToHost, ctx->stream));
+    if (node_child) CK(cudaMemcpyAsync(node_child, ctx->ob_child.p, n * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    if (node_mask) CK(cudaMemcpyAsync(node_mask, ctx->ob_mask.p, n, cudaMemcpyDeviceToHost, ctx->stream));
+    if (node_prim_off) CK(cudaMemcpyAsync(node_prim_off, ctx->ob_poff.p, n * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    if (node_prim_cnt) CK(cudaMemcpyAsync(node_prim_cnt, ctx->ob_pcnt.p, n * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    if (leaf_prims && r) CK(cudaMemcpyAsync(leaf_prims, ctx->ob_leaf.p, r * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    return gi_synchronize(ctx);
 }
 
 // ---- photons ------------------------------------------------------------------------------------------------------------------------------

@@ -45,6 +45,25 @@ int gih_scene_load(const char* path, int quiet, gih_scene** out)
     return GI_OK;
 }
 
+// Entity::boundingBox() of every primitive, [n_prims][6] (the input gi_octree_build wants next to prim_type / prim_geom)
+void gih_scene_prim_bbox(const gih_scene* s, double* out6)
+{
+    std::vector<double> b;
+    s->octree->entity_boxes(b);
+    std::memcpy(out6, b.data(), b.size() * sizeof(double));
+}
+// rebuild the loaded scene's octree on the device and flatten again; returns a GI_* code, *build_ms = device time
+int gih_scene_rebuild_device(gih_scene* s, gi_ctx* ctx, double* build_ms)
+{
+    if (!s || !ctx) return GI_ERR_INVALID;
+    int rc = s->octree->rebuild(ctx);
+    if (rc != GI_OK) return rc;
+    if (build_ms) *build_ms = s->octree->last_build_ms;
+    s->octree->flatten(s->rt->_camera, s->rt->ambient, s->flat);
+    s->desc = s->flat.desc();
+    return GI_OK;
+}
+
 const gi_scene_desc* gih_scene_desc(const gih_scene* s) { return s ? &s->desc : nullptr; }
 
 // photons, photon_depth, min_samples, max_samples, noise_thresh

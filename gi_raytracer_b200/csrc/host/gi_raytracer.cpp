@@ -1,4 +1,5 @@
 // gi_raytracer.cpp — RayTracer::run and PhotonMap::rebuild: the host-side callers of the C ABI (raytracer.h:41-165).
+#include <cstdlib>
 #include <chrono>
 #include <cstdio>
 #include <iostream>
@@ -51,7 +52,11 @@ int RayTracer::run(int w, int h)
     if (!ctx) return GI_ERR_NO_DEVICE;
     if (!_scene) return GI_ERR_NO_SCENE;
     int rc;
-    if (!_scene->valid) { _scene->rebuild(); _uploaded = false; }             // raytracer.h:56-59
+    if (!_scene->valid) {                                                        // raytracer.h:56-59
+        // Node::partition runs on the device (identical tree, tested); GI_HOST_BUILD=1 keeps the host build
+        if (std::getenv("GI_HOST_BUILD") || (rc = _scene->rebuild(ctx)) != GI_OK) _scene->rebuild();
+        _uploaded = false;
+    }
     if (!_uploaded) {
         FlatScene flat;
         _scene->flatten(_camera, ambient, flat);

@@ -316,19 +316,19 @@ void Octree::push_back(Entity* object)  // octree.cpp:25-38
 
 void Octree::push_back(Light* light) { lights.push_back(light); }  // octree.cpp:41-46
 
-void Octree::rebuild()  // octree.cpp:53-119
+void Octree::light_cones(const std::vector<Entity*>& list)  // octree.cpp:60-102
 {
-    // caustic emission cone per light (octree.cpp:60-102), including the reference's habit of continuing to
-    // accumulate avgPos/count inside the per-light loop (it only affects lights after the first)
+    // caustic emission cone per light, including the reference's habit of continuing to accumulate avgPos/count inside
+    // the per-light loop (it only affects lights after the first)
     dvec3 avgPos(0, 0, 0);
     double count = 0;
-    for (Entity* e : _root._entities)
+    for (Entity* e : list)
         if (e->material.roughness < 0.1) { avgPos = avgPos + e->boundingBox().center(); count++; }
     if (count > 0) avgPos = avgPos / count;
     for (Light* l : lights) {
         double maxAngle = 0;
         l->dir = gi::normalize(avgPos - l->pos);
-        for (Entity* e : _root._entities)
+        for (Entity* e : list)
             if (e->material.roughness < 0.1) {
                 BoundingBox bb = e->boundingBox();
                 avgPos = avgPos + bb.center();
@@ -338,8 +338,55 @@ void Octree::rebuild()  // octree.cpp:53-119
             }
         l->angle = maxAngle;
     }
+}
+
+void Octree::rebuild()  // octree.cpp:53-119
+{
+    light_cones(_root._entities);
+    _device_built = false;
     if (_root._entities.size() > GI_MAX_ENTITIES_PER_LEAF) _root.partition();  // octree.cpp:106-112
     valid = true;
+}
+
+void Octree::entity_boxes(std::vector<double>& out6) const
+{
+    out6.resize(_all.size() * 6);
+    for (size_t i = 0; i < _all.size(); i++) {
+        BoundingBox b = _all[i]->boundingBox();
+        double* o = &out6[i * 6];
+        o[0] = b.min.x; o[1] = b.min.y; o[2] = b.min.z; o[3] = b.max.x; o[4] = b.max.y; o[5] = b.max.z;
+    }
+}
+
+int Octree::rebuild(gi_ctx* ctx)  // octree.cpp:53-119 with Node::partition on the device
+{
+    // Built from the insertion-order list of ALL entities.  (Deviation, documented: the reference's second rebuild after a
+    // partition sees only the entities pushed since — the root list was cleared, octree.cpp:370 — and leaves them unreachable
+    // in the root; here a rebuild always covers every entity.)
+    light_cones(_all);
+    const size_t n = _all.size();
+    std::vector<uint8_t> type(n);
+    std::vector<double> geom(n * 9, 0.0), boxes;
+    for (size_t i = 0; i < n; i++) {
+        const Entity* e = _all[i];
+        type[i] = (uint8_t)e->kind();
+        double* g = &geom[i * 9];
+        if (const triangle* t = dynamic_cast<const triangle*>(e)) { for (int k = 0; k < 3; k++) { g[3 * k] = t->vertices[k].pos.x; g[3 * k + 1] = t->vertices[k].pos.y; g[3 * k + 2] = t->vertices[k].pos.z; } }
+        else if (const sphere* s = dynamic_cast<const sphere*>(e)) { g[0] = s->pos.x; g[1] = s->pos.y; g[2] = s->pos.z; g[3] = s->rad; }
+        else if (const cone* c = dynamic_cast<const cone*>(e)) { g[0] = c->pos.x; g[1] = c->pos.y; g[2] = c->pos.z; g[3] = c->rad; g[4] = c->height; }
+    }
+    entity_boxes(boxes);
+    const double root[6] = { _root._bbox.min.x, _root._bbox.min.y, _root._bbox.min.z, _root._bbox.max.x, _root._bbox.max.y, _root._bbox.max.z };
+    uint32_t nn = 0, nr = 0;
+    valid = false;
+    int rc = gi_octree_build(ctx, (uint32_t)n, type.data(), geom.data(), boxes.data(), root, &nn, &nr, &last_build_ms);
+    if (rc != GI_OK) return rc;
+    _dev_box.resize((size_t)nn * 6); _dev_child.resize(nn); _dev_mask.resize(nn); _dev_off.resize(nn); _dev_cnt.resize(nn); _dev_leaf.resize(nr);
+    rc = gi_octree_download(ctx, _dev_box.data(), _dev_child.data(), _dev_mask.data(), _dev_off.data(), _dev_cnt.data(), _dev_leaf.data());
+    if (rc != GI_OK) return rc;
+    _device_built = true;
+    valid = true;
+    return GI_OK;
 }
 
 // One level of Octree::Node::partition (octree.cpp:316-365): make the eight child boxes, hand every entity to each
@@ -467,7 +514,10 @@ void Octree::flatten(const Camera& cam, const dvec3& amb, FlatScene& out) const
     std::unordered_map<const Entity*, uint32_t> eid;
     for (uint32_t i = 0; i < _all.size(); i++) eid[_all[i]] = i;
     // nodes, breadth-first; existing children contiguous in child order
-    std::vector<const Node*> order = { &_root };
+    std::vector<const Node*> order;
+    if (_device_built) {
+        out.node_box = _dev_box; out.node_child = _dev_child; out.node_mask = _dev_mask; out.node_prim_off = _dev_off; out.node_prim_cnt = _dev_cnt; out.leaf_prims = _dev_leaf;
+    } else order.push_back(&_root);
     for (size_t q = 0; q < order.size(); q++) {
         const Node* n = order[q];
         uint8_t mask = 0;

@@ -135,6 +135,7 @@ struct Material {  // material.h:84-100
 };
 
 class Octree;
+struct gi_ctx;
 
 struct Entity {  // entities.h:17-49
     Entity();
@@ -273,6 +274,11 @@ class Octree {  // octree.h:17-65
     void push_back(Entity* object);   // octree.cpp:25-38
     void push_back(Light* light);     // octree.cpp:41-46
     void rebuild();                   // octree.cpp:53-119
+    // New: the same rebuild with Node::partition run on the device (gi_octree_build); flatten() then hands out the device-built
+    // arrays.  Returns a GI_* code; on failure the tree is left invalid.
+    int rebuild(gi_ctx* ctx);
+    void entity_boxes(std::vector<double>& out6) const;   // Entity::boundingBox() of every entity, insertion order
+    double last_build_ms = 0;         // device time of the last rebuild(ctx)
     // New: SoA image of the rebuilt tree for gi_scene_upload.  Primitive id = insertion order of push_back(Entity*).
     void flatten(const Camera& cam, const gi::dvec3& ambient, FlatScene& out) const;
     const std::vector<Entity*>& entities() const { return _all; }
@@ -280,6 +286,9 @@ class Octree {  // octree.h:17-65
     Node _root;
     int nodes = 0, skipped_subdiv = 0;
   private:
+    void light_cones(const std::vector<Entity*>& list);   // octree.cpp:60-102
+    bool _device_built = false; // _dev_* hold the tree instead of _root's children
+    std::vector<double> _dev_box; std::vector<uint32_t> _dev_child, _dev_off, _dev_cnt, _dev_leaf; std::vector<uint8_t> _dev_mask;
     std::vector<Entity*> _all;  // insertion order (the root list itself is cleared by partition, octree.cpp:370-371)
 };
 

@@ -17,6 +17,23 @@ def _np(ptr, n, dtype):
     return np.frombuffer(buf, dtype=dt, count=n).copy()
 
 
+def prim_boxes(path, quiet=True):
+    """loadScene(path) -> Entity::boundingBox() of every primitive, [n][6] (input of gi_octree_build); host only."""
+    L = load_library()
+    h = C.c_void_p()
+    rc = L.gih_scene_load(str(path).encode(), 1 if quiet else 0, C.byref(h))
+    if rc != 0:
+        raise RuntimeError(f"gih_scene_load({path}) failed: {rc}")
+    try:
+        n = L.gih_scene_desc(h).contents.n_prims
+        out = np.empty((n, 6))
+        if n:
+            L.gih_scene_prim_bbox(h, out.ctypes.data)
+    finally:
+        L.gih_scene_free(h)
+    return out
+
+
 def load_scene(path, quiet=True) -> SceneArrays:
     """loadScene(path) + Octree::rebuild() + Octree::flatten() -> SceneArrays (a deep copy; the C++ objects are freed)."""
     L = load_library()

@@ -218,6 +218,17 @@ int gi_fog_density(gi_ctx* ctx, size_t n, const double* pos, double* dens, doubl
 int gi_raymarch(gi_ctx* ctx, size_t n, const double* org, const double* dir, const double* tmax, uint64_t seed, int march,
                 uint8_t* hit, double* t0, double* t1, double* pos, double* col);
 
+/* ---- scene octree build on the device: Octree::rebuild / Octree::Node::partition (octree.cpp:53-119,
+ *      316-384) with triBoxOverlap's float temporaries (util.cpp:257-330), level-synchronous.  Inputs (host pointers): the
+ *      primitives in insertion order (prim_type / prim_geom as in gi_scene_desc), prim_bbox [n][6] = Entity::boundingBox()
+ *      (entities.h:103-106, 260-299, 530-557) and the root box Octree::push_back accumulated (octree.cpp:25-38).  The
+ *      result stays on the device; gi_octree_download copies it out in gi_scene_desc's node layout (any pointer may be
+ *      NULL) — the same arrays the host build + flatten produce, bit for bit. ------------------------------------- */
+int gi_octree_build(gi_ctx* ctx, uint32_t n_prims, const uint8_t* prim_type, const double* prim_geom, const double* prim_bbox,
+                    const double* root_box6, uint32_t* n_nodes, uint32_t* n_refs, double* build_ms);
+int gi_octree_download(gi_ctx* ctx, double* node_box, uint32_t* node_child, uint8_t* node_mask, uint32_t* node_prim_off,
+                       uint32_t* node_prim_cnt, uint32_t* leaf_prims);
+
 /* ---- photons: RayTracer::tracePhotons (raytracer.h:582-715); photons are {origin, dir, col} = 9 fp64 (photon.h) */
 int gi_photon_trace(gi_ctx* ctx, int count, int max_depth, uint64_t seed, uint64_t* n_stored, gi_stats* stats);
 int gi_photon_upload(gi_ctx* ctx, size_t n, const double* photons9);
