@@ -7,6 +7,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <map>
+#include <chrono>
 #include <string>
 #include <vector>
 
@@ -657,6 +658,16 @@ extern "C" int gi_octree_build(gi_ctx* ctx, uint32_t n_prims, const uint8_t* pri
     uint32_t n_nodes = 1, leaf_base = 0;
     CK(grow_keep(ctx, ctx->ob_nodebox, 48, 0)); CK(grow_keep(ctx, ctx->ob_child, 4, 0)); CK(grow_keep(ctx, ctx->ob_mask, 1, 0)); CK(grow_keep(ctx, ctx->ob_poff, 4, 0)); CK(grow_keep(ctx, ctx->ob_pcnt, 4, 0));
     CK(grow_keep(ctx, ctx->ob_leaf, std::max<size_t>(n_prims, 1) * 4, 0));
+    if (n_prims > GI_OB_MAX_LEAF) {
+        // first guess at the final size (grown when a level needs more): ~4 nodes and ~16 leaf references per primitive
+        const size_t gn = (size_t)n_prims * 4, gr = (size_t)n_prims * 16;
+        CK(grow_keep(ctx, ctx->ob_nodebox, gn * 24, 0)); CK(grow_keep(ctx, ctx->ob_child, gn * 2, 0)); CK(grow_keep(ctx, ctx->ob_mask, gn / 2, 0)); CK(grow_keep(ctx, ctx->ob_poff, gn * 2, 0));
+        CK(grow_keep(ctx, ctx->ob_pcnt, gn * 2, 0)); CK(grow_keep(ctx, ctx->ob_leaf, gr * 2, 0));
+        for (int k = 0; k < 2; k++) { CK(ctx->ob_list[k].reserve(gr * 2)); CK(ctx->ob_owner[k].reserve(gr * 2)); }
+        CK(ctx->ob_flags.reserve(gr * 16)); CK(ctx->ob_pos.reserve(gr * 16));
+    }
+    static const bool trace_build = getenv("GI_TRACE_BUILD") != nullptr;
+    auto wall0 = std::chrono::steady_clock::now();
     CK(cudaMemcpyAsync(ctx->ob_nodebox.p, root_box6, 48, cudaMemcpyHostToDevice, st));
     CK(cudaMemsetAsync(ctx->ob_child.p, 0, 4, st)); CK(cudaMemsetAsync(ctx->ob_mask.p, 0, 1, st)); CK(cudaMemsetAsync(ctx->ob_poff.p, 0, 4, st));
     CK(cudaMemcpyAsync(ctx->ob_pcnt.p, &n_prims, 4, cudaMemcpyHostToDevice, st));
@@ -715,6 +726,13 @@ extern "C" int gi_octree_build(gi_ctx* ctx, uint32_t n_prims, const uint8_t* pri
         k_ob_scatter<<<grid_for(n_items, 128), 128, 0, st>>>(L, ctx->ob_flags.as<uint32_t>(), ctx->ob_pos.as<uint32_t>(), S, ctx->ob_rank[2].as<uint32_t>(), leaf_base, ctx->ob_list[nxt].as<uint32_t>(),
                                                               ctx->ob_owner[nxt].as<uint32_t>(), ctx->ob_leaf.as<uint32_t>());
         CK(cudaGetLastError());
+        if (trace_build) {
+            cudaStreamSynchronize(st);
+            auto w1 = std::chrono::steady_clock::now();
+            fprintf(stderr, "[gi] octree level %2d: %9u items %8u active -> %8u new nodes, %9u final refs, %9u items next | %.3f ms\n", level, n_items, n_active, new_nodes, final_refs, next_items,
+                    std::chrono::duration<double, std::milli>(w1 - wall0).count());
+            wall0 = w1;
+        }
         n_nodes += new_nodes; leaf_base += final_refs; n_items = next_items; n_active = next_active; cur = nxt; level++;
         if (level > 64) return fail(ctx, GI_ERR_INVALID, "octree deeper than 64 levels");
     }
