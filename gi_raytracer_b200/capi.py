@@ -22,7 +22,7 @@ API_SYMBOLS = [
     "gi_photon_map_build", "gi_photon_map_info", "gi_photon_map_download", "gi_photon_map_slab_size",
     "gi_photon_map_slab_ptr", "gi_photon_map_adopt_slab", "gi_photon_map_reserve_slab", "gi_photon_gather",
     "gi_photon_gather_dev", "gi_render_tile", "gi_render_tile_dev", "gi_resolve", "gi_resolve_dev", "gi_last_kernel_ms",
-    "gi_last_work", "gi_scene_info", "gi_render_adaptive", "gi_render_adaptive_dev", "gi_fog_density", "gi_raymarch", "gi_octree_build", "gi_octree_download",
+    "gi_last_work", "gi_scene_info", "gi_render_adaptive", "gi_render_adaptive_dev", "gi_fog_density", "gi_raymarch", "gi_octree_build", "gi_octree_download", "gi_cancel",
 ]
 
 _LIB = None
@@ -98,6 +98,8 @@ def load_library():
     L.gih_scene_free.restype = None
     L.gih_render_scene.argtypes = [C.c_char_p, i32, i32, i32, i32, i32, i32, u64, C.c_char_p, vp, C.POINTER(GiStats), C.POINTER(GiStats),
                                    C.POINTER(C.c_double), C.POINTER(C.c_double)]
+    L.gih_render_progressive.argtypes = [C.c_char_p, i32, i32, i32, i32, i32, i32, u64, i32, i32, vp, C.POINTER(i32), C.POINTER(C.c_double)]
+    L.gi_cancel.argtypes = [vp, i32]
     _LIB = L
     return L
 
@@ -219,6 +221,10 @@ class Context:
         pos, col = np.empty((n, 3)), np.empty((n, 3))
         self._ck(self.L.gi_raymarch(self.h, n, _p(org), _p(d), _p(tmax), seed, 1 if march else 0, _p(hit), _p(t0), _p(t1), _p(pos), _p(col)))
         return hit, t0, t1, pos, col
+
+    def cancel(self, raise_=True):
+        """gi_cancel: callable from any thread while another thread is inside a render / photon call on this context."""
+        self._ck(self.L.gi_cancel(self.h, 1 if raise_ else 0))
 
     def octree_build(self, prim_type, prim_geom, prim_bbox, root_box):
         """Octree::rebuild / Node::partition on the device -> (dict of gi_scene_desc node arrays, device ms)."""

@@ -7,6 +7,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <map>
+#include <atomic>
 #include <chrono>
 #include <string>
 #include <vector>
@@ -61,6 +62,7 @@ struct gi_ctx {
     DevBuf ob_type, ob_geom, ob_bbox, ob_nodebox, ob_child, ob_mask, ob_poff, ob_pcnt, ob_leaf, ob_list[2], ob_owner[2], ob_flags, ob_pos, ob_abox[2], ob_anode[2], ob_astart[2], ob_acount[2],
         ob_slotactive[2], ob_slot[5], ob_rank[3], ob_tot;
     uint32_t ob_n_nodes = 0, ob_n_refs = 0; bool ob_valid = false;
+    std::atomic<int> cancel{ 0 };  // gi_cancel: polled at launch boundaries
     bool no_implicit = false;      // GI_NO_IMPLICIT_BOXES at gi_create: always load child boxes (for A/B tests)
     int trace_mode = 0;            // 0: thread per ray, 1: warp per ray (API batch kernels; GI_TRACE_MODE)
     uint32_t tail_threshold = 32768; // queues smaller than this finish in the tail megakernel (GI_TAIL_THRESHOLD, 0 = off)
@@ -282,6 +284,18 @@ extern "C" void gi_destroy(gi_ctx* ctx)
     cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
+
+extern "C" int gi_cancel(gi_ctx* ctx, int raise)
+{
+    if (!ctx) return GI_ERR_INVALID;
+    ctx->cancel.store(raise ? 1 : 0, std::memory_order_release);
+    return GI_OK;
+}
+// at a launch boundary: drain the stream and give up when the flag is raised
+#define GI_POLL_CANCEL(what)                                                                                     \
+    do {                                                                                                         \
+        if (ctx->cancel.load(std::memory_order_acquire)) { cudaStreamSynchronize(ctx->stream); collect_timers(ctx); return fail(ctx, GI_ERR_CANCELLED, what " cancelled"); } \
+    } while (0)
 
 extern "C" const char* gi_last_error(const gi_ctx* ctx) { return ctx ? ctx->err.c_str() : "null context"; }
 extern "C" void* gi_stream(gi_ctx* ctx) { return ctx ? (void*)ctx->stream : nullptr; }
@@ -819,6 +833,7 @@ extern "C" int gi_photon_trace(gi_ctx* ctx, int count, int max_depth, uint64_t s
         uint32_t n_active = (uint32_t)slots;
         int base_try = 0;
         for (int round = 0; base_try < 500 && n_active > 0; round++) {
+            GI_POLL_CANCEL("photon trace");
             int width = 1;
             while (width < 32 && (uint64_t)n_active * (uint64_t)(2 * width) <= (1u << 19)) width *= 2;
             CK(cudaMemsetAsync(n_out, 0, 4, ctx->stream));
@@ -1174,6 +1189,7 @@ static int render_device(gi_ctx* ctx, const gi_render_params* P, int x0, int y0,
         uint32_t n_active = n;
         const uint32_t* perm = nullptr;
         for (int depth = 0; n_active > 0 && depth <= P->max_depth; depth++) {
+            GI_POLL_CANCEL("render");
             if (depth > 0 && n_active < ctx->tail_threshold) {
                 // few paths left: one warp per path runs them to the end inside one kernel; their gathers are queued and served
                 // by one gather pipeline run afterwards (GI_TAIL_MODE=1: gathers inline)
@@ -1267,6 +1283,7 @@ static int render_device(gi_ctx* ctx, const gi_render_params* P, int x0, int y0,
         if (npx > chunk_cap) return fail(ctx, GI_ERR_INVALID, "adaptive tiles are limited to 2^23 pixels");
         k_adapt_init<<<grid_for(npx, 256), 256, 0, ctx->stream>>>(npx, *adapt);
         for (int s = 0; s < adapt->max_samples; s++) {
+            GI_POLL_CANCEL("adaptive render");
             CK(cudaMemsetAsync(adapt->n_list, 0, 4, ctx->stream));
             k_adapt_select<<<grid_for(npx, 256), 256, 0, ctx->stream>>>((uint32_t)npx, s, *adapt);
             uint32_t n = 0;
@@ -1287,6 +1304,7 @@ static int render_device(gi_ctx* ctx, const gi_render_params* P, int x0, int y0,
     CK(cudaMemsetAsync(accum_dev, 0, npx * 24, ctx->stream));
     for (uint64_t c0 = 0; c0 < total_paths; c0 += chunk_cap) {
         uint32_t n = (uint32_t)std::min<uint64_t>(chunk_cap, total_paths - c0);
+        GI_POLL_CANCEL("render");
         k_generate<<<grid_for(n, 256), 256, 0, ctx->stream>>>(ctx->S, F, s0, c0, n, qa, PS);
         launches++;
         int rcd = run_depths(n);

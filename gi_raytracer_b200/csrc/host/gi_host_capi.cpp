@@ -1,5 +1,9 @@
 // gi_host_capi.cpp — a small C facade over the host scene classes for the Python harness (tests, bench.py):
 // load a .scn through loadScene, rebuild the octree, flatten, and expose the arrays.  No device work here.
+#include <algorithm>
+#include <atomic>
+#include <chrono>
+#include <thread>
 #include <cstring>
 #include <iostream>
 #include <sstream>
@@ -109,6 +113,41 @@ int gih_render_scene(const char* path, int w, int h, int device, int max_depth, 
     if (frame_ms) *frame_ms = rt.last_frame_ms;
     delete scene;
     return GI_OK;
+}
+
+// The viewer's use of the tracer (viewer.h:29-62): run() on a worker thread with progressive bands, stop() from the calling thread
+// once `stop_after_rows` rows have been published (< 0: never), join.  rgb_out = the image as the viewer would see it;
+// *rows_done = rows published; *stop_latency_ms = time from stop() to run() returning.  Returns run()'s code.
+int gih_render_progressive(const char* path, int w, int h, int device, int max_depth, int spp_override, int photons_override, uint64_t seed, int rows_per_band, int stop_after_rows,
+                           uint8_t* rgb_out, int* rows_done, double* stop_latency_ms)
+{
+    Camera camera(gi::dvec3(10, 5, 0), gi::dvec3(0, 0, 0));
+    RayTracer rt(camera);
+    Octree* scene = new Octree();
+    loadScene(scene, rt, path);
+    rt.setScene(scene);
+    rt.device = device;
+    rt.seed = seed;
+    rt.progressive_rows = rows_per_band;
+    if (max_depth >= 0) rt.max_depth = max_depth;
+    if (spp_override > 0) { rt.min_samples = rt.max_samples = spp_override; }
+    if (photons_override >= 0) rt.photons = photons_override;
+    rt.start();
+    int rc = GI_OK;
+    std::atomic<bool> done{ false };
+    std::thread worker([&]() { rc = rt.run(w, h); done = true; });
+    auto t_stop = std::chrono::steady_clock::now();
+    bool stopped = false;
+    while (!done) {
+        if (!stopped && stop_after_rows >= 0 && rt.rows_done() >= std::max(stop_after_rows, 1)) { rt.stop(); t_stop = std::chrono::steady_clock::now(); stopped = true; }
+        std::this_thread::sleep_for(std::chrono::microseconds(200));
+    }
+    worker.join();
+    if (stop_latency_ms) *stop_latency_ms = stopped ? std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_stop).count() : 0.0;
+    if (rows_done) *rows_done = rt.rows_done();
+    if (rgb_out && rt.getImage()->rgb.size() == (size_t)w * h * 3) std::memcpy(rgb_out, rt.getImage()->rgb.data(), rt.getImage()->rgb.size());
+    delete scene;
+    return rc;
 }
 
 }  // extern "C"

@@ -1,4 +1,7 @@
 // gi_raytracer.cpp — RayTracer::run and PhotonMap::rebuild: the host-side callers of the C ABI (raytracer.h:41-165).
+#include <algorithm>
+#include <cstddef>
+#include <cstring>
 #include <cstdlib>
 #include <chrono>
 #include <cstdio>
@@ -9,6 +12,24 @@
 RayTracer::~RayTracer()
 {
     if (_ctx) gi_destroy(_ctx);
+}
+
+RayTracer::RayTracer(const RayTracer& o)
+    : photons(o.photons), photon_depth(o.photon_depth), min_samples(o.min_samples), max_samples(o.max_samples), noise_thresh(o.noise_thresh), ambient(o.ambient), _camera(o._camera),
+      max_depth(o.max_depth), min_depth(o.min_depth), seed(o.seed), device(o.device), progressive_rows(o.progressive_rows), _running(o._running.load()), _rows_done(o._rows_done.load()),
+      _scene(o._scene), _photon_map(o._photon_map), _image(o._image)
+{
+}
+
+void RayTracer::stop()
+{
+    _running = false;
+    if (_ctx) gi_cancel(_ctx, 1);
+}
+void RayTracer::start()
+{
+    _running = true;
+    if (_ctx) gi_cancel(_ctx, 0);
 }
 
 gi_ctx* RayTracer::context()
@@ -81,14 +102,32 @@ int RayTracer::run(int w, int h)
     // variance-driven per-pixel loop (raytracer.h:100-148) -> gi_render_adaptive; the result is the running-mean colour.
     gi_render_params p;
     p.width = w; p.height = h; p.max_depth = max_depth; p.min_depth = min_depth; p.spp = max_samples; p.k_photons = 32; p.caustic_max_depth = 10; p._pad = 0; p.seed = seed;
-    std::vector<double> accum((size_t)w * h * 3);
     auto f0 = std::chrono::high_resolution_clock::now();
-    int resolve_spp = p.spp;
-    if (min_samples != max_samples) {
-        if ((rc = gi_render_adaptive(ctx, &p, min_samples, max_samples, noise_thresh, 0, 0, w, h, accum.data(), nullptr, &last_frame_stats)) != GI_OK) { std::cout << "gi_render_adaptive: " << gi_last_error(ctx) << "\n"; return rc; }
-        resolve_spp = 1;
-    } else if ((rc = gi_render_tile(ctx, &p, 0, 0, w, h, 0, p.spp, accum.data(), &last_frame_stats)) != GI_OK) { std::cout << "gi_render_tile: " << gi_last_error(ctx) << "\n"; return rc; }
-    if ((rc = gi_resolve(ctx, (size_t)w * h, accum.data(), resolve_spp, _image->rgb.data())) != GI_OK) { std::cout << "gi_resolve: " << gi_last_error(ctx) << "\n"; return rc; }
+    const bool adaptive = min_samples != max_samples;
+    const int resolve_spp = adaptive ? 1 : p.spp;
+    // bands of rows, top to bottom (one band = the whole frame unless progressive_rows is set); a band that has not started
+    // when stop() arrives is skipped, like the rows of the reference's loop (raytracer.h:93-98)
+    const int band = progressive_rows > 0 ? progressive_rows : h;
+    std::vector<double> accum((size_t)w * std::min(band, h) * 3);
+    _rows_done = 0;
+    std::memset(&last_frame_stats, 0, sizeof(last_frame_stats));
+    for (int y0 = 0; y0 < h; y0 += band) {
+        if (!_running) break;
+        const int y1 = std::min(h, y0 + band);
+        gi_stats bs;
+        if (adaptive) rc = gi_render_adaptive(ctx, &p, min_samples, max_samples, noise_thresh, 0, y0, w, y1, accum.data(), nullptr, &bs);
+        else rc = gi_render_tile(ctx, &p, 0, y0, w, y1, 0, p.spp, accum.data(), &bs);
+        if (rc == GI_ERR_CANCELLED) break;   // stop() while the band was on the device: its pixels are not published
+        if (rc != GI_OK) { std::cout << "gi_render: " << gi_last_error(ctx) << "\n"; return rc; }
+        if ((rc = gi_resolve(ctx, (size_t)w * (y1 - y0), accum.data(), resolve_spp, _image->rgb.data() + (size_t)y0 * w * 3)) != GI_OK) { std::cout << "gi_resolve: " << gi_last_error(ctx) << "\n"; return rc; }
+        _rows_done = y1;
+        // totals over the bands
+        uint64_t* dst = reinterpret_cast<uint64_t*>(&last_frame_stats); const uint64_t* src = reinterpret_cast<const uint64_t*>(&bs);
+        for (size_t k = 0; k < offsetof(gi_stats, trace_ms) / 8; k++) dst[k] += src[k];
+        last_frame_stats.trace_ms += bs.trace_ms; last_frame_stats.shadow_ms += bs.shadow_ms; last_frame_stats.gather_ms += bs.gather_ms; last_frame_stats.shade_ms += bs.shade_ms;
+        last_frame_stats.total_ms += bs.total_ms; last_frame_stats.bin_ms += bs.bin_ms;
+        for (uint64_t *d2 = &last_frame_stats.tail_closest_rays, *e2 = &last_frame_stats.tail_gather_selected + 1, *s2 = &bs.tail_closest_rays; d2 != e2; ++d2, ++s2) *d2 += *s2;
+    }
     auto f1 = std::chrono::high_resolution_clock::now();
     last_frame_ms = std::chrono::duration<double, std::milli>(f1 - f0).count();
     return GI_OK;

@@ -14,6 +14,7 @@
 // with it every hit id, is identical; Octree::flatten() emits the SoA arrays of gi_scene_desc.
 #pragma once
 #include <array>
+#include <atomic>
 #include <cmath>
 #include <cstdint>
 #include <memory>
@@ -318,15 +319,26 @@ class RayTracer {  // raytracer.h:23-735
   public:
     RayTracer() = delete;
     RayTracer(const Camera& camera) : _camera(camera), _image(std::make_shared<Image>(0, 0)) {}
+    // The reference copies the tracer by value into Gui / Viewer (gui.h:19, viewer.h:16); copies share the scene, the photon
+    // map and the image.  A copy gets its own (lazily created) device context.
+    RayTracer(const RayTracer& o);
+    RayTracer& operator=(const RayTracer&) = delete;
     ~RayTracer();
     void setScene(Octree* scene);       // raytracer.h:35-39
     // raytracer.h:41-165: octree rebuild if needed, photon phase once, then the frame — all device work through gi_*.
     // Returns 0 or a GI_ERR_* code (the reference returns void and prints).
     int run(int w, int h);
     bool running() const { return _running; }
-    void stop() { _running = false; }
-    void start() { _running = true; }
+    // raytracer.h:723-725.  stop() may be called from another thread while run() is in flight (viewer.h:29-34): bands that
+    // have not started are skipped like the reference's rows, and the device call in flight is cancelled (gi_cancel).
+    void stop();
+    void start();
     std::shared_ptr<Image> getImage() const { return _image; }
+    // Progressive display: > 0 renders the frame in bands of this many rows, top to bottom, and publishes each band's pixels
+    // to the Image as soon as it is done (the reference writes pixels row by row while a 32 ms timer repaints, viewer.h:17-21).
+    // 0 (default, headless) = the whole frame in one device call.  Bands are tiles: pixels are identical either way.
+    int progressive_rows = 0;
+    int rows_done() const { return _rows_done.load(); }   // rows published so far by the run() in flight / last run()
 
     int photons = GI_PHOTONS;
     int photon_depth = GI_PHOTON_DEPTH;
@@ -345,7 +357,8 @@ class RayTracer {  // raytracer.h:23-735
     gi_ctx* context();                  // lazily created gi_ctx on `device`
 
   private:
-    bool _running = false;
+    std::atomic<bool> _running{ false };
+    std::atomic<int> _rows_done{ 0 };
     Octree* _scene = nullptr;
     PhotonMap* _photon_map = nullptr;
     std::shared_ptr<Image> _image;

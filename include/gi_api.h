@@ -35,6 +35,7 @@ extern "C" {
 #define GI_ERR_NO_SCENE (-4)    /* call needs gi_scene_upload first                */
 #define GI_ERR_NO_PHOTONS (-5)  /* call needs a built photon map                   */
 #define GI_ERR_OOM (-6)
+#define GI_ERR_CANCELLED (-7)   /* gi_cancel(ctx, 1) was raised: the call stopped at the next launch boundary */
 
 #define GI_NO_HIT 0xFFFFFFFFu
 
@@ -204,6 +205,13 @@ int gi_trace_any(gi_ctx* ctx, size_t n, const double* org, const double* dir, co
                  uint8_t* vis);
 int gi_trace_any_dev(gi_ctx* ctx, size_t n, const double* org, const double* dir, const double* maxt2, uint64_t alpha_seed,
                      uint8_t* vis);
+
+/* ---- cancellation: RayTracer::stop / start and the `_running` poll of the row loop (raytracer.h:98, 723-725; viewer.h:29-34).
+ *      gi_cancel(ctx, 1) may be called from ANY thread while another thread is inside gi_render_* / gi_photon_trace on the
+ *      same context; the call in flight returns GI_ERR_CANCELLED at its next launch boundary (between bounce depths, path
+ *      chunks, adaptive passes, photon rounds), its outputs are then incomplete.  The flag stays raised — every later
+ *      render / photon call returns GI_ERR_CANCELLED at once — until gi_cancel(ctx, 0). ------------------------------ */
+int gi_cancel(gi_ctx* ctx, int raise);
 
 /* ---- atmosphere.  The fog itself acts inside gi_render_* / gi_photon_trace (RayTracer::radiance
  *      raytracer.h:209-228, ::visible :308-316, ::tracePhotons :658-675) whenever the uploaded scene has n_fog > 0; the
