@@ -11,7 +11,7 @@ CLI = os.path.join(HERE, "global-illu")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 
 CU = [os.path.join(CSRC, "gi_api.cu")]
-CPP = [os.path.join(CSRC, "host", f) for f in ("gi_scene.cpp", "gi_loader.cpp", "gi_raytracer.cpp", "gi_host_capi.cpp")]
+CPP = [os.path.join(CSRC, "host", f) for f in ("gi_scene.cpp", "gi_loader.cpp", "gi_raytracer.cpp", "gi_host_capi.cpp", "gi_png.cpp")]
 HDR = [os.path.join(CSRC, f) for f in ("gi_device.cuh", "gi_kernels.cuh", os.path.join("host", "api_scene.inc"))] + [os.path.join(CSRC, "host", "gi_scene.hpp"),
                                                                               os.path.join(HERE, "..", "include", "gi_api.h")]
 EXTRA = os.environ.get("GI_NVCC_EXTRA", "").split()
@@ -28,7 +28,7 @@ def _stale(target, deps):
 
 def build(force=False, verbose=False):
     if force or _stale(LIB, CU + CPP + HDR):
-        cmd = [NVCC] + FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-shared", "-o", LIB] + CU + CPP
+        cmd = [NVCC] + FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-shared", "-o", LIB] + CU + CPP + ["-lz"]
         subprocess.check_call(cmd)
     if force or _stale(CLI, [LIB, os.path.join(CSRC, "cli", "global_illu.cpp")]):
         cmd = ["/usr/bin/g++", "-O2", "-std=c++17", os.path.join(CSRC, "cli", "global_illu.cpp"), "-o", CLI, "-L" + HERE, "-lgi_b200",

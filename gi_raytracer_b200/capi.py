@@ -100,6 +100,8 @@ def load_library():
                                    C.POINTER(C.c_double), C.POINTER(C.c_double)]
     L.gih_render_progressive.argtypes = [C.c_char_p, i32, i32, i32, i32, i32, i32, u64, i32, i32, vp, C.POINTER(i32), C.POINTER(C.c_double)]
     L.gi_cancel.argtypes = [vp, i32]
+    L.gih_png_decode.argtypes = [C.c_char_p, C.POINTER(i32), C.POINTER(i32), C.POINTER(i32), vp, sz]
+    L.gih_png_encode.argtypes = [C.c_char_p, i32, i32, vp]
     _LIB = L
     return L
 

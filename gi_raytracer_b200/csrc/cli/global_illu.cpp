@@ -1,5 +1,5 @@
-// global-illu — the reference's executable (main.cpp:19-46) run headless: no Qt window, the frame is written as PPM.
-// usage: global-illu [scene.scn] [width height] [out.ppm] [--device N] [--max-depth D] [--spp N] [--photons P] [--seed S]
+// global-illu — the reference's executable (main.cpp:19-46) run headless: no Qt window, the frame is written as PNG or PPM (by extension).
+// usage: global-illu [scene.scn] [width height] [out.png|out.ppm] [--device N] [--max-depth D] [--spp N] [--photons P] [--seed S]
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>

@@ -105,7 +105,11 @@ int gih_render_scene(const char* path, int w, int h, int device, int max_depth, 
     rt.start();
     int rc = rt.run(w, h);
     if (rc != GI_OK) { delete scene; return rc; }
-    if (out_ppm && *out_ppm) rt.getImage()->writePPM(out_ppm);
+    if (out_ppm && *out_ppm) {   // by extension: .png -> PNG, anything else -> binary PPM
+        const std::string o = out_ppm;
+        const bool png = o.size() > 4 && (o.compare(o.size() - 4, 4, ".png") == 0 || o.compare(o.size() - 4, 4, ".PNG") == 0);
+        if (png) rt.getImage()->writePNG(out_ppm); else rt.getImage()->writePPM(out_ppm);
+    }
     if (rgb_out) std::memcpy(rgb_out, rt.getImage()->rgb.data(), rt.getImage()->rgb.size());
     if (frame_stats) *frame_stats = rt.last_frame_stats;
     if (photon_stats) *photon_stats = rt.last_photon_stats;

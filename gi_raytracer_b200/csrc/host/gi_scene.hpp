@@ -311,6 +311,7 @@ struct Image {  // image.h:7-29 without Qt: RGB888 rows, top row first
     gi::dvec3 getPixel(int x, int y) const { const uint8_t* p = &rgb[((size_t)y * _w + x) * 3]; return { p[0] / 255., p[1] / 255., p[2] / 255. }; }
     void clear() { std::fill(rgb.begin(), rgb.end(), 0); }
     bool writePPM(const char* path) const;
+    bool writePNG(const char* path) const;   // gi_png.cpp (the reference saves through QImage::save, gui.h:39-45)
     int _w, _h;
     std::vector<uint8_t> rgb;
 };
@@ -365,6 +366,10 @@ class RayTracer {  // raytracer.h:23-735
     gi_ctx* _ctx = nullptr;
     bool _uploaded = false;
 };
+
+// PNG without Qt (gi_png.cpp): 8-bit RGBA rows top first, has_alpha as QImage::hasAlphaChannel reports it
+bool gi_png_decode(const char* path, int& width, int& height, bool& has_alpha, std::vector<uint8_t>& rgba);
+bool gi_png_encode(const char* path, int width, int height, const uint8_t* rgb);
 
 void loadScene(Octree* o, RayTracer& r, const char* fname);                                              // sceneLoader.h:5
 void loadOBJ(Octree* o, const char* fname, gi::dvec3 pos, gi::dvec3 rot, const Material& material);     // meshLoader.h:4

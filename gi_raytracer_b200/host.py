@@ -62,3 +62,22 @@ def load_scene(path, quiet=True) -> SceneArrays:
     finally:
         L.gih_scene_free(h)
     return sc
+
+
+def png_decode(path):
+    """csrc/host/gi_png.cpp: (rgba uint8 [h][w][4], has_alpha) — what QImage gave the reference's imageTexture."""
+    L = load_library()
+    w, h, a = C.c_int(), C.c_int(), C.c_int()
+    if L.gih_png_decode(str(path).encode(), C.byref(w), C.byref(h), C.byref(a), None, 0) != 0:
+        raise ValueError(f"not a decodable PNG: {path}")
+    out = np.empty((h.value, w.value, 4), dtype=np.uint8)
+    if L.gih_png_decode(str(path).encode(), C.byref(w), C.byref(h), C.byref(a), out.ctypes.data, out.size) != 0:
+        raise ValueError(f"not a decodable PNG: {path}")
+    return out, bool(a.value)
+
+
+def png_encode(path, rgb):
+    """8-bit RGB [h][w][3] -> PNG file."""
+    rgb = np.ascontiguousarray(rgb, dtype=np.uint8)
+    if load_library().gih_png_encode(str(path).encode(), rgb.shape[1], rgb.shape[0], rgb.ctypes.data) != 0:
+        raise ValueError(f"cannot write {path}")

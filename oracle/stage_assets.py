@@ -39,6 +39,8 @@ def main(src_root, out_root):
                 shutil.copyfile(src, os.path.join(odir, fn)); n += 1
             elif low.endswith((".png", ".jpg", ".jpeg")) and not low.startswith("render"):
                 decode(src, os.path.join(odir, fn + ".rgba")); n += 1
+                if low.endswith(".png"):   # the product's own loader decodes PNG itself (csrc/host/gi_png.cpp); the sidecar stays for the QImage shim and as the PIL cross-check
+                    shutil.copyfile(src, os.path.join(odir, fn)); n += 1
     print(f"staged {n} asset files into {out_root}")
 
 
