@@ -12,7 +12,7 @@ NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 
 CU = [os.path.join(CSRC, "gi_api.cu")]
 CPP = [os.path.join(CSRC, "host", f) for f in ("gi_scene.cpp", "gi_loader.cpp", "gi_raytracer.cpp", "gi_host_capi.cpp", "gi_png.cpp")]
-HDR = [os.path.join(CSRC, f) for f in ("gi_device.cuh", "gi_kernels.cuh", os.path.join("host", "api_scene.inc"))] + [os.path.join(CSRC, "host", "gi_scene.hpp"),
+HDR = [os.path.join(CSRC, f) for f in ("gi_device.cuh", "gi_kernels.cuh", "gi_octree_build.cuh", os.path.join("host", "api_scene.inc"))] + [os.path.join(CSRC, "host", "gi_scene.hpp"),
                                                                               os.path.join(HERE, "..", "include", "gi_api.h")]
 EXTRA = os.environ.get("GI_NVCC_EXTRA", "").split()
 FLAGS = EXTRA + ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-fmad=false",
@@ -24,6 +24,12 @@ def _stale(target, deps):
         return True
     t = os.path.getmtime(target)
     return any(os.path.getmtime(d) > t for d in deps)
+
+
+def build_variant(out, extra):
+    """An A/B variant of the library with extra nvcc flags (e.g. ['-DGI_REGTOP=0']), written to `out`."""
+    subprocess.check_call([NVCC] + list(extra) + FLAGS + ["-shared", "-o", out] + CU + CPP + ["-lz"])
+    return out
 
 
 def build(force=False, verbose=False):

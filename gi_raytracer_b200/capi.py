@@ -39,9 +39,10 @@ def load_library():
     global _LIB
     if _LIB is not None:
         return _LIB
-    if not os.path.exists(LIB_PATH):
-        raise FileNotFoundError(f"{LIB_PATH} is missing: run `python -m gi_raytracer_b200.build` (there is no CPU fallback)")
-    L = C.CDLL(LIB_PATH)
+    lib_path = os.environ.get("GI_LIB", LIB_PATH)   # A/B runs of kernel variants (profiles/frame_ab.py); default: the in-tree build
+    if not os.path.exists(lib_path):
+        raise FileNotFoundError(f"{lib_path} is missing: run `python -m gi_raytracer_b200.build` (there is no CPU fallback)")
+    L = C.CDLL(lib_path)
     vp, u64, sz, u32, i32 = C.c_void_p, C.c_uint64, C.c_size_t, C.c_uint32, C.c_int
     L.gi_create.argtypes = [i32, C.POINTER(vp)]
     L.gi_destroy.argtypes = [vp]

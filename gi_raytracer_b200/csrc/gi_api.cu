@@ -1309,7 +1309,7 @@ static int render_device(gi_ctx* ctx, const gi_render_params* P, int x0, int y0,
         launches++;
         int rcd = run_depths(n);
         if (rcd != GI_OK) return rcd;
-        k_accumulate<<<grid_for(npx, 256), 256, 0, ctx->stream>>>(c0, n, npx, PS.L, PS.Lc, accum_dev);
+        k_accumulate<<<grid_for(npx, 256), 256, 0, ctx->stream>>>(c0, n, npx, F.tw, F.th, PS.L, PS.Lc, accum_dev);
         launches++;
         CK(cudaGetLastError());
     }

@@ -874,9 +874,20 @@ __global__ void __launch_bounds__(WARPS * 32) k_pm_cands(const DNode* __restrict
 // Order inside a bin is arbitrary (atomics); no result depends on queue order: every path owns its accumulator and its
 // PRNG key.
 #ifndef GI_BIN_AXIS_BITS
-#define GI_BIN_AXIS_BITS 6   // cells per axis = 2^bits (C2 frame: 4 bits 30.8 ms, 5 29.8, 6 29.5, 7 29.9)
+#define GI_BIN_AXIS_BITS 5   // cells per axis = 2^bits (C2 frame with octant-only keys: 4 bits 30.8 ms, 5 29.8, 6 29.5, 7 29.9)
 #endif
-#define GI_SORT_BITS (3 * GI_BIN_AXIS_BITS + 3)
+// GI_BIN_DIR: 0 = direction octant in the LOW key bits (cell-major order: a warp holds one or two cells with all their
+// octants), 1 = octant in the HIGH bits (direction-major: a warp holds one octant over a run of adjacent Morton cells),
+// 2 = octant + dominant axis (24 direction classes, 5 bits) in the high bits
+// Measured (frame ms, caustics 1024^2 x 8 / glass 1024^2 x 4; bits per axis in brackets): 0[6] 29.75 / 62.66, 1[6] 30.24 / 60.76,
+// 2[5] 29.70 / 59.47, 2[6] 29.27 / 59.91, 3[5] 29.54 / 58.61, 3[6] 29.26 / 60.03, 4[6] 28.88 / 62.41, 2[7] 31.22 (8 M bins: the
+// histogram scan costs 2.7 ms).  Finer direction classes pay more than finer cells; 3[5] keeps the 2 M-bin histogram.
+#ifndef GI_BIN_DIR
+#define GI_BIN_DIR 3
+#endif
+// 3 = octant + the full ordering of |dx|,|dy|,|dz| (48 classes, 6 bits) in the high bits, 4 = like 2 but in the LOW bits
+#define GI_BIN_DIR_BITS (GI_BIN_DIR == 3 ? 6 : ((GI_BIN_DIR == 2 || GI_BIN_DIR == 4) ? 5 : 3))
+#define GI_SORT_BITS (3 * GI_BIN_AXIS_BITS + GI_BIN_DIR_BITS)
 #define GI_SORT_BINS (1u << GI_SORT_BITS)
 __device__ __forceinline__ uint32_t spread3(uint32_t v)   // ...cba -> ..c00b00a (Morton interleave of up to 10 bits)
 {
@@ -895,7 +906,19 @@ __global__ void k_bin_keys(uint32_t n, const double* __restrict__ org, const dou
     d3 o = ld3(org + 3 * (size_t)i), d = ld3(dir + 3 * (size_t)i);
     int cx = (int)((o.x - bmin.x) * inv_ext.x), cy = (int)((o.y - bmin.y) * inv_ext.y), cz = (int)((o.z - bmin.z) * inv_ext.z);
     cx = cx < 0 ? 0 : (cx > C ? C : cx); cy = cy < 0 ? 0 : (cy > C ? C : cy); cz = cz < 0 ? 0 : (cz > C ? C : cz);
-    uint32_t k = ((spread3((uint32_t)cx) | (spread3((uint32_t)cy) << 1) | (spread3((uint32_t)cz) << 2)) << 3) | (d.x < 0 ? 1u : 0u) | (d.y < 0 ? 2u : 0u) | (d.z < 0 ? 4u : 0u);
+    const uint32_t cell = spread3((uint32_t)cx) | (spread3((uint32_t)cy) << 1) | (spread3((uint32_t)cz) << 2);
+    uint32_t dc = (d.x < 0 ? 1u : 0u) | (d.y < 0 ? 2u : 0u) | (d.z < 0 ? 4u : 0u);
+#if GI_BIN_DIR == 2 || GI_BIN_DIR == 4
+    { const double ax = fabs(d.x), ay = fabs(d.y), az = fabs(d.z); dc |= (ax >= ay && ax >= az ? 0u : (ay >= az ? 1u : 2u)) << 3; }
+#endif
+#if GI_BIN_DIR == 3
+    { const double ax = fabs(d.x), ay = fabs(d.y), az = fabs(d.z); dc |= ((ax >= ay ? 1u : 0u) | (ay >= az ? 2u : 0u) | (ax >= az ? 4u : 0u)) << 3; }
+#endif
+#if GI_BIN_DIR == 0 || GI_BIN_DIR == 4
+    uint32_t k = (cell << GI_BIN_DIR_BITS) | dc;
+#else
+    uint32_t k = (dc << (3 * GI_BIN_AXIS_BITS)) | cell;
+#endif
     key[i] = k;
     atomicAdd(hist + k, 1u);
 }
@@ -1289,6 +1312,30 @@ __global__ void k_tail_caustic(uint32_t n, DQueue in, DPathState PS, DTailQ Q)
     st3(PS.Lc + 3 * (size_t)path, Lc);
 }
 
+// Order of the camera paths of a tile: pixel <-> slot.  Row-major order puts 32 pixels of ONE row into a warp; here the tile is
+// cut into strips of GI_TILE_ROWS rows walked column by column, so a warp covers an (32 / GI_TILE_ROWS) x GI_TILE_ROWS block of
+// pixels: closer rays, closer hit points, closer shadow rays.  Only the order in which paths sit in the queues changes — every
+// path owns its state, frames are bit-identical (tested: tiles / chunks compose).  The last strip may be shorter.
+// Measured (frame ms, caustics / glass as above, with GI_BIN_DIR 3[5]): rows 1: 29.51 / 58.67, 2: 29.08, 4: 30.91 (the bounce-form
+// autotune flipped) / 57.54, 8: 29.12 / 57.85.
+#ifndef GI_TILE_ROWS
+#define GI_TILE_ROWS 8
+#endif
+__device__ __forceinline__ void slot_to_pixel(size_t slot, int tw, int th, int& lx, int& ly)
+{
+    const size_t per = (size_t)GI_TILE_ROWS * tw;
+    const int strip = (int)(slot / per);
+    const size_t j = slot - (size_t)strip * per;
+    const int hh = min(GI_TILE_ROWS, th - strip * GI_TILE_ROWS);
+    lx = (int)(j / hh); ly = strip * GI_TILE_ROWS + (int)(j % hh);
+}
+__device__ __forceinline__ size_t pixel_to_slot(int lx, int ly, int tw, int th)
+{
+    const int strip = ly / GI_TILE_ROWS;
+    const int hh = min(GI_TILE_ROWS, th - strip * GI_TILE_ROWS);
+    return (size_t)strip * GI_TILE_ROWS * tw + (size_t)lx * hh + (size_t)(ly - strip * GI_TILE_ROWS);
+}
+
 // generate the camera paths of one chunk (path-linear range [c0, c0+n) of the tile's sample-major path space)
 __global__ void k_generate(DScene S, DFrame F, int s0, uint64_t c0, uint32_t n, DQueue q, DPathState PS)
 {
@@ -1297,8 +1344,10 @@ __global__ void k_generate(DScene S, DFrame F, int s0, uint64_t c0, uint32_t n, 
     uint64_t lin = c0 + i;
     size_t npx = (size_t)F.tw * F.th;
     int s = s0 + (int)(lin / npx);
-    size_t pix = lin % npx;
-    int y = F.y0 + (int)(pix / F.tw), x = F.x0 + (int)(pix % F.tw);
+    size_t slot = lin % npx;
+    int lx, ly;
+    slot_to_pixel(slot, F.tw, F.th, lx, ly);
+    int y = F.y0 + ly, x = F.x0 + lx;
     uint32_t idx;
     DRay r = camera_ray(S, F, x, y, s, idx);
     st3(q.o + 3 * (size_t)i, r.o); st3(q.d + 3 * (size_t)i, r.d);
@@ -1372,16 +1421,17 @@ __global__ void k_adapt_update(uint32_t n, int s, const uint32_t* __restrict__ l
 }
 
 // add the chunk's per-path radiance into the tile accumulator, samples in ascending order per pixel
-__global__ void k_accumulate(uint64_t c0, uint32_t n, size_t npx, const double* L, const double* Lc, double* accum)
+__global__ void k_accumulate(uint64_t c0, uint32_t n, size_t npx, int tw, int th, const double* L, const double* Lc, double* accum)
 {
     size_t pix = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
     if (pix >= npx) return;
     uint64_t c1 = c0 + n;
-    // paths of this pixel inside the chunk: lin = k*npx + pix
-    uint64_t k0 = c0 > pix ? (c0 - pix + npx - 1) / npx : 0;
+    // paths of this pixel inside the chunk: lin = k*npx + slot(pixel)
+    const size_t slot = pixel_to_slot((int)(pix % tw), (int)(pix / tw), tw, th);
+    uint64_t k0 = c0 > slot ? (c0 - slot + npx - 1) / npx : 0;
     double a0 = accum[3 * pix], a1 = accum[3 * pix + 1], a2 = accum[3 * pix + 2];
     for (uint64_t k = k0;; k++) {
-        uint64_t lin = k * npx + pix;
+        uint64_t lin = k * npx + slot;
         if (lin >= c1) break;
         size_t i = (size_t)(lin - c0);
         a0 += L[3 * i] + Lc[3 * i]; a1 += L[3 * i + 1] + Lc[3 * i + 1]; a2 += L[3 * i + 2] + Lc[3 * i + 2];
