@@ -382,6 +382,7 @@ def main():
             "config": {"workload": "C2 scenes/caustics 1024x1024, 8 spp per GPU (sample-index split), MAX_DEPTH 64, 1M caustic photons, k=32 gather",
                        "scene": "scenes/caustics/caustics.scn (reference assets, dragon.obj not mounted)", "width": W, "height": H, "spp_per_gpu": SPP,
                        "photons_stored": pm_info["n_kept"], "photon_map_nodes": pm_info["n_nodes"], "l2": "working set per step (path state ~2.9 GB) exceeds the 126 MB L2",
+                       "streams": "k_direct and the gather pipeline of a bounce depth with < 2^20 hits run on side streams behind the next depth's bounce kernel: per-family ms overlap and do not add up to the frame",
                        "parallelism": f"sample-split x{world}", "photon_phase_s": photon_wall, "photon_slab_bytes": slab_bytes,
                        "rays_per_step": rays_all / K, "closest_rays_per_step": int(last.closest_rays), "shadow_rays_per_step": int(last.shadow_rays), "gathers_per_step": int(last.gathers)},
             "gather": {"metric": "photon-gather Mqueries/s", "value": nq_all / (gather_ms * 1e-3) / 1e6, "unit": "Mqueries/s", "queries": nq_all,

@@ -57,12 +57,18 @@ struct gi_ctx {
     DGatherMap G{};
     // workspaces
     DevBuf w0, w1, w2, w3, w4, w5, w6, w7, w8, w9;           // API staging
-    DevBuf q_a[5], q_b[5], hl[7], ps[4], tq[5], ad[6], b_cnt, b_accum, b_scan0, b_scan1, b_misc, b_work, b_tail, b_binkey, b_binperm, b_binhist, b_bincur, b_gnode, b_gperm, b_ghist, b_gcur, b_gheavy;
+    DevBuf q_a[5], q_b[5], hl[7], ps[5], tq[5], ad[6], b_cnt, b_accum, b_scan0, b_scan1, b_misc, b_work, b_tail, b_binkey, b_binperm, b_binhist, b_bincur, b_gnode, b_gperm, b_ghist, b_gcur, b_gheavy;
     // device octree build (gi_octree_build): inputs, outputs (gi_scene_desc layout), per-level work buffers
     DevBuf ob_type, ob_geom, ob_bbox, ob_nodebox, ob_child, ob_mask, ob_poff, ob_pcnt, ob_leaf, ob_list[2], ob_owner[2], ob_flags, ob_pos, ob_abox[2], ob_anode[2], ob_astart[2], ob_acount[2],
         ob_slotactive[2], ob_slot[5], ob_rank[3], ob_tot;
     uint32_t ob_n_nodes = 0, ob_n_refs = 0; bool ob_valid = false;
     std::atomic<int> cancel{ 0 };  // gi_cancel: polled at launch boundaries
+    // side streams: k_direct (side[0]) and the gather pipeline (side[1]) of a bounce depth run behind the next depth's bounce
+    // kernel once the hit list is short (< overlap_threshold): those launches no longer fill the machine
+    cudaStream_t main_stream = nullptr, side[2] = { nullptr, nullptr };
+    cudaEvent_t side_done[2][2] = { { nullptr, nullptr }, { nullptr, nullptr } };   // [hit-list parity][side stream]
+    uint32_t overlap_threshold = 1u << 20;   // GI_OVERLAP_THRESHOLD, 0 = off
+    DevBuf hl2[7], b_scan1s;                 // second hit list (depth parity), scan scratch of the gather side stream
     bool no_implicit = false;      // GI_NO_IMPLICIT_BOXES at gi_create: always load child boxes (for A/B tests)
     int trace_mode = 0;            // 0: thread per ray, 1: warp per ray (API batch kernels; GI_TRACE_MODE)
     uint32_t tail_threshold = 32768; // queues smaller than this finish in the tail megakernel (GI_TAIL_THRESHOLD, 0 = off)
@@ -71,7 +77,7 @@ struct gi_ctx {
     double nodes_per_ray = 0;        // node tests per closest-hit ray of the last frame rendered with the current scene
     // per-scene choice between the two bounce kernels: the first full-size frame runs the form guessed from the tree, the
     // second the other one, later frames the faster of the two (bounce + direct ms per closest-hit ray)
-    uint64_t tune_sig = 0; int tune_frames = 0; double tune_cost[2] = { 0, 0 };
+    uint64_t tune_sig = 0;           // signature of the scene the statistic above belongs to
     uint32_t bin_threshold = 65536;  // queues at least this long are binned by origin cell / direction octant before the next bounce (GI_BIN_THRESHOLD, 0 = off)
     unsigned long long work_host[16] = { 0 };   // [0,1] closest nodes/prims, [2,3] any-hit, [4..6] gather depth/cand/sel, [8] rays, [9] shadow rays, [10] queries
     // timing
@@ -236,6 +242,12 @@ extern "C" int gi_create(int device, gi_ctx** out)
     gi_ctx* ctx = new gi_ctx();
     ctx->device = device;
     if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return GI_ERR_CUDA; }
+    ctx->main_stream = ctx->stream;
+    for (int k = 0; k < 2; k++) {
+        if (cudaStreamCreateWithFlags(&ctx->side[k], cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return GI_ERR_CUDA; }
+        for (int q = 0; q < 2; q++) if (cudaEventCreateWithFlags(&ctx->side_done[q][k], cudaEventDisableTiming) != cudaSuccess) { delete ctx; return GI_ERR_CUDA; }
+    }
+    if (const char* e = getenv("GI_OVERLAP_THRESHOLD")) ctx->overlap_threshold = (uint32_t)strtoul(e, nullptr, 10);
     // Halton tables are scene independent
     std::vector<uint16_t> tab; std::vector<DHaltonDim> dims;
     build_halton(tab, dims);
@@ -281,7 +293,13 @@ extern "C" void gi_destroy(gi_ctx* ctx)
     for (auto& b : ctx->ad) b.release();
     for (auto& t : ctx->pending) { cudaEventDestroy(t.a); cudaEventDestroy(t.b); }
     for (auto& e : ctx->event_pool) cudaEventDestroy(e);
-    cudaStreamDestroy(ctx->stream);
+    for (int k = 0; k < 2; k++) {
+        if (ctx->side[k]) { cudaStreamSynchronize(ctx->side[k]); cudaStreamDestroy(ctx->side[k]); }
+        for (int q = 0; q < 2; q++) if (ctx->side_done[q][k]) cudaEventDestroy(ctx->side_done[q][k]);
+    }
+    for (auto& b : ctx->hl2) b.release();
+    ctx->b_scan1s.release();
+    cudaStreamDestroy(ctx->main_stream);
     delete ctx;
 }
 
@@ -294,7 +312,12 @@ extern "C" int gi_cancel(gi_ctx* ctx, int raise)
 // at a launch boundary: drain the stream and give up when the flag is raised
 #define GI_POLL_CANCEL(what)                                                                                     \
     do {                                                                                                         \
-        if (ctx->cancel.load(std::memory_order_acquire)) { cudaStreamSynchronize(ctx->stream); collect_timers(ctx); return fail(ctx, GI_ERR_CANCELLED, what " cancelled"); } \
+        if (ctx->cancel.load(std::memory_order_acquire)) {                                                       \
+            ctx->stream = ctx->main_stream;                                                                      \
+            cudaStreamSynchronize(ctx->side[0]); cudaStreamSynchronize(ctx->side[1]); cudaStreamSynchronize(ctx->stream);                                       \
+            collect_timers(ctx);                                                                                 \
+            return fail(ctx, GI_ERR_CANCELLED, what " cancelled");                                               \
+        }                                                                                                        \
     } while (0)
 
 extern "C" const char* gi_last_error(const gi_ctx* ctx) { return ctx ? ctx->err.c_str() : "null context"; }
@@ -448,11 +471,10 @@ extern "C" int gi_scene_upload(gi_ctx* ctx, const gi_scene_desc* sc)
     S.full = full ? 1u : 0u;
     S.implicit_boxes = implicit ? 1u : 0u;
     for (int k = 0; k < 6; k++) ctx->root_box[k] = sc->node_box[k];
-    ctx->nodes_per_ray = 0;
     {
         uint64_t sig = gi_mix64(((uint64_t)sc->n_nodes << 32) ^ sc->n_refs) ^ gi_mix64(((uint64_t)sc->n_prims << 20) ^ sc->n_lights);
         for (int k = 0; k < 6; k++) { uint64_t b; std::memcpy(&b, &sc->node_box[k], 8); sig = gi_mix64(sig ^ b); }
-        if (sig != ctx->tune_sig) { ctx->tune_sig = sig; ctx->tune_frames = 0; ctx->tune_cost[0] = ctx->tune_cost[1] = 0; }
+        if (sig != ctx->tune_sig) { ctx->tune_sig = sig; ctx->nodes_per_ray = 0; }   // a new scene: forget the previous one's traversal statistics
     }
     ctx->has_scene = true;   // photons / photon map are independent state and survive a re-upload (the reference keeps its
     return GI_OK;            // map across run() calls, raytracer.h:61); rebuild it explicitly when the geometry changed
@@ -629,11 +651,12 @@ extern "C" int gi_trace_any(gi_ctx* ctx, size_t n, const double* org, const doub
 static int scan_exclusive(gi_ctx* ctx, const uint32_t* in, int stride_words, uint32_t n, uint32_t* out, uint32_t* total_dev)
 {
     uint32_t nb = (n + GI_SCAN_BLOCK - 1) / GI_SCAN_BLOCK;
-    CK(ctx->b_scan1.reserve((size_t)std::max<uint32_t>(nb, 1) * 4));
+    DevBuf& scratch = ctx->stream == ctx->main_stream ? ctx->b_scan1 : ctx->b_scan1s;   // a scan on a side stream may run beside one on the main stream
+    CK(scratch.reserve((size_t)std::max<uint32_t>(nb, 1) * 4));
     if (n) {
-        k_scan_block<<<nb, GI_SCAN_BLOCK, 0, ctx->stream>>>(in, n, out, ctx->b_scan1.as<uint32_t>(), stride_words);
-        k_scan_sums<<<1, GI_SCAN_BLOCK, 0, ctx->stream>>>(ctx->b_scan1.as<uint32_t>(), nb, total_dev);
-        k_scan_apply<<<nb, GI_SCAN_BLOCK, 0, ctx->stream>>>(out, n, ctx->b_scan1.as<uint32_t>());
+        k_scan_block<<<nb, GI_SCAN_BLOCK, 0, ctx->stream>>>(in, n, out, scratch.as<uint32_t>(), stride_words);
+        k_scan_sums<<<1, GI_SCAN_BLOCK, 0, ctx->stream>>>(scratch.as<uint32_t>(), nb, total_dev);
+        k_scan_apply<<<nb, GI_SCAN_BLOCK, 0, ctx->stream>>>(out, n, scratch.as<uint32_t>());
     } else if (total_dev) CK(cudaMemsetAsync(total_dev, 0, 4, ctx->stream));
     CK(cudaGetLastError());
     return GI_OK;
@@ -1146,6 +1169,7 @@ extern "C" int gi_photon_gather(gi_ctx* ctx, size_t n, const double* pos, const 
 static int render_device(gi_ctx* ctx, const gi_render_params* P, int x0, int y0, int x1, int y1, int s0, int s1, double* accum_dev, gi_stats* stats, DAdapt* adapt = nullptr)
 {
     const size_t npx = (size_t)(x1 - x0) * (y1 - y0);
+    ctx->stream = ctx->main_stream;
     const uint64_t total_paths = adapt ? (uint64_t)npx : (uint64_t)npx * (uint64_t)(s1 - s0);
     const uint32_t chunk_cap = (uint32_t)std::min<uint64_t>(total_paths, GI_MAX_PATHS);
     // queues (double buffered), hit list, per-path state
@@ -1153,7 +1177,13 @@ static int render_device(gi_ctx* ctx, const gi_render_params* P, int x0, int y0,
     CK(ctx->q_a[4].reserve((size_t)chunk_cap * 4)); CK(ctx->q_b[4].reserve((size_t)chunk_cap * 4));
     for (int b = 0; b < 5; b++) CK(ctx->hl[b].reserve((size_t)chunk_cap * 24));
     CK(ctx->hl[5].reserve((size_t)chunk_cap * 8)); CK(ctx->hl[6].reserve((size_t)chunk_cap * 4));
-    CK(ctx->ps[0].reserve((size_t)chunk_cap * 4)); CK(ctx->ps[1].reserve((size_t)chunk_cap * 8)); CK(ctx->ps[2].reserve((size_t)chunk_cap * 24)); CK(ctx->ps[3].reserve((size_t)chunk_cap * 24));
+    const bool overlap = ctx->overlap_threshold > 0;
+    if (overlap) {   // hit lists alternate by depth parity
+        const size_t cap2 = chunk_cap;
+        for (int b = 0; b < 5; b++) CK(ctx->hl2[b].reserve(cap2 * 24));
+        CK(ctx->hl2[5].reserve(cap2 * 8)); CK(ctx->hl2[6].reserve(cap2 * 4));
+    }
+    CK(ctx->ps[0].reserve((size_t)chunk_cap * 4)); CK(ctx->ps[1].reserve((size_t)chunk_cap * 8)); CK(ctx->ps[2].reserve((size_t)chunk_cap * 24)); CK(ctx->ps[3].reserve((size_t)chunk_cap * 24)); CK(ctx->ps[4].reserve((size_t)chunk_cap * 24));
     CK(ctx->b_cnt.reserve(sizeof(DCounters))); CK(ctx->b_misc.reserve(64));
     CK(ctx->b_tail.reserve(sizeof(DTailCounters)));
     CK(cudaMemsetAsync(ctx->b_tail.p, 0, sizeof(DTailCounters), ctx->stream));
@@ -1164,20 +1194,20 @@ static int render_device(gi_ctx* ctx, const gi_render_params* P, int x0, int y0,
     bin_inv.x = (double)(1 << GI_BIN_AXIS_BITS) / std::max(ctx->root_box[3] - ctx->root_box[0], 1e-300); bin_inv.y = (double)(1 << GI_BIN_AXIS_BITS) / std::max(ctx->root_box[4] - ctx->root_box[1], 1e-300); bin_inv.z = (double)(1 << GI_BIN_AXIS_BITS) / std::max(ctx->root_box[5] - ctx->root_box[2], 1e-300);
     DQueue qa{ ctx->q_a[0].as<double>(), ctx->q_a[1].as<double>(), ctx->q_a[2].as<double>(), ctx->q_a[3].as<double>(), ctx->q_a[4].as<uint32_t>() };
     DQueue qb{ ctx->q_b[0].as<double>(), ctx->q_b[1].as<double>(), ctx->q_b[2].as<double>(), ctx->q_b[3].as<double>(), ctx->q_b[4].as<uint32_t>() };
-    DHitList H{ ctx->hl[0].as<double>(), ctx->hl[1].as<double>(), ctx->hl[2].as<double>(), ctx->hl[3].as<double>(), ctx->hl[4].as<double>(), ctx->hl[5].as<double>(), ctx->hl[6].as<uint32_t>() };
-    DPathState PS{ ctx->ps[0].as<uint32_t>(), ctx->ps[1].as<uint64_t>(), ctx->ps[2].as<double>(), ctx->ps[3].as<double>() };
+    const DHitList H0{ ctx->hl[0].as<double>(), ctx->hl[1].as<double>(), ctx->hl[2].as<double>(), ctx->hl[3].as<double>(), ctx->hl[4].as<double>(), ctx->hl[5].as<double>(), ctx->hl[6].as<uint32_t>() };
+    const DHitList H1{ ctx->hl2[0].as<double>(), ctx->hl2[1].as<double>(), ctx->hl2[2].as<double>(), ctx->hl2[3].as<double>(), ctx->hl2[4].as<double>(), ctx->hl2[5].as<double>(), ctx->hl2[6].as<uint32_t>() };
+    DPathState PS{ ctx->ps[0].as<uint32_t>(), ctx->ps[1].as<uint64_t>(), ctx->ps[2].as<double>(), ctx->ps[3].as<double>(), ctx->ps[4].as<double>() };
     DCounters* C = ctx->b_cnt.as<DCounters>();
     DFrame F = make_frame(ctx, P->width, P->height, x0, y0, x1, y1);
     const bool have_map = ctx->has_map && ctx->pm_kept > 0;
     // long, uneven walks (deep trees): persistent warps with ray refetch; short ones: one ray per thread, launch per queue.
-    // Decided from the node tests per closest-hit ray of the previous frame of this scene (first frame: from the tree size).
-    const bool guess = ctx->S.n_nodes > 200000u;
-    const bool tunable = ctx->bounce_mode == 0 && total_paths >= (1u << 20);   // small calls neither explore nor count
-    bool persistent = ctx->bounce_mode == 2 || (ctx->bounce_mode == 0 && guess);
-    if (tunable) {
-        if (ctx->tune_frames == 1) persistent = !guess;
-        else if (ctx->tune_frames >= 2) persistent = ctx->tune_cost[1] < 0.97 * ctx->tune_cost[0];   // refetch also scrambles the hit list: it has to win clearly
-    }
+    // Decided — deterministically — from the node tests per closest-hit ray that the previous large frame of this scene tallied
+    // (first frame: from the tree size).  Measured: refetch wins at 139 (sponza stand-in, 4483 -> 3092 ms) and loses ~8 % at 28
+    // (caustics) and 60 (glass).  (A timing-based choice between the two forms flipped from run to run on scenes where they
+    // are within a few per cent of each other, which made frame times bimodal.)
+    const bool tunable = total_paths >= (1u << 20);   // small calls do not update the statistic
+    const bool long_walks = ctx->nodes_per_ray > 0 ? ctx->nodes_per_ray > 100.0 : ctx->S.n_nodes > 200000u;
+    const bool persistent = ctx->bounce_mode == 2 || (ctx->bounce_mode == 0 && long_walks);
     uint64_t n_closest = 0, n_shadow = 0, n_gather = 0, launches = 0;
     for (const char* f : { "bounce", "direct", "gather", "tail", "bin" }) fam_reset(ctx, f);
     CK(cudaMemsetAsync(work_ptr(ctx, 0), 0, 8 * sizeof(unsigned long long), ctx->stream));
@@ -1188,11 +1218,24 @@ static int render_device(gi_ctx* ctx, const gi_render_params* P, int x0, int y0,
         DQueue in = qa, out = qb;
         uint32_t n_active = n;
         const uint32_t* perm = nullptr;
+        bool pending[2] = { false, false };   // side-stream work still reading hit list 0 / 1
+        auto wait_side = [&](int par) {       // the main stream waits for the side-stream work that reads hit list `par`
+            if (!pending[par]) return;
+            cudaStreamWaitEvent(ctx->main_stream, ctx->side_done[par][0], 0); cudaStreamWaitEvent(ctx->main_stream, ctx->side_done[par][1], 0);
+            pending[par] = false;
+        };
+        int hpar = 0;                         // hit list the next bounce writes
         for (int depth = 0; n_active > 0 && depth <= P->max_depth; depth++) {
             GI_POLL_CANCEL("render");
+            // depths alternate between the two hit lists, so that a depth's shadow rays and gathers can run behind the next
+            // depth's bounce kernel when they are few (decided below, once the hit count is known)
+            hpar = overlap ? (hpar ^ 1) : 0;
+            const DHitList& H = hpar ? H1 : H0;
+            wait_side(hpar);
             if (depth > 0 && n_active < ctx->tail_threshold) {
                 // few paths left: one warp per path runs them to the end inside one kernel; their gathers are queued and served
                 // by one gather pipeline run afterwards (GI_TAIL_MODE=1: gathers inline)
+                wait_side(0); wait_side(1);   // the tail continues the paths' L / Ld / Lc sums: every earlier term must be in
                 DTailQ Q{};
                 const int last_gather_depth = std::min(P->max_depth, P->caustic_max_depth);
                 Q.qmax = ctx->tail_mode == 0 && have_map && last_gather_depth >= depth ? (uint32_t)(last_gather_depth - depth + 1) : 0u;
@@ -1239,20 +1282,32 @@ static int render_device(gi_ctx* ctx, const gi_render_params* P, int x0, int y0,
             launches++;
             n_closest += n_active;
             if (hc.n_hits) {
+                // the host has just synchronised the main stream (counters), so the side streams need no event to start
+                const bool side = overlap && hc.n_hits < ctx->overlap_threshold;
                 if (ctx->S.n_lights) {
-                    ScopedTimer t(ctx, "direct");
-                    GI_LAUNCH_M(k_direct, grid_for(hc.n_hits, GI_BLOCK), GI_BLOCK, ctx->S, *P, depth, hc.n_hits, H, PS, work_ptr(ctx, 2));
+                    if (side) ctx->stream = ctx->side[0];
+                    {
+                        ScopedTimer t(ctx, "direct");
+                        GI_LAUNCH_M(k_direct, grid_for(hc.n_hits, GI_BLOCK), GI_BLOCK, ctx->S, *P, depth, hc.n_hits, H, PS, work_ptr(ctx, 2));
+                    }
+                    ctx->stream = ctx->main_stream;
                     launches++;
                     n_shadow += (uint64_t)hc.n_hits * ctx->S.n_lights;
                 }
                 if (depth <= P->caustic_max_depth) {
                     n_gather += hc.n_hits;   // samplePhotons is called whether or not photons exist (raytracer.h:258)
                     if (have_map) {
-                        ScopedTimer t(ctx, "gather");
-                        int rcg = run_gather(ctx, hc.n_hits, H.p, H.refdir, P->k_photons, nullptr, nullptr, nullptr, H.wcaustic, PS.Lc, H.path, &launches);
+                        if (side) ctx->stream = ctx->side[1];
+                        int rcg;
+                        {
+                            ScopedTimer t(ctx, "gather");
+                            rcg = run_gather(ctx, hc.n_hits, H.p, H.refdir, P->k_photons, nullptr, nullptr, nullptr, H.wcaustic, PS.Lc, H.path, &launches);
+                        }
+                        ctx->stream = ctx->main_stream;
                         if (rcg != GI_OK) return rcg;
                     }
                 }
+                if (side) { cudaEventRecord(ctx->side_done[hpar][0], ctx->side[0]); cudaEventRecord(ctx->side_done[hpar][1], ctx->side[1]); pending[hpar] = true; }
                 CK(cudaGetLastError());
             }
             if (getenv("GI_TRACE_LAUNCHES")) {
@@ -1276,6 +1331,7 @@ static int render_device(gi_ctx* ctx, const gi_render_params* P, int x0, int y0,
                 perm = ctx->b_binperm.as<uint32_t>();
             }
         }
+        wait_side(0); wait_side(1);   // whatever follows on the main stream (accumulate, the next chunk) sees complete sums
         return GI_OK;
     };
     if (adapt) {
@@ -1295,7 +1351,7 @@ static int render_device(gi_ctx* ctx, const gi_render_params* P, int x0, int y0,
             launches++;
             int rcd = run_depths(n);
             if (rcd != GI_OK) return rcd;
-            k_adapt_update<<<grid_for(n, 256), 256, 0, ctx->stream>>>(n, s, adapt->list, PS.L, PS.Lc, *adapt);
+            k_adapt_update<<<grid_for(n, 256), 256, 0, ctx->stream>>>(n, s, adapt->list, PS.L, PS.Ld, PS.Lc, *adapt);
             launches++;
             CK(cudaGetLastError());
         }
@@ -1309,7 +1365,7 @@ static int render_device(gi_ctx* ctx, const gi_render_params* P, int x0, int y0,
         launches++;
         int rcd = run_depths(n);
         if (rcd != GI_OK) return rcd;
-        k_accumulate<<<grid_for(npx, 256), 256, 0, ctx->stream>>>(c0, n, npx, F.tw, F.th, PS.L, PS.Lc, accum_dev);
+        k_accumulate<<<grid_for(npx, 256), 256, 0, ctx->stream>>>(c0, n, npx, F.tw, F.th, PS.L, PS.Ld, PS.Lc, accum_dev);
         launches++;
         CK(cudaGetLastError());
     }
@@ -1322,11 +1378,7 @@ static int render_device(gi_ctx* ctx, const gi_render_params* P, int x0, int y0,
     float ms = 0; cudaEventElapsedTime(&ms, e0, e1);
     ctx->event_pool.push_back(e0); ctx->event_pool.push_back(e1);
     n_closest += tc.closest; n_shadow += tc.shadow; n_gather += tc.gathers;
-    if (n_closest) ctx->nodes_per_ray = (double)(ctx->work_host[0] + tc.nodes_c) / (double)n_closest;
-    if (tunable && ctx->tune_frames < 2 && n_closest > tc.closest) {
-        ctx->tune_cost[persistent ? 1 : 0] = (ctx->fam["bounce"].ms + ctx->fam["direct"].ms) / (double)(n_closest - tc.closest);   // the hit-list order the form leaves behind counts too
-        ctx->tune_frames++;
-    }
+    if (n_closest && tunable) ctx->nodes_per_ray = (double)(ctx->work_host[0] + tc.nodes_c) / (double)n_closest;
     ctx->work_host[0] += tc.nodes_c; ctx->work_host[1] += tc.prims_c; ctx->work_host[2] += tc.nodes_s; ctx->work_host[3] += tc.prims_s;
     ctx->work_host[4] += tc.g_depth; ctx->work_host[5] += tc.g_cand; ctx->work_host[6] += tc.g_sel;
     if (stats) {

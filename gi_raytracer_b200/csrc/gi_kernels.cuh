@@ -945,7 +945,9 @@ struct DHitList {
 // per path: Halton index, PRNG key, and the radiance sum in two parts — L takes the ambient / emissive / direct terms in bounce
 // order, Lc the caustic terms in bounce order; the path's radiance is L + Lc.  (Keeping the caustic terms apart lets the tail
 // hand its gathers to one batched gather run without changing the order of any sum.)
-struct DPathState { uint32_t* sample; uint64_t* key; double* L; double* Lc; };
+// Ld takes the direct-light terms in bounce order on their own: k_direct (and the gather pipeline) of depth d then touch
+// nothing the bounce kernel of depth d+1 touches, so the host may run them on side streams behind it; radiance = (L + Ld) + Lc.
+struct DPathState { uint32_t* sample; uint64_t* key; double* L; double* Lc; double* Ld; };
 struct DCounters { uint32_t n_next, n_hits; unsigned long long closest, shadow, gathers; };
 
 template <int MODE, bool IMPL>
@@ -1175,7 +1177,7 @@ __global__ void __launch_bounds__(GI_BLOCK, GI_MINB) k_direct(DScene S, gi_rende
         }
     }
     d3 w = ld3(H.wdirect + 3 * (size_t)i) * li;
-    double* L = PS.L + 3 * (size_t)path;
+    double* L = PS.Ld + 3 * (size_t)path;
     L[0] += w.x; L[1] += w.y; L[2] += w.z;
     tally2(work, wn, wp);
 }
@@ -1213,7 +1215,7 @@ __global__ void __launch_bounds__(GI_WPB * 32) k_tail(DScene S, DGatherMap G, in
     DRay r = ray_as_stored(ld3(in.o + 3 * (size_t)i), ld3(in.d + 3 * (size_t)i));
     d3 T = ld3(in.T + 3 * (size_t)i), contrib = ld3(in.contrib + 3 * (size_t)i);
     const uint64_t key = PS.key[path]; const uint32_t sample = PS.sample[path];
-    d3 L = ld3(PS.L + 3 * (size_t)path), Lc = ld3(PS.Lc + 3 * (size_t)path);
+    d3 L = ld3(PS.L + 3 * (size_t)path), Lc = ld3(PS.Lc + 3 * (size_t)path), Ld = ld3(PS.Ld + 3 * (size_t)path);
     uint32_t nq = 0;   // gather queries queued by this path
     unsigned long long c_closest = 0, c_shadow = 0, c_gather = 0, g_depth = 0, g_cand = 0, g_sel = 0;
     uint32_t nc = 0, pc = 0, ns = 0, ps = 0;
@@ -1263,7 +1265,7 @@ __global__ void __launch_bounds__(GI_WPB * 32) k_tail(DScene S, DGatherMap G, in
                     li = (ld3(light.col) * pow_like_libm(d, (1.0 / rough))) * hfrac;
                 }
             }
-            L = L + wdir * li;
+            Ld = Ld + wdir * li;
         }
         // caustic estimate (k_gather)
         if (depth <= P.caustic_max_depth) {
@@ -1286,7 +1288,7 @@ __global__ void __launch_bounds__(GI_WPB * 32) k_tail(DScene S, DGatherMap G, in
         r = make_ray(hp + hn * offset, refDir);
     }
     if (lane == 0) {
-        st3(PS.L + 3 * (size_t)path, L); st3(PS.Lc + 3 * (size_t)path, Lc);
+        st3(PS.L + 3 * (size_t)path, L); st3(PS.Lc + 3 * (size_t)path, Lc); st3(PS.Ld + 3 * (size_t)path, Ld);
         if (have_map && Q.qmax) {
             Q.count[i] = nq < Q.qmax ? nq : Q.qmax;
             for (uint32_t k = nq; k < Q.qmax; k++) st3(Q.pos + 3 * ((size_t)i * Q.qmax + k), mk3(CUDART_INF, CUDART_INF, CUDART_INF));   // unused slots: in no leaf
@@ -1357,6 +1359,7 @@ __global__ void k_generate(DScene S, DFrame F, int s0, uint64_t c0, uint32_t n, 
     PS.key[i] = ((uint64_t)((uint64_t)y * (uint64_t)F.w + (uint64_t)x) << 24) | (uint64_t)s;
     PS.L[3 * (size_t)i] = 0; PS.L[3 * (size_t)i + 1] = 0; PS.L[3 * (size_t)i + 2] = 0;
     PS.Lc[3 * (size_t)i] = 0; PS.Lc[3 * (size_t)i + 1] = 0; PS.Lc[3 * (size_t)i + 2] = 0;
+    PS.Ld[3 * (size_t)i] = 0; PS.Ld[3 * (size_t)i + 1] = 0; PS.Ld[3 * (size_t)i + 2] = 0;
 }
 
 // ---- adaptive sampling: the per-pixel loop of RayTracer::run (raytracer.h:100-148) as passes over the sample index --------------------
@@ -1400,13 +1403,14 @@ __global__ void k_generate_list(DScene S, DFrame F, int s, uint32_t n, const uin
     PS.key[i] = ((uint64_t)((uint64_t)y * (uint64_t)F.w + (uint64_t)x) << 24) | (uint64_t)s;
     PS.L[3 * (size_t)i] = 0; PS.L[3 * (size_t)i + 1] = 0; PS.L[3 * (size_t)i + 2] = 0;
     PS.Lc[3 * (size_t)i] = 0; PS.Lc[3 * (size_t)i + 1] = 0; PS.Lc[3 * (size_t)i + 2] = 0;
+    PS.Ld[3 * (size_t)i] = 0; PS.Ld[3 * (size_t)i + 1] = 0; PS.Ld[3 * (size_t)i + 2] = 0;
 }
-__global__ void k_adapt_update(uint32_t n, int s, const uint32_t* __restrict__ list, const double* __restrict__ L, const double* __restrict__ Lc, DAdapt A)
+__global__ void k_adapt_update(uint32_t n, int s, const uint32_t* __restrict__ list, const double* __restrict__ L, const double* __restrict__ Ld, const double* __restrict__ Lc, DAdapt A)
 {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const uint32_t pix = list[i];
-    const d3 rad = ld3(L + 3 * (size_t)i) + ld3(Lc + 3 * (size_t)i);
+    const d3 rad = (ld3(L + 3 * (size_t)i) + ld3(Ld + 3 * (size_t)i)) + ld3(Lc + 3 * (size_t)i);
     const d3 last = ld3(A.color + 3 * (size_t)pix);                                      // lastCol = color (:110)
     d3 color = s == 0 ? rad : (last * (1.0 * s) + rad) * (1.0 / (s + 1));              // :131-134
     double var = A.var[pix];
@@ -1421,7 +1425,7 @@ __global__ void k_adapt_update(uint32_t n, int s, const uint32_t* __restrict__ l
 }
 
 // add the chunk's per-path radiance into the tile accumulator, samples in ascending order per pixel
-__global__ void k_accumulate(uint64_t c0, uint32_t n, size_t npx, int tw, int th, const double* L, const double* Lc, double* accum)
+__global__ void k_accumulate(uint64_t c0, uint32_t n, size_t npx, int tw, int th, const double* L, const double* Ld, const double* Lc, double* accum)
 {
     size_t pix = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
     if (pix >= npx) return;
@@ -1434,7 +1438,7 @@ __global__ void k_accumulate(uint64_t c0, uint32_t n, size_t npx, int tw, int th
         uint64_t lin = k * npx + slot;
         if (lin >= c1) break;
         size_t i = (size_t)(lin - c0);
-        a0 += L[3 * i] + Lc[3 * i]; a1 += L[3 * i + 1] + Lc[3 * i + 1]; a2 += L[3 * i + 2] + Lc[3 * i + 2];
+        a0 += (L[3 * i] + Ld[3 * i]) + Lc[3 * i]; a1 += (L[3 * i + 1] + Ld[3 * i + 1]) + Lc[3 * i + 1]; a2 += (L[3 * i + 2] + Ld[3 * i + 2]) + Lc[3 * i + 2];
     }
     accum[3 * pix] = a0; accum[3 * pix + 1] = a1; accum[3 * pix + 2] = a2;
 }
