@@ -440,6 +440,10 @@ extern "C" int gi_scene_upload(gi_ctx* ctx, const gi_scene_desc* sc)
     for (uint32_t i = 0; i < sc->n_refs; i++) {
         uint32_t p = sc->leaf_prims[i];
         std::memcpy(refs[i].g, sc->prim_geom + 9 * (size_t)p, 9 * sizeof(double));
+        if (sc->prim_type[p] == GI_PRIM_TRIANGLE) {   // v0, edge1 = v1 - v0, edge2 = v2 - v0 (tri_hit)
+            double* g = refs[i].g;
+            for (int k = 0; k < 3; k++) { g[3 + k] = g[3 + k] - g[k]; g[6 + k] = g[6 + k] - g[k]; }
+        }
         refs[i].prim = p; refs[i].flags = pflags[p];
     }
     cudaStream_t st = ctx->stream;
@@ -1249,7 +1253,7 @@ static int render_device(gi_ctx* ctx, const gi_render_params* P, int x0, int y0,
                 {
                     ScopedTimer t(ctx, "tail");
                     CK(cudaMemsetAsync(&ctx->b_tail.as<DTailCounters>()->next, 0, 4, ctx->stream));
-                    const unsigned tail_grid = std::min<unsigned>(grid_for(n_active, GI_WPB), 148u * 3u);   // 3 blocks of 4 warps fit per SM at 168 registers
+                    const unsigned tail_grid = std::min<unsigned>(grid_for(n_active, GI_WPB), 148u * (unsigned)GI_TAIL_MINB);   // persistent warps: one resident wave
                     GI_LAUNCH_M(k_tail, tail_grid, GI_WPB * 32, ctx->S, ctx->G, have_map ? 1 : 0, *P, depth, n_active, in, PS, ctx->b_tail.as<DTailCounters>(), Q);
                     launches++;
                 }

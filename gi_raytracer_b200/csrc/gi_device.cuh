@@ -261,48 +261,30 @@ __device__ __forceinline__ void children_entry(const DNode& nd, const DRay& r, d
 }
 
 // push the hit children (t0c[i] >= 0) far-to-near, ties with the higher child index first, so that they pop in ascending
-// (entry distance, child index) order — the reference's sorted leaf order (octree.cpp:297-300).  A line meets at
-// most four octants: up to four hits are insertion-sorted in registers; more (grazing edges) take the general selection loop.
+// (entry distance, child index) order — the reference's sorted leaf order (octree.cpp:297-300).
+// Branch-free RANKING instead of a sort: entry distances are >= +0 and a miss is -1, so the raw 64-bit patterns compare like the
+// values with every miss above every hit.  rank(i) = number of children that come before child i in (pattern, index) order —
+// 28 integer comparisons, each settling one pair — and `order` packs the child index of every rank into 4-bit fields.  No
+// double is ever moved: the profile of the insertion-sorted version showed a quarter of the bounce kernel's instructions in
+// its predicated register shuffles (profiles/r01/ncu_full_v8_k_bounce.txt).
 __device__ __forceinline__ void push_children_ordered(const DNode& nd, double (&t0c)[8], uint32_t* stack, int& sp)
 {
-    double h0 = 0, h1 = 0, h2 = 0;           // sorted ascending (the fourth distance is never compared again); children arrive in index order, so ties stay in index order
-    int c0 = 0, c1 = 0, c2 = 0, c3 = 0, n = 0;
+    unsigned long long key[8];
+    uint32_t hits = 0;
 #pragma unroll
-    for (int i = 0; i < 8; i++) {
-        const double t = t0c[i];
-        if (t >= 0.0) {
-            if (n < 4) {
-                // the new entry goes behind every entry <= it: shift the larger ones up
-                const bool b2 = n > 2 && t < h2, b1 = n > 1 && t < h1, b0 = n > 0 && t < h0;
-                if (b2) c3 = c2;
-                if (b1) { h2 = h1; c2 = c1; }
-                if (b0) { h1 = h0; c1 = c0; }
-                if (b0) { h0 = t; c0 = i; }
-                else if (b1) { h1 = t; c1 = i; }
-                else if (b2) { h2 = t; c2 = i; }
-                else if (n == 3) c3 = i;
-                else if (n == 2) { h2 = t; c2 = i; }
-                else if (n == 1) { h1 = t; c1 = i; }
-                else { h0 = t; c0 = i; }
-            }
-            n++;
-        }
-    }
-    if (n <= 4) {
-        if (n > 3 && sp < GI_STACK_MAX) stack[sp++] = nd.child + __popc(nd.mask & ((1u << c3) - 1u));
-        if (n > 2 && sp < GI_STACK_MAX) stack[sp++] = nd.child + __popc(nd.mask & ((1u << c2) - 1u));
-        if (n > 1 && sp < GI_STACK_MAX) stack[sp++] = nd.child + __popc(nd.mask & ((1u << c1) - 1u));
-        if (n > 0 && sp < GI_STACK_MAX) stack[sp++] = nd.child + __popc(nd.mask & ((1u << c0) - 1u));
-        return;
-    }
-    for (;;) {
-        double bt = -1.0; int bi = -1;
+    for (int i = 0; i < 8; i++) { key[i] = (unsigned long long)__double_as_longlong(t0c[i]); hits += (uint32_t)(~(uint32_t)(key[i] >> 63)) & 1u; }
+    if (hits == 0) return;
+    uint32_t rank = 0;   // 4 bits per child
 #pragma unroll
-        for (int i = 0; i < 8; i++) if (t0c[i] >= bt && t0c[i] >= 0.0) { bt = t0c[i]; bi = i; }
-        if (bi < 0) break;
-        if (sp < GI_STACK_MAX) stack[sp++] = nd.child + __popc(nd.mask & ((1u << bi) - 1u));
+    for (int i = 0; i < 8; i++)
 #pragma unroll
-        for (int i = 0; i < 8; i++) if (i == bi) t0c[i] = -1.0;
+        for (int j = i + 1; j < 8; j++) rank += key[j] < key[i] ? (1u << (4 * i)) : (1u << (4 * j));   // ties: the lower index comes first
+    uint32_t order = 0;  // child index of rank r in bits [4r, 4r+3]
+#pragma unroll
+    for (int i = 0; i < 8; i++) order |= (uint32_t)i << (((rank >> (4 * i)) & 15u) * 4u);
+    for (int r = (int)hits - 1; r >= 0; r--) {
+        const uint32_t c = (order >> (4 * r)) & 7u;
+        if (sp < GI_STACK_MAX) stack[sp++] = nd.child + __popc(nd.mask & ((1u << c) - 1u));
     }
 }
 
@@ -322,8 +304,10 @@ __device__ __forceinline__ DNode load_node(const DNode* nodes, uint32_t i)
 // triangle::intersect, geometric part (entities.h:443-478): returns t > 0 or -1; u, v barycentrics
 __device__ __forceinline__ double tri_hit(const double* g, const DRay& r, double& uo, double& vo)
 {
+    // a triangle's leaf record holds v0, v1 - v0, v2 - v0: the edges the reference recomputes per test (entities.h:447-448),
+    // subtracted once at upload in the same fp64 arithmetic
     d3 v0 = mk3(g[0], g[1], g[2]);
-    d3 edge1 = mk3(g[3], g[4], g[5]) - v0, edge2 = mk3(g[6], g[7], g[8]) - v0;
+    d3 edge1 = mk3(g[3], g[4], g[5]), edge2 = mk3(g[6], g[7], g[8]);
     d3 p = cross3(r.d, edge2);
     double det = dot3(edge1, p);
     if (det < GI_D_EPSILON && det > -GI_D_EPSILON) return -1.0;

@@ -967,9 +967,7 @@ __global__ void __launch_bounds__(GI_BLOCK, GI_MINB) k_bounce(DScene S, gi_rende
         DRay r = ray_as_stored(ld3(in.o + 3 * (size_t)i), ld3(in.d + 3 * (size_t)i));
         d3 T = ld3(in.T + 3 * (size_t)i);
         contrib = ld3(in.contrib + 3 * (size_t)i);
-        uint64_t key = PS.key[path]; uint32_t sample = PS.sample[path];
-        float sx = halton_sample(S, (uint32_t)(2 + 2 * depth), sample);     // raytracer.h:172-173
-        float sy = halton_sample(S, (uint32_t)(3 + 2 * depth), sample);
+        uint64_t key = PS.key[path];
         DHit h;
         trace_closest<FULL, IMPL>(S, r, P.seed, key, (uint64_t)depth, h, wn, wp);  // :190
         double* L = PS.L + 3 * (size_t)path;
@@ -978,6 +976,9 @@ __global__ void __launch_bounds__(GI_BLOCK, GI_MINB) k_bounce(DScene S, gi_rende
             L[0] += a.x; L[1] += a.y; L[2] += a.z;
         } else {
             is_hit = true;
+            const uint32_t sample = PS.sample[path];
+            const float sx = halton_sample(S, (uint32_t)(2 + 2 * depth), sample);     // raytracer.h:172-173 (only a hit uses them)
+            const float sy = halton_sample(S, (uint32_t)(3 + 2 * depth), sample);
             double tu, tv;
             hit_surface(S, r, h, FULL, hp, hn, tu, tv);
             const gi_material& m = S.mats[S.prim_mat[h.prim]];
@@ -1089,15 +1090,15 @@ __global__ void __launch_bounds__(GI_BLOCK, GI_MINB) k_bounce_p(DScene S, gi_ren
         if (finished) {
             d3 T = ld3(in.T + 3 * (size_t)qi);
             contrib = ld3(in.contrib + 3 * (size_t)qi);
-            const uint32_t sample = PS.sample[path];
-            float sx = halton_sample(S, (uint32_t)(2 + 2 * depth), sample);     // raytracer.h:172-173
-            float sy = halton_sample(S, (uint32_t)(3 + 2 * depth), sample);
             double* L = PS.L + 3 * (size_t)path;
             if (h.prim == GI_NO_HIT) {
                 d3 a = T * ld3(S.ambient);                                       // :275
                 L[0] += a.x; L[1] += a.y; L[2] += a.z;
             } else {
                 is_hit = true;
+                const uint32_t sample = PS.sample[path];
+                const float sx = halton_sample(S, (uint32_t)(2 + 2 * depth), sample);     // raytracer.h:172-173 (only a hit uses them)
+                const float sy = halton_sample(S, (uint32_t)(3 + 2 * depth), sample);
                 double tu, tv;
                 hit_surface(S, r, h, FULL, hp, hn, tu, tv);
                 const gi_material& m = S.mats[S.prim_mat[h.prim]];
@@ -1197,8 +1198,11 @@ struct DTailQ { double* pos; double* dir; double* w; double* rgb; uint32_t* coun
 
 struct DTailCounters { unsigned long long closest, shadow, gathers, nodes_c, prims_c, nodes_s, prims_s, g_depth, g_cand, g_sel; unsigned int next; unsigned int pad; };
 
+#ifndef GI_TAIL_MINB
+#define GI_TAIL_MINB 3   // resident blocks of 4 warps per SM asked of ptxas for the tail kernel
+#endif
 template <int MODE, bool IMPL>
-__global__ void __launch_bounds__(GI_WPB * 32) k_tail(DScene S, DGatherMap G, int have_map, gi_render_params P, int depth0, uint32_t n, DQueue in, DPathState PS, DTailCounters* TC, DTailQ Q)
+__global__ void __launch_bounds__(GI_WPB * 32, GI_TAIL_MINB) k_tail(DScene S, DGatherMap G, int have_map, gi_render_params P, int depth0, uint32_t n, DQueue in, DPathState PS, DTailCounters* TC, DTailQ Q)
 {
     constexpr bool FULL = MODE != 0, FOG = MODE == 2;   // MODE 0: uv-writing opaque primitives only, 1: any scene, 2: any scene + atmosphere
     __shared__ uint32_t s_stack[GI_WPB][GI_STACK_MAX];
