@@ -311,9 +311,16 @@ __device__ __forceinline__ double tri_hit(const double* g, const DRay& r, double
     d3 p = cross3(r.d, edge2);
     double det = dot3(edge1, p);
     if (det < GI_D_EPSILON && det > -GI_D_EPSILON) return -1.0;
-    double inv_det = 1.0 / det;
     d3 tvec = r.o - v0;
-    double u = dot3(tvec, p) * inv_det;
+    const double a = dot3(tvec, p);
+    // u = a * fl(1 / det) (entities.h:455-459) is certainly negative when a and det differ in sign (|a| > 1e-300 keeps the
+    // product away from underflow) and certainly above 1 when |a| exceeds |det| by more than the two roundings can undo
+    // ((1 + 2^-49)(1 - 2^-53) > 1 + 2^-50): those candidates are rejected before the fp64 division — it alone was 3-7 % of
+    // the traversal kernels' instructions.  Everything else takes the reference's arithmetic.
+    if (((a < 0) != (det < 0)) && fabs(a) > 1e-300) return -1.0;
+    if (fabs(a) > fabs(det) * (1.0 + 0x1p-48)) return -1.0;
+    double inv_det = 1.0 / det;
+    double u = a * inv_det;
     if (u < 0 || u > 1) return -1.0;
     d3 q = cross3(tvec, edge1);
     double v = dot3(r.d, q) * inv_det;

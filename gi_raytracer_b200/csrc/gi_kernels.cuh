@@ -662,6 +662,7 @@ __global__ void __launch_bounds__(GI_GS_BLOCK) k_gather_sorted(DGatherMap M, uin
         }
     }
     const int count = (int)total < k ? (int)total : k;
+    const float delta_f = __double2float_ru(delta);
     int m = 0;                       // rows in use
     double tau = CUDART_INF; uint32_t tau_sl = 0xFFFFFFFFu;   // the k-th (distance^2, slot) once m == k
     float bound = CUDART_INF_F;      // scan stops at the first key above it
@@ -693,8 +694,10 @@ __global__ void __launch_bounds__(GI_GS_BLOCK) k_gather_sorted(DGatherMap M, uin
                 for (int i = k / 2 - 1; i >= 0; i--) heap_sift(s_d, s_sl, t, k, i, s_d[i][t], s_sl[i][t]);   // k rows filled: heapify
             }
             tau = s_d[0][t]; tau_sl = s_sl[0][t];
-            const double b = sqrt(tau) + delta;
-            bound = __double2float_ru(b * b * (1.0 + 1e-9));
+            // (sqrt(tau) + delta)^2 from above, in fp32 with every step rounded up (the bound only decides where the scan may stop;
+            // an fp64 sqrt after every heap change was 7 % of the kernel's instructions)
+            const float bf = __fadd_ru(__fsqrt_ru(__double2float_ru(tau)), delta_f);
+            bound = __fmul_ru(__fmul_ru(bf, bf), 1.000001f);
         }
     }
     if (!hard && m > 1) {
