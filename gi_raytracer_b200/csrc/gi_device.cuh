@@ -231,7 +231,8 @@ __device__ __forceinline__ double child_entry(const PlaneT& T, int i, const DRay
 // negative direction, near) planes.  t0c[i] = entry distance, or -1 when the child is absent or missed.
 #define GI_UP(a, b) ((b) > (a) ? (b) : (a))
 #define GI_DN(a, b) ((b) < (a) ? (b) : (a))
-__device__ __forceinline__ void children_entry(const DNode& nd, const DRay& r, double tmin0, double tmax0, double (&t0c)[8])
+// Returns the mask of children that exist and are hit; t0c[i] = entry distance of child i (meaningful for the hit ones).
+__device__ __forceinline__ uint32_t children_entry(const DNode& nd, const DRay& r, double tmin0, double tmax0, double (&t0c)[8])
 {
     PlaneT T;
     plane_params(nd, r, T);
@@ -249,15 +250,19 @@ __device__ __forceinline__ void children_entry(const DNode& nd, const DRay& r, d
 #pragma unroll
         for (int b = 0; b < 2; b++) { exy[a][b] = GI_UP(ex[a], ny[b]); lxy[a][b] = GI_DN(lx[a], fy[b]); }
 #pragma unroll
+    uint32_t miss = 0;
     for (int i = 0; i < 7; i++) {   // bit0 = +x, bit1 = +z, bit2 = +y
         const int bx = i & 1, bz = (i >> 1) & 1, by = (i >> 2) & 1;
         const double en = GI_UP(exy[bx][by], nz[bz]), lv = GI_DN(lxy[bx][by], fz[bz]);
-        t0c[i] = ((nd.mask >> i) & 1u) && !(lv <= en) ? en : -1.0;
+        t0c[i] = en;
+        miss |= (lv <= en ? 1u : 0u) << i;
     }
     {
         const double en = GI_UP(GI_UP(GI_UP(tmin0, nx[2]), ny[2]), nz[2]), lv = GI_DN(GI_DN(GI_DN(tmax0, fx[2]), fy[2]), fz[2]);
-        t0c[7] = ((nd.mask >> 7) & 1u) && !(lv <= en) ? en : -1.0;
+        t0c[7] = en;
+        miss |= (lv <= en ? 1u : 0u) << 7;
     }
+    return nd.mask & ~miss;
 }
 
 // push the hit children (t0c[i] >= 0) far-to-near, ties with the higher child index first, so that they pop in ascending
@@ -267,13 +272,14 @@ __device__ __forceinline__ void children_entry(const DNode& nd, const DRay& r, d
 // 28 integer comparisons, each settling one pair — and `order` packs the child index of every rank into 4-bit fields.  No
 // double is ever moved: the profile of the insertion-sorted version showed a quarter of the bounce kernel's instructions in
 // its predicated register shuffles (profiles/r01/ncu_full_v8_k_bounce.txt).
-__device__ __forceinline__ void push_children_ordered(const DNode& nd, double (&t0c)[8], uint32_t* stack, int& sp)
+__device__ __forceinline__ void push_children_ordered(const DNode& nd, const double (&t0c)[8], uint32_t hm, uint32_t* stack, int& sp)
 {
+    if (hm == 0) return;
+    // keys: the raw pattern of the entry distance (always >= +0, so patterns order like values) with the sign bit set for a
+    // child that is not hit: it ranks behind every hit
     unsigned long long key[8];
-    uint32_t hits = 0;
 #pragma unroll
-    for (int i = 0; i < 8; i++) { key[i] = (unsigned long long)__double_as_longlong(t0c[i]); hits += (uint32_t)(~(uint32_t)(key[i] >> 63)) & 1u; }
-    if (hits == 0) return;
+    for (int i = 0; i < 8; i++) key[i] = (unsigned long long)__double_as_longlong(t0c[i]) | ((unsigned long long)((~hm >> i) & 1u) << 63);
     uint32_t rank = 0;   // 4 bits per child
 #pragma unroll
     for (int i = 0; i < 8; i++)
@@ -282,7 +288,7 @@ __device__ __forceinline__ void push_children_ordered(const DNode& nd, double (&
     uint32_t order = 0;  // child index of rank r in bits [4r, 4r+3]
 #pragma unroll
     for (int i = 0; i < 8; i++) order |= (uint32_t)i << (((rank >> (4 * i)) & 15u) * 4u);
-    for (int r = (int)hits - 1; r >= 0; r--) {
+    for (int r = __popc(hm) - 1; r >= 0; r--) {
         const uint32_t c = (order >> (4 * r)) & 7u;
         if (sp < GI_STACK_MAX) stack[sp++] = nd.child + __popc(nd.mask & ((1u << c) - 1u));
     }
@@ -313,11 +319,14 @@ __device__ __forceinline__ double tri_hit(const double* g, const DRay& r, double
     if (det < GI_D_EPSILON && det > -GI_D_EPSILON) return -1.0;
     d3 tvec = r.o - v0;
     const double a = dot3(tvec, p);
-    // u = a * fl(1 / det) (entities.h:455-459) is certainly negative when a and det differ in sign (|a| > 1e-300 keeps the
+    // u = a * fl(1 / det) (entities.h:455-459) is certainly negative when a and det differ in sign (|a| > 2^-1007 keeps the
     // product away from underflow) and certainly above 1 when |a| exceeds |det| by more than the two roundings can undo
     // ((1 + 2^-49)(1 - 2^-53) > 1 + 2^-50): those candidates are rejected before the fp64 division — it alone was 3-7 % of
     // the traversal kernels' instructions.  Everything else takes the reference's arithmetic.
-    if (((a < 0) != (det < 0)) && fabs(a) > 1e-300) return -1.0;
+    {
+        const int ha = __double2hiint(a), hd = __double2hiint(det);
+        if ((ha ^ hd) < 0 && (ha & 0x7ff00000) > 0x01000000) return -1.0;   // signs differ and |a| > 2^-1007
+    }
     if (fabs(a) > fabs(det) * (1.0 + 0x1p-48)) return -1.0;
     double inv_det = 1.0 / det;
     double u = a * inv_det;
@@ -487,8 +496,9 @@ __device__ __forceinline__ void trace_walk(const DScene& S, const DRay& r, uint6
             // interior: entry distance of every existing child, then push far-to-near (ties: higher child index first,
             // so that equal-distance children pop in child order)
             double t0c[8];
+            uint32_t hm = 0;
             n_node += __popc(nd.mask);
-            if (IMPL) children_entry(nd, r, 0.0, CUDART_INF, t0c);
+            if (IMPL) hm = children_entry(nd, r, 0.0, CUDART_INF, t0c);
             else {
                 uint32_t c = nd.child;
 #pragma unroll
@@ -497,11 +507,12 @@ __device__ __forceinline__ void trace_walk(const DScene& S, const DRay& r, uint6
                     if (nd.mask & (1u << i)) {
                         DNode ch = load_node(S.nodes, c);
                         t0c[i] = box_entry(ch.bmin, ch.bmax, r, 0.0, CUDART_INF);
+                        if (t0c[i] >= 0.0) hm |= 1u << i;
                         c++;
                     }
                 }
             }
-            push_children_ordered(nd, t0c, stack, sp);
+            push_children_ordered(nd, t0c, hm, stack, sp);
             if (sp == 0) { have_leaf = false; break; }
             ni = stack[--sp];
             nd = load_node(S.nodes, ni);
@@ -578,11 +589,11 @@ __device__ __forceinline__ bool trace_visible(const DScene& S, const DRay& r, do
             n_node += __popc(nd.mask);
             if (IMPL) {
                 double t0c[8];
-                children_entry(nd, r, 0.0, tmax, t0c);
+                const uint32_t hm = children_entry(nd, r, 0.0, tmax, t0c);   // any-hit needs the mask only: the entry distances are dead code
 #pragma unroll
                 for (int i = 0; i < 8; i++) {
                     if (nd.mask & (1u << i)) {
-                        if (t0c[i] >= 0.0 && sp < GI_STACK_MAX) stack[sp++] = c;
+                        if (((hm >> i) & 1u) && sp < GI_STACK_MAX) stack[sp++] = c;
                         c++;
                     }
                 }
