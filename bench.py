@@ -8,7 +8,7 @@ isolated photon gather over the frame's primary-hit queries.
 
   metric  Mrays/s (all bounces) = (closest-hit + shadow traversals issued by the frame) / frame time
   value   whole-job throughput with everything resident in HBM (gi_render_tile_dev), CUDA events, max over ranks
-  e2e     same metric through the host-pointer C ABI: gi_scene_upload + gi_render_tile + gi_resolve with HOST buffers
+  e2e     same metric through the host-pointer C ABI: gi_scene_upload + gi_render_image with HOST buffers
   gather  photon-gather Mqueries/s (gi_photon_gather_dev) over the primary-hit queries, same frame
   N > 1   weak scaling by sample index: rank r renders samples [8r, 8r+8) of every pixel; photon map built on rank 0
           and broadcast over NCCL (outside the timed region, like the reference's cached map); per-step NCCL reduce of
@@ -301,13 +301,12 @@ def main():
                                                         "prim_nrm", "prim_uv", "prim_fnorm", "prim_mat", "mats", "tex", "tex_pixels", "lights"))
     import ctypes as C
     from gi_raytracer_b200.abi import GiStats
-    rgb8 = np.empty((H * W, 3), dtype=np.uint8)
+    rgb8 = torch.empty((H * W, 3), dtype=torch.uint8).pin_memory().numpy()
 
-    def step_e2e():
+    def step_e2e():   # what RayTracer::run does per frame: scene description in, 8-bit image and fp64 sums out (pinned host buffers)
         ctx.upload_scene(scene)
         st = GiStats()
-        ctx._ck(ctx.L.gi_render_tile(ctx.h, C.byref(P), 0, 0, W, H, s0, s1, acc_host.ctypes.data, C.byref(st)))
-        ctx._ck(ctx.L.gi_resolve(ctx.h, H * W, acc_host.ctypes.data, SPP, rgb8.ctypes.data))
+        ctx._ck(ctx.L.gi_render_image(ctx.h, C.byref(P), 0, 0, W, H, s0, s1, rgb8.ctypes.data, acc_host.ctypes.data, C.byref(st)))
         return st
 
     step_e2e()
@@ -389,8 +388,8 @@ def main():
                        "candidates_per_query": gwork[2] / max(gwork[0], 1)},
             "photons": {"tries": int(photon_stats.photon_tries) if photon_stats else None, "traces": int(photon_stats.closest_rays) if photon_stats else None,
                         "trace_ms": float(photon_stats.total_ms) if photon_stats else None},
-            "e2e": {"value": e2e_rays_all / e2e_s / 1e6, "unit": "Mrays/s", "h2d_bytes_per_step": int(scene_bytes + H * W * 24), "d2h_bytes_per_step": int(H * W * 24 + H * W * 3),
-                    "ms_per_step": 1e3 * e2e_s / K, "calls": "gi_scene_upload + gi_render_tile + gi_resolve (host pointers)"},
+            "e2e": {"value": e2e_rays_all / e2e_s / 1e6, "unit": "Mrays/s", "h2d_bytes_per_step": int(scene_bytes), "d2h_bytes_per_step": int(H * W * 24 + H * W * 3),
+                    "ms_per_step": 1e3 * e2e_s / K, "calls": "gi_scene_upload + gi_render_image (host pointers: scene arrays in, 8-bit image + fp64 sums out)"},
             "gpu_launches": int(launches_all),
             "roofline": roofline,
             "cpu_baseline": cpu,

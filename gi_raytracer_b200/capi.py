@@ -22,7 +22,7 @@ API_SYMBOLS = [
     "gi_photon_map_build", "gi_photon_map_info", "gi_photon_map_download", "gi_photon_map_slab_size",
     "gi_photon_map_slab_ptr", "gi_photon_map_adopt_slab", "gi_photon_map_reserve_slab", "gi_photon_gather",
     "gi_photon_gather_dev", "gi_render_tile", "gi_render_tile_dev", "gi_resolve", "gi_resolve_dev", "gi_last_kernel_ms",
-    "gi_last_work", "gi_scene_info", "gi_render_adaptive", "gi_render_adaptive_dev", "gi_fog_density", "gi_raymarch", "gi_octree_build", "gi_octree_download", "gi_cancel",
+    "gi_last_work", "gi_scene_info", "gi_render_adaptive", "gi_render_adaptive_dev", "gi_fog_density", "gi_raymarch", "gi_octree_build", "gi_octree_download", "gi_cancel", "gi_render_image",
 ]
 
 _LIB = None
@@ -101,6 +101,7 @@ def load_library():
                                    C.POINTER(C.c_double), C.POINTER(C.c_double)]
     L.gih_render_progressive.argtypes = [C.c_char_p, i32, i32, i32, i32, i32, i32, u64, i32, i32, vp, C.POINTER(i32), C.POINTER(C.c_double)]
     L.gi_cancel.argtypes = [vp, i32]
+    L.gi_render_image.argtypes = [vp, C.POINTER(GiRenderParams), i32, i32, i32, i32, i32, i32, vp, vp, C.POINTER(GiStats)]
     L.gih_png_decode.argtypes = [C.c_char_p, C.POINTER(i32), C.POINTER(i32), C.POINTER(i32), vp, sz]
     L.gih_png_encode.argtypes = [C.c_char_p, i32, i32, vp]
     _LIB = L
@@ -320,6 +321,15 @@ class Context:
         st = GiStats()
         self._ck(self.L.gi_render_tile(self.h, C.byref(params), x0, y0, x1, y1, s0, s1, _p(acc), C.byref(st)))
         return acc, st
+
+    def render_image(self, params: GiRenderParams, x0, y0, x1, y1, s0, s1, want_accum=False):
+        """gi_render_image: the resolved 8-bit frame (and optionally the fp64 sums), one call, no accumulator round trip."""
+        npx = (x1 - x0) * (y1 - y0)
+        rgb = np.empty((npx, 3), dtype=np.uint8)
+        acc = np.empty((npx, 3)) if want_accum else None
+        st = GiStats()
+        self._ck(self.L.gi_render_image(self.h, C.byref(params), x0, y0, x1, y1, s0, s1, _p(rgb), _p(acc) if want_accum else None, C.byref(st)))
+        return rgb, acc, st
 
     def render_adaptive(self, params: GiRenderParams, min_samples, max_samples, noise_thresh, x0, y0, x1, y1):
         """gi_render_adaptive -> (colour [npx, 3] fp64 running means, samples taken [npx] u32, GiStats)."""

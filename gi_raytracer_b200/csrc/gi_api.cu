@@ -1431,6 +1431,26 @@ extern "C" int gi_render_tile(gi_ctx* ctx, const gi_render_params* P, int x0, in
     return GI_OK;
 }
 
+// The frame as the reference's run() leaves it: rendered, resolved to 8-bit on the device, only the image (and, if asked for,
+// the fp64 sums) copied back — no host round trip of the accumulator between render and resolve.
+extern "C" int gi_render_image(gi_ctx* ctx, const gi_render_params* P, int x0, int y0, int x1, int y1, int s0, int s1, uint8_t* rgb8, double* accum, gi_stats* stats)
+{
+    if (!rgb8) return GI_ERR_INVALID;
+    int rc = check_render_args(ctx, P, x0, y0, x1, y1, s0, s1, reinterpret_cast<const double*>(rgb8));
+    if (rc != GI_OK) return rc;
+    CK(cudaSetDevice(ctx->device));
+    const size_t npx = (size_t)(x1 - x0) * (y1 - y0);
+    CK(ctx->b_accum.reserve(npx * 24)); CK(ctx->w1.reserve(npx * 3));
+    rc = render_device(ctx, P, x0, y0, x1, y1, s0, s1, ctx->b_accum.as<double>(), stats);
+    if (rc != GI_OK) return rc;
+    rc = gi_resolve_dev(ctx, npx, ctx->b_accum.as<double>(), s1 - s0, ctx->w1.as<uint8_t>());
+    if (rc != GI_OK) return rc;
+    CK(cudaMemcpyAsync(rgb8, ctx->w1.p, npx * 3, cudaMemcpyDeviceToHost, ctx->stream));
+    if (accum) CK(cudaMemcpyAsync(accum, ctx->b_accum.p, npx * 24, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return GI_OK;
+}
+
 extern "C" int gi_render_adaptive_dev(gi_ctx* ctx, const gi_render_params* P, int min_samples, int max_samples, double noise_thresh, int x0, int y0, int x1, int y1, double* color,
                                       uint32_t* samples, gi_stats* stats)
 {

@@ -108,18 +108,23 @@ int RayTracer::run(int w, int h)
     // bands of rows, top to bottom (one band = the whole frame unless progressive_rows is set); a band that has not started
     // when stop() arrives is skipped, like the rows of the reference's loop (raytracer.h:93-98)
     const int band = progressive_rows > 0 ? progressive_rows : h;
-    std::vector<double> accum((size_t)w * std::min(band, h) * 3);
+    std::vector<double> accum;
+    std::vector<uint8_t> band_rgb((size_t)w * std::min(band, h) * 3);   // a cancelled band must not touch the image: staged, then published
     _rows_done = 0;
     std::memset(&last_frame_stats, 0, sizeof(last_frame_stats));
     for (int y0 = 0; y0 < h; y0 += band) {
         if (!_running) break;
         const int y1 = std::min(h, y0 + band);
         gi_stats bs;
-        if (adaptive) rc = gi_render_adaptive(ctx, &p, min_samples, max_samples, noise_thresh, 0, y0, w, y1, accum.data(), nullptr, &bs);
-        else rc = gi_render_tile(ctx, &p, 0, y0, w, y1, 0, p.spp, accum.data(), &bs);
+        uint8_t* rows = _image->rgb.data() + (size_t)y0 * w * 3;
+        if (adaptive) {
+            accum.resize((size_t)w * (y1 - y0) * 3);
+            rc = gi_render_adaptive(ctx, &p, min_samples, max_samples, noise_thresh, 0, y0, w, y1, accum.data(), nullptr, &bs);
+            if (rc == GI_OK) rc = gi_resolve(ctx, (size_t)w * (y1 - y0), accum.data(), resolve_spp, band_rgb.data());
+        } else rc = gi_render_image(ctx, &p, 0, y0, w, y1, 0, p.spp, band_rgb.data(), nullptr, &bs);   // rendered and resolved on the device
         if (rc == GI_ERR_CANCELLED) break;   // stop() while the band was on the device: its pixels are not published
         if (rc != GI_OK) { std::cout << "gi_render: " << gi_last_error(ctx) << "\n"; return rc; }
-        if ((rc = gi_resolve(ctx, (size_t)w * (y1 - y0), accum.data(), resolve_spp, _image->rgb.data() + (size_t)y0 * w * 3)) != GI_OK) { std::cout << "gi_resolve: " << gi_last_error(ctx) << "\n"; return rc; }
+        std::memcpy(rows, band_rgb.data(), (size_t)w * (y1 - y0) * 3);
         _rows_done = y1;
         // totals over the bands
         uint64_t* dst = reinterpret_cast<uint64_t*>(&last_frame_stats); const uint64_t* src = reinterpret_cast<const uint64_t*>(&bs);

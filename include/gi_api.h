@@ -270,6 +270,11 @@ int gi_render_tile(gi_ctx* ctx, const gi_render_params* p, int x0, int y0, int x
                    gi_stats* stats);
 int gi_render_tile_dev(gi_ctx* ctx, const gi_render_params* p, int x0, int y0, int x1, int y1, int s0, int s1, double* accum,
                        gi_stats* stats);
+/* RayTracer::run's frame as it reaches the Image (raytracer.h:93-160 + image.h:14-16): samples [s0,s1) rendered and resolved
+ * (running mean over s1 - s0 samples, gamma 2.2, clamp, (int)(255c)) on the device; rgb8 [(y1-y0)*(x1-x0)][3] comes back,
+ * accum (optional, may be NULL) = the fp64 sums gi_render_tile would give. */
+int gi_render_image(gi_ctx* ctx, const gi_render_params* p, int x0, int y0, int x1, int y1, int s0, int s1, uint8_t* rgb8,
+                    double* accum, gi_stats* stats);
 /* ---- resolve: mean -> gamma 2.2 -> clamp -> (int)(255*c)  (raytracer.h:150-156, util.h:94-97, image.h:14-16) */
 /* Adaptive sampling: the per-pixel loop of RayTracer::run (raytracer.h:100-148) with `samples min max thresh`.  Every pixel
  * of the tile takes samples s = 0, 1, .. while s < max_samples && samps < min_samples (samps +1 per sample, -2 when the

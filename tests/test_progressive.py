@@ -105,3 +105,19 @@ def test_progressive_bands_and_stop_from_viewer_thread(lib_built, synth_dir):
     assert rc == 0 and 40 <= done < h and done % 8 == 0
     assert np.array_equal(part[:done], whole[:done])                         # what was published is final
     assert part[done:].max() == 0                                            # rows never started stay cleared (Image::clear, image.h:23)
+
+
+def test_render_image_equals_render_tile_plus_resolve(ctx, synth_dir):
+    """gi_render_image (what RayTracer::run calls per band) = gi_render_tile followed by gi_resolve, without the host round trip."""
+    from gi_raytracer_b200 import host
+    sc = host.load_scene(os.path.join(synth_dir, "mixed.scn"))
+    ctx.upload_scene(sc)
+    ctx.photon_trace(2000, 5, seed=3)
+    ctx.photon_map_build(None)
+    P = render_params(80, 56, 6, max_depth=6, seed=5)
+    acc, _ = ctx.render_tile(P, 8, 4, 72, 52, 0, 6)
+    img = ctx.resolve(acc, 6)
+    rgb, acc2, st = ctx.render_image(P, 8, 4, 72, 52, 0, 6, want_accum=True)
+    assert np.array_equal(rgb, img) and bits_equal(acc, acc2) and st.closest_rays > 0
+    rgb3, none, _ = ctx.render_image(P, 8, 4, 72, 52, 0, 6)
+    assert none is None and np.array_equal(rgb3, img)
