@@ -1288,8 +1288,10 @@ static int render_device(gi_ctx* ctx, const gi_render_params* P, int x0, int y0,
             if (hc.n_hits) {
                 // the host has just synchronised the main stream (counters), so the side streams need no event to start
                 const bool side = overlap && hc.n_hits < ctx->overlap_threshold;
+                static const bool big_direct = getenv("GI_BIG_DIRECT_OVERLAP") != nullptr;   // experiment: long shadow launches beside the gather
+                const bool side_d = side || (overlap && big_direct);
                 if (ctx->S.n_lights) {
-                    if (side) ctx->stream = ctx->side[0];
+                    if (side_d) ctx->stream = ctx->side[0];
                     {
                         ScopedTimer t(ctx, "direct");
                         GI_LAUNCH_M(k_direct, grid_for(hc.n_hits, GI_BLOCK), GI_BLOCK, ctx->S, *P, depth, hc.n_hits, H, PS, work_ptr(ctx, 2));
@@ -1311,7 +1313,7 @@ static int render_device(gi_ctx* ctx, const gi_render_params* P, int x0, int y0,
                         if (rcg != GI_OK) return rcg;
                     }
                 }
-                if (side) { cudaEventRecord(ctx->side_done[hpar][0], ctx->side[0]); cudaEventRecord(ctx->side_done[hpar][1], ctx->side[1]); pending[hpar] = true; }
+                if (side || side_d) { cudaEventRecord(ctx->side_done[hpar][0], ctx->side[0]); cudaEventRecord(ctx->side_done[hpar][1], ctx->side[1]); pending[hpar] = true; }
                 CK(cudaGetLastError());
             }
             if (getenv("GI_TRACE_LAUNCHES")) {
