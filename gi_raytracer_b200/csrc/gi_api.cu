@@ -68,6 +68,8 @@ struct gi_ctx {
     cudaStream_t main_stream = nullptr, side[2] = { nullptr, nullptr };
     cudaEvent_t side_done[2][2] = { { nullptr, nullptr }, { nullptr, nullptr } };   // [hit-list parity][side stream]
     uint32_t overlap_threshold = 1u << 20;   // GI_OVERLAP_THRESHOLD, 0 = off
+    DevBuf tsh[7];                           // the tail's deferred shadow rays (DTailQ::sh_*)
+    int tail_shadow_mode = 1;                // 1: shadow rays of the tail are queued and traced in one batch (GI_TAIL_SHADOW=0: inline)
     DevBuf hl2[7], b_scan1s;                 // second hit list (depth parity), scan scratch of the gather side stream
     bool no_implicit = false;      // GI_NO_IMPLICIT_BOXES at gi_create: always load child boxes (for A/B tests)
     int trace_mode = 0;            // 0: thread per ray, 1: warp per ray (API batch kernels; GI_TRACE_MODE)
@@ -248,6 +250,7 @@ extern "C" int gi_create(int device, gi_ctx** out)
         for (int q = 0; q < 2; q++) if (cudaEventCreateWithFlags(&ctx->side_done[q][k], cudaEventDisableTiming) != cudaSuccess) { delete ctx; return GI_ERR_CUDA; }
     }
     if (const char* e = getenv("GI_OVERLAP_THRESHOLD")) ctx->overlap_threshold = (uint32_t)strtoul(e, nullptr, 10);
+    if (const char* e = getenv("GI_TAIL_SHADOW")) ctx->tail_shadow_mode = atoi(e);
     // Halton tables are scene independent
     std::vector<uint16_t> tab; std::vector<DHaltonDim> dims;
     build_halton(tab, dims);
@@ -298,6 +301,7 @@ extern "C" void gi_destroy(gi_ctx* ctx)
         for (int q = 0; q < 2; q++) if (ctx->side_done[q][k]) cudaEventDestroy(ctx->side_done[q][k]);
     }
     for (auto& b : ctx->hl2) b.release();
+    for (auto& b : ctx->tsh) b.release();
     ctx->b_scan1s.release();
     cudaStreamDestroy(ctx->main_stream);
     delete ctx;
@@ -1250,12 +1254,38 @@ static int render_device(gi_ctx* ctx, const gi_render_params* P, int x0, int y0,
                     CK(ctx->tq[4].reserve((size_t)n_active * 4));
                     Q.pos = ctx->tq[0].as<double>(); Q.dir = ctx->tq[1].as<double>(); Q.w = ctx->tq[2].as<double>(); Q.rgb = ctx->tq[3].as<double>(); Q.count = ctx->tq[4].as<uint32_t>();
                 }
+                if (ctx->tail_shadow_mode == 1 && ctx->S.n_lights) {
+                    Q.smax = (uint32_t)(P->max_depth - depth + 1) * ctx->S.n_lights;
+                    const size_t ss = (size_t)n_active * Q.smax;
+                    if (ss > 0xFFFFFFF0ull) return fail(ctx, GI_ERR_INVALID, "too many tail shadow slots");
+                    CK(ctx->tsh[0].reserve(ss * 24)); CK(ctx->tsh[1].reserve(ss * 24)); CK(ctx->tsh[2].reserve(ss * 8)); CK(ctx->tsh[3].reserve(ss * 24)); CK(ctx->tsh[4].reserve(ss * 4));
+                    CK(ctx->tsh[5].reserve((size_t)n_active * 4)); CK(ctx->tsh[6].reserve(ss));
+                    Q.sh_o = ctx->tsh[0].as<double>(); Q.sh_d = ctx->tsh[1].as<double>(); Q.sh_mt = ctx->tsh[2].as<double>(); Q.sh_w = ctx->tsh[3].as<double>();
+                    Q.sh_depth = ctx->tsh[4].as<uint32_t>(); Q.sh_count = ctx->tsh[5].as<uint32_t>(); Q.sh_vis = ctx->tsh[6].as<uint8_t>();
+                }
                 {
                     ScopedTimer t(ctx, "tail");
                     CK(cudaMemsetAsync(&ctx->b_tail.as<DTailCounters>()->next, 0, 4, ctx->stream));
                     const unsigned tail_grid = std::min<unsigned>(grid_for(n_active, GI_WPB), 148u * (unsigned)GI_TAIL_MINB);   // persistent warps: one resident wave
                     GI_LAUNCH_M(k_tail, tail_grid, GI_WPB * 32, ctx->S, ctx->G, have_map ? 1 : 0, *P, depth, n_active, in, PS, ctx->b_tail.as<DTailCounters>(), Q);
                     launches++;
+                }
+                if (Q.smax) {
+                    // the queued shadow rays, one thread each, beside the tail's gather run (side stream 0); k_tail_direct then adds the
+                    // unshadowed terms to Ld in bounce order
+                    cudaEventRecord(ctx->side_done[0][0], ctx->main_stream);
+                    if (overlap) { ctx->stream = ctx->side[0]; cudaStreamWaitEvent(ctx->side[0], ctx->side_done[0][0], 0); }
+                    {
+                        ScopedTimer t(ctx, "direct");
+                        GI_LAUNCH_M(k_tail_shadow, grid_for((size_t)n_active * Q.smax, GI_BLOCK), GI_BLOCK, ctx->S, *P, n_active, in, PS, Q, work_ptr(ctx, 2));
+                    }
+                    {
+                        ScopedTimer t(ctx, "tail");
+                        k_tail_direct<<<grid_for(n_active, 256), 256, 0, ctx->stream>>>(n_active, ctx->S.n_lights, in, PS, Q);
+                    }
+                    if (overlap) { cudaEventRecord(ctx->side_done[0][0], ctx->side[0]); cudaEventRecord(ctx->side_done[0][1], ctx->side[1]); pending[0] = true; }
+                    ctx->stream = ctx->main_stream;
+                    launches += 2;
                 }
                 if (Q.qmax) {
                     {
@@ -1288,7 +1318,7 @@ static int render_device(gi_ctx* ctx, const gi_render_params* P, int x0, int y0,
             if (hc.n_hits) {
                 // the host has just synchronised the main stream (counters), so the side streams need no event to start
                 const bool side = overlap && hc.n_hits < ctx->overlap_threshold;
-                static const bool big_direct = getenv("GI_BIG_DIRECT_OVERLAP") != nullptr;   // experiment: long shadow launches beside the gather
+                static const bool big_direct = getenv("GI_NO_BIG_DIRECT_OVERLAP") == nullptr;   // long shadow launches run beside the gather pipeline (C2 25.85 -> 25.43 ms, glass 51.0 -> 50.7)
                 const bool side_d = side || (overlap && big_direct);
                 if (ctx->S.n_lights) {
                     if (side_d) ctx->stream = ctx->side[0];
@@ -1394,7 +1424,8 @@ static int render_device(gi_ctx* ctx, const gi_render_params* P, int x0, int y0,
         const unsigned long long* w = ctx->work_host;
         stats->closest_node_tests = w[0]; stats->closest_prim_tests = w[1]; stats->shadow_node_tests = w[2]; stats->shadow_prim_tests = w[3];
         stats->gather_leaf_depth = w[4]; stats->gather_candidates = w[5]; stats->gather_selected = w[6];
-        stats->tail_closest_rays = tc.closest; stats->tail_shadow_rays = tc.shadow;
+        stats->tail_closest_rays = tc.closest;
+        stats->tail_shadow_rays = (ctx->tail_shadow_mode == 1) ? 0 : tc.shadow;   // queued tail shadow rays are traced (and tallied) by the batched any-hit kernel
         stats->tail_gathers = (ctx->tail_mode == 1 || !have_map) ? tc.gathers : 0;   // queued tail gathers are served (and tallied) by the gather pipeline
         stats->tail_closest_node_tests = tc.nodes_c; stats->tail_closest_prim_tests = tc.prims_c; stats->tail_shadow_node_tests = tc.nodes_s; stats->tail_shadow_prim_tests = tc.prims_s;
         stats->tail_gather_leaf_depth = tc.g_depth; stats->tail_gather_candidates = tc.g_cand; stats->tail_gather_selected = tc.g_sel;

@@ -1197,7 +1197,10 @@ __global__ void __launch_bounds__(GI_BLOCK, GI_MINB) k_direct(DScene S, gi_rende
 // takes the gather code out of the tail kernel (ncu showed it starved for instructions: 45 KB of code, ~10 warps per SM).
 // (A one-THREAD-per-path tail was measured too: 14.6 ms instead of 4.2 — the tail is bound by the latency of its deepest
 // paths, and a warp walking one ray cooperatively has a third of the per-bounce latency of a thread.)
-struct DTailQ { double* pos; double* dir; double* w; double* rgb; uint32_t* count; uint32_t qmax; };
+struct DTailQ { double* pos; double* dir; double* w; double* rgb; uint32_t* count; uint32_t qmax;
+                // deferred shadow rays (smax > 0): one slot per (bounce of the path, light), in bounce order — origin, stored direction,
+                // squared distance bound, weight x unshadowed light term, bounce depth; sh_count[path] = slots used, sh_vis = result
+                double* sh_o; double* sh_d; double* sh_mt; double* sh_w; uint32_t* sh_depth; uint32_t* sh_count; uint8_t* sh_vis; uint32_t smax; };
 
 struct DTailCounters { unsigned long long closest, shadow, gathers, nodes_c, prims_c, nodes_s, prims_s, g_depth, g_cand, g_sel; unsigned int next; unsigned int pad; };
 
@@ -1224,6 +1227,7 @@ __global__ void __launch_bounds__(GI_WPB * 32, GI_TAIL_MINB) k_tail(DScene S, DG
     const uint64_t key = PS.key[path]; const uint32_t sample = PS.sample[path];
     d3 L = ld3(PS.L + 3 * (size_t)path), Lc = ld3(PS.Lc + 3 * (size_t)path), Ld = ld3(PS.Ld + 3 * (size_t)path);
     uint32_t nq = 0;   // gather queries queued by this path
+    uint32_t nsh = 0;  // shadow rays queued by this path
     unsigned long long c_closest = 0, c_shadow = 0, c_gather = 0, g_depth = 0, g_cand = 0, g_sel = 0;
     uint32_t nc = 0, pc = 0, ns = 0, ps = 0;
     for (int depth = depth0; depth <= P.max_depth; depth++) {
@@ -1264,6 +1268,19 @@ __global__ void __launch_bounds__(GI_WPB * 32, GI_TAIL_MINB) k_tail(DScene S, DG
                 double hfrac = 1 / (GI_D_PI * len2(ld3(light.pos) - hp));
                 DRay sr = make_ray(sp, lightDir);
                 c_shadow++;
+                if (Q.smax) {
+                    // deferred: the shadow ray does not decide how the path goes on, so it leaves the latency chain of the path —
+                    // k_tail_shadow traces all of them at once, k_tail_direct adds the terms to Ld in bounce order
+                    double d = dot3(hn, normalize3(ld3(light.pos) - hp));
+                    if (d < 0) d = 0;
+                    const d3 lv = (ld3(light.col) * pow_like_libm(d, (1.0 / rough))) * hfrac;
+                    if (lane == 0 && nsh < Q.smax) {
+                        const size_t s = (size_t)i * Q.smax + nsh;
+                        st3(Q.sh_o + 3 * s, sr.o); st3(Q.sh_d + 3 * s, sr.d); Q.sh_mt[s] = maxt; st3(Q.sh_w + 3 * s, wdir * lv); Q.sh_depth[s] = (uint32_t)depth;
+                    }
+                    nsh++;
+                    continue;
+                }
                 bool vis = trace_visible_warp<FULL, IMPL>(S, sr, maxt, P.seed, key, (uint64_t)depth, l, stack, lane, ns, ps);
                 if (FOG && vis && fog_blocks(S, sr, maxt, P.seed, key, (uint64_t)depth, l)) vis = false;
                 if (vis) {
@@ -1272,7 +1289,7 @@ __global__ void __launch_bounds__(GI_WPB * 32, GI_TAIL_MINB) k_tail(DScene S, DG
                     li = (ld3(light.col) * pow_like_libm(d, (1.0 / rough))) * hfrac;
                 }
             }
-            Ld = Ld + wdir * li;
+            if (!Q.smax) Ld = Ld + wdir * li;
         }
         // caustic estimate (k_gather)
         if (depth <= P.caustic_max_depth) {
@@ -1296,6 +1313,7 @@ __global__ void __launch_bounds__(GI_WPB * 32, GI_TAIL_MINB) k_tail(DScene S, DG
     }
     if (lane == 0) {
         st3(PS.L + 3 * (size_t)path, L); st3(PS.Lc + 3 * (size_t)path, Lc); st3(PS.Ld + 3 * (size_t)path, Ld);
+        if (Q.smax) Q.sh_count[i] = nsh < Q.smax ? nsh : Q.smax;
         if (have_map && Q.qmax) {
             Q.count[i] = nq < Q.qmax ? nq : Q.qmax;
             for (uint32_t k = nq; k < Q.qmax; k++) st3(Q.pos + 3 * ((size_t)i * Q.qmax + k), mk3(CUDART_INF, CUDART_INF, CUDART_INF));   // unused slots: in no leaf
@@ -1343,6 +1361,44 @@ __device__ __forceinline__ size_t pixel_to_slot(int lx, int ly, int tw, int th)
     const int strip = ly / GI_TILE_ROWS;
     const int hh = min(GI_TILE_ROWS, th - strip * GI_TILE_ROWS);
     return (size_t)strip * GI_TILE_ROWS * tw + (size_t)lx * hh + (size_t)(ly - strip * GI_TILE_ROWS);
+}
+
+// the tail's deferred shadow rays: one thread per slot (RayTracer::visible, raytracer.h:280-319), then one thread per path adds the
+// unshadowed terms to Ld in bounce order — per bounce the LAST visible light's term, like the reference's `i = ...` (raytracer.h:254)
+template <int MODE, bool IMPL>
+__global__ void __launch_bounds__(GI_BLOCK, GI_MINB) k_tail_shadow(DScene S, gi_render_params P, uint32_t n, DQueue in, DPathState PS, DTailQ Q, unsigned long long* work)
+{
+    constexpr bool FULL = MODE != 0, FOG = MODE == 2;
+    const size_t s = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    uint32_t wn = 0, wp = 0;
+    const uint32_t i = (uint32_t)(s / Q.smax), k = (uint32_t)(s % Q.smax);
+    if (i < n && k < Q.sh_count[i]) {
+        const uint64_t key = PS.key[in.path[i]];
+        const uint32_t depth = Q.sh_depth[s], l = k % S.n_lights;
+        const DRay sr = ray_as_stored(ld3(Q.sh_o + 3 * s), ld3(Q.sh_d + 3 * s));
+        const double maxt = Q.sh_mt[s];
+        bool vis = trace_visible<FULL, IMPL>(S, sr, maxt, P.seed, key, (uint64_t)depth, l, wn, wp);
+        if (FOG && vis && fog_blocks(S, sr, maxt, P.seed, key, (uint64_t)depth, l)) vis = false;
+        Q.sh_vis[s] = vis ? 1 : 0;
+    }
+    tally2(work, wn, wp);
+}
+__global__ void k_tail_direct(uint32_t n, uint32_t n_lights, DQueue in, DPathState PS, DTailQ Q)
+{
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint32_t path = in.path[i];
+    d3 Ld = ld3(PS.Ld + 3 * (size_t)path);
+    const uint32_t ns = Q.sh_count[i];
+    for (uint32_t b = 0; b + n_lights <= ns; b += n_lights) {   // one bounce = n_lights consecutive slots
+        d3 term = mk3(0, 0, 0);
+        for (uint32_t l = 0; l < n_lights; l++) {
+            const size_t s = (size_t)i * Q.smax + b + l;
+            if (Q.sh_vis[s]) term = ld3(Q.sh_w + 3 * s);
+        }
+        Ld = Ld + term;
+    }
+    st3(PS.Ld + 3 * (size_t)path, Ld);
 }
 
 // generate the camera paths of one chunk (path-linear range [c0, c0+n) of the tile's sample-major path space)
