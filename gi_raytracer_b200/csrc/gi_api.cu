@@ -69,7 +69,6 @@ struct gi_ctx {
     cudaEvent_t side_done[2][2] = { { nullptr, nullptr }, { nullptr, nullptr } };   // [hit-list parity][side stream]
     uint32_t overlap_threshold = 1u << 20;   // GI_OVERLAP_THRESHOLD, 0 = off
     DevBuf tsh[7];                           // the tail's deferred shadow rays (DTailQ::sh_*)
-    int tail_shadow_mode = 1;                // 1: shadow rays of the tail are queued and traced in one batch (GI_TAIL_SHADOW=0: inline)
     DevBuf hl2[7], b_scan1s;                 // second hit list (depth parity), scan scratch of the gather side stream
     bool no_implicit = false;      // GI_NO_IMPLICIT_BOXES at gi_create: always load child boxes (for A/B tests)
     int trace_mode = 0;            // 0: thread per ray, 1: warp per ray (API batch kernels; GI_TRACE_MODE)
@@ -250,7 +249,6 @@ extern "C" int gi_create(int device, gi_ctx** out)
         for (int q = 0; q < 2; q++) if (cudaEventCreateWithFlags(&ctx->side_done[q][k], cudaEventDisableTiming) != cudaSuccess) { delete ctx; return GI_ERR_CUDA; }
     }
     if (const char* e = getenv("GI_OVERLAP_THRESHOLD")) ctx->overlap_threshold = (uint32_t)strtoul(e, nullptr, 10);
-    if (const char* e = getenv("GI_TAIL_SHADOW")) ctx->tail_shadow_mode = atoi(e);
     // Halton tables are scene independent
     std::vector<uint16_t> tab; std::vector<DHaltonDim> dims;
     build_halton(tab, dims);
@@ -1254,7 +1252,7 @@ static int render_device(gi_ctx* ctx, const gi_render_params* P, int x0, int y0,
                     CK(ctx->tq[4].reserve((size_t)n_active * 4));
                     Q.pos = ctx->tq[0].as<double>(); Q.dir = ctx->tq[1].as<double>(); Q.w = ctx->tq[2].as<double>(); Q.rgb = ctx->tq[3].as<double>(); Q.count = ctx->tq[4].as<uint32_t>();
                 }
-                if (ctx->tail_shadow_mode == 1 && ctx->S.n_lights) {
+                if (ctx->S.n_lights) {
                     Q.smax = (uint32_t)(P->max_depth - depth + 1) * ctx->S.n_lights;
                     const size_t ss = (size_t)n_active * Q.smax;
                     if (ss > 0xFFFFFFF0ull) return fail(ctx, GI_ERR_INVALID, "too many tail shadow slots");
@@ -1425,7 +1423,7 @@ static int render_device(gi_ctx* ctx, const gi_render_params* P, int x0, int y0,
         stats->closest_node_tests = w[0]; stats->closest_prim_tests = w[1]; stats->shadow_node_tests = w[2]; stats->shadow_prim_tests = w[3];
         stats->gather_leaf_depth = w[4]; stats->gather_candidates = w[5]; stats->gather_selected = w[6];
         stats->tail_closest_rays = tc.closest;
-        stats->tail_shadow_rays = (ctx->tail_shadow_mode == 1) ? 0 : tc.shadow;   // queued tail shadow rays are traced (and tallied) by the batched any-hit kernel
+        stats->tail_shadow_rays = 0;   // the tail's shadow rays are queued, then traced (and tallied) by the batched any-hit kernel k_tail_shadow
         stats->tail_gathers = (ctx->tail_mode == 1 || !have_map) ? tc.gathers : 0;   // queued tail gathers are served (and tallied) by the gather pipeline
         stats->tail_closest_node_tests = tc.nodes_c; stats->tail_closest_prim_tests = tc.prims_c; stats->tail_shadow_node_tests = tc.nodes_s; stats->tail_shadow_prim_tests = tc.prims_s;
         stats->tail_gather_leaf_depth = tc.g_depth; stats->tail_gather_candidates = tc.g_cand; stats->tail_gather_selected = tc.g_sel;

@@ -249,8 +249,8 @@ __device__ __forceinline__ uint32_t children_entry(const DNode& nd, const DRay& 
     for (int a = 0; a < 2; a++)
 #pragma unroll
         for (int b = 0; b < 2; b++) { exy[a][b] = GI_UP(ex[a], ny[b]); lxy[a][b] = GI_DN(lx[a], fy[b]); }
-#pragma unroll
     uint32_t miss = 0;
+#pragma unroll
     for (int i = 0; i < 7; i++) {   // bit0 = +x, bit1 = +z, bit2 = +y
         const int bx = i & 1, bz = (i >> 1) & 1, by = (i >> 2) & 1;
         const double en = GI_UP(exy[bx][by], nz[bz]), lv = GI_DN(lxy[bx][by], fz[bz]);

@@ -1205,7 +1205,8 @@ struct DTailQ { double* pos; double* dir; double* w; double* rgb; uint32_t* coun
 struct DTailCounters { unsigned long long closest, shadow, gathers, nodes_c, prims_c, nodes_s, prims_s, g_depth, g_cand, g_sel; unsigned int next; unsigned int pad; };
 
 #ifndef GI_TAIL_MINB
-#define GI_TAIL_MINB 3   // resident blocks of 4 warps per SM asked of ptxas for the tail kernel
+#define GI_TAIL_MINB 4   // resident blocks of 4 warps per SM asked of ptxas for the tail kernel (128 registers).  With the shadow rays
+                         // deferred the kernel is small enough for it: tail 2.78 -> 2.70 ms on C2, 2.93 -> 2.62 on glass (3 -> 4; 5 loses)
 #endif
 template <int MODE, bool IMPL>
 __global__ void __launch_bounds__(GI_WPB * 32, GI_TAIL_MINB) k_tail(DScene S, DGatherMap G, int have_map, gi_render_params P, int depth0, uint32_t n, DQueue in, DPathState PS, DTailCounters* TC, DTailQ Q)
@@ -1268,28 +1269,17 @@ __global__ void __launch_bounds__(GI_WPB * 32, GI_TAIL_MINB) k_tail(DScene S, DG
                 double hfrac = 1 / (GI_D_PI * len2(ld3(light.pos) - hp));
                 DRay sr = make_ray(sp, lightDir);
                 c_shadow++;
-                if (Q.smax) {
-                    // deferred: the shadow ray does not decide how the path goes on, so it leaves the latency chain of the path —
-                    // k_tail_shadow traces all of them at once, k_tail_direct adds the terms to Ld in bounce order
-                    double d = dot3(hn, normalize3(ld3(light.pos) - hp));
-                    if (d < 0) d = 0;
-                    const d3 lv = (ld3(light.col) * pow_like_libm(d, (1.0 / rough))) * hfrac;
-                    if (lane == 0 && nsh < Q.smax) {
-                        const size_t s = (size_t)i * Q.smax + nsh;
-                        st3(Q.sh_o + 3 * s, sr.o); st3(Q.sh_d + 3 * s, sr.d); Q.sh_mt[s] = maxt; st3(Q.sh_w + 3 * s, wdir * lv); Q.sh_depth[s] = (uint32_t)depth;
-                    }
-                    nsh++;
-                    continue;
+                // deferred: the shadow ray does not decide how the path goes on, so it leaves the latency chain of the path —
+                // k_tail_shadow traces all of them at once, k_tail_direct adds the terms to Ld in bounce order
+                double d = dot3(hn, normalize3(ld3(light.pos) - hp));
+                if (d < 0) d = 0;
+                const d3 lv = (ld3(light.col) * pow_like_libm(d, (1.0 / rough))) * hfrac;
+                if (lane == 0 && nsh < Q.smax) {
+                    const size_t s = (size_t)i * Q.smax + nsh;
+                    st3(Q.sh_o + 3 * s, sr.o); st3(Q.sh_d + 3 * s, sr.d); Q.sh_mt[s] = maxt; st3(Q.sh_w + 3 * s, wdir * lv); Q.sh_depth[s] = (uint32_t)depth;
                 }
-                bool vis = trace_visible_warp<FULL, IMPL>(S, sr, maxt, P.seed, key, (uint64_t)depth, l, stack, lane, ns, ps);
-                if (FOG && vis && fog_blocks(S, sr, maxt, P.seed, key, (uint64_t)depth, l)) vis = false;
-                if (vis) {
-                    double d = dot3(hn, normalize3(ld3(light.pos) - hp));
-                    if (d < 0) d = 0;
-                    li = (ld3(light.col) * pow_like_libm(d, (1.0 / rough))) * hfrac;
-                }
+                nsh++;
             }
-            if (!Q.smax) Ld = Ld + wdir * li;
         }
         // caustic estimate (k_gather)
         if (depth <= P.caustic_max_depth) {
