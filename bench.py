@@ -128,7 +128,7 @@ def reference_arm(args):
     try:
         res = run_reference_sample(K + Wm)
     except Exception as e:  # the oracle always exists in a built tree; report honestly if the binary is missing
-        print(json.dumps({"impl": "reference", "unavailable": str(e).splitlines()[0][:200]}))
+        emit({"impl": "reference", "unavailable": str(e).splitlines()[0][:200]})
         return
     timed = res["steps"][Wm:]
     tot_rays = sum(s["rays"] for s in timed)
@@ -143,7 +143,7 @@ def reference_arm(args):
         "e2e": {"value": value, "unit": "Mrays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line))
+    emit(line)
 
 
 # ---- our arm ---------------------------------------------------------------------------------------------------------------
@@ -395,12 +395,22 @@ def main():
             "cpu_baseline": cpu,
             "clocks": clk,
         }
-        print(json.dumps(line))
+        emit(line)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
     ctx.close()
 
 
+def emit(obj):
+    """The ONE JSON line of the run goes to the real stdout; everything else printed while the run lasted went to stderr."""
+    os.write(_REAL_STDOUT, (json.dumps(obj) + "\n").encode())
+
+
+_REAL_STDOUT = 1
 if __name__ == "__main__":
+    # libraries print to fd 1 from C (NCCL's version banner, the reference's own chatter): keep stdout for the JSON line alone
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
     main()
