@@ -5,7 +5,9 @@
 
 #include "gi_device.cuh"
 
+#ifndef GI_BLOCK
 #define GI_BLOCK 128
+#endif
 #ifndef GI_MINB
 #define GI_MINB 6   // resident blocks of 128 threads per SM asked of ptxas for the thread-per-ray traversal kernels: 80 registers.
 #endif              // measured on the C2 frame (bounce + direct ms): 1-3 blocks (136-142 regs) 23.1, 4 (128) 19.4, 5 (96) 18.8, 6 (80) 17.9, 8 (64) 19.1

@@ -505,3 +505,35 @@ def test_implicit_child_boxes_equal_loaded_boxes(lib_built, synth_dir, monkeypat
         assert ci.scene_info()["implicit_boxes"] == 0
     finally:
         ce.close(); ci.close()
+
+
+@pytest.mark.skipif(not have_assets("caustics"), reason="assets not staged")
+def test_c2_full_size_frame_properties(ctx):
+    """BASELINE config 2 at its full size (1024x1024, 8 spp, MAX_DEPTH 64, 1 M photons) through size-independent properties:
+    the frame equals the union of its tiles bit for bit, sample ranges add up, work tallies are additive, a second render
+    is identical, and the photon phase stores exactly the requested number of photons for every light."""
+    from gi_raytracer_b200 import host
+    sc = host.load_scene(scene_path("caustics"))
+    ctx.upload_scene(sc)
+    n, pst = ctx.photon_trace(1000000, 5, seed=1)
+    assert n == 1000000 * sc.lights.shape[0] and pst.photon_tries >= n
+    ctx.photon_map_build(None)
+    info = ctx.photon_map_info()
+    assert info["n_kept"] <= n and info["n_kept"] > 0.99 * n       # photons on a max face / in an ulp gap are dropped, like the reference
+    W = H = 1024
+    P = render_params(W, H, 8, max_depth=64, seed=1)
+    full, st = ctx.render_tile(P, 0, 0, W, H, 0, 8)
+    again, st2 = ctx.render_tile(P, 0, 0, W, H, 0, 8)
+    assert bits_equal(full, again) and st.closest_rays == st2.closest_rays and st.closest_node_tests == st2.closest_node_tests
+    assert np.isfinite(full).all() and full.mean() > 0   # (a caustic term can be negative: col * dot(photon dir, refDir), raytracer.h:558-576)
+    img = full.reshape(H, W, 3)
+    top, s_top = ctx.render_tile(P, 0, 0, W, 400, 0, 8)
+    bot, s_bot = ctx.render_tile(P, 0, 400, W, H, 0, 8)
+    assert bits_equal(top.reshape(400, W, 3), img[:400].copy()) and bits_equal(bot.reshape(H - 400, W, 3), img[400:].copy())
+    for f in ("closest_rays", "shadow_rays", "gathers", "closest_node_tests", "closest_prim_tests", "shadow_node_tests", "shadow_prim_tests", "gather_candidates"):
+        assert getattr(s_top, f) + getattr(s_bot, f) == getattr(st, f), f
+    a, _ = ctx.render_tile(P, 0, 0, W, H, 0, 3)
+    b, _ = ctx.render_tile(P, 0, 0, W, H, 3, 8)
+    assert np.allclose(a + b, full, rtol=1e-13, atol=1e-300)
+    # every primary ray is a closest-hit ray; shadow rays = hits x lights; gathers = hits up to depth 10
+    assert st.closest_rays >= W * H * 8 and st.shadow_rays <= st.closest_rays and st.gathers <= st.shadow_rays
