@@ -537,3 +537,32 @@ def test_c2_full_size_frame_properties(ctx):
     assert np.allclose(a + b, full, rtol=1e-13, atol=1e-300)
     # every primary ray is a closest-hit ray; shadow rays = hits x lights; gathers = hits up to depth 10
     assert st.closest_rays >= W * H * 8 and st.shadow_rays <= st.closest_rays and st.gathers <= st.shadow_rays
+
+
+@pytest.mark.parametrize("name,w,h,spp,photons,rows", [("glass", 1920, 1080, 64, 275000, 400), ("sponza", 3840, 2160, 16, 0, 1200)])
+def test_large_configs_tiles_compose_at_full_size(ctx, name, w, h, spp, photons, rows):
+    """BASELINE configs 3 (glass, 1920x1080x64, deep specular chains) and 5 (sponza stand-in, 3840x2160, 16 of the 1024 spp one GPU
+    of eight takes) at full resolution: many path chunks, the tail kernel and the side streams all in play; the lower part of
+    the frame rendered as its own tile must equal the same rows of the whole frame bit for bit, tallies must add up."""
+    from gi_raytracer_b200 import host
+    if name == "glass" and not have_assets("glass"):
+        pytest.skip("assets not staged")
+    p = scene_path(name)
+    if name == "sponza" and not os.path.exists(os.path.join(os.path.dirname(p), "atrium.obj")):
+        pytest.skip("stand-in mesh not generated (scenes/make_standins.py)")
+    sc = host.load_scene(p)
+    ctx.upload_scene(sc)
+    if photons:
+        ctx.photon_trace(photons, 5, seed=1)
+    else:
+        ctx.photon_upload(np.zeros((0, 9)))
+    ctx.photon_map_build(None)
+    P = render_params(w, h, spp, max_depth=64, seed=1)
+    full, st = ctx.render_tile(P, 0, 0, w, h, 0, spp)
+    low, s_low = ctx.render_tile(P, 0, rows, w, h, 0, spp)
+    assert np.isfinite(full).all() and full.mean() > 0
+    assert bits_equal(low.reshape(h - rows, w, 3), full.reshape(h, w, 3)[rows:].copy())
+    up, s_up = ctx.render_tile(P, 0, 0, w, rows, 0, spp)
+    assert bits_equal(up.reshape(rows, w, 3), full.reshape(h, w, 3)[:rows].copy())
+    for f in ("closest_rays", "shadow_rays", "gathers", "closest_node_tests", "closest_prim_tests", "shadow_node_tests", "shadow_prim_tests"):
+        assert getattr(s_up, f) + getattr(s_low, f) == getattr(st, f), f
