@@ -539,15 +539,18 @@ def test_c2_full_size_frame_properties(ctx):
     assert st.closest_rays >= W * H * 8 and st.shadow_rays <= st.closest_rays and st.gathers <= st.shadow_rays
 
 
-@pytest.mark.parametrize("name,w,h,spp,photons,rows", [("glass", 1920, 1080, 64, 275000, 400), ("sponza", 3840, 2160, 16, 0, 1200)])
+@pytest.mark.parametrize("name,w,h,spp,photons,rows", [("glass", 1920, 1080, 64, 275000, 400), ("foliage", 1920, 1080, 16, 0, 500), ("sponza", 3840, 2160, 16, 0, 1200)])
 def test_large_configs_tiles_compose_at_full_size(ctx, name, w, h, spp, photons, rows):
-    """BASELINE configs 3 (glass, 1920x1080x64, deep specular chains) and 5 (sponza stand-in, 3840x2160, 16 of the 1024 spp one GPU
-    of eight takes) at full resolution: many path chunks, the tail kernel and the side streams all in play; the lower part of
+    """BASELINE configs 3 (glass, 1920x1080x64, deep specular chains), 4 (foliage stand-in: alpha-textured cards, the FULL traversal
+    with its stochastic alpha test; 16 of the 256 spp) and 5 (sponza stand-in, 3840x2160, 16 of the 1024 spp one GPU of eight
+    takes) at full resolution: many path chunks, the tail kernel and the side streams all in play; the lower part of
     the frame rendered as its own tile must equal the same rows of the whole frame bit for bit, tallies must add up."""
     from gi_raytracer_b200 import host
     if name == "glass" and not have_assets("glass"):
         pytest.skip("assets not staged")
     p = scene_path(name)
+    if name == "foliage" and not os.path.exists(os.path.join(os.path.dirname(p), "cards.obj")):
+        pytest.skip("stand-in mesh not generated (scenes/make_standins.py)")
     if name == "sponza" and not os.path.exists(os.path.join(os.path.dirname(p), "atrium.obj")):
         pytest.skip("stand-in mesh not generated (scenes/make_standins.py)")
     sc = host.load_scene(p)
