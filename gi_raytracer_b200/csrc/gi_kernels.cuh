@@ -1537,7 +1537,10 @@ __device__ __forceinline__ bool photon_try(const DScene& S, int count, int max_d
     while (depth < max_depth && !term) {                                                // :633
         double roughness = S.mats[S.prim_mat[cur]].roughness;
         if (roughness < 0.1) {
-            trace_closest<FULL, IMPL>(S, r, seed, path, (uint64_t)(depth + 1), h, wn, wp); n_traces++;   // :640
+            // :640 traces the ray again.  At depth 0 it is the very ray traced above (:620); without stochastic alpha (FULL) the
+            // closest hit is a pure function of the ray, so the first answer stands (the trace is still counted)
+            if (FULL || depth > 0) trace_closest<FULL, IMPL>(S, r, seed, path, (uint64_t)(depth + 1), h, wn, wp);
+            n_traces++;
             if (h.prim == GI_NO_HIT) { term = true; continue; }
             cur = h.prim;
             d3 norm; double tu, tv;
