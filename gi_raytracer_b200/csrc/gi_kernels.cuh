@@ -1228,7 +1228,7 @@ __global__ void __launch_bounds__(GI_WPB * 32, GI_TAIL_MINB) k_tail(DScene S, DG
     DRay r = ray_as_stored(ld3(in.o + 3 * (size_t)i), ld3(in.d + 3 * (size_t)i));
     d3 T = ld3(in.T + 3 * (size_t)i), contrib = ld3(in.contrib + 3 * (size_t)i);
     const uint64_t key = PS.key[path]; const uint32_t sample = PS.sample[path];
-    d3 L = ld3(PS.L + 3 * (size_t)path), Lc = ld3(PS.Lc + 3 * (size_t)path), Ld = ld3(PS.Ld + 3 * (size_t)path);
+    d3 L = ld3(PS.L + 3 * (size_t)path), Lc = ld3(PS.Lc + 3 * (size_t)path);   // Ld: k_tail_direct, from the queued shadow rays
     uint32_t nq = 0;   // gather queries queued by this path
     uint32_t nsh = 0;  // shadow rays queued by this path
     unsigned long long c_closest = 0, c_shadow = 0, c_gather = 0, g_depth = 0, g_cand = 0, g_sel = 0;
@@ -1261,8 +1261,7 @@ __global__ void __launch_bounds__(GI_WPB * 32, GI_TAIL_MINB) k_tail(DScene S, DG
             Tn = T * f;
         }
         // direct light (k_direct)
-        if (S.n_lights) {
-            d3 li = mk3(0, 0, 0);
+        {
             for (uint32_t l = 0; l < S.n_lights; l++) {
                 const gi_light& light = S.lights[l];
                 d3 sp = hp + hn * GI_D_SHADOW_BIAS;
@@ -1304,7 +1303,7 @@ __global__ void __launch_bounds__(GI_WPB * 32, GI_TAIL_MINB) k_tail(DScene S, DG
         r = make_ray(hp + hn * offset, refDir);
     }
     if (lane == 0) {
-        st3(PS.L + 3 * (size_t)path, L); st3(PS.Lc + 3 * (size_t)path, Lc); st3(PS.Ld + 3 * (size_t)path, Ld);
+        st3(PS.L + 3 * (size_t)path, L); st3(PS.Lc + 3 * (size_t)path, Lc);
         if (Q.smax) Q.sh_count[i] = nsh < Q.smax ? nsh : Q.smax;
         if (have_map && Q.qmax) {
             Q.count[i] = nq < Q.qmax ? nq : Q.qmax;
