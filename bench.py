@@ -270,6 +270,15 @@ def main():
     rays_local = sum(int(s.closest_rays) + int(s.shadow_rays) for s in stats)
     launches_local = sum(int(s.kernel_launches) for s in stats)
 
+    # -- per-family kernel durations for the roofline: the same frame on ONE stream, so that every kernel has the GPU to itself while
+    #    its events are taken (inside the overlapped frame above the families' event times cover each other)
+    ctx.configure("overlap_threshold", 0)
+    ctx.synchronize()
+    for _ in range(2):
+        serial = ctx.render_tile_dev(P, 0, 0, W, H, s0, s1, accums[0].data_ptr())
+    ctx.synchronize()
+    ctx.configure("overlap_threshold", 1 << 20)
+
     # -- isolated gather: queries = primary hits (s = 0) of the frame, resident in HBM
     o, d, _ = ctx.camera_rays(W, H, 0, 0, W, H, 0, 1)
     prim, hit, nrm, _ = ctx.trace_closest(o, d)
@@ -332,11 +341,11 @@ def main():
         g = lambda f: int(getattr(last, f))   # noqa: E731
         # the wavefront kernels' share of the work = totals minus what the tail kernel (one warp per path, deep bounces) did
         fam = {
-            "bounce": (float(last.trace_ms), bytes_closest(g("closest_rays") - g("tail_closest_rays"), g("closest_node_tests") - g("tail_closest_node_tests"),
+            "bounce": (float(serial.trace_ms), bytes_closest(g("closest_rays") - g("tail_closest_rays"), g("closest_node_tests") - g("tail_closest_node_tests"),
                                                            g("closest_prim_tests") - g("tail_closest_prim_tests"))),
-            "direct": (float(last.shadow_ms), bytes_shadow(g("shadow_rays") - g("tail_shadow_rays"), g("shadow_node_tests") - g("tail_shadow_node_tests"),
+            "direct": (float(serial.shadow_ms), bytes_shadow(g("shadow_rays") - g("tail_shadow_rays"), g("shadow_node_tests") - g("tail_shadow_node_tests"),
                                                            g("shadow_prim_tests") - g("tail_shadow_prim_tests"))),
-            "gather": (float(last.gather_ms), bytes_gather(g("gathers") - g("tail_gathers"), g("gather_leaf_depth") - g("tail_gather_leaf_depth"),
+            "gather": (float(serial.gather_ms), bytes_gather(g("gathers") - g("tail_gathers"), g("gather_leaf_depth") - g("tail_gather_leaf_depth"),
                                                            g("gather_candidates") - g("tail_gather_candidates"), g("gather_selected") - g("tail_gather_selected"))),
         }
         tail_bytes = (bytes_closest(g("tail_closest_rays"), g("tail_closest_node_tests"), g("tail_closest_prim_tests"))
@@ -360,6 +369,9 @@ def main():
                     "algorithmic_bytes_per_step": dom_bytes, "kernel_ms_per_step": dom_ms, "launches_per_step": n_launch[dom],
                     "families": {k: {"ms_per_step": v[0], "algorithmic_GBps": (v[1] / (v[0] * 1e-3) / 1e9 if v[0] > 0 else 0.0), "frac": (v[1] / (v[0] * 1e-3) / 1e9 / peak if v[0] > 0 else 0.0)}
                                  for k, v in fam.items()},
+                    "timing": "families: CUDA events around each kernel family in one extra frame rendered on ONE stream right after the timed region (inside the timed, overlapped frames the families run beside each other and their event windows cover one another); frame: the timed region itself",
+                    "families_overlapped_ms_per_step": {"bounce": float(last.trace_ms), "direct": float(last.shadow_ms), "gather": float(last.gather_ms)},
+                    "frame_serial_ms": float(serial.total_ms),
                     "tail": {"ms_per_step": float(last.shade_ms), "algorithmic_GBps": tail_bytes / (float(last.shade_ms) * 1e-3) / 1e9 if last.shade_ms > 0 else 0.0,
                              "rays": g("tail_closest_rays") + g("tail_shadow_rays"), "gathers": g("tail_gathers")},
                     "bin_ms_per_step": float(last.bin_ms),
@@ -381,7 +393,7 @@ def main():
             "config": {"workload": "C2 scenes/caustics 1024x1024, 8 spp per GPU (sample-index split), MAX_DEPTH 64, 1M caustic photons, k=32 gather",
                        "scene": "scenes/caustics/caustics.scn (reference assets, dragon.obj not mounted)", "width": W, "height": H, "spp_per_gpu": SPP,
                        "photons_stored": pm_info["n_kept"], "photon_map_nodes": pm_info["n_nodes"], "l2": "working set per step (path state ~2.9 GB) exceeds the 126 MB L2",
-                       "streams": "k_direct and the gather pipeline of a bounce depth with < 2^20 hits run on side streams behind the next depth's bounce kernel: per-family ms overlap and do not add up to the frame",
+                       "streams": "k_direct and the gather pipeline run on side streams (k_direct beside the gather; both behind the next depth's bounce kernel when a depth has < 2^20 hits); roofline.families are timed in one extra single-stream frame",
                        "parallelism": f"sample-split x{world}", "photon_phase_s": photon_wall, "photon_slab_bytes": slab_bytes,
                        "rays_per_step": rays_all / K, "closest_rays_per_step": int(last.closest_rays), "shadow_rays_per_step": int(last.shadow_rays), "gathers_per_step": int(last.gathers)},
             "gather": {"metric": "photon-gather Mqueries/s", "value": nq_all / (gather_ms * 1e-3) / 1e6, "unit": "Mqueries/s", "queries": nq_all,

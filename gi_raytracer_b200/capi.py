@@ -22,7 +22,7 @@ API_SYMBOLS = [
     "gi_photon_map_build", "gi_photon_map_info", "gi_photon_map_download", "gi_photon_map_slab_size",
     "gi_photon_map_slab_ptr", "gi_photon_map_adopt_slab", "gi_photon_map_reserve_slab", "gi_photon_gather",
     "gi_photon_gather_dev", "gi_render_tile", "gi_render_tile_dev", "gi_resolve", "gi_resolve_dev", "gi_last_kernel_ms",
-    "gi_last_work", "gi_scene_info", "gi_render_adaptive", "gi_render_adaptive_dev", "gi_fog_density", "gi_raymarch", "gi_octree_build", "gi_octree_download", "gi_cancel", "gi_render_image",
+    "gi_last_work", "gi_scene_info", "gi_render_adaptive", "gi_render_adaptive_dev", "gi_fog_density", "gi_raymarch", "gi_octree_build", "gi_octree_download", "gi_cancel", "gi_render_image", "gi_configure",
 ]
 
 _LIB = None
@@ -101,6 +101,7 @@ def load_library():
                                    C.POINTER(C.c_double), C.POINTER(C.c_double)]
     L.gih_render_progressive.argtypes = [C.c_char_p, i32, i32, i32, i32, i32, i32, u64, i32, i32, vp, C.POINTER(i32), C.POINTER(C.c_double)]
     L.gi_cancel.argtypes = [vp, i32]
+    L.gi_configure.argtypes = [vp, C.c_char_p, C.c_longlong]
     L.gi_render_image.argtypes = [vp, C.POINTER(GiRenderParams), i32, i32, i32, i32, i32, i32, vp, vp, C.POINTER(GiStats)]
     L.gih_png_decode.argtypes = [C.c_char_p, C.POINTER(i32), C.POINTER(i32), C.POINTER(i32), vp, sz]
     L.gih_png_encode.argtypes = [C.c_char_p, i32, i32, vp]
@@ -229,6 +230,10 @@ class Context:
     def cancel(self, raise_=True):
         """gi_cancel: callable from any thread while another thread is inside a render / photon call on this context."""
         self._ck(self.L.gi_cancel(self.h, 1 if raise_ else 0))
+
+    def configure(self, key, value):
+        """gi_configure: a scheduling knob (overlap_threshold, tail_threshold, bin_threshold, bounce_mode, trace_mode, tail_mode)."""
+        self._ck(self.L.gi_configure(self.h, key.encode(), int(value)))
 
     def octree_build(self, prim_type, prim_geom, prim_bbox, root_box):
         """Octree::rebuild / Node::partition on the device -> (dict of gi_scene_desc node arrays, device ms)."""

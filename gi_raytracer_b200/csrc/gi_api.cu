@@ -305,6 +305,21 @@ extern "C" void gi_destroy(gi_ctx* ctx)
     delete ctx;
 }
 
+// run-time forms of the GI_* environment knobs read at gi_create
+extern "C" int gi_configure(gi_ctx* ctx, const char* key, long long value)
+{
+    if (!ctx || !key) return GI_ERR_INVALID;
+    const std::string k = key;
+    if (k == "overlap_threshold") ctx->overlap_threshold = (uint32_t)value;
+    else if (k == "tail_threshold") ctx->tail_threshold = (uint32_t)value;
+    else if (k == "bin_threshold") ctx->bin_threshold = (uint32_t)value;
+    else if (k == "bounce_mode") ctx->bounce_mode = (int)value;
+    else if (k == "trace_mode") ctx->trace_mode = (int)value;
+    else if (k == "tail_mode") ctx->tail_mode = (int)value;
+    else return fail(ctx, GI_ERR_INVALID, "gi_configure: unknown key " + k);
+    return GI_OK;
+}
+
 extern "C" int gi_cancel(gi_ctx* ctx, int raise)
 {
     if (!ctx) return GI_ERR_INVALID;

@@ -213,6 +213,14 @@ int gi_trace_any_dev(gi_ctx* ctx, size_t n, const double* org, const double* dir
  *      render / photon call returns GI_ERR_CANCELLED at once — until gi_cancel(ctx, 0). ------------------------------ */
 int gi_cancel(gi_ctx* ctx, int raise);
 
+/* ---- scheduling knobs (new; no counterpart in the reference).  Results never depend on them (tested bit for bit).
+ *      "overlap_threshold": k_direct / the gather pipeline of a bounce depth with fewer hits than this run on side streams
+ *                           behind the next depth's bounce kernel (default 2^20, 0 = one stream: what a profiler or a
+ *                           per-kernel timing wants);
+ *      "tail_threshold" (32768), "bin_threshold" (65536), "bounce_mode" (0 auto / 1 thread per ray / 2 persistent),
+ *      "trace_mode" (0 / 1 = warp per ray in the batch kernels), "tail_mode" (0 queued / 1 inline gathers). ------------- */
+int gi_configure(gi_ctx* ctx, const char* key, long long value);
+
 /* ---- atmosphere.  The fog itself acts inside gi_render_* / gi_photon_trace (RayTracer::radiance
  *      raytracer.h:209-228, ::visible :308-316, ::tracePhotons :658-675) whenever the uploaded scene has n_fog > 0; the
  *      batch forms below expose its pieces for comparison with the reference.
