@@ -22,7 +22,7 @@ API_SYMBOLS = [
     "gi_photon_map_build", "gi_photon_map_info", "gi_photon_map_download", "gi_photon_map_slab_size",
     "gi_photon_map_slab_ptr", "gi_photon_map_adopt_slab", "gi_photon_map_reserve_slab", "gi_photon_gather",
     "gi_photon_gather_dev", "gi_render_tile", "gi_render_tile_dev", "gi_resolve", "gi_resolve_dev", "gi_last_kernel_ms",
-    "gi_last_work", "gi_scene_info", "gi_render_adaptive", "gi_render_adaptive_dev", "gi_fog_density", "gi_raymarch", "gi_octree_build", "gi_octree_download", "gi_cancel", "gi_render_image", "gi_configure",
+    "gi_last_work", "gi_scene_info", "gi_render_adaptive", "gi_render_adaptive_dev", "gi_fog_density", "gi_raymarch", "gi_octree_build", "gi_octree_download", "gi_cancel", "gi_render_image", "gi_configure", "gi_material_eval",
 ]
 
 _LIB = None
@@ -62,6 +62,7 @@ def load_library():
     for f in (L.gi_trace_any, L.gi_trace_any_dev):
         f.argtypes = [vp, sz, vp, vp, vp, u64, vp]
     L.gi_fog_density.argtypes = [vp, sz, vp, vp, vp]
+    L.gi_material_eval.argtypes = [vp, sz, vp, vp, vp, vp, vp]
     L.gi_raymarch.argtypes = [vp, sz, vp, vp, vp, u64, i32, vp, vp, vp, vp, vp]
     L.gi_octree_build.argtypes = [vp, u32, vp, vp, vp, vp, C.POINTER(u32), C.POINTER(u32), C.POINTER(C.c_double)]
     L.gi_octree_download.argtypes = [vp, vp, vp, vp, vp, vp, vp]
@@ -208,6 +209,15 @@ class Context:
         vis = np.empty(n, dtype=np.uint8)
         self._ck(self.L.gi_trace_any(self.h, n, _p(org), _p(d), _p(maxt2), alpha_seed, _p(vis)))
         return vis
+
+    def material_eval(self, prim, uv):
+        """Material::diffuse->get(uv), emissive->get(uv), Material::getAlpha(uv) for the materials of the given primitives."""
+        prim = np.ascontiguousarray(prim, dtype=np.uint32).ravel()
+        uv = _f64(uv, 2)
+        n = prim.size
+        dif, em, alpha = np.empty((n, 3)), np.empty((n, 3)), np.empty(n)
+        self._ck(self.L.gi_material_eval(self.h, n, _p(prim), _p(uv), _p(dif), _p(em), _p(alpha)))
+        return dif, em, alpha
 
     def fog_density(self, pos):
         """Octree::atmosphereDensity at points -> (density incl. the step-size factor, colour of the last containing volume)."""

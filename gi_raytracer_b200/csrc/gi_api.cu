@@ -509,6 +509,24 @@ extern "C" int gi_scene_info(gi_ctx* ctx, uint32_t out[4])
     return GI_OK;
 }
 
+// ---- materials, batch form (host pointers) ------------------------------------------------------------------------------------------
+extern "C" int gi_material_eval(gi_ctx* ctx, size_t n, const uint32_t* prim, const double* uv, double* diffuse, double* emissive, double* alpha)
+{
+    if (!ctx || (n && (!prim || !uv || !diffuse || !emissive || !alpha))) return GI_ERR_INVALID;
+    if (!ctx->has_scene) return fail(ctx, GI_ERR_NO_SCENE, "gi_material_eval needs gi_scene_upload");
+    if (!n) return GI_OK;
+    CK(cudaSetDevice(ctx->device));
+    CK(ctx->w0.reserve(n * 4)); CK(ctx->w1.reserve(n * 16)); CK(ctx->w2.reserve(n * 24)); CK(ctx->w3.reserve(n * 24)); CK(ctx->w4.reserve(n * 8));
+    CK(cudaMemcpyAsync(ctx->w0.p, prim, n * 4, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->w1.p, uv, n * 16, cudaMemcpyHostToDevice, ctx->stream));
+    k_material_eval<<<grid_for(n, 256), 256, 0, ctx->stream>>>(ctx->S, n, ctx->w0.as<uint32_t>(), ctx->w1.as<double>(), ctx->w2.as<double>(), ctx->w3.as<double>(), ctx->w4.as<double>());
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(diffuse, ctx->w2.p, n * 24, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaMemcpyAsync(emissive, ctx->w3.p, n * 24, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaMemcpyAsync(alpha, ctx->w4.p, n * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    return gi_synchronize(ctx);
+}
+
 // ---- atmosphere, batch forms (host pointers) -------------------------------------------------------------------------------------------
 extern "C" int gi_fog_density(gi_ctx* ctx, size_t n, const double* pos, double* dens, double* col)
 {

@@ -49,6 +49,21 @@ __global__ void k_raymarch(DScene S, size_t n, const double* __restrict__ org, c
     st3(pos + 3 * i, h); st3(col + 3 * i, c);
 }
 
+// ---- materials, batch form: Material::diffuse->get(uv), emissive->get(uv), Material::getAlpha(uv) (material.h:18-26, 39-45, 63-81, 90-93)
+// for the material of primitive prim[i] at uv[i] — what radiance() reads at raytracer.h:200 and the alpha test at :455
+__global__ void k_material_eval(DScene S, size_t n, const uint32_t* __restrict__ prim, const double* __restrict__ uv, double* __restrict__ dif, double* __restrict__ em, double* __restrict__ alpha)
+{
+    size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint32_t p = prim[i];
+    if (p >= S.n_prims) { st3(dif + 3 * i, mk3(0, 0, 0)); st3(em + 3 * i, mk3(0, 0, 0)); alpha[i] = 0; return; }
+    const gi_material& m = S.mats[S.prim_mat[p]];
+    const double u = uv[2 * i], v = uv[2 * i + 1];
+    st3(dif + 3 * i, tex_get(S, m.diffuse_tex, u, v));
+    st3(em + 3 * i, tex_get(S, m.emissive_tex, u, v));
+    alpha[i] = m.opacity * tex_alpha(S, m.diffuse_tex, u, v);
+}
+
 // ---- K1: camera rays (raytracer.h:74-78, 112-129) ------------------------------------------------------------------------------
 struct DFrame { int w, h, x0, y0, tw, th; double halfW, halfH; d3 center, right, up, pos; DHEnum he; };
 

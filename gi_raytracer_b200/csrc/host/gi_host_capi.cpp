@@ -32,8 +32,10 @@ int gih_scene_load(const char* path, int quiet, gih_scene** out)
     s->rt = new RayTracer(camera);
     s->octree = new Octree();
     std::string spath = path;
-    const bool api_scene = spath.size() > 4 && spath.compare(spath.size() - 4, 4, "#api") == 0;   // "<file>.scn#api": add the API-built primitives
-    if (api_scene) spath.resize(spath.size() - 4);
+    int api_variant = 0;   // "<file>.scn#api" / "#api2": add the API-built primitives of api_scene.inc
+    if (spath.size() > 4 && spath.compare(spath.size() - 4, 4, "#api") == 0) { api_variant = 1; spath.resize(spath.size() - 4); }
+    else if (spath.size() > 5 && spath.compare(spath.size() - 5, 5, "#api2") == 0) { api_variant = 2; spath.resize(spath.size() - 5); }
+    const bool api_scene = api_variant != 0;
     loadScene(s->octree, *s->rt, spath.c_str());
     if (api_scene) {
         Octree* o = s->octree;

@@ -206,6 +206,11 @@ int gi_trace_any(gi_ctx* ctx, size_t n, const double* org, const double* dir, co
 int gi_trace_any_dev(gi_ctx* ctx, size_t n, const double* org, const double* dir, const double* maxt2, uint64_t alpha_seed,
                      uint8_t* vis);
 
+/* ---- materials: texture::get / checkerboard::get / imageTexture::get + getAlpha and Material::getAlpha (material.h:18-26,
+ *      39-45, 63-81, 90-93) for the material of primitive prim[i] at uv[i] — the values RayTracer::radiance reads at
+ *      raytracer.h:200 / :269 and the alpha test at :455 / :297.  diffuse / emissive [n][3], alpha [n]; host pointers. ------ */
+int gi_material_eval(gi_ctx* ctx, size_t n, const uint32_t* prim, const double* uv, double* diffuse, double* emissive, double* alpha);
+
 /* ---- cancellation: RayTracer::stop / start and the `_running` poll of the row loop (raytracer.h:98, 723-725; viewer.h:29-34).
  *      gi_cancel(ctx, 1) may be called from ANY thread while another thread is inside gi_render_* / gi_photon_trace on the
  *      same context; the call in flight returns GI_ERR_CANCELLED at its next launch boundary (between bounce depths, path

@@ -53,6 +53,20 @@ double go_rand(uint64_t seed, uint64_t path, uint64_t depth, uint64_t site)
     uint64_t h = mix64(seed ^ mix64(path ^ mix64(depth ^ mix64(site))));
     return (double)(h >> 11) * (1.0 / 9007199254740992.0);
 }
+/* Reference-PRNG replay (checker of the checker): the reference's drand() is a thread_local xorshift64* seeded with
+ * time(0) (util.h:52-80).  gi_ref runs with time() interposed and OMP_NUM_THREADS=1, so its stream is known; when g_xs is
+ * set, the alpha cut-out draws of trace()/visible() below are taken from THAT stream in the reference's own order —
+ * one draw at the debug guard of trace() (raytracer.h:438) and one per geometric hit (`drand() < getAlpha(uv) || IOR != 1`,
+ * raytracer.h:455 and :297: drand() is evaluated first, always) — which makes the ids of an alpha-textured scene
+ * bit-comparable with the reference.  Only go_trace_closest_replay / go_trace_any_replay set it (sequential loops). */
+static _Thread_local uint64_t* g_xs = NULL;
+static inline double xs_next(uint64_t* st)
+{
+    uint64_t x = *st;
+    x ^= x >> 12; x ^= x << 25; x ^= x >> 27;
+    *st = x;
+    return (double)(x * 2685821657736338717ull) / 18446744073709551615.0;   /* / (double)ULLONG_MAX == 2^64 */
+}
 /* sites */
 #define SITE_LIGHT_U 0ull
 #define SITE_LIGHT_V 1ull
@@ -467,12 +481,23 @@ static double tex_alpha(const gi_scene_desc* sc, uint32_t id, const double* uv)
 /* Material::getAlpha (material.h:90-93) */
 static inline double mat_alpha(const gi_scene_desc* sc, const gi_material* m, const double* uv) { return m->opacity * tex_alpha(sc, m->diffuse_tex, uv); }
 
+void go_material_eval(const gi_scene_desc* sc, size_t n, const uint32_t* prim, const double* uv, double* diffuse, double* emissive, double* alpha)
+{
+    for (size_t i = 0; i < n; i++) {
+        const gi_material* m = &sc->mats[sc->prim_mat[prim[i]]];
+        st3(diffuse + 3 * i, tex_get(sc, m->diffuse_tex, uv + 2 * i));
+        st3(emissive + 3 * i, tex_get(sc, m->emissive_tex, uv + 2 * i));
+        alpha[i] = mat_alpha(sc, m, uv + 2 * i);
+    }
+}
+
 /* alpha cut-out decision `drand() < getAlpha(uv) || IOR != 1` (raytracer.h:455, :297).  The draw is keyed by the
  * (leaf node, primitive) occurrence, so duplicates of a primitive in several leaves draw independently like the
  * reference, while the outcome does not depend on visiting order. */
 static inline int alpha_pass(const gi_scene_desc* sc, uint32_t prim, uint32_t node, const double* uv, uint64_t seed, uint64_t path, uint64_t depth, uint64_t site)
 {
     const gi_material* m = &sc->mats[sc->prim_mat[prim]];
+    if (g_xs) { double r = xs_next(g_xs); return r < mat_alpha(sc, m, uv) || m->ior != 1; }   /* replay: the reference's stream and order */
     if (m->ior != 1) return 1;
     double a = mat_alpha(sc, m, uv);
     if (a >= 1.0) return 1; /* drand() < 1 holds for every draw of this generator ([0,1)) */
@@ -511,6 +536,7 @@ static void trace_one(const gi_scene_desc* sc, const ray_t* r, uint64_t seed, ui
 {
     L->n = 0;
     if (sc->n_nodes) enum_sorted(sc, 0, r, 0, INFINITY, L);
+    if (g_xs) (void)xs_next(g_xs);   /* replay: `drand() < .5 && nodes.size() > 500` (raytracer.h:438) always draws */
     v3 hit = V(0, 0, 0), norm = V(0, 0, 0); double uv[2] = { 0, 0 };
     out->hit = 0; out->prim = GI_NO_HIT; out->p = V(0, 0, 0); out->n = V(0, 0, 0); out->uv[0] = out->uv[1] = 0;
     int term = 0;
@@ -645,6 +671,31 @@ void go_trace_any(const gi_scene_desc* sc, size_t n, const double* org, const do
         ray_t r = ray_as_stored(ld3(org + 3 * i), ld3(dir + 3 * i));
         vis[i] = (uint8_t)visible_one(sc, &r, maxt2[i], alpha_seed, (uint64_t)i, 0, 0, NULL, NULL);
     }
+}
+/* sequential forms on the reference's own PRNG stream (see g_xs): *state = the interposed time() value, updated */
+void go_trace_closest_replay(const gi_scene_desc* sc, size_t n, const double* org, const double* dir, uint64_t* state, uint32_t* prim, double* hit, double* normal, double* uv)
+{
+    leaflist_t L = { 0, 0, 0 };
+    g_xs = state;
+    for (size_t i = 0; i < n; i++) {
+        ray_t r = ray_as_stored(ld3(org + 3 * i), ld3(dir + 3 * i));
+        closest_t c; trace_one(sc, &r, 0, (uint64_t)i, 0, &L, &c);
+        prim[i] = c.prim;
+        if (hit) st3(hit + 3 * i, c.p);
+        if (normal) st3(normal + 3 * i, c.n);
+        if (uv) { uv[2 * i] = c.uv[0]; uv[2 * i + 1] = c.uv[1]; }
+    }
+    g_xs = NULL;
+    free(L.v);
+}
+void go_trace_any_replay(const gi_scene_desc* sc, size_t n, const double* org, const double* dir, const double* maxt2, uint64_t* state, uint8_t* vis)
+{
+    g_xs = state;
+    for (size_t i = 0; i < n; i++) {
+        ray_t r = ray_as_stored(ld3(org + 3 * i), ld3(dir + 3 * i));
+        vis[i] = (uint8_t)visible_one(sc, &r, maxt2[i], 0, (uint64_t)i, 0, 0, NULL, NULL);
+    }
+    g_xs = NULL;
 }
 void go_trace_any_cot(const gi_scene_desc* sc, size_t n, const double* org, const double* dir, const double* maxt2, uint64_t alpha_seed, uint8_t* vis, uint32_t* n_node_tests, uint32_t* n_prim_tests)
 {

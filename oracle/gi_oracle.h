@@ -54,6 +54,14 @@ void go_trace_any(const gi_scene_desc* sc, size_t n, const double* org, const do
 /* canonical ordered traversal with early termination: same answers as go_trace_closest plus work counters */
 void go_trace_closest_cot(const gi_scene_desc* sc, size_t n, const double* org, const double* dir, uint64_t alpha_seed,
                           uint32_t* prim, double* hit, uint32_t* n_node_tests, uint32_t* n_prim_tests);
+/* the same two functions on the reference's own PRNG stream (thread_local xorshift64*, util.h:52-80), sequential:
+ * *state = the value gi_ref's interposed time() returned; makes alpha-textured scenes bit-comparable with gi_ref run with
+ * OMP_NUM_THREADS=1 (one draw per trace() call + one per geometric hit, in the reference's order) */
+void go_trace_closest_replay(const gi_scene_desc* sc, size_t n, const double* org, const double* dir, uint64_t* state, uint32_t* prim,
+                             double* hit, double* normal, double* uv);
+void go_trace_any_replay(const gi_scene_desc* sc, size_t n, const double* org, const double* dir, const double* maxt2, uint64_t* state, uint8_t* vis);
+/* Material::diffuse->get(uv) / emissive->get(uv) / Material::getAlpha(uv) (material.h:18-26, 39-45, 63-81, 90-93) */
+void go_material_eval(const gi_scene_desc* sc, size_t n, const uint32_t* prim, const double* uv, double* diffuse, double* emissive, double* alpha);
 void go_trace_any_cot(const gi_scene_desc* sc, size_t n, const double* org, const double* dir, const double* maxt2,
                       uint64_t alpha_seed, uint8_t* vis, uint32_t* n_node_tests, uint32_t* n_prim_tests);
 

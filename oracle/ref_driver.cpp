@@ -281,7 +281,7 @@ int main(int argc, char** argv)
 {
     if (argc < 3) {
         fprintf(stderr, "usage: gi_ref <scene.scn> <outdir> [--w W --h H --s0 A --s1 B --max-depth D --min-depth M --photons P --samples N --x0 --y0 --x1 --y1 --repeat R] cmd...\n"
-                        "cmds: scene halton samplers primary fog shadow photons gather radiance run time-frame time-gather bench-frame\n");
+                        "cmds: scene halton samplers primary textures fog shadow photons gather gather-knn radiance run time-frame time-gather bench-frame\n");
         return 1;
     }
     const char* scn = argv[1];
@@ -311,6 +311,7 @@ int main(int argc, char** argv)
     loadScene(scene, rt, scn);                      // main.cpp:38
     if (api_scene) {   // primitives that have no .scn keyword, added through the reference's C++ API
         Octree* o = scene;
+        const int api_variant = api_scene;
 #define V3(x, y, z) glm::dvec3(x, y, z)
 #include "../gi_raytracer_b200/csrc/host/api_scene.inc"
 #undef V3
@@ -337,16 +338,39 @@ int main(int argc, char** argv)
     // -- primary rays + closest hit ------------------------------------------------------------------
     std::vector<double> hit_pos, hit_nrm, hit_uv, ray_o, ray_d;
     std::vector<uint32_t> hit_id, ray_idx;
-    if (has("primary") || has("shadow") || has("gather") || has("time-gather") || has("fog")) {
-        for (int s = s0; s < s1; s++) for (int y = y0; y < y1; y++) for (int x = x0; x < x1; x++) {
-            int idx; Ray ray = camera_ray(rt, fr, sampler, he, w, h, x, y, s, idx);
-            glm::dvec3 p(0), n(0); glm::dvec2 uv(0); Entity* cur = nullptr;
-            bool ok = rt.trace(ray, p, n, uv, cur);
-            push3(ray_o, ray.origin); push3(ray_d, ray.dir); ray_idx.push_back((uint32_t)idx);
-            hit_id.push_back(ok ? g_eid.at(cur) : 0xFFFFFFFFu);
-            if (!ok) { p = glm::dvec3(0); n = glm::dvec3(0); uv = glm::dvec2(0); }
-            push3(hit_pos, p); push3(hit_nrm, n); push2(hit_uv, uv);
+    std::vector<double> tex_dif, tex_em, tex_alpha;
+    if (has("primary") || has("shadow") || has("gather") || has("gather-knn") || has("time-gather") || has("fog") || has("textures")) {
+        // one slot per (s, y, x) in that order; rows are spread over the OpenMP threads (trace() is const and is called
+        // concurrently by the reference itself, raytracer.h:93-160).  With OMP_NUM_THREADS=1 the rays are traced in slot order
+        // on the main thread, so the reference's thread_local xorshift stream (util.h:52-80) is consumed in that order.
+        const int tw = x1 - x0, th = y1 - y0;
+        const size_t nray = (size_t)(s1 - s0) * tw * th;
+        hit_pos.assign(nray * 3, 0); hit_nrm.assign(nray * 3, 0); hit_uv.assign(nray * 2, 0); ray_o.assign(nray * 3, 0); ray_d.assign(nray * 3, 0);
+        hit_id.assign(nray, 0xFFFFFFFFu); ray_idx.assign(nray, 0);
+        if (has("textures")) { tex_dif.assign(nray * 3, 0); tex_em.assign(nray * 3, 0); tex_alpha.assign(nray, 0); }
+        const bool want_tex = has("textures");
+#pragma omp parallel for schedule(dynamic, 1)
+        for (long row = 0; row < (long)(s1 - s0) * th; row++) {
+            const int s = s0 + (int)(row / th), y = y0 + (int)(row % th);
+            for (int x = x0; x < x1; x++) {
+                const size_t i = (size_t)row * tw + (x - x0);
+                int idx; Ray ray = camera_ray(rt, fr, sampler, he, w, h, x, y, s, idx);
+                glm::dvec3 p(0), n(0); glm::dvec2 uv(0); Entity* cur = nullptr;
+                bool ok = rt.trace(ray, p, n, uv, cur);
+                for (int k = 0; k < 3; k++) { ray_o[3 * i + k] = ray.origin[k]; ray_d[3 * i + k] = ray.dir[k]; }
+                ray_idx[i] = (uint32_t)idx;
+                hit_id[i] = ok ? g_eid.at(cur) : 0xFFFFFFFFu;
+                if (!ok) { p = glm::dvec3(0); n = glm::dvec3(0); uv = glm::dvec2(0); }
+                for (int k = 0; k < 3; k++) { hit_pos[3 * i + k] = p[k]; hit_nrm[3 * i + k] = n[k]; }
+                hit_uv[2 * i] = uv.x; hit_uv[2 * i + 1] = uv.y;
+                if (want_tex && ok) {   // material.h:18-26, 39-45, 63-81, 90-93 at the hit's uv (what radiance() reads at raytracer.h:200)
+                    glm::dvec3 dc = cur->material.diffuse->get(uv), ec = cur->material.emissive->get(uv);
+                    for (int k = 0; k < 3; k++) { tex_dif[3 * i + k] = dc[k]; tex_em[3 * i + k] = ec[k]; }
+                    tex_alpha[i] = cur->material.getAlpha(uv);
+                }
+            }
         }
+        if (want_tex) { dump("tex_dif.f64", tex_dif); dump("tex_em.f64", tex_em); dump("tex_alpha.f64", tex_alpha); }
         if (has("primary")) {
             dump("ray_o.f64", ray_o); dump("ray_d.f64", ray_d); dump("ray_idx.u32", ray_idx);
             dump("hit_id.u32", hit_id); dump("hit_pos.f64", hit_pos); dump("hit_nrm.f64", hit_nrm); dump("hit_uv.f64", hit_uv);
@@ -386,19 +410,27 @@ int main(int argc, char** argv)
 
     // -- shadow rays from the primary hits toward Halton-chosen light points ------------------------
     if (has("shadow")) {
-        std::vector<double> so, sd, smt; std::vector<uint8_t> vis;
-        for (size_t i = 0; i < hit_id.size(); i++) {
+        // one slot per (hit, light), hits in ray order; misses are skipped (slot index by prefix count)
+        std::vector<size_t> hslot(hit_id.size() + 1, 0);
+        for (size_t i = 0; i < hit_id.size(); i++) hslot[i + 1] = hslot[i] + (hit_id[i] == 0xFFFFFFFFu ? 0 : scene->lights.size());
+        const size_t nsh = hslot.back();
+        std::vector<double> so(nsh * 3), sd(nsh * 3), smt(nsh); std::vector<uint8_t> vis(nsh);
+#pragma omp parallel for schedule(dynamic, 1024)
+        for (long i = 0; i < (long)hit_id.size(); i++) {
             if (hit_id[i] == 0xFFFFFFFFu) continue;
             glm::dvec3 p(hit_pos[3 * i], hit_pos[3 * i + 1], hit_pos[3 * i + 2]), n(hit_nrm[3 * i], hit_nrm[3 * i + 1], hit_nrm[3 * i + 2]);
             glm::dvec3 rd(ray_d[3 * i], ray_d[3 * i + 1], ray_d[3 * i + 2]);
             if (glm::dot(n, rd) > 0) n *= -1.0;                                   // raytracer.h:325-329
+            size_t k = hslot[i];
             for (Light* light : scene->lights) {
                 double u = sampler.sample(2, ray_idx[i]), v = sampler.sample(3, ray_idx[i]);
                 glm::dvec3 lightDir = light->getPoint(u, v) - (p + SHADOW_BIAS * n);   // raytracer.h:233
                 double maxt = vecLengthSquared(lightDir);
                 Ray sr(p + SHADOW_BIAS * n, lightDir);                              // raytracer.h:241
                 bool v_ = rt.visible(sr, maxt);
-                push3(so, sr.origin); push3(sd, sr.dir); smt.push_back(maxt); vis.push_back(v_ ? 1 : 0);
+                for (int c = 0; c < 3; c++) { so[3 * k + c] = sr.origin[c]; sd[3 * k + c] = sr.dir[c]; }
+                smt[k] = maxt; vis[k] = v_ ? 1 : 0;
+                k++;
             }
         }
         dump("sh_o.f64", so); dump("sh_d.f64", sd); dump("sh_maxt2.f64", smt); dump("sh_vis.u8", vis);
@@ -407,7 +439,7 @@ int main(int argc, char** argv)
 
     // -- photons ----------------------------------------------------------------------------------------
     double photon_s = 0;
-    if (has("photons") || has("gather") || has("run") || has("time-frame") || has("time-gather") || has("radiance") || has("bench-frame")) {
+    if (has("photons") || has("gather") || has("gather-knn") || has("run") || has("time-frame") || has("time-gather") || has("radiance") || has("bench-frame")) {
         counters_collect(); counters_reset();
         auto t0 = std::chrono::high_resolution_clock::now();
         rt.tracePhotons(5, rt.photons, sampler, he);                                 // raytracer.h:65
@@ -440,7 +472,7 @@ int main(int argc, char** argv)
             meta << "pm_nodes=" << leaf.size() << "\n";
         }
         // -- gather on primary-hit queries ----------------------------------------------------------------
-        if (has("gather") || has("time-gather")) {
+        if (has("gather") || has("gather-knn") || has("time-gather")) {
             std::vector<double> qpos, qdir;
             for (size_t i = 0; i < hit_id.size(); i++) {
                 if (hit_id[i] == 0xFFFFFFFFu) continue;
@@ -466,6 +498,23 @@ int main(int argc, char** argv)
                 }
                 dump("q_pos.f64", qpos); dump("q_dir.f64", qdir); dump("q_est.f64", est);
                 dump("q_cand_off.u32", cand_off); dump("q_cand.u32", cand); dump("q_knn.u32", knn);
+                meta << "gather_queries=" << nq << "\n";
+            }
+            if (has("gather-knn")) {   // like `gather` without the candidate lists (full-size frames: ~100 candidates per query), all threads
+                std::vector<double> est(nq * 3); std::vector<uint32_t> ncand(nq), knn(nq * 32);
+#pragma omp parallel for schedule(dynamic, 256)
+                for (long i = 0; i < (long)nq; i++) {
+                    glm::dvec3 p(qpos[3 * i], qpos[3 * i + 1], qpos[3 * i + 2]), d(qdir[3 * i], qdir[3 * i + 1], qdir[3 * i + 2]);
+                    double scale = 0;
+                    std::vector<Photon*> c = rt._photon_map->getInRange(p, scale, 0);   // raytracer.h:538
+                    ncand[i] = (uint32_t)c.size();
+                    int count = std::min(32, (int)c.size());
+                    std::partial_sort(c.begin(), c.begin() + count, c.end(), [p](const Photon* l, const Photon* r) { return vecLengthSquared(l->origin - p) < vecLengthSquared(r->origin - p); });
+                    for (int k = 0; k < 32; k++) knn[(size_t)i * 32 + k] = k < count ? pid.at(c[k]) : 0xFFFFFFFFu;
+                    glm::dvec3 e = rt.samplePhotons(p, d, 32);                              // raytracer.h:532
+                    est[3 * i] = e.x; est[3 * i + 1] = e.y; est[3 * i + 2] = e.z;
+                }
+                dump("q_pos.f64", qpos); dump("q_dir.f64", qdir); dump("q_est.f64", est); dump("q_ncand.u32", ncand); dump("q_knn.u32", knn);
                 meta << "gather_queries=" << nq << "\n";
             }
             if (has("time-gather")) {

@@ -1,6 +1,6 @@
 #!/usr/bin/env python3
-"""TEST/BENCH INFRASTRUCTURE: stage the reference's mounted scene ASSETS (OBJ meshes, textures) into
-oracle/_ref/assets/<scene>/ (git-ignored, travels to the GPU box with the snapshot).
+"""Stage the reference's mounted scene ASSETS (OBJ meshes, textures) into
+scenes/_assets/<scene>/ (git-ignored, travels to the GPU box with the snapshot).
 
 Nothing here is reference source code: meshes are copied byte-for-byte, textures are decoded with PIL into the
 raw "GIRT" sidecar (`<name>.rgba`: magic, u32 w, u32 h, u32 has_alpha, RGBA8 rows top-first) that both the

@@ -61,4 +61,4 @@ def scene_path(name):
 
 
 def have_assets(name):
-    return os.path.isdir(os.path.join(ROOT, "oracle", "_ref", "assets", name))
+    return os.path.isdir(os.path.join(ROOT, "scenes", "_assets", name))

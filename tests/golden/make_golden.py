@@ -9,6 +9,18 @@ Fixtures (all raw outputs of the reference's own functions, OMP_NUM_THREADS=1, t
                      sampler KATs, camera rays, closest hits, shadow rays + visibility, 3000 photons, photon-map
                      cells, gather candidates / 32-nearest sets / radiance estimates.
   caustics_small.npz scenes/caustics/caustics.scn at 40x40: rays, hits, shadows, 2500 photons + gather.
+  api_small.npz      tests/synth.py `small.scn` + the API-built primitives of csrc/host/api_scene.inc (`gi_ref --api-scene 1`: analytic
+                     sphere and cones, sphereMesh / coneMesh / quadMesh / boxMesh generators, a checkerboard material) at 56x56, s in
+                     [0,2): rays, closest hits (ids, points, normals, uvs), shadow rays + visibility, texture::get / getAlpha at
+                     the hits.  Pins sphere::intersect, cone::intersect and checkerboard::get (entities.h:60-101, 158-258; material.h:32-49).
+  cones_small.npz    the same base scene + `--api-scene 2`: two analytic cones and a sphere in an UNPARTITIONED root (15 entities) — the only
+                     configuration in which the reference can hit a cone at all (entities.h:38-41); pins cone::intersect's hits.
+  cards_small.npz    tests/synth.py `cards_op.scn` (alpha-textured cards at opacity 0.85 x texture alpha, ground at opacity 0.6) at 56x56,
+                     s in [0,2), run with OMP_NUM_THREADS=1 and time() = 424242: the reference's own xorshift64* stream is then known, and
+                     the port replays it (go_trace_closest_replay): ids / hits / shadow bits of the STOCHASTIC alpha path,
+                     imageTexture::get / getAlpha (raytracer.h:455, :297; material.h:51-81, 90-93).
+  mixed_small.npz    tests/synth.py `mixed.scn` the same way: analytic spheres inside a PARTITIONED octree, a checkerboard, a refractive
+                     material with opacity 0.5 (IOR != 1 passes the alpha test whatever the draw).
   fog_small.npz      scenes/caustics_fog_dense at 40x40 (same geometry, camera and rays as caustics_small): the HeightFog
                      parameters and noise grid as the reference's constructor filled it, Octree::atmosphereDensity at 4000
                      points, Octree::atmosphereBounds on the primary rays.
@@ -54,6 +66,29 @@ def main():
     out["meta_w_h_s0_s1"] = np.array([40, 40, 0, 1])
     np.savez_compressed(os.path.join(HERE, "caustics_small.npz"), **out)
     print("caustics_small", meta)
+    import synth
+    sd = tempfile.mkdtemp(prefix="synth_")
+    synth.write_all(sd)
+    HIT_FILES = ["ray_o.f64", "ray_d.f64", "ray_idx.u32", "hit_id.u32", "hit_pos.f64", "hit_nrm.f64", "hit_uv.f64", "sh_o.f64", "sh_d.f64", "sh_maxt2.f64", "sh_vis.u8",
+                 "tex_dif.f64", "tex_em.f64", "tex_alpha.f64"]
+    d, meta = R.run_ref(os.path.join(sd, "small.scn"), ["primary", "shadow", "textures"], w=56, h=56, s0=0, s1=2, api_scene=1, photons=0)
+    out = pack(d, HIT_FILES)
+    out["meta_w_h_s0_s1"] = np.array([56, 56, 0, 2])
+    np.savez_compressed(os.path.join(HERE, "api_small.npz"), **out)
+    print("api_small", meta)
+    d, meta = R.run_ref(os.path.join(sd, "small.scn"), ["primary", "shadow", "textures"], w=56, h=56, s0=0, s1=2, api_scene=2, photons=0)
+    out = pack(d, HIT_FILES)
+    out["meta_w_h_s0_s1"] = np.array([56, 56, 0, 2])
+    np.savez_compressed(os.path.join(HERE, "cones_small.npz"), **out)
+    print("cones_small", meta)
+    T = 424242
+    for scn, name in (("cards_op.scn", "cards_small"), ("mixed.scn", "mixed_small")):
+        d, meta = R.run_ref(os.path.join(sd, scn), ["primary", "shadow", "textures"], w=56, h=56, s0=0, s1=2, photons=0, threads=1, time_value=T)
+        out = pack(d, HIT_FILES)
+        out["meta_w_h_s0_s1"] = np.array([56, 56, 0, 2])
+        out["xorshift_seed"] = np.array([T], dtype=np.uint64)
+        np.savez_compressed(os.path.join(HERE, name + ".npz"), **out)
+        print(name, meta)
     d, meta = R.run_ref(os.path.join(root, "scenes/caustics_fog_dense/caustics_fog_dense.scn"), ["scene", "primary", "fog"], w=40, h=40, s0=0, s1=1, photons=10)
     out = pack(d, ["fog_params.f64", "fog_grid.f64", "fog_pos.f64", "fog_dens.f64", "fog_col.f64", "fogb_hit.u8", "fogb_t.f64"])
     np.savez_compressed(os.path.join(HERE, "fog_small.npz"), **out)

@@ -38,6 +38,9 @@ def lib():
     L.go_trace_any.argtypes = [vp, sz, vp, vp, vp, u64, vp]
     L.go_trace_closest_cot.argtypes = [vp, sz, vp, vp, u64, vp, vp, vp, vp]
     L.go_trace_any_cot.argtypes = [vp, sz, vp, vp, vp, u64, vp, vp, vp]
+    L.go_trace_closest_replay.argtypes = [vp, sz, vp, vp, vp, vp, vp, vp, vp]
+    L.go_trace_any_replay.argtypes = [vp, sz, vp, vp, vp, vp, vp]
+    L.go_material_eval.argtypes = [vp, sz, vp, vp, vp, vp, vp]
     L.go_pmap_build.restype = vp
     L.go_pmap_build.argtypes = [sz, vp, vp]
     L.go_pmap_free.argtypes = [vp]
@@ -161,6 +164,44 @@ def trace_any_cot(scene, org, d, maxt2, alpha_seed=0):
     desc = scene.desc()
     L.go_trace_any_cot(C.byref(desc), n, _p(org), _p(d), _p(maxt2), alpha_seed, _p(vis), _p(nn), _p(npr))
     return vis, nn, npr
+
+
+def trace_closest_replay(scene, org, d, state):
+    """RayTracer::trace on the reference's own xorshift64* stream (sequential; `state` = the interposed time() value or the
+    state a previous replay call returned) -> (prim, hit, normal, uv, new state)."""
+    L = lib()
+    org, d = _f64(org, 3), _f64(d, 3)
+    n = org.shape[0]
+    prim = np.empty(n, dtype=np.uint32)
+    hit, nrm, uv = np.empty((n, 3)), np.empty((n, 3)), np.empty((n, 2))
+    st = C.c_uint64(state)
+    desc = scene.desc()
+    L.go_trace_closest_replay(C.byref(desc), n, _p(org), _p(d), C.byref(st), _p(prim), _p(hit), _p(nrm), _p(uv))
+    return prim, hit, nrm, uv, st.value
+
+
+def trace_any_replay(scene, org, d, maxt2, state):
+    L = lib()
+    org, d = _f64(org, 3), _f64(d, 3)
+    maxt2 = np.ascontiguousarray(maxt2, dtype=np.float64)
+    n = org.shape[0]
+    vis = np.empty(n, dtype=np.uint8)
+    st = C.c_uint64(state)
+    desc = scene.desc()
+    L.go_trace_any_replay(C.byref(desc), n, _p(org), _p(d), _p(maxt2), C.byref(st), _p(vis))
+    return vis, st.value
+
+
+def material_eval(scene, prim, uv):
+    """Material::diffuse->get(uv), emissive->get(uv), Material::getAlpha(uv) of the primitives' materials (material.h)."""
+    L = lib()
+    prim = np.ascontiguousarray(prim, dtype=np.uint32)
+    uv = _f64(uv, 2)
+    n = prim.shape[0]
+    dif, em, alpha = np.empty((n, 3)), np.empty((n, 3)), np.empty(n)
+    desc = scene.desc()
+    L.go_material_eval(C.byref(desc), n, _p(prim), _p(uv), _p(dif), _p(em), _p(alpha))
+    return dif, em, alpha
 
 
 def fog_density(scene, pos):

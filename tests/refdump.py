@@ -11,7 +11,7 @@ from gi_raytracer_b200.abi import SceneArrays, GI_TEX_CONST
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 GI_REF = os.path.join(ROOT, "oracle", "_ref", "gi_ref")
 GI_REF_FAST = os.path.join(ROOT, "oracle", "_ref", "gi_ref_fast")
-ASSETS = os.path.join(ROOT, "oracle", "_ref", "assets")
+ASSETS = os.path.join(ROOT, "scenes", "_assets")
 
 _EXT = {"f64": np.float64, "f32": np.float32, "u32": np.uint32, "u8": np.uint8}
 

@@ -201,6 +201,10 @@ mesh cards.obj 0 0 0 0 0 0 1
 light -6 9 -4 150 150 150 .5
 """
 
+# like CARDS_SCN with material opacities below 1 on top of the texture alpha (Material::getAlpha = opacity * texture alpha,
+# material.h:90-93): a constant-colour ground at opacity 0.6 and the cards at 0.85 — every geometric hit is a stochastic decision
+CARDS_OP_SCN = CARDS_SCN.replace("mat 1 0 1 1 1", "mat 1 0 1 0.6 1").replace("mat 2 0 1 1 1", "mat 2 0 1 0.85 1").replace("alpha holes", "alpha holes, opacities below one")
+
 SMALL_SCN = """# twelve-triangle scene: the root is a single leaf (not partitioned)
 samples 2 2 0.0015
 photons 0 5
@@ -241,7 +245,7 @@ def write_all(d, atrium_cols=10):
     cards(os.path.join(d, "cards.obj"))
     leaf_texture(os.path.join(d, "leaf.png"))
     atrium(os.path.join(d, "atrium.obj"), cols=atrium_cols)
-    for name, text in (("mixed", MIXED_SCN), ("cards", CARDS_SCN), ("small", SMALL_SCN), ("atrium", ATRIUM_SCN)):
+    for name, text in (("mixed", MIXED_SCN), ("cards", CARDS_SCN), ("cards_op", CARDS_OP_SCN), ("small", SMALL_SCN), ("atrium", ATRIUM_SCN)):
         _no_keywords_in_comments(text)
         p = os.path.join(d, name + ".scn")
         with open(p, "w") as f:

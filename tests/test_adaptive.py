@@ -39,7 +39,7 @@ def adaptive_scene(tmp_path_factory):
     if not R.have_assets("cornell"):
         pytest.skip("assets not staged")
     d = tmp_path_factory.mktemp("adaptive")
-    os.symlink(os.path.join(ROOT, "oracle", "_ref", "assets", "cornell"), os.path.join(d, "assets"))
+    os.symlink(os.path.join(ROOT, "scenes", "_assets", "cornell"), os.path.join(d, "assets"))
     p = os.path.join(d, "adaptive.scn")
     with open(p, "w") as f:
         f.write(SCN)

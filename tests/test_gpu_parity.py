@@ -72,6 +72,66 @@ def test_golden_rays_hits_shadows_gather(ctx, which, golden_cornell, golden_caus
     assert np.allclose(rgb, g["q_est_f64"].reshape(-1, 3), rtol=1e-12, atol=0)
 
 
+def _golden(name):
+    return np.load(os.path.join(os.path.dirname(__file__), "golden", name + ".npz"))
+
+
+@pytest.mark.parametrize("name,scn,kinds_hit", [("api_small", "small.scn#api", {0, 1}), ("cones_small", "small.scn#api2", {0, 1, 2}), ("mixed_small", "mixed.scn", {0, 1})])
+def test_golden_sphere_cone_checker_hits_vs_reference(ctx, synth_dir, name, scn, kinds_hit):
+    """sphere::intersect / cone::intersect / checkerboard::get (entities.h:60-101, 158-258; material.h:32-49) against fixtures the
+    REFERENCE wrote (`gi_ref --api-scene 1|2`, and the `mixed` scene whose semi-opaque materials all have IOR != 1, so its ids are
+    PRNG-free): primitive ids and shadow bits bit-exact; hit points / normals / uvs bit-exact on triangles and within 1e-12 on the
+    analytic primitives (CUDA's sqrt is IEEE, its atan2 / asin differ from glibc's in the last ulps); texture values bit-exact."""
+    from gi_raytracer_b200 import host
+    g = _golden(name)
+    sc = host.load_scene(os.path.join(synth_dir, scn))
+    ctx.upload_scene(sc)
+    w, h, s0, s1 = [int(v) for v in g["meta_w_h_s0_s1"]]
+    o, d, ix = ctx.camera_rays(w, h, 0, 0, w, h, s0, s1)
+    ro, rd = g["ray_o_f64"].reshape(-1, 3), g["ray_d_f64"].reshape(-1, 3)
+    assert bits_equal(ix, g["ray_idx_u32"]) and bits_equal(o, ro) and bits_equal(d, rd)
+    prim, hit, nrm, uv = ctx.trace_closest(ro, rd)
+    rid = g["hit_id_u32"]
+    assert bits_equal(prim, rid), f"{(prim != rid).sum()} ids differ from the reference"
+    m = rid != 0xFFFFFFFF
+    kind = np.full(rid.shape, 255, dtype=np.uint8); kind[m] = sc.prim_type[rid[m]]
+    assert set(int(k) for k in np.unique(kind[m])) == kinds_hit
+    rh, rn, ruv = g["hit_pos_f64"].reshape(-1, 3), g["hit_nrm_f64"].reshape(-1, 3), g["hit_uv_f64"].reshape(-1, 2)
+    tri = kind == 0
+    assert bits_equal(hit[tri], rh[tri]) and bits_equal(nrm[tri], rn[tri])
+    assert bits_equal(hit[~m], rh[~m])
+    ana = m & ~tri
+    assert np.allclose(hit[ana], rh[ana], rtol=0, atol=1e-12) and np.allclose(nrm[ana], rn[ana], rtol=0, atol=1e-12)
+    assert np.array_equal(np.isnan(uv), np.isnan(ruv)) and np.allclose(uv, ruv, rtol=0, atol=1e-13, equal_nan=True)
+    vis = ctx.trace_any(g["sh_o_f64"].reshape(-1, 3), g["sh_d_f64"].reshape(-1, 3), g["sh_maxt2_f64"])
+    if name == "mixed_small":   # the reference's shadow test drew from its PRNG only where IOR == 1 and alpha < 1: nowhere in this scene
+        pass
+    assert bits_equal(vis, g["sh_vis_u8"])
+    dif, em, al = ctx.material_eval(rid[m], ruv[m])
+    assert bits_equal(dif, g["tex_dif_f64"].reshape(-1, 3)[m]) and bits_equal(em, g["tex_em_f64"].reshape(-1, 3)[m]) and bits_equal(al, g["tex_alpha_f64"][m])
+
+
+def test_golden_alpha_texture_values_vs_reference(ctx, synth_dir):
+    """imageTexture::get / getAlpha and Material::getAlpha (material.h:63-81, 90-93) at the reference's own hit uvs of the
+    alpha-card scene: alpha bit-exact, colour = pow(c / 255, 2.2) within 4 ulp of glibc's."""
+    from gi_raytracer_b200 import host
+    g = _golden("cards_small")
+    sc = host.load_scene(os.path.join(synth_dir, "cards_op.scn"))
+    ctx.upload_scene(sc)
+    rid, ruv = g["hit_id_u32"], g["hit_uv_f64"].reshape(-1, 2)
+    m = rid != 0xFFFFFFFF
+    dif, em, al = ctx.material_eval(rid[m], ruv[m])
+    assert bits_equal(al, g["tex_alpha_f64"][m]) and np.unique(al).size >= 3
+    ref = g["tex_dif_f64"].reshape(-1, 3)[m]
+    assert np.allclose(dif, ref, rtol=1e-15 * 4, atol=0)
+    # the geometric part of the stochastic path is PRNG-free: with every draw passing (alpha_seed irrelevant once opacities are 1)
+    # the device and the restatement agree bit for bit on the reference's rays
+    ro, rd = g["ray_o_f64"].reshape(-1, 3), g["ray_d_f64"].reshape(-1, 3)
+    for seed in (0, 424242):
+        a, b = ctx.trace_closest(ro, rd, alpha_seed=seed), O.trace_closest(sc, ro, rd, alpha_seed=seed)
+        assert all(bits_equal(x, y) for x, y in zip(a, b))
+
+
 # ---- against the CPU restatement on seeded inputs ------------------------------------------------------------------------------
 def _load(name, synth_dir):
     from gi_raytracer_b200 import host
@@ -542,8 +602,8 @@ def test_c2_full_size_frame_properties(ctx):
 @pytest.mark.parametrize("name,w,h,spp,photons,rows", [("glass", 1920, 1080, 64, 275000, 400), ("foliage", 1920, 1080, 16, 0, 500), ("sponza", 3840, 2160, 16, 0, 1200)])
 def test_large_configs_tiles_compose_at_full_size(ctx, name, w, h, spp, photons, rows):
     """BASELINE configs 3 (glass, 1920x1080x64, deep specular chains), 4 (foliage stand-in: alpha-textured cards, the FULL traversal
-    with its stochastic alpha test; 16 of the 256 spp) and 5 (sponza stand-in, 3840x2160, 16 of the 1024 spp one GPU of eight
-    takes) at full resolution: many path chunks, the tail kernel and the side streams all in play; the lower part of
+    with its stochastic alpha test; 16 of the 256 spp) and 5 (sponza stand-in, 3840x2160, 16 of the 1024 spp — one GPU of eight
+    takes 128 of them; the wrapped range s >= 480 is covered by test_full_size.py) at full resolution: many path chunks, the tail kernel and the side streams all in play; the lower part of
     the frame rendered as its own tile must equal the same rows of the whole frame bit for bit, tallies must add up."""
     from gi_raytracer_b200 import host
     if name == "glass" and not have_assets("glass"):
