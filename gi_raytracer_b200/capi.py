@@ -23,9 +23,21 @@ API_SYMBOLS = [
     "gi_photon_map_slab_ptr", "gi_photon_map_adopt_slab", "gi_photon_map_reserve_slab", "gi_photon_gather",
     "gi_photon_gather_dev", "gi_render_tile", "gi_render_tile_dev", "gi_resolve", "gi_resolve_dev", "gi_last_kernel_ms",
     "gi_last_work", "gi_scene_info", "gi_render_adaptive", "gi_render_adaptive_dev", "gi_fog_density", "gi_raymarch", "gi_octree_build", "gi_octree_download", "gi_cancel", "gi_render_image", "gi_configure", "gi_material_eval",
+    "gi_rows_of_part", "gi_render_rows", "gi_render_rows_dev", "gi_comm_unique_id", "gi_comm_init", "gi_comm_destroy", "gi_comm_info", "gi_photon_map_bcast",
+    "gi_framebuffer_reduce", "gi_framebuffer_gather", "gi_render_rows_image",
 ]
 
 _LIB = None
+
+
+def comm_unique_id():
+    """gi_comm_unique_id: 128 bytes to hand to every rank's Context.comm_init (made on ONE rank)."""
+    L = load_library()
+    buf = (C.c_uint8 * 128)()
+    rc = L.gi_comm_unique_id(buf, 128)
+    if rc != 0:
+        raise GiError(rc, "gi_comm_unique_id failed (libnccl.so.2 not loadable?)")
+    return bytes(buf)
 
 
 class GiError(RuntimeError):
@@ -63,7 +75,25 @@ def load_library():
         f.argtypes = [vp, sz, vp, vp, vp, u64, vp]
     L.gi_fog_density.argtypes = [vp, sz, vp, vp, vp]
     L.gi_material_eval.argtypes = [vp, sz, vp, vp, vp, vp, vp]
-    L.gi_raymarch.argtypes = [vp, sz, vp, vp, vp, u64, i32, vp, vp, vp, vp, vp]
+    def sig(name, argtypes):
+        # GI_LIB names an A/B build of the library (profiles/ab_variants.sh), possibly older than this binding: a symbol it lacks is
+        # skipped there; the in-tree library must export every one (tests/test_abi.py)
+        try:
+            getattr(L, name).argtypes = argtypes
+        except AttributeError:
+            if "GI_LIB" not in os.environ:
+                raise
+    sig("gi_rows_of_part", [i32, i32, i32, i32])
+    for f in ("gi_render_rows", "gi_render_rows_dev"):
+        sig(f, [vp, C.POINTER(GiRenderParams), i32, i32, i32, i32, i32, vp, C.POINTER(GiStats)])
+    sig("gi_comm_unique_id", [vp, sz])
+    sig("gi_comm_init", [vp, vp, sz, i32, i32])
+    sig("gi_comm_destroy", [vp])
+    sig("gi_comm_info", [vp, C.POINTER(i32), C.POINTER(i32), C.POINTER(i32)])
+    sig("gi_photon_map_bcast", [vp, i32])
+    sig("gi_framebuffer_reduce", [vp, vp, sz, i32])
+    sig("gi_framebuffer_gather", [vp, vp, sz, i32, i32, vp, i32])
+    sig("gi_render_rows_image", [vp, C.POINTER(GiRenderParams), i32, i32, i32, vp, i32, C.POINTER(GiStats)])
     L.gi_octree_build.argtypes = [vp, u32, vp, vp, vp, vp, C.POINTER(u32), C.POINTER(u32), C.POINTER(C.c_double)]
     L.gi_octree_download.argtypes = [vp, vp, vp, vp, vp, vp, vp]
     L.gih_scene_prim_bbox.argtypes = [vp, vp]
@@ -354,6 +384,56 @@ class Context:
         st = GiStats()
         self._ck(self.L.gi_render_adaptive(self.h, C.byref(params), min_samples, max_samples, float(noise_thresh), x0, y0, x1, y1, col.ctypes.data, ns.ctypes.data, C.byref(st)))
         return col, ns, st
+
+    # -- tile split / multi-GPU ---------------------------------------------------------------------------------------------
+    def rows_of_part(self, height, block_rows, nparts, part):
+        n = self.L.gi_rows_of_part(height, block_rows, nparts, part)
+        if n < 0:
+            raise GiError(n, "bad row plan")
+        return n
+
+    def render_rows(self, params: GiRenderParams, block_rows, nparts, part, s0, s1):
+        """gi_render_rows: the rows of one part of the interleaved row-block plan -> (accum [local rows * width, 3], GiStats)."""
+        rows = self.rows_of_part(params.height, block_rows, nparts, part)
+        acc = np.empty((rows * params.width, 3))
+        st = GiStats()
+        self._ck(self.L.gi_render_rows(self.h, C.byref(params), block_rows, nparts, part, s0, s1, _p(acc), C.byref(st)))
+        return acc, st
+
+    def render_rows_dev(self, params: GiRenderParams, block_rows, nparts, part, s0, s1, accum_ptr):
+        st = GiStats()
+        self._ck(self.L.gi_render_rows_dev(self.h, C.byref(params), block_rows, nparts, part, s0, s1, accum_ptr, C.byref(st)))
+        return st
+
+    def comm_init(self, id_bytes, rank, nranks):
+        """gi_comm_init: collective over the nranks contexts; id_bytes = the 128 bytes of comm_unique_id() made on one rank."""
+        buf = (C.c_uint8 * 128).from_buffer_copy(bytes(id_bytes)[:128].ljust(128, b"\0"))
+        self._ck(self.L.gi_comm_init(self.h, buf, 128, rank, nranks))
+
+    def comm_destroy(self):
+        self._ck(self.L.gi_comm_destroy(self.h))
+
+    def comm_info(self):
+        r, n, v = C.c_int(), C.c_int(), C.c_int()
+        self._ck(self.L.gi_comm_info(self.h, C.byref(r), C.byref(n), C.byref(v)))
+        return dict(rank=r.value, nranks=n.value, nccl_version=v.value)
+
+    def photon_map_bcast(self, root=0):
+        self._ck(self.L.gi_photon_map_bcast(self.h, root))
+
+    def framebuffer_reduce(self, accum_ptr, count, root=0):
+        self._ck(self.L.gi_framebuffer_reduce(self.h, accum_ptr, count, root))
+
+    def framebuffer_gather(self, local_ptr, row_bytes, height, block_rows, frame_ptr, root=0):
+        self._ck(self.L.gi_framebuffer_gather(self.h, local_ptr, row_bytes, height, block_rows, frame_ptr, root))
+
+    def render_rows_image(self, params: GiRenderParams, block_rows, s0, s1, root=0):
+        """gi_render_rows_image: this rank's rows rendered, resolved and gathered; the root gets the 8-bit frame [h * w, 3] (others None)."""
+        info = self.comm_info()
+        rgb = np.empty((params.height * params.width, 3), dtype=np.uint8) if info["rank"] == root else None
+        st = GiStats()
+        self._ck(self.L.gi_render_rows_image(self.h, C.byref(params), block_rows, s0, s1, _p(rgb), root, C.byref(st)))
+        return rgb, st
 
     def render_tile_dev(self, params: GiRenderParams, x0, y0, x1, y1, s0, s1, accum_ptr):
         st = GiStats()

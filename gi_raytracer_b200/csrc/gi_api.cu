@@ -80,6 +80,11 @@ struct gi_ctx {
     // second the other one, later frames the faster of the two (bounce + direct ms per closest-hit ray)
     uint64_t tune_sig = 0;           // signature of the scene the statistic above belongs to
     uint32_t bin_threshold = 65536;  // queues at least this long are binned by origin cell / direction octant before the next bounce (GI_BIN_THRESHOLD, 0 = off)
+    struct gi_comm* comm = nullptr;  // gi_comm_init: the NCCL communicator of this context (gi_comm.inc)
+    DevBuf b_comm, b_stage;          // collective scratch: size word; the root's staging area of gi_framebuffer_gather
+    DevBuf b_err;                    // DScene::err: the sticky device error word
+    uint32_t dev_err = 0;            // its last read-back (collect_timers)
+    int n_sm = 148;                  // multiprocessors of the device (persistent kernels are sized from it)
     unsigned long long work_host[16] = { 0 };   // [0,1] closest nodes/prims, [2,3] any-hit, [4..6] gather depth/cand/sel, [8] rays, [9] shadow rays, [10] queries
     // timing
     std::vector<TimedLaunch> pending;
@@ -138,11 +143,23 @@ struct ScopedTimer {   // records an event pair around the launches issued in it
     ScopedTimer(gi_ctx* c, const char* fam) : ctx(c) { t.fam = fam; t.a = get_event(c); t.b = get_event(c); cudaEventRecord(t.a, c->stream); }
     ~ScopedTimer() { cudaEventRecord(t.b, ctx->stream); ctx->pending.push_back(t); }
 };
+struct EventPair {     // a start / stop event pair that goes back to the pool on every exit path (early returns included)
+    gi_ctx* ctx; cudaEvent_t a, b;
+    explicit EventPair(gi_ctx* c) : ctx(c), a(get_event(c)), b(get_event(c)) {}
+    ~EventPair() { ctx->event_pool.push_back(a); ctx->event_pool.push_back(b); }
+    EventPair(const EventPair&) = delete;
+    EventPair& operator=(const EventPair&) = delete;
+    float ms() const { float v = 0; cudaEventElapsedTime(&v, a, b); return v; }
+};
 static void fam_reset(gi_ctx* ctx, const char* fam) { ctx->fam[fam] = FamStat(); }
 static unsigned long long* work_ptr(gi_ctx* ctx, int slot) { return ctx->b_work.as<unsigned long long>() + slot; }
 static void collect_timers(gi_ctx* ctx)   // after a stream sync
 {
     if (ctx->b_work.p) cudaMemcpy(ctx->work_host, ctx->b_work.p, 8 * sizeof(unsigned long long), cudaMemcpyDeviceToHost);
+    if (ctx->b_err.p) {
+        uint32_t e = 0;
+        if (cudaMemcpy(&e, ctx->b_err.p, 4, cudaMemcpyDeviceToHost) == cudaSuccess && e) { ctx->dev_err |= e; cudaMemset(ctx->b_err.p, 0, 4); }
+    }
     static const bool trace_launches = getenv("GI_TRACE_LAUNCHES") != nullptr;
     for (auto& t : ctx->pending) {
         float ms = 0;
@@ -213,7 +230,7 @@ static DFrame make_frame(const gi_ctx* ctx, int w, int h, int x0, int y0, int x1
 {
     DFrame F{};
     const gi_camera& c = ctx->S.cam;
-    F.w = w; F.h = h; F.x0 = x0; F.y0 = y0; F.tw = x1 - x0; F.th = y1 - y0;
+    F.w = w; F.h = h; F.x0 = x0; F.y0 = y0; F.tw = x1 - x0; F.th = y1 - y0; F.rb = 0; F.rstride = 0;
     F.halfW = (c.sensor_diag * w) / (std::sqrt((double)w * w + h * h));   // raytracer.h:74-75
     F.halfH = F.halfW * ((double)h / w);
     auto v = [](const double* p) { d3 r; r.x = p[0]; r.y = p[1]; r.z = p[2]; return r; };
@@ -230,6 +247,8 @@ static DFrame make_frame(const gi_ctx* ctx, int w, int h, int x0, int y0, int x1
 // ---- lifetime -----------------------------------------------------------------------------------------------------------------------
 extern "C" const char* gi_version(void) { return GI_VERSION; }
 
+extern "C" void gi_destroy(gi_ctx* ctx);
+extern "C" int gi_comm_destroy(gi_ctx* ctx);
 extern "C" int gi_create(int device, gi_ctx** out)
 {
     if (!out) return GI_ERR_INVALID;
@@ -242,21 +261,25 @@ extern "C" int gi_create(int device, gi_ctx** out)
     if (cudaSetDevice(device) != cudaSuccess) return GI_ERR_NO_DEVICE;
     gi_ctx* ctx = new gi_ctx();
     ctx->device = device;
-    if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return GI_ERR_CUDA; }
+    // every failure below goes through gi_destroy, which releases whatever exists so far (streams, events, buffers)
+    if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) { ctx->stream = nullptr; gi_destroy(ctx); return GI_ERR_CUDA; }
     ctx->main_stream = ctx->stream;
     for (int k = 0; k < 2; k++) {
-        if (cudaStreamCreateWithFlags(&ctx->side[k], cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return GI_ERR_CUDA; }
-        for (int q = 0; q < 2; q++) if (cudaEventCreateWithFlags(&ctx->side_done[q][k], cudaEventDisableTiming) != cudaSuccess) { delete ctx; return GI_ERR_CUDA; }
+        if (cudaStreamCreateWithFlags(&ctx->side[k], cudaStreamNonBlocking) != cudaSuccess) { ctx->side[k] = nullptr; gi_destroy(ctx); return GI_ERR_CUDA; }
+        for (int q = 0; q < 2; q++) if (cudaEventCreateWithFlags(&ctx->side_done[q][k], cudaEventDisableTiming) != cudaSuccess) { ctx->side_done[q][k] = nullptr; gi_destroy(ctx); return GI_ERR_CUDA; }
     }
     if (const char* e = getenv("GI_OVERLAP_THRESHOLD")) ctx->overlap_threshold = (uint32_t)strtoul(e, nullptr, 10);
     // Halton tables are scene independent
     std::vector<uint16_t> tab; std::vector<DHaltonDim> dims;
     build_halton(tab, dims);
-    if (ctx->b_htab.reserve(tab.size() * 2) != cudaSuccess || ctx->b_hdims.reserve(dims.size() * sizeof(DHaltonDim)) != cudaSuccess) { delete ctx; return GI_ERR_OOM; }
+    if (ctx->b_htab.reserve(tab.size() * 2) != cudaSuccess || ctx->b_hdims.reserve(dims.size() * sizeof(DHaltonDim)) != cudaSuccess) { gi_destroy(ctx); return GI_ERR_OOM; }
     cudaMemcpy(ctx->b_htab.p, tab.data(), tab.size() * 2, cudaMemcpyHostToDevice);
     cudaMemcpy(ctx->b_hdims.p, dims.data(), dims.size() * sizeof(DHaltonDim), cudaMemcpyHostToDevice);
-    if (ctx->b_work.reserve(16 * sizeof(unsigned long long)) != cudaSuccess) { delete ctx; return GI_ERR_OOM; }
+    if (ctx->b_work.reserve(16 * sizeof(unsigned long long)) != cudaSuccess || ctx->b_err.reserve(16) != cudaSuccess) { gi_destroy(ctx); return GI_ERR_OOM; }
     cudaMemset(ctx->b_work.p, 0, 16 * sizeof(unsigned long long));
+    cudaMemset(ctx->b_err.p, 0, 16);
+    ctx->S.err = ctx->b_err.as<uint32_t>();
+    ctx->n_sm = prop.multiProcessorCount > 0 ? prop.multiProcessorCount : 148;
     ctx->S.halton_tab = ctx->b_htab.as<uint16_t>();
     ctx->S.halton_dims = ctx->b_hdims.as<DHaltonDim>();
     if (getenv("GI_NO_IMPLICIT_BOXES")) ctx->no_implicit = true;
@@ -273,7 +296,9 @@ extern "C" void gi_destroy(gi_ctx* ctx)
 {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
-    cudaStreamSynchronize(ctx->stream);
+    if (ctx->main_stream) cudaStreamSynchronize(ctx->main_stream);
+    gi_comm_destroy(ctx);
+    ctx->b_err.release(); ctx->b_comm.release(); ctx->b_stage.release();
     DevBuf* all[] = { &ctx->b_nodes, &ctx->b_refs, &ctx->b_geom, &ctx->b_nrm, &ctx->b_uv, &ctx->b_fnorm, &ctx->b_pmat, &ctx->b_ptype, &ctx->b_mats, &ctx->b_tex, &ctx->b_texpx,
                       &ctx->b_lights, &ctx->b_htab, &ctx->b_hdims, &ctx->b_fogs, &ctx->b_foggrid, &ctx->b_photons, &ctx->b_slab, &ctx->w0, &ctx->w1, &ctx->w2, &ctx->w3, &ctx->w4, &ctx->w5, &ctx->w6, &ctx->w7,
                       &ctx->w8, &ctx->w9, &ctx->b_cnt, &ctx->b_accum, &ctx->b_scan0, &ctx->b_scan1, &ctx->b_misc, &ctx->b_work, &ctx->b_tail, &ctx->b_binkey, &ctx->b_binperm,
@@ -301,7 +326,7 @@ extern "C" void gi_destroy(gi_ctx* ctx)
     for (auto& b : ctx->hl2) b.release();
     for (auto& b : ctx->tsh) b.release();
     ctx->b_scan1s.release();
-    cudaStreamDestroy(ctx->main_stream);
+    if (ctx->main_stream) cudaStreamDestroy(ctx->main_stream);
     delete ctx;
 }
 
@@ -344,6 +369,10 @@ extern "C" int gi_synchronize(gi_ctx* ctx)
     if (!ctx) return GI_ERR_INVALID;
     CK(cudaStreamSynchronize(ctx->stream));
     collect_timers(ctx);
+    if (ctx->dev_err & GI_DEV_ERR_STACK) {   // a traversal ran out of stack: the results of the calls since the last synchronisation are not to be trusted
+        ctx->dev_err = 0;
+        return fail(ctx, GI_ERR_INVALID, "traversal stack overflow (octree too deep for GI_STACK_MAX): results discarded");
+    }
     return GI_OK;
 }
 extern "C" int gi_last_work(gi_ctx* ctx, const char* family, uint64_t out[4])
@@ -387,6 +416,21 @@ extern "C" int gi_scene_upload(gi_ctx* ctx, const gi_scene_desc* sc)
         if (m) { uint32_t nc = (uint32_t)__builtin_popcount(m); if ((uint64_t)sc->node_child[i] + nc > sc->n_nodes || sc->node_child[i] <= i) return fail(ctx, GI_ERR_INVALID, "node child range out of bounds"); }
         if ((uint64_t)sc->node_prim_off[i] + sc->node_prim_cnt[i] > sc->n_refs) return fail(ctx, GI_ERR_INVALID, "leaf primitive range out of bounds");
     }
+    {   // tree depth (children come after their parent, checked above): the traversal stack holds <= 3 entries per level for an
+        // ordinary ray (at most four children of a node are met, one is walked into); a tree beyond that bound is refused here,
+        // and a ray that still overflows (zero direction components can meet all eight children) raises the sticky device error
+        std::vector<uint8_t> depth(sc->n_nodes, 0);
+        uint32_t max_depth = 0;
+        for (uint32_t i = 0; i < sc->n_nodes; i++) {
+            const uint32_t m = sc->node_mask[i];
+            if (!m) continue;
+            if (depth[i] >= 250) return fail(ctx, GI_ERR_INVALID, "octree deeper than 250 levels");
+            const uint32_t nc = (uint32_t)__builtin_popcount(m);
+            for (uint32_t c = 0; c < nc; c++) depth[sc->node_child[i] + c] = (uint8_t)(depth[i] + 1);
+            max_depth = std::max<uint32_t>(max_depth, depth[i] + 1u);
+        }
+        if (3 * max_depth + 8 > GI_STACK_MAX) return fail(ctx, GI_ERR_INVALID, "octree too deep for the traversal stack (3 * depth + 8 > GI_STACK_MAX)");
+    }
     for (uint32_t i = 0; i < sc->n_refs; i++) if (sc->leaf_prims[i] >= sc->n_prims) return fail(ctx, GI_ERR_INVALID, "leaf primitive id out of bounds");
     for (uint32_t i = 0; i < sc->n_prims; i++) if (sc->prim_mat[i] >= sc->n_mats || sc->prim_type[i] > GI_PRIM_CONE) return fail(ctx, GI_ERR_INVALID, "primitive material/type out of bounds");
     for (uint32_t i = 0; i < sc->n_mats; i++) if (sc->mats[i].diffuse_tex >= sc->n_tex || sc->mats[i].emissive_tex >= sc->n_tex) return fail(ctx, GI_ERR_INVALID, "material texture out of bounds");
@@ -415,6 +459,8 @@ extern "C" int gi_scene_upload(gi_ctx* ctx, const gi_scene_desc* sc)
         const double* lo = n.bmin; const double* hi = n.bmax;
         double mid[3], h[3];
         for (int k = 0; k < 3; k++) { mid[k] = lo[k] + .5 * (hi[k] - lo[k]); h[k] = .5 * (hi[k] - lo[k]); }
+        // the sequence walk (children_sequence) needs the planes in order: min <= mid <= mid + h and mid <= max
+        for (int k = 0; k < 3; k++) if (!(lo[k] <= mid[k] && mid[k] <= mid[k] + h[k] && mid[k] <= hi[k])) implicit = false;
         uint32_t c = n.child;
         for (int ci = 0; ci < 8; ci++) {
             if (!(n.mask & (1u << ci))) continue;
@@ -728,7 +774,7 @@ extern "C" int gi_octree_build(gi_ctx* ctx, uint32_t n_prims, const uint8_t* pri
         CK(cudaMemcpyAsync(ctx->ob_geom.p, prim_geom, (size_t)n_prims * 72, cudaMemcpyHostToDevice, st));
         CK(cudaMemcpyAsync(ctx->ob_bbox.p, prim_bbox, (size_t)n_prims * 48, cudaMemcpyHostToDevice, st));
     }
-    cudaEvent_t e0 = get_event(ctx), e1 = get_event(ctx);
+    EventPair ev(ctx); const cudaEvent_t e0 = ev.a, e1 = ev.b;
     cudaEventRecord(e0, st);
     // root (octree.cpp:25-38 grew its box; :106: it is split only when it holds more than 16 entities)
     uint32_t n_nodes = 1, leaf_base = 0;
@@ -815,7 +861,6 @@ extern "C" int gi_octree_build(gi_ctx* ctx, uint32_t n_prims, const uint8_t* pri
     cudaEventRecord(e1, st);
     CK(cudaStreamSynchronize(st));
     float ms = 0; cudaEventElapsedTime(&ms, e0, e1);
-    ctx->event_pool.push_back(e0); ctx->event_pool.push_back(e1);
     ctx->ob_n_nodes = n_nodes; ctx->ob_n_refs = leaf_base; ctx->ob_valid = true;
     if (n_nodes_out) *n_nodes_out = n_nodes;
     if (n_refs_out) *n_refs_out = leaf_base;
@@ -883,7 +928,7 @@ extern "C" int gi_photon_trace(gi_ctx* ctx, int count, int max_depth, uint64_t s
     DPhotonOut O{ ctx->w0.as<double>(), ctx->w1.as<uint8_t>(), ctx->b_misc.as<unsigned long long>(), ctx->b_misc.as<unsigned long long>() + 1, work_ptr(ctx, 0) };
     CK(cudaMemsetAsync(work_ptr(ctx, 0), 0, 16, ctx->stream));
     fam_reset(ctx, "photon_trace");
-    cudaEvent_t e0 = get_event(ctx), e1 = get_event(ctx);
+    EventPair ev(ctx); const cudaEvent_t e0 = ev.a, e1 = ev.b;
     cudaEventRecord(e0, ctx->stream);
     uint64_t launches = 4;
     {
@@ -925,7 +970,6 @@ extern "C" int gi_photon_trace(gi_ctx* ctx, int count, int max_depth, uint64_t s
     rc = gi_synchronize(ctx);
     if (rc != GI_OK) return rc;
     float ms = 0; cudaEventElapsedTime(&ms, e0, e1);
-    ctx->event_pool.push_back(e0); ctx->event_pool.push_back(e1);
     ctx->n_photons = (uint32_t)host[2];
     if (n_stored) *n_stored = ctx->n_photons;
     ctx->work_host[8] = host[1];
@@ -961,6 +1005,7 @@ extern "C" int gi_photon_map_build(gi_ctx* ctx, const double* box6)
     if (!ctx) return GI_ERR_INVALID;
     if (!box6 && !ctx->has_scene) return fail(ctx, GI_ERR_NO_SCENE, "gi_photon_map_build needs a root box (scene or box6)");
     CK(cudaSetDevice(ctx->device));
+    ctx->has_map = false;   // set again by bind_slab at the very end: a failure below must not leave ctx->G pointing at a freed slab
     const uint32_t n = (uint32_t)ctx->n_photons;
     double box[6];
     for (int k = 0; k < 6; k++) box[k] = box6 ? box6[k] : ctx->root_box[k];
@@ -977,7 +1022,7 @@ extern "C" int gi_photon_map_build(gi_ctx* ctx, const double* box6)
     M.nodes = ctx->w0.as<DNode>(); M.n_nodes = ctx->w3.as<uint32_t>(); M.cap_nodes = cap_nodes; M.ph = ctx->b_photons.as<double>(); M.n_photons = n;
     M.pnode = ctx->w1.as<uint32_t>(); M.pid = ctx->w2.as<uint32_t>(); M.n_kept = ctx->w3.as<uint32_t>() + 1; M.overflow = ctx->w3.as<uint32_t>() + 2;
     fam_reset(ctx, "pm_build");
-    cudaEvent_t e0 = get_event(ctx), e1 = get_event(ctx);
+    EventPair ev(ctx); const cudaEvent_t e0 = ev.a, e1 = ev.b;
     cudaEventRecord(e0, ctx->stream);
     k_pm_init<<<grid_for(std::max<uint32_t>(n, 1), 256), 256, 0, ctx->stream>>>(M, ctx->w4.as<double>());
     CK(cudaGetLastError());
@@ -1065,7 +1110,6 @@ extern "C" int gi_photon_map_build(gi_ctx* ctx, const double* box6)
     CK(cudaMemcpyAsync(base, &h, sizeof(h), cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
     float ms = 0; cudaEventElapsedTime(&ms, e0, e1);
-    ctx->event_pool.push_back(e0); ctx->event_pool.push_back(e1);
     ctx->fam["pm_build"].ms = ms; ctx->fam["pm_build"].launches = 1;
     bind_slab(ctx, h);
     return GI_OK;
@@ -1136,7 +1180,15 @@ extern "C" int gi_photon_map_adopt_slab(gi_ctx* ctx, size_t bytes)
     CK(cudaSetDevice(ctx->device));
     SlabHeader h;
     CK(cudaMemcpy(&h, ctx->b_slab.p, sizeof(h), cudaMemcpyDeviceToHost));
-    if (h.magic != GI_SLAB_MAGIC || h.total != bytes || h.off_pid + (uint64_t)h.n_kept * 4 > bytes || h.off_cand_rec + (uint64_t)h.n_cand * 32 > bytes) return fail(ctx, GI_ERR_INVALID, "bad photon map slab");
+    ctx->has_map = false;
+    // every section must lie inside the slab, in the builder's order, 256-byte aligned (a truncated or mismatched broadcast must
+    // not become out-of-bounds reads in the gather)
+    auto sect = [&](uint64_t off, uint64_t len, uint64_t next) { return (off & 255u) == 0 && off >= 256 && off + len <= next && next <= bytes; };
+    const bool ok = h.magic == GI_SLAB_MAGIC && h.total == bytes && h.n_nodes >= 1 && h.n_leaves <= h.n_nodes
+                    && sect(h.off_nodes, (uint64_t)h.n_nodes * sizeof(DNode), h.off_pos) && sect(h.off_pos, (uint64_t)h.n_kept * 32, h.off_dircol)
+                    && sect(h.off_dircol, (uint64_t)h.n_kept * 48, h.off_pid) && sect(h.off_pid, (uint64_t)h.n_kept * 4, h.off_cand_off)
+                    && sect(h.off_cand_off, ((uint64_t)h.n_nodes + 1) * 4, h.off_cand_rec) && sect(h.off_cand_rec, (uint64_t)h.n_cand * 32, bytes);
+    if (!ok) return fail(ctx, GI_ERR_INVALID, "bad photon map slab");
     bind_slab(ctx, h);
     return GI_OK;
 }
@@ -1161,7 +1213,7 @@ static int run_gather(gi_ctx* ctx, uint32_t n, const double* pos, const double* 
     }
     k_gather_sorted<<<grid_for(n, GI_GS_BLOCK), GI_GS_BLOCK, 0, ctx->stream>>>(ctx->G, n, order ? ctx->b_gperm.as<uint32_t>() : nullptr, ctx->b_gnode.as<uint32_t>(), pos, dir, k, rgb, knn, n_cand,
                                                                               weight, accum, accum_idx, work_ptr(ctx, 4), heavy_cnt + 4, heavy_cnt);
-    k_gather_heavy<<<148 * 4, GI_WPB * 32, 0, ctx->stream>>>(ctx->G, heavy_cnt + 4, heavy_cnt, heavy_cnt + 1, ctx->b_gnode.as<uint32_t>(), pos, dir, k, rgb, knn, n_cand, weight, accum, accum_idx);
+    k_gather_heavy<<<ctx->n_sm * 4, GI_WPB * 32, 0, ctx->stream>>>(ctx->G, heavy_cnt + 4, heavy_cnt, heavy_cnt + 1, ctx->b_gnode.as<uint32_t>(), pos, dir, k, rgb, knn, n_cand, weight, accum, accum_idx);
     CK(cudaGetLastError());
     if (launches) *launches += order ? 7 : 3;
     return GI_OK;
@@ -1205,8 +1257,18 @@ extern "C" int gi_photon_gather(gi_ctx* ctx, size_t n, const double* pos, const 
 // ---- frame ------------------------------------------------------------------------------------------------------------------------------------
 // Fixed sample range [s0, s1) into accum_dev (sums), or — with `adapt` — the reference's adaptive per-pixel loop: accum_dev then
 // receives the final running-mean colour of each pixel and adapt->s_done the samples taken.
-static int render_device(gi_ctx* ctx, const gi_render_params* P, int x0, int y0, int x1, int y1, int s0, int s1, double* accum_dev, gi_stats* stats, DAdapt* adapt = nullptr)
+// rows of part `part` of `nparts` under the tile split's plan: blocks part, part + nparts, .. of block_rows rows
+static inline int rows_of_part(int height, int block_rows, int nparts, int part)
 {
+    int n = 0;
+    for (int b = part, y0; (y0 = b * block_rows) < height; b += nparts) n += std::min(block_rows, height - y0);
+    return n;
+}
+struct RowPlan { int block_rows, nparts, part; };
+static int render_device(gi_ctx* ctx, const gi_render_params* P, int x0, int y0, int x1, int y1, int s0, int s1, double* accum_dev, gi_stats* stats, DAdapt* adapt = nullptr,
+                         const RowPlan* rows = nullptr)
+{
+    if (rows) { x0 = 0; x1 = P->width; y0 = rows->part * rows->block_rows; y1 = y0 + rows_of_part(P->height, rows->block_rows, rows->nparts, rows->part); }   // y1 - y0 = local rows
     const size_t npx = (size_t)(x1 - x0) * (y1 - y0);
     ctx->stream = ctx->main_stream;
     const uint64_t total_paths = adapt ? (uint64_t)npx : (uint64_t)npx * (uint64_t)(s1 - s0);
@@ -1238,6 +1300,7 @@ static int render_device(gi_ctx* ctx, const gi_render_params* P, int x0, int y0,
     DPathState PS{ ctx->ps[0].as<uint32_t>(), ctx->ps[1].as<uint64_t>(), ctx->ps[2].as<double>(), ctx->ps[3].as<double>(), ctx->ps[4].as<double>() };
     DCounters* C = ctx->b_cnt.as<DCounters>();
     DFrame F = make_frame(ctx, P->width, P->height, x0, y0, x1, y1);
+    if (rows) { F.rb = rows->block_rows; F.rstride = rows->block_rows * rows->nparts; }
     const bool have_map = ctx->has_map && ctx->pm_kept > 0;
     // long, uneven walks (deep trees): persistent warps with ray refetch; short ones: one ray per thread, launch per queue.
     // Decided — deterministically — from the node tests per closest-hit ray that the previous large frame of this scene tallied
@@ -1250,7 +1313,7 @@ static int render_device(gi_ctx* ctx, const gi_render_params* P, int x0, int y0,
     uint64_t n_closest = 0, n_shadow = 0, n_gather = 0, launches = 0;
     for (const char* f : { "bounce", "direct", "gather", "tail", "bin" }) fam_reset(ctx, f);
     CK(cudaMemsetAsync(work_ptr(ctx, 0), 0, 8 * sizeof(unsigned long long), ctx->stream));
-    cudaEvent_t e0 = get_event(ctx), e1 = get_event(ctx);
+    EventPair ev(ctx); const cudaEvent_t e0 = ev.a, e1 = ev.b;
     cudaEventRecord(e0, ctx->stream);
     // the bounce loop over one batch of n camera paths sitting in qa / PS
     auto run_depths = [&](uint32_t n) -> int {
@@ -1297,7 +1360,7 @@ static int render_device(gi_ctx* ctx, const gi_render_params* P, int x0, int y0,
                 {
                     ScopedTimer t(ctx, "tail");
                     CK(cudaMemsetAsync(&ctx->b_tail.as<DTailCounters>()->next, 0, 4, ctx->stream));
-                    const unsigned tail_grid = std::min<unsigned>(grid_for(n_active, GI_WPB), 148u * (unsigned)GI_TAIL_MINB);   // persistent warps: one resident wave
+                    const unsigned tail_grid = std::min<unsigned>(grid_for(n_active, GI_WPB), (unsigned)ctx->n_sm * (unsigned)GI_TAIL_MINB);   // persistent warps: one resident wave
                     GI_LAUNCH_M(k_tail, tail_grid, GI_WPB * 32, ctx->S, ctx->G, have_map ? 1 : 0, *P, depth, n_active, in, PS, ctx->b_tail.as<DTailCounters>(), Q);
                     launches++;
                 }
@@ -1336,7 +1399,7 @@ static int render_device(gi_ctx* ctx, const gi_render_params* P, int x0, int y0,
             {
                 ScopedTimer t(ctx, "bounce");
                 if (persistent) {
-                    const unsigned grid = std::min<unsigned>(grid_for(n_active, GI_BLOCK), 148u * GI_MINB);
+                    const unsigned grid = std::min<unsigned>(grid_for(n_active, GI_BLOCK), (unsigned)ctx->n_sm * GI_MINB);
                     GI_LAUNCH_M(k_bounce_p, grid, GI_BLOCK, ctx->S, *P, depth, n_active, in, perm, out, H, PS, C, work_ptr(ctx, 0), ctx->b_misc.as<uint32_t>());
                 } else GI_LAUNCH_M(k_bounce, grid_for(n_active, GI_BLOCK), GI_BLOCK, ctx->S, *P, depth, n_active, in, perm, out, H, PS, C, work_ptr(ctx, 0));
             }
@@ -1443,7 +1506,6 @@ static int render_device(gi_ctx* ctx, const gi_render_params* P, int x0, int y0,
     int rc = gi_synchronize(ctx);
     if (rc != GI_OK) return rc;
     float ms = 0; cudaEventElapsedTime(&ms, e0, e1);
-    ctx->event_pool.push_back(e0); ctx->event_pool.push_back(e1);
     n_closest += tc.closest; n_shadow += tc.shadow; n_gather += tc.gathers;
     if (n_closest && tunable) ctx->nodes_per_ray = (double)(ctx->work_host[0] + tc.nodes_c) / (double)n_closest;
     ctx->work_host[0] += tc.nodes_c; ctx->work_host[1] += tc.prims_c; ctx->work_host[2] += tc.nodes_s; ctx->work_host[3] += tc.prims_s;
@@ -1515,6 +1577,45 @@ extern "C" int gi_render_image(gi_ctx* ctx, const gi_render_params* P, int x0, i
     return GI_OK;
 }
 
+// ---- tile split: the rows of one part of the frame under the interleaved row-block plan, rendered in ONE wavefront.
+// accum [local rows][width][3] compact; a part's pixels are exactly those of the one-GPU frame (same Halton indices, same PRNG keys).
+extern "C" int gi_rows_of_part(int height, int block_rows, int nparts, int part)
+{
+    if (height <= 0 || block_rows <= 0 || nparts <= 0 || part < 0 || part >= nparts) return GI_ERR_INVALID;
+    return rows_of_part(height, block_rows, nparts, part);
+}
+static int check_rows_args(gi_ctx* ctx, const gi_render_params* P, int block_rows, int nparts, int part, int s0, int s1, const void* out)
+{
+    if (!ctx || !P || !out) return GI_ERR_INVALID;
+    if (block_rows <= 0 || nparts <= 0 || part < 0 || part >= nparts) return fail(ctx, GI_ERR_INVALID, "bad row plan");
+    int rc = check_render_args(ctx, P, 0, 0, P->width, P->height, s0, s1, reinterpret_cast<const double*>(out));
+    if (rc != GI_OK) return rc;
+    if (rows_of_part(P->height, block_rows, nparts, part) == 0) return fail(ctx, GI_ERR_INVALID, "this part of the row plan is empty");
+    return GI_OK;
+}
+extern "C" int gi_render_rows_dev(gi_ctx* ctx, const gi_render_params* P, int block_rows, int nparts, int part, int s0, int s1, double* accum, gi_stats* stats)
+{
+    int rc = check_rows_args(ctx, P, block_rows, nparts, part, s0, s1, accum);
+    if (rc != GI_OK) return rc;
+    CK(cudaSetDevice(ctx->device));
+    const RowPlan rp{ block_rows, nparts, part };
+    return render_device(ctx, P, 0, 0, 0, 0, s0, s1, accum, stats, nullptr, &rp);
+}
+extern "C" int gi_render_rows(gi_ctx* ctx, const gi_render_params* P, int block_rows, int nparts, int part, int s0, int s1, double* accum, gi_stats* stats)
+{
+    int rc = check_rows_args(ctx, P, block_rows, nparts, part, s0, s1, accum);
+    if (rc != GI_OK) return rc;
+    CK(cudaSetDevice(ctx->device));
+    const size_t npx = (size_t)rows_of_part(P->height, block_rows, nparts, part) * (size_t)P->width;
+    CK(ctx->b_accum.reserve(npx * 24));
+    const RowPlan rp{ block_rows, nparts, part };
+    rc = render_device(ctx, P, 0, 0, 0, 0, s0, s1, ctx->b_accum.as<double>(), stats, nullptr, &rp);
+    if (rc != GI_OK) return rc;
+    CK(cudaMemcpyAsync(accum, ctx->b_accum.p, npx * 24, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return GI_OK;
+}
+
 extern "C" int gi_render_adaptive_dev(gi_ctx* ctx, const gi_render_params* P, int min_samples, int max_samples, double noise_thresh, int x0, int y0, int x1, int y1, double* color,
                                       uint32_t* samples, gi_stats* stats)
 {
@@ -1569,3 +1670,5 @@ extern "C" int gi_resolve(gi_ctx* ctx, size_t n_pixels, const double* accum, int
     CK(cudaStreamSynchronize(ctx->stream));
     return GI_OK;
 }
+
+#include "gi_comm.inc"

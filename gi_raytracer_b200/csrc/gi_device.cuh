@@ -56,7 +56,9 @@ struct DScene {
     uint32_t n_fog;                  // Octree::at: HeightFog volumes (atmosphere.h), in push_back order
     const gi_fog* fogs;
     const double* fog_grid;          // noise grids of all volumes, concatenated
+    uint32_t* err;                   // sticky device error word (bit 0: a traversal stack overflowed) — read back at every synchronisation
 };
+#define GI_DEV_ERR_STACK 1u
 
 // ---- fp64 vectors in glm's evaluation order -------------------------------------------------------------
 struct d3 { double x, y, z; };
@@ -265,34 +267,35 @@ __device__ __forceinline__ uint32_t children_entry(const DNode& nd, const DRay& 
     return nd.mask & ~miss;
 }
 
-// push the hit children (t0c[i] >= 0) far-to-near, ties with the higher child index first, so that they pop in ascending
-// (entry distance, child index) order — the reference's sorted leaf order (octree.cpp:297-300).
-// Branch-free RANKING instead of a sort: entry distances are >= +0 and a miss is -1, so the raw 64-bit patterns compare like the
-// values with every miss above every hit.  rank(i) = number of children that come before child i in (pattern, index) order —
-// 28 integer comparisons, each settling one pair — and `order` packs the child index of every rank into 4-bit fields.  No
-// double is ever moved: the profile of the insertion-sorted version showed a quarter of the bounce kernel's instructions in
-// its predicated register shuffles (profiles/r01/ncu_full_v8_k_bounce.txt).
-__device__ __forceinline__ void push_children_ordered(const DNode& nd, const double (&t0c)[8], uint32_t hm, uint32_t* stack, int& sp)
+// ---- one interior step -------------------------------------------------------------------------------------------------------------
+// (Measured and dropped in round 2: deriving the <= 4 children a ray can meet as the SEQUENCE of octants along it — sort the three
+//  mid-plane crossings, test the four segments — instead of slab-testing all eight children and ranking them.  It is exact and needs
+//  fewer fp64 comparisons on paper, but fp64 min / max / select are 3-4 instructions each on sm_100 and the computation is one long
+//  dependent chain, where the eight independent slab tests + integer ranking below overlap: closest-hit kernels ran 30-50 % SLOWER
+//  (profiles/r02/README.md, variants v4 / v20 against v21).)
+template <bool IMPL, bool ORDERED>
+__device__ __forceinline__ uint32_t children_general(const DNode* __restrict__ nodes, const DNode& nd, const DRay& r, double tmax0, uint32_t& seq);
+
+// ---- per-thread traversal stack: GI_STACK_MAX node indices in local memory (its top lines stay in L1; a shared-memory stack was
+// measured 5-8 % slower: it shrinks the L1 the node and leaf records live in).  An overflow raises the sticky error word — a plain
+// store of a constant, every writer writes the same bit: an atomicOr here (warp-aggregated REDUX + elected REDG) in the middle of the
+// hottest loop of every traversal kernel cost 40-60 % of their speed even though it never executed.
+struct TStack { uint32_t e[GI_STACK_MAX]; };
+__device__ __forceinline__ void stack_push(TStack& st, int& sp, uint32_t v, uint32_t* err)
 {
-    if (hm == 0) return;
-    // keys: the raw pattern of the entry distance (always >= +0, so patterns order like values) with the sign bit set for a
-    // child that is not hit: it ranks behind every hit
-    unsigned long long key[8];
-#pragma unroll
-    for (int i = 0; i < 8; i++) key[i] = (unsigned long long)__double_as_longlong(t0c[i]) | ((unsigned long long)((~hm >> i) & 1u) << 63);
-    uint32_t rank = 0;   // 4 bits per child
-#pragma unroll
-    for (int i = 0; i < 8; i++)
-#pragma unroll
-        for (int j = i + 1; j < 8; j++) rank += key[j] < key[i] ? (1u << (4 * i)) : (1u << (4 * j));   // ties: the lower index comes first
-    uint32_t order = 0;  // child index of rank r in bits [4r, 4r+3]
-#pragma unroll
-    for (int i = 0; i < 8; i++) order |= (uint32_t)i << (((rank >> (4 * i)) & 15u) * 4u);
-    for (int r = __popc(hm) - 1; r >= 0; r--) {
-        const uint32_t c = (order >> (4 * r)) & 7u;
-        if (sp < GI_STACK_MAX) stack[sp++] = nd.child + __popc(nd.mask & ((1u << c) - 1u));
-    }
+    if (sp < GI_STACK_MAX) st.e[sp++] = v;
+    else *reinterpret_cast<volatile uint32_t*>(err) = GI_DEV_ERR_STACK;
 }
+__device__ __forceinline__ uint32_t stack_pop(TStack& st, int& sp) { return st.e[--sp]; }
+#ifndef GI_BLOCK
+#define GI_BLOCK 128
+#endif
+
+// (Measured and dropped in round 2: a per-ray "mailbox" of the primitives it has already missed — the reference's octree stores a
+//  triangle in every leaf it overlaps, ~45-50 references per triangle in the foliage / atrium stand-ins, and a ray re-tests it in each —
+//  as an 8-entry ring in shared memory looked up before the fp64 test.  Even there the look-ups cost more than the skipped tests saved:
+//  frames 8 % slower on both stand-ins, 2-3 % on caustics / glass; profiles/r02/README.md.)
+#define GI_TSTACK_DECL(name) TStack name
 
 __device__ __forceinline__ DNode load_node(const DNode* nodes, uint32_t i)
 {
@@ -305,6 +308,57 @@ __device__ __forceinline__ DNode load_node(const DNode* nodes, uint32_t i)
     n.child = t.x; n.prim_off = t.y; n.prim_cnt = t.z; n.mask = t.w;
     return n;
 }
+
+
+template <bool IMPL, bool ORDERED>
+__device__ __forceinline__ uint32_t children_general(const DNode* __restrict__ nodes, const DNode& nd, const DRay& r, double tmax0, uint32_t& seq)
+{
+    double t0c[8];
+    uint32_t hm = 0;
+    if (IMPL) hm = children_entry(nd, r, 0.0, tmax0, t0c);
+    else {
+        uint32_t c = nd.child;
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+            t0c[i] = -1.0;
+            if (nd.mask & (1u << i)) {
+                DNode ch = load_node(nodes, c);
+                t0c[i] = box_entry(ch.bmin, ch.bmax, r, 0.0, tmax0);
+                if (t0c[i] >= 0.0) hm |= 1u << i;
+                c++;
+            }
+        }
+    }
+    seq = 0;
+    if (hm == 0) return 0;
+    if (!ORDERED) {   // any-hit: visiting order is free
+        uint32_t n = 0;
+#pragma unroll
+        for (int i = 0; i < 8; i++) if ((hm >> i) & 1u) { seq |= (uint32_t)i << (4 * n); n++; }
+        return n;
+    }
+    // ascending (entry distance, child index) — the reference's sorted leaf order (octree.cpp:297-300) — by RANKING:
+    // entry distances are >= +0, so the raw 64-bit patterns compare like the values; a child that is not hit gets the sign bit and
+    // ranks behind every hit.  rank(i) = number of children before child i: 28 integer comparisons, no double is moved.
+    unsigned long long key[8];
+#pragma unroll
+    for (int i = 0; i < 8; i++) key[i] = (unsigned long long)__double_as_longlong(t0c[i]) | ((unsigned long long)((~hm >> i) & 1u) << 63);
+    uint32_t rank = 0;   // 4 bits per child
+#pragma unroll
+    for (int i = 0; i < 8; i++)
+#pragma unroll
+        for (int j = i + 1; j < 8; j++) rank += key[j] < key[i] ? (1u << (4 * i)) : (1u << (4 * j));   // ties: the lower index comes first
+#pragma unroll
+    for (int i = 0; i < 8; i++) seq |= (uint32_t)i << (((rank >> (4 * i)) & 15u) * 4u);
+    return (uint32_t)__popc(hm);
+}
+// one interior step: the hit children of nd in visiting order (4 bits each in seq), their number returned
+template <bool IMPL, bool ORDERED>
+__device__ __forceinline__ uint32_t interior_step(const DNode* __restrict__ nodes, const DNode& nd, const DRay& r, double tmax0, uint32_t& seq)
+{
+    return children_general<IMPL, ORDERED>(nodes, nd, r, tmax0, seq);
+}
+__device__ __forceinline__ uint32_t child_node(const DNode& nd, uint32_t c) { return nd.child + __popc(nd.mask & ((1u << c) - 1u)); }
 
 // ---- primitives (entities.h) ---------------------------------------------------------------------------------------------
 // triangle::intersect, geometric part (entities.h:443-478): returns t > 0 or -1; u, v barycentrics
@@ -359,21 +413,25 @@ __device__ __forceinline__ d3 vec_mat(d3 v, const double* m)
 {
     return mk3(m[0] * v.x + m[1] * v.y + m[2] * v.z, m[3] * v.x + m[4] * v.y + m[5] * v.z, m[6] * v.x + m[7] * v.y + m[8] * v.z);
 }
-__device__ __noinline__ bool cone_hit(const double* g, const double* rot, const DRay& r, double& t_out, d3& n_out)
+// Out of line (cones are rare): everything goes in and out BY VALUE — a pointer to the caller's geometry registers or ray would force
+// them into local memory for every primitive test of every kernel (the profile of the first version showed exactly that:
+// ten 8-byte local stores per candidate).
+struct ConeHit { double t; d3 n; bool ok; };
+__device__ __noinline__ ConeHit cone_hit_v(d3 pos, double rad, double height, const double* __restrict__ rot, d3 ro, d3 rd)
 {
-    d3 pos = mk3(g[0], g[1], g[2]); double rad = g[3], height = g[4];
-    d3 origin = vec_mat(r.o - pos, rot), dir = vec_mat(r.d, rot);
+    ConeHit H; H.ok = false; H.t = 0; H.n = mk3(0, 0, 0);
+    d3 origin = vec_mat(ro - pos, rot), dir = vec_mat(rd, rot);
     double phiMax = 2 * GI_D_PI;
     double kq = (rad / height) * (rad / height);
     double A = dir.x * dir.x + dir.y * dir.y - kq * dir.z * dir.z;
     double B = 2 * (dir.x * origin.x + dir.y * origin.y - kq * dir.z * (origin.z - height));
     double C = origin.x * origin.x + origin.y * origin.y - kq * (origin.z - height) * (origin.z - height);
     double discrim = B * B - 4.0 * A * C;
-    if (discrim < 0) return false;
+    if (discrim < 0) return H;
     double rootDiscrim = sqrt(discrim);
     double q = (B < 0) ? -.5 * (B - rootDiscrim) : -.5 * (B + rootDiscrim);
     double t_1 = q / A, t_2 = C / q;
-    if (t_1 < 0 && t_2 < 0) return false;
+    if (t_1 < 0 && t_2 < 0) return H;
     if (t_1 > t_2) { double tmp = t_1; t_1 = t_2; t_2 = tmp; }
     double thit = t_1;
     if (t_1 < 0) thit = t_2; else if (t_2 < 0) thit = t_1;
@@ -381,19 +439,25 @@ __device__ __noinline__ bool cone_hit(const double* g, const double* rot, const 
     double phi = atan2(phit.y, phit.x);
     if (phi < 0.) phi += 2.0 * GI_D_PI;
     if (phit.z < 0 || phit.z > height || phi > phiMax) {
-        if (thit == t_2) return false;
+        if (thit == t_2) return H;
         thit = t_2;
         phit = origin + dir * thit;
         phi = atan2(phit.y, phit.x);
         if (phi < 0.) phi += 2.0 * GI_D_PI;
-        if (phit.z < 0 || phit.z > height || phi > phiMax) return false;
+        if (phit.z < 0 || phit.z > height || phi > phiMax) return H;
     }
     double vpar = phit.z / height;
     d3 dpdu = mk3(-phiMax * phit.y, phiMax * phit.x, 0);
     d3 dpdv = mk3(-phit.x / (1.0 - vpar), -phit.y / (1.0 - vpar), height);
-    n_out = normalize3(cross3(dpdu, dpdv));
-    t_out = thit;
-    return true;
+    H.n = normalize3(cross3(dpdu, dpdv));
+    H.t = thit; H.ok = true;
+    return H;
+}
+__device__ __forceinline__ bool cone_hit(const double* g, const double* rot, const DRay& r, double& t_out, d3& n_out)
+{
+    const ConeHit H = cone_hit_v(mk3(g[0], g[1], g[2]), g[3], g[4], rot, r.o, r.d);
+    t_out = H.t; n_out = H.n;
+    return H.ok;
 }
 
 // ---- textures / materials (material.h) -----------------------------------------------------------------------------------
@@ -464,10 +528,10 @@ struct DHit {
 // The walk is resumable: its state is (stack, TraceState, out).  trace_begin tests the root, trace_walk pops leaves until the
 // ray is done (stack empty, or the stop rule fired) — or, with BAIL, until fewer than `min_active` lanes of the warp are still
 // walking (*warp_active, a shared-memory counter each lane decrements when its ray is done), so that a persistent kernel can
-// hand the idle lanes new rays (k_bounce).
+// hand the idle lanes new rays (k_bounce_p).
 struct TraceState { int sp; bool term; double best_d2, cur_tu, cur_tv; };
 
-__device__ __forceinline__ bool trace_begin(const DScene& S, const DRay& r, DHit& out, TraceState& st, uint32_t* stack, uint32_t& n_node)
+__device__ __forceinline__ bool trace_begin(const DScene& S, const DRay& r, DHit& out, TraceState& st, TStack& stack, uint32_t& n_node)
 {
     st.sp = 0; st.term = false; st.best_d2 = 0;
     st.cur_tu = 0; st.cur_tv = 0;   // `uv` local of RayTracer::trace: survives across candidates (raytracer.h:385)
@@ -476,64 +540,60 @@ __device__ __forceinline__ bool trace_begin(const DScene& S, const DRay& r, DHit
     DNode root = load_node(S.nodes, 0);
     n_node++;
     if (box_entry(root.bmin, root.bmax, r, 0.0, CUDART_INF) < 0.0) return false;
-    stack[st.sp++] = 0;
+    stack_push(stack, st.sp, 0u, S.err);
     return true;
 }
 
+// one leaf record: 5 x 16-byte loads through the read-only path
+struct LeafRec { double g[9]; uint32_t prim, flags; };
+__device__ __forceinline__ LeafRec load_leafref(const DLeafRef* refs, uint32_t k)
+{
+    const double2* rp = reinterpret_cast<const double2*>(refs + k);
+    LeafRec L;
+    const double2 a0 = __ldg(rp), a1 = __ldg(rp + 1), a2 = __ldg(rp + 2), a3 = __ldg(rp + 3);
+    const uint4 tail = __ldg(reinterpret_cast<const uint4*>(rp + 4));
+    L.g[0] = a0.x; L.g[1] = a0.y; L.g[2] = a1.x; L.g[3] = a1.y; L.g[4] = a2.x; L.g[5] = a2.y; L.g[6] = a3.x; L.g[7] = a3.y;
+    L.g[8] = __hiloint2double((int)tail.y, (int)tail.x);
+    L.prim = tail.z; L.flags = tail.w;
+    return L;
+}
+
 template <bool FULL, bool IMPL, bool BAIL>
-__device__ __forceinline__ void trace_walk(const DScene& S, const DRay& r, uint64_t seed, uint64_t path, uint64_t depth, DHit& out, TraceState& st, uint32_t* stack, uint32_t& n_node,
-                                           uint32_t& n_prim, volatile int* warp_active = nullptr, int min_active = 0)
+__device__ __forceinline__ void trace_walk(const DScene& S, const DRay& r, uint64_t seed, uint64_t path, uint64_t depth, DHit& out, TraceState& st, TStack& stack,
+                                           uint32_t& n_node, uint32_t& n_prim, volatile int* warp_active = nullptr, int min_active = 0)
 {
     int sp = st.sp;
     bool term = st.term;
     // "while-while": every lane first walks interior nodes until a leaf is on top (the warp re-converges after that
     // inner loop), then all lanes test primitives together — instead of mixing leaf work and interior work in one loop.
     while (sp > 0 && !term) {
-        uint32_t ni = stack[--sp];
+        uint32_t ni = stack_pop(stack, sp);
         DNode nd = load_node(S.nodes, ni);
         bool have_leaf = true;
         while (nd.mask != 0) {
-            // interior: entry distance of every existing child, then push far-to-near (ties: higher child index first,
-            // so that equal-distance children pop in child order)
-            double t0c[8];
-            uint32_t hm = 0;
+            // interior: the hit children in visiting order; the nearest is walked into at once, the others are pushed far-to-near
+            uint32_t seq;
             n_node += __popc(nd.mask);
-            if (IMPL) hm = children_entry(nd, r, 0.0, CUDART_INF, t0c);
-            else {
-                uint32_t c = nd.child;
-#pragma unroll
-                for (int i = 0; i < 8; i++) {
-                    t0c[i] = -1.0;
-                    if (nd.mask & (1u << i)) {
-                        DNode ch = load_node(S.nodes, c);
-                        t0c[i] = box_entry(ch.bmin, ch.bmax, r, 0.0, CUDART_INF);
-                        if (t0c[i] >= 0.0) hm |= 1u << i;
-                        c++;
-                    }
-                }
-            }
-            push_children_ordered(nd, t0c, hm, stack, sp);
-            if (sp == 0) { have_leaf = false; break; }
-            ni = stack[--sp];
+            const uint32_t n = interior_step<IMPL, true>(S.nodes, nd, r, CUDART_INF, seq);
+            for (int j = (int)n - 1; j >= 1; j--) stack_push(stack, sp, child_node(nd, (seq >> (4 * j)) & 7u), S.err);
+            if (n == 0) {
+                if (sp == 0) { have_leaf = false; break; }
+                ni = stack_pop(stack, sp);
+            } else ni = child_node(nd, seq & 7u);
             nd = load_node(S.nodes, ni);
         }
         if (have_leaf) {
             const DLeafRef* refs = S.refs + nd.prim_off;
             n_prim += nd.prim_cnt;
             for (uint32_t k = 0; k < nd.prim_cnt; k++) {
-                const double2* rp = reinterpret_cast<const double2*>(refs + k);
-                double g[9];
-                double2 a0 = __ldg(rp), a1 = __ldg(rp + 1), a2 = __ldg(rp + 2), a3 = __ldg(rp + 3);
-                g[0] = a0.x; g[1] = a0.y; g[2] = a1.x; g[3] = a1.y; g[4] = a2.x; g[5] = a2.y; g[6] = a3.x; g[7] = a3.y;
-                uint4 tail = __ldg(reinterpret_cast<const uint4*>(rp + 4));
-                g[8] = __hiloint2double((int)tail.y, (int)tail.x);
-                uint32_t prim = tail.z, flags = tail.w;
+                const LeafRec L = load_leafref(refs, k);
+                const uint32_t prim = L.prim, flags = L.flags;
                 double t, u = 0, v = 0; d3 cn = mk3(0, 0, 0);
                 bool ok;
                 uint32_t kind = LF_KIND(flags);
-                if (kind == GI_PRIM_TRIANGLE) { t = tri_hit(g, r, u, v); ok = t > 0; }
-                else if (kind == GI_PRIM_SPHERE) ok = sphere_hit(g, r, t);
-                else ok = cone_hit(g, S.prim_nrm + 9 * (size_t)prim, r, t, cn);
+                if (kind == GI_PRIM_TRIANGLE) { t = tri_hit(L.g, r, u, v); ok = t > 0; }
+                else if (kind == GI_PRIM_SPHERE) ok = sphere_hit(L.g, r, t);
+                else ok = cone_hit(L.g, S.prim_nrm + 9 * (size_t)prim, r, t, cn);
                 if (!ok) continue;
                 d3 hit = r.o + r.d * t;
                 if (FULL) {
@@ -559,75 +619,55 @@ __device__ __forceinline__ void trace_walk(const DScene& S, const DRay& r, uint6
 template <bool FULL, bool IMPL>
 __device__ __forceinline__ void trace_closest(const DScene& S, const DRay& r, uint64_t seed, uint64_t path, uint64_t depth, DHit& out, uint32_t& n_node, uint32_t& n_prim)
 {
-    uint32_t stack[GI_STACK_MAX];
+    GI_TSTACK_DECL(stack);
     TraceState st;
     if (trace_begin(S, r, out, st, stack, n_node)) trace_walk<FULL, IMPL, false>(S, r, seed, path, depth, out, st, stack, n_node, n_prim);
 }
 
 // ---- any hit: RayTracer::visible (raytracer.h:280-319) over Octree::Node::intersect (octree.cpp:256-282) -------------------------
 // Returns true when nothing blocks the segment.  Visiting order is free: the alpha draw is keyed by the (leaf, primitive)
-// occurrence, so the outcome equals the reference's first-blocker search for any order.
+// occurrence, so the outcome equals the reference's first-blocker search for any order.  The children met by the segment come
+// from the same interior step as the closest-hit walk (with the segment's tmax), nearest first.
 template <bool FULL, bool IMPL>
 __device__ __forceinline__ bool trace_visible(const DScene& S, const DRay& r, double mt, uint64_t seed, uint64_t path, uint64_t depth, uint64_t light, uint32_t& n_node, uint32_t& n_prim)
 {
     if (S.n_nodes == 0) return true;
     const double tmax = sqrt(mt) - GI_D_SHADOW_BIAS;   // raytracer.h:283
-    uint32_t stack[GI_STACK_MAX];
+    GI_TSTACK_DECL(stack);
     int sp = 0;
     {
         DNode root = load_node(S.nodes, 0);
         n_node++;
         if (box_entry(root.bmin, root.bmax, r, 0.0, tmax) < 0.0) return true;
-        stack[sp++] = 0;
+        stack_push(stack, sp, 0u, S.err);
     }
     while (sp > 0) {
-        uint32_t ni = stack[--sp];
+        uint32_t ni = stack_pop(stack, sp);
         DNode nd = load_node(S.nodes, ni);
         bool have_leaf = true;
         while (nd.mask != 0) {
-            uint32_t c = nd.child;
+            uint32_t seq;
             n_node += __popc(nd.mask);
-            if (IMPL) {
-                double t0c[8];
-                const uint32_t hm = children_entry(nd, r, 0.0, tmax, t0c);   // any-hit needs the mask only: the entry distances are dead code
-#pragma unroll
-                for (int i = 0; i < 8; i++) {
-                    if (nd.mask & (1u << i)) {
-                        if (((hm >> i) & 1u) && sp < GI_STACK_MAX) stack[sp++] = c;
-                        c++;
-                    }
-                }
-            } else {
-#pragma unroll
-                for (int i = 0; i < 8; i++) {
-                    if (nd.mask & (1u << i)) {
-                        DNode ch = load_node(S.nodes, c);
-                        if (box_entry(ch.bmin, ch.bmax, r, 0.0, tmax) >= 0.0 && sp < GI_STACK_MAX) stack[sp++] = c;
-                        c++;
-                    }
-                }
-            }
-            if (sp == 0) { have_leaf = false; break; }
-            ni = stack[--sp];
+            const uint32_t n = interior_step<IMPL, false>(S.nodes, nd, r, tmax, seq);
+            for (int j = (int)n - 1; j >= 1; j--) stack_push(stack, sp, child_node(nd, (seq >> (4 * j)) & 7u), S.err);
+            if (n == 0) {
+                if (sp == 0) { have_leaf = false; break; }
+                ni = stack_pop(stack, sp);
+            } else ni = child_node(nd, seq & 7u);
             nd = load_node(S.nodes, ni);
         }
         if (!have_leaf) break;
         const DLeafRef* refs = S.refs + nd.prim_off;
         for (uint32_t k = 0; k < nd.prim_cnt; k++) {
-            const double2* rp = reinterpret_cast<const double2*>(refs + k);
-            double g[9];
-            double2 a0 = __ldg(rp), a1 = __ldg(rp + 1), a2 = __ldg(rp + 2), a3 = __ldg(rp + 3);
-            g[0] = a0.x; g[1] = a0.y; g[2] = a1.x; g[3] = a1.y; g[4] = a2.x; g[5] = a2.y; g[6] = a3.x; g[7] = a3.y;
-            uint4 tail = __ldg(reinterpret_cast<const uint4*>(rp + 4));
-            g[8] = __hiloint2double((int)tail.y, (int)tail.x);
-            uint32_t prim = tail.z, flags = tail.w;
+            const LeafRec L = load_leafref(refs, k);
+            const uint32_t prim = L.prim, flags = L.flags;
             double t, u = 0, v = 0; d3 cn;
             bool ok;
             n_prim++;
             uint32_t kind = LF_KIND(flags);
-            if (kind == GI_PRIM_TRIANGLE) { t = tri_hit(g, r, u, v); ok = t > 0; }
-            else if (kind == GI_PRIM_SPHERE) ok = sphere_hit(g, r, t);
-            else ok = cone_hit(g, S.prim_nrm + 9 * (size_t)prim, r, t, cn);
+            if (kind == GI_PRIM_TRIANGLE) { t = tri_hit(L.g, r, u, v); ok = t > 0; }
+            else if (kind == GI_PRIM_SPHERE) ok = sphere_hit(L.g, r, t);
+            else ok = cone_hit(L.g, S.prim_nrm + 9 * (size_t)prim, r, t, cn);
             if (!ok) continue;
             d3 pos = r.o + r.d * t;
             if (FULL && (flags & LF_ALPHA)) {
@@ -728,7 +768,7 @@ __device__ __forceinline__ void trace_closest_warp(const DScene& S, const DRay& 
         }
         if (t0 >= 0.0 && sp + rank < GI_STACK_MAX) stack[sp + rank] = cidx;
         sp += __popc(valid);
-        if (sp > GI_STACK_MAX) sp = GI_STACK_MAX;
+        if (sp > GI_STACK_MAX) { sp = GI_STACK_MAX; if (lane == 0) atomicOr(S.err, GI_DEV_ERR_STACK); }
         __syncwarp();
     }
 }
@@ -798,7 +838,7 @@ __device__ __forceinline__ bool trace_visible_warp(const DScene& S, const DRay& 
         uint32_t valid = __ballot_sync(0xffffffffu, in) & 0xffu;
         if (in) { int pos = sp + __popc(valid & ((1u << lane) - 1u)); if (pos < GI_STACK_MAX) stack[pos] = cidx; }
         sp += __popc(valid);
-        if (sp > GI_STACK_MAX) sp = GI_STACK_MAX;
+        if (sp > GI_STACK_MAX) { sp = GI_STACK_MAX; if (lane == 0) atomicOr(S.err, GI_DEV_ERR_STACK); }
         __syncwarp();
     }
     return true;

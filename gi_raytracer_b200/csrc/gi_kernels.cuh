@@ -5,12 +5,11 @@
 
 #include "gi_device.cuh"
 
-#ifndef GI_BLOCK
-#define GI_BLOCK 128
-#endif
 #ifndef GI_MINB
-#define GI_MINB 6   // resident blocks of 128 threads per SM asked of ptxas for the thread-per-ray traversal kernels: 80 registers.
-#endif              // measured on the C2 frame (bounce + direct ms): 1-3 blocks (136-142 regs) 23.1, 4 (128) 19.4, 5 (96) 18.8, 6 (80) 17.9, 8 (64) 19.1
+#define GI_MINB 8   // resident blocks of 128 threads per SM asked of ptxas for the thread-per-ray traversal kernels: 64 registers.
+#endif              // round 1 (C2 bounce + direct ms): 1-3 blocks (136-142 regs) 23.1, 4 (128) 19.4, 5 (96) 18.8, 6 (80) 17.9, 8 (64) 19.1; round 2, after the
+                    // by-value cone test and the later T / contrib loads took pressure off the walk: 8 beats 6 on every config (C2 frame 24.7 vs 25.2 ms,
+                    // glass 49.4 vs 51.6, foliage 488 vs 512, atrium 461 vs 472; profiles/r02/ab_t7.txt)
 #define GI_PM_LEAF_MAX 16   // MAX_PHOTONS_PER_LEAF (util.h:15)
 
 // ---- K0: Halton known-answer entry points -----------------------------------------------------------------------------------
@@ -65,7 +64,10 @@ __global__ void k_material_eval(DScene S, size_t n, const uint32_t* __restrict__
 }
 
 // ---- K1: camera rays (raytracer.h:74-78, 112-129) ------------------------------------------------------------------------------
-struct DFrame { int w, h, x0, y0, tw, th; double halfW, halfH; d3 center, right, up, pos; DHEnum he; };
+// tile = local pixel space tw x th.  A rectangle maps local row ly to image row y0 + ly; the tile split's row plan (blocks of `rb`
+// rows every `rstride` rows, gi_render_rows) maps it to y0 + (ly / rb) * rstride + ly % rb.  rb = 0 means a plain rectangle.
+struct DFrame { int w, h, x0, y0, tw, th, rb, rstride; double halfW, halfH; d3 center, right, up, pos; DHEnum he; };
+__device__ __forceinline__ int frame_row(const DFrame& F, int ly) { return F.rb ? F.y0 + (ly / F.rb) * F.rstride + ly % F.rb : F.y0 + ly; }
 
 __device__ __forceinline__ DRay camera_ray(const DScene& S, const DFrame& F, int x, int y, int s, uint32_t& idx_out)
 {
@@ -87,7 +89,7 @@ __global__ void k_camera_rays(DScene S, DFrame F, int s0, size_t n, double* org,
     size_t npx = (size_t)F.tw * F.th;
     int s = s0 + (int)(i / npx);
     size_t p = i % npx;
-    int y = F.y0 + (int)(p / F.tw), x = F.x0 + (int)(p % F.tw);
+    int y = frame_row(F, (int)(p / F.tw)), x = F.x0 + (int)(p % F.tw);
     uint32_t idx;
     DRay r = camera_ray(S, F, x, y, s, idx);
     st3(org + 3 * i, r.o); st3(dir + 3 * i, r.d);
@@ -985,11 +987,11 @@ __global__ void __launch_bounds__(GI_BLOCK, GI_MINB) k_bounce(DScene S, gi_rende
     if (active) {
         path = in.path[i];
         DRay r = ray_as_stored(ld3(in.o + 3 * (size_t)i), ld3(in.d + 3 * (size_t)i));
-        d3 T = ld3(in.T + 3 * (size_t)i);
-        contrib = ld3(in.contrib + 3 * (size_t)i);
         uint64_t key = PS.key[path];
         DHit h;
         trace_closest<FULL, IMPL>(S, r, P.seed, key, (uint64_t)depth, h, wn, wp);  // :190
+        d3 T = ld3(in.T + 3 * (size_t)i);               // read after the walk: twelve registers less across it
+        contrib = ld3(in.contrib + 3 * (size_t)i);
         double* L = PS.L + 3 * (size_t)path;
         if (h.prim == GI_NO_HIT) {
             d3 a = T * ld3(S.ambient);                                       // :275
@@ -1066,7 +1068,7 @@ __global__ void __launch_bounds__(GI_BLOCK, GI_MINB) k_bounce_p(DScene S, gi_ren
     __shared__ int s_walking[GI_BLOCK / 32];
     const unsigned lane = threadIdx.x & 31u;
     const int wib = threadIdx.x >> 5;
-    uint32_t stack[GI_STACK_MAX];
+    GI_TSTACK_DECL(stack);
     TraceState st; st.sp = 0; st.term = false; st.best_d2 = 0; st.cur_tu = 0; st.cur_tv = 0;
     DHit h; h.prim = GI_NO_HIT;
     DRay r = ray_as_stored(mk3(0, 0, 0), mk3(1, 0, 0));
@@ -1418,7 +1420,7 @@ __global__ void k_generate(DScene S, DFrame F, int s0, uint64_t c0, uint32_t n, 
     size_t slot = lin % npx;
     int lx, ly;
     slot_to_pixel(slot, F.tw, F.th, lx, ly);
-    int y = F.y0 + ly, x = F.x0 + lx;
+    int y = frame_row(F, ly), x = F.x0 + lx;
     uint32_t idx;
     DRay r = camera_ray(S, F, x, y, s, idx);
     st3(q.o + 3 * (size_t)i, r.o); st3(q.d + 3 * (size_t)i, r.d);
@@ -1462,7 +1464,7 @@ __global__ void k_generate_list(DScene S, DFrame F, int s, uint32_t n, const uin
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const uint32_t pix = list[i];
-    int y = F.y0 + (int)(pix / F.tw), x = F.x0 + (int)(pix % F.tw);
+    int y = frame_row(F, (int)(pix / F.tw)), x = F.x0 + (int)(pix % F.tw);
     uint32_t idx;
     DRay r = camera_ray(S, F, x, y, s, idx);
     st3(q.o + 3 * (size_t)i, r.o); st3(q.d + 3 * (size_t)i, r.d);

@@ -353,18 +353,26 @@ class RayTracer {  // raytracer.h:23-735
     int max_depth = 64, min_depth = 2;
     uint64_t seed = 1;
     int device = 0;
+    // New (the reference is one process on one machine's CPU cores): gpus > 1 splits a fixed-sample frame over the devices device ..
+    // device + gpus - 1 — interleaved 16-row blocks per GPU (gi_render_rows_image), the photon map built once on the first and broadcast,
+    // the 8-bit rows gathered there (NCCL from the C ABI).  The pixels are those of the one-GPU frame, bit for bit.
+    int gpus = 1;
     gi_stats last_frame_stats{}, last_photon_stats{};
     double last_photon_ms = 0, last_frame_ms = 0;
     gi_ctx* context();                  // lazily created gi_ctx on `device`
+    int run_multi(int w, int h);        // run() when gpus > 1 (fixed sample counts; adaptive sampling stays on one GPU)
 
   private:
     std::atomic<bool> _running{ false };
     std::atomic<int> _rows_done{ 0 };
     Octree* _scene = nullptr;
-    PhotonMap* _photon_map = nullptr;
+    std::shared_ptr<PhotonMap> _photon_map;   // shared by copies of the tracer (the reference shares a raw pointer it never frees)
     std::shared_ptr<Image> _image;
-    gi_ctx* _ctx = nullptr;
-    bool _uploaded = false;
+    std::atomic<gi_ctx*> _ctx{ nullptr };      // read by stop() / start() from other threads
+    bool _uploaded = false;                     // this tracer's context holds the scene
+    bool _map_in_ctx = false;                   // ... and the photon map (validity is per context: a copy has its own)
+    std::vector<gi_ctx*> _peers;                // contexts on the other GPUs of a multi-GPU run (owned; communicator rank = index + 1)
+    bool _peers_have_scene = false;
 };
 
 // PNG without Qt (gi_png.cpp): 8-bit RGBA rows top first, has_alpha as QImage::hasAlphaChannel reports it

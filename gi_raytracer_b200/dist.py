@@ -1,8 +1,11 @@
-"""Multi-GPU plumbing: one process per GPU, torch.distributed over NCCL/NVLink (gloo on CPU for the tests).
+"""Multi-GPU plumbing: one process per GPU.
 
 The path shards without a data-path collective (pixels, samples and photons are independent).  Only two
 exchanges exist: the photon map is built once on the root rank and broadcast as one slab, and the per-rank framebuffer
-partial sums are reduced (sample split) or gathered (tile split) at the end of a frame."""
+partial sums are reduced (sample split) or gathered (tile split) at the end of a frame.  On GPUs both are the C ABI's own
+NCCL calls (gi_comm_init / gi_photon_map_bcast / gi_framebuffer_reduce / gi_framebuffer_gather, csrc/gi_comm.inc); torch.distributed
+only carries the 128-byte communicator id between the processes (init_comm).  The torch.distributed forms of the same protocols
+(broadcast_slab, reduce_accum, gather_rows) remain for the world-2 gloo tests on CPU."""
 import numpy as np
 import torch
 import torch.distributed as dist
@@ -33,6 +36,16 @@ def row_blocks(height, world, block=16):
     return out
 
 
+def init_comm(ctx, rank, world, device):
+    """gi_comm_init on every rank: rank 0 makes the NCCL unique id (gi_comm_unique_id), torch.distributed carries its 128 bytes."""
+    from . import capi
+    buf = torch.zeros(128, dtype=torch.uint8, device=device)
+    if rank == 0:
+        buf.copy_(torch.frombuffer(bytearray(capi.comm_unique_id()), dtype=torch.uint8))
+    dist.broadcast(buf, src=0)
+    ctx.comm_init(bytes(buf.cpu().numpy().tobytes()), rank, world)
+
+
 def broadcast_slab(make_root_slab, reserve, adopt, rank, root, device):
     """Broadcast a photon-map slab.  make_root_slab() -> (ptr, nbytes) on the root; reserve(nbytes) -> ptr and
     adopt(nbytes) on the others.  Pointers are device pointers (or torch CPU uint8 tensors under gloo)."""
@@ -53,8 +66,14 @@ def broadcast_slab(make_root_slab, reserve, adopt, rank, root, device):
 
 
 def share_photon_map(ctx, rank, world, root=0):
-    """Root has a built map; every other rank receives it over NCCL and adopts it."""
+    """Root has a built map; every other rank receives it over NCCL and adopts it.  With a gi_comm on the context this is the C ABI's
+    own gi_photon_map_bcast; the torch.distributed form below is what the gloo tests drive."""
     if world == 1:
+        return ctx.photon_map_slab()[1]
+    if ctx.comm_info()["nranks"] == world:
+        ctx.synchronize()
+        ctx.photon_map_bcast(root)
+        ctx.synchronize()
         return ctx.photon_map_slab()[1]
     device = torch.device("cuda", ctx.device)
     ctx.synchronize()

@@ -289,6 +289,14 @@ int gi_render_tile_dev(gi_ctx* ctx, const gi_render_params* p, int x0, int y0, i
 int gi_render_image(gi_ctx* ctx, const gi_render_params* p, int x0, int y0, int x1, int y1, int s0, int s1, uint8_t* rgb8,
                     double* accum, gi_stats* stats);
 /* ---- resolve: mean -> gamma 2.2 -> clamp -> (int)(255*c)  (raytracer.h:150-156, util.h:94-97, image.h:14-16) */
+/* ---- tile split of the frame (the loop being split is the row loop of RayTracer::run, raytracer.h:93-160, whose rows the
+ *      reference hands to its threads `schedule(dynamic, 10)`): part `part` of `nparts` owns the row blocks part, part + nparts, ..
+ *      of block_rows rows each.  gi_rows_of_part = how many rows that is (or GI_ERR_INVALID); gi_render_rows renders them in ONE
+ *      wavefront into accum [local rows][width][3] (compact, block after block) — the same pixels, bit for bit, as the one-GPU frame. */
+int gi_rows_of_part(int height, int block_rows, int nparts, int part);
+int gi_render_rows(gi_ctx* ctx, const gi_render_params* p, int block_rows, int nparts, int part, int s0, int s1, double* accum, gi_stats* stats);
+int gi_render_rows_dev(gi_ctx* ctx, const gi_render_params* p, int block_rows, int nparts, int part, int s0, int s1, double* accum, gi_stats* stats);
+
 /* Adaptive sampling: the per-pixel loop of RayTracer::run (raytracer.h:100-148) with `samples min max thresh`.  Every pixel
  * of the tile takes samples s = 0, 1, .. while s < max_samples && samps < min_samples (samps +1 per sample, -2 when the
  * smoothed change of the running mean stays above noise_thresh).  color[n_pixels][3] receives the final running-mean colour
@@ -299,6 +307,29 @@ int gi_render_adaptive_dev(gi_ctx* ctx, const gi_render_params* p, int min_sampl
                            double* color, uint32_t* samples, gi_stats* stats);
 int gi_resolve(gi_ctx* ctx, size_t n_pixels, const double* accum, int spp, uint8_t* rgb8);
 int gi_resolve_dev(gi_ctx* ctx, size_t n_pixels, const double* accum, int spp, uint8_t* rgb8);
+
+/* ---- multi-GPU (new; the reference is a single process): one gi_ctx per GPU, NCCL over NVLink bound at run time (dlopen), used only
+ *      for the two exchanges the path has — the photon map "built once and broadcast" (the reference builds it once per scene,
+ *      raytracer.h:61-71) and the framebuffer at the end of a frame.  Everything runs on gi_stream(ctx).
+ *      gi_comm_unique_id: 128 bytes made on one rank (ncclGetUniqueId); the caller hands them to the others (file, socket, MPI,
+ *        torch.distributed, a shared variable between threads);
+ *      gi_comm_init: collective over the nranks contexts (ncclCommInitRank); one communicator per ctx;
+ *      gi_photon_map_bcast: the root's built map (one slab) to every rank, adopted after its header is validated;
+ *      gi_framebuffer_reduce: sample split — fp64 partial sums (count doubles, device pointer) added onto the root, in place;
+ *      gi_framebuffer_gather: tile split — each rank's compact rows (gi_render_rows' plan; row_bytes per image row: 3 * width for the
+ *        resolved 8-bit image, 24 * width for the fp64 sums; device pointers) into the root's frame [height][row_bytes]. ------------ */
+#define GI_COMM_ID_BYTES 128
+int gi_comm_unique_id(void* id, size_t bytes);
+int gi_comm_init(gi_ctx* ctx, const void* id, size_t bytes, int rank, int nranks);
+int gi_comm_destroy(gi_ctx* ctx);
+int gi_comm_info(gi_ctx* ctx, int* rank, int* nranks, int* nccl_version);
+int gi_photon_map_bcast(gi_ctx* ctx, int root);
+int gi_framebuffer_reduce(gi_ctx* ctx, double* accum_dev, size_t count, int root);
+int gi_framebuffer_gather(gi_ctx* ctx, const void* local_dev, size_t row_bytes, int height, int block_rows, void* frame_dev, int root);
+/* the tile split as one call per rank (RayTracer::run with several GPUs): render this context's rows (part = its rank in its communicator;
+ * no communicator = the whole frame), resolve them on the device, gather the 8-bit rows on `root`, copy the frame to the root's HOST
+ * buffer rgb8 [height][width][3] (ignored elsewhere).  Collective over the communicator. */
+int gi_render_rows_image(gi_ctx* ctx, const gi_render_params* p, int block_rows, int s0, int s1, uint8_t* rgb8, int root, gi_stats* stats);
 
 /* ---- kernel-level hooks for bench.py's roofline (device buffers owned by the ctx) -------------------------- */
 /* average duration (ms) of the last launches of the named kernel family, measured with CUDA events on gi_stream */

@@ -11,7 +11,7 @@ import tempfile
 from collections import defaultdict
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-LIB = os.path.join(ROOT, "gi_raytracer_b200", "libgi_b200.so")
+LIB = os.environ.get("GI_LIB") or os.path.join(ROOT, "gi_raytracer_b200", "libgi_b200.so")   # the library the profiled run loaded
 
 
 def line_map(sym):

@@ -629,3 +629,32 @@ def test_large_configs_tiles_compose_at_full_size(ctx, name, w, h, spp, photons,
     assert bits_equal(up.reshape(rows, w, 3), full.reshape(h, w, 3)[:rows].copy())
     for f in ("closest_rays", "shadow_rays", "gathers", "closest_node_tests", "closest_prim_tests", "shadow_node_tests", "shadow_prim_tests"):
         assert getattr(s_up, f) + getattr(s_low, f) == getattr(st, f), f
+
+
+def test_row_plan_parts_compose_to_the_frame(ctx, synth_dir):
+    """gi_render_rows (tile split): the interleaved row blocks of every part, put back at their rows, are the one-call
+    frame bit for bit — for part counts that do and do not divide the block count, and a frame height that is not a multiple of the
+    block size."""
+    sc = _load("mixed", synth_dir)
+    ctx.upload_scene(sc)
+    ctx.photon_trace(3000, 5, seed=2)
+    ctx.photon_map_build(None)
+    w, h, spp, block = 96, 77, 3, 16
+    P = render_params(w, h, spp, max_depth=6, seed=8)
+    full, st = ctx.render_tile(P, 0, 0, w, h, 0, spp)
+    full = full.reshape(h, w, 3)
+    for nparts in (1, 2, 3, 5, 8):
+        frame = np.full((h, w, 3), np.nan)
+        rays = 0
+        for part in range(nparts):
+            if part * block >= h:
+                with pytest.raises(Exception):
+                    ctx.render_rows(P, block, nparts, part, 0, spp)   # an empty part is refused, not rendered as nothing
+                continue
+            acc, ps = ctx.render_rows(P, block, nparts, part, 0, spp)
+            rows = [y for b in range(part, (h + block - 1) // block, nparts) for y in range(b * block, min(h, (b + 1) * block))]
+            assert acc.shape[0] == len(rows) * w == ctx.rows_of_part(h, block, nparts, part) * w
+            frame[rows] = acc.reshape(len(rows), w, 3)
+            rays += ps.closest_rays + ps.shadow_rays
+        assert bits_equal(frame, full), nparts
+        assert rays == st.closest_rays + st.shadow_rays
