@@ -24,7 +24,8 @@ API_SYMBOLS = [
     "gi_photon_gather_dev", "gi_render_tile", "gi_render_tile_dev", "gi_resolve", "gi_resolve_dev", "gi_last_kernel_ms",
     "gi_last_work", "gi_scene_info", "gi_render_adaptive", "gi_render_adaptive_dev", "gi_fog_density", "gi_raymarch", "gi_octree_build", "gi_octree_download", "gi_cancel", "gi_render_image", "gi_configure", "gi_material_eval",
     "gi_rows_of_part", "gi_render_rows", "gi_render_rows_dev", "gi_comm_unique_id", "gi_comm_init", "gi_comm_destroy", "gi_comm_info", "gi_photon_map_bcast",
-    "gi_framebuffer_reduce", "gi_framebuffer_gather", "gi_render_rows_image",
+    "gi_framebuffer_reduce", "gi_framebuffer_gather", "gi_render_rows_image", "gi_octree_intersect", "gi_octree_intersect_sorted", "gi_photon_in_range",
+    "gi_prim_intersect",
 ]
 
 _LIB = None
@@ -94,6 +95,11 @@ def load_library():
     sig("gi_framebuffer_reduce", [vp, vp, sz, i32])
     sig("gi_framebuffer_gather", [vp, vp, sz, i32, i32, vp, i32])
     sig("gi_render_rows_image", [vp, C.POINTER(GiRenderParams), i32, i32, i32, vp, i32, C.POINTER(GiStats)])
+    L.gi_raymarch.argtypes = [vp, sz, vp, vp, vp, u64, i32, vp, vp, vp, vp, vp]
+    sig("gi_octree_intersect", [vp, sz, vp, vp, vp, vp, u32, vp, vp])
+    sig("gi_octree_intersect_sorted", [vp, sz, vp, vp, vp, vp, u32, vp, vp, vp])
+    sig("gi_photon_in_range", [vp, sz, vp, u32, vp, vp])
+    sig("gi_prim_intersect", [vp, sz, vp, vp, vp, vp, vp, vp, vp, vp])
     L.gi_octree_build.argtypes = [vp, u32, vp, vp, vp, vp, C.POINTER(u32), C.POINTER(u32), C.POINTER(C.c_double)]
     L.gi_octree_download.argtypes = [vp, vp, vp, vp, vp, vp, vp]
     L.gih_scene_prim_bbox.argtypes = [vp, vp]
@@ -248,6 +254,49 @@ class Context:
         dif, em, alpha = np.empty((n, 3)), np.empty((n, 3)), np.empty(n)
         self._ck(self.L.gi_material_eval(self.h, n, _p(prim), _p(uv), _p(dif), _p(em), _p(alpha)))
         return dif, em, alpha
+
+    # -- the reference's scene-API queries, batch forms -----------------------------------------------------------------------------
+    def octree_intersect(self, org, d, tmin, tmax, cap=256):
+        """Octree::intersect -> (prim ids [n, cap] (valid up to min(count, cap)), counts [n])."""
+        org, d = _f64(org, 3), _f64(d, 3)
+        n = org.shape[0]
+        tmin = np.ascontiguousarray(np.broadcast_to(np.asarray(tmin, dtype=np.float64), (n,)))
+        tmax = np.ascontiguousarray(np.broadcast_to(np.asarray(tmax, dtype=np.float64), (n,)))
+        ids = np.full((n, cap), 0xFFFFFFFF, dtype=np.uint32)
+        cnt = np.zeros(n, dtype=np.uint32)
+        self._ck(self.L.gi_octree_intersect(self.h, n, _p(org), _p(d), _p(tmin), _p(tmax), cap, _p(ids), _p(cnt)))
+        return ids, cnt
+
+    def octree_intersect_sorted(self, org, d, tmin, tmax, cap=64):
+        """Octree::intersectSorted -> (flattened node ids [n, cap], entry distances [n, cap], counts [n])."""
+        org, d = _f64(org, 3), _f64(d, 3)
+        n = org.shape[0]
+        tmin = np.ascontiguousarray(np.broadcast_to(np.asarray(tmin, dtype=np.float64), (n,)))
+        tmax = np.ascontiguousarray(np.broadcast_to(np.asarray(tmax, dtype=np.float64), (n,)))
+        nodes = np.full((n, cap), 0xFFFFFFFF, dtype=np.uint32)
+        t0 = np.zeros((n, cap))
+        cnt = np.zeros(n, dtype=np.uint32)
+        self._ck(self.L.gi_octree_intersect_sorted(self.h, n, _p(org), _p(d), _p(tmin), _p(tmax), cap, _p(nodes), _p(t0), _p(cnt)))
+        return nodes, t0, cnt
+
+    def photon_in_range(self, pos, cap=512):
+        """PhotonMap::getInRange -> (original photon ids [n, cap], counts [n])."""
+        pos = _f64(pos, 3)
+        n = pos.shape[0]
+        ids = np.full((n, cap), 0xFFFFFFFF, dtype=np.uint32)
+        cnt = np.zeros(n, dtype=np.uint32)
+        self._ck(self.L.gi_photon_in_range(self.h, n, _p(pos), cap, _p(ids), _p(cnt)))
+        return ids, cnt
+
+    def prim_intersect(self, prim, org, d):
+        """Entity::intersect of primitive prim[i] with ray i -> (ok, hit, normal, uv, wrote_uv)."""
+        prim = np.ascontiguousarray(prim, dtype=np.uint32).ravel()
+        org, d = _f64(org, 3), _f64(d, 3)
+        n = prim.size
+        ok, wrote = np.zeros(n, dtype=np.uint8), np.zeros(n, dtype=np.uint8)
+        hit, nrm, uv = np.zeros((n, 3)), np.zeros((n, 3)), np.zeros((n, 2))
+        self._ck(self.L.gi_prim_intersect(self.h, n, _p(prim), _p(org), _p(d), _p(ok), _p(hit), _p(nrm), _p(uv), _p(wrote)))
+        return ok, hit, nrm, uv, wrote
 
     def fog_density(self, pos):
         """Octree::atmosphereDensity at points -> (density incl. the step-size factor, colour of the last containing volume)."""

@@ -14,6 +14,7 @@
 
 #include "gi_kernels.cuh"
 #include "gi_octree_build.cuh"
+#include "gi_query.cuh"
 
 #define GI_VERSION "gi_b200 0.1.0 (sm_100a)"
 #define GI_MAX_PATHS (1u << 23)   // paths in flight per chunk of the wavefront
@@ -1669,6 +1670,92 @@ extern "C" int gi_resolve(gi_ctx* ctx, size_t n_pixels, const double* accum, int
     CK(cudaMemcpyAsync(rgb8, ctx->w1.p, n_pixels * 3, cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
     return GI_OK;
+}
+
+// ---- scene-API queries, batch forms (host pointers; gi_query.cuh) ---------------------------------------------------------------------------
+static int upload_rays(gi_ctx* ctx, size_t n, const double* org, const double* dir, const double* tmin, const double* tmax)
+{
+    CK(ctx->w0.reserve(n * 24)); CK(ctx->w1.reserve(n * 24)); CK(ctx->w2.reserve(n * 8)); CK(ctx->w3.reserve(n * 8));
+    CK(cudaMemcpyAsync(ctx->w0.p, org, n * 24, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->w1.p, dir, n * 24, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->w2.p, tmin, n * 8, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->w3.p, tmax, n * 8, cudaMemcpyHostToDevice, ctx->stream));
+    return GI_OK;
+}
+extern "C" int gi_octree_intersect(gi_ctx* ctx, size_t n, const double* org, const double* dir, const double* tmin, const double* tmax, uint32_t cap, uint32_t* prim_ids, uint32_t* counts)
+{
+    if (!ctx || (n && (!org || !dir || !tmin || !tmax || !counts || (cap && !prim_ids)))) return GI_ERR_INVALID;
+    if (!ctx->has_scene) return fail(ctx, GI_ERR_NO_SCENE, "gi_octree_intersect needs gi_scene_upload");
+    if (!n) return GI_OK;
+    CK(cudaSetDevice(ctx->device));
+    int rc = upload_rays(ctx, n, org, dir, tmin, tmax);
+    if (rc != GI_OK) return rc;
+    CK(ctx->w4.reserve(std::max<size_t>(n * cap, 1) * 4)); CK(ctx->w5.reserve(n * 4));
+    k_octree_intersect<<<grid_for(n, 128), 128, 0, ctx->stream>>>(ctx->S, n, ctx->w0.as<double>(), ctx->w1.as<double>(), ctx->w2.as<double>(), ctx->w3.as<double>(), cap, ctx->w4.as<uint32_t>(),
+                                                                 ctx->w5.as<uint32_t>());
+    CK(cudaGetLastError());
+    if (cap) CK(cudaMemcpyAsync(prim_ids, ctx->w4.p, n * cap * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaMemcpyAsync(counts, ctx->w5.p, n * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    return gi_synchronize(ctx);
+}
+extern "C" int gi_octree_intersect_sorted(gi_ctx* ctx, size_t n, const double* org, const double* dir, const double* tmin, const double* tmax, uint32_t cap, uint32_t* node_ids, double* t0,
+                                          uint32_t* counts)
+{
+    if (!ctx || (n && (!org || !dir || !tmin || !tmax || !counts || !cap || !node_ids || !t0))) return GI_ERR_INVALID;
+    if (!ctx->has_scene) return fail(ctx, GI_ERR_NO_SCENE, "gi_octree_intersect_sorted needs gi_scene_upload");
+    if (!n) return GI_OK;
+    CK(cudaSetDevice(ctx->device));
+    int rc = upload_rays(ctx, n, org, dir, tmin, tmax);
+    if (rc != GI_OK) return rc;
+    CK(ctx->w4.reserve(n * cap * 4)); CK(ctx->w5.reserve(n * 4)); CK(ctx->w6.reserve(n * cap * 8));
+    k_octree_intersect_sorted<<<grid_for(n, 128), 128, 0, ctx->stream>>>(ctx->S, n, ctx->w0.as<double>(), ctx->w1.as<double>(), ctx->w2.as<double>(), ctx->w3.as<double>(), cap,
+                                                                        ctx->w4.as<uint32_t>(), ctx->w6.as<double>(), ctx->w5.as<uint32_t>());
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(node_ids, ctx->w4.p, n * cap * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaMemcpyAsync(t0, ctx->w6.p, n * cap * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaMemcpyAsync(counts, ctx->w5.p, n * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    return gi_synchronize(ctx);
+}
+extern "C" int gi_photon_in_range(gi_ctx* ctx, size_t n, const double* pos, uint32_t cap, uint32_t* photon_ids, uint32_t* counts)
+{
+    if (!ctx || (n && (!pos || !counts || (cap && !photon_ids)))) return GI_ERR_INVALID;
+    if (!ctx->has_map) return fail(ctx, GI_ERR_NO_PHOTONS, "gi_photon_in_range needs gi_photon_map_build");
+    if (!n) return GI_OK;
+    CK(cudaSetDevice(ctx->device));
+    CK(ctx->w0.reserve(n * 24)); CK(ctx->w4.reserve(std::max<size_t>(n * cap, 1) * 4)); CK(ctx->w5.reserve(n * 4)); CK(ctx->w3.reserve(16));
+    CK(cudaMemcpyAsync(ctx->w0.p, pos, n * 24, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemsetAsync(ctx->w3.p, 0, 4, ctx->stream));
+    k_photon_in_range<<<grid_for(n, GI_WPB), GI_WPB * 32, 0, ctx->stream>>>(ctx->G, n, ctx->w0.as<double>(), cap, ctx->w4.as<uint32_t>(), ctx->w5.as<uint32_t>(), ctx->w3.as<uint32_t>());
+    CK(cudaGetLastError());
+    uint32_t ovf = 0;
+    if (cap) CK(cudaMemcpyAsync(photon_ids, ctx->w4.p, n * cap * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaMemcpyAsync(counts, ctx->w5.p, n * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaMemcpyAsync(&ovf, ctx->w3.p, 4, cudaMemcpyDeviceToHost, ctx->stream));
+    int rc = gi_synchronize(ctx);
+    if (rc != GI_OK) return rc;
+    if (ovf) return fail(ctx, GI_ERR_INVALID, "photon map too deep for the candidate walk");
+    return GI_OK;
+}
+extern "C" int gi_prim_intersect(gi_ctx* ctx, size_t n, const uint32_t* prim, const double* org, const double* dir, uint8_t* ok, double* hit, double* normal, double* uv, uint8_t* wrote_uv)
+{
+    if (!ctx || (n && (!prim || !org || !dir || !ok || !hit || !normal || !uv || !wrote_uv))) return GI_ERR_INVALID;
+    if (!ctx->has_scene) return fail(ctx, GI_ERR_NO_SCENE, "gi_prim_intersect needs gi_scene_upload");
+    if (!n) return GI_OK;
+    CK(cudaSetDevice(ctx->device));
+    CK(ctx->w0.reserve(n * 24)); CK(ctx->w1.reserve(n * 24)); CK(ctx->w2.reserve(n * 4)); CK(ctx->w3.reserve(n * 2)); CK(ctx->w4.reserve(n * 24)); CK(ctx->w5.reserve(n * 24)); CK(ctx->w6.reserve(n * 16));
+    CK(cudaMemcpyAsync(ctx->w0.p, org, n * 24, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->w1.p, dir, n * 24, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->w2.p, prim, n * 4, cudaMemcpyHostToDevice, ctx->stream));
+    uint8_t* flags = ctx->w3.as<uint8_t>();
+    k_prim_intersect<<<grid_for(n, 128), 128, 0, ctx->stream>>>(ctx->S, n, ctx->w2.as<uint32_t>(), ctx->w0.as<double>(), ctx->w1.as<double>(), flags, ctx->w4.as<double>(), ctx->w5.as<double>(),
+                                                               ctx->w6.as<double>(), flags + n);
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(ok, flags, n, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaMemcpyAsync(wrote_uv, flags + n, n, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaMemcpyAsync(hit, ctx->w4.p, n * 24, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaMemcpyAsync(normal, ctx->w5.p, n * 24, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaMemcpyAsync(uv, ctx->w6.p, n * 16, cudaMemcpyDeviceToHost, ctx->stream));
+    return gi_synchronize(ctx);
 }
 
 #include "gi_comm.inc"

@@ -148,7 +148,30 @@ void PhotonMap::rebuild(gi_ctx* ctx)  // photonMap.cpp:33-47
         if (gi_photon_upload(ctx, staged.size(), buf.data()) != GI_OK) return;
     }
     double box[6] = { min.x, min.y, min.z, max.x, max.y, max.z };
-    if (gi_photon_map_build(ctx, box) == GI_OK) valid = true;
+    if (gi_photon_map_build(ctx, box) == GI_OK) { valid = true; _ctx = ctx; _host.clear(); }
+}
+
+std::vector<Photon*> PhotonMap::getInRange(gi::dvec3& pos, double& scale, double dist) const   // photonMap.cpp:50-68 (scale / dist are unused there too)
+{
+    (void)scale; (void)dist;
+    std::vector<Photon*> res;
+    if (!valid || !_ctx) return res;
+    if (_host.empty()) {
+        size_t n = 0;
+        if (gi_photon_count(_ctx, &n) != GI_OK || !n) return res;
+        std::vector<double> buf(n * 9);
+        if (gi_photon_download(_ctx, n, buf.data()) != GI_OK) return res;
+        _host.reserve(n);
+        for (size_t i = 0; i < n; i++) { const double* p = &buf[9 * i]; _host.emplace_back(gi::dvec3(p[0], p[1], p[2]), gi::dvec3(p[3], p[4], p[5]), gi::dvec3(p[6], p[7], p[8])); }
+    }
+    const double q[3] = { pos.x, pos.y, pos.z };
+    uint32_t cap = 256, count = 0;
+    std::vector<uint32_t> ids(cap);
+    if (gi_photon_in_range(_ctx, 1, q, cap, ids.data(), &count) != GI_OK) return res;
+    if (count > cap) { cap = count; ids.resize(cap); if (gi_photon_in_range(_ctx, 1, q, cap, ids.data(), &count) != GI_OK) return res; }
+    res.reserve(count);
+    for (uint32_t k = 0; k < count; k++) if (ids[k] < _host.size()) res.push_back(&_host[ids[k]]);
+    return res;
 }
 
 int RayTracer::run(int w, int h)
@@ -170,6 +193,7 @@ int RayTracer::run(int w, int h)
         _scene->flatten(_camera, ambient, flat);
         gi_scene_desc d = flat.desc();
         if ((rc = gi_scene_upload(ctx, &d)) != GI_OK) { std::cout << "gi_scene_upload: " << gi_last_error(ctx) << "\n"; return rc; }
+        _scene->attach(ctx, flat);   // Octree::intersect / intersectSorted and Entity::intersect now answer from this device
         _uploaded = true;
     }
     if (!_running) return GI_OK;                                                 // stop() arrived while the context was being created

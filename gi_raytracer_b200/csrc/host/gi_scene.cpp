@@ -308,6 +308,7 @@ void Octree::push_back(Entity* object)  // octree.cpp:25-38
         _root._bbox.min = object->boundingBox().min;
     }
     _root._entities.push_back(object);
+    object->_owner = this; object->_id = (uint32_t)_all.size();
     _all.push_back(object);
     _root._bbox.max = gi::vmax(_root._bbox.max, object->boundingBox().max);
     _root._bbox.min = gi::vmin(_root._bbox.min, object->boundingBox().min);
@@ -606,5 +607,60 @@ bool Image::writePPM(const char* path) const
     std::fprintf(f, "P6\n%d %d\n255\n", _w, _h);
     std::fwrite(rgb.data(), 1, rgb.size(), f);
     std::fclose(f);
+    return true;
+}
+
+// ---- the reference's query members as batch-of-one device calls (octree.h:54,56; entities.h:24) -----------------------------------------------
+void Octree::attach(gi_ctx* ctx, const FlatScene& flat)
+{
+    _query_ctx = ctx;
+    _query_nodes.clear();
+    const size_t nn = flat.node_mask.size();
+    _query_nodes.reserve(nn);
+    for (size_t i = 0; i < nn; i++) {
+        const double* b = &flat.node_box[6 * i];
+        std::unique_ptr<Node> n(new Node(BoundingBox(dvec3(b[0], b[1], b[2]), dvec3(b[3], b[4], b[5]))));
+        if (!flat.node_mask[i]) for (uint32_t k = 0; k < flat.node_prim_cnt[i]; k++) n->_entities.push_back(_all[flat.leaf_prims[flat.node_prim_off[i] + k]]);
+        _query_nodes.push_back(std::move(n));
+    }
+}
+
+std::vector<Entity*> Octree::intersect(const Ray& ray, double tmin, double tmax) const
+{
+    std::vector<Entity*> res;
+    if (!_query_ctx) return res;
+    const double o[3] = { ray.origin.x, ray.origin.y, ray.origin.z }, d[3] = { ray.dir.x, ray.dir.y, ray.dir.z };
+    uint32_t cap = 256, count = 0;   // res.reserve(256) in the reference (octree.cpp:153)
+    std::vector<uint32_t> ids(cap);
+    if (gi_octree_intersect(_query_ctx, 1, o, d, &tmin, &tmax, cap, ids.data(), &count) != GI_OK) return res;
+    if (count > cap) { cap = count; ids.resize(cap); if (gi_octree_intersect(_query_ctx, 1, o, d, &tmin, &tmax, cap, ids.data(), &count) != GI_OK) return res; }
+    res.reserve(count);
+    for (uint32_t k = 0; k < count; k++) res.push_back(_all[ids[k]]);
+    return res;
+}
+
+std::vector<std::pair<const Octree::Node*, double>> Octree::intersectSorted(const Ray& ray, double tmin, double tmax) const
+{
+    std::vector<std::pair<const Node*, double>> res;
+    if (!_query_ctx) return res;
+    const double o[3] = { ray.origin.x, ray.origin.y, ray.origin.z }, d[3] = { ray.dir.x, ray.dir.y, ray.dir.z };
+    uint32_t cap = 64, count = 0;
+    std::vector<uint32_t> nodes(cap); std::vector<double> t0(cap);
+    if (gi_octree_intersect_sorted(_query_ctx, 1, o, d, &tmin, &tmax, cap, nodes.data(), t0.data(), &count) != GI_OK) return res;
+    if (count > cap) { cap = count; nodes.resize(cap); t0.resize(cap); if (gi_octree_intersect_sorted(_query_ctx, 1, o, d, &tmin, &tmax, cap, nodes.data(), t0.data(), &count) != GI_OK) return res; }
+    for (uint32_t k = 0; k < count; k++) if (nodes[k] < _query_nodes.size()) res.emplace_back(_query_nodes[nodes[k]].get(), t0[k]);
+    return res;
+}
+
+bool Entity::intersect(const Ray& ray, dvec3& hit, dvec3& norm, gi::dvec2& uv) const
+{
+    gi_ctx* ctx = _owner ? _owner->attached() : nullptr;
+    if (!ctx) return false;
+    const double o[3] = { ray.origin.x, ray.origin.y, ray.origin.z }, d[3] = { ray.dir.x, ray.dir.y, ray.dir.z };
+    uint8_t ok = 0, wrote = 0;
+    double h[3], n[3], t[2];
+    if (gi_prim_intersect(ctx, 1, &_id, o, d, &ok, h, n, t, &wrote) != GI_OK || !ok) return false;
+    hit = dvec3(h[0], h[1], h[2]); norm = dvec3(n[0], n[1], n[2]);
+    if (wrote) uv = gi::dvec2(t[0], t[1]);
     return true;
 }

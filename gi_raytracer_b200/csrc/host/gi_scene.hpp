@@ -19,6 +19,8 @@
 #include <cstdint>
 #include <memory>
 #include <string>
+#include <type_traits>
+#include <utility>
 #include <vector>
 
 #include "../../../include/gi_api.h"
@@ -42,6 +44,14 @@ struct dvec3 {
     dvec3() {}
     dvec3(double a, double b, double c) : x(a), y(b), z(c) {}
     explicit dvec3(double s) : x(s), y(s), z(s) {}
+    // any other 3-vector type with x, y, z members converts both ways — glm::dvec3 in a translation unit of the reference tree
+    // (main.cpp, the scene loader's callers) is accepted wherever this API takes a gi::dvec3, and a result can be assigned back
+    template <class V, class = decltype(double(std::declval<const V&>().x) + double(std::declval<const V&>().y) + double(std::declval<const V&>().z)),
+              class = typename std::enable_if<!std::is_same<typename std::decay<V>::type, dvec3>::value>::type>
+    dvec3(const V& v) : x(v.x), y(v.y), z(v.z) {}
+    template <class V, class = decltype(V(0.0, 0.0, 0.0)), class = decltype(std::declval<V&>().x),
+              class = typename std::enable_if<!std::is_same<typename std::decay<V>::type, dvec3>::value && !std::is_arithmetic<V>::value>::type>
+    explicit operator V() const { return V(x, y, z); }
     double& operator[](int i) { return (&x)[i]; }
     const double& operator[](int i) const { return (&x)[i]; }
 };
@@ -144,9 +154,15 @@ struct Entity {  // entities.h:17-49
     virtual ~Entity() {}
     virtual int kind() const = 0;                       // GI_PRIM_* (replaces the virtual intersect(ray) dispatch)
     virtual bool intersect(BoundingBox) { return false; }  // entities.h:38-41 (cone inherits this: never assigned to a child)
+    // entities.h:24: the ray test of this entity.  A batch-of-one gi_prim_intersect on the context that holds the entity's scene
+    // (Octree::attach, done by RayTracer::run): false — like a miss — while the scene is not on a device.  uv is left alone where
+    // the reference leaves it alone (cones, triangles without vertex normals).
+    bool intersect(const Ray& ray, gi::dvec3& hit, gi::dvec3& norm, gi::dvec2& uv) const;
     virtual BoundingBox boundingBox() const = 0;
     gi::dvec3 pos, rot;
     Material material;
+    Octree* _owner = nullptr;      // set by Octree::push_back
+    uint32_t _id = 0;              // primitive id = insertion index
 };
 
 struct sphere : Entity {  // entities.h:51-142
@@ -283,6 +299,14 @@ class Octree {  // octree.h:17-65
     // New: SoA image of the rebuilt tree for gi_scene_upload.  Primitive id = insertion order of push_back(Entity*).
     void flatten(const Camera& cam, const gi::dvec3& ambient, FlatScene& out) const;
     const std::vector<Entity*>& entities() const { return _all; }
+    // octree.h:54,56 — the reference's two ray queries, answered by the device that holds the flattened tree (batch-of-one
+    // gi_octree_intersect / gi_octree_intersect_sorted).  attach() names that context (RayTracer::run does it after the upload);
+    // without one the queries return nothing.  intersectSorted's Node pointers are images of the flattened nodes (box and
+    // entities of each leaf), valid until the next rebuild.
+    std::vector<Entity*> intersect(const Ray& ray, double tmin, double tmax) const;
+    std::vector<std::pair<const Node*, double>> intersectSorted(const Ray& ray, double tmin, double tmax) const;
+    void attach(gi_ctx* ctx, const FlatScene& flat);
+    gi_ctx* attached() const { return _query_ctx; }
     bool valid = false;
     Node _root;
     int nodes = 0, skipped_subdiv = 0;
@@ -291,6 +315,8 @@ class Octree {  // octree.h:17-65
     bool _device_built = false; // _dev_* hold the tree instead of _root's children
     std::vector<double> _dev_box; std::vector<uint32_t> _dev_child, _dev_off, _dev_cnt, _dev_leaf; std::vector<uint8_t> _dev_mask;
     std::vector<Entity*> _all;  // insertion order (the root list itself is cleared by partition, octree.cpp:370-371)
+    gi_ctx* _query_ctx = nullptr;
+    std::vector<std::unique_ptr<Node>> _query_nodes;   // one image per flattened node (attach)
 };
 
 class PhotonMap {  // photonMap.h:13-49 — a handle on the device-resident map
@@ -299,9 +325,15 @@ class PhotonMap {  // photonMap.h:13-49 — a handle on the device-resident map
     void reserve(int) {}
     void push_back(Photon* p) { staged.push_back(*p); }   // photons supplied by the caller (uploaded by rebuild)
     void rebuild(gi_ctx* ctx);                             // photonMap.cpp:33-47 -> gi_photon_upload (if staged) + gi_photon_map_build
+    // photonMap.h:45 — the candidate photons of a query point, Node::get's order (batch-of-one gi_photon_in_range on the context the
+    // map was built in).  The Photon objects are a host copy of the device's photon array, fetched on first use.
+    std::vector<Photon*> getInRange(gi::dvec3& pos, double& scale, double dist) const;
     bool valid = false;
     gi::dvec3 min, max;
     std::vector<Photon> staged;
+  private:
+    gi_ctx* _ctx = nullptr;
+    mutable std::vector<Photon> _host;   // device photons, original order
 };
 
 struct Image {  // image.h:7-29 without Qt: RGB888 rows, top row first

@@ -206,6 +206,25 @@ int gi_trace_any(gi_ctx* ctx, size_t n, const double* org, const double* dir, co
 int gi_trace_any_dev(gi_ctx* ctx, size_t n, const double* org, const double* dir, const double* maxt2, uint64_t alpha_seed,
                      uint8_t* vis);
 
+/* ---- the scene-API queries the reference exposes beside its renderer, as batches (host pointers); the preserved C++ members
+ *      Octree::intersect / intersectSorted, PhotonMap::getInRange and Entity::intersect (csrc/host) are batch-of-one calls of these.
+ *      gi_octree_intersect: Octree::intersect (octree.cpp:150-185, 256-282): the entities of every non-empty leaf the segment
+ *        [tmin, tmax] meets, in the recursion's order (a primitive once per leaf it sits in): prim_ids [n][cap], counts [n] = the
+ *        full count (may exceed cap);
+ *      gi_octree_intersect_sorted: Octree::intersectSorted (octree.cpp:188-211, 285-313): the non-empty leaves (flattened node
+ *        index of gi_scene_desc) with their entry distance, ascending, equal keys in discovery order: node_ids / t0 [n][cap];
+ *      gi_photon_in_range: PhotonMap::getInRange (photonMap.cpp:50-92, 115-134): the candidate photons of a query point (original
+ *        photon indices, Node::get's order): photon_ids [n][cap], counts = the full count;
+ *      gi_prim_intersect: Entity::intersect(ray, hit, norm, uv) of primitive prim[i] (entities.h:60-101, 158-258, 443-490); uv is
+ *        written only where the reference writes it (wrote_uv). --------------------------------------------------------------------- */
+int gi_octree_intersect(gi_ctx* ctx, size_t n, const double* org, const double* dir, const double* tmin, const double* tmax, uint32_t cap, uint32_t* prim_ids,
+                        uint32_t* counts);
+int gi_octree_intersect_sorted(gi_ctx* ctx, size_t n, const double* org, const double* dir, const double* tmin, const double* tmax, uint32_t cap, uint32_t* node_ids,
+                               double* t0, uint32_t* counts);
+int gi_photon_in_range(gi_ctx* ctx, size_t n, const double* pos, uint32_t cap, uint32_t* photon_ids, uint32_t* counts);
+int gi_prim_intersect(gi_ctx* ctx, size_t n, const uint32_t* prim, const double* org, const double* dir, uint8_t* ok, double* hit, double* normal, double* uv,
+                      uint8_t* wrote_uv);
+
 /* ---- materials: texture::get / checkerboard::get / imageTexture::get + getAlpha and Material::getAlpha (material.h:18-26,
  *      39-45, 63-81, 90-93) for the material of primitive prim[i] at uv[i] — the values RayTracer::radiance reads at
  *      raytracer.h:200 / :269 and the alpha test at :455 / :297.  diffuse / emissive [n][3], alpha [n]; host pointers. ------ */

@@ -672,6 +672,48 @@ void go_trace_any(const gi_scene_desc* sc, size_t n, const double* org, const do
         vis[i] = (uint8_t)visible_one(sc, &r, maxt2[i], alpha_seed, (uint64_t)i, 0, 0, NULL, NULL);
     }
 }
+/* Octree::intersect (octree.cpp:150-185, 256-282): the entities of every non-empty leaf met by [tmin, tmax], in the recursion's order */
+static void octree_intersect_rec(const gi_scene_desc* sc, uint32_t node, const ray_t* r, double tmin, double tmax, uint32_t cap, uint32_t* ids, uint32_t* cnt)
+{
+    if (!box_hit(sc->node_box + 6 * (size_t)node, r, tmin, tmax, NULL)) return;   /* intersectSimple: same folds, same early rejects */
+    uint8_t mask = sc->node_mask[node];
+    if (!mask) {
+        const uint32_t* l = sc->leaf_prims + sc->node_prim_off[node];
+        for (uint32_t k = 0; k < sc->node_prim_cnt[node]; k++, (*cnt)++) if (*cnt < cap) ids[*cnt] = l[k];
+        return;
+    }
+    uint32_t c = sc->node_child[node];
+    for (int i = 0; i < 8; i++) if (mask & (1u << i)) octree_intersect_rec(sc, c++, r, tmin, tmax, cap, ids, cnt);
+}
+void go_octree_intersect(const gi_scene_desc* sc, size_t n, const double* org, const double* dir, const double* tmin, const double* tmax, uint32_t cap, uint32_t* ids, uint32_t* counts)
+{
+#pragma omp parallel for schedule(dynamic, 64)
+    for (long i = 0; i < (long)n; i++) {
+        ray_t r = ray_as_stored(ld3(org + 3 * i), ld3(dir + 3 * i));
+        uint32_t c = 0;
+        if (sc->n_nodes) octree_intersect_rec(sc, 0, &r, tmin[i], tmax[i], cap, ids + (size_t)i * cap, &c);
+        counts[i] = c;
+    }
+}
+/* Octree::intersectSorted (octree.cpp:188-211, 285-313): flattened node index and entry distance of every non-empty leaf, sorted */
+void go_octree_intersect_sorted(const gi_scene_desc* sc, size_t n, const double* org, const double* dir, const double* tmin, const double* tmax, uint32_t cap, uint32_t* nodes, double* t0,
+                                uint32_t* counts)
+{
+#pragma omp parallel
+    {
+        leaflist_t L = { 0, 0, 0 };
+#pragma omp for schedule(dynamic, 64)
+        for (long i = 0; i < (long)n; i++) {
+            ray_t r = ray_as_stored(ld3(org + 3 * i), ld3(dir + 3 * i));
+            L.n = 0;
+            if (sc->n_nodes) enum_sorted(sc, 0, &r, tmin[i], tmax[i], &L);
+            for (size_t k = 0; k < L.n && k < cap; k++) { nodes[(size_t)i * cap + k] = L.v[k].node; t0[(size_t)i * cap + k] = L.v[k].t0; }
+            counts[i] = (uint32_t)L.n;
+        }
+        free(L.v);
+    }
+}
+
 /* sequential forms on the reference's own PRNG stream (see g_xs): *state = the interposed time() value, updated */
 void go_trace_closest_replay(const gi_scene_desc* sc, size_t n, const double* org, const double* dir, uint64_t* state, uint32_t* prim, double* hit, double* normal, double* uv)
 {

@@ -54,6 +54,11 @@ void go_trace_any(const gi_scene_desc* sc, size_t n, const double* org, const do
 /* canonical ordered traversal with early termination: same answers as go_trace_closest plus work counters */
 void go_trace_closest_cot(const gi_scene_desc* sc, size_t n, const double* org, const double* dir, uint64_t alpha_seed,
                           uint32_t* prim, double* hit, uint32_t* n_node_tests, uint32_t* n_prim_tests);
+/* Octree::intersect / Octree::intersectSorted as callable queries (octree.cpp:150-211, 256-313) */
+void go_octree_intersect(const gi_scene_desc* sc, size_t n, const double* org, const double* dir, const double* tmin, const double* tmax, uint32_t cap, uint32_t* ids,
+                         uint32_t* counts);
+void go_octree_intersect_sorted(const gi_scene_desc* sc, size_t n, const double* org, const double* dir, const double* tmin, const double* tmax, uint32_t cap, uint32_t* nodes,
+                                double* t0, uint32_t* counts);
 /* the same two functions on the reference's own PRNG stream (thread_local xorshift64*, util.h:52-80), sequential:
  * *state = the value gi_ref's interposed time() returned; makes alpha-textured scenes bit-comparable with gi_ref run with
  * OMP_NUM_THREADS=1 (one draw per trace() call + one per geometric hit, in the reference's order) */

@@ -281,7 +281,7 @@ int main(int argc, char** argv)
 {
     if (argc < 3) {
         fprintf(stderr, "usage: gi_ref <scene.scn> <outdir> [--w W --h H --s0 A --s1 B --max-depth D --min-depth M --photons P --samples N --x0 --y0 --x1 --y1 --repeat R] cmd...\n"
-                        "cmds: scene halton samplers primary textures fog shadow photons gather gather-knn radiance run time-frame time-gather bench-frame\n");
+                        "cmds: scene halton samplers primary textures queries fog shadow photons gather gather-knn radiance run time-frame time-gather bench-frame\n");
         return 1;
     }
     const char* scn = argv[1];
@@ -339,7 +339,7 @@ int main(int argc, char** argv)
     std::vector<double> hit_pos, hit_nrm, hit_uv, ray_o, ray_d;
     std::vector<uint32_t> hit_id, ray_idx;
     std::vector<double> tex_dif, tex_em, tex_alpha;
-    if (has("primary") || has("shadow") || has("gather") || has("gather-knn") || has("time-gather") || has("fog") || has("textures")) {
+    if (has("primary") || has("shadow") || has("gather") || has("gather-knn") || has("time-gather") || has("fog") || has("textures") || has("queries")) {
         // one slot per (s, y, x) in that order; rows are spread over the OpenMP threads (trace() is const and is called
         // concurrently by the reference itself, raytracer.h:93-160).  With OMP_NUM_THREADS=1 the rays are traced in slot order
         // on the main thread, so the reference's thread_local xorshift stream (util.h:52-80) is consumed in that order.
@@ -408,6 +408,21 @@ int main(int argc, char** argv)
         dump("fogb_hit.u8", bh); dump("fogb_t.f64", bt);
     }
 
+    // -- the octree's two ray queries as the reference's callers see them: Octree::intersectSorted for every primary ray (leaf boxes +
+    //    entry distances, in the returned order) and, below, Octree::intersect for every shadow ray (entity ids, in the returned order)
+    if (has("queries")) {
+        std::vector<uint32_t> off = { 0 }; std::vector<double> box, t0;
+        for (size_t i = 0; i < hit_id.size(); i++) {
+            Ray ray(glm::dvec3(ray_o[3 * i], ray_o[3 * i + 1], ray_o[3 * i + 2]), glm::dvec3(ray_d[3 * i], ray_d[3 * i + 1], ray_d[3 * i + 2]));
+            ray.dir = glm::dvec3(ray_d[3 * i], ray_d[3 * i + 1], ray_d[3 * i + 2]);   // the traced ray's stored direction, not a re-normalised copy (ray.h:7-17)
+            ray.invDir = glm::dvec3(1.0 / ray.dir.x, 1.0 / ray.dir.y, 1.0 / ray.dir.z);
+            auto leaves = scene->intersectSorted(ray, 0, INFINITY);                  // raytracer.h:389
+            for (auto& l : leaves) { push3(box, l.first->_bbox.min); push3(box, l.first->_bbox.max); t0.push_back(l.second); }
+            off.push_back((uint32_t)t0.size());
+        }
+        dump("ls_off.u32", off); dump("ls_box.f64", box); dump("ls_t0.f64", t0);
+    }
+
     // -- shadow rays from the primary hits toward Halton-chosen light points ------------------------
     if (has("shadow")) {
         // one slot per (hit, light), hits in ray order; misses are skipped (slot index by prefix count)
@@ -415,6 +430,8 @@ int main(int argc, char** argv)
         for (size_t i = 0; i < hit_id.size(); i++) hslot[i + 1] = hslot[i] + (hit_id[i] == 0xFFFFFFFFu ? 0 : scene->lights.size());
         const size_t nsh = hslot.back();
         std::vector<double> so(nsh * 3), sd(nsh * 3), smt(nsh); std::vector<uint8_t> vis(nsh);
+        const bool want_queries = has("queries");
+        std::vector<uint32_t> qc_cnt(want_queries ? nsh : 0); std::vector<std::vector<uint32_t>> qc_ids(want_queries ? nsh : 0);
 #pragma omp parallel for schedule(dynamic, 1024)
         for (long i = 0; i < (long)hit_id.size(); i++) {
             if (hit_id[i] == 0xFFFFFFFFu) continue;
@@ -428,12 +445,23 @@ int main(int argc, char** argv)
                 double maxt = vecLengthSquared(lightDir);
                 Ray sr(p + SHADOW_BIAS * n, lightDir);                              // raytracer.h:241
                 bool v_ = rt.visible(sr, maxt);
+                if (want_queries) {
+                    std::vector<Entity*> c = scene->intersect(sr, 0, sqrt(maxt) - SHADOW_BIAS);   // raytracer.h:283
+                    qc_cnt[k] = (uint32_t)c.size();
+                    qc_ids[k].reserve(c.size());
+                    for (Entity* e : c) qc_ids[k].push_back(g_eid.at(e));
+                }
                 for (int c = 0; c < 3; c++) { so[3 * k + c] = sr.origin[c]; sd[3 * k + c] = sr.dir[c]; }
                 smt[k] = maxt; vis[k] = v_ ? 1 : 0;
                 k++;
             }
         }
         dump("sh_o.f64", so); dump("sh_d.f64", sd); dump("sh_maxt2.f64", smt); dump("sh_vis.u8", vis);
+        if (want_queries) {
+            std::vector<uint32_t> off = { 0 }, ids;
+            for (size_t k = 0; k < nsh; k++) { ids.insert(ids.end(), qc_ids[k].begin(), qc_ids[k].end()); off.push_back((uint32_t)ids.size()); }
+            dump("sc_off.u32", off); dump("sc_id.u32", ids);
+        }
         meta << "shadow_rays=" << vis.size() << "\n";
     }
 

@@ -8,7 +8,8 @@ Fixtures (all raw outputs of the reference's own functions, OMP_NUM_THREADS=1, t
   cornell_small.npz  scenes/cornell/cornell.scn at 48x48, s in [0,2): scene dump (entities, octree), Halton KATs,
                      sampler KATs, camera rays, closest hits, shadow rays + visibility, 3000 photons, photon-map
                      cells, gather candidates / 32-nearest sets / radiance estimates.
-  caustics_small.npz scenes/caustics/caustics.scn at 40x40: rays, hits, shadows, 2500 photons + gather.
+  caustics_small.npz scenes/caustics/caustics.scn at 40x40: rays, hits, shadows, 2500 photons + gather; Octree::intersectSorted's leaf lists
+                     (boxes + entry distances) of the primary rays and Octree::intersect's entity lists of the shadow rays.
   api_small.npz      tests/synth.py `small.scn` + the API-built primitives of csrc/host/api_scene.inc (`gi_ref --api-scene 1`: analytic
                      sphere and cones, sphereMesh / coneMesh / quadMesh / boxMesh generators, a checkerboard material) at 56x56, s in
                      [0,2): rays, closest hits (ids, points, normals, uvs), shadow rays + visibility, texture::get / getAlpha at
@@ -61,8 +62,8 @@ def main():
     out["meta_w_h_s0_s1"] = np.array([48, 48, 0, 2])
     np.savez_compressed(os.path.join(HERE, "cornell_small.npz"), **out)
     print("cornell_small", meta)
-    d, meta = R.run_ref(os.path.join(root, "scenes/caustics/caustics.scn"), ["scene", "primary", "shadow", "photons", "gather"], w=40, h=40, s0=0, s1=1, photons=2500)
-    out = pack(d, SCENE_FILES + RAY_FILES)
+    d, meta = R.run_ref(os.path.join(root, "scenes/caustics/caustics.scn"), ["scene", "primary", "queries", "shadow", "photons", "gather"], w=40, h=40, s0=0, s1=1, photons=2500)
+    out = pack(d, SCENE_FILES + RAY_FILES + ["ls_off.u32", "ls_box.f64", "ls_t0.f64", "sc_off.u32", "sc_id.u32"])
     out["meta_w_h_s0_s1"] = np.array([40, 40, 0, 1])
     np.savez_compressed(os.path.join(HERE, "caustics_small.npz"), **out)
     print("caustics_small", meta)

@@ -41,6 +41,8 @@ def lib():
     L.go_trace_closest_replay.argtypes = [vp, sz, vp, vp, vp, vp, vp, vp, vp]
     L.go_trace_any_replay.argtypes = [vp, sz, vp, vp, vp, vp, vp]
     L.go_material_eval.argtypes = [vp, sz, vp, vp, vp, vp, vp]
+    L.go_octree_intersect.argtypes = [vp, sz, vp, vp, vp, vp, u32, vp, vp]
+    L.go_octree_intersect_sorted.argtypes = [vp, sz, vp, vp, vp, vp, u32, vp, vp, vp]
     L.go_pmap_build.restype = vp
     L.go_pmap_build.argtypes = [sz, vp, vp]
     L.go_pmap_free.argtypes = [vp]
@@ -164,6 +166,33 @@ def trace_any_cot(scene, org, d, maxt2, alpha_seed=0):
     desc = scene.desc()
     L.go_trace_any_cot(C.byref(desc), n, _p(org), _p(d), _p(maxt2), alpha_seed, _p(vis), _p(nn), _p(npr))
     return vis, nn, npr
+
+
+def octree_intersect(scene, org, d, tmin, tmax, cap=256):
+    L = lib()
+    org, d = _f64(org, 3), _f64(d, 3)
+    n = org.shape[0]
+    tmin = np.ascontiguousarray(np.broadcast_to(np.asarray(tmin, dtype=np.float64), (n,)))
+    tmax = np.ascontiguousarray(np.broadcast_to(np.asarray(tmax, dtype=np.float64), (n,)))
+    ids = np.full((n, cap), 0xFFFFFFFF, dtype=np.uint32)
+    cnt = np.zeros(n, dtype=np.uint32)
+    desc = scene.desc()
+    L.go_octree_intersect(C.byref(desc), n, _p(org), _p(d), _p(tmin), _p(tmax), cap, _p(ids), _p(cnt))
+    return ids, cnt
+
+
+def octree_intersect_sorted(scene, org, d, tmin, tmax, cap=64):
+    L = lib()
+    org, d = _f64(org, 3), _f64(d, 3)
+    n = org.shape[0]
+    tmin = np.ascontiguousarray(np.broadcast_to(np.asarray(tmin, dtype=np.float64), (n,)))
+    tmax = np.ascontiguousarray(np.broadcast_to(np.asarray(tmax, dtype=np.float64), (n,)))
+    nodes = np.full((n, cap), 0xFFFFFFFF, dtype=np.uint32)
+    t0 = np.zeros((n, cap))
+    cnt = np.zeros(n, dtype=np.uint32)
+    desc = scene.desc()
+    L.go_octree_intersect_sorted(C.byref(desc), n, _p(org), _p(d), _p(tmin), _p(tmax), cap, _p(nodes), _p(t0), _p(cnt))
+    return nodes, t0, cnt
 
 
 def trace_closest_replay(scene, org, d, state):

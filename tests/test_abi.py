@@ -54,3 +54,13 @@ def test_product_does_not_import_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".cpp", ".hpp", ".h")):
                 text = open(os.path.join(dirpath, f), errors="ignore").read()
                 assert "gi_oracle" not in text and "liboracle" not in text and "oracle_lib" not in text, os.path.join(dirpath, f)
+
+
+def test_every_binding_declares_its_argument_types(lib_built):
+    """A ctypes function without argtypes passes Python ints as 32-bit C ints: 64-bit pointers and sizes get truncated (a crash on the
+    GPU box, nothing on a CPU-only run).  Every declared entry point must have its signature set in capi.load_library."""
+    from gi_raytracer_b200 import capi
+    L = capi.load_library()
+    no_args = {"gi_version"}
+    missing = [n for n in capi.API_SYMBOLS if n not in no_args and getattr(L, n).argtypes is None]
+    assert not missing, missing

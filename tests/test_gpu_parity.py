@@ -658,3 +658,47 @@ def test_row_plan_parts_compose_to_the_frame(ctx, synth_dir):
             rays += ps.closest_rays + ps.shadow_rays
         assert bits_equal(frame, full), nparts
         assert rays == st.closest_rays + st.shadow_rays
+
+
+def test_scene_api_queries_vs_reference(ctx, golden_caustics):
+    """The batch forms behind the preserved C++ members Octree::intersectSorted / Octree::intersect / PhotonMap::getInRange /
+    Entity::intersect (gi_octree_intersect_sorted, gi_octree_intersect, gi_photon_in_range, gi_prim_intersect) against what the
+    reference's own members returned for the same rays / points: same leaves in the same order with bit-equal entry distances, same
+    entity lists, same candidate photons in the same order, same hit points / normals / uvs."""
+    g = golden_caustics
+    sc = R.scene_from_npz(g)
+    ctx.upload_scene(sc)
+    ro, rd = g["ray_o_f64"].reshape(-1, 3), g["ray_d_f64"].reshape(-1, 3)
+    nodes, t0, cnt = ctx.octree_intersect_sorted(ro, rd, 0.0, np.inf, cap=64)
+    off = g["ls_off_u32"]
+    assert bits_equal(cnt, np.diff(off).astype(np.uint32))
+    rb, rt = g["ls_box_f64"].reshape(-1, 6), g["ls_t0_f64"]
+    for i in range(ro.shape[0]):
+        k = int(cnt[i])
+        assert bits_equal(sc.node_box[nodes[i, :k]], rb[off[i]:off[i + 1]]) and bits_equal(t0[i, :k], rt[off[i]:off[i + 1]])
+    so, sd, mt = g["sh_o_f64"].reshape(-1, 3), g["sh_d_f64"].reshape(-1, 3), g["sh_maxt2_f64"]
+    ids, c2 = ctx.octree_intersect(so, sd, 0.0, np.sqrt(mt) - 1e-4, cap=512)
+    off, rid = g["sc_off_u32"], g["sc_id_u32"]
+    assert bits_equal(c2, np.diff(off).astype(np.uint32))
+    for i in range(so.shape[0]):
+        assert np.array_equal(ids[i, :c2[i]], rid[off[i]:off[i + 1]])
+    # a too small cap reports the full count and fills what fits
+    ids4, c4 = ctx.octree_intersect(so[:50], sd[:50], 0.0, np.sqrt(mt[:50]) - 1e-4, cap=4)
+    assert bits_equal(c4, c2[:50]) and all(np.array_equal(ids4[i, :min(4, c4[i])], ids[i, :min(4, c4[i])]) for i in range(50))
+    # PhotonMap::getInRange: candidate photons in the reference's order
+    ctx.photon_upload(g["photons_f64"].reshape(-1, 9))
+    ctx.photon_map_build(sc.root_box)
+    qp = g["q_pos_f64"].reshape(-1, 3)
+    pid, pc = ctx.photon_in_range(qp, cap=1024)
+    off, cand = g["q_cand_off_u32"], g["q_cand_u32"]
+    assert bits_equal(pc, np.diff(off).astype(np.uint32)) and pc.max() <= 1024
+    for i in range(qp.shape[0]):
+        assert np.array_equal(pid[i, :pc[i]], cand[off[i]:off[i + 1]])
+    # Entity::intersect: the hit primitive of every primary ray, tested on its own
+    rid = g["hit_id_u32"]
+    m = rid != 0xFFFFFFFF
+    ok, hit, nrm, uv, wrote = ctx.prim_intersect(rid[m], ro[m], rd[m])
+    assert ok.all() and wrote.all()
+    assert bits_equal(hit, g["hit_pos_f64"].reshape(-1, 3)[m]) and bits_equal(nrm, g["hit_nrm_f64"].reshape(-1, 3)[m]) and bits_equal(uv, g["hit_uv_f64"].reshape(-1, 2)[m])
+    ok2, *_ = ctx.prim_intersect(np.roll(rid[m], 7), ro[m], rd[m])   # mostly other primitives: mostly misses
+    assert ok2.mean() < 0.5

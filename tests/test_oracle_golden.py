@@ -159,3 +159,24 @@ def test_stochastic_alpha_path_replays_reference_stream(lib_built, synth_dir, na
         assert (counter != prim).any()
     else:
         assert 1 in set(int(k) for k in np.unique(sc.prim_type[prim[m]]))  # analytic spheres inside a partitioned octree
+
+
+def test_octree_queries_vs_reference(golden_caustics):
+    """Octree::intersectSorted (leaf boxes and entry distances, in the returned order) for the primary rays and Octree::intersect
+    (entity ids, in the returned order) for the shadow rays, as the reference returned them (octree.cpp:150-211, 256-313)."""
+    g = golden_caustics
+    sc = R.scene_from_npz(g)
+    ro, rd = g["ray_o_f64"].reshape(-1, 3), g["ray_d_f64"].reshape(-1, 3)
+    nodes, t0, cnt = O.octree_intersect_sorted(sc, ro, rd, 0.0, np.inf, cap=64)
+    off = g["ls_off_u32"]
+    assert bits_equal(cnt, np.diff(off).astype(np.uint32)) and cnt.max() <= 64 and cnt.max() > 4
+    rb, rt = g["ls_box_f64"].reshape(-1, 6), g["ls_t0_f64"]
+    for i in range(ro.shape[0]):
+        k = int(cnt[i])
+        assert bits_equal(sc.node_box[nodes[i, :k]], rb[off[i]:off[i + 1]]) and bits_equal(t0[i, :k], rt[off[i]:off[i + 1]])
+    so, sd, mt = g["sh_o_f64"].reshape(-1, 3), g["sh_d_f64"].reshape(-1, 3), g["sh_maxt2_f64"]
+    ids, c2 = O.octree_intersect(sc, so, sd, 0.0, np.sqrt(mt) - 1e-4, cap=512)
+    off, rid = g["sc_off_u32"], g["sc_id_u32"]
+    assert bits_equal(c2, np.diff(off).astype(np.uint32)) and c2.max() <= 512
+    for i in range(so.shape[0]):
+        assert np.array_equal(ids[i, :c2[i]], rid[off[i]:off[i + 1]])
