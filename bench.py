@@ -388,20 +388,22 @@ def main():
             st = GiStats()
             ctx._ck(ctx.L.gi_render_image(ctx.h, C.byref(P_samples), 0, 0, W, H, s0, s1, rgb8.numpy().ctypes.data, acc_host.numpy().ctypes.data, C.byref(st)))
             return st
+        # (the read-backs run on torch's own stream after the context's stream has drained: a torch copy enqueued on the context's
+        #  external stream would tie the tensors' lifetime to a stream that gi_destroy takes away)
         if tiles:
             st = step_tiles()
+            ctx.synchronize()
             if rank == 0:
-                with torch.cuda.stream(stream):
-                    rgb8.copy_(frame_rgb, non_blocking=True)
+                rgb8.copy_(frame_rgb)
         else:
             st = step_samples()
             if rank == 0:
                 accum = accums[(step_no[0] - 1) & 1]
                 ctx.resolve_dev(H * W, accum.data_ptr(), SPP * world, frame_rgb.data_ptr())
-                with torch.cuda.stream(stream):
-                    rgb8.copy_(frame_rgb, non_blocking=True)
-                    acc_host.copy_(accum, non_blocking=True)
-        ctx.synchronize()
+            ctx.synchronize()
+            if rank == 0:
+                rgb8.copy_(frame_rgb)
+                acc_host.copy_(accum)
         return st
 
     step_e2e()
@@ -519,6 +521,7 @@ def main():
             line["tile_split"] = {"scaling": "strong", "metric": "Mrays/s (all bounces)", "value": other_rays / (other_ms * 1e-3) / 1e6, "ms_per_step": other_ms / K,
                                   "frame": f"{W}x{H}, {SPP} spp (the N = 1 frame), interleaved {BLOCK_ROWS}-row blocks, gather of the 8-bit rows inside the timed region"}
         emit(line)
+    torch.cuda.synchronize(dev)
     if world > 1:
         dist.barrier()
         ctx.comm_destroy()

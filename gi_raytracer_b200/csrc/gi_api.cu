@@ -500,19 +500,8 @@ extern "C" int gi_scene_upload(gi_ctx* ctx, const gi_scene_desc* sc)
         if (mat_alpha[sc->prim_mat[i]]) { f |= LF_ALPHA; full = true; }
         pflags[i] = f;
     }
-    std::vector<DLeafRef> refs(sc->n_refs);
-    for (uint32_t i = 0; i < sc->n_refs; i++) {
-        uint32_t p = sc->leaf_prims[i];
-        std::memcpy(refs[i].g, sc->prim_geom + 9 * (size_t)p, 9 * sizeof(double));
-        if (sc->prim_type[p] == GI_PRIM_TRIANGLE) {   // v0, edge1 = v1 - v0, edge2 = v2 - v0 (tri_hit)
-            double* g = refs[i].g;
-            for (int k = 0; k < 3; k++) { g[3 + k] = g[3 + k] - g[k]; g[6 + k] = g[6 + k] - g[k]; }
-        }
-        refs[i].prim = p; refs[i].flags = pflags[p];
-    }
     cudaStream_t st = ctx->stream;
     CK(upload(ctx->b_nodes, nodes.data(), nodes.size(), st));
-    CK(upload(ctx->b_refs, refs.data(), refs.size(), st));
     CK(upload(ctx->b_geom, sc->prim_geom, (size_t)sc->n_prims * 9, st));
     CK(upload(ctx->b_nrm, sc->prim_nrm, (size_t)sc->n_prims * 9, st));
     CK(upload(ctx->b_uv, sc->prim_uv, (size_t)sc->n_prims * 6, st));
@@ -525,6 +514,15 @@ extern "C" int gi_scene_upload(gi_ctx* ctx, const gi_scene_desc* sc)
     CK(upload(ctx->b_lights, sc->lights, (size_t)sc->n_lights, st));
     CK(upload(ctx->b_fogs, sc->fogs, (size_t)sc->n_fog, st));
     CK(upload(ctx->b_foggrid, sc->fog_grid, (size_t)(sc->n_fog ? sc->fog_grid_count : 0), st));
+    // leaf records: expanded on the device (k_build_leafrefs) from what was just uploaded + the leaf index list and the per-primitive flags
+    CK(ctx->b_refs.reserve(std::max<size_t>(sc->n_refs, 1) * sizeof(DLeafRef)));
+    if (sc->n_refs) {
+        CK(upload(ctx->w8, sc->leaf_prims, (size_t)sc->n_refs, st));
+        CK(upload(ctx->w9, pflags.data(), pflags.size(), st));
+        k_build_leafrefs<<<grid_for(sc->n_refs, 256), 256, 0, st>>>(sc->n_refs, ctx->w8.as<uint32_t>(), ctx->b_geom.as<double>(), ctx->b_ptype.as<uint8_t>(), ctx->w9.as<uint32_t>(),
+                                                                   ctx->b_refs.as<DLeafRef>());
+        CK(cudaGetLastError());
+    }
     CK(cudaStreamSynchronize(st));   // the host staging vectors die at return
     DScene& S = ctx->S;
     S.nodes = ctx->b_nodes.as<DNode>(); S.refs = ctx->b_refs.as<DLeafRef>();

@@ -63,6 +63,28 @@ __global__ void k_material_eval(DScene S, size_t n, const uint32_t* __restrict__
     alpha[i] = m.opacity * tex_alpha(S, m.diffuse_tex, u, v);
 }
 
+// ---- scene upload: the leaf records are expanded ON THE DEVICE from the primitive arrays and the leaf index list — the host sends
+// 9 doubles per PRIMITIVE and 4 bytes per leaf reference instead of an 80-byte record per reference (the atrium stand-in: 72 MB instead
+// of 1.06 GB).  A triangle's record holds v0, v1 - v0, v2 - v0: the edges the reference recomputes per test (entities.h:447-448),
+// subtracted here once in the same fp64 arithmetic.
+__global__ void k_build_leafrefs(uint32_t n_refs, const uint32_t* __restrict__ leaf_prims, const double* __restrict__ prim_geom, const uint8_t* __restrict__ prim_type,
+                                 const uint32_t* __restrict__ prim_flags, DLeafRef* __restrict__ refs)
+{
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_refs) return;
+    const uint32_t p = leaf_prims[i];
+    const double* g = prim_geom + 9 * (size_t)p;
+    DLeafRef r;
+#pragma unroll
+    for (int k = 0; k < 9; k++) r.g[k] = g[k];
+    if (prim_type[p] == GI_PRIM_TRIANGLE) {
+#pragma unroll
+        for (int k = 0; k < 3; k++) { r.g[3 + k] = r.g[3 + k] - r.g[k]; r.g[6 + k] = r.g[6 + k] - r.g[k]; }
+    }
+    r.prim = p; r.flags = prim_flags[p];
+    refs[i] = r;
+}
+
 // ---- K1: camera rays (raytracer.h:74-78, 112-129) ------------------------------------------------------------------------------
 // tile = local pixel space tw x th.  A rectangle maps local row ly to image row y0 + ly; the tile split's row plan (blocks of `rb`
 // rows every `rstride` rows, gi_render_rows) maps it to y0 + (ly / rb) * rstride + ly % rb.  rb = 0 means a plain rectangle.
@@ -630,6 +652,8 @@ __global__ void k_gather_locate(DGatherMap M, uint32_t n, const double* __restri
 #endif
 // GI_GS_MIN_GROUP:       // ... unless at least this many lanes of the warp share the list
 #define GI_GS_BLOCK 64   // 64 columns x 32 rows x 12 B = 24 KB of shared memory per block
+// (measured and dropped in round 2: the k nearest as an ascending sorted column with insertion from the end instead of the max-heap +
+//  final heap sort — no sort afterwards, but 27 % slower: 1.18 vs 0.93 ms for the 776 666 C2 queries, profiles/r02/ab_gather.txt)
 
 // max-heap of (distance^2, slot) pairs in one thread's column of shared memory: put (d, sl) into the hole at `i` of a heap of
 // `n` rows and sift it down

@@ -49,7 +49,35 @@ def pack(d, names):
     return {n.replace(".", "_"): R.load(d, n) for n in names}
 
 
+# Tier T6 on CONVERGED images: the five configs' scenes at 40x40, 256 spp, the config's MAX_DEPTH, rendered twice by the
+# reference (radiance() per pixel through the row loop of run(), two time() seeds).  Minutes of CPU per scene: run on its own with
+#     python tests/golden/make_golden.py converged
+CONVERGED = {   # name: scene file stem, directory, max depth, photons
+    "C1": ("cornell", "cornell", 4, 100000), "C2": ("caustics", "caustics", 64, 200000), "C3": ("glass", "glass", 64, 100000),
+    "C4": ("foliage", "foliage", 64, 0), "C5": ("sponza", "sponza", 64, 0),
+}
+CONVERGED_RES, CONVERGED_SPP = 40, 256
+
+
+def converged(only=None):
+    root = os.path.dirname(os.path.dirname(HERE))
+    for name, (stem, sdir, depth, photons) in CONVERGED.items():
+        if only and name not in only:
+            continue
+        out = {}
+        for tag, tv in (("a", 1001), ("b", 2002)):
+            d, meta = R.run_ref(os.path.join(root, "scenes", sdir, stem + ".scn"), ["radiance"], threads=os.cpu_count(), time_value=tv, w=CONVERGED_RES, h=CONVERGED_RES,
+                                samples=CONVERGED_SPP, max_depth=depth, photons=photons)
+            assert meta["radiance_spp"] == CONVERGED_SPP
+            out["radiance_" + tag] = R.load(d, "radiance.f64").reshape(-1, 3)
+        out["meta_res_spp_depth_photons"] = np.array([CONVERGED_RES, CONVERGED_SPP, depth, photons])
+        np.savez_compressed(os.path.join(HERE, f"converged_{name}.npz"), **out)
+        print("converged", name, float(out["radiance_a"].mean()), float(out["radiance_b"].mean()), flush=True)
+
+
 def main():
+    if len(sys.argv) > 1 and sys.argv[1] == "converged":
+        return converged(sys.argv[2:])
     root = os.path.dirname(os.path.dirname(HERE))
     d, meta = R.run_ref(os.path.join(root, "scenes/cornell/cornell.scn"), ["scene", "halton", "samplers", "primary", "shadow", "photons", "gather"],
                         w=48, h=48, s0=0, s1=2, photons=3000)
