@@ -77,6 +77,7 @@ struct gi_ctx {
     int tail_mode = 0;               // tail gathers: 0 queued and served by one gather pipeline run, 1 inline in the tail kernel (GI_TAIL_MODE)
     int bounce_mode = 0;             // 0: pick per scene, 1: always one ray per thread, 2: always persistent warps with refetch (GI_BOUNCE_MODE)
     double nodes_per_ray = 0;        // node tests per closest-hit ray of the last frame rendered with the current scene
+    double prims_per_ray = 0;        // primitive tests per closest-hit ray, likewise
     // per-scene choice between the two bounce kernels: the first full-size frame runs the form guessed from the tree, the
     // second the other one, later frames the faster of the two (bounce + direct ms per closest-hit ray)
     uint64_t tune_sig = 0;           // signature of the scene the statistic above belongs to
@@ -540,7 +541,7 @@ extern "C" int gi_scene_upload(gi_ctx* ctx, const gi_scene_desc* sc)
     {
         uint64_t sig = gi_mix64(((uint64_t)sc->n_nodes << 32) ^ sc->n_refs) ^ gi_mix64(((uint64_t)sc->n_prims << 20) ^ sc->n_lights);
         for (int k = 0; k < 6; k++) { uint64_t b; std::memcpy(&b, &sc->node_box[k], 8); sig = gi_mix64(sig ^ b); }
-        if (sig != ctx->tune_sig) { ctx->tune_sig = sig; ctx->nodes_per_ray = 0; }   // a new scene: forget the previous one's traversal statistics
+        if (sig != ctx->tune_sig) { ctx->tune_sig = sig; ctx->nodes_per_ray = 0; ctx->prims_per_ray = 0; }   // a new scene: forget the previous one's traversal statistics
     }
     ctx->has_scene = true;   // photons / photon map are independent state and survive a re-upload (the reference keeps its
     return GI_OK;            // map across run() calls, raytracer.h:61); rebuild it explicitly when the geometry changed
@@ -1307,7 +1308,10 @@ static int render_device(gi_ctx* ctx, const gi_render_params* P, int x0, int y0,
     // (caustics) and 60 (glass).  (A timing-based choice between the two forms flipped from run to run on scenes where they
     // are within a few per cent of each other, which made frame times bimodal.)
     const bool tunable = total_paths >= (1u << 20);   // small calls do not update the statistic
-    const bool long_walks = ctx->nodes_per_ray > 0 ? ctx->nodes_per_ray > 100.0 : ctx->S.n_nodes > 200000u;
+    // (round 2, 64-register kernels, frame ms classic -> refetch: atrium 264 -> 224, but foliage 212 -> 227, glass 49.2 -> 52.4, caustics 24.6 -> 25.8:
+    //  the foliage stand-in walks as many nodes per ray as the atrium (213 vs 139) but tests MORE primitives than nodes (219 vs 76) — its
+    //  warps are held up by leaf work that all lanes share, not by a few long walks, and refetch only adds its overhead there)
+    const bool long_walks = ctx->nodes_per_ray > 0 ? (ctx->nodes_per_ray > 100.0 && ctx->prims_per_ray < ctx->nodes_per_ray) : (ctx->S.n_nodes > 200000u && !ctx->S.full);
     const bool persistent = ctx->bounce_mode == 2 || (ctx->bounce_mode == 0 && long_walks);
     uint64_t n_closest = 0, n_shadow = 0, n_gather = 0, launches = 0;
     for (const char* f : { "bounce", "direct", "gather", "tail", "bin" }) fam_reset(ctx, f);
@@ -1506,7 +1510,10 @@ static int render_device(gi_ctx* ctx, const gi_render_params* P, int x0, int y0,
     if (rc != GI_OK) return rc;
     float ms = 0; cudaEventElapsedTime(&ms, e0, e1);
     n_closest += tc.closest; n_shadow += tc.shadow; n_gather += tc.gathers;
-    if (n_closest && tunable) ctx->nodes_per_ray = (double)(ctx->work_host[0] + tc.nodes_c) / (double)n_closest;
+    if (n_closest && tunable) {
+        ctx->nodes_per_ray = (double)(ctx->work_host[0] + tc.nodes_c) / (double)n_closest;
+        ctx->prims_per_ray = (double)(ctx->work_host[1] + tc.prims_c) / (double)n_closest;
+    }
     ctx->work_host[0] += tc.nodes_c; ctx->work_host[1] += tc.prims_c; ctx->work_host[2] += tc.nodes_s; ctx->work_host[3] += tc.prims_s;
     ctx->work_host[4] += tc.g_depth; ctx->work_host[5] += tc.g_cand; ctx->work_host[6] += tc.g_sel;
     if (stats) {
