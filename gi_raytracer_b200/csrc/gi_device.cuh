@@ -274,7 +274,7 @@ __device__ __forceinline__ uint32_t children_entry(const DNode& nd, const DRay& 
 //  dependent chain, where the eight independent slab tests + integer ranking below overlap: closest-hit kernels ran 30-50 % SLOWER
 //  (profiles/r02/README.md, variants v4 / v20 against v21).)
 template <bool IMPL, bool ORDERED>
-__device__ __forceinline__ uint32_t children_general(const DNode* __restrict__ nodes, const DNode& nd, const DRay& r, double tmax0, uint32_t& seq);
+__device__ __forceinline__ uint32_t children_general(const DNode* __restrict__ nodes, const DNode& nd, const DRay& r, double tmax0, uint32_t& seq, double mark_t, uint32_t& n_near);
 
 // ---- per-thread traversal stack: GI_STACK_MAX node indices in local memory (its top lines stay in L1; a shared-memory stack was
 // measured 5-8 % slower: it shrinks the L1 the node and leaf records live in).  An overflow raises the sticky error word — a plain
@@ -310,8 +310,9 @@ __device__ __forceinline__ DNode load_node(const DNode* nodes, uint32_t i)
 }
 
 
+// n_near = how many of the hit children are entered before mark_t (they come first in `seq`; ORDERED only)
 template <bool IMPL, bool ORDERED>
-__device__ __forceinline__ uint32_t children_general(const DNode* __restrict__ nodes, const DNode& nd, const DRay& r, double tmax0, uint32_t& seq)
+__device__ __forceinline__ uint32_t children_general(const DNode* __restrict__ nodes, const DNode& nd, const DRay& r, double tmax0, uint32_t& seq, double mark_t, uint32_t& n_near)
 {
     double t0c[8];
     uint32_t hm = 0;
@@ -329,7 +330,7 @@ __device__ __forceinline__ uint32_t children_general(const DNode* __restrict__ n
             }
         }
     }
-    seq = 0;
+    seq = 0; n_near = 0;
     if (hm == 0) return 0;
     if (!ORDERED) {   // any-hit: visiting order is free
         uint32_t n = 0;
@@ -350,13 +351,25 @@ __device__ __forceinline__ uint32_t children_general(const DNode* __restrict__ n
         for (int j = i + 1; j < 8; j++) rank += key[j] < key[i] ? (1u << (4 * i)) : (1u << (4 * j));   // ties: the lower index comes first
 #pragma unroll
     for (int i = 0; i < 8; i++) seq |= (uint32_t)i << (((rank >> (4 * i)) & 15u) * 4u);
+    if (mark_t < CUDART_INF) {
+        uint32_t far = 0;
+#pragma unroll
+        for (int i = 0; i < 8; i++) far |= (t0c[i] >= mark_t ? 1u : 0u) << i;
+        n_near = (uint32_t)__popc(hm & ~far);
+    } else n_near = (uint32_t)__popc(hm);
     return (uint32_t)__popc(hm);
 }
 // one interior step: the hit children of nd in visiting order (4 bits each in seq), their number returned
 template <bool IMPL, bool ORDERED>
 __device__ __forceinline__ uint32_t interior_step(const DNode* __restrict__ nodes, const DNode& nd, const DRay& r, double tmax0, uint32_t& seq)
 {
-    return children_general<IMPL, ORDERED>(nodes, nd, r, tmax0, seq);
+    uint32_t n_near;
+    return children_general<IMPL, ORDERED>(nodes, nd, r, tmax0, seq, CUDART_INF, n_near);
+}
+template <bool IMPL>
+__device__ __forceinline__ uint32_t interior_step_marked(const DNode* __restrict__ nodes, const DNode& nd, const DRay& r, uint32_t& seq, double mark_t, uint32_t& n_near)
+{
+    return children_general<IMPL, true>(nodes, nd, r, CUDART_INF, seq, mark_t, n_near);
 }
 __device__ __forceinline__ uint32_t child_node(const DNode& nd, uint32_t c) { return nd.child + __popc(nd.mask & ((1u << c) - 1u)); }
 
@@ -486,13 +499,17 @@ __device__ __forceinline__ double tex_alpha(const DScene& S, uint32_t id, double
     return tex_pixel(S, t, u, v)[3] / 255.0;
 }
 // `drand() < material.getAlpha(uv) || IOR != 1` (raytracer.h:455,:297) with an occurrence-keyed counter draw
-__device__ __forceinline__ bool alpha_pass(const DScene& S, uint32_t prim, uint32_t node, double u, double v, uint64_t seed, uint64_t path, uint64_t depth, uint64_t site)
+// `frac` (when given) is set when the candidate was cut out at a FRACTIONAL alpha (0 < a < 1): another occurrence of the same
+// primitive in another leaf draws again and may pass — the closest-hit walk must not prune behind such a candidate (trace_walk).
+__device__ __forceinline__ bool alpha_pass(const DScene& S, uint32_t prim, uint32_t node, double u, double v, uint64_t seed, uint64_t path, uint64_t depth, uint64_t site, bool* frac = nullptr)
 {
     const gi_material& m = S.mats[S.prim_mat[prim]];
     if (m.ior != 1) return true;
     double a = m.opacity * tex_alpha(S, m.diffuse_tex, u, v);
     if (a >= 1.0) return true;
-    return gi_rand(seed, path, depth, SITE(site, ((uint64_t)node << 28) ^ prim)) < a;
+    const bool pass = gi_rand(seed, path, depth, SITE(site, ((uint64_t)node << 28) ^ prim)) < a;
+    if (frac) *frac = !pass && a > 0.0;
+    return pass;
 }
 
 // uv of a uv-writing primitive at barycentrics (u,v) (entities.h:482 for triangles, :93-96 for spheres)
@@ -518,9 +535,31 @@ __device__ __forceinline__ void prim_uv_at(const DScene& S, uint32_t prim, d3 hi
 // it is the first or STRICTLY closer in |hit-o|^2; the walk stops after the first leaf in which an accepted hit lies
 // inside the leaf box (raytracer.h:446-472).  There is deliberately no pruning against the best distance: the reference
 // has none, and keeping its exact visiting rule is what makes ids bit-identical.
+//
+// What the walk does NOT keep is the reference's walking on after the result is final.  Whenever the accepted hit was first met from a
+// leaf that does not contain it (a triangle is stored in every leaf it overlaps), the reference never stops: the same hit met again in
+// the leaf that does contain it is not STRICTLY closer, so `term` is never set (raytracer.h:457-466) and every remaining leaf along the
+// ray is tested — 60-75 % of all node and primitive tests on the foliage / atrium stand-ins.  Nothing met in a node the ray enters at
+// t0 >= t_hit can be accepted: |hit - o|^2 is monotone in the ray parameter, and a closer hit POINT lies in a leaf entered before t_hit,
+// which is visited.  One exception: a candidate cut out at a FRACTIONAL alpha draws again in every other leaf that holds it
+// (raytracer.h:455) and may be accepted there.  Rules (oracle/gi_oracle.c trace_one_cot(prune = 1) follows the same ones and counts the
+// same tests; hits, ids, uvs are those of the unpruned walk bit for bit):
+//   R1  a child entered at t0 >= t_hit (t_hit of the moment it is tested) is marked `beyond` (scenes without stochastic alpha: it is
+//       simply not taken — the slab test runs against the segment [0, t_hit));
+//   R2  a node popped unmarked while a hit exists is marked when its own t0 >= t_hit (entries pushed before the hit was found);
+//   R3  a marked node is dropped when it is reached, provided no fractional-alpha rejection lies in front of the hit
+//       (t_hit <= t_frac); otherwise it is walked like the reference does.
+// Leaves are reached in ascending t0, so when R3 drops a node every leaf entered before t_hit has been tested already.
+#define GI_NODE_BEYOND 0x80000000u
+#ifdef GI_NO_PRUNE
+#define GI_PRUNE_T(t) CUDART_INF
+#else
+#define GI_PRUNE_T(t) (t)
+#endif
+#define GI_NODE_INDEX 0x7fffffffu
 struct DHit {
     uint32_t prim;     // GI_NO_HIT on miss
-    double t, u, v;    // ray parameter and barycentrics (triangles)
+    double t, u, v;    // ray parameter (+inf on a miss: the walk's pruning bound) and barycentrics (triangles)
     double tu, tv;     // uv as RayTracer::trace returns it (FULL traversal only; otherwise derived from prim,u,v)
     d3 n;              // cone normal (cones only)
 };
@@ -529,13 +568,31 @@ struct DHit {
 // ray is done (stack empty, or the stop rule fired) — or, with BAIL, until fewer than `min_active` lanes of the warp are still
 // walking (*warp_active, a shared-memory counter each lane decrements when its ray is done), so that a persistent kernel can
 // hand the idle lanes new rays (k_bounce_p).
-struct TraceState { int sp; bool term; double best_d2, cur_tu, cur_tv; };
+struct TraceState { int sp; bool term; double best_d2, cur_tu, cur_tv, frac_t; };   // frac_t: see R1-R3 above (+inf: none); t_hit is DHit::t (+inf while there is no hit)
+
+// R2 + R3 for a node taken off the stack
+template <bool FULL>
+__device__ __forceinline__ bool node_dropped(const DNode& nd, uint32_t entry, const DRay& r, double hit_t, double frac_t)
+{
+#ifdef GI_NO_PRUNE   // A/B switch: the reference's full walk (profiles/r02/README.md)
+    return false;
+#endif
+    if (!(hit_t < CUDART_INF)) return false;                         // no hit yet
+    if (FULL) {
+        if (hit_t > frac_t) return false;                             // a fractional-alpha rejection in front of the hit: the reference's walk
+        if (entry & GI_NODE_BEYOND) return true;                      // R1 mark
+    }
+#ifdef GI_R2_LEAF_ONLY   // A/B switch: interior nodes popped late are expanded (their children fail R1) instead of slab-tested
+    if (nd.mask != 0) return false;
+#endif
+    return box_entry(nd.bmin, nd.bmax, r, 0.0, hit_t) < 0.0;          // R2: entered at or beyond the hit
+}
 
 __device__ __forceinline__ bool trace_begin(const DScene& S, const DRay& r, DHit& out, TraceState& st, TStack& stack, uint32_t& n_node)
 {
-    st.sp = 0; st.term = false; st.best_d2 = 0;
+    st.sp = 0; st.term = false; st.best_d2 = 0; st.frac_t = CUDART_INF;
     st.cur_tu = 0; st.cur_tv = 0;   // `uv` local of RayTracer::trace: survives across candidates (raytracer.h:385)
-    out.prim = GI_NO_HIT; out.t = 0; out.u = 0; out.v = 0; out.tu = 0; out.tv = 0; out.n = mk3(0, 0, 0);
+    out.prim = GI_NO_HIT; out.t = CUDART_INF; out.u = 0; out.v = 0; out.tu = 0; out.tv = 0; out.n = mk3(0, 0, 0);
     if (S.n_nodes == 0) return false;
     DNode root = load_node(S.nodes, 0);
     n_node++;
@@ -564,23 +621,39 @@ __device__ __forceinline__ void trace_walk(const DScene& S, const DRay& r, uint6
 {
     int sp = st.sp;
     bool term = st.term;
+    double frac_t = st.frac_t;
     // "while-while": every lane first walks interior nodes until a leaf is on top (the warp re-converges after that
     // inner loop), then all lanes test primitives together — instead of mixing leaf work and interior work in one loop.
     while (sp > 0 && !term) {
-        uint32_t ni = stack_pop(stack, sp);
-        DNode nd = load_node(S.nodes, ni);
-        bool have_leaf = true;
-        while (nd.mask != 0) {
-            // interior: the hit children in visiting order; the nearest is walked into at once, the others are pushed far-to-near
-            uint32_t seq;
-            n_node += __popc(nd.mask);
-            const uint32_t n = interior_step<IMPL, true>(S.nodes, nd, r, CUDART_INF, seq);
-            for (int j = (int)n - 1; j >= 1; j--) stack_push(stack, sp, child_node(nd, (seq >> (4 * j)) & 7u), S.err);
-            if (n == 0) {
-                if (sp == 0) { have_leaf = false; break; }
-                ni = stack_pop(stack, sp);
-            } else ni = child_node(nd, seq & 7u);
+        // ONE pop site, ONE node load, ONE drop test for both ways of getting the next node (nearest child / popped entry): with a copy
+        // of the load sequence in each branch the lanes of a warp waited for each other's loads (bounce kernels +45 %,
+        // profiles/r02/ab_t11.txt)
+        bool need_pop = true, have_leaf = false;
+        uint32_t ent = 0, ni = 0;
+        DNode nd;
+        for (;;) {
+            if (need_pop) {
+                if (sp == 0) break;
+                ent = stack_pop(stack, sp);
+            }
+            ni = ent & GI_NODE_INDEX;
             nd = load_node(S.nodes, ni);
+            if (need_pop && node_dropped<FULL>(nd, ent, r, out.t, frac_t)) continue;   // R2 / R3
+            if (nd.mask == 0) { have_leaf = true; break; }
+            // interior: the hit children in visiting order; the nearest is walked into at once, the others are pushed far-to-near
+            uint32_t seq, n;
+            n_node += __popc(nd.mask);
+            if (FULL) {
+                uint32_t n_near;
+                n = interior_step_marked<IMPL>(S.nodes, nd, r, seq, GI_PRUNE_T(out.t), n_near);
+                if (n_near == 0 && out.t <= frac_t) n = 0;   // every child is beyond the hit and R3 holds: reached next, they would all be dropped
+                for (int j = (int)n - 1; j >= 1; j--) stack_push(stack, sp, child_node(nd, (seq >> (4 * j)) & 7u) | ((uint32_t)j >= n_near ? GI_NODE_BEYOND : 0u), S.err);
+            } else {
+                n = interior_step<IMPL, true>(S.nodes, nd, r, GI_PRUNE_T(out.t), seq);   // R1 + R3 at once: the segment ends at the hit
+                for (int j = (int)n - 1; j >= 1; j--) stack_push(stack, sp, child_node(nd, (seq >> (4 * j)) & 7u), S.err);
+            }
+            need_pop = n == 0;
+            if (!need_pop) ent = child_node(nd, seq & 7u);
         }
         if (have_leaf) {
             const DLeafRef* refs = S.refs + nd.prim_off;
@@ -598,7 +671,13 @@ __device__ __forceinline__ void trace_walk(const DScene& S, const DRay& r, uint6
                 d3 hit = r.o + r.d * t;
                 if (FULL) {
                     if (flags & LF_WRITES_UV) prim_uv_at(S, prim, hit, u, v, st.cur_tu, st.cur_tv);
-                    if ((flags & LF_ALPHA) && !alpha_pass(S, prim, ni, st.cur_tu, st.cur_tv, seed, path, depth, SITE_ALPHA_TRACE)) continue;
+                    if (flags & LF_ALPHA) {
+                        bool frac = false;
+                        if (!alpha_pass(S, prim, ni, st.cur_tu, st.cur_tv, seed, path, depth, SITE_ALPHA_TRACE, &frac)) {
+                            if (frac && t < frac_t) frac_t = t;
+                            continue;
+                        }
+                    }
                 }
                 double d2 = len2(hit - r.o);
                 if (out.prim == GI_NO_HIT || d2 < st.best_d2) {
@@ -613,6 +692,7 @@ __device__ __forceinline__ void trace_walk(const DScene& S, const DRay& r, uint6
             else if (*warp_active < min_active) break;             // too few lanes still walking: go and fetch rays
         }
     }
+    st.frac_t = frac_t;
     st.sp = sp; st.term = term;
 }
 
@@ -693,7 +773,7 @@ __device__ __forceinline__ void trace_closest_warp(const DScene& S, const DRay& 
                                                    uint32_t& n_node, uint32_t& n_prim)
 {
     int sp = 0;
-    out.prim = GI_NO_HIT; out.t = 0; out.u = 0; out.v = 0; out.tu = 0; out.tv = 0; out.n = mk3(0, 0, 0);
+    out.prim = GI_NO_HIT; out.t = CUDART_INF; out.u = 0; out.v = 0; out.tu = 0; out.tv = 0; out.n = mk3(0, 0, 0);
     double best_d2 = 0, cur_tu = 0, cur_tv = 0;
     if (S.n_nodes == 0) return;
     {
@@ -705,10 +785,13 @@ __device__ __forceinline__ void trace_closest_warp(const DScene& S, const DRay& 
         __syncwarp();
     }
     bool term = false;
+    double frac_t = CUDART_INF;   // R1-R3 of trace_walk, uniform over the warp (t_hit is out.t)
     while (sp > 0 && !term) {
-        uint32_t ni = stack[sp - 1]; sp--;
+        const uint32_t ent = stack[sp - 1]; sp--;
+        const uint32_t ni = ent & GI_NODE_INDEX;
         __syncwarp();
         DNode nd = load_node(S.nodes, ni);
+        if (node_dropped<FULL>(nd, ent, r, out.t, frac_t)) continue;
         if (nd.mask == 0) {
             n_prim += nd.prim_cnt;
             for (uint32_t base = 0; base < nd.prim_cnt; base += 32) {
@@ -739,7 +822,13 @@ __device__ __forceinline__ void trace_closest_warp(const DScene& S, const DRay& 
                     d3 hit = r.o + r.d * ct;
                     if (FULL) {
                         if (cflags & LF_WRITES_UV) prim_uv_at(S, cprim, hit, cu, cv, cur_tu, cur_tv);
-                        if ((cflags & LF_ALPHA) && !alpha_pass(S, cprim, ni, cur_tu, cur_tv, seed, path, depth, SITE_ALPHA_TRACE)) continue;
+                        if (cflags & LF_ALPHA) {
+                            bool frac = false;
+                            if (!alpha_pass(S, cprim, ni, cur_tu, cur_tv, seed, path, depth, SITE_ALPHA_TRACE, &frac)) {
+                                if (frac && ct < frac_t) frac_t = ct;
+                                continue;
+                            }
+                        }
                     }
                     double d2 = len2(hit - r.o);
                     if (out.prim == GI_NO_HIT || d2 < best_d2) {
@@ -752,13 +841,17 @@ __device__ __forceinline__ void trace_closest_warp(const DScene& S, const DRay& 
             continue;
         }
         n_node += __popc(nd.mask);
+        // R1: without stochastic alpha the children are tested against the segment [0, t_hit); with it, against the whole ray and marked
+        const double seg = FULL ? CUDART_INF : GI_PRUNE_T(out.t);
         double t0 = -1.0; uint32_t cidx = 0;
         if (lane < 8 && ((nd.mask >> lane) & 1u)) {
             cidx = nd.child + __popc(nd.mask & ((1u << lane) - 1u));
-            if (IMPL) { PlaneT T; plane_params(nd, r, T); t0 = child_entry(T, lane, r, 0.0, CUDART_INF); }
-            else { DNode ch = load_node(S.nodes, cidx); t0 = box_entry(ch.bmin, ch.bmax, r, 0.0, CUDART_INF); }
+            if (IMPL) { PlaneT T; plane_params(nd, r, T); t0 = child_entry(T, lane, r, 0.0, seg); }
+            else { DNode ch = load_node(S.nodes, cidx); t0 = box_entry(ch.bmin, ch.bmax, r, 0.0, seg); }
+            if (FULL && t0 >= GI_PRUNE_T(out.t)) cidx |= GI_NODE_BEYOND;
         }
         uint32_t valid = __ballot_sync(0xffffffffu, t0 >= 0.0) & 0xffu;
+        if (FULL && out.t <= frac_t && (__ballot_sync(0xffffffffu, t0 >= 0.0 && !(cidx & GI_NODE_BEYOND)) & 0xffu) == 0) valid = 0;   // all beyond, R3 holds: none is pushed
         // far-to-near on the stack: rank = children that come before me in descending (t0, child index) order
         int rank = 0;
 #pragma unroll
@@ -766,7 +859,7 @@ __device__ __forceinline__ void trace_closest_warp(const DScene& S, const DRay& 
             double tj = __shfl_sync(0xffffffffu, t0, j);
             if (((valid >> j) & 1u) && j != lane && (tj > t0 || (tj == t0 && j > lane))) rank++;
         }
-        if (t0 >= 0.0 && sp + rank < GI_STACK_MAX) stack[sp + rank] = cidx;
+        if (((valid >> lane) & 1u) && lane < 8 && sp + rank < GI_STACK_MAX) stack[sp + rank] = cidx;
         sp += __popc(valid);
         if (sp > GI_STACK_MAX) { sp = GI_STACK_MAX; if (lane == 0) atomicOr(S.err, GI_DEV_ERR_STACK); }
         __syncwarp();

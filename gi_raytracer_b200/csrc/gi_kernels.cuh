@@ -1093,7 +1093,7 @@ __global__ void __launch_bounds__(GI_BLOCK, GI_MINB) k_bounce_p(DScene S, gi_ren
     const unsigned lane = threadIdx.x & 31u;
     const int wib = threadIdx.x >> 5;
     GI_TSTACK_DECL(stack);
-    TraceState st; st.sp = 0; st.term = false; st.best_d2 = 0; st.cur_tu = 0; st.cur_tv = 0;
+    TraceState st; st.sp = 0; st.term = false; st.best_d2 = 0; st.cur_tu = 0; st.cur_tv = 0; st.frac_t = CUDART_INF;
     DHit h; h.prim = GI_NO_HIT;
     DRay r = ray_as_stored(mk3(0, 0, 0), mk3(1, 0, 0));
     uint32_t qi = 0, path = 0, wn = 0, wp = 0;

@@ -327,6 +327,9 @@ static inline int box_overlap(const double* a, const double* o)
  * primitives (entities.h)
  * ---------------------------------------------------------------------------------------------------------- */
 typedef struct { v3 p, n; double u, v; } hit_t; /* u,v only written when the primitive writes uv */
+/* ray parameter of the last successful primitive test of this thread (what the device keeps as DHit::t); only the pruned
+ * canonical traversal below reads it */
+static __thread double g_last_t;
 
 /* triangle::intersect(ray, hit, normal, uv) (entities.h:443-490) */
 static inline int tri_hit(const gi_scene_desc* sc, uint32_t id, const ray_t* r, v3* hp, v3* hn, double* huv)
@@ -346,6 +349,7 @@ static inline int tri_hit(const gi_scene_desc* sc, uint32_t id, const ray_t* r, 
     if (v < 0 || u + v > 1) return 0;
     double t = dot(edge2, q) * inv_det;
     if (t <= 0) return 0;
+    g_last_t = t;
     *hp = add(r->o, scale(r->d, t));
     const double* nn = sc->prim_nrm + 9 * (size_t)id;
     v3 n0 = ld3(nn), n1 = ld3(nn + 3), n2 = ld3(nn + 6);
@@ -375,8 +379,8 @@ static inline int sphere_hit(const gi_scene_desc* sc, uint32_t id, const ray_t* 
     double t_2 = -1 * d + sr;
     if (t_1 < 0 && t_2 < 0) return 0;
     v3 ip;
-    if ((t_1 < t_2 && t_1 > 0) || t_2 < 0) ip = add(r->o, scale(r->d, t_1));
-    else ip = add(r->o, scale(r->d, t_2));
+    if ((t_1 < t_2 && t_1 > 0) || t_2 < 0) { ip = add(r->o, scale(r->d, t_1)); g_last_t = t_1; }
+    else { ip = add(r->o, scale(r->d, t_2)); g_last_t = t_2; }
     *hp = ip;
     *hn = normalize(sub(ip, pos));
     v3 dd = V((pos.x - ip.x) / rad, (pos.y - ip.y) / rad, (pos.z - ip.z) / rad);
@@ -430,6 +434,7 @@ static inline int cone_hit(const gi_scene_desc* sc, uint32_t id, const ray_t* r,
         if (phi < 0.) phi += 2.f * GO_PI;
         if (phit.z < 0 || phit.z > height || phi > phiMax) return 0;
     }
+    g_last_t = thit;
     *hp = add(r->o, scale(r->d, thit));
     double vpar = phit.z / height;
     v3 dpdu = V(-phiMax * phit.y, phiMax * phit.x, 0);
@@ -494,14 +499,18 @@ void go_material_eval(const gi_scene_desc* sc, size_t n, const uint32_t* prim, c
 /* alpha cut-out decision `drand() < getAlpha(uv) || IOR != 1` (raytracer.h:455, :297).  The draw is keyed by the
  * (leaf node, primitive) occurrence, so duplicates of a primitive in several leaves draw independently like the
  * reference, while the outcome does not depend on visiting order. */
+static __thread int g_alpha_frac;   /* the last alpha_pass rejected a candidate whose alpha is fractional (0 < a < 1): another occurrence of it may pass */
 static inline int alpha_pass(const gi_scene_desc* sc, uint32_t prim, uint32_t node, const double* uv, uint64_t seed, uint64_t path, uint64_t depth, uint64_t site)
 {
     const gi_material* m = &sc->mats[sc->prim_mat[prim]];
+    g_alpha_frac = 0;
     if (g_xs) { double r = xs_next(g_xs); return r < mat_alpha(sc, m, uv) || m->ior != 1; }   /* replay: the reference's stream and order */
     if (m->ior != 1) return 1;
     double a = mat_alpha(sc, m, uv);
     if (a >= 1.0) return 1; /* drand() < 1 holds for every draw of this generator ([0,1)) */
-    return go_rand(seed, path, depth, SITE(site, ((uint64_t)node << 28) ^ prim)) < a;
+    const int pass = go_rand(seed, path, depth, SITE(site, ((uint64_t)node << 28) ^ prim)) < a;
+    g_alpha_frac = !pass && a > 0.0;
+    return pass;
 }
 
 /* ------------------------------------------------------------------------------------------------------------
@@ -576,28 +585,50 @@ void go_trace_closest(const gi_scene_desc* sc, size_t n, const double* org, cons
 /* Canonical ordered traversal: pop node; test each existing child box; descend front-to-back (entry t0,
  * ties in child order); at a non-empty leaf test every primitive in stored order; stop after the first leaf in which
  * an accepted hit lies inside the leaf box.  Same acceptance rules as trace_one; counts box and primitive tests. */
-typedef struct { uint32_t node; double t0; } stk_t;
-static void trace_one_cot(const gi_scene_desc* sc, const ray_t* r, uint64_t seed, uint64_t path, uint64_t depth, closest_t* out, uint32_t* nn, uint32_t* np)
+typedef struct { uint32_t node; double t0; int beyond; } stk_t;
+/* prune != 0: the traversal the device executes (same hits, fewer tests; this variant counts them).
+ * The reference keeps walking to the end of the ray whenever the accepted hit was first met from a leaf that does not contain it: the
+ * same hit met again is not STRICTLY closer, so `term` never fires (raytracer.h:457-466).  But nothing met in a node the ray enters at
+ * t0 >= t_hit can be accepted — |hit - o|^2 is monotone in the ray parameter, and a closer hit point lies in a leaf entered before
+ * t_hit, which is visited — with one exception: a candidate cut out at a FRACTIONAL alpha draws again in every other leaf that holds
+ * it (raytracer.h:455) and may be accepted there.  Rules (gi_device.cuh trace_walk follows them to the letter):
+ *   R1  a child entered at t0 >= t_hit (t_hit of the moment it is tested) is marked `beyond`;
+ *   R2  a node popped unmarked while a hit exists is marked when its own t0 >= t_hit (entries pushed before the hit was found);
+ *   R3  a marked node is dropped when it is reached, provided no fractional-alpha rejection lies in front of the hit
+ *       (t_hit <= t_frac); otherwise it is walked like the reference does.
+ * Leaves are reached in ascending t0, so when R3 drops a node every leaf entered before t_hit has been tested already and t_frac
+ * is final for the region in front of the hit. */
+static void trace_one_cot(const gi_scene_desc* sc, const ray_t* r, uint64_t seed, uint64_t path, uint64_t depth, closest_t* out, uint32_t* nn, uint32_t* np, int prune)
 {
+    double hit_t = INFINITY, frac_t = INFINITY;   /* ray parameter of the accepted hit; least ray parameter of a fractional-alpha rejection */
     stk_t stack[8 * 64]; int sp = 0;
     uint32_t n_node = 0, n_prim = 0;
     v3 hit = V(0, 0, 0), norm = V(0, 0, 0); double uv[2] = { 0, 0 };
     out->hit = 0; out->prim = GI_NO_HIT; out->p = V(0, 0, 0); out->n = V(0, 0, 0); out->uv[0] = out->uv[1] = 0;
     double t0;
-    if (sc->n_nodes) { n_node++; if (box_hit(sc->node_box, r, 0, INFINITY, &t0)) { stack[sp].node = 0; stack[sp].t0 = t0; sp++; } }
+    if (sc->n_nodes) { n_node++; if (box_hit(sc->node_box, r, 0, INFINITY, &t0)) { stack[sp].node = 0; stack[sp].t0 = t0; stack[sp].beyond = 0; sp++; } }
     int term = 0;
     while (sp > 0 && !term) {
         stk_t cur = stack[--sp];
         uint8_t mask = sc->node_mask[cur.node];
+        if (prune) {
+            int beyond = cur.beyond;
+            if (!beyond && out->hit && cur.t0 >= hit_t) beyond = 1;            /* R2 */
+            if (beyond && hit_t <= frac_t) continue;                            /* R3 */
+        }
         if (!mask) {
             const uint32_t* ids = sc->leaf_prims + sc->node_prim_off[cur.node];
             for (uint32_t k = 0; k < sc->node_prim_cnt[cur.node]; k++) {
                 uint32_t id = ids[k]; n_prim++;
-                if (prim_hit(sc, id, r, &hit, &norm, uv) && alpha_pass(sc, id, cur.node, uv, seed, path, depth, SITE_ALPHA_TRACE)) {
-                    if (!out->hit || len2(sub(hit, r->o)) < len2(sub(out->p, r->o))) {
-                        out->prim = id; out->p = hit; out->n = norm; out->uv[0] = uv[0]; out->uv[1] = uv[1]; out->hit = 1;
-                        if (box_contains(sc->node_box + 6 * (size_t)cur.node, hit)) term = 1;
-                    }
+                if (!prim_hit(sc, id, r, &hit, &norm, uv)) continue;
+                if (!alpha_pass(sc, id, cur.node, uv, seed, path, depth, SITE_ALPHA_TRACE)) {
+                    if (g_alpha_frac && g_last_t < frac_t) frac_t = g_last_t;
+                    continue;
+                }
+                if (!out->hit || len2(sub(hit, r->o)) < len2(sub(out->p, r->o))) {
+                    out->prim = id; out->p = hit; out->n = norm; out->uv[0] = uv[0]; out->uv[1] = uv[1]; out->hit = 1;
+                    hit_t = g_last_t;
+                    if (box_contains(sc->node_box + 6 * (size_t)cur.node, hit)) term = 1;
                 }
             }
             continue;
@@ -609,7 +640,7 @@ static void trace_one_cot(const gi_scene_desc* sc, const ray_t* r, uint64_t seed
             if (box_hit(sc->node_box + 6 * (size_t)c, r, 0, INFINITY, &t0)) {
                 int j = nc++;
                 while (j > 0 && ch[j - 1].t0 > t0) { ch[j] = ch[j - 1]; j--; }
-                ch[j].node = c; ch[j].t0 = t0;
+                ch[j].node = c; ch[j].t0 = t0; ch[j].beyond = out->hit && t0 >= hit_t;   /* R1 */
             }
             c++;
         }
@@ -618,18 +649,27 @@ static void trace_one_cot(const gi_scene_desc* sc, const ray_t* r, uint64_t seed
     if (nn) *nn = n_node;
     if (np) *np = n_prim;
 }
-void go_trace_closest_cot(const gi_scene_desc* sc, size_t n, const double* org, const double* dir, uint64_t alpha_seed, uint32_t* prim, double* hit, uint32_t* n_node_tests, uint32_t* n_prim_tests)
+static void trace_closest_cot_n(const gi_scene_desc* sc, size_t n, const double* org, const double* dir, uint64_t alpha_seed, uint32_t* prim, double* hit, uint32_t* n_node_tests, uint32_t* n_prim_tests, int prune)
 {
 #pragma omp parallel for schedule(dynamic, 256)
     for (long i = 0; i < (long)n; i++) {
         ray_t r = ray_as_stored(ld3(org + 3 * i), ld3(dir + 3 * i));
         closest_t c; uint32_t a, b;
-        trace_one_cot(sc, &r, alpha_seed, (uint64_t)i, 0, &c, &a, &b);
+        trace_one_cot(sc, &r, alpha_seed, (uint64_t)i, 0, &c, &a, &b, prune);
         if (prim) prim[i] = c.prim;
         if (hit) st3(hit + 3 * i, c.p);
         if (n_node_tests) n_node_tests[i] = a;
         if (n_prim_tests) n_prim_tests[i] = b;
     }
+}
+
+void go_trace_closest_cot(const gi_scene_desc* sc, size_t n, const double* org, const double* dir, uint64_t alpha_seed, uint32_t* prim, double* hit, uint32_t* n_node_tests, uint32_t* n_prim_tests)
+{
+    trace_closest_cot_n(sc, n, org, dir, alpha_seed, prim, hit, n_node_tests, n_prim_tests, 0);
+}
+void go_trace_closest_cot_pruned(const gi_scene_desc* sc, size_t n, const double* org, const double* dir, uint64_t alpha_seed, uint32_t* prim, double* hit, uint32_t* n_node_tests, uint32_t* n_prim_tests)
+{
+    trace_closest_cot_n(sc, n, org, dir, alpha_seed, prim, hit, n_node_tests, n_prim_tests, 1);
 }
 
 /* ------------------------------------------------------------------------------------------------------------

@@ -54,6 +54,9 @@ void go_trace_any(const gi_scene_desc* sc, size_t n, const double* org, const do
 /* canonical ordered traversal with early termination: same answers as go_trace_closest plus work counters */
 void go_trace_closest_cot(const gi_scene_desc* sc, size_t n, const double* org, const double* dir, uint64_t alpha_seed,
                           uint32_t* prim, double* hit, uint32_t* n_node_tests, uint32_t* n_prim_tests);
+/* the same hits with the device's pruning (children tested against [0, t_best) once a hit is accepted): counts what the kernels execute */
+void go_trace_closest_cot_pruned(const gi_scene_desc* sc, size_t n, const double* org, const double* dir, uint64_t alpha_seed,
+                          uint32_t* prim, double* hit, uint32_t* n_node_tests, uint32_t* n_prim_tests);
 /* Octree::intersect / Octree::intersectSorted as callable queries (octree.cpp:150-211, 256-313) */
 void go_octree_intersect(const gi_scene_desc* sc, size_t n, const double* org, const double* dir, const double* tmin, const double* tmax, uint32_t cap, uint32_t* ids,
                          uint32_t* counts);

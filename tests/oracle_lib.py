@@ -37,6 +37,7 @@ def lib():
     L.go_trace_closest.argtypes = [vp, sz, vp, vp, u64, vp, vp, vp, vp]
     L.go_trace_any.argtypes = [vp, sz, vp, vp, vp, u64, vp]
     L.go_trace_closest_cot.argtypes = [vp, sz, vp, vp, u64, vp, vp, vp, vp]
+    L.go_trace_closest_cot_pruned.argtypes = [vp, sz, vp, vp, u64, vp, vp, vp, vp]
     L.go_trace_any_cot.argtypes = [vp, sz, vp, vp, vp, u64, vp, vp, vp]
     L.go_trace_closest_replay.argtypes = [vp, sz, vp, vp, vp, vp, vp, vp, vp]
     L.go_trace_any_replay.argtypes = [vp, sz, vp, vp, vp, vp, vp]
@@ -134,14 +135,15 @@ def trace_closest(scene, org, d, alpha_seed=0):
     return prim, hit, nrm, uv
 
 
-def trace_closest_cot(scene, org, d, alpha_seed=0):
+def trace_closest_cot(scene, org, d, alpha_seed=0, pruned=False):
+    """canonical ordered traversal with test counts; pruned=True counts what the device executes (same hits)"""
     L = lib()
     org, d = _f64(org, 3), _f64(d, 3)
     n = org.shape[0]
     prim, nn, npr = (np.empty(n, dtype=np.uint32) for _ in range(3))
     hit = np.empty((n, 3))
     desc = scene.desc()
-    L.go_trace_closest_cot(C.byref(desc), n, _p(org), _p(d), alpha_seed, _p(prim), _p(hit), _p(nn), _p(npr))
+    (L.go_trace_closest_cot_pruned if pruned else L.go_trace_closest_cot)(C.byref(desc), n, _p(org), _p(d), alpha_seed, _p(prim), _p(hit), _p(nn), _p(npr))
     return prim, hit, nn, npr
 
 

@@ -395,16 +395,20 @@ def test_error_codes_and_empty_inputs(lib_built):
 
 
 def test_device_work_tallies_equal_canonical_traversal_counts(ctx, golden_cornell):
-    """The node / primitive test counters the roofline uses are those of the canonical ordered traversal,
-    counted independently on the CPU for the same rays."""
+    """The node / primitive test counters the roofline uses are those of the canonical ordered traversal with the
+    device's pruning rules R1-R3 (gi_device.cuh; oracle/gi_oracle.c trace_one_cot), counted independently on the CPU for the same
+    rays: never more than the reference's own walk, and the same hits."""
     g = golden_cornell
     sc = R.scene_from_npz(g)
     ctx.upload_scene(sc)
     ro, rd = g["ray_o_f64"].reshape(-1, 3), g["ray_d_f64"].reshape(-1, 3)
-    ctx.trace_closest(ro, rd)
+    prim, hit, _, _ = ctx.trace_closest(ro, rd)
     rays, nn, npr, _ = ctx.last_work("trace_closest")
-    _, _, cn, cp = O.trace_closest_cot(sc, ro, rd)
+    p2, h2, cn, cp = O.trace_closest_cot(sc, ro, rd, pruned=True)
+    _, _, fn, fp = O.trace_closest_cot(sc, ro, rd)
+    assert bits_equal(prim, p2) and bits_equal(hit, h2)
     assert rays == ro.shape[0] and nn == int(cn.sum()) and npr == int(cp.sum())
+    assert (cn <= fn).all() and (cp <= fp).all()
     so, sd, mt = g["sh_o_f64"].reshape(-1, 3), g["sh_d_f64"].reshape(-1, 3), g["sh_maxt2_f64"]
     ctx.trace_any(so, sd, mt)
     rays, nn, npr, _ = ctx.last_work("trace_any")
@@ -421,6 +425,28 @@ def test_device_work_tallies_equal_canonical_traversal_counts(ctx, golden_cornel
     q, dsum, csum, ssum = ctx.last_work("gather")
     _, _, nc, dl = O.PMap(g["photons_f64"].reshape(-1, 9), sc.root_box).gather(qp, qd, 32)
     assert q == qp.shape[0] and csum == int(nc.sum()) and ssum == int(np.minimum(nc, 32).sum()) and dsum == int(dl.sum())
+
+
+@pytest.mark.parametrize("name", ["cards", "mixed", "atrium", "glass"])
+def test_pruned_walk_tallies_and_hits_on_alpha_and_mesh_scenes(ctx, synth_dir, name):
+    """R1-R3 on scenes where they matter: alpha-textured cards (a fractional-alpha rejection in front of the hit must switch the
+    pruning off, raytracer.h:455), spheres / cones, the atrium of large triangles, the glass mesh.  The device's counters equal the
+    CPU count of the same rules, the hits equal the UNPRUNED walk of the reference's semantics bit for bit, and the pruning removes work."""
+    sc = _load(name, synth_dir)
+    ctx.upload_scene(sc)
+    o, d, _ = ctx.camera_rays(80, 80, 0, 0, 80, 80, 0, 1)
+    ro, rdir = random_rays(sc, 12000, seed=23)
+    o, d = np.concatenate([o, ro]), np.concatenate([d, rdir])
+    for seed in (0, 777):
+        prim, hit, nrm, uv = ctx.trace_closest(o, d, alpha_seed=seed)
+        rays, nn, npr, _ = ctx.last_work("trace_closest")
+        p1, h1, cn, cp = O.trace_closest_cot(sc, o, d, alpha_seed=seed, pruned=True)
+        p0, h0, fn, fp = O.trace_closest_cot(sc, o, d, alpha_seed=seed)
+        assert bits_equal(p0, p1) and bits_equal(prim, p0)
+        if not (sc.prim_type == 2).any():
+            assert bits_equal(h0, h1) and bits_equal(hit, h0)
+        assert rays == o.shape[0] and nn == int(cn.sum()) and npr == int(cp.sum()), (name, nn, int(cn.sum()), npr, int(cp.sum()))
+        assert (cn <= fn).all() and (cp <= fp).all() and int(cp.sum()) < int(fp.sum())
 
 
 def test_warp_per_ray_kernels_equal_thread_per_ray(lib_built, synth_dir, monkeypatch):

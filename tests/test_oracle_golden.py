@@ -63,6 +63,10 @@ def test_rays_hits_shadows_photonmap_gather(which, golden_cornell, golden_causti
     p2, h2, nn, npr = O.trace_closest_cot(sc, ro, rd)
     assert bits_equal(p2, prim) and bits_equal(h2, hit)
     assert nn.mean() > 5 and npr.mean() > 1
+    # the pruned walk the device executes (rules R1-R3): the reference's ids and hit points with no more tests than the full walk
+    p3, h3, nn3, npr3 = O.trace_closest_cot(sc, ro, rd, pruned=True)
+    assert bits_equal(p3, g["hit_id_u32"]) and bits_equal(h3, g["hit_pos_f64"].reshape(-1, 3))
+    assert (nn3 <= nn).all() and (npr3 <= npr).all()
     # shadow rays
     vis = O.trace_any(sc, g["sh_o_f64"].reshape(-1, 3), g["sh_d_f64"].reshape(-1, 3), g["sh_maxt2_f64"])
     assert bits_equal(vis, g["sh_vis_u8"])
