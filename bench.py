@@ -469,6 +469,7 @@ def main():
                     "achieved": achieved, "peak": peak, "peak_kind": peak_kind, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                     "algorithmic_bytes_per_step": dom_bytes, "kernel_ms_per_step": dom_ms, "launches_per_step": fam_launches[dom],
                     "families": famd,
+                    "counts": "node / primitive tests are the device's own tallies = the canonical ordered traversal of SURVEY 8d with the walk's pruning rules R1-R3 (what the kernels execute; tests/test_gpu_parity.py checks them against the CPU count of the same rules) - the reference's unpruned walk tests more, so these bytes are the smaller, executed figure",
                     "timing": "families: CUDA events around each kernel family in one extra frame rendered on ONE stream right after the timed region (inside the timed, overlapped frames the families run beside each other and their event windows cover one another); frame: the timed region itself",
                     "families_overlapped_ms_per_step": {"bounce": float(last.trace_ms), "direct": float(last.shadow_ms), "gather": float(last.gather_ms)},
                     "frame_serial_ms": float(serial.total_ms),

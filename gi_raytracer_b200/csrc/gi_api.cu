@@ -1308,10 +1308,11 @@ static int render_device(gi_ctx* ctx, const gi_render_params* P, int x0, int y0,
     // (caustics) and 60 (glass).  (A timing-based choice between the two forms flipped from run to run on scenes where they
     // are within a few per cent of each other, which made frame times bimodal.)
     const bool tunable = total_paths >= (1u << 20);   // small calls do not update the statistic
-    // (round 2, 64-register kernels, frame ms classic -> refetch: atrium 264 -> 224, but foliage 212 -> 227, glass 49.2 -> 52.4, caustics 24.6 -> 25.8:
-    //  the foliage stand-in walks as many nodes per ray as the atrium (213 vs 139) but tests MORE primitives than nodes (219 vs 76) — its
-    //  warps are held up by leaf work that all lanes share, not by a few long walks, and refetch only adds its overhead there)
-    const bool long_walks = ctx->nodes_per_ray > 0 ? (ctx->nodes_per_ray > 100.0 && ctx->prims_per_ray < ctx->nodes_per_ray) : (ctx->S.n_nodes > 200000u && !ctx->S.full);
+    // (round 2, 64-register kernels, before the pruned walk; frame ms classic -> refetch: atrium 264 -> 224, foliage 212 -> 227, glass 49.2 -> 52.4,
+    //  caustics 24.6 -> 25.8.  With the pruned walk (rules R1-R3 of gi_device.cuh) the long tails inside a warp are what is left of the walks on
+    //  the two stand-ins, and refetch wins on both: atrium 164 -> 153, foliage 133 -> 124; glass 157 -> 169 still loses (profiles/r02/ab_t14.txt).
+    //  Node tests per ray after pruning: caustics 24, glass 45, foliage ~85, atrium 105.)
+    const bool long_walks = ctx->nodes_per_ray > 0 ? ctx->nodes_per_ray > 64.0 : ctx->S.n_nodes > 200000u;
     const bool persistent = ctx->bounce_mode == 2 || (ctx->bounce_mode == 0 && long_walks);
     uint64_t n_closest = 0, n_shadow = 0, n_gather = 0, launches = 0;
     for (const char* f : { "bounce", "direct", "gather", "tail", "bin" }) fam_reset(ctx, f);

@@ -542,8 +542,8 @@ __device__ __forceinline__ void prim_uv_at(const DScene& S, uint32_t prim, d3 hi
 // ray is tested — 60-75 % of all node and primitive tests on the foliage / atrium stand-ins.  Nothing met in a node the ray enters at
 // t0 >= t_hit can be accepted: |hit - o|^2 is monotone in the ray parameter, and a closer hit POINT lies in a leaf entered before t_hit,
 // which is visited.  One exception: a candidate cut out at a FRACTIONAL alpha draws again in every other leaf that holds it
-// (raytracer.h:455) and may be accepted there.  Rules (oracle/gi_oracle.c trace_one_cot(prune = 1) follows the same ones and counts the
-// same tests; hits, ids, uvs are those of the unpruned walk bit for bit):
+// (raytracer.h:455) and may be accepted there.  Rules (the test suite's CPU checker counts the same rules independently and compares
+// the tallies; hits, ids, uvs are those of the unpruned walk bit for bit):
 //   R1  a child entered at t0 >= t_hit (t_hit of the moment it is tested) is marked `beyond` (scenes without stochastic alpha: it is
 //       simply not taken — the slab test runs against the segment [0, t_hit));
 //   R2  a node popped unmarked while a hit exists is marked when its own t0 >= t_hit (entries pushed before the hit was found);
