@@ -282,6 +282,8 @@ extern "C" int gi_create(int device, gi_ctx** out)
     cudaMemset(ctx->b_err.p, 0, 16);
     ctx->S.err = ctx->b_err.as<uint32_t>();
     ctx->n_sm = prop.multiProcessorCount > 0 ? prop.multiProcessorCount : 148;
+    // k_gather_sorted keeps 24 KB of heaps per 64-thread block: nine blocks per SM need the largest shared-memory carve-out
+    cudaFuncSetAttribute(k_gather_sorted, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared);
     ctx->S.halton_tab = ctx->b_htab.as<uint16_t>();
     ctx->S.halton_dims = ctx->b_hdims.as<DHaltonDim>();
     if (getenv("GI_NO_IMPLICIT_BOXES")) ctx->no_implicit = true;

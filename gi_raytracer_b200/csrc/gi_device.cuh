@@ -188,7 +188,6 @@ __device__ __forceinline__ bool box_contains(const double* bmin, const double* b
     return p.x >= bmin[0] && p.y >= bmin[1] && p.z >= bmin[2] && p.x < bmax[0] && p.y < bmax[1] && p.z < bmax[2];
 }
 
-
 // ---- implicit child boxes ----------------------------------------------------------------------------------------------------
 // Octree::Node::partition (octree.cpp:318-328) derives the eight child boxes from the parent box alone: per axis the planes
 // are P0 = min, P1 = mid = min + .5*(max-min) (bit-identical to min + .5*d), P2 = mid + .5*d and P3 = max; the lower half is
@@ -582,9 +581,6 @@ __device__ __forceinline__ bool node_dropped(const DNode& nd, uint32_t entry, co
         if (hit_t > frac_t) return false;                             // a fractional-alpha rejection in front of the hit: the reference's walk
         if (entry & GI_NODE_BEYOND) return true;                      // R1 mark
     }
-#ifdef GI_R2_LEAF_ONLY   // A/B switch: interior nodes popped late are expanded (their children fail R1) instead of slab-tested
-    if (nd.mask != 0) return false;
-#endif
     return box_entry(nd.bmin, nd.bmax, r, 0.0, hit_t) < 0.0;          // R2: entered at or beyond the hit
 }
 
@@ -622,38 +618,67 @@ __device__ __forceinline__ void trace_walk(const DScene& S, const DRay& r, uint6
     int sp = st.sp;
     bool term = st.term;
     double frac_t = st.frac_t;
-    // "while-while": every lane first walks interior nodes until a leaf is on top (the warp re-converges after that
-    // inner loop), then all lanes test primitives together — instead of mixing leaf work and interior work in one loop.
+    // Two forms of the search for the next leaf, same rules, same tallies (measured on all five scenes, profiles/r02/ab_t17_walker_forms.txt):
+    //  * FULL or BAIL: ONE pop site, ONE node load, ONE drop test for both ways of getting the next node (nearest child / popped entry);
+    //  * otherwise the round-1 loop (pop + load in front of it, one load at its bottom) with the drop test folded in: a dropped node
+    //    counts as an interior node without hit children.  8 % faster on the glass scene, 7 % on cornell, within 1 % on caustics.
+    // What must not happen in either form is a copy of the load sequence in each branch of "nearest child or pop": the lanes of a warp
+    // then wait for each other's loads (bounce kernels +45 %, profiles/r02/ab_t11_load_sites.txt).  Also measured and dropped: the inverse
+    // direction in shared memory during the walk (to keep the direction in registers for the primitive tests: 30-50 % slower), the leaf
+    // box re-read from memory when a hit is accepted instead of kept in registers (50-60 % slower), 72 / 80 registers (ab_t12, ab_t16).
     while (sp > 0 && !term) {
-        // ONE pop site, ONE node load, ONE drop test for both ways of getting the next node (nearest child / popped entry): with a copy
-        // of the load sequence in each branch the lanes of a warp waited for each other's loads (bounce kernels +45 %,
-        // profiles/r02/ab_t11.txt)
-        bool need_pop = true, have_leaf = false;
+        bool have_leaf;
         uint32_t ent = 0, ni = 0;
         DNode nd;
-        for (;;) {
-            if (need_pop) {
-                if (sp == 0) break;
-                ent = stack_pop(stack, sp);
+        if (FULL || BAIL) {
+            bool need_pop = true;
+            have_leaf = false;
+            for (;;) {
+                if (need_pop) {
+                    if (sp == 0) break;
+                    ent = stack_pop(stack, sp);
+                }
+                ni = ent & GI_NODE_INDEX;
+                nd = load_node(S.nodes, ni);
+                if (need_pop && node_dropped<FULL>(nd, ent, r, out.t, frac_t)) continue;   // R2 / R3
+                if (nd.mask == 0) { have_leaf = true; break; }
+                // interior: the hit children in visiting order; the nearest is walked into at once, the others are pushed far-to-near
+                uint32_t seq, n;
+                n_node += __popc(nd.mask);
+                if (FULL) {
+                    uint32_t n_near;
+                    n = interior_step_marked<IMPL>(S.nodes, nd, r, seq, GI_PRUNE_T(out.t), n_near);
+                    if (n_near == 0 && out.t <= frac_t) n = 0;   // every child is beyond the hit and R3 holds: reached next, they would all be dropped
+                    for (int j = (int)n - 1; j >= 1; j--) stack_push(stack, sp, child_node(nd, (seq >> (4 * j)) & 7u) | ((uint32_t)j >= n_near ? GI_NODE_BEYOND : 0u), S.err);
+                } else {
+                    n = interior_step<IMPL, true>(S.nodes, nd, r, GI_PRUNE_T(out.t), seq);   // R1 + R3 at once: the segment ends at the hit
+                    for (int j = (int)n - 1; j >= 1; j--) stack_push(stack, sp, child_node(nd, (seq >> (4 * j)) & 7u), S.err);
+                }
+                need_pop = n == 0;
+                if (!need_pop) ent = child_node(nd, seq & 7u);
             }
+        } else {
+            ent = stack_pop(stack, sp);
             ni = ent & GI_NODE_INDEX;
             nd = load_node(S.nodes, ni);
-            if (need_pop && node_dropped<FULL>(nd, ent, r, out.t, frac_t)) continue;   // R2 / R3
-            if (nd.mask == 0) { have_leaf = true; break; }
-            // interior: the hit children in visiting order; the nearest is walked into at once, the others are pushed far-to-near
-            uint32_t seq, n;
-            n_node += __popc(nd.mask);
-            if (FULL) {
-                uint32_t n_near;
-                n = interior_step_marked<IMPL>(S.nodes, nd, r, seq, GI_PRUNE_T(out.t), n_near);
-                if (n_near == 0 && out.t <= frac_t) n = 0;   // every child is beyond the hit and R3 holds: reached next, they would all be dropped
-                for (int j = (int)n - 1; j >= 1; j--) stack_push(stack, sp, child_node(nd, (seq >> (4 * j)) & 7u) | ((uint32_t)j >= n_near ? GI_NODE_BEYOND : 0u), S.err);
-            } else {
-                n = interior_step<IMPL, true>(S.nodes, nd, r, GI_PRUNE_T(out.t), seq);   // R1 + R3 at once: the segment ends at the hit
-                for (int j = (int)n - 1; j >= 1; j--) stack_push(stack, sp, child_node(nd, (seq >> (4 * j)) & 7u), S.err);
+            bool popped = true;
+            have_leaf = true;
+            while (nd.mask != 0) {
+                uint32_t seq = 0, n = 0;
+                if (!(popped && node_dropped<FULL>(nd, ent, r, out.t, frac_t))) {   // R2 / R3: a dropped node has no hit children
+                    n_node += __popc(nd.mask);
+                    n = interior_step<IMPL, true>(S.nodes, nd, r, GI_PRUNE_T(out.t), seq);   // R1 + R3 at once: the segment ends at the hit
+                    for (int j = (int)n - 1; j >= 1; j--) stack_push(stack, sp, child_node(nd, (seq >> (4 * j)) & 7u), S.err);
+                }
+                popped = n == 0;
+                if (popped) {
+                    if (sp == 0) { have_leaf = false; break; }
+                    ent = stack_pop(stack, sp);
+                } else ent = child_node(nd, seq & 7u);
+                ni = ent & GI_NODE_INDEX;
+                nd = load_node(S.nodes, ni);
             }
-            need_pop = n == 0;
-            if (!need_pop) ent = child_node(nd, seq & 7u);
+            if (have_leaf && popped && node_dropped<FULL>(nd, ent, r, out.t, frac_t)) have_leaf = false;   // a leaf taken off the stack
         }
         if (have_leaf) {
             const DLeafRef* refs = S.refs + nd.prim_off;

@@ -655,86 +655,38 @@ __global__ void k_gather_locate(DGatherMap M, uint32_t n, const double* __restri
 #define GI_GS_MIN_GROUP 33
 #endif
 // GI_GS_MIN_GROUP:       // ... unless at least this many lanes of the warp share the list
-#define GI_GS_BLOCK 64   // 64 columns x 32 rows x 12 B = 24 KB of shared memory per block (25.5 KB with the paired rows)
+#define GI_GS_BLOCK 64   // 64 columns x 32 rows x 12 B = 24 KB of shared memory per block
 // (measured and dropped in round 2: the k nearest as an ascending sorted column with insertion from the end instead of the max-heap +
 //  final heap sort — no sort afterwards, but 27 % slower: 1.18 vs 0.93 ms for the 776 666 C2 queries, profiles/r02/ab_gather.txt)
 
-// max-heap of (distance^2, slot) pairs in one thread's column of shared memory: put (d, sl) into the hole at `i` of a heap of
-// `n` rows and sift it down.
-// Storage variant GI_HEAP_PAIRS (measured, NOT the default): row r lives in 16-byte word (r + 1) >> 1, half (r + 1) & 1 of the thread's
-// column, so the two children 2i + 1, 2i + 2 of row i are ONE word (i + 1) and a level of the sift costs one LDS.128 + one LDS.64 instead
-// of four loads.  Fewer instructions, but the single-row stores become 2-way bank conflicts (16-byte stride per lane): the isolated
-// C2 gather ran 9 % SLOWER (0.953 vs 0.875 ms, profiles/r02/ab_t13_bin_atomics_heap.txt).
-#ifndef GI_HEAP_PAIRS
-#define GI_HEAP_PAIRS 0
-#endif
-#if GI_HEAP_PAIRS
+// max-heap of (distance^2, slot) pairs in one thread's column of shared memory ([row][thread]: conflict-free for any mix of rows);
+// sift(n, i, d, sl) puts (d, sl) into the hole at row i of a heap of n rows and sifts it down.
+// Measured against this form in round 2 and dropped, all with identical index sets (profiles/r02/ab_t13_bin_atomics_heap.txt,
+// ab_t15_heap_regtop.txt; isolated C2 gather, 776 666 queries, this form 0.88 ms):
+//   * sibling pairs as one 16-byte word (one LDS.128 per level, but single-row stores become 2-way bank conflicts): 0.95 ms;
+//   * bottom-up extraction in the final sort (one comparison per level, but always the full height): 0.90 ms;
+//   * rows 0..2 in registers (no shared-memory access on the first level, 29 rows -> a tenth block per SM; but every access by a
+//     run-time row number turns into a branch ladder, 96 registers): 1.16 ms;
+//   * an ascending sorted column with insertion from the end instead of heap + heap sort (ab_gather.txt): 1.18 ms.
+#define GI_GS_ROWS 32
 struct GHeap {
-    double2 (*d)[GI_GS_BLOCK]; uint2 (*s)[GI_GS_BLOCK]; int t;
-    __device__ __forceinline__ double& D(int r) const { return reinterpret_cast<double*>(&d[(r + 1) >> 1][t])[(r + 1) & 1]; }
-    __device__ __forceinline__ uint32_t& S(int r) const { return reinterpret_cast<uint32_t*>(&s[(r + 1) >> 1][t])[(r + 1) & 1]; }
-    // both children of row i (the second is garbage when 2i + 2 is past the heap: the caller checks)
-    __device__ __forceinline__ void kids(int i, double& d0, uint32_t& s0, double& d1, uint32_t& s1) const
+    double (*sd)[GI_GS_BLOCK]; uint32_t (*ss)[GI_GS_BLOCK]; int t;
+    __device__ __forceinline__ void get(int r, double& d, uint32_t& s) const { d = sd[r][t]; s = ss[r][t]; }
+    __device__ __forceinline__ void set(int r, double d, uint32_t s) { sd[r][t] = d; ss[r][t] = s; }
+    __device__ __forceinline__ void sift(int n, int i, double d, uint32_t sl)
     {
-        const double2 a = d[i + 1][t]; const uint2 b = s[i + 1][t];
-        d0 = a.x; d1 = a.y; s0 = b.x; s1 = b.y;
+        for (;;) {
+            int c = 2 * i + 1;
+            if (c >= n) break;
+            double cd = sd[c][t]; uint32_t cs = ss[c][t];
+            if (c + 1 < n) { const double e = sd[c + 1][t]; const uint32_t es = ss[c + 1][t]; if (kv_less(cd, cs, e, es)) { c++; cd = e; cs = es; } }
+            if (!kv_less(d, sl, cd, cs)) break;
+            sd[i][t] = cd; ss[i][t] = cs; i = c;
+        }
+        sd[i][t] = d; ss[i][t] = sl;
     }
 };
-#define GI_GHEAP_DECL(h) __shared__ double2 s_hd[17][GI_GS_BLOCK]; __shared__ uint2 s_hs[17][GI_GS_BLOCK]; GHeap h; h.d = s_hd; h.s = s_hs; h.t = threadIdx.x
-#else
-struct GHeap {
-    double (*d)[GI_GS_BLOCK]; uint32_t (*s)[GI_GS_BLOCK]; int t;
-    __device__ __forceinline__ double& D(int r) const { return d[r][t]; }
-    __device__ __forceinline__ uint32_t& S(int r) const { return s[r][t]; }
-    __device__ __forceinline__ void kids(int i, double& d0, uint32_t& s0, double& d1, uint32_t& s1) const
-    {
-        d0 = d[2 * i + 1][t]; s0 = s[2 * i + 1][t]; d1 = d[2 * i + 2 < 32 ? 2 * i + 2 : 31][t]; s1 = s[2 * i + 2 < 32 ? 2 * i + 2 : 31][t];
-    }
-};
-#define GI_GHEAP_DECL(h) __shared__ double s_hd[32][GI_GS_BLOCK]; __shared__ uint32_t s_hs[32][GI_GS_BLOCK]; GHeap h; h.d = s_hd; h.s = s_hs; h.t = threadIdx.x
-#endif
-__device__ __forceinline__ void heap_sift(const GHeap& H, int n, int i, double d, uint32_t sl)
-{
-    for (;;) {
-        int c = 2 * i + 1;
-        if (c >= n) break;
-        double cd, d2; uint32_t cs, s2;
-        H.kids(i, cd, cs, d2, s2);
-        if (c + 1 < n && kv_less(cd, cs, d2, s2)) { c++; cd = d2; cs = s2; }
-        if (!kv_less(d, sl, cd, cs)) break;
-        H.D(i) = cd; H.S(i) = cs; i = c;
-    }
-    H.D(i) = d; H.S(i) = sl;
-}
-// the extraction step of the final heap sort.  Variant GI_HEAP_FLOYD (measured, NOT the default): bottom-up — the hole left by the root
-// walks down along the larger child to a leaf without comparing against the value to re-insert, which then sifts up; one key comparison
-// per level instead of two, but always the full height: 2 % slower (0.895 vs 0.875 ms, same file).
-#ifndef GI_HEAP_FLOYD
-#define GI_HEAP_FLOYD 0
-#endif
-__device__ __forceinline__ void heap_replace_root_bottom_up(const GHeap& H, int n, double d, uint32_t sl)
-{
-#if GI_HEAP_FLOYD
-    int i = 0;
-    for (;;) {
-        int c = 2 * i + 1;
-        if (c >= n) break;
-        double cd, d2; uint32_t cs, s2;
-        H.kids(i, cd, cs, d2, s2);
-        if (c + 1 < n && kv_less(cd, cs, d2, s2)) { c++; cd = d2; cs = s2; }
-        H.D(i) = cd; H.S(i) = cs; i = c;
-    }
-    while (i > 0) {
-        const int p = (i - 1) >> 1;
-        const double pd = H.D(p); const uint32_t ps = H.S(p);
-        if (!kv_less(pd, ps, d, sl)) break;
-        H.D(i) = pd; H.S(i) = ps; i = p;
-    }
-    H.D(i) = d; H.S(i) = sl;
-#else
-    heap_sift(H, n, 0, d, sl);
-#endif
-}
+#define GI_GHEAP_DECL(h) __shared__ double s_hd[GI_GS_ROWS][GI_GS_BLOCK]; __shared__ uint32_t s_hs[GI_GS_ROWS][GI_GS_BLOCK]; GHeap h; h.sd = s_hd; h.ss = s_hs; h.t = threadIdx.x
 
 // Each leaf's candidate list is stored in ascending distance from the CENTRE of the leaf box (k_pm_cand_order), with that
 // squared distance (rounded down) beside it.  A query point q lies inside the leaf box, so for a candidate c
@@ -795,13 +747,13 @@ __global__ void __launch_bounds__(GI_GS_BLOCK) k_gather_sorted(DGatherMap M, uin
             const double d = len2(cs[u].pos - p);
             if (m == k) {
                 if (!kv_less(d, sl, tau, tau_sl)) continue;
-                heap_sift(H, k, 0, d, sl);                      // replaces the root
+                H.sift(k, 0, d, sl);                            // replaces the root
             } else {
-                H.D(m) = d; H.S(m) = sl; m++;
+                H.set(m, d, sl); m++;
                 if (m < k) continue;
-                for (int i = k / 2 - 1; i >= 0; i--) heap_sift(H, k, i, H.D(i), H.S(i));   // k rows filled: heapify
+                for (int i = k / 2 - 1; i >= 0; i--) { double hd; uint32_t hs; H.get(i, hd, hs); H.sift(k, i, hd, hs); }   // k rows filled: heapify
             }
-            tau = H.D(0); tau_sl = H.S(0);
+            H.get(0, tau, tau_sl);
             // (sqrt(tau) + delta)^2 from above, in fp32 with every step rounded up (the bound only decides where the scan may stop;
             // an fp64 sqrt after every heap change was 7 % of the kernel's instructions)
             const float bf = __fadd_ru(__fsqrt_ru(__double2float_ru(tau)), delta_f);
@@ -809,25 +761,32 @@ __global__ void __launch_bounds__(GI_GS_BLOCK) k_gather_sorted(DGatherMap M, uin
         }
     }
     if (!hard && m > 1) {
-        if (m < k) for (int i = m / 2 - 1; i >= 0; i--) heap_sift(H, m, i, H.D(i), H.S(i));   // fewer than k candidates: not a heap yet
+        if (m < k) for (int i = m / 2 - 1; i >= 0; i--) { double hd; uint32_t hs; H.get(i, hd, hs); H.sift(m, i, hd, hs); }   // fewer than k candidates: not a heap yet
         for (int n2 = m - 1; n2 > 0; n2--) {   // heap sort: the largest goes to the end, the rest is re-heaped
-            const double ld = H.D(n2); const uint32_t ls = H.S(n2);
-            H.D(n2) = H.D(0); H.S(n2) = H.S(0);
-            heap_replace_root_bottom_up(H, n2, ld, ls);
+            double ld, rd; uint32_t ls, rs;
+            H.get(n2, ld, ls); H.get(0, rd, rs);
+            H.set(n2, rd, rs);
+            H.sift(n2, 0, ld, ls);
         }
     }
     d3 res = mk3(0, 0, 0);
     if (total > 0 && !hard) {
         // radiance estimate (raytracer.h:545-576), ascending distance
         for (int r = 0; r < count; r++) {
-            const double2* dc = reinterpret_cast<const double2*>(M.dircol + 6 * (size_t)H.S(r));
+            double rd_; uint32_t rs_; H.get(r, rd_, rs_);
+            const double2* dc = reinterpret_cast<const double2*>(M.dircol + 6 * (size_t)rs_);
             double2 a = __ldg(dc), b = __ldg(dc + 1), c = __ldg(dc + 2);
             res = res + mk3(b.y, c.x, c.y) * dot3(mk3(a.x, a.y, b.x), dq);
         }
-        const double den = GI_D_PI * H.D(count - 1);
+        double kd_; uint32_t ks_; H.get(count - 1, kd_, ks_);
+        const double den = GI_D_PI * kd_;
         res = mk3(res.x / den, res.y / den, res.z / den);
     }
-    if (have && knn && !hard) for (int r = 0; r < k; r++) knn[(size_t)q * k + r] = r < count ? __ldg(M.pid + H.S(r)) : GI_NO_HIT;
+    if (have && knn && !hard) for (int r = 0; r < k; r++) {
+        double rd_ = 0; uint32_t rs_ = 0;
+        if (r < count) H.get(r, rd_, rs_);
+        knn[(size_t)q * k + r] = r < count ? __ldg(M.pid + rs_) : GI_NO_HIT;
+    }
     // long lists: queue the query for k_gather_heavy (one warp per query, taken from a shared counter — in leaf order these
     // queries sit next to each other, and 32 of them in one warp would be a serial chain of milliseconds)
     {
