@@ -11,7 +11,7 @@ CLI = os.path.join(HERE, "global-illu")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 
 CU = [os.path.join(CSRC, "gi_api.cu")]
-CPP = [os.path.join(CSRC, "host", f) for f in ("gi_scene.cpp", "gi_loader.cpp", "gi_raytracer.cpp", "gi_host_capi.cpp", "gi_png.cpp")]
+CPP = [os.path.join(CSRC, "host", f) for f in ("gi_scene.cpp", "gi_loader.cpp", "gi_raytracer.cpp", "gi_host_capi.cpp", "gi_png.cpp", "gi_jpg.cpp")]
 HDR = [os.path.join(CSRC, f) for f in ("gi_device.cuh", "gi_kernels.cuh", "gi_octree_build.cuh", os.path.join("host", "api_scene.inc"))] + [os.path.join(CSRC, "host", "gi_scene.hpp"),
                                                                               os.path.join(HERE, "..", "include", "gi_api.h")]
 EXTRA = os.environ.get("GI_NVCC_EXTRA", "").split()

@@ -142,6 +142,7 @@ def load_library():
     L.gi_render_image.argtypes = [vp, C.POINTER(GiRenderParams), i32, i32, i32, i32, i32, i32, vp, vp, C.POINTER(GiStats)]
     L.gih_png_decode.argtypes = [C.c_char_p, C.POINTER(i32), C.POINTER(i32), C.POINTER(i32), vp, sz]
     L.gih_png_encode.argtypes = [C.c_char_p, i32, i32, vp]
+    L.gih_jpg_decode.argtypes = [C.c_char_p, C.POINTER(i32), C.POINTER(i32), vp, sz]
     _LIB = L
     return L
 

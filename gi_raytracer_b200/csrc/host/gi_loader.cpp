@@ -16,16 +16,21 @@ using gi::dvec3;
 
 imageTexture::imageTexture(const char* name, dvec2 t) : texture(dvec3(0, 0, 0)), fname(name), tile(t)
 {
-    // QImage(fname) (material.h:57): PNG files are decoded here (gi_png.cpp); other formats (the reference's scenes hold one
-    // unused JPG) and stand-in textures come as a raw sidecar `<name>.rgba` written by oracle/stage_assets.py
+    // QImage(fname) (material.h:57): PNG and JPEG files are decoded here (gi_png.cpp, gi_jpg.cpp); anything else, and the
+    // stand-in textures, come as a raw sidecar `<name>.rgba` written by scenes/stage_assets.py
     if (gi_png_decode(fname.c_str(), width, height, has_alpha, rgba)) {
+        std::cout << "loading texture: " << fname << "\nsize: " << width << ", " << height << "\n";
+        return;
+    }
+    if (gi_jpg_decode(fname.c_str(), width, height, rgba)) {
+        has_alpha = false;   // QImage::hasAlphaChannel of a JPEG
         std::cout << "loading texture: " << fname << "\nsize: " << width << ", " << height << "\n";
         return;
     }
     width = height = 0; has_alpha = false; rgba.clear();
     std::string side = fname + ".rgba";
     FILE* f = std::fopen(side.c_str(), "rb");
-    if (!f) { std::cout << "error while opening texture: " << fname << " (no PNG, no sidecar " << side << ")\n"; return; }
+    if (!f) { std::cout << "error while opening texture: " << fname << " (no PNG / JPEG, no sidecar " << side << ")\n"; return; }
     char magic[4];
     uint32_t hdr[3];
     if (std::fread(magic, 1, 4, f) == 4 && std::memcmp(magic, "GIRT", 4) == 0 && std::fread(hdr, 4, 3, f) == 3) {

@@ -410,6 +410,8 @@ class RayTracer {  // raytracer.h:23-735
 // PNG without Qt (gi_png.cpp): 8-bit RGBA rows top first, has_alpha as QImage::hasAlphaChannel reports it
 bool gi_png_decode(const char* path, int& width, int& height, bool& has_alpha, std::vector<uint8_t>& rgba);
 bool gi_png_encode(const char* path, int width, int height, const uint8_t* rgb);
+// JPEG without Qt (gi_jpg.cpp): 8-bit RGBA rows top first (alpha 255: QImage::hasAlphaChannel is false for a JPEG), libjpeg's pixels
+bool gi_jpg_decode(const char* path, int& width, int& height, std::vector<uint8_t>& rgba);
 
 void loadScene(Octree* o, RayTracer& r, const char* fname);                                              // sceneLoader.h:5
 void loadOBJ(Octree* o, const char* fname, gi::dvec3 pos, gi::dvec3 rot, const Material& material);     // meshLoader.h:4

@@ -76,6 +76,18 @@ def png_decode(path):
     return out, bool(a.value)
 
 
+def jpg_decode(path):
+    """csrc/host/gi_jpg.cpp: rgba uint8 [h][w][4] (alpha 255) — libjpeg's pixels, what QImage gave the reference's imageTexture."""
+    L = load_library()
+    w, h = C.c_int(), C.c_int()
+    if L.gih_jpg_decode(str(path).encode(), C.byref(w), C.byref(h), None, 0) != 0:
+        raise ValueError(f"not a decodable JPEG: {path}")
+    out = np.empty((h.value, w.value, 4), dtype=np.uint8)
+    if L.gih_jpg_decode(str(path).encode(), C.byref(w), C.byref(h), out.ctypes.data, out.size) != 0:
+        raise ValueError(f"not a decodable JPEG: {path}")
+    return out
+
+
 def png_encode(path, rgb):
     """8-bit RGB [h][w][3] -> PNG file."""
     rgb = np.ascontiguousarray(rgb, dtype=np.uint8)
