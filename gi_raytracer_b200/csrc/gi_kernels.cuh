@@ -1241,19 +1241,28 @@ __global__ void __launch_bounds__(GI_BLOCK, GI_MINB) k_direct(DScene S, gi_rende
     if (i >= n) { tally2(work, 0, 0); return; }
     uint32_t path = H.path[i];
     uint64_t key = PS.key[path];
-    d3 p = ld3(H.p + 3 * (size_t)i), nn = ld3(H.n + 3 * (size_t)i);
-    double rough = H.rough[i];
     d3 li = mk3(0, 0, 0);
     for (uint32_t l = 0; l < S.n_lights; l++) {
         const gi_light& light = S.lights[l];
-        d3 sp = p + nn * GI_D_SHADOW_BIAS;
-        d3 lightDir = light_point(light, gi_rand(P.seed, key, (uint64_t)depth, SITE(SITE_LIGHT_U, l)), gi_rand(P.seed, key, (uint64_t)depth, SITE(SITE_LIGHT_V, l))) - sp;   // :233
-        double maxt = len2(lightDir);
-        double hfrac = 1 / (GI_D_PI * len2(ld3(light.pos) - p));                                                             // :238
-        DRay sr = make_ray(sp, lightDir);                                                                                     // :241
+        DRay sr; double maxt;
+        {
+            const d3 p = ld3(H.p + 3 * (size_t)i), nn = ld3(H.n + 3 * (size_t)i);
+            d3 sp = p + nn * GI_D_SHADOW_BIAS;
+            d3 lightDir = light_point(light, gi_rand(P.seed, key, (uint64_t)depth, SITE(SITE_LIGHT_U, l)), gi_rand(P.seed, key, (uint64_t)depth, SITE(SITE_LIGHT_V, l))) - sp;   // :233
+            maxt = len2(lightDir);
+            sr = make_ray(sp, lightDir);                                                                                      // :241
+        }
         bool vis = trace_visible<FULL, IMPL>(S, sr, maxt, P.seed, key, (uint64_t)depth, l, wn, wp);                                 // :243
         if (FOG && vis && fog_blocks(S, sr, maxt, P.seed, key, (uint64_t)depth, l)) vis = false;                              // :308-316
         if (vis) {
+            // the hit point, normal and roughness are read AGAIN here instead of kept across the walk: eleven live doubles next to the
+            // ray made ptxas spill nine of them inside the interior loop of the traversal (9 STL.64 + 14 LDL.64 per node step, three
+            // times the bytes of the node record itself).  The pointers go through an empty asm so that the loads are not merged.
+            const double* hp = H.p; const double* hn = H.n; const double* hr = H.rough;
+            asm volatile("" : "+l"(hp), "+l"(hn), "+l"(hr));
+            const d3 p = ld3(hp + 3 * (size_t)i), nn = ld3(hn + 3 * (size_t)i);
+            const double rough = hr[i];
+            const double hfrac = 1 / (GI_D_PI * len2(ld3(light.pos) - p));                                                   // :238
             double d = dot3(nn, normalize3(ld3(light.pos) - p));
             if (d < 0) d = 0;
             double lv = pow_like_libm(d, (1.0 / rough));                                                                      // :252
