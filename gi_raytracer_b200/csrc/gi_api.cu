@@ -40,6 +40,7 @@ struct DevBuf {
 struct FamStat { double ms = 0; uint64_t launches = 0; };
 struct TimedLaunch { std::string fam; cudaEvent_t a, b; };
 
+#define GI_NHL 6   // hit lists in the ring (sched_mode 1 / 2; mode 0 alternates between the first two)
 struct gi_ctx {
     int device = 0;
     cudaStream_t stream = nullptr;
@@ -67,10 +68,26 @@ struct gi_ctx {
     // side streams: k_direct (side[0]) and the gather pipeline (side[1]) of a bounce depth run behind the next depth's bounce
     // kernel once the hit list is short (< overlap_threshold): those launches no longer fill the machine
     cudaStream_t main_stream = nullptr, side[2] = { nullptr, nullptr };
-    cudaEvent_t side_done[2][2] = { { nullptr, nullptr }, { nullptr, nullptr } };   // [hit-list parity][side stream]
+    cudaEvent_t side_done[GI_NHL][2] = {};   // [hit list of the ring][side stream]
+    cudaEvent_t fork_ev = nullptr;           // main stream -> side streams (the tail's queued shadow rays and gathers)
     uint32_t overlap_threshold = 1u << 20;   // GI_OVERLAP_THRESHOLD, 0 = off
+    // sched_mode (GI_SCHED_MODE): how a chunk's kernels are laid over the three streams when overlap is on.
+    //   0  shadow rays of a depth beside its gather pipeline; both behind the NEXT depth's bounce kernel only when the depth is short
+    //      (< overlap_threshold hits); everything is drained before the tail starts.
+    //   1  "deferred": the main stream carries only what decides how paths go on — generate, bounce kernels, binning, the tail
+    //      kernel — at the higher stream priority; EVERY depth's shadow rays go to side stream 0 and every gather pipeline run to side
+    //      stream 1 (the tail's queued ones included), reading hit lists out of a ring of GI_NHL (memory: 132 B per path of a chunk and list).  The short, latency-bound launches
+    //      of the deep bounces and the tail's one-warp-per-path walk then run underneath the long depth-0 / depth-1 launches
+    //      instead of after them.  Per path the sums keep their order: L is only touched on the main stream, Ld only on side 0,
+    //      Lc only on side 1, each in bounce order.
+    //   2  like 1, but the shadow rays / gathers of a depth that is FOLLOWED BY ANOTHER LONG bounce launch are held back until the
+    //      chain of bounce kernels has thinned out: two long traversal launches side by side only fight for L1 (k_gather_sorted also
+    //      asks for the largest shared-memory carve-out), while beside the short launches and the tail they are free.  With the
+    //      persistent-warp bounce form the shadow rays still start at once (they fill the thin ends of those walks).
+    int sched_mode = 1;
     DevBuf tsh[7];                           // the tail's deferred shadow rays (DTailQ::sh_*)
     DevBuf hl2[7], b_scan1s;                 // second hit list (depth parity), scan scratch of the gather side stream
+    DevBuf hlr[GI_NHL - 2][7];               // hit lists 3 .. GI_NHL of the ring (sched_mode 1 / 2)
     bool no_implicit = false;      // GI_NO_IMPLICIT_BOXES at gi_create: always load child boxes (for A/B tests)
     int trace_mode = 0;            // 0: thread per ray, 1: warp per ray (API batch kernels; GI_TRACE_MODE)
     uint32_t tail_threshold = 32768; // queues smaller than this finish in the tail megakernel (GI_TAIL_THRESHOLD, 0 = off)
@@ -264,13 +281,20 @@ extern "C" int gi_create(int device, gi_ctx** out)
     gi_ctx* ctx = new gi_ctx();
     ctx->device = device;
     // every failure below goes through gi_destroy, which releases whatever exists so far (streams, events, buffers)
-    if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) { ctx->stream = nullptr; gi_destroy(ctx); return GI_ERR_CUDA; }
+    // the main stream carries the critical chain of a frame (bounce kernels, tail) and gets the higher priority: its blocks are placed
+    // before the waiting blocks of the shadow / gather launches on the side streams (GI_STREAM_PRIO=0: all equal)
+    int prio_least = 0, prio_greatest = 0;
+    cudaDeviceGetStreamPriorityRange(&prio_least, &prio_greatest);
+    if (const char* e = getenv("GI_STREAM_PRIO")) { if (atoi(e) == 0) prio_greatest = prio_least; }
+    if (cudaStreamCreateWithPriority(&ctx->stream, cudaStreamNonBlocking, prio_greatest) != cudaSuccess) { ctx->stream = nullptr; gi_destroy(ctx); return GI_ERR_CUDA; }
     ctx->main_stream = ctx->stream;
     for (int k = 0; k < 2; k++) {
-        if (cudaStreamCreateWithFlags(&ctx->side[k], cudaStreamNonBlocking) != cudaSuccess) { ctx->side[k] = nullptr; gi_destroy(ctx); return GI_ERR_CUDA; }
-        for (int q = 0; q < 2; q++) if (cudaEventCreateWithFlags(&ctx->side_done[q][k], cudaEventDisableTiming) != cudaSuccess) { ctx->side_done[q][k] = nullptr; gi_destroy(ctx); return GI_ERR_CUDA; }
+        if (cudaStreamCreateWithPriority(&ctx->side[k], cudaStreamNonBlocking, prio_least) != cudaSuccess) { ctx->side[k] = nullptr; gi_destroy(ctx); return GI_ERR_CUDA; }
+        for (int q = 0; q < GI_NHL; q++) if (cudaEventCreateWithFlags(&ctx->side_done[q][k], cudaEventDisableTiming) != cudaSuccess) { ctx->side_done[q][k] = nullptr; gi_destroy(ctx); return GI_ERR_CUDA; }
     }
+    if (cudaEventCreateWithFlags(&ctx->fork_ev, cudaEventDisableTiming) != cudaSuccess) { ctx->fork_ev = nullptr; gi_destroy(ctx); return GI_ERR_CUDA; }
     if (const char* e = getenv("GI_OVERLAP_THRESHOLD")) ctx->overlap_threshold = (uint32_t)strtoul(e, nullptr, 10);
+    if (const char* e = getenv("GI_SCHED_MODE")) ctx->sched_mode = atoi(e);
     // Halton tables are scene independent
     std::vector<uint16_t> tab; std::vector<DHaltonDim> dims;
     build_halton(tab, dims);
@@ -325,9 +349,11 @@ extern "C" void gi_destroy(gi_ctx* ctx)
     for (auto& e : ctx->event_pool) cudaEventDestroy(e);
     for (int k = 0; k < 2; k++) {
         if (ctx->side[k]) { cudaStreamSynchronize(ctx->side[k]); cudaStreamDestroy(ctx->side[k]); }
-        for (int q = 0; q < 2; q++) if (ctx->side_done[q][k]) cudaEventDestroy(ctx->side_done[q][k]);
+        for (int q = 0; q < GI_NHL; q++) if (ctx->side_done[q][k]) cudaEventDestroy(ctx->side_done[q][k]);
     }
+    if (ctx->fork_ev) cudaEventDestroy(ctx->fork_ev);
     for (auto& b : ctx->hl2) b.release();
+    for (auto& l : ctx->hlr) for (auto& b : l) b.release();
     for (auto& b : ctx->tsh) b.release();
     ctx->b_scan1s.release();
     if (ctx->main_stream) cudaStreamDestroy(ctx->main_stream);
@@ -345,6 +371,7 @@ extern "C" int gi_configure(gi_ctx* ctx, const char* key, long long value)
     else if (k == "bounce_mode") ctx->bounce_mode = (int)value;
     else if (k == "trace_mode") ctx->trace_mode = (int)value;
     else if (k == "tail_mode") ctx->tail_mode = (int)value;
+    else if (k == "sched_mode") ctx->sched_mode = (int)value;
     else return fail(ctx, GI_ERR_INVALID, "gi_configure: unknown key " + k);
     return GI_OK;
 }
@@ -1281,10 +1308,14 @@ static int render_device(gi_ctx* ctx, const gi_render_params* P, int x0, int y0,
     for (int b = 0; b < 5; b++) CK(ctx->hl[b].reserve((size_t)chunk_cap * 24));
     CK(ctx->hl[5].reserve((size_t)chunk_cap * 8)); CK(ctx->hl[6].reserve((size_t)chunk_cap * 4));
     const bool overlap = ctx->overlap_threshold > 0;
-    if (overlap) {   // hit lists alternate by depth parity
-        const size_t cap2 = chunk_cap;
-        for (int b = 0; b < 5; b++) CK(ctx->hl2[b].reserve(cap2 * 24));
-        CK(ctx->hl2[5].reserve(cap2 * 8)); CK(ctx->hl2[6].reserve(cap2 * 4));
+    const bool deferred = overlap && ctx->sched_mode >= 1;   // see gi_ctx::sched_mode
+    const bool holdback = overlap && ctx->sched_mode == 2;
+    const int nhl = deferred ? GI_NHL : (overlap ? 2 : 1);   // hit lists in use: depths take them in turn
+    DevBuf* hls[GI_NHL] = { ctx->hl, ctx->hl2 };
+    for (int r = 2; r < GI_NHL; r++) hls[r] = ctx->hlr[r - 2];
+    for (int r = 1; r < nhl; r++) {
+        for (int b = 0; b < 5; b++) CK(hls[r][b].reserve((size_t)chunk_cap * 24));
+        CK(hls[r][5].reserve((size_t)chunk_cap * 8)); CK(hls[r][6].reserve((size_t)chunk_cap * 4));
     }
     CK(ctx->ps[0].reserve((size_t)chunk_cap * 4)); CK(ctx->ps[1].reserve((size_t)chunk_cap * 8)); CK(ctx->ps[2].reserve((size_t)chunk_cap * 24)); CK(ctx->ps[3].reserve((size_t)chunk_cap * 24)); CK(ctx->ps[4].reserve((size_t)chunk_cap * 24));
     CK(ctx->b_cnt.reserve(sizeof(DCounters))); CK(ctx->b_misc.reserve(64));
@@ -1297,8 +1328,8 @@ static int render_device(gi_ctx* ctx, const gi_render_params* P, int x0, int y0,
     bin_inv.x = (double)(1 << GI_BIN_AXIS_BITS) / std::max(ctx->root_box[3] - ctx->root_box[0], 1e-300); bin_inv.y = (double)(1 << GI_BIN_AXIS_BITS) / std::max(ctx->root_box[4] - ctx->root_box[1], 1e-300); bin_inv.z = (double)(1 << GI_BIN_AXIS_BITS) / std::max(ctx->root_box[5] - ctx->root_box[2], 1e-300);
     DQueue qa{ ctx->q_a[0].as<double>(), ctx->q_a[1].as<double>(), ctx->q_a[2].as<double>(), ctx->q_a[3].as<double>(), ctx->q_a[4].as<uint32_t>() };
     DQueue qb{ ctx->q_b[0].as<double>(), ctx->q_b[1].as<double>(), ctx->q_b[2].as<double>(), ctx->q_b[3].as<double>(), ctx->q_b[4].as<uint32_t>() };
-    const DHitList H0{ ctx->hl[0].as<double>(), ctx->hl[1].as<double>(), ctx->hl[2].as<double>(), ctx->hl[3].as<double>(), ctx->hl[4].as<double>(), ctx->hl[5].as<double>(), ctx->hl[6].as<uint32_t>() };
-    const DHitList H1{ ctx->hl2[0].as<double>(), ctx->hl2[1].as<double>(), ctx->hl2[2].as<double>(), ctx->hl2[3].as<double>(), ctx->hl2[4].as<double>(), ctx->hl2[5].as<double>(), ctx->hl2[6].as<uint32_t>() };
+    DHitList Hs[GI_NHL];
+    for (int r = 0; r < GI_NHL; r++) Hs[r] = DHitList{ hls[r][0].as<double>(), hls[r][1].as<double>(), hls[r][2].as<double>(), hls[r][3].as<double>(), hls[r][4].as<double>(), hls[r][5].as<double>(), hls[r][6].as<uint32_t>() };
     DPathState PS{ ctx->ps[0].as<uint32_t>(), ctx->ps[1].as<uint64_t>(), ctx->ps[2].as<double>(), ctx->ps[3].as<double>(), ctx->ps[4].as<double>() };
     DCounters* C = ctx->b_cnt.as<DCounters>();
     DFrame F = make_frame(ctx, P->width, P->height, x0, y0, x1, y1);
@@ -1326,27 +1357,72 @@ static int render_device(gi_ctx* ctx, const gi_render_params* P, int x0, int y0,
         DQueue in = qa, out = qb;
         uint32_t n_active = n;
         const uint32_t* perm = nullptr;
-        bool pending[2] = { false, false };   // side-stream work still reading hit list 0 / 1
+        bool pending[GI_NHL] = {};   // side-stream work still reading hit list r of the ring
         auto wait_side = [&](int par) {       // the main stream waits for the side-stream work that reads hit list `par`
             if (!pending[par]) return;
             cudaStreamWaitEvent(ctx->main_stream, ctx->side_done[par][0], 0); cudaStreamWaitEvent(ctx->main_stream, ctx->side_done[par][1], 0);
             pending[par] = false;
+        };
+        auto wait_all_sides = [&]() { for (int r = 0; r < GI_NHL; r++) wait_side(r); };
+        // sched_mode 2: the shadow rays / gathers of a depth that is followed by another LONG bounce launch are held back (not even
+        // enqueued) until the chain of bounce kernels has thinned out, the ring needs their hit list, or the chunk ends
+        struct Held { int depth; uint32_t n_hits; int slot; bool direct, gather; };
+        std::vector<Held> held;
+        auto launch_side = [&](Held& h, bool do_direct, bool do_gather) -> int {   // on the side streams; the host has seen bounce(h.depth) finish
+            const DHitList& HH = Hs[h.slot];
+            if (do_direct && h.direct) {
+                ctx->stream = ctx->side[0];
+                {
+                    ScopedTimer t(ctx, "direct");
+                    GI_LAUNCH_M(k_direct, grid_for(h.n_hits, GI_BLOCK), GI_BLOCK, ctx->S, *P, h.depth, h.n_hits, HH, PS, work_ptr(ctx, 2));
+                }
+                cudaEventRecord(ctx->side_done[h.slot][0], ctx->side[0]);
+                ctx->stream = ctx->main_stream;
+                launches++; h.direct = false; pending[h.slot] = true;
+            }
+            if (do_gather && h.gather) {
+                ctx->stream = ctx->side[1];
+                int rcg;
+                {
+                    ScopedTimer t(ctx, "gather");
+                    rcg = run_gather(ctx, h.n_hits, HH.p, HH.refdir, P->k_photons, nullptr, nullptr, nullptr, HH.wcaustic, PS.Lc, HH.path, &launches);
+                }
+                cudaEventRecord(ctx->side_done[h.slot][1], ctx->side[1]);
+                ctx->stream = ctx->main_stream;
+                h.gather = false; pending[h.slot] = true;
+                if (rcg != GI_OK) return rcg;
+            }
+            return GI_OK;
+        };
+        auto release_held = [&]() -> int {   // in depth order: Ld / Lc receive their terms in bounce order
+            for (auto& h : held) { int rcs = launch_side(h, true, true); if (rcs != GI_OK) return rcs; }
+            held.clear();
+            return GI_OK;
         };
         int hpar = 0;                         // hit list the next bounce writes
         for (int depth = 0; n_active > 0 && depth <= P->max_depth; depth++) {
             GI_POLL_CANCEL("render");
             // depths alternate between the two hit lists, so that a depth's shadow rays and gathers can run behind the next
             // depth's bounce kernel when they are few (decided below, once the hit count is known)
-            hpar = overlap ? (hpar ^ 1) : 0;
-            const DHitList& H = hpar ? H1 : H0;
+            hpar = (hpar + 1) % nhl;
+            const DHitList& H = Hs[hpar];
+            for (const auto& h : held) if (h.slot == hpar) { int rcs = release_held(); if (rcs != GI_OK) return rcs; break; }   // the ring has come round
             wait_side(hpar);
             if (depth > 0 && n_active < ctx->tail_threshold) {
                 // few paths left: one warp per path runs them to the end inside one kernel; their gathers are queued and served
                 // by one gather pipeline run afterwards (GI_TAIL_MODE=1: gathers inline)
-                wait_side(0); wait_side(1);   // the tail continues the paths' L / Ld / Lc sums: every earlier term must be in
                 DTailQ Q{};
                 const int last_gather_depth = std::min(P->max_depth, P->caustic_max_depth);
                 Q.qmax = ctx->tail_mode == 0 && have_map && last_gather_depth >= depth ? (uint32_t)(last_gather_depth - depth + 1) : 0u;
+                // The tail continues the paths' L / Ld / Lc sums, every earlier term must be in: L is the main stream's own; the tail's
+                // Ld terms are added by k_tail_direct on side stream 0 behind every k_direct, its Lc terms by k_tail_caustic behind every
+                // gather run — on side stream 1 in the deferred schedule (which then needs no wait here, unless the tail kernel makes
+                // its gathers inline and so touches Lc itself: k_tail's `lc_rw`), on the main stream otherwise.
+                { int rcs = release_held(); if (rcs != GI_OK) return rcs; }   // ahead of the tail's own side-stream work
+                const bool tail_lc_rw = have_map && Q.qmax == 0 && depth <= P->caustic_max_depth;
+                if (!deferred || tail_lc_rw) wait_all_sides();
+                const bool tail_sides = deferred && !tail_lc_rw;   // the tail's queued work goes behind the side streams' earlier work
+                const int tp = tail_sides ? hpar : 0;              // the (free) ring slot whose events mark that work
                 const size_t slots = (size_t)n_active * Q.qmax;
                 if (Q.qmax) {
                     if (slots > 0xFFFFFFF0ull) return fail(ctx, GI_ERR_INVALID, "too many tail gather slots");
@@ -1370,11 +1446,11 @@ static int render_device(gi_ctx* ctx, const gi_render_params* P, int x0, int y0,
                     GI_LAUNCH_M(k_tail, tail_grid, GI_WPB * 32, ctx->S, ctx->G, have_map ? 1 : 0, *P, depth, n_active, in, PS, ctx->b_tail.as<DTailCounters>(), Q);
                     launches++;
                 }
+                if (overlap) cudaEventRecord(ctx->fork_ev, ctx->main_stream);   // k_tail has filled the queues
                 if (Q.smax) {
                     // the queued shadow rays, one thread each, beside the tail's gather run (side stream 0); k_tail_direct then adds the
                     // unshadowed terms to Ld in bounce order
-                    cudaEventRecord(ctx->side_done[0][0], ctx->main_stream);
-                    if (overlap) { ctx->stream = ctx->side[0]; cudaStreamWaitEvent(ctx->side[0], ctx->side_done[0][0], 0); }
+                    if (overlap) { ctx->stream = ctx->side[0]; cudaStreamWaitEvent(ctx->side[0], ctx->fork_ev, 0); }
                     {
                         ScopedTimer t(ctx, "direct");
                         GI_LAUNCH_M(k_tail_shadow, grid_for((size_t)n_active * Q.smax, GI_BLOCK), GI_BLOCK, ctx->S, *P, n_active, in, PS, Q, work_ptr(ctx, 2));
@@ -1383,19 +1459,26 @@ static int render_device(gi_ctx* ctx, const gi_render_params* P, int x0, int y0,
                         ScopedTimer t(ctx, "tail");
                         k_tail_direct<<<grid_for(n_active, 256), 256, 0, ctx->stream>>>(n_active, ctx->S.n_lights, in, PS, Q);
                     }
-                    if (overlap) { cudaEventRecord(ctx->side_done[0][0], ctx->side[0]); cudaEventRecord(ctx->side_done[0][1], ctx->side[1]); pending[0] = true; }
                     ctx->stream = ctx->main_stream;
                     launches += 2;
                 }
                 if (Q.qmax) {
+                    if (tail_sides) { ctx->stream = ctx->side[1]; cudaStreamWaitEvent(ctx->side[1], ctx->fork_ev, 0); }
+                    int rcg;
                     {
                         ScopedTimer t(ctx, "gather");
-                        int rcg = run_gather(ctx, (uint32_t)slots, Q.pos, Q.dir, P->k_photons, Q.rgb, nullptr, nullptr, nullptr, nullptr, nullptr, &launches);
-                        if (rcg != GI_OK) return rcg;
+                        rcg = run_gather(ctx, (uint32_t)slots, Q.pos, Q.dir, P->k_photons, Q.rgb, nullptr, nullptr, nullptr, nullptr, nullptr, &launches);
                     }
-                    ScopedTimer t(ctx, "tail");
-                    k_tail_caustic<<<grid_for(n_active, 256), 256, 0, ctx->stream>>>(n_active, in, PS, Q);
-                    launches++;
+                    if (rcg == GI_OK) {
+                        ScopedTimer t(ctx, "tail");
+                        k_tail_caustic<<<grid_for(n_active, 256), 256, 0, ctx->stream>>>(n_active, in, PS, Q);
+                        launches++;
+                    }
+                    ctx->stream = ctx->main_stream;
+                    if (rcg != GI_OK) return rcg;
+                }
+                if (overlap && (Q.smax || (tail_sides && Q.qmax))) {
+                    cudaEventRecord(ctx->side_done[tp][0], ctx->side[0]); cudaEventRecord(ctx->side_done[tp][1], ctx->side[1]); pending[tp] = true;
                 }
                 CK(cudaGetLastError());
                 break;
@@ -1415,9 +1498,20 @@ static int render_device(gi_ctx* ctx, const gi_render_params* P, int x0, int y0,
             CK(cudaStreamSynchronize(ctx->stream));
             launches++;
             n_closest += n_active;
-            if (hc.n_hits) {
+            if (hc.n_hits && holdback) {
+                if (ctx->S.n_lights) n_shadow += (uint64_t)hc.n_hits * ctx->S.n_lights;
+                const bool wants_gather = depth <= P->caustic_max_depth;
+                if (wants_gather) n_gather += hc.n_hits;   // samplePhotons is called whether or not photons exist (raytracer.h:258)
+                held.push_back(Held{ depth, hc.n_hits, hpar, ctx->S.n_lights > 0, wants_gather && have_map });
+                const bool next_long = hc.n_next >= ctx->overlap_threshold && hc.n_next >= ctx->tail_threshold && depth + 1 <= P->max_depth;
+                int rcs = GI_OK;
+                if (!next_long) rcs = release_held();                          // the chain has thinned out (or ends): everything held goes to the side streams
+                else if (persistent) rcs = launch_side(held.back(), true, false);   // shadow rays fill the thin ends of the persistent warps' walks; the gather waits
+                if (rcs != GI_OK) return rcs;
+                CK(cudaGetLastError());
+            } else if (hc.n_hits) {
                 // the host has just synchronised the main stream (counters), so the side streams need no event to start
-                const bool side = overlap && hc.n_hits < ctx->overlap_threshold;
+                const bool side = deferred || (overlap && hc.n_hits < ctx->overlap_threshold);
                 static const bool big_direct = getenv("GI_NO_BIG_DIRECT_OVERLAP") == nullptr;   // long shadow launches run beside the gather pipeline (C2 25.85 -> 25.43 ms, glass 51.0 -> 50.7)
                 const bool side_d = side || (overlap && big_direct);
                 if (ctx->S.n_lights) {
@@ -1467,7 +1561,8 @@ static int render_device(gi_ctx* ctx, const gi_render_params* P, int x0, int y0,
                 perm = ctx->b_binperm.as<uint32_t>();
             }
         }
-        wait_side(0); wait_side(1);   // whatever follows on the main stream (accumulate, the next chunk) sees complete sums
+        { int rcs = release_held(); if (rcs != GI_OK) return rcs; }
+        wait_all_sides();   // whatever follows on the main stream (accumulate, the next chunk) sees complete sums
         return GI_OK;
     };
     if (adapt) {

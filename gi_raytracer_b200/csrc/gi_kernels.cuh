@@ -1315,7 +1315,10 @@ __global__ void __launch_bounds__(GI_WPB * 32, GI_TAIL_MINB) k_tail(DScene S, DG
     DRay r = ray_as_stored(ld3(in.o + 3 * (size_t)i), ld3(in.d + 3 * (size_t)i));
     d3 T = ld3(in.T + 3 * (size_t)i), contrib = ld3(in.contrib + 3 * (size_t)i);
     const uint64_t key = PS.key[path]; const uint32_t sample = PS.sample[path];
-    d3 L = ld3(PS.L + 3 * (size_t)path), Lc = ld3(PS.Lc + 3 * (size_t)path);   // Ld: k_tail_direct, from the queued shadow rays
+    // Ld: k_tail_direct, from the queued shadow rays.  Lc is this kernel's only when it makes its gathers inline (lc_rw); with queued
+    // gathers it must not even be read and written back: gather runs of earlier depths may still be adding to it on a side stream
+    const bool lc_rw = have_map && Q.qmax == 0 && depth0 <= P.caustic_max_depth;
+    d3 L = ld3(PS.L + 3 * (size_t)path), Lc = lc_rw ? ld3(PS.Lc + 3 * (size_t)path) : mk3(0, 0, 0);
     uint32_t nq = 0;   // gather queries queued by this path
     uint32_t nsh = 0;  // shadow rays queued by this path
     unsigned long long c_closest = 0, c_shadow = 0, c_gather = 0, g_depth = 0, g_cand = 0, g_sel = 0;
@@ -1390,7 +1393,8 @@ __global__ void __launch_bounds__(GI_WPB * 32, GI_TAIL_MINB) k_tail(DScene S, DG
         r = make_ray(hp + hn * offset, refDir);
     }
     if (lane == 0) {
-        st3(PS.L + 3 * (size_t)path, L); st3(PS.Lc + 3 * (size_t)path, Lc);
+        st3(PS.L + 3 * (size_t)path, L);
+        if (lc_rw) st3(PS.Lc + 3 * (size_t)path, Lc);
         if (Q.smax) Q.sh_count[i] = nsh < Q.smax ? nsh : Q.smax;
         if (have_map && Q.qmax) {
             Q.count[i] = nq < Q.qmax ? nq : Q.qmax;
