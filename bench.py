@@ -498,7 +498,7 @@ def main():
             "config": {"workload": workload_name(args.config, cfg, SPP) + (" per GPU (sample-index split)" if not tiles else " (frame split into interleaved 16-row blocks)"),
                        "scene": f"scenes/{cfg['scene']}/{cfg['scene']}.scn ({cfg['note']})", "width": W, "height": H, "spp_per_step": SPP, "frame_spp": frame_spp,
                        "photons_stored": pm_info["n_kept"], "photon_map_nodes": pm_info["n_nodes"], "l2": "working set per step (path state ~2.9 GB) exceeds the 126 MB L2",
-                       "streams": "k_direct and the gather pipeline run on side streams (k_direct beside the gather; both behind the next depth's bounce kernel when a depth has < 2^20 hits); roofline.families are timed in one extra single-stream frame",
+                       "streams": "three streams per context: generate / bounce kernels / binning / the tail kernel on the main stream (highest priority), every depth's shadow rays on side stream 0, every gather run on side stream 1, hit lists in a ring of eight (gi_ctx::sched_mode 1); roofline.families are timed in one extra single-stream frame",
                        "parallelism": (f"tile-split x{world} (gi_render_rows + gi_framebuffer_gather of 8-bit rows)" if tiles else f"sample-split x{world} (gi_framebuffer_reduce of fp64 sums)"),
                        "collective": ("none (N = 1)" if world == 1 else ("disabled (GI_BENCH_NO_REDUCE)" if no_reduce else "inside the timed region, on the render stream")),
                        "photon_phase_s": photon_wall, "photon_slab_bytes": slab_bytes, "photon_bcast_s": bcast_s if world > 1 else 0.0,

@@ -40,7 +40,7 @@ struct DevBuf {
 struct FamStat { double ms = 0; uint64_t launches = 0; };
 struct TimedLaunch { std::string fam; cudaEvent_t a, b; };
 
-#define GI_NHL 6   // hit lists in the ring (sched_mode 1 / 2; mode 0 alternates between the first two)
+#define GI_NHL 8   // most hit lists the ring can hold (gi_ctx::ring are used; sched_mode 0 alternates between the first two)
 struct gi_ctx {
     int device = 0;
     cudaStream_t stream = nullptr;
@@ -80,14 +80,15 @@ struct gi_ctx {
     //      of the deep bounces and the tail's one-warp-per-path walk then run underneath the long depth-0 / depth-1 launches
     //      instead of after them.  Per path the sums keep their order: L is only touched on the main stream, Ld only on side 0,
     //      Lc only on side 1, each in bounce order.
-    //   2  like 1, but the shadow rays / gathers of a depth that is FOLLOWED BY ANOTHER LONG bounce launch are held back until the
-    //      chain of bounce kernels has thinned out: two long traversal launches side by side only fight for L1 (k_gather_sorted also
-    //      asks for the largest shared-memory carve-out), while beside the short launches and the tail they are free.  With the
-    //      persistent-warp bounce form the shadow rays still start at once (they fill the thin ends of those walks).
+    //      (Measured and dropped, profiles/r02/ab_t23: holding the side work of a depth back while ANOTHER LONG bounce launch follows, so that
+    //      long traversal launches never run side by side — slower on every scene, caustics 19.14 -> 19.59 ms, glass 135.7 -> 140.5.)
+    //      ring: hit lists in use (GI_RING, 2..GI_NHL): with four, bounce d+4 waited for the shadow rays / gathers of depth d —
+    //      cornell 46.0 ms against 43.9 with six; glass 140.8 / 135.6 / 132.8 ms with four / six / eight (profiles/r02/ab_t24).
     int sched_mode = 1;
+    int ring = 8;
     DevBuf tsh[7];                           // the tail's deferred shadow rays (DTailQ::sh_*)
     DevBuf hl2[7], b_scan1s;                 // second hit list (depth parity), scan scratch of the gather side stream
-    DevBuf hlr[GI_NHL - 2][7];               // hit lists 3 .. GI_NHL of the ring (sched_mode 1 / 2)
+    DevBuf hlr[GI_NHL - 2][7];               // hit lists 3 .. GI_NHL of the ring (sched_mode 1)
     bool no_implicit = false;      // GI_NO_IMPLICIT_BOXES at gi_create: always load child boxes (for A/B tests)
     int trace_mode = 0;            // 0: thread per ray, 1: warp per ray (API batch kernels; GI_TRACE_MODE)
     uint32_t tail_threshold = 32768; // queues smaller than this finish in the tail megakernel (GI_TAIL_THRESHOLD, 0 = off)
@@ -285,16 +286,24 @@ extern "C" int gi_create(int device, gi_ctx** out)
     // before the waiting blocks of the shadow / gather launches on the side streams (GI_STREAM_PRIO=0: all equal)
     int prio_least = 0, prio_greatest = 0;
     cudaDeviceGetStreamPriorityRange(&prio_least, &prio_greatest);
-    if (const char* e = getenv("GI_STREAM_PRIO")) { if (atoi(e) == 0) prio_greatest = prio_least; }
+    // GI_STREAM_PRIO: 0 all equal, 1 main above both side streams, 2 main > shadow rays > gathers, 3 main > gathers > shadow rays.
+    // Measured (profiles/r02/ab_t22, ab_t24; caustics / glass / cornell frame ms): 1: 19.11 / 135.6 / 44.0, 2: 19.05 / 134.5 / 43.9,
+    // 3: 20.33 / 148.3 / 49.8; without priorities the deferred schedule LOSES to the old one (20.98 against 20.54 on caustics).
+    int prio_mode = 2;
+    if (const char* e = getenv("GI_STREAM_PRIO")) prio_mode = atoi(e);
+    if (prio_mode == 0) prio_greatest = prio_least;
+    const int prio_mid = prio_least - prio_greatest >= 2 ? prio_least - 1 : prio_least;   // numerically lower = higher priority
+    const int side_prio[2] = { prio_mode == 2 ? prio_mid : prio_least, prio_mode == 3 ? prio_mid : prio_least };
     if (cudaStreamCreateWithPriority(&ctx->stream, cudaStreamNonBlocking, prio_greatest) != cudaSuccess) { ctx->stream = nullptr; gi_destroy(ctx); return GI_ERR_CUDA; }
     ctx->main_stream = ctx->stream;
     for (int k = 0; k < 2; k++) {
-        if (cudaStreamCreateWithPriority(&ctx->side[k], cudaStreamNonBlocking, prio_least) != cudaSuccess) { ctx->side[k] = nullptr; gi_destroy(ctx); return GI_ERR_CUDA; }
+        if (cudaStreamCreateWithPriority(&ctx->side[k], cudaStreamNonBlocking, side_prio[k]) != cudaSuccess) { ctx->side[k] = nullptr; gi_destroy(ctx); return GI_ERR_CUDA; }
         for (int q = 0; q < GI_NHL; q++) if (cudaEventCreateWithFlags(&ctx->side_done[q][k], cudaEventDisableTiming) != cudaSuccess) { ctx->side_done[q][k] = nullptr; gi_destroy(ctx); return GI_ERR_CUDA; }
     }
     if (cudaEventCreateWithFlags(&ctx->fork_ev, cudaEventDisableTiming) != cudaSuccess) { ctx->fork_ev = nullptr; gi_destroy(ctx); return GI_ERR_CUDA; }
     if (const char* e = getenv("GI_OVERLAP_THRESHOLD")) ctx->overlap_threshold = (uint32_t)strtoul(e, nullptr, 10);
     if (const char* e = getenv("GI_SCHED_MODE")) ctx->sched_mode = atoi(e);
+    if (const char* e = getenv("GI_RING")) ctx->ring = atoi(e);
     // Halton tables are scene independent
     std::vector<uint16_t> tab; std::vector<DHaltonDim> dims;
     build_halton(tab, dims);
@@ -372,6 +381,7 @@ extern "C" int gi_configure(gi_ctx* ctx, const char* key, long long value)
     else if (k == "trace_mode") ctx->trace_mode = (int)value;
     else if (k == "tail_mode") ctx->tail_mode = (int)value;
     else if (k == "sched_mode") ctx->sched_mode = (int)value;
+    else if (k == "ring") ctx->ring = (int)value;
     else return fail(ctx, GI_ERR_INVALID, "gi_configure: unknown key " + k);
     return GI_OK;
 }
@@ -1309,8 +1319,7 @@ static int render_device(gi_ctx* ctx, const gi_render_params* P, int x0, int y0,
     CK(ctx->hl[5].reserve((size_t)chunk_cap * 8)); CK(ctx->hl[6].reserve((size_t)chunk_cap * 4));
     const bool overlap = ctx->overlap_threshold > 0;
     const bool deferred = overlap && ctx->sched_mode >= 1;   // see gi_ctx::sched_mode
-    const bool holdback = overlap && ctx->sched_mode == 2;
-    const int nhl = deferred ? GI_NHL : (overlap ? 2 : 1);   // hit lists in use: depths take them in turn
+    const int nhl = deferred ? std::min(std::max(ctx->ring, 2), GI_NHL) : (overlap ? 2 : 1);   // hit lists in use: depths take them in turn
     DevBuf* hls[GI_NHL] = { ctx->hl, ctx->hl2 };
     for (int r = 2; r < GI_NHL; r++) hls[r] = ctx->hlr[r - 2];
     for (int r = 1; r < nhl; r++) {
@@ -1364,41 +1373,6 @@ static int render_device(gi_ctx* ctx, const gi_render_params* P, int x0, int y0,
             pending[par] = false;
         };
         auto wait_all_sides = [&]() { for (int r = 0; r < GI_NHL; r++) wait_side(r); };
-        // sched_mode 2: the shadow rays / gathers of a depth that is followed by another LONG bounce launch are held back (not even
-        // enqueued) until the chain of bounce kernels has thinned out, the ring needs their hit list, or the chunk ends
-        struct Held { int depth; uint32_t n_hits; int slot; bool direct, gather; };
-        std::vector<Held> held;
-        auto launch_side = [&](Held& h, bool do_direct, bool do_gather) -> int {   // on the side streams; the host has seen bounce(h.depth) finish
-            const DHitList& HH = Hs[h.slot];
-            if (do_direct && h.direct) {
-                ctx->stream = ctx->side[0];
-                {
-                    ScopedTimer t(ctx, "direct");
-                    GI_LAUNCH_M(k_direct, grid_for(h.n_hits, GI_BLOCK), GI_BLOCK, ctx->S, *P, h.depth, h.n_hits, HH, PS, work_ptr(ctx, 2));
-                }
-                cudaEventRecord(ctx->side_done[h.slot][0], ctx->side[0]);
-                ctx->stream = ctx->main_stream;
-                launches++; h.direct = false; pending[h.slot] = true;
-            }
-            if (do_gather && h.gather) {
-                ctx->stream = ctx->side[1];
-                int rcg;
-                {
-                    ScopedTimer t(ctx, "gather");
-                    rcg = run_gather(ctx, h.n_hits, HH.p, HH.refdir, P->k_photons, nullptr, nullptr, nullptr, HH.wcaustic, PS.Lc, HH.path, &launches);
-                }
-                cudaEventRecord(ctx->side_done[h.slot][1], ctx->side[1]);
-                ctx->stream = ctx->main_stream;
-                h.gather = false; pending[h.slot] = true;
-                if (rcg != GI_OK) return rcg;
-            }
-            return GI_OK;
-        };
-        auto release_held = [&]() -> int {   // in depth order: Ld / Lc receive their terms in bounce order
-            for (auto& h : held) { int rcs = launch_side(h, true, true); if (rcs != GI_OK) return rcs; }
-            held.clear();
-            return GI_OK;
-        };
         int hpar = 0;                         // hit list the next bounce writes
         for (int depth = 0; n_active > 0 && depth <= P->max_depth; depth++) {
             GI_POLL_CANCEL("render");
@@ -1406,7 +1380,6 @@ static int render_device(gi_ctx* ctx, const gi_render_params* P, int x0, int y0,
             // depth's bounce kernel when they are few (decided below, once the hit count is known)
             hpar = (hpar + 1) % nhl;
             const DHitList& H = Hs[hpar];
-            for (const auto& h : held) if (h.slot == hpar) { int rcs = release_held(); if (rcs != GI_OK) return rcs; break; }   // the ring has come round
             wait_side(hpar);
             if (depth > 0 && n_active < ctx->tail_threshold) {
                 // few paths left: one warp per path runs them to the end inside one kernel; their gathers are queued and served
@@ -1418,7 +1391,6 @@ static int render_device(gi_ctx* ctx, const gi_render_params* P, int x0, int y0,
                 // Ld terms are added by k_tail_direct on side stream 0 behind every k_direct, its Lc terms by k_tail_caustic behind every
                 // gather run — on side stream 1 in the deferred schedule (which then needs no wait here, unless the tail kernel makes
                 // its gathers inline and so touches Lc itself: k_tail's `lc_rw`), on the main stream otherwise.
-                { int rcs = release_held(); if (rcs != GI_OK) return rcs; }   // ahead of the tail's own side-stream work
                 const bool tail_lc_rw = have_map && Q.qmax == 0 && depth <= P->caustic_max_depth;
                 if (!deferred || tail_lc_rw) wait_all_sides();
                 const bool tail_sides = deferred && !tail_lc_rw;   // the tail's queued work goes behind the side streams' earlier work
@@ -1498,18 +1470,7 @@ static int render_device(gi_ctx* ctx, const gi_render_params* P, int x0, int y0,
             CK(cudaStreamSynchronize(ctx->stream));
             launches++;
             n_closest += n_active;
-            if (hc.n_hits && holdback) {
-                if (ctx->S.n_lights) n_shadow += (uint64_t)hc.n_hits * ctx->S.n_lights;
-                const bool wants_gather = depth <= P->caustic_max_depth;
-                if (wants_gather) n_gather += hc.n_hits;   // samplePhotons is called whether or not photons exist (raytracer.h:258)
-                held.push_back(Held{ depth, hc.n_hits, hpar, ctx->S.n_lights > 0, wants_gather && have_map });
-                const bool next_long = hc.n_next >= ctx->overlap_threshold && hc.n_next >= ctx->tail_threshold && depth + 1 <= P->max_depth;
-                int rcs = GI_OK;
-                if (!next_long) rcs = release_held();                          // the chain has thinned out (or ends): everything held goes to the side streams
-                else if (persistent) rcs = launch_side(held.back(), true, false);   // shadow rays fill the thin ends of the persistent warps' walks; the gather waits
-                if (rcs != GI_OK) return rcs;
-                CK(cudaGetLastError());
-            } else if (hc.n_hits) {
+            if (hc.n_hits) {
                 // the host has just synchronised the main stream (counters), so the side streams need no event to start
                 const bool side = deferred || (overlap && hc.n_hits < ctx->overlap_threshold);
                 static const bool big_direct = getenv("GI_NO_BIG_DIRECT_OVERLAP") == nullptr;   // long shadow launches run beside the gather pipeline (C2 25.85 -> 25.43 ms, glass 51.0 -> 50.7)
@@ -1561,7 +1522,6 @@ static int render_device(gi_ctx* ctx, const gi_render_params* P, int x0, int y0,
                 perm = ctx->b_binperm.as<uint32_t>();
             }
         }
-        { int rcs = release_held(); if (rcs != GI_OK) return rcs; }
         wait_all_sides();   // whatever follows on the main stream (accumulate, the next chunk) sees complete sums
         return GI_OK;
     };

@@ -1,7 +1,7 @@
 #!/usr/bin/env python3
 """A/B of the frame schedule (gi_ctx::sched_mode, stream priorities) in ONE process: for every scene the frame time (median of N
 frames after two warm-up frames) and the SHA-1 of the fp64 accumulator under each variant — the accumulators must be byte-identical.
-usage: python profiles/sched_ab.py [--scenes caustics,glass,...] [--frames 5] [--variants 0:0,0:1,1:0,1:1]   (sched_mode:stream_prio)"""
+usage: python profiles/sched_ab.py [--scenes caustics,glass,...] [--frames 5] [--variants 0:0,1:1,1:1:8:65536]   (sched_mode:GI_STREAM_PRIO[:ring[:tail_threshold]])"""
 import argparse, hashlib, os, statistics, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from gi_raytracer_b200 import host
@@ -30,12 +30,14 @@ for scene in a.scenes.split(","):
     acc = torch.zeros((w * h, 3), dtype=torch.float64, device="cuda")
     ref = None
     for var in a.variants.split(","):
-        mode, prio = (int(x) for x in var.split(":"))
+        f4 = [int(x) for x in var.split(":")] + [8, 32768]
+        mode, prio = f4[0], f4[1]
+        ring, tail = (f4[2], f4[3]) if len(f4) >= 6 else ((f4[2], 32768) if len(f4) == 5 else (8, 32768))
         os.environ["GI_STREAM_PRIO"] = str(prio)   # read at gi_create
         ctx = Context(0); ctx.upload_scene(sc)
         if photons:
             ctx.photon_trace(photons, pdepth, seed=1); ctx.photon_map_build(None)
-        ctx.configure("sched_mode", mode)
+        ctx.configure("sched_mode", mode); ctx.configure("ring", ring); ctx.configure("tail_threshold", tail)
         rows = []
         for f in range(a.frames + 2):
             st = ctx.render_tile_dev(P, 0, 0, w, h, 0, spp, acc.data_ptr())
@@ -43,7 +45,7 @@ for scene in a.scenes.split(","):
         med = lambda k: statistics.median(getattr(s, k) for s in rows)
         digest = hashlib.sha1(acc.cpu().numpy().tobytes()).hexdigest()[:16]
         if ref is None: ref = digest
-        line = (f"{scene:9s} sched {mode} prio {prio}: frame {med('total_ms'):9.3f} ms (min {min(s.total_ms for s in rows):9.3f}) | bounce {med('trace_ms'):8.3f} direct {med('shadow_ms'):8.3f} "
+        line = (f"{scene:9s} sched {mode} prio {prio} ring {ring} tail {tail:6d}: frame {med('total_ms'):9.3f} ms (min {min(s.total_ms for s in rows):9.3f}) | bounce {med('trace_ms'):8.3f} direct {med('shadow_ms'):8.3f} "
                 f"gather {med('gather_ms'):8.3f} tail {med('shade_ms'):7.3f} | launches {rows[-1].kernel_launches} rays {rows[-1].closest_rays + rows[-1].shadow_rays} sha1 {digest} {'same' if digest == ref else 'DIFFERENT'}")
         print(line, flush=True)
         if a.serial:

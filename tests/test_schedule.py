@@ -1,8 +1,7 @@
 """The frame schedules give the same frame, bit for bit.  gi_ctx::sched_mode lays a chunk's kernels over the context's three
 streams in two ways (0: a depth's shadow rays and gathers behind the next bounce only when the depth is short, everything drained
 before the tail; 1: every depth's shadow rays / gathers on the side streams, hit lists in a ring, the tail kernel not waiting for
-them; 2: like 1 with the side work of long depths held back until the chain of bounce kernels has thinned out); overlap_threshold 0
-puts everything on ONE stream.  Per path the sums L / Ld / Lc receive their terms in bounce order
+them); overlap_threshold 0 puts everything on ONE stream.  Per path the sums L / Ld / Lc receive their terms in bounce order
 under all of them (raytracer.h:167-276 is one recursion per path), so the fp64 accumulators must be byte-identical — a race
 between the streams would show as a difference.  Small tail thresholds make the wavefront run deep enough to wrap the ring."""
 import os
@@ -20,15 +19,16 @@ def _frames(ctx, P, w, h, spp, tail_thresholds):
     try:
         for tt in tail_thresholds:
             ctx.configure("tail_threshold", tt)
-            for name, overlap, mode in (("one stream", 0, 0), ("sched 0", 1 << 20, 0), ("sched 1", 1 << 20, 1), ("sched 2", 1 << 20, 2),
-                                        ("sched 0, long shadow launches only", 1, 0), ("sched 2, every launch counts as long", 1, 2)):
+            for name, overlap, mode in (("one stream", 0, 0), ("sched 0", 1 << 20, 0), ("sched 1", 1 << 20, 1), ("sched 1, ring of 3", 1 << 20, 13),
+                                        ("sched 0, long shadow launches only", 1, 0)):
                 ctx.configure("overlap_threshold", overlap)
-                ctx.configure("sched_mode", mode)
+                ctx.configure("sched_mode", mode % 10)
+                ctx.configure("ring", 3 if mode >= 10 else 8)
                 for rep in range(2):   # twice: the second frame runs with warm buffers and the autotuned bounce form
                     acc, st = ctx.render_tile(P, 0, 0, w, h, 0, spp)
                     out[(tt, name, rep)] = (acc, st)
     finally:
-        ctx.configure("tail_threshold", 32768); ctx.configure("overlap_threshold", 1 << 20); ctx.configure("sched_mode", 1)
+        ctx.configure("tail_threshold", 32768); ctx.configure("overlap_threshold", 1 << 20); ctx.configure("sched_mode", 1); ctx.configure("ring", 8)
     return out
 
 
