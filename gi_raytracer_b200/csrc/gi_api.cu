@@ -67,7 +67,8 @@ struct gi_ctx {
     std::atomic<int> cancel{ 0 };  // gi_cancel: polled at launch boundaries
     // side streams: k_direct (side[0]) and the gather pipeline (side[1]) of a bounce depth run behind the next depth's bounce
     // kernel once the hit list is short (< overlap_threshold): those launches no longer fill the machine
-    cudaStream_t main_stream = nullptr, side[2] = { nullptr, nullptr };
+    cudaStream_t main_stream = nullptr, side[2] = { nullptr, nullptr };   // side: the pair in use — one of side_pairs
+    cudaStream_t side_pairs[2][2] = {};      // [0] at the main stream's priority (sched_mode 0), [1] below it (the deferred schedule)
     cudaEvent_t side_done[GI_NHL][2] = {};   // [hit list of the ring][side stream]
     cudaEvent_t fork_ev = nullptr;           // main stream -> side streams (the tail's queued shadow rays and gathers)
     uint32_t overlap_threshold = 1u << 20;   // GI_OVERLAP_THRESHOLD, 0 = off
@@ -84,8 +85,12 @@ struct gi_ctx {
     //      long traversal launches never run side by side — slower on every scene, caustics 19.14 -> 19.59 ms, glass 135.7 -> 140.5.)
     //      ring: hit lists in use (GI_RING, 2..GI_NHL): with four, bounce d+4 waited for the shadow rays / gathers of depth d —
     //      cornell 46.0 ms against 43.9 with six; glass 140.8 / 135.6 / 132.8 ms with four / six / eight (profiles/r02/ab_t24).
-    int sched_mode = 1;
+    //   2  (default) 1, unless the last large frame of this scene had nothing short in it — no tail, no depth below 2^20
+    //      hits (cornell at MAX_DEPTH 4: five long depths): then there is nothing latency-bound to put underneath the long launches,
+    //      and running them side by side only costs (frames 43.9 or 45.8 ms from one run to the next, against a steady 43.9 under 0).
+    int sched_mode = 2;
     int ring = 8;
+    int sched_hint = 1;              // sched_mode 2: 1 = the last large frame of this scene had short launches or a tail (or none was rendered yet)
     DevBuf tsh[7];                           // the tail's deferred shadow rays (DTailQ::sh_*)
     DevBuf hl2[7], b_scan1s;                 // second hit list (depth parity), scan scratch of the gather side stream
     DevBuf hlr[GI_NHL - 2][7];               // hit lists 3 .. GI_NHL of the ring (sched_mode 1)
@@ -297,7 +302,11 @@ extern "C" int gi_create(int device, gi_ctx** out)
     if (cudaStreamCreateWithPriority(&ctx->stream, cudaStreamNonBlocking, prio_greatest) != cudaSuccess) { ctx->stream = nullptr; gi_destroy(ctx); return GI_ERR_CUDA; }
     ctx->main_stream = ctx->stream;
     for (int k = 0; k < 2; k++) {
-        if (cudaStreamCreateWithPriority(&ctx->side[k], cudaStreamNonBlocking, side_prio[k]) != cudaSuccess) { ctx->side[k] = nullptr; gi_destroy(ctx); return GI_ERR_CUDA; }
+        // two pairs of side streams: the round-1 schedule wants its shadow rays at the priority of the gather pipeline beside them (below
+        // it they starve and spill into the next bounce kernel: cornell 43.9 -> 47.0 ms), the deferred schedule wants both below the main stream
+        if (cudaStreamCreateWithPriority(&ctx->side_pairs[0][k], cudaStreamNonBlocking, prio_greatest) != cudaSuccess) { ctx->side_pairs[0][k] = nullptr; gi_destroy(ctx); return GI_ERR_CUDA; }
+        if (cudaStreamCreateWithPriority(&ctx->side_pairs[1][k], cudaStreamNonBlocking, side_prio[k]) != cudaSuccess) { ctx->side_pairs[1][k] = nullptr; gi_destroy(ctx); return GI_ERR_CUDA; }
+        ctx->side[k] = ctx->side_pairs[1][k];
         for (int q = 0; q < GI_NHL; q++) if (cudaEventCreateWithFlags(&ctx->side_done[q][k], cudaEventDisableTiming) != cudaSuccess) { ctx->side_done[q][k] = nullptr; gi_destroy(ctx); return GI_ERR_CUDA; }
     }
     if (cudaEventCreateWithFlags(&ctx->fork_ev, cudaEventDisableTiming) != cudaSuccess) { ctx->fork_ev = nullptr; gi_destroy(ctx); return GI_ERR_CUDA; }
@@ -357,7 +366,7 @@ extern "C" void gi_destroy(gi_ctx* ctx)
     for (auto& t : ctx->pending) { cudaEventDestroy(t.a); cudaEventDestroy(t.b); }
     for (auto& e : ctx->event_pool) cudaEventDestroy(e);
     for (int k = 0; k < 2; k++) {
-        if (ctx->side[k]) { cudaStreamSynchronize(ctx->side[k]); cudaStreamDestroy(ctx->side[k]); }
+        for (int pr = 0; pr < 2; pr++) if (ctx->side_pairs[pr][k]) { cudaStreamSynchronize(ctx->side_pairs[pr][k]); cudaStreamDestroy(ctx->side_pairs[pr][k]); }
         for (int q = 0; q < GI_NHL; q++) if (ctx->side_done[q][k]) cudaEventDestroy(ctx->side_done[q][k]);
     }
     if (ctx->fork_ev) cudaEventDestroy(ctx->fork_ev);
@@ -580,7 +589,7 @@ extern "C" int gi_scene_upload(gi_ctx* ctx, const gi_scene_desc* sc)
     {
         uint64_t sig = gi_mix64(((uint64_t)sc->n_nodes << 32) ^ sc->n_refs) ^ gi_mix64(((uint64_t)sc->n_prims << 20) ^ sc->n_lights);
         for (int k = 0; k < 6; k++) { uint64_t b; std::memcpy(&b, &sc->node_box[k], 8); sig = gi_mix64(sig ^ b); }
-        if (sig != ctx->tune_sig) { ctx->tune_sig = sig; ctx->nodes_per_ray = 0; ctx->prims_per_ray = 0; }   // a new scene: forget the previous one's traversal statistics
+        if (sig != ctx->tune_sig) { ctx->tune_sig = sig; ctx->nodes_per_ray = 0; ctx->prims_per_ray = 0; ctx->sched_hint = 1; }   // a new scene: forget the previous one's traversal statistics
     }
     ctx->has_scene = true;   // photons / photon map are independent state and survive a re-upload (the reference keeps its
     return GI_OK;            // map across run() calls, raytracer.h:61); rebuild it explicitly when the geometry changed
@@ -1318,7 +1327,9 @@ static int render_device(gi_ctx* ctx, const gi_render_params* P, int x0, int y0,
     for (int b = 0; b < 5; b++) CK(ctx->hl[b].reserve((size_t)chunk_cap * 24));
     CK(ctx->hl[5].reserve((size_t)chunk_cap * 8)); CK(ctx->hl[6].reserve((size_t)chunk_cap * 4));
     const bool overlap = ctx->overlap_threshold > 0;
-    const bool deferred = overlap && ctx->sched_mode >= 1;   // see gi_ctx::sched_mode
+    const bool deferred = overlap && (ctx->sched_mode == 1 || (ctx->sched_mode == 2 && ctx->sched_hint != 0));   // see gi_ctx::sched_mode
+    bool had_short = false;   // this frame ran a tail or a depth of fewer than 2^20 hits
+    for (int k = 0; k < 2; k++) ctx->side[k] = ctx->side_pairs[deferred ? 1 : 0][k];   // (both pairs are idle between calls: every call drains them)
     const int nhl = deferred ? std::min(std::max(ctx->ring, 2), GI_NHL) : (overlap ? 2 : 1);   // hit lists in use: depths take them in turn
     DevBuf* hls[GI_NHL] = { ctx->hl, ctx->hl2 };
     for (int r = 2; r < GI_NHL; r++) hls[r] = ctx->hlr[r - 2];
@@ -1382,6 +1393,7 @@ static int render_device(gi_ctx* ctx, const gi_render_params* P, int x0, int y0,
             const DHitList& H = Hs[hpar];
             wait_side(hpar);
             if (depth > 0 && n_active < ctx->tail_threshold) {
+                had_short = true;
                 // few paths left: one warp per path runs them to the end inside one kernel; their gathers are queued and served
                 // by one gather pipeline run afterwards (GI_TAIL_MODE=1: gathers inline)
                 DTailQ Q{};
@@ -1471,6 +1483,7 @@ static int render_device(gi_ctx* ctx, const gi_render_params* P, int x0, int y0,
             launches++;
             n_closest += n_active;
             if (hc.n_hits) {
+                if (hc.n_hits < (1u << 20)) had_short = true;   // (the hint does not follow the overlap_threshold knob: bench.py turns that to 0 for its single-stream frame)
                 // the host has just synchronised the main stream (counters), so the side streams need no event to start
                 const bool side = deferred || (overlap && hc.n_hits < ctx->overlap_threshold);
                 static const bool big_direct = getenv("GI_NO_BIG_DIRECT_OVERLAP") == nullptr;   // long shadow launches run beside the gather pipeline (C2 25.85 -> 25.43 ms, glass 51.0 -> 50.7)
@@ -1568,6 +1581,7 @@ static int render_device(gi_ctx* ctx, const gi_render_params* P, int x0, int y0,
     if (rc != GI_OK) return rc;
     float ms = 0; cudaEventElapsedTime(&ms, e0, e1);
     n_closest += tc.closest; n_shadow += tc.shadow; n_gather += tc.gathers;
+    if (tunable) ctx->sched_hint = had_short ? 1 : 0;
     if (n_closest && tunable) {
         ctx->nodes_per_ray = (double)(ctx->work_host[0] + tc.nodes_c) / (double)n_closest;
         ctx->prims_per_ray = (double)(ctx->work_host[1] + tc.prims_c) / (double)n_closest;

@@ -19,7 +19,7 @@ def _frames(ctx, P, w, h, spp, tail_thresholds):
     try:
         for tt in tail_thresholds:
             ctx.configure("tail_threshold", tt)
-            for name, overlap, mode in (("one stream", 0, 0), ("sched 0", 1 << 20, 0), ("sched 1", 1 << 20, 1), ("sched 1, ring of 3", 1 << 20, 13),
+            for name, overlap, mode in (("one stream", 0, 0), ("sched 0", 1 << 20, 0), ("sched 1", 1 << 20, 1), ("sched 1, ring of 3", 1 << 20, 13), ("sched 2", 1 << 20, 2),
                                         ("sched 0, long shadow launches only", 1, 0)):
                 ctx.configure("overlap_threshold", overlap)
                 ctx.configure("sched_mode", mode % 10)
@@ -28,7 +28,7 @@ def _frames(ctx, P, w, h, spp, tail_thresholds):
                     acc, st = ctx.render_tile(P, 0, 0, w, h, 0, spp)
                     out[(tt, name, rep)] = (acc, st)
     finally:
-        ctx.configure("tail_threshold", 32768); ctx.configure("overlap_threshold", 1 << 20); ctx.configure("sched_mode", 1); ctx.configure("ring", 8)
+        ctx.configure("tail_threshold", 32768); ctx.configure("overlap_threshold", 1 << 20); ctx.configure("sched_mode", 2); ctx.configure("ring", 8)
     return out
 
 
