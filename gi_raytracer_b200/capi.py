@@ -322,7 +322,7 @@ class Context:
         self._ck(self.L.gi_cancel(self.h, 1 if raise_ else 0))
 
     def configure(self, key, value):
-        """gi_configure: a scheduling knob (overlap_threshold, tail_threshold, bin_threshold, bounce_mode, trace_mode, tail_mode)."""
+        """gi_configure: a scheduling knob (overlap_threshold, sched_mode, ring, tail_threshold, bin_threshold, bounce_mode, trace_mode, tail_mode)."""
         self._ck(self.L.gi_configure(self.h, key.encode(), int(value)))
 
     def octree_build(self, prim_type, prim_geom, prim_bbox, root_box):

@@ -238,9 +238,14 @@ int gi_material_eval(gi_ctx* ctx, size_t n, const uint32_t* prim, const double* 
 int gi_cancel(gi_ctx* ctx, int raise);
 
 /* ---- scheduling knobs (new; no counterpart in the reference).  Results never depend on them (tested bit for bit).
- *      "overlap_threshold": k_direct / the gather pipeline of a bounce depth with fewer hits than this run on side streams
- *                           behind the next depth's bounce kernel (default 2^20, 0 = one stream: what a profiler or a
- *                           per-kernel timing wants);
+ *      "overlap_threshold": 0 = every kernel of a frame on ONE stream (what a profiler or a per-kernel timing wants); otherwise
+ *                           (default 2^20) the frame runs on the context's three streams as "sched_mode" says, and under
+ *                           sched_mode 0 this is the hit count below which a depth counts as short;
+ *      "sched_mode":        0 = a depth's shadow rays beside its gather run, both behind the next depth's bounce kernel only when the
+ *                           depth is short, everything drained before the tail; 1 = "deferred": bounce kernels / binning / tail kernel
+ *                           on the main stream at the highest stream priority, every depth's shadow rays on side stream 0, every
+ *                           gather run on side stream 1, hit lists in a ring of "ring" (default 8, 2..8); 2 (default) = 1 unless
+ *                           the last large frame of the scene had neither a tail nor a short depth, then 0;
  *      "tail_threshold" (32768), "bin_threshold" (65536), "bounce_mode" (0 auto / 1 thread per ray / 2 persistent),
  *      "trace_mode" (0 / 1 = warp per ray in the batch kernels), "tail_mode" (0 queued / 1 inline gathers). ------------- */
 int gi_configure(gi_ctx* ctx, const char* key, long long value);
