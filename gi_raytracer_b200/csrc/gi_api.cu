@@ -71,6 +71,8 @@ struct gi_ctx {
     cudaStream_t side_pairs[2][2] = {};      // [0] at the main stream's priority (sched_mode 0), [1] below it (the deferred schedule)
     cudaEvent_t side_done[GI_NHL][2] = {};   // [hit list of the ring][side stream]
     cudaEvent_t fork_ev = nullptr;           // main stream -> side streams (the tail's queued shadow rays and gathers)
+    cudaStream_t gather_aux = nullptr;       // k_gather_heavy beside the rest of a gather run (run_gather)
+    cudaEvent_t gather_ev[2] = { nullptr, nullptr };   // [0] locate done (calling stream -> aux), [1] heavy done (aux -> calling stream)
     uint32_t overlap_threshold = 1u << 20;   // GI_OVERLAP_THRESHOLD, 0 = off
     // sched_mode (GI_SCHED_MODE): how a chunk's kernels are laid over the three streams when overlap is on.
     //   0  shadow rays of a depth beside its gather pipeline; both behind the NEXT depth's bounce kernel only when the depth is short
@@ -310,6 +312,9 @@ extern "C" int gi_create(int device, gi_ctx** out)
         for (int q = 0; q < GI_NHL; q++) if (cudaEventCreateWithFlags(&ctx->side_done[q][k], cudaEventDisableTiming) != cudaSuccess) { ctx->side_done[q][k] = nullptr; gi_destroy(ctx); return GI_ERR_CUDA; }
     }
     if (cudaEventCreateWithFlags(&ctx->fork_ev, cudaEventDisableTiming) != cudaSuccess) { ctx->fork_ev = nullptr; gi_destroy(ctx); return GI_ERR_CUDA; }
+    if (cudaStreamCreateWithPriority(&ctx->gather_aux, cudaStreamNonBlocking, prio_least) != cudaSuccess) { ctx->gather_aux = nullptr; gi_destroy(ctx); return GI_ERR_CUDA; }
+    for (int k = 0; k < 2; k++) if (cudaEventCreateWithFlags(&ctx->gather_ev[k], cudaEventDisableTiming) != cudaSuccess) { ctx->gather_ev[k] = nullptr; gi_destroy(ctx); return GI_ERR_CUDA; }
+    if (getenv("GI_NO_GATHER_AUX")) { cudaStreamDestroy(ctx->gather_aux); ctx->gather_aux = nullptr; }   // A/B: the long lists after the thread-per-query kernel, on its stream
     if (const char* e = getenv("GI_OVERLAP_THRESHOLD")) ctx->overlap_threshold = (uint32_t)strtoul(e, nullptr, 10);
     if (const char* e = getenv("GI_SCHED_MODE")) ctx->sched_mode = atoi(e);
     if (const char* e = getenv("GI_RING")) ctx->ring = atoi(e);
@@ -370,6 +375,8 @@ extern "C" void gi_destroy(gi_ctx* ctx)
         for (int q = 0; q < GI_NHL; q++) if (ctx->side_done[q][k]) cudaEventDestroy(ctx->side_done[q][k]);
     }
     if (ctx->fork_ev) cudaEventDestroy(ctx->fork_ev);
+    if (ctx->gather_aux) { cudaStreamSynchronize(ctx->gather_aux); cudaStreamDestroy(ctx->gather_aux); }
+    for (int k = 0; k < 2; k++) if (ctx->gather_ev[k]) cudaEventDestroy(ctx->gather_ev[k]);
     for (auto& b : ctx->hl2) b.release();
     for (auto& l : ctx->hlr) for (auto& b : l) b.release();
     for (auto& b : ctx->tsh) b.release();
@@ -1253,15 +1260,28 @@ static int run_gather(gi_ctx* ctx, uint32_t n, const double* pos, const double* 
     uint32_t* heavy_cnt = ctx->b_gheavy.as<uint32_t>();      // [0] queued, [1] next; the queue starts at [4]
     CK(cudaMemsetAsync(heavy_cnt, 0, 16, ctx->stream));
     if (order) { CK(ctx->b_gperm.reserve((size_t)n * 4)); CK(ctx->b_ghist.reserve((size_t)nk * 4)); CK(ctx->b_gcur.reserve((size_t)nk * 4)); CK(cudaMemsetAsync(ctx->b_ghist.p, 0, (size_t)nk * 4, ctx->stream)); }
-    k_gather_locate<<<grid_for(n, 256), 256, 0, ctx->stream>>>(ctx->G, n, pos, ctx->b_gnode.as<uint32_t>(), order ? ctx->b_ghist.as<uint32_t>() : nullptr, work_ptr(ctx, 4));
+    k_gather_locate<<<grid_for(n, 256), 256, 0, ctx->stream>>>(ctx->G, n, pos, ctx->b_gnode.as<uint32_t>(), order ? ctx->b_ghist.as<uint32_t>() : nullptr, work_ptr(ctx, 4), heavy_cnt + 4, heavy_cnt);
+    // the long lists (queued by the locate kernel) go to persistent warps on the auxiliary stream, beside the counting sort and the
+    // thread-per-query kernel; the calling stream takes them back in before anything that follows (the next depth's gather adds to the same Lc sums)
+    const bool aux = ctx->overlap_threshold > 0 && ctx->gather_aux != nullptr;
+    const cudaStream_t hs = aux ? ctx->gather_aux : ctx->stream;
+    auto launch_heavy = [&]() {
+        k_gather_heavy<<<ctx->n_sm * 4, GI_WPB * 32, 0, hs>>>(ctx->G, heavy_cnt + 4, heavy_cnt, heavy_cnt + 1, ctx->b_gnode.as<uint32_t>(), pos, dir, k, rgb, knn, n_cand, weight, accum, accum_idx);
+    };
+    if (aux) {
+        cudaEventRecord(ctx->gather_ev[0], ctx->stream); cudaStreamWaitEvent(hs, ctx->gather_ev[0], 0);
+        launch_heavy();
+        cudaEventRecord(ctx->gather_ev[1], hs);
+    }
     if (order) {
         int rc = scan_exclusive(ctx, ctx->b_ghist.as<uint32_t>(), 1, nk, ctx->b_gcur.as<uint32_t>(), nullptr);
         if (rc != GI_OK) return rc;
         k_bin_scatter<<<grid_for(n, 256), 256, 0, ctx->stream>>>(n, ctx->b_gnode.as<uint32_t>(), ctx->b_gcur.as<uint32_t>(), ctx->b_gperm.as<uint32_t>());
     }
     k_gather_sorted<<<grid_for(n, GI_GS_BLOCK), GI_GS_BLOCK, 0, ctx->stream>>>(ctx->G, n, order ? ctx->b_gperm.as<uint32_t>() : nullptr, ctx->b_gnode.as<uint32_t>(), pos, dir, k, rgb, knn, n_cand,
-                                                                              weight, accum, accum_idx, work_ptr(ctx, 4), heavy_cnt + 4, heavy_cnt);
-    k_gather_heavy<<<ctx->n_sm * 4, GI_WPB * 32, 0, ctx->stream>>>(ctx->G, heavy_cnt + 4, heavy_cnt, heavy_cnt + 1, ctx->b_gnode.as<uint32_t>(), pos, dir, k, rgb, knn, n_cand, weight, accum, accum_idx);
+                                                                              weight, accum, accum_idx, work_ptr(ctx, 4));
+    if (aux) cudaStreamWaitEvent(ctx->stream, ctx->gather_ev[1], 0);
+    else launch_heavy();
     CK(cudaGetLastError());
     if (launches) *launches += order ? 7 : 3;
     return GI_OK;

@@ -624,7 +624,16 @@ __device__ __forceinline__ GatherOut gather_warp(const DGatherMap& M, d3 p, d3 d
 //                     The k nearest so far are a max-heap in a per-thread column of shared memory; the scan of the
 //                     (centre-ordered) list stops early; a heap sort orders the k for the sum (details at the kernel).
 //   k_gather_heavy    lists longer than GI_GS_MAX_CANDS: persistent warps stream them, 32 candidates per step.
-__global__ void k_gather_locate(DGatherMap M, uint32_t n, const double* __restrict__ qpos, uint32_t* __restrict__ qnode, uint32_t* __restrict__ hist, unsigned long long* work)
+#ifndef GI_GS_MAX_CANDS
+#define GI_GS_MAX_CANDS 256u
+#endif
+// GI_GS_MAX_CANDS: longer candidate lists are streamed by a whole warp (k_gather_heavy) instead of by one thread.  The locate kernel
+// already knows the leaf and so the length of the list: it queues those queries, and the host starts k_gather_heavy — persistent
+// warps, latency-bound, 16 warps per SM — on an auxiliary stream right away, BESIDE the counting sort and k_gather_sorted instead of
+// after them.  (Until round 2 k_gather_sorted queued them; a rule that kept a long list with its thread when enough lanes of the warp
+// shared it was measured and never paid: profiles/r02/ab_t20_heavy_thresholds.txt.)
+__global__ void k_gather_locate(DGatherMap M, uint32_t n, const double* __restrict__ qpos, uint32_t* __restrict__ qnode, uint32_t* __restrict__ hist, unsigned long long* work,
+                                uint32_t* __restrict__ heavy, uint32_t* __restrict__ heavy_n)
 {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     uint32_t depth = 0;
@@ -638,6 +647,17 @@ __global__ void k_gather_locate(DGatherMap M, uint32_t n, const double* __restri
             const unsigned peers = __match_any_sync(live, key);
             if ((threadIdx.x & 31u) == (unsigned)(__ffs(peers) - 1)) atomicAdd(hist + key, (uint32_t)__popc(peers));
         }
+        // long lists: queue the query for k_gather_heavy (one warp per query, taken from a shared counter)
+        const bool hard = found && __ldg(M.cand_off + node + 1) - __ldg(M.cand_off + node) > GI_GS_MAX_CANDS;
+        const unsigned hm = __ballot_sync(live, hard);
+        if (hm) {
+            const unsigned lane = threadIdx.x & 31u;
+            const int leader = __ffs(hm) - 1;
+            uint32_t base = 0;
+            if (lane == (unsigned)leader) base = atomicAdd(heavy_n, (uint32_t)__popc(hm));
+            base = __shfl_sync(live, base, leader);
+            if (hard) heavy[base + __popc(hm & ((1u << lane) - 1u))] = i;
+        }
     }
     if (work) {
         unsigned long long wd = depth;
@@ -647,14 +667,6 @@ __global__ void k_gather_locate(DGatherMap M, uint32_t n, const double* __restri
     }
 }
 
-#ifndef GI_GS_MAX_CANDS
-#define GI_GS_MAX_CANDS 256u
-#endif
-// GI_GS_MAX_CANDS:   // longer candidate lists are streamed by the whole warp ...
-#ifndef GI_GS_MIN_GROUP
-#define GI_GS_MIN_GROUP 33
-#endif
-// GI_GS_MIN_GROUP:       // ... unless at least this many lanes of the warp share the list
 #define GI_GS_BLOCK 64   // 64 columns x 32 rows x 12 B = 24 KB of shared memory per block
 // (measured and dropped in round 2: the k nearest as an ascending sorted column with insertion from the end instead of the max-heap +
 //  final heap sort — no sort afterwards, but 27 % slower: 1.18 vs 0.93 ms for the 776 666 C2 queries, profiles/r02/ab_gather.txt)
@@ -700,8 +712,7 @@ struct GHeap {
 __global__ void __launch_bounds__(GI_GS_BLOCK) k_gather_sorted(DGatherMap M, uint32_t n, const uint32_t* __restrict__ perm, const uint32_t* __restrict__ qnode,
                                                                  const double* __restrict__ qpos, const double* __restrict__ qdir, int k, double* __restrict__ rgb,
                                                                  uint32_t* __restrict__ knn, uint32_t* __restrict__ ncand, const double* __restrict__ weight,
-                                                                 double* __restrict__ accum, const uint32_t* __restrict__ accum_idx, unsigned long long* work,
-                                                                 uint32_t* __restrict__ heavy, uint32_t* __restrict__ heavy_n)
+                                                                 double* __restrict__ accum, const uint32_t* __restrict__ accum_idx, unsigned long long* work)
 {
     GI_GHEAP_DECL(H);                            // per-thread heap, then sorted list: row = rank, column = thread
     const int t = threadIdx.x, lane = t & 31;
@@ -726,12 +737,9 @@ __global__ void __launch_bounds__(GI_GS_BLOCK) k_gather_sorted(DGatherMap M, uin
     int m = 0;                       // rows in use
     double tau = CUDART_INF; uint32_t tau_sl = 0xFFFFFFFFu;   // the k-th (distance^2, slot) once m == k
     float bound = CUDART_INF_F;      // scan stops at the first key above it
-    // long lists (a large leaf next to a dense region touches thousands of small ones) are streamed by the whole warp, 32
-    // candidates per step, instead of by one thread
-    // ... unless several lanes of this warp sit in that same leaf (in leaf order they usually do): one pass over the list then
-    // serves all of them, each lane against its own point
-    const uint32_t same_leaf = __match_any_sync(0xffffffffu, node);
-    const bool hard = total > GI_GS_MAX_CANDS && __popc(same_leaf) < GI_GS_MIN_GROUP;
+    // long lists (a large leaf next to a dense region touches thousands of small ones) are streamed by a whole warp, 32 candidates
+    // per step, instead of by one thread: k_gather_locate has queued those queries for k_gather_heavy, this kernel leaves them alone
+    const bool hard = total > GI_GS_MAX_CANDS;
     // the list is read four records ahead of their use (eight independent 16-byte loads in flight per thread); the stop test
     // is made once per group, so the scan may run up to three candidates past the bound — they are simply rejected
     const uint32_t n_scan = hard ? 0u : total;
@@ -786,17 +794,6 @@ __global__ void __launch_bounds__(GI_GS_BLOCK) k_gather_sorted(DGatherMap M, uin
         double rd_ = 0; uint32_t rs_ = 0;
         if (r < count) H.get(r, rd_, rs_);
         knn[(size_t)q * k + r] = r < count ? __ldg(M.pid + rs_) : GI_NO_HIT;
-    }
-    // long lists: queue the query for k_gather_heavy (one warp per query, taken from a shared counter — in leaf order these
-    // queries sit next to each other, and 32 of them in one warp would be a serial chain of milliseconds)
-    {
-        const uint32_t hm = __ballot_sync(0xffffffffu, hard);
-        if (hm) {
-            uint32_t base = 0;
-            if (lane == 0) base = atomicAdd(heavy_n, (uint32_t)__popc(hm));
-            base = __shfl_sync(0xffffffffu, base, 0);
-            if (hard) heavy[base + __popc(hm & ((1u << lane) - 1u))] = q;
-        }
     }
     if (have && !hard) {
         if (rgb) st3(rgb + 3 * (size_t)q, res);
