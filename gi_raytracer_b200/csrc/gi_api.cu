@@ -1263,7 +1263,8 @@ static int run_gather(gi_ctx* ctx, uint32_t n, const double* pos, const double* 
     k_gather_locate<<<grid_for(n, 256), 256, 0, ctx->stream>>>(ctx->G, n, pos, ctx->b_gnode.as<uint32_t>(), order ? ctx->b_ghist.as<uint32_t>() : nullptr, work_ptr(ctx, 4), heavy_cnt + 4, heavy_cnt);
     // the long lists (queued by the locate kernel) go to persistent warps on the auxiliary stream, beside the counting sort and the
     // thread-per-query kernel; the calling stream takes them back in before anything that follows (the next depth's gather adds to the same Lc sums)
-    const bool aux = ctx->overlap_threshold > 0 && ctx->gather_aux != nullptr;
+    // (also when overlap_threshold = 0 keeps the FAMILIES of a frame on one stream: the auxiliary stream is the gather pipeline's own)
+    const bool aux = ctx->gather_aux != nullptr;
     const cudaStream_t hs = aux ? ctx->gather_aux : ctx->stream;
     auto launch_heavy = [&]() {
         k_gather_heavy<<<ctx->n_sm * 4, GI_WPB * 32, 0, hs>>>(ctx->G, heavy_cnt + 4, heavy_cnt, heavy_cnt + 1, ctx->b_gnode.as<uint32_t>(), pos, dir, k, rgb, knn, n_cand, weight, accum, accum_idx);
