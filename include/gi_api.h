@@ -165,7 +165,10 @@ int gi_create(int device, gi_ctx** out);
 void gi_destroy(gi_ctx* ctx);
 const char* gi_last_error(const gi_ctx* ctx);
 const char* gi_version(void);
-/* the CUDA stream all work of this ctx is enqueued on (a cudaStream_t), for callers that time with events */
+/* the CUDA stream the work of this ctx is enqueued on (a cudaStream_t), for callers that time with events or enqueue their own
+ * work behind a *_dev call.  A frame also uses side streams the context owns (shadow rays, gather runs, the gather's long lists:
+ * "sched_mode" below); every call joins them back into this stream before it returns, so work enqueued here afterwards sees
+ * complete results. */
 void* gi_stream(gi_ctx* ctx);
 int gi_synchronize(gi_ctx* ctx);
 
